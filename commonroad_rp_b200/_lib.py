@@ -1,0 +1,300 @@
+"""ctypes binding of the C-ABI in include/rp_b200.h (librp_b200.so, built in-tree by build.py).
+
+There is deliberately NO CPU fallback: if the CUDA library is missing or a call fails, an
+exception is raised.  ``Engine`` is a thin owner of one ``rp_ctx`` (one CUDA device + stream).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librp_b200.so")
+
+N_REASONS = 8
+N_STATE_ROWS = 14
+STATE_ROWS = ("x", "y", "theta", "v", "a", "kappa", "kappa_dot",
+              "s", "d", "theta_cl", "s_dot", "s_ddot", "d_dot", "d_ddot")
+REASON_NAMES = ("none", "velocity", "acceleration", "kappa", "kappa_dot", "yaw_rate", "projection", "ref_range")
+CONSTRAINT_BITS = {"velocity": 1, "acceleration": 2, "kappa": 4, "kappa_dot": 8, "yaw_rate": 16}
+ST_FEASIBLE, ST_KINEMATIC, ST_COLLISION, ST_FILTERED = 0, 1, 2, 3
+VELOCITY_KEEPING, STOPPING = 0, 1
+COST_DEFAULT, COST_FAILSAFE, COST_NONE = 0, 1, 2
+
+
+class RpError(RuntimeError):
+    pass
+
+
+class VehicleParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("length", "width", "wb_rear_axle", "wheelbase", "a_max", "v_switch",
+                                          "delta_max", "v_delta_max", "kappa_max")]
+
+
+class PlanInputs(C.Structure):
+    _fields_ = [
+        ("x0_lon", C.c_double * 3), ("x0_lat", C.c_double * 3), ("x0_orientation", C.c_double),
+        ("x0_time_step", C.c_int32), ("low_vel_mode", C.c_int32), ("lon_mode", C.c_int32), ("N", C.c_int32),
+        ("dt", C.c_double), ("factor", C.c_int32), ("draw_all", C.c_int32), ("constraint_mask", C.c_uint32),
+        ("cost_kind", C.c_int32), ("has_desired_speed", C.c_int32), ("has_desired_s", C.c_int32),
+        ("desired_speed", C.c_double), ("desired_s", C.c_double), ("desired_d", C.c_double), ("w_a", C.c_double),
+        ("want_all_states", C.c_int32), ("check_collision", C.c_int32),
+    ]
+
+
+class PlanResult(C.Structure):
+    _fields_ = [
+        ("winner", C.c_int32), ("n_candidates", C.c_int32), ("n_feasible", C.c_int32),
+        ("n_infeasible_kinematics", C.c_int32), ("n_infeasible_collision", C.c_int32),
+        ("n_collision_total", C.c_int32), ("reason_counts", C.c_int32 * N_REASONS), ("winner_cost", C.c_double),
+    ]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+
+# every symbol include/rp_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "rp_last_error": (C.c_char_p, []),
+    "rp_version": (C.c_int, []),
+    "rp_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rp_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "rp_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "rp_ctx_set_vehicle": (C.c_int, [C.c_void_p, C.POINTER(VehicleParams)]),
+    "rp_ctx_set_reference": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
+    "rp_ctx_set_obstacles": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int, _ip, _ip, _dp, C.c_int, _dp, C.c_double]),
+    "rp_plan_grid": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _ip, C.c_int, _dp, C.c_int, _dp,
+                               C.POINTER(PlanResult)]),
+    "rp_grid_upload": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _ip, C.c_int, _dp, C.c_int, _dp]),
+    "rp_grid_launch": (C.c_int, [C.c_void_p]),
+    "rp_grid_result": (C.c_int, [C.c_void_p, C.POINTER(PlanResult)]),
+    "rp_plan_list": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _dp, _ip, _bp, C.POINTER(PlanResult)]),
+    "rp_set_candidate_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "rp_fetch_states": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "rp_fetch_candidates": (C.c_int, [C.c_void_p, _dp, _ip, _ip, _ip]),
+    "rp_fetch_coeffs": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    "rp_solve_coeffs": (C.c_int, [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, _dp]),
+    "rp_collide_poses": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, C.c_double, C.c_double, _bp]),
+    "rp_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "rp_launches_per_plan": (C.c_int, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load_library():
+    """Load librp_b200.so and declare every signature.  Raises RpError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RpError("CUDA library %s not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None and a.size else C.cast(None, t)
+
+
+def traj_len_of(delta_tau, dt):
+    """len(np.arange(0, np.round(delta_tau + dt, 5), dt))  (reactive_planner.py:733, :748)."""
+    return len(np.arange(0, np.round(delta_tau + dt, 5), dt))
+
+
+class Engine:
+    """One device-resident planning context."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        self._check(self._lib.rp_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._ctx)))
+        self.device = int(device)
+        self._N = None
+        self._n_cand = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.rp_last_error()
+            raise RpError("rp_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.rp_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scenario-static tables ----
+    def set_vehicle(self, length, width, wb_rear_axle, wheelbase, a_max, v_switch, delta_max, v_delta_max,
+                    kappa_max=None):
+        if kappa_max is None:
+            kappa_max = np.tan(delta_max) / wheelbase            # utility/config.py:222
+        vp = VehicleParams(length, width, wb_rear_axle, wheelbase, a_max, v_switch, delta_max, v_delta_max,
+                           float(kappa_max))
+        self._check(self._lib.rp_ctx_set_vehicle(self._ctx, C.byref(vp)))
+
+    def set_reference(self, ref_pos, ref_theta, ref_curv, ref_curv_d, path_xy, path_s, path_normals, proj_limit):
+        arrs = [_f64(a) for a in (ref_pos, ref_theta, ref_curv, ref_curv_d, path_xy, path_s, path_normals)]
+        n = arrs[0].shape[0]
+        assert all(a.shape[0] == n for a in arrs), "reference arrays must have equal length"
+        self._check(self._lib.rp_ctx_set_reference(self._ctx, n, *[_p(a, _dp) for a in arrs], float(proj_limit)))
+
+    def set_obstacles(self, static_obb=None, dyn_t0=None, dyn_boxes=None, tris=None, cell_size=0.0):
+        """static_obb (n,5): cx, cy, theta, half_len, half_wid.  dyn_boxes: list of (K_i,5) arrays."""
+        so = _f64(static_obb if static_obb is not None else np.zeros((0, 5))).reshape(-1, 5)
+        t0 = _i32(dyn_t0 if dyn_t0 is not None else np.zeros(0))
+        boxes = [] if dyn_boxes is None else [_f64(b).reshape(-1, 5) for b in dyn_boxes]
+        ln = _i32([len(b) for b in boxes])
+        cat = _f64(np.concatenate(boxes, axis=0)) if boxes else np.zeros((0, 5))
+        tr = _f64(tris if tris is not None else np.zeros((0, 6))).reshape(-1, 6)
+        self._check(self._lib.rp_ctx_set_obstacles(self._ctx, so.shape[0], _p(so, _dp), len(boxes), _p(t0, _ip),
+                                                   _p(ln, _ip), _p(cat, _dp), tr.shape[0], _p(tr, _dp),
+                                                   float(cell_size)))
+
+    # ---- planning ----
+    @staticmethod
+    def make_inputs(x0_lon, x0_lat, x0_orientation, x0_time_step, low_vel_mode, lon_mode, N, dt, factor=1,
+                    draw_all=False, constraints=("velocity", "acceleration", "kappa", "kappa_dot", "yaw_rate"),
+                    cost_kind=COST_DEFAULT, desired_speed=None, desired_s=None, desired_d=0.0, w_a=5.0,
+                    want_all_states=False, check_collision=True):
+        pi = PlanInputs()
+        pi.x0_lon[:] = [float(v) for v in x0_lon]
+        pi.x0_lat[:] = [float(v) for v in x0_lat]
+        pi.x0_orientation = float(x0_orientation)
+        pi.x0_time_step = int(x0_time_step)
+        pi.low_vel_mode = int(bool(low_vel_mode))
+        pi.lon_mode = STOPPING if lon_mode in (STOPPING, "stopping") else VELOCITY_KEEPING
+        pi.N = int(N)
+        pi.dt = float(dt)
+        pi.factor = int(factor)
+        pi.draw_all = int(bool(draw_all))
+        mask = 0
+        for name in constraints:
+            mask |= CONSTRAINT_BITS[name]
+        pi.constraint_mask = mask
+        pi.cost_kind = int(cost_kind)
+        pi.has_desired_speed = int(desired_speed is not None)
+        pi.has_desired_s = int(desired_s is not None)
+        pi.desired_speed = float(desired_speed) if desired_speed is not None else 0.0
+        pi.desired_s = float(desired_s) if desired_s is not None else 0.0
+        pi.desired_d = float(desired_d)
+        pi.w_a = float(w_a)
+        pi.want_all_states = int(bool(want_all_states))
+        pi.check_collision = int(bool(check_collision))
+        return pi
+
+    def _grid_args(self, inputs, t, lon, d, traj_len):
+        t = _f64(t)
+        lon = _f64(lon)
+        d = _f64(d)
+        if traj_len is None:
+            traj_len = [traj_len_of(tt, inputs.dt) for tt in t]
+        tl = _i32(traj_len)
+        self._N = inputs.N
+        self._n_cand = t.size * lon.size * d.size
+        self._keep = (t, lon, d, tl)
+        return (C.byref(inputs), t.size, _p(t, _dp), _p(tl, _ip), lon.size, _p(lon, _dp), d.size, _p(d, _dp))
+
+    def plan_grid(self, inputs, t, lon, d, traj_len=None):
+        res = PlanResult()
+        self._check(self._lib.rp_plan_grid(self._ctx, *self._grid_args(inputs, t, lon, d, traj_len), C.byref(res)))
+        return res
+
+    def grid_upload(self, inputs, t, lon, d, traj_len=None):
+        self._check(self._lib.rp_grid_upload(self._ctx, *self._grid_args(inputs, t, lon, d, traj_len)))
+
+    def grid_launch(self):
+        self._check(self._lib.rp_grid_launch(self._ctx))
+
+    def grid_result(self):
+        res = PlanResult()
+        self._check(self._lib.rp_grid_result(self._ctx, C.byref(res)))
+        return res
+
+    def plan_list(self, inputs, coeffs_lon, coeffs_lat, traj_len, skip=None):
+        cl = _f64(coeffs_lon).reshape(-1, 6)
+        ct = _f64(coeffs_lat).reshape(-1, 6)
+        tl = _i32(traj_len)
+        sk = np.ascontiguousarray(skip, dtype=np.uint8) if skip is not None else None
+        self._N = inputs.N
+        self._n_cand = cl.shape[0]
+        res = PlanResult()
+        self._check(self._lib.rp_plan_list(self._ctx, C.byref(inputs), cl.shape[0], _p(cl, _dp), _p(ct, _dp),
+                                           _p(tl, _ip), _p(sk, _bp) if sk is not None else C.cast(None, _bp),
+                                           C.byref(res)))
+        return res
+
+    def set_candidate_range(self, first, count):
+        self._check(self._lib.rp_set_candidate_range(self._ctx, int(first), int(count)))
+
+    def synchronize(self):
+        self._check(self._lib.rp_ctx_synchronize(self._ctx))
+
+    # ---- results ----
+    def fetch_states(self, idx):
+        out = np.empty((N_STATE_ROWS, self._N + 1), dtype=np.float64)
+        self._check(self._lib.rp_fetch_states(self._ctx, int(idx), _p(out, _dp)))
+        return out
+
+    def fetch_candidates(self):
+        n = self._n_cand
+        cost = np.empty(n, dtype=np.float64)
+        status = np.empty(n, dtype=np.int32)
+        reason = np.empty(n, dtype=np.int32)
+        step = np.empty(n, dtype=np.int32)
+        self._check(self._lib.rp_fetch_candidates(self._ctx, _p(cost, _dp), _p(status, _ip), _p(reason, _ip),
+                                                  _p(step, _ip)))
+        return cost, status, reason, step
+
+    def fetch_coeffs(self):
+        n = self._n_cand
+        cl = np.empty((n, 6), dtype=np.float64)
+        ct = np.empty((n, 6), dtype=np.float64)
+        tau = np.full(n, np.nan, dtype=np.float64)
+        self._check(self._lib.rp_fetch_coeffs(self._ctx, _p(cl, _dp), _p(ct, _dp), _p(tau, _dp)))
+        return cl, ct, tau
+
+    def solve_coeffs(self, kind, x0, xd, tau):
+        kind = _i32(kind)
+        x0 = _f64(x0).reshape(-1, 3)
+        xd = _f64(xd).reshape(-1, 3)
+        tau = _f64(tau)
+        out = np.empty((kind.size, 6), dtype=np.float64)
+        self._check(self._lib.rp_solve_coeffs(self._ctx, kind.size, _p(kind, _ip), _p(x0, _dp), _p(xd, _dp),
+                                              _p(tau, _dp), _p(out, _dp)))
+        return out
+
+    def collide_poses(self, pose, time_idx, half_length, half_width):
+        pose = _f64(pose).reshape(-1, 3)
+        ti = _i32(time_idx)
+        hit = np.zeros(pose.shape[0], dtype=np.uint8)
+        self._check(self._lib.rp_collide_poses(self._ctx, pose.shape[0], _p(pose, _dp), _p(ti, _ip),
+                                               float(half_length), float(half_width), _p(hit, _bp)))
+        return hit.astype(bool)
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 4)()
+        self._check(self._lib.rp_last_stage_ms(self._ctx, ms))
+        return [float(v) for v in ms]
+
+    def launches_per_plan(self):
+        return int(self._lib.rp_launches_per_plan(self._ctx))

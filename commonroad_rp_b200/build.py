@@ -1,0 +1,29 @@
+"""In-tree build of the CUDA library (sm_100a only).  The .so is git-ignored but travels to the GPU box."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "csrc", "rp_capi.cu")
+OUT = os.path.join(HERE, "librp_b200.so")
+DEPS = [SRC, os.path.join(HERE, "csrc", "rp_kernels.cuh"), os.path.join(HERE, "csrc", "rp_device.cuh"),
+        os.path.join(ROOT, "include", "rp_b200.h")]
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              # the reference evaluates every expression as separate IEEE multiplies/adds: no contraction
+              "--fmad=false",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build_library(force=False, verbose=False):
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+        return OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc"), "-o", OUT, SRC]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

@@ -1,0 +1,804 @@
+// rp_capi.cu -- host side of the C-ABI declared in include/rp_b200.h: device-resident scenario
+// tables, per-cycle upload / launch / result, and the small stand-alone entry points.
+// No torch types cross this boundary; PyTorch only supplies the stream handle.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rp_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define RP_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(RP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return RP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(bytes, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(RP_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cap = want;
+        return RP_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return RP_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(bytes, 4096);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return fail(RP_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        cap = want;
+        return RP_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct rp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    int max_smem_optin = 0;
+
+    bool have_vehicle = false, have_ref = false;
+    rp_vehicle_params veh{};
+
+    // reference tables
+    int ref_n = 0, ref_same_s = 0;
+    double ref_limit = 0;
+    DevBuf d_ref;                       // 9 arrays of ref_n doubles
+
+    // obstacles (host copies; device tables rebuilt lazily when the vehicle or obstacles change)
+    std::vector<double> h_static, h_dyn, h_tri;
+    std::vector<int> h_dyn_t0, h_dyn_len;
+    double cell_size = 2.0;
+    bool obstacles_dirty = true;
+    DevBuf d_obb, d_tri, d_cell_start, d_cell_items, d_dyn_box, d_dyn_meta;
+    rp::ObstacleTables obs{};
+
+    // per-cycle
+    rp_plan_inputs in{};
+    int mode = 0, n_t = 0, n_lon = 0, n_d = 0, n_cand = 0;
+    int range_first = 0, range_count = -1;
+    bool have_inputs = false, have_plan = false, states_all_valid = false;
+    DevBuf d_samples;                   // t | lon | d (doubles) then traj_len (ints)
+    DevBuf d_lon_coef, d_lat_coef, d_lat_tau, d_skip;
+    DevBuf d_cost, d_info, d_states_all, d_states_one, d_result, d_index;
+    PinBuf h_stage, h_result;
+    size_t off_t = 0, off_lon = 0, off_d = 0, off_len = 0;
+
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+};
+
+namespace {
+
+using rp::PlanParams;
+
+int bind(rp_ctx* ctx) {
+    if (!ctx) return fail(RP_ERR_ARG, "null context");
+    RP_CUDA(cudaSetDevice(ctx->device));
+    return RP_OK;
+}
+
+// ---- static broad-phase grid ------------------------------------------------------------------
+int build_obstacle_tables(rp_ctx* ctx) {
+    if (!ctx->have_vehicle) return fail(RP_ERR_STATE, "rp_ctx_set_vehicle must precede planning");
+    const double hl = 0.5 * ctx->veh.length, hw = 0.5 * ctx->veh.width;
+    const double r_ego = std::sqrt(hl * hl + hw * hw);
+    const double infl = r_ego * (1.0 + 1e-9) + 1e-6;
+    const int n_obb = (int)(ctx->h_static.size() / 5);
+    const int n_tri = (int)(ctx->h_tri.size() / 6);
+    const int n_prim = n_obb + n_tri;
+
+    std::vector<double> obb((size_t)std::max(n_obb, 1) * rp::kBoxStride, 0.0);
+    std::vector<double> lo_x(n_prim), hi_x(n_prim), lo_y(n_prim), hi_y(n_prim);
+    for (int q = 0; q < n_obb; ++q) {
+        const double* s = &ctx->h_static[(size_t)q * 5];
+        const double c = std::cos(s[2]), sn = std::sin(s[2]);
+        double* o = &obb[(size_t)q * rp::kBoxStride];
+        o[0] = s[0]; o[1] = s[1]; o[2] = c; o[3] = sn; o[4] = s[3]; o[5] = s[4];
+        o[6] = std::sqrt(s[3] * s[3] + s[4] * s[4]); o[7] = 1.0;
+        const double ex = std::fabs(c) * s[3] + std::fabs(sn) * s[4];
+        const double ey = std::fabs(sn) * s[3] + std::fabs(c) * s[4];
+        lo_x[q] = s[0] - ex - infl; hi_x[q] = s[0] + ex + infl;
+        lo_y[q] = s[1] - ey - infl; hi_y[q] = s[1] + ey + infl;
+    }
+    for (int q = 0; q < n_tri; ++q) {
+        const double* t = &ctx->h_tri[(size_t)q * 6];
+        lo_x[n_obb + q] = std::min({t[0], t[2], t[4]}) - infl; hi_x[n_obb + q] = std::max({t[0], t[2], t[4]}) + infl;
+        lo_y[n_obb + q] = std::min({t[1], t[3], t[5]}) - infl; hi_y[n_obb + q] = std::max({t[1], t[3], t[5]}) + infl;
+    }
+    rp::ObstacleTables& O = ctx->obs;
+    O = rp::ObstacleTables{};
+    O.n_obb = n_obb;
+    O.n_tri = n_tri;
+    if (n_prim > 0) {
+        double gx0 = lo_x[0], gx1 = hi_x[0], gy0 = lo_y[0], gy1 = hi_y[0];
+        for (int q = 1; q < n_prim; ++q) {
+            gx0 = std::min(gx0, lo_x[q]); gx1 = std::max(gx1, hi_x[q]);
+            gy0 = std::min(gy0, lo_y[q]); gy1 = std::max(gy1, hi_y[q]);
+        }
+        double cell = ctx->cell_size > 0 ? ctx->cell_size : 2.0;
+        double w = gx1 - gx0, h = gy1 - gy0;
+        while ((std::ceil(w / cell) + 1) * (std::ceil(h / cell) + 1) > 4.0e6) cell *= 2.0;
+        const int gnx = (int)std::ceil(w / cell) + 1, gny = (int)std::ceil(h / cell) + 1;
+        const double inv = 1.0 / cell;
+        std::vector<int> start((size_t)gnx * gny + 1, 0);
+        auto span = [&](int q, int& ix0, int& ix1, int& iy0, int& iy1) {
+            ix0 = std::max(0, (int)std::floor((lo_x[q] - gx0) * inv) - 0);
+            ix1 = std::min(gnx - 1, (int)std::floor((hi_x[q] - gx0) * inv));
+            iy0 = std::max(0, (int)std::floor((lo_y[q] - gy0) * inv));
+            iy1 = std::min(gny - 1, (int)std::floor((hi_y[q] - gy0) * inv));
+        };
+        for (int q = 0; q < n_prim; ++q) {
+            int ix0, ix1, iy0, iy1;
+            span(q, ix0, ix1, iy0, iy1);
+            for (int iy = iy0; iy <= iy1; ++iy)
+                for (int ix = ix0; ix <= ix1; ++ix) ++start[(size_t)iy * gnx + ix + 1];
+        }
+        for (size_t q = 1; q < start.size(); ++q) start[q] += start[q - 1];
+        std::vector<int> items((size_t)std::max(start.back(), 1));
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int q = 0; q < n_prim; ++q) {
+            int ix0, ix1, iy0, iy1;
+            span(q, ix0, ix1, iy0, iy1);
+            for (int iy = iy0; iy <= iy1; ++iy)
+                for (int ix = ix0; ix <= ix1; ++ix) items[(size_t)fill[(size_t)iy * gnx + ix]++] = q;
+        }
+        if (int rc = ctx->d_obb.ensure(obb.size() * sizeof(double))) return rc;
+        if (int rc = ctx->d_tri.ensure(std::max<size_t>(ctx->h_tri.size(), 6) * sizeof(double))) return rc;
+        if (int rc = ctx->d_cell_start.ensure(start.size() * sizeof(int))) return rc;
+        if (int rc = ctx->d_cell_items.ensure(items.size() * sizeof(int))) return rc;
+        RP_CUDA(cudaMemcpyAsync(ctx->d_obb.p, obb.data(), obb.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_tri)
+            RP_CUDA(cudaMemcpyAsync(ctx->d_tri.p, ctx->h_tri.data(), ctx->h_tri.size() * sizeof(double),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaMemcpyAsync(ctx->d_cell_start.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaMemcpyAsync(ctx->d_cell_items.p, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaStreamSynchronize(ctx->stream));     // host vectors go out of scope
+        O.obb = ctx->d_obb.as<double>();
+        O.tri = ctx->d_tri.as<double>();
+        O.gnx = gnx; O.gny = gny; O.gx0 = gx0; O.gy0 = gy0; O.inv_cell = inv;
+        O.cell_start = ctx->d_cell_start.as<int>();
+        O.cell_items = ctx->d_cell_items.as<int>();
+    }
+    // dynamic obstacles
+    const int n_dyn = (int)ctx->h_dyn_t0.size();
+    O.n_dyn = n_dyn;
+    if (n_dyn > 0) {
+        const size_t total = ctx->h_dyn.size() / 5;
+        std::vector<double> box(total * rp::kBoxStride);
+        for (size_t q = 0; q < total; ++q) {
+            const double* s = &ctx->h_dyn[q * 5];
+            double* o = &box[q * rp::kBoxStride];
+            o[0] = s[0]; o[1] = s[1]; o[2] = std::cos(s[2]); o[3] = std::sin(s[2]); o[4] = s[3]; o[5] = s[4];
+            o[6] = std::sqrt(s[3] * s[3] + s[4] * s[4]); o[7] = 1.0;
+        }
+        std::vector<int> meta((size_t)3 * n_dyn);
+        int off = 0;
+        for (int o = 0; o < n_dyn; ++o) {
+            meta[o] = ctx->h_dyn_t0[o];
+            meta[n_dyn + o] = ctx->h_dyn_len[o];
+            meta[2 * n_dyn + o] = off;
+            off += ctx->h_dyn_len[o];
+        }
+        if (int rc = ctx->d_dyn_box.ensure(std::max<size_t>(box.size(), 8) * sizeof(double))) return rc;
+        if (int rc = ctx->d_dyn_meta.ensure(meta.size() * sizeof(int))) return rc;
+        if (!box.empty())
+            RP_CUDA(cudaMemcpyAsync(ctx->d_dyn_box.p, box.data(), box.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaMemcpyAsync(ctx->d_dyn_meta.p, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaStreamSynchronize(ctx->stream));
+        O.dyn_t0 = ctx->d_dyn_meta.as<int>();
+        O.dyn_len = ctx->d_dyn_meta.as<int>() + n_dyn;
+        O.dyn_off = ctx->d_dyn_meta.as<int>() + 2 * n_dyn;
+        O.dyn_box = ctx->d_dyn_box.as<double>();
+    }
+    ctx->obstacles_dirty = false;
+    return RP_OK;
+}
+
+// ---- launch geometry of the fused kernel ---------------------------------------------------------
+struct Geometry {
+    int threads, C, n_groups, grid, stage_ref, stage_dyn;
+    size_t smem;
+    bool big;       // needs the 1024-thread instantiation
+};
+
+int plan_geometry(rp_ctx* ctx, int Np1, int count, Geometry& G) {
+    if (Np1 < 2 || Np1 > 1024) return fail(RP_ERR_ARG, "N + 1 must be in [2, 1024]");
+    G.big = Np1 > 256;
+    G.C = G.big ? 1 : std::max(1, 256 / Np1);
+    G.threads = ((G.C * Np1 + 31) / 32) * 32;
+    G.n_groups = (count + G.C - 1) / G.C;
+    const size_t scratch = (size_t)G.C * (9 * Np1 + 14 + 40 + 6) * sizeof(double) +
+                           (size_t)G.C * (Np1 + 4) * sizeof(int) + 16;
+    const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
+    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * rp::kBoxStride * sizeof(double);
+    const size_t budget = (size_t)ctx->max_smem_optin;
+    G.smem = scratch;
+    if (G.smem > budget) return fail(RP_ERR_ARG, "horizon too long for shared-memory scratch");
+    G.stage_ref = (ref_bytes <= 72 * 1024 && G.smem + ref_bytes <= budget) ? 1 : 0;
+    if (G.stage_ref) G.smem += ref_bytes;
+    G.stage_dyn = (ctx->obs.n_dyn > 0 && dyn_bytes <= 64 * 1024 && G.smem + dyn_bytes <= budget) ? 1 : 0;
+    if (G.stage_dyn) G.smem += dyn_bytes;
+    int occ = 0;
+    if (G.big) {
+        RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<1024>, G.threads, G.smem));
+    } else {
+        RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<256>, G.threads, G.smem));
+    }
+    if (occ < 1) return fail(RP_ERR_CUDA, "fused kernel does not fit on an SM");
+    G.grid = std::max(1, std::min(G.n_groups, occ * ctx->num_sms));
+    return RP_OK;
+}
+
+void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G) {
+    P.in = ctx->in;
+    P.lim.a_max = ctx->veh.a_max;
+    P.lim.v_switch = ctx->veh.v_switch;
+    P.lim.wheelbase = ctx->veh.wheelbase;
+    P.lim.v_delta_max = ctx->veh.v_delta_max;
+    P.lim.kappa_max = ctx->veh.kappa_max;
+    P.half_len = 0.5 * ctx->veh.length;
+    P.half_wid = 0.5 * ctx->veh.width;
+    P.wb_rear = ctx->veh.wb_rear_axle;
+    P.r_ego = std::sqrt(P.half_len * P.half_len + P.half_wid * P.half_wid);
+    const double* base = ctx->d_ref.as<double>();
+    const int n = ctx->ref_n;
+    P.ref.n = n;
+    P.ref.same_s = ctx->ref_same_s;
+    P.ref.limit = ctx->ref_limit;
+    P.ref.pos = base; P.ref.theta = base + n; P.ref.curv = base + 2 * n; P.ref.curv_d = base + 3 * n;
+    P.ref.px = base + 4 * n; P.ref.py = base + 5 * n; P.ref.nx = base + 6 * n; P.ref.ny = base + 7 * n;
+    P.ref.ps = base + 8 * n;
+    P.obs = ctx->obs;
+    P.C = G.C;
+    P.Np1 = ctx->in.N + 1;
+    P.n_groups = G.n_groups;
+    P.stage_ref = G.stage_ref;
+    P.stage_dyn = G.stage_dyn;
+    P.mode = ctx->mode;
+    P.n_t = ctx->n_t; P.n_lon = ctx->n_lon; P.n_d = ctx->n_d;
+    P.n_cand = ctx->n_cand;
+    if (ctx->mode == 0) {
+        const char* sb = static_cast<const char*>(ctx->d_samples.p);
+        P.lon_samples = reinterpret_cast<const double*>(sb + ctx->off_lon);
+        P.traj_len = reinterpret_cast<const int*>(sb + ctx->off_len);
+        P.skip = nullptr;
+    } else {
+        P.lon_samples = nullptr;
+        P.traj_len = reinterpret_cast<const int*>(static_cast<const char*>(ctx->d_samples.p) + ctx->off_len);
+        P.skip = ctx->d_skip.p ? ctx->d_skip.as<uint8_t>() : nullptr;
+    }
+    P.lon_coef = ctx->d_lon_coef.as<double>();
+    P.lat_coef = ctx->d_lat_coef.as<double>();
+}
+
+int launch_fused(rp_ctx* ctx, const PlanParams& P, const Geometry& G) {
+    if (G.big) rp::fused_kernel<1024><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+    else rp::fused_kernel<256><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+    RP_CUDA(cudaGetLastError());
+    return RP_OK;
+}
+
+int check_ready(rp_ctx* ctx) {
+    if (!ctx->have_vehicle) return fail(RP_ERR_STATE, "vehicle parameters not set");
+    if (!ctx->have_ref) return fail(RP_ERR_STATE, "reference tables not set");
+    if (ctx->obstacles_dirty)
+        if (int rc = build_obstacle_tables(ctx)) return rc;
+    return RP_OK;
+}
+
+int check_inputs(const rp_plan_inputs* in) {
+    if (!in) return fail(RP_ERR_ARG, "null inputs");
+    if (in->N < 1 || in->N > 1023) return fail(RP_ERR_ARG, "N out of range");
+    if (!(in->dt > 0)) return fail(RP_ERR_ARG, "dt must be positive");
+    if (in->lon_mode != RP_VELOCITY_KEEPING && in->lon_mode != RP_STOPPING) return fail(RP_ERR_ARG, "invalid lon_mode");
+    if (in->cost_kind < RP_COST_DEFAULT || in->cost_kind > RP_COST_NONE) return fail(RP_ERR_ARG, "invalid cost_kind");
+    return RP_OK;
+}
+
+// winner (or arbitrary candidate) state block via an index-mode launch
+int launch_states_for_index(rp_ctx* ctx, const int* d_index, int count, double* d_out) {
+    Geometry G;
+    const int Np1 = ctx->in.N + 1;
+    if (int rc = plan_geometry(ctx, Np1, count, G)) return rc;
+    PlanParams P{};
+    fill_common(ctx, P, G);
+    P.first = 0;
+    P.count = count;
+    P.index = d_index;
+    P.cost = nullptr;
+    P.info = nullptr;
+    P.states = d_out;
+    P.states_by_slot = 1;
+    P.in.draw_all = 1;          // produce states whatever the verdict was
+    P.in.check_collision = 0;
+    P.in.cost_kind = RP_COST_NONE;
+    return launch_fused(ctx, P, G);
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* rp_last_error(void) { return g_err.c_str(); }
+int rp_version(void) { return 100; }
+
+int rp_ctx_create(int device, void* stream, rp_ctx** out) {
+    if (!out) return fail(RP_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    int n_dev = 0;
+    RP_CUDA(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(RP_ERR_ARG, "invalid CUDA device index");
+    RP_CUDA(cudaSetDevice(device));
+    rp_ctx* ctx = new rp_ctx();
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return fail(RP_ERR_CUDA, cudaGetErrorString(e)); }
+        ctx->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    if (ctx->d_result.ensure(sizeof(rp::PlanResultDev)) || ctx->h_result.ensure(sizeof(rp::PlanResultDev)) ||
+        ctx->d_index.ensure(sizeof(int))) {
+        rp_ctx_destroy(ctx);
+        return RP_ERR_NOMEM;
+    }
+    *out = ctx;
+    return RP_OK;
+}
+
+int rp_ctx_destroy(rp_ctx* ctx) {
+    if (!ctx) return RP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->d_ref, &ctx->d_obb, &ctx->d_tri, &ctx->d_cell_start, &ctx->d_cell_items, &ctx->d_dyn_box,
+                      &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
+                      &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all, &ctx->d_states_one,
+                      &ctx->d_result, &ctx->d_index})
+        b->release();
+    ctx->h_stage.release();
+    ctx->h_result.release();
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RP_OK;
+}
+
+int rp_ctx_synchronize(rp_ctx* ctx) {
+    if (int rc = bind(ctx)) return rc;
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RP_OK;
+}
+
+int rp_ctx_set_vehicle(rp_ctx* ctx, const rp_vehicle_params* vp) {
+    if (int rc = bind(ctx)) return rc;
+    if (!vp) return fail(RP_ERR_ARG, "null vehicle parameters");
+    if (!(vp->length > 0 && vp->width > 0 && vp->wheelbase > 0)) return fail(RP_ERR_ARG, "vehicle dimensions must be positive");
+    ctx->veh = *vp;
+    ctx->have_vehicle = true;
+    ctx->obstacles_dirty = true;       // broad-phase inflation depends on the ego circumradius
+    return RP_OK;
+}
+
+int rp_ctx_set_reference(rp_ctx* ctx, int n, const double* ref_pos, const double* ref_theta, const double* ref_curv,
+                         const double* ref_curv_d, const double* path_xy, const double* path_s,
+                         const double* path_normal_xy, double proj_limit) {
+    if (int rc = bind(ctx)) return rc;
+    if (n < 2) return fail(RP_ERR_ARG, "reference path needs at least 2 points");
+    if (!ref_pos || !ref_theta || !ref_curv || !ref_curv_d || !path_xy || !path_s || !path_normal_xy)
+        return fail(RP_ERR_ARG, "null reference array");
+    for (int q = 1; q < n; ++q)
+        if (!(ref_pos[q] > ref_pos[q - 1]) || !(path_s[q] > path_s[q - 1]))
+            return fail(RP_ERR_ARG, "ref_pos / path_s must be strictly increasing");
+    std::vector<double> pack((size_t)9 * n);
+    std::memcpy(&pack[0], ref_pos, n * sizeof(double));
+    std::memcpy(&pack[(size_t)n], ref_theta, n * sizeof(double));
+    std::memcpy(&pack[(size_t)2 * n], ref_curv, n * sizeof(double));
+    std::memcpy(&pack[(size_t)3 * n], ref_curv_d, n * sizeof(double));
+    for (int q = 0; q < n; ++q) {
+        pack[(size_t)4 * n + q] = path_xy[2 * q];
+        pack[(size_t)5 * n + q] = path_xy[2 * q + 1];
+        pack[(size_t)6 * n + q] = path_normal_xy[2 * q];
+        pack[(size_t)7 * n + q] = path_normal_xy[2 * q + 1];
+    }
+    std::memcpy(&pack[(size_t)8 * n], path_s, n * sizeof(double));
+    if (int rc = ctx->d_ref.ensure(pack.size() * sizeof(double))) return rc;
+    RP_CUDA(cudaMemcpyAsync(ctx->d_ref.p, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->ref_n = n;
+    ctx->ref_same_s = std::memcmp(ref_pos, path_s, n * sizeof(double)) == 0 ? 1 : 0;
+    ctx->ref_limit = proj_limit;
+    ctx->have_ref = true;
+    return RP_OK;
+}
+
+int rp_ctx_set_obstacles(rp_ctx* ctx, int n_static, const double* static_obb, int n_dyn, const int32_t* dyn_t0,
+                         const int32_t* dyn_len, const double* dyn_obb, int n_tri, const double* tris,
+                         double cell_size) {
+    if (int rc = bind(ctx)) return rc;
+    if (n_static < 0 || n_dyn < 0 || n_tri < 0) return fail(RP_ERR_ARG, "negative obstacle count");
+    if ((n_static && !static_obb) || (n_dyn && (!dyn_t0 || !dyn_len)) || (n_tri && !tris))
+        return fail(RP_ERR_ARG, "null obstacle array");
+    size_t total = 0;
+    for (int o = 0; o < n_dyn; ++o) {
+        if (dyn_len[o] < 0) return fail(RP_ERR_ARG, "negative dynamic obstacle length");
+        total += (size_t)dyn_len[o];
+    }
+    if (total && !dyn_obb) return fail(RP_ERR_ARG, "null dynamic obstacle boxes");
+    ctx->h_static.assign(static_obb, static_obb + (size_t)n_static * 5);
+    ctx->h_dyn_t0.assign(dyn_t0, dyn_t0 + n_dyn);
+    ctx->h_dyn_len.assign(dyn_len, dyn_len + n_dyn);
+    ctx->h_dyn.assign(dyn_obb, dyn_obb + total * 5);
+    ctx->h_tri.assign(tris, tris + (size_t)n_tri * 6);
+    ctx->cell_size = cell_size > 0 ? cell_size : 2.0;
+    ctx->obstacles_dirty = true;
+    return RP_OK;
+}
+
+int rp_set_candidate_range(rp_ctx* ctx, int first, int count) {
+    if (!ctx) return fail(RP_ERR_ARG, "null context");
+    if (count >= 0 && first < 0) return fail(RP_ERR_ARG, "negative range start");
+    ctx->range_first = count < 0 ? 0 : first;
+    ctx->range_count = count;
+    return RP_OK;
+}
+
+int rp_grid_upload(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double* t, const int32_t* traj_len, int n_lon,
+                   const double* lon, int n_d, const double* d) {
+    if (int rc = bind(ctx)) return rc;
+    if (int rc = check_inputs(in)) return rc;
+    if (n_t < 0 || n_lon < 0 || n_d < 0) return fail(RP_ERR_ARG, "negative sample count");
+    if ((n_t && (!t || !traj_len)) || (n_lon && !lon) || (n_d && !d)) return fail(RP_ERR_ARG, "null sample array");
+    const long long n_cand = (long long)n_t * n_lon * n_d;
+    if (n_cand > 0x7fffffffLL / 8) return fail(RP_ERR_ARG, "bundle too large");
+    for (int q = 0; q < n_t; ++q)
+        if (traj_len[q] < 1 || traj_len[q] > in->N + 1) return fail(RP_ERR_ARG, "traj_len out of [1, N+1]");
+    ctx->in = *in;
+    ctx->mode = 0;
+    ctx->n_t = n_t; ctx->n_lon = n_lon; ctx->n_d = n_d;
+    ctx->n_cand = (int)n_cand;
+    ctx->off_t = 0;
+    ctx->off_lon = ctx->off_t + (size_t)n_t * sizeof(double);
+    ctx->off_d = ctx->off_lon + (size_t)n_lon * sizeof(double);
+    ctx->off_len = ctx->off_d + (size_t)n_d * sizeof(double);
+    const size_t bytes = ctx->off_len + (size_t)n_t * sizeof(int);
+    if (int rc = ctx->h_stage.ensure(bytes)) return rc;
+    if (int rc = ctx->d_samples.ensure(bytes)) return rc;
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));       // staging buffer may still be in flight
+    char* hs = static_cast<char*>(ctx->h_stage.p);
+    if (n_t) std::memcpy(hs + ctx->off_t, t, (size_t)n_t * sizeof(double));
+    if (n_lon) std::memcpy(hs + ctx->off_lon, lon, (size_t)n_lon * sizeof(double));
+    if (n_d) std::memcpy(hs + ctx->off_d, d, (size_t)n_d * sizeof(double));
+    if (n_t) std::memcpy(hs + ctx->off_len, traj_len, (size_t)n_t * sizeof(int));
+    if (bytes) RP_CUDA(cudaMemcpyAsync(ctx->d_samples.p, hs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_inputs = true;
+    ctx->have_plan = false;
+    return RP_OK;
+}
+
+static int launch_plan(rp_ctx* ctx) {
+    if (int rc = check_ready(ctx)) return rc;
+    const int Np1 = ctx->in.N + 1;
+    const int n = ctx->n_cand;
+    int first = 0, count = n;
+    if (ctx->range_count >= 0) {
+        first = std::min(ctx->range_first, n);
+        count = std::min(ctx->range_count, n - first);
+    }
+    if (int rc = ctx->d_cost.ensure((size_t)std::max(n, 1) * sizeof(double))) return rc;
+    if (int rc = ctx->d_info.ensure((size_t)std::max(n, 1) * sizeof(int))) return rc;
+    if (int rc = ctx->d_states_one.ensure((size_t)14 * Np1 * sizeof(double))) return rc;
+    ctx->states_all_valid = false;
+    if (ctx->in.want_all_states) {
+        if (int rc = ctx->d_states_all.ensure((size_t)std::max(n, 1) * 14 * Np1 * sizeof(double))) return rc;
+    }
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (ctx->mode == 0 && n > 0) {
+        const int n_lon_sys = ctx->n_t * ctx->n_lon;
+        const int n_lat_sys = ctx->in.low_vel_mode ? n : ctx->n_t * ctx->n_d;
+        if (int rc = ctx->d_lon_coef.ensure((size_t)n_lon_sys * 6 * sizeof(double))) return rc;
+        if (int rc = ctx->d_lat_coef.ensure((size_t)n_lat_sys * 6 * sizeof(double))) return rc;
+        if (int rc = ctx->d_lat_tau.ensure((size_t)n_lat_sys * sizeof(double))) return rc;
+        const char* sb = static_cast<const char*>(ctx->d_samples.p);
+        const int total = n_lon_sys + n_lat_sys;
+        rp::coeff_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(
+            ctx->n_t, ctx->n_lon, ctx->n_d, ctx->in.low_vel_mode, ctx->in.lon_mode,
+            reinterpret_cast<const double*>(sb + ctx->off_t), reinterpret_cast<const double*>(sb + ctx->off_lon),
+            reinterpret_cast<const double*>(sb + ctx->off_d), ctx->in.x0_lon[0], ctx->in.x0_lon[1], ctx->in.x0_lon[2],
+            ctx->in.x0_lat[0], ctx->in.x0_lat[1], ctx->in.x0_lat[2], ctx->d_lon_coef.as<double>(),
+            ctx->d_lat_coef.as<double>(), ctx->d_lat_tau.as<double>());
+        RP_CUDA(cudaGetLastError());
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (count > 0) {
+        Geometry G;
+        if (int rc = plan_geometry(ctx, Np1, count, G)) return rc;
+        PlanParams P{};
+        fill_common(ctx, P, G);
+        P.first = first;
+        P.count = count;
+        P.index = nullptr;
+        P.cost = ctx->d_cost.as<double>();
+        P.info = ctx->d_info.as<int>();
+        P.states = ctx->in.want_all_states ? ctx->d_states_all.as<double>() : nullptr;
+        P.states_by_slot = 0;
+        if (int rc = launch_fused(ctx, P, G)) return rc;
+        ctx->states_all_valid = ctx->in.want_all_states != 0;
+    }
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    rp::PlanResultDev* dres = ctx->d_result.as<rp::PlanResultDev>();
+    rp::finalize_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, n, dres);
+    RP_CUDA(cudaGetLastError());
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    // winner's 14 x (N+1) state block; the winner index never leaves the device
+    if (count > 0) {
+        if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one.as<double>())) return rc;
+    }
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    ctx->ev_valid = true;
+    ctx->have_plan = true;
+    return RP_OK;
+}
+
+int rp_grid_launch(rp_ctx* ctx) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ctx->have_inputs || ctx->mode != 0) return fail(RP_ERR_STATE, "rp_grid_upload must precede rp_grid_launch");
+    return launch_plan(ctx);
+}
+
+int rp_grid_result(rp_ctx* ctx, rp_plan_result* out) {
+    if (int rc = bind(ctx)) return rc;
+    if (!out) return fail(RP_ERR_ARG, "null result");
+    if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
+    RP_CUDA(cudaMemcpyAsync(ctx->h_result.p, ctx->d_result.p, sizeof(rp::PlanResultDev), cudaMemcpyDeviceToHost, ctx->stream));
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = static_cast<rp::PlanResultDev*>(ctx->h_result.p)->r;
+    return RP_OK;
+}
+
+int rp_plan_grid(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double* t, const int32_t* traj_len, int n_lon,
+                 const double* lon, int n_d, const double* d, rp_plan_result* out) {
+    if (int rc = rp_grid_upload(ctx, in, n_t, t, traj_len, n_lon, lon, n_d, d)) return rc;
+    if (int rc = rp_grid_launch(ctx)) return rc;
+    return rp_grid_result(ctx, out);
+}
+
+int rp_plan_list(rp_ctx* ctx, const rp_plan_inputs* in, int n_cand, const double* coeffs_lon, const double* coeffs_lat,
+                 const int32_t* traj_len, const uint8_t* skip, rp_plan_result* out) {
+    if (int rc = bind(ctx)) return rc;
+    if (int rc = check_inputs(in)) return rc;
+    if (n_cand < 0) return fail(RP_ERR_ARG, "negative candidate count");
+    if (n_cand && (!coeffs_lon || !coeffs_lat || !traj_len)) return fail(RP_ERR_ARG, "null candidate array");
+    for (int q = 0; q < n_cand; ++q)
+        if (traj_len[q] < 1 || traj_len[q] > in->N + 1) return fail(RP_ERR_ARG, "traj_len out of [1, N+1]");
+    ctx->in = *in;
+    ctx->mode = 1;
+    ctx->n_t = ctx->n_lon = ctx->n_d = 0;
+    ctx->n_cand = n_cand;
+    ctx->off_len = 0;
+    const size_t nb = (size_t)std::max(n_cand, 1);
+    if (int rc = ctx->d_samples.ensure(nb * sizeof(int))) return rc;
+    if (int rc = ctx->d_lon_coef.ensure(nb * 6 * sizeof(double))) return rc;
+    if (int rc = ctx->d_lat_coef.ensure(nb * 6 * sizeof(double))) return rc;
+    if (n_cand) {
+        RP_CUDA(cudaMemcpyAsync(ctx->d_samples.p, traj_len, (size_t)n_cand * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaMemcpyAsync(ctx->d_lon_coef.p, coeffs_lon, (size_t)n_cand * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaMemcpyAsync(ctx->d_lat_coef.p, coeffs_lat, (size_t)n_cand * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (skip && n_cand) {
+        if (int rc = ctx->d_skip.ensure(nb)) return rc;
+        RP_CUDA(cudaMemcpyAsync(ctx->d_skip.p, skip, (size_t)n_cand, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        ctx->d_skip.release();
+    }
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));       // pageable host buffers are the caller's
+    ctx->have_inputs = true;
+    if (int rc = launch_plan(ctx)) return rc;
+    return rp_grid_result(ctx, out);
+}
+
+int rp_fetch_states(rp_ctx* ctx, int idx, double* out) {
+    if (int rc = bind(ctx)) return rc;
+    if (!out) return fail(RP_ERR_ARG, "null output");
+    if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
+    if (idx < 0 || idx >= ctx->n_cand) return fail(RP_ERR_ARG, "candidate index out of range");
+    const size_t bytes = (size_t)14 * (ctx->in.N + 1) * sizeof(double);
+    const rp::PlanResultDev* hres = static_cast<rp::PlanResultDev*>(ctx->h_result.p);
+    if (ctx->states_all_valid) {
+        RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_all.as<double>() + (size_t)idx * 14 * (ctx->in.N + 1), bytes,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        RP_CUDA(cudaMemcpyAsync(ctx->h_result.p, ctx->d_result.p, sizeof(rp::PlanResultDev), cudaMemcpyDeviceToHost, ctx->stream));
+        RP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (hres->r.winner != idx) {
+            // lazily re-evaluate one candidate (TrajectorySample views of non-winners)
+            RP_CUDA(cudaMemcpyAsync(ctx->d_index.p, &idx, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            if (int rc = ctx->d_states_all.ensure(bytes)) return rc;
+            if (int rc = launch_states_for_index(ctx, ctx->d_index.as<int>(), 1, ctx->d_states_all.as<double>())) return rc;
+            RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_all.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_one.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RP_OK;
+}
+
+int rp_fetch_candidates(rp_ctx* ctx, double* cost, int32_t* status, int32_t* reason, int32_t* step) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
+    const int n = ctx->n_cand;
+    if (n == 0) return RP_OK;
+    if (cost) RP_CUDA(cudaMemcpyAsync(cost, ctx->d_cost.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int> info;
+    if (status || reason || step) {
+        info.resize(n);
+        RP_CUDA(cudaMemcpyAsync(info.data(), ctx->d_info.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < (int)info.size(); ++q) {
+        if (status) status[q] = info[q] & 0xFF;
+        if (reason) reason[q] = (info[q] >> 8) & 0xFF;
+        if (step) step[q] = ((info[q] >> 16) & 0xFFFF) - 1;
+    }
+    return RP_OK;
+}
+
+int rp_fetch_coeffs(rp_ctx* ctx, double* coeffs_lon, double* coeffs_lat, double* delta_tau_lat) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
+    const int n = ctx->n_cand;
+    if (n == 0) return RP_OK;
+    if (ctx->mode == 1) {
+        if (coeffs_lon) RP_CUDA(cudaMemcpyAsync(coeffs_lon, ctx->d_lon_coef.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+        if (coeffs_lat) RP_CUDA(cudaMemcpyAsync(coeffs_lat, ctx->d_lat_coef.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+        RP_CUDA(cudaStreamSynchronize(ctx->stream));
+        return RP_OK;
+    }
+    const int n_lon_sys = ctx->n_t * ctx->n_lon;
+    const bool lv = ctx->in.low_vel_mode != 0;
+    const int n_lat_sys = lv ? n : ctx->n_t * ctx->n_d;
+    std::vector<double> hl((size_t)n_lon_sys * 6), ht((size_t)n_lat_sys * 6), htau((size_t)n_lat_sys);
+    RP_CUDA(cudaMemcpyAsync(hl.data(), ctx->d_lon_coef.p, hl.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RP_CUDA(cudaMemcpyAsync(ht.data(), ctx->d_lat_coef.p, ht.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RP_CUDA(cudaMemcpyAsync(htau.data(), ctx->d_lat_tau.p, htau.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n; ++k) {
+        const int per_t = ctx->n_lon * ctx->n_d;
+        const int it = k / per_t, rem = k - it * per_t, il = rem / ctx->n_d, id = rem - il * ctx->n_d;
+        const size_t ql = (size_t)(it * ctx->n_lon + il), qt = lv ? (size_t)k : (size_t)(it * ctx->n_d + id);
+        if (coeffs_lon) std::memcpy(coeffs_lon + (size_t)k * 6, &hl[ql * 6], 48);
+        if (coeffs_lat) std::memcpy(coeffs_lat + (size_t)k * 6, &ht[qt * 6], 48);
+        if (delta_tau_lat) delta_tau_lat[k] = htau[qt];
+    }
+    return RP_OK;
+}
+
+int rp_solve_coeffs(rp_ctx* ctx, int n, const int32_t* kind, const double* x0, const double* xd, const double* tau,
+                    double* coeffs) {
+    if (int rc = bind(ctx)) return rc;
+    if (n < 0) return fail(RP_ERR_ARG, "negative count");
+    if (n == 0) return RP_OK;
+    if (!kind || !x0 || !xd || !tau || !coeffs) return fail(RP_ERR_ARG, "null array");
+    DevBuf dk, dx0, dxd, dtau, dc, dok;
+    int rc = RP_OK;
+    auto cleanup = [&]() { dk.release(); dx0.release(); dxd.release(); dtau.release(); dc.release(); dok.release(); };
+    if ((rc = dk.ensure((size_t)n * 4)) || (rc = dx0.ensure((size_t)n * 24)) || (rc = dxd.ensure((size_t)n * 24)) ||
+        (rc = dtau.ensure((size_t)n * 8)) || (rc = dc.ensure((size_t)n * 48)) || (rc = dok.ensure((size_t)n * 4))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemcpyAsync(dk.p, kind, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dx0.p, x0, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dxd.p, xd, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dtau.p, tau, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    rp::solve_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dk.as<int>(), dx0.as<double>(), dxd.as<double>(),
+                                                               dtau.as<double>(), dc.as<double>(), dok.as<int>());
+    std::vector<int> ok(n);
+    cudaMemcpyAsync(coeffs, dc.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(ok.data(), dok.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e));
+    for (int q = 0; q < n; ++q)
+        if (!ok[q]) return fail(RP_ERR_ARG, "singular system in rp_solve_coeffs (numpy raises LinAlgError)");
+    return RP_OK;
+}
+
+int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time_idx, double half_length,
+                     double half_width, uint8_t* hit) {
+    if (int rc = bind(ctx)) return rc;
+    if (n < 0) return fail(RP_ERR_ARG, "negative count");
+    if (n == 0) return RP_OK;
+    if (!pose || !time_idx || !hit) return fail(RP_ERR_ARG, "null array");
+    if (!ctx->have_vehicle) return fail(RP_ERR_STATE, "vehicle parameters not set");
+    const double r_q = std::sqrt(half_length * half_length + half_width * half_width);
+    const double r_v = std::sqrt(0.25 * ctx->veh.length * ctx->veh.length + 0.25 * ctx->veh.width * ctx->veh.width);
+    if (r_q > r_v * (1.0 + 1e-12))
+        return fail(RP_ERR_ARG, "query box larger than the vehicle the broad-phase grid was built for");
+    if (ctx->obstacles_dirty)
+        if (int rc = build_obstacle_tables(ctx)) return rc;
+    DevBuf dp, dt, dh;
+    int rc = RP_OK;
+    auto cleanup = [&]() { dp.release(); dt.release(); dh.release(); };
+    if ((rc = dp.ensure((size_t)n * 24)) || (rc = dt.ensure((size_t)n * 4)) || (rc = dh.ensure((size_t)n))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemcpyAsync(dp.p, pose, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dt.p, time_idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    rp::collide_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dp.as<double>(), dt.as<int>(), half_length,
+                                                                 half_width, r_q, ctx->obs, dh.as<uint8_t>());
+    cudaMemcpyAsync(hit, dh.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e));
+    return RP_OK;
+}
+
+int rp_last_stage_ms(rp_ctx* ctx, float* ms4) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ms4) return fail(RP_ERR_ARG, "null output");
+    if (!ctx->ev_valid) return fail(RP_ERR_STATE, "no plan launched");
+    RP_CUDA(cudaEventSynchronize(ctx->ev[4]));
+    for (int q = 0; q < 4; ++q) RP_CUDA(cudaEventElapsedTime(&ms4[q], ctx->ev[q], ctx->ev[q + 1]));
+    return RP_OK;
+}
+
+int rp_launches_per_plan(rp_ctx* ctx) {
+    if (!ctx) return 0;
+    return ctx->mode == 0 ? 4 : 3;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+/*
+ * rp_b200.h -- C-ABI of the B200-native candidate-trajectory engine.
+ *
+ * Drop-in boundary for ONE hot path of commonroad-reactive-planner (reference paths relative to
+ * /root/reference): everything ReactivePlanner.plan() does between sampling the (t, lon, d) end
+ * states and returning the optimal trajectory sample:
+ *
+ *   sampling.py:202-242            enumeration  t x lon x (d U {d0})
+ *   polynomial_trajectory.py:292-360  quintic / quartic coefficient solve
+ *   reactive_planner.py:715-969    _check_kinematics (evaluation, Frenet->Cartesian, limits, extension)
+ *   reactive_planner.py:971-1017   _check_constraints
+ *   cost_function.py:51-71, :85-92 DefaultCostFunction / DefaultCostFunctionFailSafe
+ *   trajectories.py:502-510        TrajectoryBundle.sort  (here: feasible arg-min)
+ *   reactive_planner.py:1019-1063  _check_collisions (discrete ego-vs-obstacle check)
+ *   reactive_planner.py:1065-1136  _get_optimal_trajectory
+ *
+ * The reference has no FFI today (its operator API is the Python class surface); these are the
+ * entry points a binding for that path would call.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions: plain pointers and sizes, host buffers unless the name says "_dev"; all floating
+ * point is IEEE fp64; every function returns 0 on success and a negative rp_status on failure,
+ * with a message available from rp_last_error().  "No feasible candidate" is NOT an error
+ * (winner == -1).  A context is bound to one CUDA device and one stream; calls on one context
+ * are not re-entrant, distinct contexts may be used from distinct threads.
+ */
+#ifndef RP_B200_H
+#define RP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rp_ctx rp_ctx;
+
+enum rp_status {
+    RP_OK = 0,
+    RP_ERR_ARG = -1,      /* invalid argument            */
+    RP_ERR_CUDA = -2,     /* CUDA runtime failure        */
+    RP_ERR_STATE = -3,    /* call order (missing tables) */
+    RP_ERR_NOMEM = -4
+};
+
+/* candidate status (FeasibilityStatus, trajectories.py:18-22; FILTERED = filter_goals_behind, :545-550) */
+enum rp_cand_status { RP_FEASIBLE = 0, RP_INFEASIBLE_KINEMATIC = 1, RP_INFEASIBLE_COLLISION = 2, RP_FILTERED = 3 };
+
+/* reason of a kinematic rejection: keys of infeasible_reason_dict (reactive_planner.py:799,803,979-1016),
+ * plus the projection-domain rejection (:911-917) which the reference counts but does not name. */
+enum rp_reason {
+    RP_R_NONE = 0, RP_R_VELOCITY = 1, RP_R_ACCELERATION = 2, RP_R_KAPPA = 3, RP_R_KAPPA_DOT = 4,
+    RP_R_YAW_RATE = 5, RP_R_PROJECTION = 6, RP_R_REF_RANGE = 7, RP_N_REASONS = 8
+};
+
+/* constraints_to_check bit mask (utility/config.py:127-128) */
+enum rp_constraint_bits {
+    RP_C_VELOCITY = 1, RP_C_ACCELERATION = 2, RP_C_KAPPA = 4, RP_C_KAPPA_DOT = 8, RP_C_YAW_RATE = 16
+};
+
+enum rp_lon_mode { RP_VELOCITY_KEEPING = 0, RP_STOPPING = 1 };          /* sampling.py:244-266 */
+enum rp_cost_kind { RP_COST_DEFAULT = 0, RP_COST_FAILSAFE = 1, RP_COST_NONE = 2 };
+
+/* order of the 14 state rows returned by rp_fetch_states (CartesianSample / CurviLinearSample,
+ * trajectories.py:61-332) */
+enum rp_state_row {
+    RP_X = 0, RP_Y, RP_THETA, RP_V, RP_A, RP_KAPPA, RP_KAPPA_DOT,
+    RP_S, RP_D, RP_THETA_CL, RP_S_DOT, RP_S_DDOT, RP_D_DOT, RP_D_DDOT, RP_N_STATE_ROWS
+};
+
+/* VehicleConfiguration (utility/config.py:194-222); kappa_max = tan(delta_max) / wheelbase is
+ * computed by the HOST (same expression as :222) so both sides compare against the same double. */
+typedef struct rp_vehicle_params {
+    double length, width;
+    double wb_rear_axle;
+    double wheelbase;
+    double a_max, v_switch;
+    double delta_max, v_delta_max;
+    double kappa_max;
+} rp_vehicle_params;
+
+/* per-cycle scalar inputs of plan() (reactive_planner.py:570-665) */
+typedef struct rp_plan_inputs {
+    double x0_lon[3];            /* s, s_dot, s_ddot                       (:591)           */
+    double x0_lat[3];            /* d, d_dot, d_ddot                                         */
+    double x0_orientation;       /* x_0.orientation                        (:866)           */
+    int32_t x0_time_step;        /* x_0.time_step                          (:1040)          */
+    int32_t low_vel_mode;        /* x_0.velocity < low_vel_mode_threshold  (:594)           */
+    int32_t lon_mode;            /* rp_lon_mode                                              */
+    int32_t N;                   /* time_steps_computation                                   */
+    double dt;
+    int32_t factor;              /* config.planning.factor                 (:1040)          */
+    int32_t draw_all;            /* _draw_traj_set: no pre-filter, no early exit (:97, :796, :903) */
+    uint32_t constraint_mask;    /* rp_constraint_bits                                       */
+    int32_t cost_kind;           /* rp_cost_kind                                             */
+    int32_t has_desired_speed;   /* DefaultCostFunction.desired_speed is not None            */
+    int32_t has_desired_s;       /* DefaultCostFunction.desired_s is not None                */
+    double desired_speed, desired_s, desired_d, w_a;
+    int32_t want_all_states;     /* 1: keep the 14 x (N+1) state block of EVERY candidate     */
+    int32_t check_collision;     /* 0: skip a13 (collision flags all clear)                  */
+} rp_plan_inputs;
+
+typedef struct rp_plan_result {
+    int32_t winner;                        /* enumeration index of the optimal candidate, -1 if none   */
+    int32_t n_candidates;
+    int32_t n_feasible;                    /* kinematically feasible (before the collision check)     */
+    int32_t n_infeasible_kinematics;       /* ReactivePlanner.infeasible_count_kinematics (:1119)     */
+    int32_t n_infeasible_collision;        /* colliders ranked before the winner (:1043; App. B#12)   */
+    int32_t n_collision_total;             /* all kinematically feasible candidates that collide      */
+    int32_t reason_counts[RP_N_REASONS];   /* infeasible_reason_dict (+ projection)                   */
+    double winner_cost;
+} rp_plan_result;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+const char* rp_last_error(void);
+int rp_version(void);
+/* stream: a cudaStream_t created by the caller on `device` (e.g. torch.cuda.current_stream().cuda_stream),
+ * or NULL to let the context create its own. */
+int rp_ctx_create(int device, void* stream, rp_ctx** out);
+int rp_ctx_destroy(rp_ctx* ctx);
+int rp_ctx_synchronize(rp_ctx* ctx);
+
+/* ---- scenario-static tables (set once, device resident) ------------------------------------- */
+/* VehicleConfiguration -> constants of a6/a7/a13 */
+int rp_ctx_set_vehicle(rp_ctx* ctx, const rp_vehicle_params* vp);
+
+/* CoordinateSystem (utility/utils_coordinate_system.py:113-118, :167-174): the planner's four
+ * reference arrays plus the curvilinear frame's own polyline tables for (s,d)->(x,y):
+ * path_xy[n][2] vertices, path_s[n] cumulative length, path_normal_xy[n][2] per-vertex
+ * pseudo-normals, proj_limit = lateral projection-domain limit. */
+int rp_ctx_set_reference(rp_ctx* ctx, int n_pts, const double* ref_pos, const double* ref_theta,
+                         const double* ref_curv, const double* ref_curv_d, const double* path_xy,
+                         const double* path_s, const double* path_normal_xy, double proj_limit);
+
+/* pycrcc.CollisionChecker content (reactive_planner.py:234-251):
+ *   static_obb[n_static][5]   = cx, cy, theta, half_length, half_width   (static obstacles + OBB road boundary)
+ *   dynamic obstacle o: time indices dyn_t0[o] .. dyn_t0[o]+dyn_len[o]-1, boxes dyn_obb[sum(len)][5] concatenated
+ *   tris[n_tri][6]            = x1, y1, x2, y2, x3, y3                   (triangulated road boundary)
+ * cell_size: edge of the uniform broad-phase grid over the static primitives (<= 0: default 2 m). */
+int rp_ctx_set_obstacles(rp_ctx* ctx, int n_static, const double* static_obb, int n_dyn,
+                         const int32_t* dyn_t0, const int32_t* dyn_len, const double* dyn_obb,
+                         int n_tri, const double* tris, double cell_size);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* Grid form (FixedIntervalSampling.generate_trajectories_at_level, sampling.py:202-242): the three
+ * ORDERED sample lists as the host's Python sets iterate them; traj_len[i] =
+ * len(np.arange(0, np.round(t[i] + dt, 5), dt)) (reactive_planner.py:733).  Candidate enumeration
+ * index = (i_t * n_lon + i_lon) * n_d + i_d.  lon = target velocities (velocity_keeping) or
+ * target positions (stopping). */
+int rp_plan_grid(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double* t, const int32_t* traj_len,
+                 int n_lon, const double* lon, int n_d, const double* d, rp_plan_result* out);
+
+/* The same three stages separately, so that a caller can keep inputs resident in HBM:
+ *   upload: host -> device copy of the inputs (asynchronous on the context's stream)
+ *   launch: coefficient solve + fused evaluation + arg-min + winner states (no host sync)
+ *   result: device -> host copy of rp_plan_result and synchronisation */
+int rp_grid_upload(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double* t, const int32_t* traj_len,
+                   int n_lon, const double* lon, int n_d, const double* d);
+int rp_grid_launch(rp_ctx* ctx);
+int rp_grid_result(rp_ctx* ctx, rp_plan_result* out);
+
+/* List form (any SamplingSpace, e.g. CorridorSampling, sampling.py:340-397): per-candidate
+ * polynomial coefficients as the host built them; skip[i] != 0 marks candidates dropped by
+ * filter_goals_behind (may be NULL). */
+int rp_plan_list(rp_ctx* ctx, const rp_plan_inputs* in, int n_cand, const double* coeffs_lon,
+                 const double* coeffs_lat, const int32_t* traj_len, const uint8_t* skip,
+                 rp_plan_result* out);
+
+/* Shard of the enumeration space [first, first+count) for multi-GPU bundles; affects the next
+ * rp_grid_launch / rp_plan_grid.  count < 0 resets to the whole bundle. */
+int rp_set_candidate_range(rp_ctx* ctx, int first, int count);
+
+/* ---- results of the last plan call ----------------------------------------------------------- */
+/* 14 x (N+1) state rows (rp_state_row order) of candidate idx; available for the winner always,
+ * for every candidate when want_all_states was set.  Other indices are re-evaluated on demand. */
+int rp_fetch_states(rp_ctx* ctx, int idx, double* out);
+/* per-candidate arrays of length n_candidates (any pointer may be NULL) */
+int rp_fetch_candidates(rp_ctx* ctx, double* cost, int32_t* status, int32_t* reason, int32_t* step);
+/* coefficients as solved on the device: lon[n][6], lat[n][6], delta_tau_lat[n] */
+int rp_fetch_coeffs(rp_ctx* ctx, double* coeffs_lon, double* coeffs_lat, double* delta_tau_lat);
+
+/* ---- stand-alone pieces ---------------------------------------------------------------------- */
+/* batched coefficient solve (polynomial_trajectory.py:292-360): kind 0 = quartic
+ * (x_d = target velocity in xd[i][0]), 1 = quintic; x0[n][3], xd[n][3], tau[n] -> coeffs[n][6] */
+int rp_solve_coeffs(rp_ctx* ctx, int n, const int32_t* kind, const double* x0, const double* xd,
+                    const double* tau, double* coeffs);
+/* pycrcc.CollisionChecker.collide for n ego boxes: pose[n][3] = cx, cy, theta (box centre),
+ * time_idx[n]; half extents from the arguments -> hit[n] (0/1) */
+int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time_idx,
+                     double half_length, double half_width, uint8_t* hit);
+
+/* device timing of the last rp_grid_launch stages in milliseconds: [coeff, fused, argmin, winner] */
+int rp_last_stage_ms(rp_ctx* ctx, float* ms4);
+/* number of kernels rp_grid_launch enqueues (for bench.py's gpu_launches) */
+int rp_launches_per_plan(rp_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RP_B200_H */

@@ -250,9 +250,33 @@ class Triangle:
 class ShapeGroup:
     def __init__(self):
         self.shapes = []
+        self._bound = None
 
     def add_shape(self, shape):
         self.shapes.append(shape)
+        self._bound = None
+
+    def near(self, box):
+        """Members whose bounding circle reaches the bounding circle of ``box`` (exact pre-selection:
+        shapes that fail this cannot overlap; keeps the pure-Python narrow phase affordable)."""
+        if self._bound is None:
+            c = np.zeros((len(self.shapes), 2))
+            r = np.zeros(len(self.shapes))
+            for k, sh in enumerate(self.shapes):
+                if isinstance(sh, Triangle):
+                    c[k] = sh.v.mean(axis=0)
+                    r[k] = np.max(np.linalg.norm(sh.v - c[k], axis=1))
+                else:
+                    c[k] = (sh.cx, sh.cy)
+                    r[k] = math.hypot(sh.r_x, sh.r_y)
+            self._bound = (c, r)
+        c, r = self._bound
+        if len(r) == 0:
+            return []
+        rb = math.hypot(box.r_x, box.r_y)
+        reach = (r + rb) * (1.0 + 1e-9) + 1e-9
+        hit = (c[:, 0] - box.cx) ** 2 + (c[:, 1] - box.cy) ** 2 <= reach * reach
+        return [self.shapes[k] for k in np.nonzero(hit)[0]]
 
 
 class TimeVariantCollisionObject:
@@ -322,9 +346,11 @@ def obb_triangle_overlap(a, tri):
 
 def shapes_overlap(a, b):
     if isinstance(a, ShapeGroup):
-        return any(shapes_overlap(s, b) for s in a.shapes)
+        members = a.near(b) if isinstance(b, RectOBB) else a.shapes
+        return any(shapes_overlap(s, b) for s in members)
     if isinstance(b, ShapeGroup):
-        return any(shapes_overlap(a, s) for s in b.shapes)
+        members = b.near(a) if isinstance(a, RectOBB) else b.shapes
+        return any(shapes_overlap(a, s) for s in members)
     if isinstance(a, RectOBB) and isinstance(b, RectOBB):
         return obb_obb_overlap(a, b)
     if isinstance(a, RectOBB) and isinstance(b, Triangle):

@@ -1,0 +1,157 @@
+"""Shared test plumbing: build oracle-format problems from synthetic scenarios, feed the SAME
+arrays through the C-ABI, and compare.  The oracle is only ever the checker here."""
+import numpy as np
+
+from commonroad_rp_b200.utility import synthetic
+from oracle import rp_oracle as O
+
+STATE_RTOL = 1e-9       # BASELINE.json north_star: states and costs within 1e-9 relative in fp64
+
+
+def set_order(values):
+    """iteration order of ``set(ndarray)`` -- the expression the reference samples with (sampling.py:83,98,116)."""
+    return [float(v) for v in set(np.asarray(values, dtype=np.float64))]
+
+
+def d_order(values, d0):
+    """``samples_d.union({x_0_lat[0]})`` iteration order (sampling.py:226)."""
+    return [float(v) for v in set(np.asarray(values, dtype=np.float64)).union({d0})]
+
+
+def level_sets(level, t_min, horizon, dt, v_lo, v_hi, d_lo=-3.0, d_hi=3.0):
+    """The reference's per-level sample sets (sampling.py:80-118) as ordered lists."""
+    n = 3
+    for _ in range(level):
+        n = n * 2 - 1
+    step = int((1 / (level + 1)) / dt)
+    samp = set(np.arange(t_min, round(horizon + dt, 2), step * dt))
+    samp.discard(round(horizon + dt, 2))
+    t = [float(x) for x in samp]
+    v = set_order(np.linspace(v_lo, v_hi, n))
+    d = set(np.linspace(d_lo, d_hi, n))
+    return t, v, d
+
+
+def make_problem(scn, t, lon, d, x0_lon, x0_lat, N=20, dt=0.1, lon_mode="velocity_keeping", low_vel_mode=False,
+                 x0_orientation=None, x0_time_step=0, factor=1, draw_all=False, constraints=O.CONSTRAINTS,
+                 desired_speed=15.0, desired_s=None, desired_d=0.0, w_a=5, cost_kind="default", smooth=True,
+                 tables=None):
+    ref, ccosy, _ = tables if tables is not None else O.reference_tables(scn["ref_path"], smooth=smooth)
+    if x0_orientation is None:
+        j = int(np.argmax(ref["ref_pos"] > x0_lon[0])) - 1
+        x0_orientation = float(ref["ref_theta"][j])
+    return {
+        "t": np.asarray(t, dtype=np.float64), "lon": np.asarray(lon, dtype=np.float64),
+        "d": np.asarray(d, dtype=np.float64),
+        "x0_lon": np.asarray(x0_lon, dtype=np.float64), "x0_lat": np.asarray(x0_lat, dtype=np.float64),
+        "x0_orientation": float(x0_orientation), "x0_time_step": int(x0_time_step),
+        "lon_mode": lon_mode, "low_vel_mode": bool(low_vel_mode), "dt": dt, "N": N, "factor": factor,
+        "draw_all": bool(draw_all), "constraints": tuple(constraints),
+        "cost": {"kind": cost_kind, "desired_speed": desired_speed, "desired_s": desired_s, "desired_d": desired_d,
+                 "w_a": w_a},
+        "vehicle": O.vehicle_dict(), "ref": ref, "ccosy": ccosy,
+        "obstacles": {k: scn[k] for k in ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes",
+                                          "boundary_tris")},
+    }
+
+
+def obstacle_arrays(obst):
+    """scenario-dict obstacles -> the C-ABI's (static_obb, dyn_t0, dyn_boxes, tris)."""
+    sb = np.asarray(obst.get("static_boxes", np.zeros((0, 5))), dtype=np.float64).reshape(-1, 5)
+    static = np.stack([sb[:, 0], sb[:, 1], sb[:, 2], 0.5 * sb[:, 3], 0.5 * sb[:, 4]], axis=1)
+    bb = np.asarray(obst.get("boundary_boxes", np.zeros((0, 5))), dtype=np.float64).reshape(-1, 5)
+    static = np.concatenate([static, bb], axis=0)
+    dyn_boxes = []
+    for st, lw in zip(obst.get("dyn_states", ()), obst.get("dyn_lw", ())):
+        st = np.asarray(st, dtype=np.float64).reshape(-1, 3)
+        dyn_boxes.append(np.concatenate([st, np.full((len(st), 1), 0.5 * lw[0]), np.full((len(st), 1), 0.5 * lw[1])],
+                                        axis=1))
+    tris = np.asarray(obst.get("boundary_tris", np.zeros((0, 6))), dtype=np.float64).reshape(-1, 6)
+    return static, np.asarray(obst.get("dyn_t0", ()), dtype=np.int32), dyn_boxes, tris
+
+
+def engine_for(prob, device=0, stream=None):
+    from commonroad_rp_b200._lib import Engine
+    eng = Engine(device, stream)
+    v = prob["vehicle"]
+    eng.set_vehicle(v["length"], v["width"], v["wb_rear_axle"], v["wheelbase"], v["a_max"], v["v_switch"],
+                    v["delta_max"], v["v_delta_max"])
+    r, c = prob["ref"], prob["ccosy"]
+    eng.set_reference(r["ref_pos"], r["ref_theta"], r["ref_curv"], r["ref_curv_d"], c["path"], c["S"], c["normals"],
+                      c["limit"])
+    static, t0, dyn_boxes, tris = obstacle_arrays(prob["obstacles"])
+    eng.set_obstacles(static, t0, dyn_boxes, tris)
+    return eng
+
+
+def inputs_for(prob, want_all_states=False, check_collision=True):
+    from commonroad_rp_b200 import _lib
+    cost = prob["cost"]
+    kind = {"default": _lib.COST_DEFAULT, "failsafe": _lib.COST_FAILSAFE}[cost.get("kind", "default")]
+    return _lib.Engine.make_inputs(
+        prob["x0_lon"], prob["x0_lat"], prob["x0_orientation"], prob["x0_time_step"], prob["low_vel_mode"],
+        prob["lon_mode"], prob["N"], prob["dt"], factor=prob["factor"], draw_all=prob.get("draw_all", False),
+        constraints=prob["constraints"], cost_kind=kind, desired_speed=cost.get("desired_speed"),
+        desired_s=cost.get("desired_s"), desired_d=cost.get("desired_d", 0.0), w_a=cost.get("w_a", 5),
+        want_all_states=want_all_states, check_collision=check_collision)
+
+
+def run_engine_grid(eng, prob, want_all_states=True):
+    res = eng.plan_grid(inputs_for(prob, want_all_states), prob["t"], prob["lon"], prob["d"])
+    cost, status, reason, step = eng.fetch_candidates()
+    cl, ct, tau = eng.fetch_coeffs()
+    out = {
+        "n": res.n_candidates, "winner": res.winner, "winner_cost": res.winner_cost,
+        "n_feasible": res.n_feasible, "n_infeasible_kinematics": res.n_infeasible_kinematics,
+        "n_infeasible_collision": res.n_infeasible_collision, "n_collision_total": res.n_collision_total,
+        "reason_counts": list(res.reason_counts), "cost": cost, "status": status, "reason": reason, "step": step,
+        "coeffs_lon": cl, "coeffs_lat": ct, "delta_tau_lat": tau,
+    }
+    if res.winner >= 0:
+        out["winner_states"] = eng.fetch_states(res.winner)
+    if want_all_states:
+        out["states"] = np.stack([eng.fetch_states(k) for k in range(res.n_candidates)]) if res.n_candidates else None
+    return out
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(a), np.abs(b))
+    err = np.abs(a - b)
+    # absolute floor: quantities that are differences of O(1..100) numbers (angles, offsets near zero)
+    return float(np.max(err / np.maximum(scale, 1.0))) if err.size else 0.0
+
+
+def assert_parity(o, g, prob, check_states=True, tag=""):
+    """oracle output ``o`` (rp_oracle.plan_grid, full_collision=True) vs engine output ``g``."""
+    n = o["n"]
+    assert g["n"] == n, tag
+    # coefficients: LAPACK LU vs in-register LU; conditioning bounds this by ~1e-10 relative
+    assert rel_err(o["coeffs_lon"], g["coeffs_lon"]) < 1e-9, tag
+    assert rel_err(o["coeffs_lat"], g["coeffs_lat"]) < 1e-9, tag
+    # flags: bit exact
+    o_status = o["status"]
+    assert np.array_equal(o_status, g["status"]), "%s status mismatch at %s" % (tag, np.nonzero(o_status != g["status"])[0][:10])
+    kin = o_status == O.ST_KINEMATIC
+    assert np.array_equal(o["reason"][kin], g["reason"][kin]), tag
+    assert np.array_equal(o["bad_step"][kin], g["step"][kin]), tag
+    col = o_status == O.ST_COLLISION
+    assert np.array_equal(o["collide_step"][col], g["step"][col]), tag
+    # selected index and counters: bit exact
+    assert o["winner"] == g["winner"], tag
+    assert o["n_infeasible_kinematics"] == g["n_infeasible_kinematics"], tag
+    assert o["n_infeasible_collision"] == g["n_infeasible_collision"], tag
+    from commonroad_rp_b200._lib import REASON_NAMES
+    for name, cnt in o["reasons"].items():
+        assert g["reason_counts"][REASON_NAMES.index(name)] == cnt, (tag, name)
+    # costs within 1e-9 relative
+    feas = (o_status == O.ST_FEASIBLE) | (o_status == O.ST_COLLISION)
+    if feas.any():
+        assert rel_err(o["cost"][feas], g["cost"][feas]) < STATE_RTOL, tag
+    if check_states and o.get("states") is not None and g.get("states") is not None:
+        have = ~np.isnan(o["states"][:, 0, 0])
+        if have.any():
+            assert rel_err(o["states"][have], g["states"][have]) < STATE_RTOL, tag
+    if o["winner"] >= 0 and o.get("states") is not None:
+        assert rel_err(o["states"][o["winner"]], g["winner_states"]) < STATE_RTOL, tag

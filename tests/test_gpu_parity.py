@@ -1,0 +1,53 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from commonroad_rp_b200.utility import synthetic
+from oracle import rp_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _bundle(seed, level, N, low_vel=False, lon_mode="velocity_keeping", draw_all=False, s_dot0=15.0, d0=0.3,
+            amplitude=20.0, wavelength=40.0, t_min=0.4, x0_time_step=0, desired_s=None, static_offset=0.0):
+    scn = synthetic.make_scenario(seed=seed, amplitude=amplitude, wavelength=wavelength, static_offset=static_offset)
+    dt = 0.1
+    if lon_mode == "velocity_keeping":
+        lo = max(0.0, s_dot0 - 0.125 * N * dt * 11.5)
+        hi = max(lo + 5.0, s_dot0 + 2)
+    else:
+        lo, hi = desired_s - 1.0, desired_s + 1.0
+    t, lon, dset = H.level_sets(level, t_min, N * dt, dt, lo, hi)
+    d = [float(x) for x in dset.union({d0})]
+    tables = O.reference_tables(scn["ref_path"])
+    s0 = float(tables[0]["ref_pos"][10])
+    return H.make_problem(scn, t, lon, d, [s0, s_dot0, 0.0], [d0, 0.0, 0.0], N=N, dt=dt, lon_mode=lon_mode,
+                          low_vel_mode=low_vel, draw_all=draw_all, desired_speed=s_dot0, desired_s=desired_s,
+                          x0_time_step=x0_time_step, tables=tables, w_a=5 if lon_mode == "velocity_keeping" else 1)
+
+
+CASES = [
+    dict(seed=0, level=1, N=20),
+    dict(seed=0, level=2, N=20),
+    dict(seed=1, level=3, N=20, d0=-0.4),
+    dict(seed=2, level=2, N=60, s_dot0=12.0),
+    dict(seed=3, level=2, N=20, low_vel=True, s_dot0=3.0),
+    dict(seed=4, level=2, N=30, s_dot0=1.0, low_vel=False),          # standstill carry branch
+    dict(seed=5, level=2, N=20, draw_all=True),
+    dict(seed=6, level=2, N=30, lon_mode="stopping", s_dot0=8.0, desired_s=24.0),
+    dict(seed=7, level=2, N=20, amplitude=0.0, static_offset=1.0),
+    dict(seed=8, level=1, N=20, x0_time_step=30),
+    dict(seed=9, level=2, N=7, t_min=0.2),                           # N+1 == 8: pairwise-sum edge
+    dict(seed=10, level=2, N=6, t_min=0.2),                          # N+1 < 8: plain-loop sum
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+def test_bundle_parity(case):
+    prob = _bundle(**case)
+    o = O.plan_grid(prob, want_states=True, full_collision=True)
+    eng = H.engine_for(prob)
+    g = H.run_engine_grid(eng, prob, want_all_states=True)
+    H.assert_parity(o, g, prob, tag=str(case))
+    eng.close()
