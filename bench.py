@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- candidate-trajectory throughput of the B200 engine (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores
+
+Workload (config.workload): BASELINE.json configs[3], the synthetic dense sampling sweep
+64 d x 64 v x 32 t end states over a 60-step horizon (131 072 candidates x 61 time steps per
+replanning cycle), SURVEY.md section 8d.  One "step" = one replanning cycle over that bundle:
+coefficient solve, fused evaluation (kinematics, projection, cost, collision), feasible arg-min and
+the winner's state block.
+
+  value      candidates/s with the sample lists already resident in HBM (K x rp_grid_launch,
+             device time by CUDA events on the launching stream, L2 flushed between iterations)
+  e2e        the same through the public host-buffer call (rp_plan_grid + rp_fetch_states): H2D of the
+             cycle's inputs and D2H of the result + winner states inside the timed region
+  roofline   the fused kernel against the MEASURED FP64-FMA peak (this path is FP64-pipe bound, not
+             HBM or tensor bound -- SURVEY 8d); algorithmic work = 200 flop per candidate-timestep
+  N > 1      the bundle grows with N (64*N velocity samples) and is sharded t-major over the ranks; one
+             small NCCL all-gather of (cost, index) records picks the global arg-min (weak scaling)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_CAND_STEP = 200.0      # SURVEY.md section 8d "ALGORITHMIC work per unit"
+STATE_BYTES_PER_CAND_STEP = 112.0
+METRIC = "candidate_trajectories_per_sec"
+UNIT = "candidates/s"
+N_HORIZON = 60
+DT = 0.1
+
+
+# --------------------------------------------------------------------------------------------------
+def dense_workload(n_gpus=1, seed=0):
+    """Scenario + ordered sample lists of the dense sweep.  The enumeration order is the host's
+    Python-set order, as the reference iterates it (sampling.py:218-226)."""
+    from commonroad_rp_b200.utility import synthetic
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    scn = synthetic.make_scenario(seed=seed)
+    t, v, d, d0 = synthetic.dense_grid(n_v=64 * n_gpus)
+    cosy = CoordinateSystem(scn["ref_path"])
+    s0 = float(cosy.ref_pos[10])
+    j = int(np.argmax(cosy.ref_pos > s0)) - 1
+    work = {
+        "scn": scn, "cosy": cosy,
+        "t": [float(x) for x in set(t)], "lon": [float(x) for x in set(v)],
+        "d": [float(x) for x in set(d).union({d0})],
+        "x0_lon": [s0, 15.0, 0.0], "x0_lat": [d0, 0.0, 0.0], "x0_orientation": float(cosy.ref_theta[j]),
+        "desired_speed": 15.0,
+    }
+    work["n_cand"] = len(work["t"]) * len(work["lon"]) * len(work["d"])
+    return work
+
+
+def obstacle_arrays(scn):
+    sb = np.asarray(scn["static_boxes"], dtype=np.float64).reshape(-1, 5)
+    static = np.stack([sb[:, 0], sb[:, 1], sb[:, 2], 0.5 * sb[:, 3], 0.5 * sb[:, 4]], axis=1)
+    static = np.concatenate([static, np.asarray(scn["boundary_boxes"], dtype=np.float64).reshape(-1, 5)], axis=0)
+    dyn = []
+    for st, lw in zip(scn["dyn_states"], scn["dyn_lw"]):
+        st = np.asarray(st, dtype=np.float64).reshape(-1, 3)
+        dyn.append(np.concatenate([st, np.full((len(st), 1), 0.5 * lw[0]), np.full((len(st), 1), 0.5 * lw[1])], axis=1))
+    return static, np.asarray(scn["dyn_t0"], dtype=np.int32), dyn
+
+
+def make_engine(work, device, stream):
+    from commonroad_rp_b200._lib import Engine
+    from commonroad_rp_b200.utility.config import VehicleConfiguration
+    veh = VehicleConfiguration()
+    eng = Engine(device, stream)
+    eng.set_vehicle(veh.length, veh.width, veh.wb_rear_axle, veh.wheelbase, veh.a_max, veh.v_switch, veh.delta_max,
+                    veh.v_delta_max, veh.kappa_max)
+    tb = work["cosy"].device_tables()
+    eng.set_reference(tb["ref_pos"], tb["ref_theta"], tb["ref_curv"], tb["ref_curv_d"], tb["path_xy"], tb["path_s"],
+                      tb["path_normals"], tb["proj_limit"])
+    static, t0, dyn = obstacle_arrays(work["scn"])
+    eng.set_obstacles(static, t0, dyn)
+    return eng
+
+
+def make_inputs(work, want_all_states=False):
+    from commonroad_rp_b200._lib import Engine
+    return Engine.make_inputs(work["x0_lon"], work["x0_lat"], work["x0_orientation"], 0, False, "velocity_keeping",
+                              N_HORIZON, DT, desired_speed=work["desired_speed"], desired_d=0.0, w_a=5.0,
+                              want_all_states=want_all_states)
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_port_rate(work, stride, workers, repeats=1):
+    """The oracle port (reference algorithm restated, oracle/rp_oracle.py) on a sub-grid of the same
+    workload: every ``stride``-th v and d sample.  Returns (candidates/s, description, seconds)."""
+    from oracle import rp_oracle as O
+    from commonroad_rp_b200.utility.config import VehicleConfiguration
+    veh = VehicleConfiguration()
+    tb = work["cosy"].device_tables()
+    prob = {
+        "t": np.array(work["t"]), "lon": np.array(work["lon"][::stride]), "d": np.array(work["d"][::stride]),
+        "x0_lon": np.array(work["x0_lon"]), "x0_lat": np.array(work["x0_lat"]),
+        "x0_orientation": work["x0_orientation"], "x0_time_step": 0, "lon_mode": "velocity_keeping",
+        "low_vel_mode": False, "dt": DT, "N": N_HORIZON, "factor": 1, "draw_all": False,
+        "constraints": O.CONSTRAINTS,
+        "cost": {"kind": "default", "desired_speed": work["desired_speed"], "desired_s": None, "desired_d": 0.0, "w_a": 5},
+        "vehicle": {"length": veh.length, "width": veh.width, "wb_rear_axle": veh.wb_rear_axle,
+                    "wheelbase": veh.wheelbase, "a_max": veh.a_max, "v_switch": veh.v_switch,
+                    "delta_max": veh.delta_max, "v_delta_max": veh.v_delta_max},
+        "ref": {"ref_pos": tb["ref_pos"], "ref_theta": tb["ref_theta"], "ref_curv": tb["ref_curv"],
+                "ref_curv_d": tb["ref_curv_d"]},
+        "ccosy": {"path": tb["path_xy"], "S": tb["path_s"], "normals": tb["path_normals"], "limit": tb["proj_limit"]},
+        "obstacles": {k: work["scn"][k] for k in ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes",
+                                                  "boundary_tris")},
+    }
+    n = len(prob["t"]) * len(prob["lon"]) * len(prob["d"])
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        if workers <= 1:
+            O.plan_grid(prob, want_states=False, full_collision=False)
+        else:
+            O.plan_grid_parallel(prob, workers)
+    dt_s = (time.perf_counter() - t0) / repeats
+    desc = "every %d-th v and d sample of the dense sweep: %d candidates x %d steps per cycle" % (stride, n, N_HORIZON + 1)
+    return n / dt_s, desc, dt_s, n
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python and
+    cannot travel to the GPU box) with all host cores, fork-parallel like reactive_planner.py:1084-1111."""
+    if rank != 0:
+        return
+    work = dense_workload(1)
+    cores = os.cpu_count() or 1
+    stride = 8
+    # calibrate so that steps + warmup stay within a few minutes
+    rate, desc, sec, n = cpu_port_rate(work, 16, cores)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    while stride > 1 and (len(work["t"]) * (64 // (stride // 2)) ** 2) / rate < budget:
+        stride //= 2
+    for _ in range(args.warmup):
+        cpu_port_rate(work, stride, cores)
+    times, n_s = [], 0
+    for _ in range(args.steps):
+        rate, desc, sec, n_s = cpu_port_rate(work, stride, cores)
+        times.append(sec)
+    total = float(np.sum(times))
+    value = n_s * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "dense sampling sweep 64 d x 64 v x 32 t, 60-step horizon (BASELINE configs[3])",
+                   "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cand_timesteps_per_sec": value * (N_HORIZON + 1), "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-states", action="store_true", help="also time the full-state (HBM-heavy) variant")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    work = dense_workload(n_gpus)
+    # a dedicated (non-default) stream shared by torch and the engine, so that torch's CUDA events
+    # bracket exactly the kernels the C-ABI launches
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng = make_engine(work, local_rank, stream.cuda_stream)
+    inputs = make_inputs(work)
+    n_total = work["n_cand"]
+    per_rank = (n_total + world - 1) // world
+    first = rank * per_rank
+    count = max(0, min(per_rank, n_total - first))
+    if world > 1:
+        eng.set_candidate_range(first, count)
+    Np1 = N_HORIZON + 1
+
+    from commonroad_rp_b200.parallel import global_argmin
+    rec = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    def step_device():
+        eng.grid_launch()
+        if world > 1:
+            return global_argmin(eng, rec, world)
+        return None
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    eng.grid_upload(inputs, work["t"], work["lon"], work["d"])
+    fp64_peak = eng.measure_fp64_peak()
+    # clocks are sampled from the warm-up to the end of the e2e loop (the same kernels throughout);
+    # nvidia-smi needs a few hundred ms to start, so keep the GPU under this load until it reports
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if rank == 0:
+        t_wait = time.perf_counter()
+        while len(sampler.rows) < 3 and time.perf_counter() - t_wait < 3.0:
+            step_device()
+            torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                     # L2 flush between timed iterations (outside the event pair)
+        starts[k].record(stream)
+        step_device()
+        stops[k].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    fused_ms = [eng.stage_ms(back)[1] for back in range(min(args.steps, 64))]
+    stage_ms = np.mean([eng.stage_ms(back) for back in range(min(args.steps, 64))], axis=0)
+    total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    res = eng.grid_result()
+
+    # ---- end to end through the host-buffer API ----
+    t_np, lon_np, d_np = np.array(work["t"]), np.array(work["lon"]), np.array(work["d"])
+    for _ in range(2):
+        r = eng.plan_grid(inputs, t_np, lon_np, d_np)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = eng.plan_grid(inputs, t_np, lon_np, d_np)
+        if world > 1:
+            global_argmin(eng, rec, world)
+        if r.winner >= 0:
+            eng.fetch_states(r.winner)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - e2e_t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    clocks = sampler.stop() if rank == 0 else None
+    import ctypes
+    from commonroad_rp_b200 import _lib
+    h2d = 8 * (len(work["t"]) + len(work["lon"]) + len(work["d"])) + 4 * len(work["t"]) + ctypes.sizeof(_lib.PlanInputs)
+    d2h = ctypes.sizeof(_lib.PlanResult) + 4 + 14 * Np1 * 8
+
+    full = None
+    if args.full_states and world == 1:
+        fin = make_inputs(work, want_all_states=True)
+        eng.grid_upload(fin, work["t"], work["lon"], work["d"])
+        for _ in range(3):
+            eng.grid_launch()
+        torch.cuda.synchronize()
+        ms = []
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            eng.grid_launch()
+            torch.cuda.synchronize()
+            ms.append(eng.stage_ms(0)[1])
+        full = float(np.mean(ms))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    value = n_total * args.steps / (total_ms * 1e-3)
+    fused_mean_ms = float(np.mean(fused_ms))
+    cand_steps_launch = count * Np1
+    achieved_tf = cand_steps_launch * FLOP_PER_CAND_STEP / (fused_mean_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "dense sampling sweep 64 d x %d v x 32 t, 60-step horizon (BASELINE configs[3]%s)"
+                               % (64 * n_gpus, "" if n_gpus == 1 else "; v grid scaled with N, bundle sharded t-major, NCCL arg-min"),
+                   "candidates_per_cycle": n_total, "time_steps": Np1, "l2": "flushed between timed iterations (256 MiB fill)",
+                   "mode": "select-only (winner states materialised), fmad off for parity"},
+        "cand_timesteps_per_sec": value * Np1,
+        "p50_cycle_ms": float(np.median(step_ms)),
+        "stage_ms": {"coeff": float(stage_ms[0]), "fused": float(stage_ms[1]), "argmin": float(stage_ms[2]),
+                     "winner_states": float(stage_ms[3])},
+        "winner": int(res.winner), "n_feasible": int(res.n_feasible),
+        "e2e": {"value": n_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "rp_plan_grid + rp_fetch_states (host buffers)"},
+        "gpu_launches": int(eng.launches_per_plan() * args.steps),
+        "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                     "kernel": "rp::fused_kernel<256>", "kernel_ms": fused_mean_ms,
+                     "peak_source": "DFMA micro-benchmark measured in this run (FMA = 2 flop); "
+                                    "algorithmic work = 200 flop per candidate-timestep (SURVEY 8d)",
+                     "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_kind},
+    }
+    if full is not None:
+        gbs = cand_steps_launch * STATE_BYTES_PER_CAND_STEP / (full * 1e-3) / 1e9
+        line["roofline_full_states"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                        "frac": gbs / peaks.get("hbm_gbs"), "traffic": None, "kernel_ms": full,
+                                        "peak_source": peak_kind + " (MEASURED_PEAKS.json)"}
+    if not args.no_cpu_baseline:
+        cores = 1
+        rate, desc, sec, n_s = cpu_port_rate(dense_workload(1), 8, cores)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                                "seconds": sec}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librp_b200.so")
+LIB_PATH = os.environ.get("RP_B200_LIB", os.path.join(_HERE, "librp_b200.so"))   # override: kernel A/B experiments
 
 N_REASONS = 8
 N_STATE_ROWS = 14
@@ -71,12 +71,16 @@ SIGNATURES = {
     "rp_grid_result": (C.c_int, [C.c_void_p, C.POINTER(PlanResult)]),
     "rp_plan_list": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _dp, _ip, _bp, C.POINTER(PlanResult)]),
     "rp_set_candidate_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "rp_export_record_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rp_count_colliders_before_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rp_fetch_states": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "rp_fetch_candidates": (C.c_int, [C.c_void_p, _dp, _ip, _ip, _ip]),
     "rp_fetch_coeffs": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "rp_solve_coeffs": (C.c_int, [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, _dp]),
     "rp_collide_poses": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, C.c_double, C.c_double, _bp]),
     "rp_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "rp_stage_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "rp_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "rp_launches_per_plan": (C.c_int, [C.c_void_p]),
 }
 
@@ -246,6 +250,13 @@ class Engine:
     def set_candidate_range(self, first, count):
         self._check(self._lib.rp_set_candidate_range(self._ctx, int(first), int(count)))
 
+    def export_record_dev(self, dev_ptr):
+        self._check(self._lib.rp_export_record_dev(self._ctx, C.c_void_p(int(dev_ptr))))
+
+    def count_colliders_before_dev(self, dev_winner_ptr, dev_out_ptr):
+        self._check(self._lib.rp_count_colliders_before_dev(self._ctx, C.c_void_p(int(dev_winner_ptr)),
+                                                            C.c_void_p(int(dev_out_ptr))))
+
     def synchronize(self):
         self._check(self._lib.rp_ctx_synchronize(self._ctx))
 
@@ -295,6 +306,16 @@ class Engine:
         ms = (C.c_float * 4)()
         self._check(self._lib.rp_last_stage_ms(self._ctx, ms))
         return [float(v) for v in ms]
+
+    def stage_ms(self, back=0):
+        ms = (C.c_float * 4)()
+        self._check(self._lib.rp_stage_ms(self._ctx, int(back), ms))
+        return [float(v) for v in ms]
+
+    def measure_fp64_peak(self):
+        tf = C.c_double()
+        self._check(self._lib.rp_measure_fp64_peak(self._ctx, C.byref(tf)))
+        return float(tf.value)
 
     def launches_per_plan(self):
         return int(self._lib.rp_launches_per_plan(self._ctx))

@@ -107,8 +107,10 @@ struct rp_ctx {
     PinBuf h_stage, h_result;
     size_t off_t = 0, off_lon = 0, off_d = 0, off_len = 0;
 
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ev_valid = false;
+    static constexpr int kEvRing = 64;
+    cudaEvent_t ev_ring[kEvRing][5] = {};
+    cudaEvent_t* ev = ev_ring[0];       // event set of the launch in flight
+    long long n_launches = 0;
 };
 
 namespace {
@@ -387,7 +389,8 @@ int rp_ctx_create(int device, void* stream, rp_ctx** out) {
     }
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    for (auto& set : ctx->ev_ring)
+        for (auto& e : set) cudaEventCreate(&e);
     if (ctx->d_result.ensure(sizeof(rp::PlanResultDev)) || ctx->h_result.ensure(sizeof(rp::PlanResultDev)) ||
         ctx->d_index.ensure(sizeof(int))) {
         rp_ctx_destroy(ctx);
@@ -408,8 +411,9 @@ int rp_ctx_destroy(rp_ctx* ctx) {
         b->release();
     ctx->h_stage.release();
     ctx->h_result.release();
-    for (auto& e : ctx->ev)
-        if (e) cudaEventDestroy(e);
+    for (auto& set : ctx->ev_ring)
+        for (auto& e : set)
+            if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RP_OK;
@@ -543,6 +547,7 @@ static int launch_plan(rp_ctx* ctx) {
     if (ctx->in.want_all_states) {
         if (int rc = ctx->d_states_all.ensure((size_t)std::max(n, 1) * 14 * Np1 * sizeof(double))) return rc;
     }
+    ctx->ev = ctx->ev_ring[ctx->n_launches % rp_ctx::kEvRing];
     cudaEventRecord(ctx->ev[0], ctx->stream);
     if (ctx->mode == 0 && n > 0) {
         const int n_lon_sys = ctx->n_t * ctx->n_lon;
@@ -586,7 +591,7 @@ static int launch_plan(rp_ctx* ctx) {
         if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one.as<double>())) return rc;
     }
     cudaEventRecord(ctx->ev[4], ctx->stream);
-    ctx->ev_valid = true;
+    ++ctx->n_launches;
     ctx->have_plan = true;
     return RP_OK;
 }
@@ -787,12 +792,84 @@ int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time
     return RP_OK;
 }
 
-int rp_last_stage_ms(rp_ctx* ctx, float* ms4) {
+int rp_stage_ms(rp_ctx* ctx, int back, float* ms4) {
     if (int rc = bind(ctx)) return rc;
     if (!ms4) return fail(RP_ERR_ARG, "null output");
-    if (!ctx->ev_valid) return fail(RP_ERR_STATE, "no plan launched");
-    RP_CUDA(cudaEventSynchronize(ctx->ev[4]));
-    for (int q = 0; q < 4; ++q) RP_CUDA(cudaEventElapsedTime(&ms4[q], ctx->ev[q], ctx->ev[q + 1]));
+    if (back < 0 || back >= rp_ctx::kEvRing || back >= ctx->n_launches) return fail(RP_ERR_STATE, "no such launch in the event ring");
+    cudaEvent_t* ev = ctx->ev_ring[(ctx->n_launches - 1 - back) % rp_ctx::kEvRing];
+    RP_CUDA(cudaEventSynchronize(ev[4]));
+    for (int q = 0; q < 4; ++q) RP_CUDA(cudaEventElapsedTime(&ms4[q], ev[q], ev[q + 1]));
+    return RP_OK;
+}
+
+int rp_last_stage_ms(rp_ctx* ctx, float* ms4) { return rp_stage_ms(ctx, 0, ms4); }
+
+// FP64 pipe peak by a DFMA micro-benchmark (the roofline denominator SURVEY 8d asks to measure)
+namespace {
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+}  // namespace
+
+int rp_measure_fp64_peak(rp_ctx* ctx, double* tflops) {
+    if (int rc = bind(ctx)) return rc;
+    if (!tflops) return fail(RP_ERR_ARG, "null output");
+    DevBuf sink;
+    const int blocks = ctx->num_sms * 8, threads = 256, iters = 20000;
+    if (int rc = sink.ensure((size_t)blocks * threads * sizeof(double))) return rc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(sink.as<double>(), iters, 1.0 + rep);
+        cudaEventRecord(e1, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { sink.release(); return fail(RP_ERR_CUDA, cudaGetErrorString(e)); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    sink.release();
+    *tflops = best;
+    return RP_OK;
+}
+
+int rp_export_record_dev(rp_ctx* ctx, double* dev_dst4) {
+    if (int rc = bind(ctx)) return rc;
+    if (!dev_dst4) return fail(RP_ERR_ARG, "null device pointer");
+    if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
+    rp::export_record_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_result.as<rp::PlanResultDev>(), dev_dst4);
+    RP_CUDA(cudaGetLastError());
+    return RP_OK;
+}
+
+int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double* dev_out1) {
+    if (int rc = bind(ctx)) return rc;
+    if (!dev_winner2 || !dev_out1) return fail(RP_ERR_ARG, "null device pointer");
+    if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
+    const int n = ctx->n_cand;
+    int first = 0, count = n;
+    if (ctx->range_count >= 0) {
+        first = std::min(ctx->range_first, n);
+        count = std::min(ctx->range_count, n - first);
+    }
+    RP_CUDA(cudaMemsetAsync(dev_out1, 0, sizeof(double), ctx->stream));
+    const int blocks = std::max(1, std::min(ctx->num_sms, (count + 255) / 256));
+    rp::count_before_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first,
+                                                              count, dev_winner2, dev_out1);
+    RP_CUDA(cudaGetLastError());
     return RP_OK;
 }
 

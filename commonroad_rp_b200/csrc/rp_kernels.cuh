@@ -125,8 +125,11 @@ __global__ void solve_kernel(int n, const int* __restrict__ kind, const double* 
 // block is persistent over candidate groups so that the reference-path table and the per-step
 // dynamic-obstacle rows are staged into shared memory once.
 // ------------------------------------------------------------------------------------------------
+#ifndef RP_FUSED_MIN_BLOCKS
+#define RP_FUSED_MIN_BLOCKS 2
+#endif
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT) fused_kernel(const __grid_constant__ PlanParams P) {
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? RP_FUSED_MIN_BLOCKS : 1) fused_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
     const int Np1 = P.Np1;
     const int C = P.C;
@@ -611,6 +614,43 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
         for (int z = 0; z < 8; ++z) r.reason_counts[z] = counts[8 + z];
         out->n_filtered = counts[3];
     }
+}
+
+// ---- multi-GPU bundle shards: each rank owns a contiguous tile of the enumeration space --------
+// record = [local best cost (+inf if none), its enumeration index (as double, +inf if none),
+//           kinematically infeasible count, kinematically feasible count]
+__global__ void export_record_kernel(const PlanResultDev* __restrict__ res, double* __restrict__ dst) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const bool has = res->r.winner >= 0;
+    dst[0] = has ? res->r.winner_cost : inf;
+    dst[1] = has ? (double)res->r.winner : inf;
+    dst[2] = (double)res->r.n_infeasible_kinematics;
+    dst[3] = (double)res->r.n_feasible;
+}
+
+// colliders of this shard ranked before the GLOBAL winner (lazy collision count, App. B#12)
+__global__ void __launch_bounds__(256) count_before_kernel(const double* __restrict__ cost, const int* __restrict__ info,
+                                                           int first, int count, const double* __restrict__ winner,
+                                                           double* __restrict__ out) {
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    const double wc = winner[0];
+    const double wi = winner[1];
+    const bool none = !(wi < __longlong_as_double(0x7ff0000000000000LL));
+    int local = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const int k = first + q;
+        if ((info[k] & 0xFF) == ST_COLLISION) {
+            const double c = cost[k];
+            if (none || c < wc || (c == wc && (double)k < wi)) ++local;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&total, local);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(out, (double)total);
 }
 
 // pycrcc.CollisionChecker.collide for a batch of ego boxes (rp_collide_poses)

@@ -169,6 +169,14 @@ int rp_plan_list(rp_ctx* ctx, const rp_plan_inputs* in, int n_cand, const double
  * rp_grid_launch / rp_plan_grid.  count < 0 resets to the whole bundle. */
 int rp_set_candidate_range(rp_ctx* ctx, int first, int count);
 
+/* Multi-GPU arg-min plumbing for sharded bundles (device pointers, asynchronous on the context's stream):
+ * rp_export_record_dev writes [best cost (+inf if none), best enumeration index as double (+inf if none),
+ * n_infeasible_kinematics, n_feasible] of this rank's shard to dev_dst4 for an NCCL all-gather;
+ * rp_count_colliders_before_dev writes to dev_out1 how many of this shard's colliding candidates rank
+ * before the GLOBAL winner dev_winner2 = [cost, index] (lazy collision count, reactive_planner.py:1031-1063). */
+int rp_export_record_dev(rp_ctx* ctx, double* dev_dst4);
+int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double* dev_out1);
+
 /* ---- results of the last plan call ----------------------------------------------------------- */
 /* 14 x (N+1) state rows (rp_state_row order) of candidate idx; available for the winner always,
  * for every candidate when want_all_states was set.  Other indices are re-evaluated on demand. */
@@ -190,6 +198,10 @@ int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time
 
 /* device timing of the last rp_grid_launch stages in milliseconds: [coeff, fused, argmin, winner] */
 int rp_last_stage_ms(rp_ctx* ctx, float* ms4);
+/* the same for the launch `back` launches ago (0 = last; the context keeps the last 64) */
+int rp_stage_ms(rp_ctx* ctx, int back, float* ms4);
+/* measurement aid: FP64 FMA peak of the device in TFLOP/s from a DFMA micro-benchmark (roofline denominator) */
+int rp_measure_fp64_peak(rp_ctx* ctx, double* tflops);
 /* number of kernels rp_grid_launch enqueues (for bench.py's gpu_launches) */
 int rp_launches_per_plan(rp_ctx* ctx);
 

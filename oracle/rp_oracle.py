@@ -544,3 +544,52 @@ def reference_tables(ref_path, smooth=True):
     ref = {"ref_pos": ref_pos, "ref_theta": ref_theta, "ref_curv": ref_curv, "ref_curv_d": ref_curv_d}
     ccosy = {"path": path, "S": cc.pathlength, "normals": cc.normals, "limit": cc.projection_domain_limit}
     return ref, ccosy, cc
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's only parallelism: contiguous candidate chunks checked in forked workers, results
+# pickled back (reactive_planner.py:1084-1111).  Used by bench.py --impl reference.
+# ------------------------------------------------------------------------------------------------
+_PAR = {}
+
+
+def _par_chunk(bounds):
+    lo, hi = bounds
+    cl, ct, dtl, prob = _PAR["cl"], _PAR["ct"], _PAR["dtl"], _PAR["prob"]
+    ccosy = _ccosy_from(prob)
+    out = []
+    for k in range(lo, hi):
+        ok, r, bs, st = check_kinematics_one(cl[k], ct[k], dtl[k], prob, ccosy)
+        out.append((k, ok, r, st if ok else None))
+    return out
+
+
+def plan_grid_parallel(prob, workers):
+    import math as _m
+    import multiprocessing as mp
+    cl, ct, dtl, dtt, behind = enumerate_grid(prob["t"], prob["lon"], prob["d"], prob["x0_lon"], prob["x0_lat"],
+                                              prob["lon_mode"], prob["low_vel_mode"])
+    n = len(dtl)
+    _PAR.update(cl=cl, ct=ct, dtl=dtl, prob=prob)
+    chunk = _m.ceil(n / workers)
+    bounds = [(i * chunk, min(n, (i + 1) * chunk)) for i in range(workers) if i * chunk < n]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(bounds)) as pool:
+        parts = pool.map(_par_chunk, bounds)
+    feasible = {}
+    for part in parts:
+        for k, ok, r, st in part:
+            if ok:
+                feasible[k] = st
+    cost = {k: evaluate_cost(st, prob["cost"]) for k, st in feasible.items()}
+    order = sorted(feasible, key=lambda k: (cost[k], k))
+    checker = build_checker(prob["obstacles"])
+    winner, n_col = -1, 0
+    for k in order:
+        if candidate_collides(feasible[k], prob, checker) >= 0:
+            n_col += 1
+        else:
+            winner = k
+            break
+    return {"n": n, "winner": winner, "n_infeasible_kinematics": n - len(feasible), "n_infeasible_collision": n_col,
+            "winner_cost": cost.get(winner)}
