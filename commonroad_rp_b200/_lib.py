@@ -130,6 +130,7 @@ class Engine:
         self.device = int(device)
         self._N = None
         self._n_cand = 0
+        self.plan_generation = 0      # bumped by every upload; lazy TrajectorySample views check it
 
     def _check(self, rc):
         if rc != 0:
@@ -216,6 +217,7 @@ class Engine:
         self._N = inputs.N
         self._n_cand = t.size * lon.size * d.size
         self._keep = (t, lon, d, tl)
+        self.plan_generation += 1
         return (C.byref(inputs), t.size, _p(t, _dp), _p(tl, _ip), lon.size, _p(lon, _dp), d.size, _p(d, _dp))
 
     def plan_grid(self, inputs, t, lon, d, traj_len=None):
@@ -241,6 +243,7 @@ class Engine:
         sk = np.ascontiguousarray(skip, dtype=np.uint8) if skip is not None else None
         self._N = inputs.N
         self._n_cand = cl.shape[0]
+        self.plan_generation += 1
         res = PlanResult()
         self._check(self._lib.rp_plan_list(self._ctx, C.byref(inputs), cl.shape[0], _p(cl, _dp), _p(ct, _dp),
                                            _p(tl, _ip), _p(sk, _bp) if sk is not None else C.cast(None, _bp),

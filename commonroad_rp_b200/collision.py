@@ -1,0 +1,247 @@
+"""Obstacle containers with the surface of ``commonroad_dc.pycrcc`` that the reference planner uses
+(``reactive_planner.py:28-31, :234-251, :1040-1042``): ``RectOBB, RectAABB, Triangle, ShapeGroup,
+TimeVariantCollisionObject, CollisionChecker``.  They are plain host-side descriptions; the narrow
+phase runs on the device (separating-axis kernels in csrc/rp_device.cuh).  ``CollisionChecker`` packs
+itself into the arrays of ``rp_ctx_set_obstacles``; ``collide()`` answers single queries through
+``rp_collide_poses`` -- there is no host narrow phase.
+
+commonroad_dc is not installable here, so semantics follow SURVEY.md App. D#2 (parity unpinned):
+closed shapes (touching counts as collision), time-variant objects collide only at common time
+indices, static objects at every index.
+"""
+import math
+from typing import List, Optional
+
+import numpy as np
+
+
+class RectOBB:
+    """Oriented box: half extents r_x (along the heading) and r_y, heading, centre."""
+
+    def __init__(self, r_x: float, r_y: float, orientation: float, cx: float, cy: float):
+        self.r_x, self.r_y, self.orientation, self.cx, self.cy = float(r_x), float(r_y), float(orientation), float(cx), float(cy)
+
+    def center(self):
+        return np.array([self.cx, self.cy])
+
+    def row(self):
+        return (self.cx, self.cy, self.orientation, self.r_x, self.r_y)
+
+
+class RectAABB(RectOBB):
+    def __init__(self, r_x: float, r_y: float, cx: float, cy: float):
+        super().__init__(r_x, r_y, 0.0, cx, cy)
+
+
+class Triangle:
+    def __init__(self, x1, y1, x2, y2, x3, y3):
+        self.vertices = (float(x1), float(y1), float(x2), float(y2), float(x3), float(y3))
+
+    def row(self):
+        return self.vertices
+
+
+class ShapeGroup:
+    def __init__(self):
+        self._shapes = []
+
+    def add_shape(self, shape):
+        self._shapes.append(shape)
+
+    def unpack(self):
+        return list(self._shapes)
+
+
+class TimeVariantCollisionObject:
+    """One shape per consecutive time index starting at ``time_start_idx``."""
+
+    def __init__(self, time_start_idx: int):
+        self._t0 = int(time_start_idx)
+        self._shapes = []
+
+    def append_obstacle(self, shape):
+        self._shapes.append(shape)
+
+    def time_start_idx(self) -> int:
+        return self._t0
+
+    def time_end_idx(self) -> int:
+        return self._t0 + len(self._shapes) - 1
+
+    def obstacle_at_time(self, time_idx: int):
+        k = time_idx - self._t0
+        return self._shapes[k] if 0 <= k < len(self._shapes) else None
+
+
+class CollisionChecker:
+    """Set of static shapes, shape groups and time-variant objects."""
+
+    def __init__(self):
+        self._objects = []
+        self._engine = None
+        self._engine_dims = None
+        self._version = 0
+
+    def add_collision_object(self, obj):
+        self._objects.append(obj)
+        self._version += 1
+
+    def obstacles(self):
+        return list(self._objects)
+
+    @property
+    def version(self) -> int:
+        return self._version
+
+    # ---- packing for rp_ctx_set_obstacles ----
+    def device_arrays(self) -> dict:
+        static, tris, dyn_t0, dyn_boxes = [], [], [], []
+
+        def add_static(shape):
+            if isinstance(shape, ShapeGroup):
+                for s in shape.unpack():
+                    add_static(s)
+            elif isinstance(shape, Triangle):
+                tris.append(shape.row())
+            elif isinstance(shape, RectOBB):
+                static.append(shape.row())
+            else:
+                raise TypeError("<CollisionChecker>: unsupported shape %r (only boxes and triangles)" % type(shape))
+
+        for obj in self._objects:
+            if isinstance(obj, TimeVariantCollisionObject):
+                rows = []
+                for k in range(obj.time_start_idx(), obj.time_end_idx() + 1):
+                    sh = obj.obstacle_at_time(k)
+                    if not isinstance(sh, RectOBB):
+                        raise TypeError("<CollisionChecker>: time-variant obstacles must consist of boxes")
+                    rows.append(sh.row())
+                dyn_t0.append(obj.time_start_idx())
+                dyn_boxes.append(np.asarray(rows, dtype=np.float64).reshape(-1, 5))
+            else:
+                add_static(obj)
+        return {"static_obb": np.asarray(static, dtype=np.float64).reshape(-1, 5),
+                "dyn_t0": np.asarray(dyn_t0, dtype=np.int32), "dyn_boxes": dyn_boxes,
+                "tris": np.asarray(tris, dtype=np.float64).reshape(-1, 6)}
+
+    def upload(self, engine, cell_size: float = 0.0):
+        arr = self.device_arrays()
+        engine.set_obstacles(arr["static_obb"], arr["dyn_t0"], arr["dyn_boxes"], arr["tris"], cell_size)
+
+    # ---- pycrcc-style query ----
+    def collide(self, obj) -> bool:
+        """True if any object of the checker intersects ``obj`` (a box or a time-variant object of boxes).
+        Runs on the device."""
+        if isinstance(obj, TimeVariantCollisionObject):
+            times = list(range(obj.time_start_idx(), obj.time_end_idx() + 1))
+            boxes = [obj.obstacle_at_time(k) for k in times]
+            static_query = False
+        elif isinstance(obj, RectOBB):
+            times, boxes, static_query = [0], [obj], True
+        else:
+            raise TypeError("<CollisionChecker.collide>: unsupported query object %r" % type(obj))
+        if not boxes:
+            return False
+        if static_query and any(isinstance(o, TimeVariantCollisionObject) for o in self._objects):
+            raise TypeError("<CollisionChecker.collide>: static query against time-variant obstacles")
+        hl = max(b.r_x for b in boxes)
+        hw = max(b.r_y for b in boxes)
+        if any(b.r_x != hl or b.r_y != hw for b in boxes):
+            return any(self.collide(_single(b, t)) for b, t in zip(boxes, times))
+        eng = self._query_engine(hl, hw)
+        pose = np.array([[b.cx, b.cy, b.orientation] for b in boxes], dtype=np.float64)
+        return bool(eng.collide_poses(pose, np.asarray(times, dtype=np.int32), hl, hw).any())
+
+    def _query_engine(self, hl, hw):
+        from commonroad_rp_b200._device import current_device_and_stream
+        from commonroad_rp_b200._lib import Engine
+        state = (hl, hw, self._version)
+        if self._engine is None:
+            dev, stream = current_device_and_stream()
+            self._engine = Engine(dev, stream)
+        if self._engine_dims != state:
+            # the broad-phase grid is inflated by the query box's circumradius
+            self._engine.set_vehicle(2 * hl, 2 * hw, 0.0, 1.0, 1.0, 1.0, 0.5, 0.5)
+            self.upload(self._engine)
+            self._engine_dims = state
+        return self._engine
+
+
+def _single(box, t):
+    tvo = TimeVariantCollisionObject(t)
+    tvo.append_obstacle(box)
+    return tvo
+
+
+# ---- construction from CommonRoad scenario objects (duck-typed commonroad-io) -----------------------
+def _shape_box(shape, position, orientation):
+    """commonroad.geometry.shape.Rectangle (length, width[, center, orientation]) placed at a state."""
+    length = getattr(shape, "length", None)
+    width = getattr(shape, "width", None)
+    if length is None or width is None:
+        raise TypeError("<create_collision_object>: only rectangular obstacle shapes are supported")
+    off = np.asarray(getattr(shape, "center", (0.0, 0.0)), dtype=np.float64)
+    local_th = float(getattr(shape, "orientation", 0.0))
+    c, s = math.cos(orientation), math.sin(orientation)
+    cx = position[0] + c * off[0] - s * off[1]
+    cy = position[1] + s * off[0] + c * off[1]
+    return RectOBB(0.5 * length, 0.5 * width, orientation + local_th, cx, cy)
+
+
+def create_collision_object(obstacle):
+    """commonroad_dc ... pycrcc_collision_dispatch.create_collision_object for static / dynamic obstacles
+    with rectangular shapes (reference call sites reactive_planner.py:236, :239)."""
+    init = obstacle.initial_state
+    prediction = getattr(obstacle, "prediction", None)
+    if prediction is None:
+        return _shape_box(obstacle.obstacle_shape, init.position, init.orientation)
+    tvo = TimeVariantCollisionObject(int(init.time_step))
+    tvo.append_obstacle(_shape_box(obstacle.obstacle_shape, init.position, init.orientation))
+    states = prediction.trajectory.state_list
+    expected = int(init.time_step) + 1
+    for st in states:
+        if int(st.time_step) != expected:
+            raise ValueError("<create_collision_object>: prediction must cover consecutive time steps")
+        tvo.append_obstacle(_shape_box(obstacle.obstacle_shape, st.position, st.orientation))
+        expected += 1
+    return tvo
+
+
+def create_road_boundary_obstacle(scenario, width: float = 0.1):
+    """Road boundary as thin boxes along every lanelet border that has no adjacent lanelet (the
+    'obb_rectangles' flavour of commonroad_dc.boundary.create_road_boundary_obstacle; reference call
+    site reactive_planner.py:247).  Returns (None, ShapeGroup)."""
+    sg = ShapeGroup()
+    for ll in scenario.lanelet_network.lanelets:
+        for side, adj in (("left_vertices", "adj_left"), ("right_vertices", "adj_right")):
+            if getattr(ll, adj, None) is not None:
+                continue
+            pts = np.asarray(getattr(ll, side), dtype=np.float64)
+            for p, q in zip(pts[:-1], pts[1:]):
+                seg = q - p
+                length = float(np.hypot(seg[0], seg[1]))
+                if length <= 0.0:
+                    continue
+                mid = 0.5 * (p + q)
+                sg.add_shape(RectOBB(0.5 * length, 0.5 * width, math.atan2(seg[1], seg[0]), mid[0], mid[1]))
+    return None, sg
+
+
+def checker_from_arrays(static_boxes=(), dyn_t0=(), dyn_states=(), dyn_lw=(), boundary_boxes=(), boundary_tris=()):
+    """CollisionChecker from a scenario dict of ``utility.synthetic`` (static_boxes rows are
+    cx, cy, theta, LENGTH, WIDTH; boundary_boxes rows carry half extents)."""
+    cc = CollisionChecker()
+    for cx, cy, th, l, w in np.asarray(static_boxes, dtype=np.float64).reshape(-1, 5):
+        cc.add_collision_object(RectOBB(0.5 * l, 0.5 * w, th, cx, cy))
+    for t0, st, lw in zip(dyn_t0, dyn_states, dyn_lw):
+        tvo = TimeVariantCollisionObject(int(t0))
+        for cx, cy, th in np.asarray(st, dtype=np.float64).reshape(-1, 3):
+            tvo.append_obstacle(RectOBB(0.5 * lw[0], 0.5 * lw[1], th, cx, cy))
+        cc.add_collision_object(tvo)
+    sg = ShapeGroup()
+    for cx, cy, th, hl, hw in np.asarray(boundary_boxes, dtype=np.float64).reshape(-1, 5):
+        sg.add_shape(RectOBB(hl, hw, th, cx, cy))
+    for tri in np.asarray(boundary_tris, dtype=np.float64).reshape(-1, 6):
+        sg.add_shape(Triangle(*tri))
+    cc.add_collision_object(sg)
+    return cc

