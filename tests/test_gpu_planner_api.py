@@ -1,0 +1,281 @@
+"""GPU tests of the public Python surface: lazy TrajectorySample views, the generic plug-in paths (custom
+cost function, list-form sampling space), draw mode, stand-alone solves / collision queries, error
+behaviour, and size-independent properties on the full BASELINE-size bundle."""
+import copy
+
+import numpy as np
+import pytest
+
+from commonroad_rp_b200.utility import synthetic
+from oracle import rp_oracle as O
+from oracle import third_party as tp
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _planner(seed=0, N=20, draw=False, s_dot0=15.0, d0=0.3, mode="velocity_keeping"):
+    from commonroad_rp_b200 import collision
+    from commonroad_rp_b200.reactive_planner import ReactivePlanner
+    from commonroad_rp_b200.state import ReactivePlannerState
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    scn = synthetic.make_scenario(seed=seed)
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = N
+    cfg.sampling.longitudinal_mode = mode
+    cfg.debug.draw_traj_set = draw
+    cfg.debug.save_plots = draw
+
+    class _Empty:
+        static_obstacles, dynamic_obstacles = (), ()
+        lanelet_network = type("LN", (), {"lanelets": ()})()
+
+    cfg.update(scenario=_Empty(), planning_problem=None)
+    p = ReactivePlanner(cfg)
+    co = CoordinateSystem(scn["ref_path"])
+    cc = collision.checker_from_arrays(**{k: scn[k] for k in ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw",
+                                                              "boundary_boxes", "boundary_tris")})
+    s0 = float(co.ref_pos[10])
+    j = int(np.argmax(co.ref_pos > s0)) - 1
+    pos = co.convert_to_cartesian_coords(s0, d0)
+    x0 = ReactivePlannerState(time_step=0, position=pos, orientation=float(co.ref_theta[j]), velocity=s_dot0,
+                              acceleration=0.0, yaw_rate=0.0, steering_angle=0.0)
+    p.reset(initial_state_cart=x0, initial_state_curv=([s0, s_dot0, 0.0], [d0, 0.0, 0.0]), collision_checker=cc,
+            coordinate_system=co)
+    p.set_desired_velocity(desired_velocity=s_dot0, current_speed=s_dot0)
+    return p, scn
+
+
+def test_plan_returns_reference_shaped_tuple():
+    p, _ = _planner()
+    out = p.plan()
+    assert out is not None and len(out) == 4
+    cart, curv, lon_list, lat_list = out
+    assert len(cart.state_list) == p.N + 1 == len(curv.state_list) == len(lon_list) == len(lat_list)
+    st = cart.state_list[3]
+    assert st.time_step == 3 and st.position.shape == (2,)
+    assert st.yaw_rate == pytest.approx((cart.state_list[3].orientation - cart.state_list[2].orientation) / p.dt)
+    assert len(p.planning_times) == 1 and p.infeasible_count_kinematics > 0
+    assert set(p.infeasible_reason_dict) == set(p.config.planning.constraints_to_check)
+    # re-planning from the planned state works like run_planner.py:84-86
+    p.reset(initial_state_cart=cart.state_list[1], initial_state_curv=(lon_list[1], lat_list[1]),
+            collision_checker=p.collision_checker, coordinate_system=p.coordinate_system)
+    assert p.plan() is not None
+
+
+def test_custom_cost_function_goes_through_python_evaluate():
+    from commonroad_rp_b200.cost_function import CostFunction, DefaultCostFunction
+    p, _ = _planner(seed=2)
+    base = p.plan(current_sampling_level=2)
+    calls = []
+
+    class Mine(CostFunction):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def evaluate(self, trajectory):
+            calls.append(1)
+            return self.inner.evaluate(trajectory)
+
+    inner = DefaultCostFunction(15.0, desired_d=0.0, desired_s=None)
+    p.set_cost_function(Mine(inner))
+    p.reset(initial_state_cart=p.x_0, initial_state_curv=p.x_0_cl, collision_checker=p.collision_checker,
+            coordinate_system=p.coordinate_system)
+    mine = p.plan(current_sampling_level=2)
+    assert len(calls) > 10
+    a = np.array([s.position for s in base[0].state_list])
+    b = np.array([s.position for s in mine[0].state_list])
+    assert np.allclose(a, b, rtol=0, atol=1e-12)          # same winner as the fused device cost
+
+
+def test_list_form_matches_grid_form():
+    """a custom SamplingSpace (only generate_trajectories_at_level) reaches the GPU through rp_plan_list"""
+    from commonroad_rp_b200.sampling import FixedIntervalSampling, SamplingSpace
+    p, _ = _planner(seed=1)
+    grid = p.plan(current_sampling_level=1)
+    counts = (p.infeasible_count_kinematics, p.infeasible_count_collision)
+    inner = p.sampling_space
+
+    class ListOnly(SamplingSpace):
+        def __init__(self):
+            super().__init__(inner.num_sampling_levels)
+
+        def generate_trajectories_at_level(self, level, x0_lon, x0_lat, mode, low_vel):
+            return inner.generate_trajectories_at_level(level, x0_lon, x0_lat, mode, low_vel)
+
+    p.set_sampling_space(ListOnly())
+    p.reset(initial_state_cart=p.x_0, initial_state_curv=p.x_0_cl, collision_checker=p.collision_checker,
+            coordinate_system=p.coordinate_system)
+    lst = p.plan(current_sampling_level=1)
+    assert (p.infeasible_count_kinematics, p.infeasible_count_collision) == counts
+    a = np.array([[s.position[0], s.position[1], s.velocity] for s in grid[0].state_list])
+    b = np.array([[s.position[0], s.position[1], s.velocity] for s in lst[0].state_list])
+    assert np.array_equal(a, b)
+
+
+def test_draw_mode_stores_all_trajectories_as_views():
+    from commonroad_rp_b200.trajectories import FeasibilityStatus
+    p, _ = _planner(seed=5, draw=True)
+    assert p.plan(current_sampling_level=1) is not None
+    st = p.stored_trajectories
+    assert st is not None and len(st) == p.last_result.n_candidates
+    labels = [t.feasibility_label for t in st]
+    assert FeasibilityStatus.FEASIBLE in labels and FeasibilityStatus.INFEASIBLE_KINEMATIC in labels
+    t_inf = next(t for t in st if t.feasibility_label == FeasibilityStatus.INFEASIBLE_KINEMATIC)
+    assert t_inf.cartesian is not None and len(t_inf.cartesian.x) == p.N + 1           # states kept for plotting
+    snap = copy.deepcopy(st[:5])
+    p.reset(initial_state_cart=p.x_0, initial_state_curv=p.x_0_cl, collision_checker=p.collision_checker,
+            coordinate_system=p.coordinate_system)
+    p.plan(current_sampling_level=1)
+    assert all(s.cartesian is not None for s in snap)                                    # deep copies survive re-planning
+
+
+def test_bundle_views_and_sort():
+    p, _ = _planner(seed=0)
+    x0_lon, x0_lat = p.x_0_cl
+    bundle = p._create_trajectory_bundle(x0_lon, x0_lat, samp_level=1)
+    best = p._get_optimal_trajectory(bundle)
+    assert len(bundle.trajectories) == p.last_result.n_candidates
+    feas = [t for t in bundle.trajectories if t.feasibility_label is not None and t.feasibility_label.value == "feasible"]
+    assert best.cost == min(t.cost for t in feas)
+    assert feas[0].cartesian is not None and feas[0].trajectory_long.coeffs.shape == (6,)
+    bundle.trajectories = feas
+    bundle.sort()
+    assert bundle.min_costs().cost == best.cost and bundle.max_costs().cost >= best.cost
+
+
+def test_standalone_polynomial_solve_kat():
+    """coefficient solve against np.linalg.solve on the reference's own matrices (polynomial_trajectory.py:305-315)"""
+    from commonroad_rp_b200.polynomial_trajectory import QuarticTrajectory, QuinticTrajectory, solve_batch
+    rng = np.random.default_rng(0)
+    n = 500
+    tau = rng.uniform(0.2, 6.0, n)
+    x0 = rng.uniform(-5, 5, (n, 3)) * np.array([10, 3, 1])
+    xd = rng.uniform(-5, 5, (n, 3)) * np.array([10, 3, 0])
+    kind = rng.integers(0, 2, n)
+    got = solve_batch(kind, x0, xd, tau)
+    for q in range(n):
+        want = O.solve_quartic(x0[q, 0], x0[q, 1], x0[q, 2], tau[q], xd[q, 0]) if kind[q] == 0 else \
+            O.solve_quintic(x0[q, 0], x0[q, 1], x0[q, 2], xd[q, 0], xd[q, 1], xd[q, 2], tau[q])
+        assert H.rel_err(want, got[q]) < 1e-9
+    single = QuinticTrajectory(0, 2.0, np.array([0., 1., 0.]), np.array([1., 0., 0.]))
+    assert np.allclose(single.coeffs, [0, 1, 0, -0.25, 0.0625, 0], atol=1e-12)
+    assert np.allclose(QuarticTrajectory(0, 2.0, np.array([0., 1., 0.]), np.array([3., 0.])).coeffs, [0, 1, 0, 0.5, -0.125, 0])
+
+
+def test_collision_queries_match_oracle():
+    from commonroad_rp_b200 import collision
+    scn = synthetic.make_scenario(seed=4)
+    keys = ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes", "boundary_tris")
+    cc = collision.checker_from_arrays(**{k: scn[k] for k in keys})
+    cc.add_collision_object(collision.Triangle(100.0, -30.0, 104.0, -30.0, 102.0, -26.0))
+    ocheck = O.build_checker({k: scn[k] for k in keys})
+    sg = tp.ShapeGroup()
+    sg.add_shape(tp.Triangle(100.0, -30.0, 104.0, -30.0, 102.0, -26.0))
+    ocheck.add_collision_object(sg)
+    rng = np.random.default_rng(1)
+    n_hit = 0
+    for _ in range(300):
+        x = rng.uniform(0, 299)
+        y = 20 * np.sin(x / 40) + rng.uniform(-7, 7)
+        if rng.random() < 0.15:
+            x, y = rng.uniform(98, 106), rng.uniform(-32, -24)
+        th = rng.uniform(-np.pi, np.pi)
+        t = int(rng.integers(0, 120))
+        ego = collision.TimeVariantCollisionObject(t)
+        ego.append_obstacle(collision.RectOBB(2.25, 0.8, th, x, y))
+        oego = tp.TimeVariantCollisionObject(t)
+        oego.append_obstacle(tp.RectOBB(2.25, 0.8, th, x, y))
+        want = ocheck.collide(oego)
+        assert cc.collide(ego) == want
+        n_hit += want
+    assert 20 < n_hit < 280
+
+
+def test_error_behaviour():
+    from commonroad_rp_b200._lib import Engine, RpError
+    eng = Engine(0)
+    with pytest.raises(RpError):
+        eng.grid_launch()                                   # nothing uploaded
+    inputs = Engine.make_inputs([0, 1, 0], [0, 0, 0], 0.0, 0, False, "velocity_keeping", 20, 0.1, desired_speed=1.0)
+    with pytest.raises(RpError):
+        eng.plan_grid(inputs, [1.0], [1.0], [0.0])          # tables missing
+    with pytest.raises(RpError):
+        eng.set_reference([0, 0], [0, 0], [0, 0], [0, 0], np.zeros((2, 2)), [0, 0], np.zeros((2, 2)), 20.0)   # not increasing
+    with pytest.raises(RpError):
+        Engine(99)
+    # empty bundle: not an error, winner -1
+    prob_scn = synthetic.make_scenario(seed=0)
+    tables = O.reference_tables(prob_scn["ref_path"])
+    prob = H.make_problem(prob_scn, [1.0], [10.0], [0.0], [float(tables[0]["ref_pos"][10]), 10.0, 0.0], [0.0, 0, 0], tables=tables)
+    e2 = H.engine_for(prob)
+    res = e2.plan_grid(H.inputs_for(prob), [], [], [])
+    assert res.winner == -1 and res.n_candidates == 0
+    # ragged traj_len / out-of-domain s: candidate leaves the reference path => projection rejection, no crash
+    prob["x0_lon"][0] = float(tables[0]["ref_pos"][-3])
+    res = e2.plan_grid(H.inputs_for(prob), [2.0], [10.0, 15.0], [0.0, 1.0])
+    assert res.winner == -1 and res.n_infeasible_kinematics == 4
+    e2.close()
+    eng.close()
+
+
+# ---- BASELINE-size bundle: size-independent properties ----------------------------------------------------
+def test_full_size_dense_bundle_properties():
+    import bench
+    work = bench.dense_workload(1)
+    eng = bench.make_engine(work, 0, None)
+    inputs = bench.make_inputs(work)
+    res = eng.plan_grid(inputs, work["t"], work["lon"], work["d"])
+    n = work["n_cand"]
+    assert res.n_candidates == n == 131072
+    cost, status, reason, step = eng.fetch_candidates()
+    ws = eng.fetch_states(res.winner)
+    # (1) arg-min property: the winner is the lexicographic minimum over feasible, collision-free candidates
+    ok = status == 0
+    assert ok.any() and res.winner == int(np.flatnonzero(ok)[np.argmin(cost[ok])])     # first minimum = lowest index
+    assert cost[res.winner] == res.winner_cost == cost[ok].min()
+    # (2) counters are consistent with the per-candidate verdicts
+    assert res.n_feasible == int(((status == 0) | (status == 2)).sum())
+    assert res.n_infeasible_kinematics == int((status == 1).sum()) and res.n_collision_total == int((status == 2).sum())
+    assert res.n_infeasible_collision == int(((status == 2) & ((cost < res.winner_cost) | ((cost == res.winner_cost) & (np.arange(n) < res.winner)))).sum())
+    assert sum(res.reason_counts) == res.n_infeasible_kinematics
+    # (3) idempotence: a second evaluation is bit-identical
+    res2 = eng.plan_grid(inputs, work["t"], work["lon"], work["d"])
+    cost2, status2, _, _ = eng.fetch_candidates()
+    assert res2.winner == res.winner and np.array_equal(status, status2) and np.array_equal(cost, cost2, equal_nan=True)
+    # (4) sharding: two t-major shards merge to the same winner / counters
+    recs = []
+    for first, count in ((0, n // 2), (n // 2, n - n // 2)):
+        eng.set_candidate_range(first, count)
+        r = eng.plan_grid(inputs, work["t"], work["lon"], work["d"])
+        recs.append(r)
+    eng.set_candidate_range(0, -1)
+    best = min((r for r in recs if r.winner >= 0), key=lambda r: (r.winner_cost, r.winner))
+    assert best.winner == res.winner and sum(r.n_infeasible_kinematics for r in recs) == res.n_infeasible_kinematics
+    # (5) full-state mode gives the same verdicts and the winner's block equals the select-only one
+    fin = bench.make_inputs(work, want_all_states=True)
+    res3 = eng.plan_grid(fin, work["t"], work["lon"], work["d"])
+    assert res3.winner == res.winner and np.array_equal(eng.fetch_states(res.winner), ws)
+    # (6) a seeded sample of candidates agrees with the oracle (flags exact, states 1e-9)
+    cl, ct, _ = eng.fetch_coeffs()
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(n, 48, replace=False))
+    tb = work["cosy"].device_tables()
+    prob = H.make_problem(work["scn"], work["t"], work["lon"], work["d"], work["x0_lon"], work["x0_lat"], N=60,
+                          x0_orientation=work["x0_orientation"], desired_speed=15.0,
+                          tables=({"ref_pos": tb["ref_pos"], "ref_theta": tb["ref_theta"], "ref_curv": tb["ref_curv"],
+                                   "ref_curv_d": tb["ref_curv_d"]},
+                                  {"path": tb["path_xy"], "S": tb["path_s"], "normals": tb["path_normals"],
+                                   "limit": tb["proj_limit"]}, None))
+    ocl, oct_, odt, _, _ = O.enumerate_grid(prob["t"], prob["lon"], prob["d"], prob["x0_lon"], prob["x0_lat"],
+                                            "velocity_keeping", False)
+    o = O.plan_candidates(ocl[pick], oct_[pick], odt[pick], prob, want_states=True, full_collision=True)
+    assert np.array_equal(o["status"], status[pick])
+    kin = o["status"] != O.ST_KINEMATIC
+    assert H.rel_err(o["cost"][kin], cost[pick][kin]) < 1e-9
+    for q, k in enumerate(pick):
+        if kin[q]:
+            assert H.rel_err(o["states"][q], eng.fetch_states(int(k))) < 1e-9
+    eng.close()
