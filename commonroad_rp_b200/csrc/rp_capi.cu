@@ -71,6 +71,13 @@ struct PinBuf {
     }
 };
 
+// launch geometry of the fused kernel
+struct Geometry {
+    int threads, Cmax, n_groups, n_segs, grid, stage_ref, stage_dyn;
+    size_t smem;
+    bool big;       // needs the 1024-thread instantiation
+};
+
 }  // namespace
 
 struct rp_ctx {
@@ -106,6 +113,18 @@ struct rp_ctx {
     DevBuf d_cost, d_info, d_states_all, d_states_one, d_result, d_index;
     PinBuf h_stage, h_result;
     size_t off_t = 0, off_lon = 0, off_d = 0, off_len = 0;
+
+    // fused-kernel work decomposition (segments of equal traj_len)
+    std::vector<int> h_traj_len;
+    bool segs_dirty = true;
+    long long tables_version = 0;
+    DevBuf d_segs, d_segs_index;
+    PinBuf h_segs, h_segs_index;
+    Geometry main_geom{}, index_geom{};
+    int index_geom_np1 = -1, index_geom_count = -1;
+    long long index_geom_tables = -1;
+    double ref_inv_step = 1.0, ps_inv_step = 1.0;
+    int smem_granted[2] = {0, 0};
 
     static constexpr int kEvRing = 64;
     cudaEvent_t ev_ring[kEvRing][5] = {};
@@ -237,26 +256,34 @@ int build_obstacle_tables(rp_ctx* ctx) {
         O.dyn_box = ctx->d_dyn_box.as<double>();
     }
     ctx->obstacles_dirty = false;
+    ctx->segs_dirty = true;            // shared-memory staging depends on the obstacle counts
+    ++ctx->tables_version;
     return RP_OK;
 }
 
 // ---- launch geometry of the fused kernel ---------------------------------------------------------
-struct Geometry {
-    int threads, C, n_groups, grid, stage_ref, stage_dyn;
-    size_t smem;
-    bool big;       // needs the 1024-thread instantiation
-};
-
-int plan_geometry(rp_ctx* ctx, int Np1, int count, Geometry& G) {
+// Fill C / g_begin of the segments (k ranges and tl given), size shared memory, query occupancy.
+int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G) {
     if (Np1 < 2 || Np1 > 1024) return fail(RP_ERR_ARG, "N + 1 must be in [2, 1024]");
     G.big = Np1 > 256;
-    G.C = G.big ? 1 : std::max(1, 256 / Np1);
-    G.threads = ((G.C * Np1 + 31) / 32) * 32;
-    G.n_groups = (count + G.C - 1) / G.C;
-    const size_t scratch = (size_t)G.C * (9 * Np1 + 14 + 40 + 6) * sizeof(double) +
-                           (size_t)G.C * (Np1 + 4) * sizeof(int) + 16;
+    G.threads = G.big ? ((Np1 + 31) / 32) * 32 : 256;
+    const size_t per_slot = (size_t)(rp::kRows * Np1 + rp::kSlotExtra) * sizeof(double) +
+                            (size_t)(Np1 + rp::F_WORDS) * sizeof(int);
+    const int c_budget = std::max<int>(1, (int)((52 * 1024) / per_slot));
+    G.Cmax = 1;
+    G.n_groups = 0;
+    for (auto& sg : segs) {
+        const int tl = std::max(1, std::min(sg.tl, Np1));
+        sg.tl = tl;
+        sg.C = G.big ? 1 : std::max(1, std::min(c_budget, G.threads / tl));
+        sg.g_begin = G.n_groups;
+        G.n_groups += (std::max(0, sg.k_end - sg.k_begin) + sg.C - 1) / sg.C;
+        G.Cmax = std::max(G.Cmax, sg.C);
+    }
+    G.n_segs = (int)segs.size();
+    const size_t scratch = (size_t)G.Cmax * per_slot + (size_t)G.n_segs * sizeof(rp::Segment) + 64;
     const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
-    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * rp::kBoxStride * sizeof(double);
+    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * rp::kDynFields * sizeof(double);
     const size_t budget = (size_t)ctx->max_smem_optin;
     G.smem = scratch;
     if (G.smem > budget) return fail(RP_ERR_ARG, "horizon too long for shared-memory scratch");
@@ -265,19 +292,21 @@ int plan_geometry(rp_ctx* ctx, int Np1, int count, Geometry& G) {
     G.stage_dyn = (ctx->obs.n_dyn > 0 && dyn_bytes <= 64 * 1024 && G.smem + dyn_bytes <= budget) ? 1 : 0;
     if (G.stage_dyn) G.smem += dyn_bytes;
     int occ = 0;
-    if (G.big) {
-        RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-        RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<1024>, G.threads, G.smem));
-    } else {
-        RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-        RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<256>, G.threads, G.smem));
+    // the attribute is a per-function maximum: only ever raise it (main and index launches share the kernel)
+    int& granted = ctx->smem_granted[G.big ? 1 : 0];
+    if ((int)G.smem > granted) {
+        if (G.big) RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        else RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        granted = (int)G.smem;
     }
+    if (G.big) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<1024>, G.threads, G.smem));
+    else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<256>, G.threads, G.smem));
     if (occ < 1) return fail(RP_ERR_CUDA, "fused kernel does not fit on an SM");
     G.grid = std::max(1, std::min(G.n_groups, occ * ctx->num_sms));
     return RP_OK;
 }
 
-void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G) {
+void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G, const rp::Segment* d_segs) {
     P.in = ctx->in;
     P.lim.a_max = ctx->veh.a_max;
     P.lim.v_switch = ctx->veh.v_switch;
@@ -296,10 +325,14 @@ void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G) {
     P.ref.pos = base; P.ref.theta = base + n; P.ref.curv = base + 2 * n; P.ref.curv_d = base + 3 * n;
     P.ref.px = base + 4 * n; P.ref.py = base + 5 * n; P.ref.nx = base + 6 * n; P.ref.ny = base + 7 * n;
     P.ref.ps = base + 8 * n;
+    P.ref_inv_step = ctx->ref_inv_step;
+    P.ps_inv_step = ctx->ps_inv_step;
     P.obs = ctx->obs;
-    P.C = G.C;
-    P.Np1 = ctx->in.N + 1;
+    P.segs = d_segs;
+    P.n_segs = G.n_segs;
     P.n_groups = G.n_groups;
+    P.Cmax = G.Cmax;
+    P.Np1 = ctx->in.N + 1;
     P.stage_ref = G.stage_ref;
     P.stage_dyn = G.stage_dyn;
     P.mode = ctx->mode;
@@ -326,6 +359,50 @@ int launch_fused(rp_ctx* ctx, const PlanParams& P, const Geometry& G) {
     return RP_OK;
 }
 
+// segment table of the main launch: one segment per sampled t (grid) clipped to the candidate range,
+// or one segment over the list.  Rebuilt (and re-uploaded) only when inputs / range / tables changed.
+int prepare_main_geometry(rp_ctx* ctx, int first, int count) {
+    if (!ctx->segs_dirty) return RP_OK;
+    const int Np1 = ctx->in.N + 1;
+    std::vector<rp::Segment> segs;
+    if (ctx->mode == 0) {
+        const int per_t = ctx->n_lon * ctx->n_d;
+        for (int it = 0; it < ctx->n_t && per_t > 0; ++it) {
+            const int b = std::max(first, it * per_t), e = std::min(first + count, (it + 1) * per_t);
+            if (b < e) segs.push_back(rp::Segment{b, e, ctx->h_traj_len[it], 0, 0});
+        }
+    } else if (count > 0) {
+        segs.push_back(rp::Segment{first, first + count, Np1, 0, 0});
+    }
+    if (segs.empty()) segs.push_back(rp::Segment{0, 0, Np1, 0, 0});
+    if (int rc = plan_geometry(ctx, Np1, segs, ctx->main_geom)) return rc;
+    const size_t bytes = segs.size() * sizeof(rp::Segment);
+    if (int rc = ctx->h_segs.ensure(bytes)) return rc;
+    if (int rc = ctx->d_segs.ensure(bytes)) return rc;
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));        // a previous launch may still read the staging copy
+    std::memcpy(ctx->h_segs.p, segs.data(), bytes);
+    RP_CUDA(cudaMemcpyAsync(ctx->d_segs.p, ctx->h_segs.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->segs_dirty = false;
+    return RP_OK;
+}
+
+int prepare_index_geometry(rp_ctx* ctx, int count) {
+    const int Np1 = ctx->in.N + 1;
+    if (ctx->index_geom_np1 == Np1 && ctx->index_geom_count == count && ctx->index_geom_tables == ctx->tables_version)
+        return RP_OK;
+    std::vector<rp::Segment> segs{rp::Segment{0, count, Np1, 0, 0}};
+    if (int rc = plan_geometry(ctx, Np1, segs, ctx->index_geom)) return rc;
+    if (int rc = ctx->h_segs_index.ensure(sizeof(rp::Segment))) return rc;
+    if (int rc = ctx->d_segs_index.ensure(sizeof(rp::Segment))) return rc;
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(ctx->h_segs_index.p, segs.data(), sizeof(rp::Segment));
+    RP_CUDA(cudaMemcpyAsync(ctx->d_segs_index.p, ctx->h_segs_index.p, sizeof(rp::Segment), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->index_geom_np1 = Np1;
+    ctx->index_geom_count = count;
+    ctx->index_geom_tables = ctx->tables_version;
+    return RP_OK;
+}
+
 int check_ready(rp_ctx* ctx) {
     if (!ctx->have_vehicle) return fail(RP_ERR_STATE, "vehicle parameters not set");
     if (!ctx->have_ref) return fail(RP_ERR_STATE, "reference tables not set");
@@ -345,13 +422,9 @@ int check_inputs(const rp_plan_inputs* in) {
 
 // winner (or arbitrary candidate) state block via an index-mode launch
 int launch_states_for_index(rp_ctx* ctx, const int* d_index, int count, double* d_out) {
-    Geometry G;
-    const int Np1 = ctx->in.N + 1;
-    if (int rc = plan_geometry(ctx, Np1, count, G)) return rc;
+    if (int rc = prepare_index_geometry(ctx, count)) return rc;
     PlanParams P{};
-    fill_common(ctx, P, G);
-    P.first = 0;
-    P.count = count;
+    fill_common(ctx, P, ctx->index_geom, ctx->d_segs_index.as<rp::Segment>());
     P.index = d_index;
     P.cost = nullptr;
     P.info = nullptr;
@@ -360,7 +433,7 @@ int launch_states_for_index(rp_ctx* ctx, const int* d_index, int count, double* 
     P.in.draw_all = 1;          // produce states whatever the verdict was
     P.in.check_collision = 0;
     P.in.cost_kind = RP_COST_NONE;
-    return launch_fused(ctx, P, G);
+    return launch_fused(ctx, P, ctx->index_geom);
 }
 
 }  // namespace
@@ -407,10 +480,12 @@ int rp_ctx_destroy(rp_ctx* ctx) {
     for (DevBuf* b : {&ctx->d_ref, &ctx->d_obb, &ctx->d_tri, &ctx->d_cell_start, &ctx->d_cell_items, &ctx->d_dyn_box,
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all, &ctx->d_states_one,
-                      &ctx->d_result, &ctx->d_index})
+                      &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index})
         b->release();
     ctx->h_stage.release();
     ctx->h_result.release();
+    ctx->h_segs.release();
+    ctx->h_segs_index.release();
     for (auto& set : ctx->ev_ring)
         for (auto& e : set)
             if (e) cudaEventDestroy(e);
@@ -463,6 +538,10 @@ int rp_ctx_set_reference(rp_ctx* ctx, int n, const double* ref_pos, const double
     ctx->ref_n = n;
     ctx->ref_same_s = std::memcmp(ref_pos, path_s, n * sizeof(double)) == 0 ? 1 : 0;
     ctx->ref_limit = proj_limit;
+    ctx->ref_inv_step = (double)(n - 1) / (ref_pos[n - 1] - ref_pos[0]);
+    ctx->ps_inv_step = (double)(n - 1) / (path_s[n - 1] - path_s[0]);
+    ctx->segs_dirty = true;
+    ++ctx->tables_version;
     ctx->have_ref = true;
     return RP_OK;
 }
@@ -495,6 +574,7 @@ int rp_set_candidate_range(rp_ctx* ctx, int first, int count) {
     if (count >= 0 && first < 0) return fail(RP_ERR_ARG, "negative range start");
     ctx->range_first = count < 0 ? 0 : first;
     ctx->range_count = count;
+    ctx->segs_dirty = true;
     return RP_OK;
 }
 
@@ -526,6 +606,8 @@ int rp_grid_upload(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double*
     if (n_d) std::memcpy(hs + ctx->off_d, d, (size_t)n_d * sizeof(double));
     if (n_t) std::memcpy(hs + ctx->off_len, traj_len, (size_t)n_t * sizeof(int));
     if (bytes) RP_CUDA(cudaMemcpyAsync(ctx->d_samples.p, hs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_traj_len.assign(traj_len, traj_len + n_t);
+    ctx->segs_dirty = true;
     ctx->have_inputs = true;
     ctx->have_plan = false;
     return RP_OK;
@@ -567,18 +649,15 @@ static int launch_plan(rp_ctx* ctx) {
     }
     cudaEventRecord(ctx->ev[1], ctx->stream);
     if (count > 0) {
-        Geometry G;
-        if (int rc = plan_geometry(ctx, Np1, count, G)) return rc;
+        if (int rc = prepare_main_geometry(ctx, first, count)) return rc;
         PlanParams P{};
-        fill_common(ctx, P, G);
-        P.first = first;
-        P.count = count;
+        fill_common(ctx, P, ctx->main_geom, ctx->d_segs.as<rp::Segment>());
         P.index = nullptr;
         P.cost = ctx->d_cost.as<double>();
         P.info = ctx->d_info.as<int>();
         P.states = ctx->in.want_all_states ? ctx->d_states_all.as<double>() : nullptr;
         P.states_by_slot = 0;
-        if (int rc = launch_fused(ctx, P, G)) return rc;
+        if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
         ctx->states_all_valid = ctx->in.want_all_states != 0;
     }
     cudaEventRecord(ctx->ev[2], ctx->stream);
@@ -648,6 +727,7 @@ int rp_plan_list(rp_ctx* ctx, const rp_plan_inputs* in, int n_cand, const double
         ctx->d_skip.release();
     }
     RP_CUDA(cudaStreamSynchronize(ctx->stream));       // pageable host buffers are the caller's
+    ctx->segs_dirty = true;
     ctx->have_inputs = true;
     if (int rc = launch_plan(ctx)) return rc;
     return rp_grid_result(ctx, out);
