@@ -118,7 +118,7 @@ struct rp_ctx {
     std::vector<int> h_traj_len;
     bool segs_dirty = true;
     long long tables_version = 0;
-    DevBuf d_segs, d_segs_index;
+    DevBuf d_segs, d_segs_index, d_argmin;
     PinBuf h_segs, h_segs_index;
     Geometry main_geom{}, index_geom{};
     int index_geom_np1 = -1, index_geom_count = -1;
@@ -159,7 +159,11 @@ int build_obstacle_tables(rp_ctx* ctx) {
         const double c = std::cos(s[2]), sn = std::sin(s[2]);
         double* o = &obb[(size_t)q * rp::kBoxStride];
         o[0] = s[0]; o[1] = s[1]; o[2] = c; o[3] = sn; o[4] = s[3]; o[5] = s[4];
-        o[6] = std::sqrt(s[3] * s[3] + s[4] * s[4]); o[7] = 1.0;
+        o[6] = std::sqrt(s[3] * s[3] + s[4] * s[4]);
+        {
+            const double rr = (r_ego + o[6]) * 1.000000001 + 1e-9;     // same formula as rp::reach2
+            o[7] = rr * rr;
+        }
         const double ex = std::fabs(c) * s[3] + std::fabs(sn) * s[4];
         const double ey = std::fabs(sn) * s[3] + std::fabs(c) * s[4];
         lo_x[q] = s[0] - ex - infl; hi_x[q] = s[0] + ex + infl;
@@ -480,7 +484,7 @@ int rp_ctx_destroy(rp_ctx* ctx) {
     for (DevBuf* b : {&ctx->d_ref, &ctx->d_obb, &ctx->d_tri, &ctx->d_cell_start, &ctx->d_cell_items, &ctx->d_dyn_box,
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all, &ctx->d_states_one,
-                      &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index})
+                      &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin})
         b->release();
     ctx->h_stage.release();
     ctx->h_result.release();
@@ -662,7 +666,15 @@ static int launch_plan(rp_ctx* ctx) {
     }
     cudaEventRecord(ctx->ev[2], ctx->stream);
     rp::PlanResultDev* dres = ctx->d_result.as<rp::PlanResultDev>();
-    rp::finalize_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, n, dres);
+    {
+        if (int rc = ctx->d_argmin.ensure(sizeof(rp::ArgminScratch))) return rc;
+        rp::ArgminScratch* sc = ctx->d_argmin.as<rp::ArgminScratch>();
+        RP_CUDA(cudaMemsetAsync(sc, 0, sizeof(int) * 16, ctx->stream));
+        const int nb = std::max(1, std::min(512, std::min(2 * ctx->num_sms, (count + 255) / 256)));
+        rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc);
+        rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres);
+        rp::count_before_result_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, dres);
+    }
     RP_CUDA(cudaGetLastError());
     cudaEventRecord(ctx->ev[3], ctx->stream);
     // winner's 14 x (N+1) state block; the winner index never leaves the device
@@ -955,7 +967,7 @@ int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double
 
 int rp_launches_per_plan(rp_ctx* ctx) {
     if (!ctx) return 0;
-    return ctx->mode == 0 ? 4 : 3;
+    return ctx->mode == 0 ? 6 : 5;     // coeff, fused, argmin partial / merge / count, winner states
 }
 
 }  // extern "C"

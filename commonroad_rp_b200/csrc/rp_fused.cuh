@@ -248,9 +248,9 @@ fused_kernel(const __grid_constant__ PlanParams P) {
         bool carry = false;
         if (act) {
             if (!low_vel) {
-                if (sv > 0.001) dp = dv / sv; else dp = 0.;
+                if (sv > 0.001) dp = ddiv(dv, sv); else dp = 0.;
                 const double ddot = da - dp * sa;
-                if (sv > 0.001) dpp = ddot / (sv * sv); else dpp = 0.;
+                if (sv > 0.001) dpp = ddiv(ddot, sv * sv); else dpp = 0.;
             } else {
                 dp = dv;
                 dpp = da;
@@ -260,7 +260,7 @@ fused_kernel(const __grid_constant__ PlanParams P) {
             j0 = wrap ? R.n - 1 : ub - 1;
             j1 = wrap ? 0 : ub;
             const double p0 = R.pos[j0], p1 = R.pos[j1];
-            lam = (s - p0) / (p1 - p0);
+            lam = ddiv(s - p0, p1 - p0);
             th_ref = interpolate_angle(s, p0, p1, R.theta[j0], R.theta[j1]);
             carry = !(sv > 0.001) && !low_vel;
             if (!carry) {
@@ -299,11 +299,11 @@ fused_kernel(const __grid_constant__ PlanParams P) {
                 cosT = cos(th_cl);
                 tanT = tan(th_cl);
             }
-            const double q = cosT / oneKrD;
+            const double q = ddiv(cosT, oneKrD);
             kappa = (dpp + (k_r * dp + k_r_d * d) * tanT) * cosT * (q * q) + q * k_r;
-            v = sv * (oneKrD / cosT);
-            a = sa * oneKrD / cosT + ((sv * sv) / cosT) * (oneKrD * tanT * (kappa * oneKrD / cosT - k_r) -
-                                                            (k_r_d * d + k_r * dp));
+            v = sv * ddiv(oneKrD, cosT);
+            a = ddiv(sa * oneKrD, cosT) + ddiv(sv * sv, cosT) * (oneKrD * tanT * (ddiv(kappa * oneKrD, cosT) - k_r) -
+                                                                (k_r_d * d + k_r * dp));
             s_kap[i] = kappa;
         }
         __syncthreads();                                                            // theta/kappa rows complete

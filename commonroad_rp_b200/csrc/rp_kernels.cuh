@@ -89,71 +89,60 @@ __global__ void solve_kernel(int n, const int* __restrict__ kind, const double* 
 
 // ------------------------------------------------------------------------------------------------
 // a12/a14: arg-min over feasible, collision-free candidates on (cost, enumeration index) -- the
-// element a stable ascending sort puts first -- then the counters of the cycle.  One block.
+// element a stable ascending sort puts first -- then the counters of the cycle.  Three small launches:
+// per-block partial minima + winner-independent counters, a one-block merge, and the count of colliders
+// ranked before the winner (what the reference's lazy collision pass counts, App. B#12).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool lex_less(double c1, int i1, double c2, int i2) {
     return (c1 < c2) || (c1 == c2 && i1 < i2);
 }
 
-__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ cost, const int* __restrict__ info,
-                                                        int first, int count, int n_cand, PlanResultDev* out) {
-    __shared__ double w_cost[32];
-    __shared__ int w_idx[32];
-    __shared__ int counts[16];
-    __shared__ double best_cost_s;
-    __shared__ int best_idx_s;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    if (tid < 16) counts[tid] = 0;
+struct ArgminPartial {
+    double cost;
+    int idx;
+    int pad;
+};
 
-    double bc = __longlong_as_double(0x7ff0000000000000LL);       // +inf
-    int bi = 0x7fffffff;
-    for (int q = tid; q < count; q += blockDim.x) {
-        const int k = first + q;
-        if ((info[k] & 0xFF) == ST_FEASIBLE) {
-            const double cc = cost[k];
-            if (lex_less(cc, k, bc, bi)) { bc = cc; bi = k; }
-        }
-    }
+struct ArgminScratch {
+    int counts[16];        // [0] feasible(kin), [2] colliders total, [3] filtered, [8..15] reasons
+    ArgminPartial part[512];
+};
+
+__device__ __forceinline__ void warp_lexmin(double& bc, int& bi) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const double oc = __shfl_down_sync(0xffffffffu, bc, off);
         const int oi = __shfl_down_sync(0xffffffffu, bi, off);
         if (lex_less(oc, oi, bc, bi)) { bc = oc; bi = oi; }
     }
-    if (lane == 0) { w_cost[warp] = bc; w_idx[warp] = bi; }
-    __syncthreads();
-    if (warp == 0) {
-        const int nw = (blockDim.x + 31) >> 5;
-        bc = lane < nw ? w_cost[lane] : __longlong_as_double(0x7ff0000000000000LL);
-        bi = lane < nw ? w_idx[lane] : 0x7fffffff;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double oc = __shfl_down_sync(0xffffffffu, bc, off);
-            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-            if (lex_less(oc, oi, bc, bi)) { bc = oc; bi = oi; }
-        }
-        if (lane == 0) { best_cost_s = bc; best_idx_s = bi; }
-    }
-    __syncthreads();
-    const double wc = best_cost_s;
-    const int wi = best_idx_s;
-    const bool has_winner = wi != 0x7fffffff;
+}
 
-    // counters: [0] feasible(kin), [1] colliders before winner, [2] colliders total, [3] filtered, [8..15] reasons
-    int l_feas = 0, l_colb = 0, l_colt = 0, l_filt = 0;
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) argmin_partial_kernel(const double* __restrict__ cost, const int* __restrict__ info,
+                                                             int first, int count, ArgminScratch* sc) {
+    __shared__ double w_cost[8];
+    __shared__ int w_idx[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double bc = __longlong_as_double(0x7ff0000000000000LL);       // +inf
+    int bi = 0x7fffffff;
+    int l_feas = 0, l_colt = 0, l_filt = 0;
     int l_reason[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int q = tid; q < count; q += blockDim.x) {
+    for (int q = blockIdx.x * blockDim.x + tid; q < count; q += gridDim.x * blockDim.x) {
         const int k = first + q;
         const int w = info[k];
         const int st = w & 0xFF;
         if (st == ST_FEASIBLE) {
             ++l_feas;
+            const double cc = cost[k];
+            if (lex_less(cc, k, bc, bi)) { bc = cc; bi = k; }
         } else if (st == ST_COLLISION) {
             ++l_feas;
             ++l_colt;
-            // lazy check visits candidates in (cost, index) order up to the winner (App. B#12)
-            if (!has_winner || lex_less(cost[k], k, wc, wi)) ++l_colb;
         } else if (st == ST_KINEMATIC) {
             const int r = (w >> 8) & 0x7;
 #pragma unroll
@@ -162,33 +151,75 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
             ++l_filt;
         }
     }
-    auto wsum = [](int v) {
+    warp_lexmin(bc, bi);
+    if (lane == 0) { w_cost[warp] = bc; w_idx[warp] = bi; }
+    l_feas = warp_sum(l_feas); l_colt = warp_sum(l_colt); l_filt = warp_sum(l_filt);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-        return v;
-    };
-    l_feas = wsum(l_feas); l_colb = wsum(l_colb); l_colt = wsum(l_colt); l_filt = wsum(l_filt);
-#pragma unroll
-    for (int z = 0; z < 8; ++z) l_reason[z] = wsum(l_reason[z]);
+    for (int z = 0; z < 8; ++z) l_reason[z] = warp_sum(l_reason[z]);
     if (lane == 0) {
-        atomicAdd(&counts[0], l_feas); atomicAdd(&counts[1], l_colb); atomicAdd(&counts[2], l_colt);
-        atomicAdd(&counts[3], l_filt);
+        if (l_feas) atomicAdd(&sc->counts[0], l_feas);
+        if (l_colt) atomicAdd(&sc->counts[2], l_colt);
+        if (l_filt) atomicAdd(&sc->counts[3], l_filt);
 #pragma unroll
-        for (int z = 0; z < 8; ++z) atomicAdd(&counts[8 + z], l_reason[z]);
+        for (int z = 0; z < 8; ++z)
+            if (l_reason[z]) atomicAdd(&sc->counts[8 + z], l_reason[z]);
     }
     __syncthreads();
-    if (tid == 0) {
-        rp_plan_result& r = out->r;
-        r.winner = has_winner ? wi : -1;
-        r.winner_cost = has_winner ? wc : __longlong_as_double(0x7ff8000000000000LL);
-        r.n_candidates = count;
-        r.n_feasible = counts[0];
-        r.n_infeasible_kinematics = count - counts[3] - counts[0];
-        r.n_infeasible_collision = counts[1];
-        r.n_collision_total = counts[2];
-        for (int z = 0; z < 8; ++z) r.reason_counts[z] = counts[8 + z];
-        out->n_filtered = counts[3];
+    if (warp == 0) {
+        bc = lane < 8 ? w_cost[lane] : __longlong_as_double(0x7ff0000000000000LL);
+        bi = lane < 8 ? w_idx[lane] : 0x7fffffff;
+        warp_lexmin(bc, bi);
+        if (lane == 0) { sc->part[blockIdx.x].cost = bc; sc->part[blockIdx.x].idx = bi; }
     }
+}
+
+__global__ void __launch_bounds__(512) argmin_merge_kernel(const ArgminScratch* __restrict__ sc, int n_part, int count,
+                                                           PlanResultDev* out) {
+    __shared__ double w_cost[16];
+    __shared__ int w_idx[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double bc = tid < n_part ? sc->part[tid].cost : __longlong_as_double(0x7ff0000000000000LL);
+    int bi = tid < n_part ? sc->part[tid].idx : 0x7fffffff;
+    warp_lexmin(bc, bi);
+    if (lane == 0) { w_cost[warp] = bc; w_idx[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        bc = lane < 16 ? w_cost[lane] : __longlong_as_double(0x7ff0000000000000LL);
+        bi = lane < 16 ? w_idx[lane] : 0x7fffffff;
+        warp_lexmin(bc, bi);
+        if (lane == 0) {
+            const bool has_winner = bi != 0x7fffffff;
+            rp_plan_result& r = out->r;
+            r.winner = has_winner ? bi : -1;
+            r.winner_cost = has_winner ? bc : __longlong_as_double(0x7ff8000000000000LL);
+            r.n_candidates = count;
+            r.n_feasible = sc->counts[0];
+            r.n_infeasible_kinematics = count - sc->counts[3] - sc->counts[0];
+            r.n_infeasible_collision = 0;              // filled by count_before_result_kernel
+            r.n_collision_total = sc->counts[2];
+            for (int z = 0; z < 8; ++z) r.reason_counts[z] = sc->counts[8 + z];
+            out->n_filtered = sc->counts[3];
+        }
+    }
+}
+
+// colliders ranked before the winner (all colliders when there is no winner)
+__global__ void __launch_bounds__(256) count_before_result_kernel(const double* __restrict__ cost,
+                                                                  const int* __restrict__ info, int first, int count,
+                                                                  PlanResultDev* out) {
+    if (out->r.n_collision_total == 0) return;
+    const int wi = out->r.winner;
+    const double wc = out->r.winner_cost;
+    const bool none = wi < 0;
+    int local = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const int k = first + q;
+        if ((info[k] & 0xFF) == ST_COLLISION) {
+            if (none || lex_less(cost[k], k, wc, wi)) ++local;
+        }
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&out->r.n_infeasible_collision, local);
 }
 
 // ---- multi-GPU bundle shards: each rank owns a contiguous tile of the enumeration space --------
