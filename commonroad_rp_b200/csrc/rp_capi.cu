@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -270,10 +271,27 @@ int build_obstacle_tables(rp_ctx* ctx) {
 int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G) {
     if (Np1 < 2 || Np1 > 1024) return fail(RP_ERR_ARG, "N + 1 must be in [2, 1024]");
     G.big = Np1 > 256;
+    static const int env_threads = std::getenv("RP_THREADS") ? std::atoi(std::getenv("RP_THREADS")) : 0;
+    static const int env_stage_ref = std::getenv("RP_STAGE_REF") ? std::atoi(std::getenv("RP_STAGE_REF")) : 1;
+    static const int env_stage_dyn = std::getenv("RP_STAGE_DYN") ? std::atoi(std::getenv("RP_STAGE_DYN")) : 1;
+    static const int env_scratch_kb = std::getenv("RP_SCRATCH_KB") ? std::atoi(std::getenv("RP_SCRATCH_KB")) : 48;
     G.threads = G.big ? ((Np1 + 31) / 32) * 32 : 256;
+    if (!G.big && env_threads >= 32 && env_threads <= 256 && env_threads >= Np1) G.threads = (env_threads / 32) * 32;
     const size_t per_slot = (size_t)(rp::kRows * Np1 + rp::kSlotExtra) * sizeof(double) +
                             (size_t)(Np1 + rp::F_WORDS) * sizeof(int);
-    const int c_budget = std::max<int>(1, (int)((52 * 1024) / per_slot));
+    // Shared-memory policy (measured on B200, profiles/README.md): three resident blocks per SM beat two,
+    // so a block may use ~1/3 of the SM's shared memory.  Priority: the per-step dynamic-obstacle rows
+    // (bank-conflict-free staging is worth 35 %), then per-slot scratch (lane utilisation for short
+    // trajectories), then the reference tables (no measurable gain over L1-resident global reads).
+    const size_t budget = (size_t)ctx->max_smem_optin;
+    const size_t target = std::min<size_t>(budget, G.big ? budget : (size_t)74 * 1024);
+    const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
+    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * rp::kDynFields * sizeof(double);
+    const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 64;
+    G.stage_dyn = (env_stage_dyn && ctx->obs.n_dyn > 0 && dyn_bytes <= 32 * 1024 && fixed + per_slot + dyn_bytes <= target) ? 1 : 0;
+    const size_t avail = target - fixed - (G.stage_dyn ? dyn_bytes : 0);
+    const size_t scratch_cap = std::min<size_t>(avail, (size_t)env_scratch_kb * 1024);
+    const int c_budget = std::max<int>(1, (int)(scratch_cap / per_slot));
     G.Cmax = 1;
     G.n_groups = 0;
     for (auto& sg : segs) {
@@ -285,16 +303,10 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
         G.Cmax = std::max(G.Cmax, sg.C);
     }
     G.n_segs = (int)segs.size();
-    const size_t scratch = (size_t)G.Cmax * per_slot + (size_t)G.n_segs * sizeof(rp::Segment) + 64;
-    const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
-    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * rp::kDynFields * sizeof(double);
-    const size_t budget = (size_t)ctx->max_smem_optin;
-    G.smem = scratch;
+    G.smem = (size_t)G.Cmax * per_slot + fixed + (G.stage_dyn ? dyn_bytes : 0);
     if (G.smem > budget) return fail(RP_ERR_ARG, "horizon too long for shared-memory scratch");
-    G.stage_ref = (ref_bytes <= 72 * 1024 && G.smem + ref_bytes <= budget) ? 1 : 0;
+    G.stage_ref = (env_stage_ref && G.smem + ref_bytes <= target) ? 1 : 0;
     if (G.stage_ref) G.smem += ref_bytes;
-    G.stage_dyn = (ctx->obs.n_dyn > 0 && dyn_bytes <= 64 * 1024 && G.smem + dyn_bytes <= budget) ? 1 : 0;
-    if (G.stage_dyn) G.smem += dyn_bytes;
     int occ = 0;
     // the attribute is a per-function maximum: only ever raise it (main and index launches share the kernel)
     int& granted = ctx->smem_granted[G.big ? 1 : 0];

@@ -78,7 +78,7 @@ constexpr int kRows = 11;         // th, kap, x, y, tx, ty, ct0..ct4
 constexpr int kSlotExtra = 16 + 40 + 5 + 5 + 2;
 
 #ifndef RP_FUSED_MIN_BLOCKS
-#define RP_FUSED_MIN_BLOCKS 2
+#define RP_FUSED_MIN_BLOCKS 3
 #endif
 
 template <int MAXT>
@@ -121,7 +121,6 @@ fused_kernel(const __grid_constant__ PlanParams P) {
             row[0] = present ? b[0] : 1.0e300;               // absent: parked far away, the circle reject drops it
             row[Np1] = present ? b[1] : 1.0e300;
             row[2 * Np1] = present ? reach2(P.r_ego, b[6]) : 0.0;
-            row[3 * Np1] = b[2]; row[4 * Np1] = b[3]; row[5 * Np1] = b[4]; row[6 * Np1] = b[5];
         }
         dyn_stage = dst;
         sp += (size_t)total * kDynFields;
@@ -142,6 +141,9 @@ fused_kernel(const __grid_constant__ PlanParams P) {
     const bool fs = in.cost_kind == RP_COST_FAILSAFE;
     const double w_a = fs ? 1.0 : in.w_a;
     const double des_d = fs ? 0.0 : in.desired_d;
+    // element-strided loops over (slot, step) pairs advance without integer division
+    const int e_c0 = tid / Np1, e_i0 = tid - e_c0 * Np1;
+    const int e_dc = T / Np1, e_di = T - e_dc * Np1;
     __syncthreads();
 
     for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
@@ -363,8 +365,8 @@ fused_kernel(const __grid_constant__ PlanParams P) {
 
         // ---- horizon extension (trajectories.py:168-197, :302-332), element-strided over the tails ----
         const int n_elem = C * Np1;
-        for (int e = tid; e < n_elem; e += T) {
-            const int c2 = e / Np1, i2 = e - c2 * Np1;
+        for (int e = tid, c2 = e_c0, i2 = e_i0; e < n_elem; e += T, c2 += e_dc, i2 += e_di) {
+            if (i2 >= Np1) { i2 -= Np1; ++c2; }
             const unsigned* fl = s_flags_all + (size_t)c2 * F_WORDS;
             const int tl2 = (int)fl[F_TL];
             if (!(fl[F_STATE] & S_KEEP) || i2 < tl2) continue;
@@ -377,8 +379,8 @@ fused_kernel(const __grid_constant__ PlanParams P) {
             sc[5 * Np1 + i2] = dt * v_tmp * last[15];
         }
         __syncthreads();
-        for (int e = tid; e < n_elem; e += T) {
-            const int c2 = e / Np1, i2 = e - c2 * Np1;
+        for (int e = tid, c2 = e_c0, i2 = e_i0; e < n_elem; e += T, c2 += e_dc, i2 += e_di) {
+            if (i2 >= Np1) { i2 -= Np1; ++c2; }
             const unsigned* fl = s_flags_all + (size_t)c2 * F_WORDS;
             const int tl2 = (int)fl[F_TL];
             const unsigned st2 = fl[F_STATE];
@@ -460,8 +462,8 @@ fused_kernel(const __grid_constant__ PlanParams P) {
 
         // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), element-strided ----------------
         if (in.check_collision) {
-            for (int e = tid; e < n_elem; e += T) {
-                const int c2 = e / Np1, i2 = e - c2 * Np1;
+            for (int e = tid, c2 = e_c0, i2 = e_i0; e < n_elem; e += T, c2 += e_dc, i2 += e_di) {
+                if (i2 >= Np1) { i2 -= Np1; ++c2; }
                 unsigned* fl = s_flags_all + (size_t)c2 * F_WORDS;
                 if (!(fl[F_STATE] & S_KINOK)) continue;
                 const double* sc = slots + (size_t)c2 * per_slot;
@@ -471,7 +473,7 @@ fused_kernel(const __grid_constant__ PlanParams P) {
                 const double ecx = sc[2 * Np1 + i2] + P.wb_rear * ct;
                 const double ecy = sc[3 * Np1 + i2] + P.wb_rear * st;
                 const int tidx = in.x0_time_step + i2 * in.factor;
-                const bool hit = (dyn_stage ? dyn_collides_staged(dyn_stage, O.n_dyn, Np1, i2, ecx, ecy, ct, st, P.half_len, P.half_wid)
+                const bool hit = (dyn_stage ? dyn_collides_staged(O, dyn_stage, Np1, i2, tidx, ecx, ecy, ct, st, P.half_len, P.half_wid)
                                             : dyn_collides_global(O, tidx, ecx, ecy, ct, st, P.half_len, P.half_wid, P.r_ego)) ||
                                  static_collides(O, ecx, ecy, ct, st, P.half_len, P.half_wid);
                 if (hit)
