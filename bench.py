@@ -89,11 +89,11 @@ def make_engine(work, device, stream):
     return eng
 
 
-def make_inputs(work, want_all_states=False):
+def make_inputs(work, want_all_states=False, check_collision=1):
     from commonroad_rp_b200._lib import Engine
     return Engine.make_inputs(work["x0_lon"], work["x0_lat"], work["x0_orientation"], 0, False, "velocity_keeping",
                               N_HORIZON, DT, desired_speed=work["desired_speed"], desired_d=0.0, w_a=5.0,
-                              want_all_states=want_all_states)
+                              want_all_states=want_all_states, check_collision=check_collision)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -358,6 +358,27 @@ def main():
             ms.append(eng.stage_ms(0)[1])
         full = float(np.mean(ms))
 
+    # lazy collision pass (the reference's own semantics, reactive_planner.py:1031-1063): same winner and
+    # counters, candidates costlier than the best collision-free one so far are not visited
+    lazy_ms = None
+    if world == 1:
+        lin = make_inputs(work, check_collision=2)
+        eng.grid_upload(lin, work["t"], work["lon"], work["d"])
+        for _ in range(3):
+            eng.grid_launch()
+        torch.cuda.synchronize()
+        l0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        l1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            l0[k].record(stream)
+            eng.grid_launch()
+            l1[k].record(stream)
+        torch.cuda.synchronize()
+        lazy_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(l0, l1)]))
+        lazy_res = eng.grid_result()
+        assert lazy_res.winner == res.winner and lazy_res.n_infeasible_collision == res.n_infeasible_collision
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -393,6 +414,9 @@ def main():
                                     "algorithmic work = 200 flop per candidate-timestep (SURVEY 8d)",
                      "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_kind},
     }
+    if lazy_ms is not None:
+        line["lazy_collision"] = {"value": n_total / (lazy_ms * 1e-3), "unit": UNIT, "ms_per_step": lazy_ms,
+                                  "note": "check_collision=2: same winner / counters, costlier candidates not visited"}
     if full is not None:
         gbs = cand_steps_launch * STATE_BYTES_PER_CAND_STEP / (full * 1e-3) / 1e9
         line["roofline_full_states"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",

@@ -17,7 +17,8 @@ STATE_ROWS = ("x", "y", "theta", "v", "a", "kappa", "kappa_dot",
               "s", "d", "theta_cl", "s_dot", "s_ddot", "d_dot", "d_ddot")
 REASON_NAMES = ("none", "velocity", "acceleration", "kappa", "kappa_dot", "yaw_rate", "projection", "ref_range")
 CONSTRAINT_BITS = {"velocity": 1, "acceleration": 2, "kappa": 4, "kappa_dot": 8, "yaw_rate": 16}
-ST_FEASIBLE, ST_KINEMATIC, ST_COLLISION, ST_FILTERED = 0, 1, 2, 3
+ST_FEASIBLE, ST_KINEMATIC, ST_COLLISION, ST_FILTERED, ST_UNCHECKED = 0, 1, 2, 3, 4
+COLLISION_OFF, COLLISION_ALL, COLLISION_LAZY = 0, 1, 2
 VELOCITY_KEEPING, STOPPING = 0, 1
 COST_DEFAULT, COST_FAILSAFE, COST_NONE = 0, 1, 2
 
@@ -204,7 +205,7 @@ class Engine:
         pi.desired_d = float(desired_d)
         pi.w_a = float(w_a)
         pi.want_all_states = int(bool(want_all_states))
-        pi.check_collision = int(bool(check_collision))
+        pi.check_collision = int(check_collision) if not isinstance(check_collision, bool) else int(check_collision)
         return pi
 
     def _grid_args(self, inputs, t, lon, d, traj_len):

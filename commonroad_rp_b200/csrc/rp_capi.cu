@@ -119,7 +119,7 @@ struct rp_ctx {
     std::vector<int> h_traj_len;
     bool segs_dirty = true;
     long long tables_version = 0;
-    DevBuf d_segs, d_segs_index, d_argmin;
+    DevBuf d_segs, d_segs_index, d_argmin, d_best;
     PinBuf h_segs, h_segs_index;
     Geometry main_geom{}, index_geom{};
     int index_geom_np1 = -1, index_geom_count = -1;
@@ -496,7 +496,7 @@ int rp_ctx_destroy(rp_ctx* ctx) {
     for (DevBuf* b : {&ctx->d_ref, &ctx->d_obb, &ctx->d_tri, &ctx->d_cell_start, &ctx->d_cell_items, &ctx->d_dyn_box,
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all, &ctx->d_states_one,
-                      &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin})
+                      &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best})
         b->release();
     ctx->h_stage.release();
     ctx->h_result.release();
@@ -673,6 +673,11 @@ static int launch_plan(rp_ctx* ctx) {
         P.info = ctx->d_info.as<int>();
         P.states = ctx->in.want_all_states ? ctx->d_states_all.as<double>() : nullptr;
         P.states_by_slot = 0;
+        if (ctx->in.check_collision == 2) {
+            if (int rc = ctx->d_best.ensure(sizeof(unsigned long long))) return rc;
+            RP_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, sizeof(unsigned long long), ctx->stream));   // ~1.4e306
+            P.best_bits = ctx->d_best.as<unsigned long long>();
+        }
         if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
         ctx->states_all_valid = ctx->in.want_all_states != 0;
     }

@@ -50,6 +50,7 @@ struct PlanParams {
     int* info;                   // [n_cand]   status | reason << 8 | (step + 1) << 16
     double* states;              // [.][14][N+1] indexed by candidate (states_by_slot = 0) or slot
     int states_by_slot;
+    unsigned long long* best_bits;   // lazy collision mode: bit pattern of the best collision-free cost so far
     int Np1;                     // N + 1
     int stage_ref, stage_dyn;
 };
@@ -70,7 +71,7 @@ __device__ __forceinline__ int upper_bound_guess(const double* __restrict__ a, i
 }
 
 // per-slot integer scratch
-enum : int { F_BAD = 0, F_PBAD = 1, F_PRE = 2, F_COL = 3, F_TL = 4, F_STATE = 5, F_K = 6, F_WORDS = 8 };
+enum : int { F_BAD = 0, F_PBAD = 1, F_PRE = 2, F_COL = 3, F_TL = 4, F_STATE = 5, F_K = 6, F_GATE = 7, F_WORDS = 8 };
 // F_STATE bits
 enum : unsigned { S_VALID = 1u, S_FILTERED = 2u, S_ALIVE = 4u, S_KINOK = 8u, S_KEEP = 16u };
 // per-slot double scratch beyond the rows: last[16] acc[40] sums[5] park[5] (+pad)
@@ -460,12 +461,58 @@ fused_kernel(const __grid_constant__ PlanParams P) {
             }
         }
 
+        // total cost of slot c2 from its five sums and the parked end / mid values, in the reference's order
+        auto total_cost = [&](int c2) {
+            const double* sums = slots + (size_t)c2 * per_slot + kRows * Np1 + 16 + 40;
+            const double* park = sums + 5;
+            double costs = 0.0;
+            costs += sums[0];
+            if (!fs && in.has_desired_speed) {
+                const double e1 = park[0] - in.desired_speed, e2 = park[4] - in.desired_speed;
+                costs += sums[1] + (50 * (e1 * e1)) + (100 * (e2 * e2));
+            }
+            if (!fs && in.has_desired_s) {
+                const double e = 20 * (in.desired_s - park[1]);
+                costs += sums[2] + e * e;
+            }
+            {
+                const double e = 20 * (des_d - park[2]);
+                costs += sums[3] + e * e;
+            }
+            {
+                const double e = 5 * fabs(park[3]);
+                costs += sums[4] + e * e;
+            }
+            return costs;
+        };
+        // ---- lazy collision mode: the reference checks candidates in cost order and stops at the first
+        // collision-free one (reactive_planner.py:1031-1063).  In parallel form: a candidate whose cost exceeds
+        // the best collision-free cost found so far can be neither the winner nor a collider ranked before it,
+        // so its check is skipped (status RP_FEASIBLE_UNCHECKED).  Winner and lazy collision count are exact.
+        const bool lazy = in.check_collision == 2 && in.cost_kind != RP_COST_NONE && P.best_bits != nullptr;
+        if (lazy) {
+            __syncthreads();                                   // sums complete
+            if (tid < C) {
+                unsigned* fl = s_flags_all + (size_t)tid * F_WORDS;
+                unsigned gate = 0u;
+                if (fl[F_STATE] & S_KINOK) {
+                    const double cst = total_cost(tid);
+                    const unsigned long long best = *reinterpret_cast<volatile unsigned long long*>(P.best_bits);
+                    gate = !((unsigned long long)__double_as_longlong(cst) > best) ? 1u : 0u;   // costs are >= 0: bit order == value order
+                    if (cst != cst) gate = 1u;                 // NaN cost: keep full semantics
+                }
+                fl[F_GATE] = gate;
+            }
+            __syncthreads();
+        }
+
         // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), element-strided ----------------
         if (in.check_collision) {
             for (int e = tid, c2 = e_c0, i2 = e_i0; e < n_elem; e += T, c2 += e_dc, i2 += e_di) {
                 if (i2 >= Np1) { i2 -= Np1; ++c2; }
                 unsigned* fl = s_flags_all + (size_t)c2 * F_WORDS;
                 if (!(fl[F_STATE] & S_KINOK)) continue;
+                if (lazy && fl[F_GATE] == 0u) continue;
                 const double* sc = slots + (size_t)c2 * per_slot;
                 const double th2 = sc[i2];
                 double st, ct;
@@ -488,8 +535,6 @@ fused_kernel(const __grid_constant__ PlanParams P) {
             const unsigned st2 = fl[F_STATE];
             if (st2 & S_VALID) {
                 const double* sc = slots + (size_t)tid * per_slot;
-                const double* sums = sc + kRows * Np1 + 16 + 40;
-                const double* park = sums + 5;
                 int status, reason = R_NONE, step = -1;
                 double cost = __longlong_as_double(0x7ff8000000000000LL);   // NaN
                 const unsigned pre2 = fl[F_PRE], bad2 = fl[F_BAD], pbad2 = fl[F_PBAD];
@@ -508,29 +553,16 @@ fused_kernel(const __grid_constant__ PlanParams P) {
                     step = (int)pbad2;
                 } else {
                     status = ST_FEASIBLE;
-                    if (in.cost_kind != RP_COST_NONE) {
-                        double costs = 0.0;
-                        costs += sums[0];
-                        if (!fs && in.has_desired_speed) {
-                            const double e1 = park[0] - in.desired_speed, e2 = park[4] - in.desired_speed;
-                            costs += sums[1] + (50 * (e1 * e1)) + (100 * (e2 * e2));
-                        }
-                        if (!fs && in.has_desired_s) {
-                            const double e = 20 * (in.desired_s - park[1]);
-                            costs += sums[2] + e * e;
-                        }
-                        {
-                            const double e = 20 * (des_d - park[2]);
-                            costs += sums[3] + e * e;
-                        }
-                        {
-                            const double e = 5 * fabs(park[3]);
-                            costs += sums[4] + e * e;
-                        }
-                        cost = costs;
-                    }
+                    if (in.cost_kind != RP_COST_NONE) cost = total_cost(tid);
                     const unsigned cstep = fl[F_COL];
                     if (cstep != NONE) { status = ST_COLLISION; step = (int)cstep; }
+                    else if (lazy) {
+                        if (fl[F_GATE] == 0u) status = ST_UNCHECKED;
+                        else if (cost == cost) {
+                            const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);
+                            if (cb < *reinterpret_cast<volatile unsigned long long*>(P.best_bits)) atomicMin(P.best_bits, cb);
+                        }
+                    }
                 }
                 const int k2 = (int)fl[F_K];
                 P.info[k2] = pack_info(status, reason, step);

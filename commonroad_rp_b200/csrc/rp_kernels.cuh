@@ -143,6 +143,8 @@ __global__ void __launch_bounds__(256) argmin_partial_kernel(const double* __res
         } else if (st == ST_COLLISION) {
             ++l_feas;
             ++l_colt;
+        } else if (st == ST_UNCHECKED) {
+            ++l_feas;
         } else if (st == ST_KINEMATIC) {
             const int r = (w >> 8) & 0x7;
 #pragma unroll

@@ -348,7 +348,10 @@ class ReactivePlanner(object):
             self.config.sampling.longitudinal_mode, self.N, self.dt, factor=p.factor, draw_all=self._draw_traj_set,
             constraints=p.constraints_to_check, cost_kind=cost_spec["cost_kind"],
             desired_speed=cost_spec["desired_speed"], desired_s=cost_spec["desired_s"],
-            desired_d=cost_spec["desired_d"], w_a=cost_spec["w_a"], want_all_states=want_all_states)
+            desired_d=cost_spec["desired_d"], w_a=cost_spec["w_a"], want_all_states=want_all_states,
+            # the reference's collision pass is lazy (:1031-1063); full flags only when every trajectory is kept
+            check_collision=_lib.COLLISION_ALL if (want_all_states or cost_spec["cost_kind"] == _lib.COST_NONE)
+            else _lib.COLLISION_LAZY)
 
     def _device_cost_spec(self):
         """Fused device cost for the built-in cost functions; None for user subclasses that bring their own
@@ -472,7 +475,7 @@ class ReactivePlanner(object):
 
         if self._draw_traj_set:
             status = arrays["status"]
-            order = [k for k in range(dev["n"]) if status[k] in (0, 2)] + [k for k in range(dev["n"]) if status[k] == 1]
+            order = [k for k in range(dev["n"]) if status[k] in (0, 2, 4)] + [k for k in range(dev["n"]) if status[k] == 1]
             self.stored_trajectories = [self._view(trajectory_bundle, k, arrays) for k in order]
 
         if winner < 0:

@@ -133,7 +133,8 @@ class _DeviceBacking:
 
 
 _STATUS_TO_LABEL = {0: FeasibilityStatus.FEASIBLE, 1: FeasibilityStatus.INFEASIBLE_KINEMATIC,
-                    2: FeasibilityStatus.INFEASIBLE_COLLISION, 3: None}
+                    2: FeasibilityStatus.INFEASIBLE_COLLISION, 3: None,
+                    4: FeasibilityStatus.FEASIBLE}     # lazy collision pass never visited it (as in the reference)
 
 
 class TrajectorySample(Sample):
@@ -199,7 +200,7 @@ class TrajectorySample(Sample):
         b = self._backing
         if b is not None and self._cartesian is None and b.engine.plan_generation == b.generation:
             status = int(b.bundle_arrays["status"][b.index])
-            if status in (0, 2) or b.bundle_arrays.get("all_states", False):
+            if status in (0, 2, 4) or b.bundle_arrays.get("all_states", False):
                 self._materialise()
 
     # ---- reference API ----

@@ -43,7 +43,8 @@ enum rp_status {
 };
 
 /* candidate status (FeasibilityStatus, trajectories.py:18-22; FILTERED = filter_goals_behind, :545-550) */
-enum rp_cand_status { RP_FEASIBLE = 0, RP_INFEASIBLE_KINEMATIC = 1, RP_INFEASIBLE_COLLISION = 2, RP_FILTERED = 3 };
+enum rp_cand_status { RP_FEASIBLE = 0, RP_INFEASIBLE_KINEMATIC = 1, RP_INFEASIBLE_COLLISION = 2, RP_FILTERED = 3,
+                      RP_FEASIBLE_UNCHECKED = 4 /* lazy collision mode: kinematically feasible, never visited */ };
 
 /* reason of a kinematic rejection: keys of infeasible_reason_dict (reactive_planner.py:799,803,979-1016),
  * plus the projection-domain rejection (:911-917) which the reference counts but does not name. */
@@ -96,7 +97,10 @@ typedef struct rp_plan_inputs {
     int32_t has_desired_s;       /* DefaultCostFunction.desired_s is not None                */
     double desired_speed, desired_s, desired_d, w_a;
     int32_t want_all_states;     /* 1: keep the 14 x (N+1) state block of EVERY candidate     */
-    int32_t check_collision;     /* 0: skip a13 (collision flags all clear)                  */
+    int32_t check_collision;     /* 0: skip a13; 1: check every kinematically feasible candidate; 2: lazy, like the
+                                    reference's cost-ordered pass (:1031-1063): candidates costlier than the best
+                                    collision-free one found so far are not visited.  Winner and
+                                    n_infeasible_collision are identical in modes 1 and 2.              */
 } rp_plan_inputs;
 
 typedef struct rp_plan_result {
@@ -105,7 +109,7 @@ typedef struct rp_plan_result {
     int32_t n_feasible;                    /* kinematically feasible (before the collision check)     */
     int32_t n_infeasible_kinematics;       /* ReactivePlanner.infeasible_count_kinematics (:1119)     */
     int32_t n_infeasible_collision;        /* colliders ranked before the winner (:1043; App. B#12)   */
-    int32_t n_collision_total;             /* all kinematically feasible candidates that collide      */
+    int32_t n_collision_total;             /* kinematically feasible candidates found colliding (all of them in mode 1) */
     int32_t reason_counts[RP_N_REASONS];   /* infeasible_reason_dict (+ projection)                   */
     double winner_cost;
 } rp_plan_result;

@@ -279,3 +279,32 @@ def test_full_size_dense_bundle_properties():
         if kin[q]:
             assert H.rel_err(o["states"][q], eng.fetch_states(int(k))) < 1e-9
     eng.close()
+
+
+def test_lazy_collision_mode_is_exact_for_reference_outputs():
+    """check_collision = 2 skips candidates costlier than the best collision-free one found so far; the
+    winner, the lazy collision count (reactive_planner.py:1043) and every verdict ranked before the winner
+    must equal full checking."""
+    from commonroad_rp_b200 import _lib
+    from tests.test_gpu_parity import _bundle
+    for case in (dict(seed=2, level=2, N=60, s_dot0=12.0), dict(seed=1, level=3, N=20, d0=-0.4), dict(seed=0, level=1, N=20)):
+        prob = _bundle(**case)
+        eng = H.engine_for(prob)
+        full = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
+        cost_f, status_f, _, step_f = eng.fetch_candidates()
+        lazy = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_LAZY), prob["t"], prob["lon"], prob["d"])
+        cost_l, status_l, _, step_l = eng.fetch_candidates()
+        assert lazy.winner == full.winner and lazy.winner_cost == full.winner_cost
+        assert lazy.n_infeasible_collision == full.n_infeasible_collision
+        assert lazy.n_infeasible_kinematics == full.n_infeasible_kinematics and lazy.n_feasible == full.n_feasible
+        assert np.array_equal(cost_f, cost_l, equal_nan=True)
+        n = len(cost_f)
+        idx = np.arange(n)
+        before = (cost_f < full.winner_cost) | ((cost_f == full.winner_cost) & (idx <= full.winner)) if full.winner >= 0 \
+            else np.ones(n, dtype=bool)
+        assert np.array_equal(status_f[before], status_l[before]) and np.array_equal(step_f[before], step_l[before])
+        unchecked = status_l == _lib.ST_UNCHECKED
+        assert np.all(np.isin(status_f[unchecked], (0, 2))) and not (unchecked & before).any()
+        others = ~unchecked
+        assert np.array_equal(status_f[others], status_l[others])
+        eng.close()
