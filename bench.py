@@ -157,6 +157,99 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------------------------------
+def _cyclic_fixture(name="ZAM_Over-1_1"):
+    """Replanning cycles of a bundled reference scenario (inputs recorded by oracle/make_golden.py)."""
+    from tests import golden_io
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cyc_%s.npz" % name))
+    meta = json.loads(str(z["meta"]))
+    return z, meta, golden_io.unpack_obstacles(z, "ob_")
+
+
+def replanning_latency_b200(name="ZAM_Over-1_1", repeats=5):
+    """p50 wall time of ReactivePlanner.plan() (this repo's drop-in API) over the scenario's replanning cycles."""
+    from commonroad_rp_b200 import collision
+    from commonroad_rp_b200.reactive_planner import ReactivePlanner
+    from commonroad_rp_b200.state import ReactivePlannerState
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    z, meta, ob = _cyclic_fixture(name)
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = meta["N"]
+    cfg.planning.low_vel_mode_threshold = meta["low_vel_mode_threshold"]
+    cfg.sampling.t_min = meta["t_min"]
+
+    class _Empty:
+        static_obstacles, dynamic_obstacles = (), ()
+        lanelet_network = type("LN", (), {"lanelets": ()})()
+
+    cfg.update(scenario=_Empty(), planning_problem=None)
+    planner = ReactivePlanner(cfg)
+    cc = collision.checker_from_arrays(**ob)
+    co = CoordinateSystem(z["ref_path_raw"])
+    times = []
+    for rep in range(repeats + 1):
+        for ci in range(meta["n_cycles"]):
+            x = z["c%d_x0" % ci]
+            x0 = ReactivePlannerState(time_step=int(x[7]), position=np.array([x[0], x[1]]), orientation=x[2],
+                                      velocity=x[3], acceleration=x[4], yaw_rate=x[5], steering_angle=x[6])
+            planner.reset(initial_state_cart=x0, initial_state_curv=(list(z["c%d_x0_lon" % ci]), list(z["c%d_x0_lat" % ci])),
+                          collision_checker=cc, coordinate_system=co)
+            planner.set_desired_velocity(desired_velocity=meta["desired_velocity"] if ci == 0 else None,
+                                         current_speed=x0.velocity)
+            t0 = time.perf_counter()
+            out = planner.plan()
+            dt_s = time.perf_counter() - t0
+            assert (out is not None) == meta["cycles"][ci]["ok"]
+            if rep > 0:
+                times.append(dt_s)
+    t_ms = np.array(times) * 1e3
+    return {"p50_ms": float(np.percentile(t_ms, 50)), "p95_ms": float(np.percentile(t_ms, 95)), "cycles": len(t_ms),
+            "scenario": "%s, N=%d, cyclic replanning inputs of the reference run (tests/golden)" % (name, meta["N"]),
+            "api": "ReactivePlanner.plan()"}
+
+
+def replanning_latency_port(name="ZAM_Over-1_1", max_cycles=6):
+    """The same cycles through the oracle port (level escalation as reactive_planner.py:616-636), single process."""
+    from oracle import rp_oracle as O
+    from commonroad_rp_b200.sampling import FixedIntervalSampling, VelocitySampling
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    z, meta, ob = _cyclic_fixture(name)
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = meta["N"]
+    cfg.sampling.t_min = meta["t_min"]
+    fs = FixedIntervalSampling(cfg)
+    veh = cfg.vehicle
+    horizon = meta["N"] * meta["dt"]
+    times = []
+    for ci in range(min(max_cycles, meta["n_cycles"])):
+        x = z["c%d_x0" % ci]
+        v0 = float(x[3])
+        lo = max(0, v0 - 0.125 * horizon * veh.a_max)
+        fs.samples_v = VelocitySampling(lo, max(lo + 5.0, v0 + 2), 4)
+        x0_lon, x0_lat = z["c%d_x0_lon" % ci], z["c%d_x0_lat" % ci]
+        t0 = time.perf_counter()
+        for level in range(1, 4):
+            t, lon, d = fs.sample_grid(level, x0_lat, "velocity_keeping")
+            prob = {"t": t, "lon": lon, "d": d, "x0_lon": x0_lon, "x0_lat": x0_lat, "x0_orientation": float(x[2]),
+                    "x0_time_step": int(x[7]), "lon_mode": "velocity_keeping",
+                    "low_vel_mode": bool(v0 < meta["low_vel_mode_threshold"]), "dt": meta["dt"], "N": meta["N"],
+                    "factor": 1, "draw_all": False, "constraints": O.CONSTRAINTS,
+                    "cost": {"kind": "default", "desired_speed": meta["desired_velocity"], "desired_s": None,
+                             "desired_d": 0.0, "w_a": 5},
+                    "vehicle": {"length": veh.length, "width": veh.width, "wb_rear_axle": veh.wb_rear_axle,
+                                "wheelbase": veh.wheelbase, "a_max": veh.a_max, "v_switch": veh.v_switch,
+                                "delta_max": veh.delta_max, "v_delta_max": veh.v_delta_max},
+                    "ref": {k: z[k] for k in ("ref_pos", "ref_theta", "ref_curv", "ref_curv_d")},
+                    "ccosy": {"path": z["cc_path"], "S": z["cc_S"], "normals": z["cc_normals"], "limit": 20.0},
+                    "obstacles": ob}
+            if O.plan_grid(prob, want_states=False, full_collision=False)["winner"] >= 0:
+                break
+        times.append(time.perf_counter() - t0)
+    t_ms = np.array(times) * 1e3
+    return {"p50_ms": float(np.percentile(t_ms, 50)), "p95_ms": float(np.percentile(t_ms, 95)), "cycles": len(t_ms),
+            "scenario": "%s, N=%d" % (name, meta["N"]), "api": "oracle port, single process"}
+
+
 def cpu_port_rate(work, stride, workers, repeats=1):
     """The oracle port (reference algorithm restated, oracle/rp_oracle.py) on a sub-grid of the same
     workload: every ``stride``-th v and d sample.  Returns (candidates/s, description, seconds)."""
@@ -222,6 +315,7 @@ def run_reference_arm(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "cand_timesteps_per_sec": value * (N_HORIZON + 1), "gpu_launches": 0,
+        "p50_replanning_cycle_ms": replanning_latency_port(),
     }
     print(json.dumps(line))
 
@@ -405,7 +499,7 @@ def main():
         "e2e": {"value": n_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "rp_plan_grid + rp_fetch_states (host buffers)"},
-        "gpu_launches": int(eng.launches_per_plan() * args.steps),
+        "gpu_launches": int((eng.launches_per_plan() + (2 if world > 1 else 0)) * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
@@ -422,7 +516,9 @@ def main():
         line["roofline_full_states"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                         "frac": gbs / peaks.get("hbm_gbs"), "traffic": None, "kernel_ms": full,
                                         "peak_source": peak_kind + " (MEASURED_PEAKS.json)"}
+    line["p50_replanning_cycle_ms"] = replanning_latency_b200()
     if not args.no_cpu_baseline:
+        line["p50_replanning_cycle_ms"]["cpu_port"] = replanning_latency_port()
         cores = 1
         rate, desc, sec, n_s = cpu_port_rate(dense_workload(1), 8, cores)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,

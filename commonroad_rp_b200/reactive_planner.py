@@ -582,12 +582,13 @@ class ReactivePlanner(object):
         x_0_lon, x_0_lat = self.x_0_cl
         self._low_vel_mode = True if self.x_0.velocity < self.config.planning.low_vel_mode_threshold else False
 
-        logger.info("=================== Starting Planning Cycle ===================")
-        logger.info(f"time_step={self.x_0.time_step} position={self.x_0.position} velocity={self.x_0.velocity} "
-                    f"orientation={self.x_0.orientation}")
-        logger.info(f"longitudinal state = {x_0_lon}  lateral state = {x_0_lat}")
-        logger.info(f"mode: {self.config.sampling.longitudinal_mode}  desired velocity: {self._desired_speed} m/s  "
-                    f"desired longitudinal position: {self._desired_lon_position} m")
+        if logger.isEnabledFor(logging.INFO):      # the f-strings format numpy arrays: skip when nobody listens
+            logger.info("=================== Starting Planning Cycle ===================")
+            logger.info(f"time_step={self.x_0.time_step} position={self.x_0.position} velocity={self.x_0.velocity} "
+                        f"orientation={self.x_0.orientation}")
+            logger.info(f"longitudinal state = {x_0_lon}  lateral state = {x_0_lat}")
+            logger.info(f"mode: {self.config.sampling.longitudinal_mode}  desired velocity: {self._desired_speed} m/s  "
+                        f"desired longitudinal position: {self._desired_lon_position} m")
 
         optimal_trajectory = None
         bundle = None
