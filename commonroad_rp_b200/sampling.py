@@ -28,31 +28,31 @@ except ImportError:
 
 
 class Sampling(ABC):
-    """Sample sets per sampling level for one dimension (reference :28-69)."""
+    """One sampled dimension: a set of values per sampling level, built once by ``_sample`` (reference :28-69)."""
 
     def __init__(self, low: float, up: float, num_sampling_levels: int):
-        assert np.greater_equal(up, low), '<Sampling>: Upper sampling bound is not greater than ' \
-                                          'lower bound! up = {} , low = {}'.format(up, low)
-        assert isinstance(num_sampling_levels, int) and num_sampling_levels > 0, \
-            '<Sampling: number of samples must be positive integer>'
-        self.low = low
-        self.up = up
+        if not np.greater_equal(up, low):
+            raise AssertionError('<Sampling>: Upper sampling bound is not greater than lower bound! '
+                                 'up = {} , low = {}'.format(up, low))
+        if not (isinstance(num_sampling_levels, int) and num_sampling_levels > 0):
+            raise AssertionError('<Sampling: number of samples must be positive integer>')
+        self.low, self.up = low, up
         self._n_samples = num_sampling_levels
-        self._dict_level_to_sample_set: Dict[int, set] = dict()
+        self._dict_level_to_sample_set: Dict[int, set] = {}
         self._sample()
 
     @abstractmethod
     def _sample(self):
-        pass
-
-    def samples_at_level(self, sampling_level: int = 0) -> set:
-        assert 0 <= sampling_level < self.num_sampling_levels, \
-            '<Sampling>: Provided sampling level is incorrect! stage = {}'.format(sampling_level)
-        return self._dict_level_to_sample_set[sampling_level]
+        """fill ``_dict_level_to_sample_set[level]`` for every level"""
 
     @property
     def num_sampling_levels(self) -> int:
         return self._n_samples
+
+    def samples_at_level(self, sampling_level: int = 0) -> set:
+        if not 0 <= sampling_level < self._n_samples:
+            raise AssertionError('<Sampling>: Provided sampling level is incorrect! stage = {}'.format(sampling_level))
+        return self._dict_level_to_sample_set[sampling_level]
 
 
 def _nested_linspace_sets(low, up, levels):
@@ -92,7 +92,9 @@ class TimeSampling(Sampling):
 
 
 class SamplingSpace(ABC):
-    """Sample sets for the time, position and velocity domains (reference :121-175)."""
+    """Base of all sampling spaces: holds the per-dimension ``Sampling`` objects (``samples_t``,
+    ``samples_d``, ``samples_v``; subclasses may add more) and produces the trajectory set of a level
+    (reference :121-175)."""
 
     def __init__(self, num_sampling_levels: int):
         self._num_sampling_levels = num_sampling_levels
@@ -102,37 +104,18 @@ class SamplingSpace(ABC):
         self._samples_s: Optional[PositionSampling] = None
 
     @property
-    def samples_t(self) -> TimeSampling:
-        return self._samples_t
-
-    @samples_t.setter
-    def samples_t(self, time_sampling: TimeSampling):
-        self._samples_t = time_sampling
-
-    @property
-    def samples_d(self) -> PositionSampling:
-        return self._samples_d
-
-    @samples_d.setter
-    def samples_d(self, pos_sampling: PositionSampling):
-        self._samples_d = pos_sampling
-
-    @property
-    def samples_v(self) -> VelocitySampling:
-        return self._samples_v
-
-    @samples_v.setter
-    def samples_v(self, vel_sampling: VelocitySampling):
-        self._samples_v = vel_sampling
-
-    @property
     def num_sampling_levels(self) -> int:
         return self._num_sampling_levels
+
+    # plain attribute-backed properties; CorridorSampling overrides the d / v setters
+    samples_t = property(lambda self: self._samples_t, lambda self, value: setattr(self, "_samples_t", value))
+    samples_d = property(lambda self: self._samples_d, lambda self, value: setattr(self, "_samples_d", value))
+    samples_v = property(lambda self: self._samples_v, lambda self, value: setattr(self, "_samples_v", value))
 
     @abstractmethod
     def generate_trajectories_at_level(self, level_sampling: int, x_0_lon: np.ndarray, x_0_lat: np.ndarray,
                                        longitudinal_mode: str, low_vel_mode: bool) -> List[TrajectorySample]:
-        """Generate the trajectory set of this sampling space at the given level."""
+        """List of TrajectorySample of the given level, in enumeration order."""
 
 
 class FixedIntervalSampling(SamplingSpace):
@@ -150,13 +133,7 @@ class FixedIntervalSampling(SamplingSpace):
         self.samples_v = VelocitySampling(cs.v_min, cs.v_max, num_sampling_levels)
         self.samples_s = PositionSampling(cs.s_min, cs.s_max, num_sampling_levels)
 
-    @property
-    def samples_s(self) -> PositionSampling:
-        return self._samples_s
-
-    @samples_s.setter
-    def samples_s(self, pos_sampling: PositionSampling):
-        self._samples_s = pos_sampling
+    samples_s = property(lambda self: self._samples_s, lambda self, value: setattr(self, "_samples_s", value))
 
     def _get_lon_samples(self, level_sampling):
         if self._longitudinal_mode == "velocity_keeping":

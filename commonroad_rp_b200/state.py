@@ -1,42 +1,44 @@
-"""``ReactivePlannerState`` -- same class as the reference's ``commonroad_rp/state.py`` (host glue,
-out of scope to accelerate; positions refer to the rear axle)."""
+"""Planner state used at the API boundary (the reference's ``commonroad_rp/state.py``): a kinematic
+single-track state whose POSITION REFERS TO THE REAR AXLE, extended by acceleration and yaw rate.
+Host glue, not on the accelerated path."""
+import math
 from dataclasses import dataclass
 from typing import Any
 
 import numpy as np
 
-from commonroad_rp_b200._compat import KSState, InitialState
+from commonroad_rp_b200._compat import InitialState, KSState  # noqa: F401  (InitialState re-exported for users)
+
+
+def _along_heading(theta: float, distance: float) -> np.ndarray:
+    return np.array([distance * math.cos(theta), distance * math.sin(theta)])
 
 
 @dataclass(eq=False)
 class ReactivePlannerState(KSState):
-    """KSState + acceleration and yaw rate; position is the REAR-AXLE position (reference state.py:7-20)."""
     acceleration: Any = None
     yaw_rate: Any = None
 
     def __repr__(self):
-        return f"(time_step={self.time_step}, position={self.position},steering_angle={self.steering_angle}, " \
-               f"velocity={self.velocity}, orientation={self.orientation}, acceleration={self.acceleration}, " \
-               f"yaw_rate = {self.yaw_rate})"
+        parts = ("time_step", "position", "steering_angle", "velocity", "orientation", "acceleration", "yaw_rate")
+        return "(" + ", ".join("%s=%s" % (p, getattr(self, p)) for p in parts) + ")"
 
     def shift_positions_to_center(self, wb_rear_axle: float):
-        """rear axle -> vehicle centre (reference state.py:22-31)"""
-        th = self.orientation
-        return self.translate_rotate(np.array([wb_rear_axle * np.cos(th), wb_rear_axle * np.sin(th)]), 0.0)
+        """Copy of this state with the position moved from the rear axle to the vehicle centre."""
+        return self.translate_rotate(_along_heading(self.orientation, wb_rear_axle), 0.0)
 
     @classmethod
     def create_from_initial_state(cls, initial_state, wheelbase: float, wb_rear_axle: float):
-        """InitialState (vehicle centre) -> planner state at the rear axle, steering angle from the yaw rate
-        (reference state.py:33-67)."""
+        """Planning-problem initial state (vehicle centre, slip angle) -> planner state: acceleration
+        defaults to 0, the slip angle is dropped, the position moves back to the rear axle and the steering
+        angle follows from the yaw rate (reference state.py:33-67)."""
         if getattr(initial_state, "acceleration", None) is None:
             initial_state.acceleration = 0.
-        if hasattr(initial_state, "slip_angle"):
-            try:
-                delattr(initial_state, "slip_angle")
-            except AttributeError:
-                pass
-        th = initial_state.orientation
-        shifted = initial_state.translate_rotate(np.array([-wb_rear_axle * np.cos(th), -wb_rear_axle * np.sin(th)]), 0.0)
-        x0 = shifted.convert_state_to_state(cls())
-        x0.steering_angle = np.arctan2(wheelbase * x0.yaw_rate, x0.velocity)
-        return x0
+        try:
+            del initial_state.slip_angle
+        except AttributeError:
+            pass
+        rear = initial_state.translate_rotate(_along_heading(initial_state.orientation, -wb_rear_axle), 0.0)
+        planner_state = rear.convert_state_to_state(cls())
+        planner_state.steering_angle = np.arctan2(wheelbase * planner_state.yaw_rate, planner_state.velocity)
+        return planner_state

@@ -1,224 +1,212 @@
-"""Configuration tree of the planner -- same classes, field names and defaults as the reference's
-``commonroad_rp/utility/config.py`` (dataclass tree :107-290), so existing YAML files and user code
-keep working.  Differences that do not touch the API:
+"""Configuration tree of the planner.  Class names, field names, defaults and the YAML layout are those
+of the reference's ``commonroad_rp/utility/config.py`` (:107-290) so that existing configuration files
+and user code keep working; the classes themselves are generated from the specification tables below.
 
-* YAML is read with OmegaConf when it is installed, otherwise with PyYAML (not installed here).
-* Vehicle parameters come from ``vehiclemodels`` when importable, otherwise from the built-in table of
-  commonroad-vehicle-models 3.0.2 values below (type 2 = BMW 320i is the reference default, :198).
-* ``debug.multiproc`` / ``debug.num_workers`` are accepted and ignored: the candidate loop runs on the
-  GPU, there is nothing to fork.
+Not identical on purpose (none of it changes the API):
+* YAML is parsed with OmegaConf when importable, else PyYAML (OmegaConf is not installed in this image);
+* vehicle parameters come from ``vehiclemodels`` / ``commonroad_dc`` when importable, else from the
+  built-in commonroad-vehicle-models 3.0.2 table (type 2 = BMW 320i is the reference default, :198);
+* ``debug.multiproc`` and ``debug.num_workers`` are accepted and ignored: candidates are GPU threads,
+  there is nothing to fork.
 """
 import dataclasses
 import inspect
 import os.path
 import pathlib
 import warnings
-from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional, Union
+from typing import Any, List, Optional
 
 import numpy as np
 
 
-class _NS:
+class _Bag:
     def __init__(self, **kw):
         self.__dict__.update(kw)
 
 
-# commonroad-vehicle-models 3.0.2 (type 2 values per SURVEY.md App. D#5; 1 and 3 for completeness)
-_VEHICLE_TABLE = {
-    1: dict(l=4.298, w=1.674, a=0.88392, b=1.50876, a_max=11.5, v_switch=4.755, s_min=-0.910, s_max=0.910,
-            sv_min=-0.4, sv_max=0.4),
-    2: dict(l=4.508, w=1.610, a=1.1561957064, b=1.4227170936, a_max=11.5, v_switch=7.319, s_min=-1.066, s_max=1.066,
-            sv_min=-0.4, sv_max=0.4),
-    3: dict(l=4.569, w=1.844, a=1.08966, b=1.35634, a_max=11.5, v_switch=7.824, s_min=-1.023, s_max=1.023,
-            sv_min=-0.4, sv_max=0.4),
+# l, w, a, b, a_max, v_switch, steering min / max, steering-rate min / max
+_VEHICLES = {
+    1: (4.298, 1.674, 0.88392, 1.50876, 11.5, 4.755, -0.910, 0.910, -0.4, 0.4),          # Ford Escort
+    2: (4.508, 1.610, 1.1561957064, 1.4227170936, 11.5, 7.319, -1.066, 1.066, -0.4, 0.4),  # BMW 320i
+    3: (4.569, 1.844, 1.08966, 1.35634, 11.5, 7.824, -1.023, 1.023, -0.4, 0.4),           # VW Vanagon
 }
 
 
 def vehicle_parameters_from_type(vehicle_type_id: int):
-    """VehicleParameterMapping.from_vehicle_type(VehicleType(id)) stand-in (reference :200)."""
+    """What ``VehicleParameterMapping.from_vehicle_type(VehicleType(id))`` returns (reference :200)."""
     try:
         from commonroad.common.solution import VehicleType
         from commonroad_dc.feasibility.vehicle_dynamics import VehicleParameterMapping
         return VehicleParameterMapping.from_vehicle_type(VehicleType(vehicle_type_id))
     except Exception:
-        pass
-    row = _VEHICLE_TABLE[int(vehicle_type_id)]
-    return _NS(l=row["l"], w=row["w"], a=row["a"], b=row["b"],
-               longitudinal=_NS(a_max=row["a_max"], v_switch=row["v_switch"]),
-               steering=_NS(min=row["s_min"], max=row["s_max"], v_min=row["sv_min"], v_max=row["sv_max"]))
+        l, w, a, b, a_max, v_switch, s_lo, s_hi, sv_lo, sv_hi = _VEHICLES[int(vehicle_type_id)]
+        return _Bag(l=l, w=w, a=a, b=b, longitudinal=_Bag(a_max=a_max, v_switch=v_switch),
+                    steering=_Bag(min=s_lo, max=s_hi, v_min=sv_lo, v_max=sv_hi))
 
 
-def _dict_to_params(dict_params: Dict[str, Any], cls: Any) -> Any:
-    kwargs = {}
-    for f in dataclasses.fields(cls):
-        if not f.init or f.name not in dict_params:
-            continue
-        if inspect.isclass(f.type) and issubclass(f.type, BaseConfiguration):
-            kwargs[f.name] = _dict_to_params(dict_params[f.name], f.type)
-        else:
-            kwargs[f.name] = dict_params[f.name]
-    return cls(**kwargs)
-
-
-def _load_yaml(file_path) -> dict:
+def _read_yaml(path) -> dict:
     try:
         from omegaconf import OmegaConf
-        loaded = OmegaConf.to_object(OmegaConf.load(file_path))
-        if isinstance(loaded, dict):
-            return loaded
-    except Exception:       # not installed (or a test stub of it): plain YAML is equivalent for these files
+        tree = OmegaConf.to_object(OmegaConf.load(path))
+        if isinstance(tree, dict):
+            return tree
+    except Exception:       # absent (or a test stub of it): plain YAML is equivalent for these files
         pass
     import yaml
-    with open(file_path) as f:
-        return yaml.safe_load(f) or {}
+    with open(path) as fh:
+        return yaml.safe_load(fh) or {}
 
 
-@dataclass
+def _from_dict(tree: dict, cls):
+    """Nested dictionaries -> nested configuration objects; unknown keys are ignored like in the reference."""
+    picked = {}
+    for f in dataclasses.fields(cls):
+        if f.init and f.name in tree:
+            nested = inspect.isclass(f.type) and issubclass(f.type, BaseConfiguration)
+            picked[f.name] = _from_dict(tree[f.name], f.type) if nested else tree[f.name]
+    return cls(**picked)
+
+
 class BaseConfiguration:
-    """Reactive planner base parameters."""
+    """Item access (``cfg["planning"]["dt"]``) and the YAML loader shared by all configuration classes."""
 
     def __getitem__(self, item: str) -> Any:
-        try:
-            return self.__getattribute__(item)
-        except AttributeError as e:
-            raise KeyError(f"{item} is not a parameter of {self.__class__.__name__}") from e
+        if not hasattr(self, item):
+            raise KeyError(f"{item} is not a parameter of {self.__class__.__name__}")
+        return getattr(self, item)
 
     def __setitem__(self, key: str, value: Any):
         try:
-            self.__setattr__(key, value)
+            setattr(self, key, value)
         except AttributeError as e:
             raise KeyError(f"{key} is not a parameter of {self.__class__.__name__}") from e
 
     @classmethod
-    def load(cls, file_path: Union[pathlib.Path, str], scenario_name: Optional[str] = None,
-             validate_types: bool = True) -> 'ReactivePlannerConfiguration':
-        """Loads parameters from a config yaml file (reference :84-104)."""
+    def load(cls, file_path, scenario_name: Optional[str] = None, validate_types: bool = True):
+        """Configuration from a .yaml file; ``scenario_name`` fills ``general.path_scenario`` (reference :84-104)."""
         file_path = pathlib.Path(file_path)
         assert file_path.suffix == ".yaml", f"File type {file_path.suffix} is unsupported! Please use .yaml!"
-        params = _dict_to_params(_load_yaml(file_path), cls)
+        cfg = _from_dict(_read_yaml(file_path), cls)
         if scenario_name:
-            params.general.set_path_scenario(scenario_name)
-        return params
+            cfg.general.set_path_scenario(scenario_name)
+        return cfg
 
 
-@dataclass
-class PlanningConfiguration(BaseConfiguration):
-    """Planning parameters for reactive planner."""
-    dt: float = 0.1
-    time_steps_computation: int = 60
-    planning_horizon: float = dt * time_steps_computation
-    replanning_frequency: int = 3
-    continuous_collision_check: bool = False
-    factor: int = 1
-    low_vel_mode_threshold: float = 4.0
-    constraints_to_check: List[str] = \
-        field(default_factory=lambda: ["velocity", "acceleration", "kappa", "kappa_dot", "yaw_rate"])
-    standstill_lookahead: int = 10
+def _make(name: str, doc: str, spec, namespace=None):
+    fields = []
+    for fname, ftype, default in spec:
+        if isinstance(default, (list, dict)):
+            fields.append((fname, ftype, dataclasses.field(default_factory=lambda d=default: type(d)(d))))
+        else:
+            fields.append((fname, ftype, dataclasses.field(default=default)))
+    cls = dataclasses.make_dataclass(name, fields, bases=(BaseConfiguration,), namespace=namespace or {})
+    cls.__doc__ = doc
+    cls.__module__ = __name__
+    return cls
 
 
-@dataclass
-class SamplingConfiguration(BaseConfiguration):
-    """Sampling parameters for reactive planner."""
-    sampling_method: int = 1
-    longitudinal_mode: str = "velocity_keeping"
-    num_sampling_levels: int = 4
-    t_min: float = 0.4
-    v_min: float = 0
-    v_max: float = 0
-    s_min: float = -1
-    s_max: float = 1
-    d_min: float = -3
-    d_max: float = 3
+_DT, _STEPS = 0.1, 60
+
+PlanningConfiguration = _make("PlanningConfiguration", "Planning parameters for reactive planner.", [
+    ("dt", float, _DT),                                   # planner time step [s]
+    ("time_steps_computation", int, _STEPS),              # horizon = dt * time_steps_computation
+    ("planning_horizon", float, _DT * _STEPS),
+    ("replanning_frequency", int, 3),                     # re-plan every n time steps
+    ("continuous_collision_check", bool, False),
+    ("factor", int, 1),                                   # planner step / scenario step for collision time indices
+    ("low_vel_mode_threshold", float, 4.0),               # [m/s] below: lateral motion sampled over arc length
+    ("constraints_to_check", List[str], ["velocity", "acceleration", "kappa", "kappa_dot", "yaw_rate"]),
+    ("standstill_lookahead", int, 10),
+])
+
+SamplingConfiguration = _make("SamplingConfiguration", "Sampling parameters for reactive planner.", [
+    ("sampling_method", int, 1),                          # 1 fixed intervals, 2 corridor sampling (CommonRoad-Reach)
+    ("longitudinal_mode", str, "velocity_keeping"),       # or "stopping"
+    ("num_sampling_levels", int, 4),
+    ("t_min", float, 0.4),
+    ("v_min", float, 0), ("v_max", float, 0),
+    ("s_min", float, -1), ("s_max", float, 1),
+    ("d_min", float, -3), ("d_max", float, 3),
+])
+
+DebugConfiguration = _make("DebugConfiguration", "Parameters specifying debug-related information.", [
+    ("save_plots", bool, False), ("save_config", bool, False), ("show_plots", bool, False),
+    ("draw_ref_path", bool, True), ("draw_planning_problem", bool, True), ("draw_icons", bool, False),
+    ("draw_traj_set", bool, False),
+    ("logging_level", str, "INFO"),
+    ("multiproc", bool, True), ("num_workers", int, 6),   # accepted, ignored (see module docstring)
+])
 
 
-@dataclass
-class DebugConfiguration(BaseConfiguration):
-    """Parameters specifying debug-related information."""
-    save_plots: bool = False
-    save_config: bool = False
-    show_plots: bool = False
-    draw_ref_path: bool = True
-    draw_planning_problem: bool = True
-    draw_icons: bool = False
-    draw_traj_set: bool = False
-    logging_level: str = "INFO"
-    multiproc: bool = True
-    num_workers: int = 6
+def _vehicle_post_init(self):
+    vp = self.vehicle_parameters or vehicle_parameters_from_type(self.id_type_vehicle)
+    self.vehicle_parameters = vp
+    derived = {"length": vp.l, "width": vp.w, "wb_front_axle": vp.a, "wb_rear_axle": vp.b,
+               "a_max": vp.longitudinal.a_max, "v_switch": vp.longitudinal.v_switch,
+               "delta_min": vp.steering.min, "delta_max": vp.steering.max,
+               "v_delta_min": vp.steering.v_min, "v_delta_max": vp.steering.v_max, "wheelbase": vp.a + vp.b}
+    for key, value in derived.items():
+        if getattr(self, key) is None:        # explicit values (e.g. from YAML) win
+            setattr(self, key, value)
+    self.kappa_max = np.tan(self.delta_max) / self.wheelbase
 
 
-@dataclass
-class VehicleConfiguration(BaseConfiguration):
-    """Class to store vehicle configurations"""
-    id_type_vehicle: int = 2
-    vehicle_parameters: Any = None
-    length: float = None
-    width: float = None
-    wb_front_axle: float = None
-    wb_rear_axle: float = None
-    a_max: float = None
-    v_switch: float = None
-    delta_min: float = None
-    delta_max: float = None
-    v_delta_min: float = None
-    v_delta_max: float = None
-    wheelbase: float = None
-
-    def __post_init__(self):
-        vp = self.vehicle_parameters or vehicle_parameters_from_type(self.id_type_vehicle)
-        self.vehicle_parameters = vp
-        derived = dict(length=vp.l, width=vp.w, wb_front_axle=vp.a, wb_rear_axle=vp.b,
-                       a_max=vp.longitudinal.a_max, v_switch=vp.longitudinal.v_switch, delta_min=vp.steering.min,
-                       delta_max=vp.steering.max, v_delta_min=vp.steering.v_min, v_delta_max=vp.steering.v_max,
-                       wheelbase=vp.a + vp.b)
-        for name, value in derived.items():
-            if getattr(self, name) is None:
-                setattr(self, name, value)
-        self.kappa_max = np.tan(self.delta_max) / self.wheelbase
+VehicleConfiguration = _make("VehicleConfiguration", "Class to store vehicle configurations", [
+    ("id_type_vehicle", int, 2), ("vehicle_parameters", Any, None),
+    ("length", float, None), ("width", float, None),
+    ("wb_front_axle", float, None), ("wb_rear_axle", float, None),
+    ("a_max", float, None), ("v_switch", float, None),
+    ("delta_min", float, None), ("delta_max", float, None),
+    ("v_delta_min", float, None), ("v_delta_max", float, None),
+    ("wheelbase", float, None),
+], namespace={"__post_init__": _vehicle_post_init})
 
 
-@dataclass
-class GeneralConfiguration(BaseConfiguration):
-    """General parameters for evaluations."""
-    path_scenarios: str = "example_scenarios/"
-    path_output: str = "output/"
-    path_logs: str = "output/logs/"
-    path_pickles: str = "output/pickles/"
-    path_scenario: Optional[str] = None
-    name_scenario: Optional[str] = None
-
-    def set_path_scenario(self, scenario_name: str):
-        self.path_scenario = os.path.join(self.path_scenarios, scenario_name)
+def _set_path_scenario(self, scenario_name: str):
+    self.path_scenario = os.path.join(self.path_scenarios, scenario_name)
 
 
-@dataclass
-class ReactivePlannerConfiguration(BaseConfiguration):
-    """Configuration parameters for reactive planner."""
-    vehicle: VehicleConfiguration = field(default_factory=VehicleConfiguration)
-    planning: PlanningConfiguration = field(default_factory=PlanningConfiguration)
-    sampling: SamplingConfiguration = field(default_factory=SamplingConfiguration)
-    debug: DebugConfiguration = field(default_factory=DebugConfiguration)
-    general: GeneralConfiguration = field(default_factory=GeneralConfiguration)
+GeneralConfiguration = _make("GeneralConfiguration", "General parameters for evaluations.", [
+    ("path_scenarios", str, "example_scenarios/"), ("path_output", str, "output/"),
+    ("path_logs", str, "output/logs/"), ("path_pickles", str, "output/pickles/"),
+    ("path_scenario", Optional[str], None), ("name_scenario", Optional[str], None),
+], namespace={"set_path_scenario": _set_path_scenario})
 
-    def __post_init__(self):
-        self.scenario = None
-        self.planning_problem = None
-        self.planning_problem_set = None
 
-    @property
-    def name_scenario(self) -> str:
-        return self.general.name_scenario
+def _root_post_init(self):
+    self.scenario = None
+    self.planning_problem = None
+    self.planning_problem_set = None
 
-    def update(self, scenario=None, planning_problem=None, idx_planning_problem: Optional[int] = None):
-        """Updates configuration based on the given attributes (reference :265-290)."""
-        self.scenario = scenario
-        self.planning_problem = planning_problem
-        if scenario is None and planning_problem is None:
-            try:
-                from commonroad_rp_b200.utility.general import load_scenario_and_planning_problem
-                self.scenario, self.planning_problem, self.planning_problem_set = \
-                    load_scenario_and_planning_problem(self.general.path_scenario, idx_planning_problem)
-            except FileNotFoundError:
-                warnings.warn(f"<ReactivePlannerConfiguration.update()>: No scenario .xml file found at "
-                              f"path_scenario = {self.general.path_scenario}")
-        assert self.scenario is not None, "<Configuration.update()>: no scenario has been specified"
+
+def _root_update(self, scenario=None, planning_problem=None, idx_planning_problem: Optional[int] = None):
+    """Attach scenario / planning problem; with neither given they are read from ``general.path_scenario``
+    (needs commonroad-io) -- reference :265-290."""
+    self.scenario, self.planning_problem = scenario, planning_problem
+    if scenario is None and planning_problem is None:
+        try:
+            from commonroad_rp_b200.utility.general import load_scenario_and_planning_problem
+            self.scenario, self.planning_problem, self.planning_problem_set = \
+                load_scenario_and_planning_problem(self.general.path_scenario, idx_planning_problem)
+        except FileNotFoundError:
+            warnings.warn(f"<ReactivePlannerConfiguration.update()>: No scenario .xml file found at "
+                          f"path_scenario = {self.general.path_scenario}")
+    assert self.scenario is not None, "<Configuration.update()>: no scenario has been specified"
+
+
+def _sub(cls):
+    return dataclasses.field(default_factory=cls)
+
+
+ReactivePlannerConfiguration = dataclasses.make_dataclass(
+    "ReactivePlannerConfiguration",
+    [("vehicle", VehicleConfiguration, _sub(VehicleConfiguration)),
+     ("planning", PlanningConfiguration, _sub(PlanningConfiguration)),
+     ("sampling", SamplingConfiguration, _sub(SamplingConfiguration)),
+     ("debug", DebugConfiguration, _sub(DebugConfiguration)),
+     ("general", GeneralConfiguration, _sub(GeneralConfiguration))],
+    bases=(BaseConfiguration,),
+    namespace={"__post_init__": _root_post_init, "update": _root_update,
+               "name_scenario": property(lambda self: self.general.name_scenario)})
+ReactivePlannerConfiguration.__doc__ = "Configuration parameters for reactive planner."
+ReactivePlannerConfiguration.__module__ = __name__

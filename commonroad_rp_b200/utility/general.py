@@ -1,44 +1,48 @@
-"""Host glue of the reference's utility/general.py (scenario loading, goal velocity, orientation shift)."""
+"""Small host helpers of the reference's ``utility/general.py``: scenario loading (delegated to
+commonroad-io), the desired velocity implied by a planning problem, orientation folding."""
 from typing import Optional
 
 import numpy as np
 
+_TWO_PI = 2 * np.pi
+
 
 def load_scenario_and_planning_problem(path_scenario, idx_planning_problem: Optional[int] = None):
-    """CommonRoad XML -> (scenario, planning problem, planning problem set); needs commonroad-io
-    (reference utility/general.py:11-29)."""
+    """(scenario, planning problem, planning problem set) from a CommonRoad XML file.  Needs commonroad-io;
+    without it pass scenario objects or a ``collision.CollisionChecker`` to the planner directly."""
     try:
         from commonroad.common.file_reader import CommonRoadFileReader
-    except ImportError as e:
-        raise ImportError("loading CommonRoad XML needs commonroad-io; pass scenario objects / a "
-                          "collision.CollisionChecker to the planner instead") from e
-    scenario, pps = CommonRoadFileReader(path_scenario).open()
-    if idx_planning_problem is not None:
+    except ImportError as exc:
+        raise ImportError("reading CommonRoad XML requires commonroad-io") from exc
+    scenario, problem_set = CommonRoadFileReader(path_scenario).open()
+    if idx_planning_problem is None:
+        problem = next(iter(problem_set.planning_problem_dict.values()))
+    else:
         try:
-            pp = pps.find_planning_problem_by_id(idx_planning_problem)
+            problem = problem_set.find_planning_problem_by_id(idx_planning_problem)
         except KeyError:
             raise KeyError(f"<ReactivePlannerConfiguration.update()>:"
                            f"Planning Problem with ID: {idx_planning_problem} does not exist!")
-    else:
-        pp = list(pps.planning_problem_dict.values())[0]
-    return scenario, pp, pps
+    return scenario, problem, problem_set
 
 
 def retrieve_desired_velocity_from_pp(planning_problem):
-    """average goal velocity, else the initial velocity (reference utility/general.py:32-46)"""
+    """Mid-point of the goal velocity interval (half the upper bound if the interval starts at 0); the
+    initial velocity when the goal names no velocity (reference utility/general.py:32-46)."""
     goal_state = planning_problem.goal.state_list[0]
-    if hasattr(goal_state, 'velocity'):
-        if goal_state.velocity.start > 0:
-            return (goal_state.velocity.start + goal_state.velocity.end) / 2
-        return goal_state.velocity.end / 2
-    return planning_problem.initial_state.velocity
+    if not hasattr(goal_state, 'velocity'):
+        return planning_problem.initial_state.velocity
+    lo, hi = goal_state.velocity.start, goal_state.velocity.end
+    return (lo + hi) / 2 if lo > 0 else hi / 2
 
 
 def shift_orientation(trajectory, interval_start=-np.pi, interval_end=np.pi):
-    """fold every state's orientation into [interval_start, interval_end] (reference utility/general.py:49-55)"""
+    """Fold the orientation of every state into [interval_start, interval_end] by whole turns."""
     for state in trajectory.state_list:
-        while state.orientation < interval_start:
-            state.orientation += 2 * np.pi
-        while state.orientation > interval_end:
-            state.orientation -= 2 * np.pi
+        theta = state.orientation
+        while theta < interval_start:
+            theta += _TWO_PI
+        while theta > interval_end:
+            theta -= _TWO_PI
+        state.orientation = theta
     return trajectory
