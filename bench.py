@@ -250,6 +250,50 @@ def replanning_latency_port(name="ZAM_Over-1_1", max_cycles=6):
             "scenario": "%s, N=%d" % (name, meta["N"]), "api": "oracle port, single process"}
 
 
+def scenario_batch_rate(device, stream_handle, n_scenarios=32, cycles=3):
+    """BASELINE configs[4] shape on one rank: independent seeded scenarios, default level-3 grid at N = 60
+    (29 t x 17 v x 18 d = 8 874 candidates each), one resident device context per scenario, launches
+    enqueued back to back (commonroad_rp_b200.parallel.ScenarioBatch).  Returns candidates/s."""
+    import torch
+    from commonroad_rp_b200 import collision
+    from commonroad_rp_b200._lib import Engine
+    from commonroad_rp_b200.parallel import ScenarioBatch
+    from commonroad_rp_b200.sampling import FixedIntervalSampling, VelocitySampling
+    from commonroad_rp_b200.utility import synthetic
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    cfg = ReactivePlannerConfiguration()
+    keys = ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes", "boundary_tris")
+    batch = ScenarioBatch(device, stream_handle)
+    cycle, n_cand = [], 0
+    for sid in range(n_scenarios):
+        scn, s_dot0, d0 = synthetic.scenario_seeded(sid)
+        co = CoordinateSystem(scn["ref_path"])
+        batch.add_scenario(cfg.vehicle, co, collision.checker_from_arrays(**{k: scn[k] for k in keys}))
+        fs = FixedIntervalSampling(cfg)
+        lo = max(0, s_dot0 - 0.125 * fs.horizon * cfg.vehicle.a_max)
+        fs.samples_v = VelocitySampling(lo, max(lo + 5.0, s_dot0 + 2), 4)
+        t, lon, d = fs.sample_grid(3, [d0, 0.0, 0.0], "velocity_keeping")
+        s0 = float(co.ref_pos[10])
+        j = int(np.argmax(co.ref_pos > s0)) - 1
+        inputs = Engine.make_inputs([s0, s_dot0, 0.0], [d0, 0.0, 0.0], float(co.ref_theta[j]), 0, s_dot0 < 4.0,
+                                    "velocity_keeping", N_HORIZON, DT, desired_speed=s_dot0)
+        cycle.append((inputs, t, lon, d))
+        n_cand += len(t) * len(lon) * len(d)
+    batch.plan(cycle)                                   # warm-up (allocations, geometry)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(cycles):
+        res = batch.plan(cycle)
+    torch.cuda.synchronize()
+    dt_s = (time.perf_counter() - t0) / cycles
+    n_win = sum(1 for r in res if r.winner >= 0)
+    batch.close()
+    return {"value": n_cand / dt_s, "unit": UNIT, "scenarios": n_scenarios, "candidates_per_scenario": n_cand // n_scenarios,
+            "ms_per_cycle_of_all_scenarios": 1e3 * dt_s, "scenarios_with_winner": n_win,
+            "note": "wall clock incl. H2D of every scenario's inputs and D2H of every result (host buffers)"}
+
+
 def cpu_port_rate(work, stride, workers, repeats=1):
     """The oracle port (reference algorithm restated, oracle/rp_oracle.py) on a sub-grid of the same
     workload: every ``stride``-th v and d sample.  Returns (candidates/s, description, seconds)."""
@@ -517,6 +561,7 @@ def main():
                                         "frac": gbs / peaks.get("hbm_gbs"), "traffic": None, "kernel_ms": full,
                                         "peak_source": peak_kind + " (MEASURED_PEAKS.json)"}
     line["p50_replanning_cycle_ms"] = replanning_latency_b200()
+    line["scenario_batch"] = scenario_batch_rate(local_rank, stream.cuda_stream)
     if not args.no_cpu_baseline:
         line["p50_replanning_cycle_ms"]["cpu_port"] = replanning_latency_port()
         cores = 1

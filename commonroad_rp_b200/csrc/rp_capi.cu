@@ -125,7 +125,11 @@ struct rp_ctx {
     int index_geom_np1 = -1, index_geom_count = -1;
     long long index_geom_tables = -1;
     double ref_inv_step = 1.0, ps_inv_step = 1.0;
-    int smem_granted[2] = {0, 0};
+
+    // "copy done" events of the pinned staging buffers: a buffer is rewritten only after ITS last copy finished
+    // (waiting on the whole stream would serialise back-to-back cycles of many contexts sharing one stream)
+    cudaEvent_t ev_stage = nullptr, ev_segs = nullptr, ev_result = nullptr;
+    bool stage_pending = false, segs_pending = false;
 
     static constexpr int kEvRing = 64;
     cudaEvent_t ev_ring[kEvRing][5] = {};
@@ -309,7 +313,9 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
     if (G.stage_ref) G.smem += ref_bytes;
     int occ = 0;
     // the attribute is a per-function maximum: only ever raise it (main and index launches share the kernel)
-    int& granted = ctx->smem_granted[G.big ? 1 : 0];
+    // (per device, shared by all contexts of the process: the attribute belongs to the function, not the context)
+    static int g_granted[64][2] = {};
+    int& granted = g_granted[ctx->device & 63][G.big ? 1 : 0];
     if ((int)G.smem > granted) {
         if (G.big) RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         else RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
@@ -395,9 +401,11 @@ int prepare_main_geometry(rp_ctx* ctx, int first, int count) {
     const size_t bytes = segs.size() * sizeof(rp::Segment);
     if (int rc = ctx->h_segs.ensure(bytes)) return rc;
     if (int rc = ctx->d_segs.ensure(bytes)) return rc;
-    RP_CUDA(cudaStreamSynchronize(ctx->stream));        // a previous launch may still read the staging copy
+    if (ctx->segs_pending) RP_CUDA(cudaEventSynchronize(ctx->ev_segs));      // the previous copy of this buffer
     std::memcpy(ctx->h_segs.p, segs.data(), bytes);
     RP_CUDA(cudaMemcpyAsync(ctx->d_segs.p, ctx->h_segs.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RP_CUDA(cudaEventRecord(ctx->ev_segs, ctx->stream));
+    ctx->segs_pending = true;
     ctx->segs_dirty = false;
     return RP_OK;
 }
@@ -480,6 +488,9 @@ int rp_ctx_create(int device, void* stream, rp_ctx** out) {
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (auto& set : ctx->ev_ring)
         for (auto& e : set) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_segs, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_result, cudaEventDisableTiming);
     if (ctx->d_result.ensure(sizeof(rp::PlanResultDev)) || ctx->h_result.ensure(sizeof(rp::PlanResultDev)) ||
         ctx->d_index.ensure(sizeof(int))) {
         rp_ctx_destroy(ctx);
@@ -505,6 +516,8 @@ int rp_ctx_destroy(rp_ctx* ctx) {
     for (auto& set : ctx->ev_ring)
         for (auto& e : set)
             if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->ev_stage, ctx->ev_segs, ctx->ev_result})
+        if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RP_OK;
@@ -615,13 +628,17 @@ int rp_grid_upload(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double*
     const size_t bytes = ctx->off_len + (size_t)n_t * sizeof(int);
     if (int rc = ctx->h_stage.ensure(bytes)) return rc;
     if (int rc = ctx->d_samples.ensure(bytes)) return rc;
-    RP_CUDA(cudaStreamSynchronize(ctx->stream));       // staging buffer may still be in flight
+    if (ctx->stage_pending) RP_CUDA(cudaEventSynchronize(ctx->ev_stage));     // last copy out of this buffer
     char* hs = static_cast<char*>(ctx->h_stage.p);
     if (n_t) std::memcpy(hs + ctx->off_t, t, (size_t)n_t * sizeof(double));
     if (n_lon) std::memcpy(hs + ctx->off_lon, lon, (size_t)n_lon * sizeof(double));
     if (n_d) std::memcpy(hs + ctx->off_d, d, (size_t)n_d * sizeof(double));
     if (n_t) std::memcpy(hs + ctx->off_len, traj_len, (size_t)n_t * sizeof(int));
-    if (bytes) RP_CUDA(cudaMemcpyAsync(ctx->d_samples.p, hs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) {
+        RP_CUDA(cudaMemcpyAsync(ctx->d_samples.p, hs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaEventRecord(ctx->ev_stage, ctx->stream));
+        ctx->stage_pending = true;
+    }
     ctx->h_traj_len.assign(traj_len, traj_len + n_t);
     ctx->segs_dirty = true;
     ctx->have_inputs = true;
@@ -715,7 +732,8 @@ int rp_grid_result(rp_ctx* ctx, rp_plan_result* out) {
     if (!out) return fail(RP_ERR_ARG, "null result");
     if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
     RP_CUDA(cudaMemcpyAsync(ctx->h_result.p, ctx->d_result.p, sizeof(rp::PlanResultDev), cudaMemcpyDeviceToHost, ctx->stream));
-    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    RP_CUDA(cudaEventRecord(ctx->ev_result, ctx->stream));
+    RP_CUDA(cudaEventSynchronize(ctx->ev_result));
     *out = static_cast<rp::PlanResultDev*>(ctx->h_result.p)->r;
     return RP_OK;
 }

@@ -534,7 +534,6 @@ fused_kernel(const __grid_constant__ PlanParams P) {
             const unsigned* fl = s_flags_all + (size_t)tid * F_WORDS;
             const unsigned st2 = fl[F_STATE];
             if (st2 & S_VALID) {
-                const double* sc = slots + (size_t)tid * per_slot;
                 int status, reason = R_NONE, step = -1;
                 double cost = __longlong_as_double(0x7ff8000000000000LL);   // NaN
                 const unsigned pre2 = fl[F_PRE], bad2 = fl[F_BAD], pbad2 = fl[F_PBAD];

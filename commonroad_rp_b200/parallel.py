@@ -36,3 +36,59 @@ def global_argmin(engine, rec: torch.Tensor, world: int, group=None):
     engine.count_colliders_before_dev(winner.data_ptr(), before.data_ptr())
     dist.all_reduce(before, group=group)
     return winner, totals, before
+
+
+class ScenarioBatch:
+    """Independent scenarios evaluated back to back (BASELINE config 5: scenario-major sharding, no exchange
+    on the data path).  Every scenario keeps its own device context (reference tables, obstacle tables,
+    verdict buffers stay resident); a replanning cycle uploads all inputs, enqueues all launches without
+    any host synchronisation in between, and only then collects the results, so the kernels of consecutive
+    scenarios run back to back on the stream while the host is already enqueueing the next ones."""
+
+    def __init__(self, device=None, stream=None):
+        from commonroad_rp_b200._device import current_device_and_stream
+        if device is None or stream is None:
+            dev, st = current_device_and_stream()
+            device = dev if device is None else device
+            stream = st if stream is None else stream
+        self.device, self.stream = device, stream
+        self.engines = []
+
+    def add_scenario(self, vehicle, coordinate_system, collision_checker):
+        """vehicle: VehicleConfiguration; coordinate_system: CoordinateSystem; collision_checker:
+        collision.CollisionChecker.  Returns the scenario's index."""
+        from commonroad_rp_b200._lib import Engine
+        eng = Engine(self.device, self.stream)
+        eng.set_vehicle(vehicle.length, vehicle.width, vehicle.wb_rear_axle, vehicle.wheelbase, vehicle.a_max,
+                        vehicle.v_switch, vehicle.delta_max, vehicle.v_delta_max, vehicle.kappa_max)
+        tb = coordinate_system.device_tables()
+        eng.set_reference(tb["ref_pos"], tb["ref_theta"], tb["ref_curv"], tb["ref_curv_d"], tb["path_xy"],
+                          tb["path_s"], tb["path_normals"], tb["proj_limit"])
+        collision_checker.upload(eng)
+        self.engines.append(eng)
+        return len(self.engines) - 1
+
+    def __len__(self):
+        return len(self.engines)
+
+    def upload(self, cycle_inputs):
+        """cycle_inputs[k] = (rp_plan_inputs, t, lon, d) of scenario k."""
+        for eng, (inputs, t, lon, d) in zip(self.engines, cycle_inputs):
+            eng.grid_upload(inputs, t, lon, d)
+
+    def launch(self):
+        for eng in self.engines:
+            eng.grid_launch()
+
+    def results(self):
+        return [eng.grid_result() for eng in self.engines]
+
+    def plan(self, cycle_inputs):
+        self.upload(cycle_inputs)
+        self.launch()
+        return self.results()
+
+    def close(self):
+        for eng in self.engines:
+            eng.close()
+        self.engines = []

@@ -308,3 +308,45 @@ def test_lazy_collision_mode_is_exact_for_reference_outputs():
         others = ~unchecked
         assert np.array_equal(status_f[others], status_l[others])
         eng.close()
+
+
+def test_scenario_batch_equals_individual_plans():
+    """config-5 shape: independent seeded scenarios evaluated back to back give what each gives alone"""
+    from commonroad_rp_b200 import _lib, collision
+    from commonroad_rp_b200.parallel import ScenarioBatch
+    from commonroad_rp_b200.utility.config import VehicleConfiguration
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    veh = VehicleConfiguration()
+    batch = ScenarioBatch()
+    cycle, single = [], []
+    keys = ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes", "boundary_tris")
+    for sid in range(6):
+        scn, s_dot0, d0 = synthetic.scenario_seeded(sid)
+        co = CoordinateSystem(scn["ref_path"])
+        cc = collision.checker_from_arrays(**{k: scn[k] for k in keys})
+        batch.add_scenario(veh, co, cc)
+        lo = max(0.0, s_dot0 - 0.125 * 2.0 * veh.a_max)
+        t, lon, dset = H.level_sets(2, 0.4, 2.0, 0.1, lo, max(lo + 5.0, s_dot0 + 2))
+        d = [float(x) for x in dset.union({d0})]
+        s0 = float(co.ref_pos[10])
+        j = int(np.argmax(co.ref_pos > s0)) - 1
+        inputs = _lib.Engine.make_inputs([s0, s_dot0, 0.0], [d0, 0.0, 0.0], float(co.ref_theta[j]), 0, s_dot0 < 4.0,
+                                         "velocity_keeping", 20, 0.1, desired_speed=s_dot0)
+        cycle.append((inputs, t, lon, d))
+        eng = _lib.Engine(0)
+        eng.set_vehicle(veh.length, veh.width, veh.wb_rear_axle, veh.wheelbase, veh.a_max, veh.v_switch, veh.delta_max,
+                        veh.v_delta_max, veh.kappa_max)
+        tb = co.device_tables()
+        eng.set_reference(tb["ref_pos"], tb["ref_theta"], tb["ref_curv"], tb["ref_curv_d"], tb["path_xy"], tb["path_s"],
+                          tb["path_normals"], tb["proj_limit"])
+        cc.upload(eng)
+        r = eng.plan_grid(inputs, t, lon, d)
+        single.append((r.winner, r.winner_cost, r.n_infeasible_kinematics, r.n_infeasible_collision))
+        eng.close()
+    for rep in range(2):                      # second cycle reuses the resident tables and staging buffers
+        got = [(r.winner, r.winner_cost, r.n_infeasible_kinematics, r.n_infeasible_collision) for r in batch.plan(cycle)]
+        assert [g[0] for g in got] == [s[0] for s in single]
+        assert all(g[2:] == s[2:] for g, s in zip(got, single))
+        assert all((g[1] == s[1]) or (np.isnan(g[1]) and np.isnan(s[1])) for g, s in zip(got, single))
+    assert len({g[0] for g in got}) > 1       # the scenarios really differ
+    batch.close()
