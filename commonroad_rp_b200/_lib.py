@@ -21,6 +21,7 @@ ST_FEASIBLE, ST_KINEMATIC, ST_COLLISION, ST_FILTERED, ST_UNCHECKED = 0, 1, 2, 3,
 COLLISION_OFF, COLLISION_ALL, COLLISION_LAZY = 0, 1, 2
 VELOCITY_KEEPING, STOPPING = 0, 1
 COST_DEFAULT, COST_FAILSAFE, COST_NONE = 0, 1, 2
+KERNEL_AUTO, KERNEL_STEP_PARALLEL, KERNEL_CANDIDATE_MAJOR = 0, 1, 2
 
 
 class RpError(RuntimeError):
@@ -72,6 +73,7 @@ SIGNATURES = {
     "rp_grid_result": (C.c_int, [C.c_void_p, C.POINTER(PlanResult)]),
     "rp_plan_list": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _dp, _ip, _bp, C.POINTER(PlanResult)]),
     "rp_set_candidate_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "rp_ctx_set_kernel_policy": (C.c_int, [C.c_void_p, C.c_int]),
     "rp_export_record_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rp_count_colliders_before_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rp_fetch_states": (C.c_int, [C.c_void_p, C.c_int, _dp]),
@@ -250,6 +252,10 @@ class Engine:
                                            _p(tl, _ip), _p(sk, _bp) if sk is not None else C.cast(None, _bp),
                                            C.byref(res)))
         return res
+
+    def set_kernel_policy(self, policy):
+        """KERNEL_AUTO / KERNEL_STEP_PARALLEL / KERNEL_CANDIDATE_MAJOR (identical results, different schedule)."""
+        self._check(self._lib.rp_ctx_set_kernel_policy(self._ctx, int(policy)))
 
     def set_candidate_range(self, first, count):
         self._check(self._lib.rp_set_candidate_range(self._ctx, int(first), int(count)))

@@ -121,7 +121,10 @@ struct rp_ctx {
     long long tables_version = 0;
     DevBuf d_segs, d_segs_index, d_argmin, d_best;
     PinBuf h_segs, h_segs_index;
-    Geometry main_geom{}, index_geom{};
+    Geometry main_geom{}, index_geom{}, cand_geom{};
+    bool main_is_cand = false;          // geometry in main_geom/d_segs belongs to the candidate-major kernel
+    int kernel_policy = RP_KERNEL_AUTO;
+    DevBuf d_work;
     int index_geom_np1 = -1, index_geom_count = -1;
     long long index_geom_tables = -1;
     double ref_inv_step = 1.0, ps_inv_step = 1.0;
@@ -328,6 +331,65 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
     return RP_OK;
 }
 
+// Launch geometry of the candidate-major kernel (rp_cand.cuh): segments sorted by traj_len, longest first,
+// cut into chunks of 32 candidates that the warps of a persistent grid draw from a counter.
+int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, int n_acc_rows) {
+    static const int env_stage_ref = std::getenv("RP_CAND_STAGE_REF") ? std::atoi(std::getenv("RP_CAND_STAGE_REF")) : 0;
+    std::stable_sort(segs.begin(), segs.end(), [](const rp::Segment& a, const rp::Segment& b) { return a.tl > b.tl; });
+    G.big = false;
+    G.threads = RP_CAND_THREADS;
+    G.Cmax = 32;
+    G.n_groups = 0;
+    for (auto& sg : segs) {
+        sg.tl = std::max(1, std::min(sg.tl, Np1));
+        sg.C = 32;
+        sg.g_begin = G.n_groups;
+        G.n_groups += (std::max(0, sg.k_end - sg.k_begin) + 31) / 32;
+    }
+    G.n_segs = (int)segs.size();
+    const size_t budget = (size_t)ctx->max_smem_optin;
+    const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
+    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * rp::kDynFields * sizeof(double);
+    const size_t acc_bytes = (size_t)n_acc_rows * 8 * G.threads * sizeof(double);
+    const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 64;
+    G.stage_dyn = (ctx->obs.n_dyn > 0 && dyn_bytes <= 32 * 1024) ? 1 : 0;
+    G.smem = acc_bytes + fixed + (G.stage_dyn ? dyn_bytes : 0);
+    G.stage_ref = (env_stage_ref && G.smem + ref_bytes <= budget / 3) ? 1 : 0;
+    if (G.stage_ref) G.smem += ref_bytes;
+    if (G.smem > budget) return fail(RP_ERR_ARG, "candidate-major kernel: shared-memory need exceeds the SM");
+    static int g_granted[64] = {};
+    int& granted = g_granted[ctx->device & 63];
+    if ((int)G.smem > granted) {
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        granted = (int)G.smem;
+    }
+    int occ = 0;
+    RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::cand_kernel<RP_CAND_THREADS>, G.threads, G.smem));
+    if (occ < 1) return fail(RP_ERR_CUDA, "candidate-major kernel does not fit on an SM");
+    const int warps_per_block = G.threads / 32;
+    G.grid = std::max(1, std::min((G.n_groups + warps_per_block - 1) / warps_per_block, occ * ctx->num_sms));
+    return RP_OK;
+}
+
+// np.sum accumulator rows of the candidate-major kernel: acceleration, lateral offset, orientation (+ velocity, + position)
+int cand_acc_rows(const rp_plan_inputs& in) {
+    if (in.cost_kind == RP_COST_NONE) return 0;
+    const bool fs = in.cost_kind == RP_COST_FAILSAFE;
+    return 3 + ((!fs && in.has_desired_speed) ? 1 : 0) + ((!fs && in.has_desired_s) ? 1 : 0);
+}
+
+// which kernel evaluates the main launch (the winner-state / on-demand launches always use fused_kernel)
+bool use_cand_kernel(const rp_ctx* ctx, int count) {
+    static const int env_kernel = std::getenv("RP_KERNEL") ? std::atoi(std::getenv("RP_KERNEL")) : -1;
+    static const int env_min = std::getenv("RP_CAND_MIN") ? std::atoi(std::getenv("RP_CAND_MIN")) : 24576;
+    const int Np1 = ctx->in.N + 1;
+    if (ctx->in.want_all_states || ctx->in.draw_all || Np1 > 128) return false;     // not handled by cand_kernel
+    const int policy = env_kernel >= 0 ? env_kernel : ctx->kernel_policy;
+    if (policy == RP_KERNEL_STEP_PARALLEL) return false;
+    if (policy == RP_KERNEL_CANDIDATE_MAJOR) return true;
+    return count >= env_min;
+}
+
 void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G, const rp::Segment* d_segs) {
     P.in = ctx->in;
     P.lim.a_max = ctx->veh.a_max;
@@ -397,7 +459,11 @@ int prepare_main_geometry(rp_ctx* ctx, int first, int count) {
         segs.push_back(rp::Segment{first, first + count, Np1, 0, 0});
     }
     if (segs.empty()) segs.push_back(rp::Segment{0, 0, Np1, 0, 0});
-    if (int rc = plan_geometry(ctx, Np1, segs, ctx->main_geom)) return rc;
+    ctx->main_is_cand = use_cand_kernel(ctx, count);
+    if (ctx->main_is_cand) {
+        // (list form: one segment in list order; traj_len varies per candidate, lanes diverge on i < tl only)
+        if (int rc = plan_cand_geometry(ctx, Np1, segs, ctx->main_geom, cand_acc_rows(ctx->in))) return rc;
+    } else if (int rc = plan_geometry(ctx, Np1, segs, ctx->main_geom)) return rc;
     const size_t bytes = segs.size() * sizeof(rp::Segment);
     if (int rc = ctx->h_segs.ensure(bytes)) return rc;
     if (int rc = ctx->d_segs.ensure(bytes)) return rc;
@@ -507,7 +573,8 @@ int rp_ctx_destroy(rp_ctx* ctx) {
     for (DevBuf* b : {&ctx->d_ref, &ctx->d_obb, &ctx->d_tri, &ctx->d_cell_start, &ctx->d_cell_items, &ctx->d_dyn_box,
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all, &ctx->d_states_one,
-                      &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best})
+                      &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best,
+                      &ctx->d_work})
         b->release();
     ctx->h_stage.release();
     ctx->h_result.release();
@@ -595,6 +662,14 @@ int rp_ctx_set_obstacles(rp_ctx* ctx, int n_static, const double* static_obb, in
     ctx->h_tri.assign(tris, tris + (size_t)n_tri * 6);
     ctx->cell_size = cell_size > 0 ? cell_size : 2.0;
     ctx->obstacles_dirty = true;
+    return RP_OK;
+}
+
+int rp_ctx_set_kernel_policy(rp_ctx* ctx, int policy) {
+    if (!ctx) return fail(RP_ERR_ARG, "null context");
+    if (policy < RP_KERNEL_AUTO || policy > RP_KERNEL_CANDIDATE_MAJOR) return fail(RP_ERR_ARG, "invalid kernel policy");
+    ctx->kernel_policy = policy;
+    ctx->segs_dirty = true;
     return RP_OK;
 }
 
@@ -695,7 +770,15 @@ static int launch_plan(rp_ctx* ctx) {
             RP_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, sizeof(unsigned long long), ctx->stream));   // ~1.4e306
             P.best_bits = ctx->d_best.as<unsigned long long>();
         }
-        if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
+        if (ctx->main_is_cand) {
+            if (int rc = ctx->d_work.ensure(sizeof(int))) return rc;
+            RP_CUDA(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(int), ctx->stream));
+            P.work_counter = ctx->d_work.as<int>();
+            P.n_acc_rows = cand_acc_rows(ctx->in);
+            const Geometry& G = ctx->main_geom;
+            rp::cand_kernel<RP_CAND_THREADS><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+            RP_CUDA(cudaGetLastError());
+        } else if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
         ctx->states_all_valid = ctx->in.want_all_states != 0;
     }
     cudaEventRecord(ctx->ev[2], ctx->stream);

@@ -53,6 +53,9 @@ struct PlanParams {
     unsigned long long* best_bits;   // lazy collision mode: bit pattern of the best collision-free cost so far
     int Np1;                     // N + 1
     int stage_ref, stage_dyn;
+    // ---- candidate-major kernel (rp_cand.cuh) ----
+    int* work_counter;           // chunk dispenser (zeroed before the launch)
+    int n_acc_rows;              // np.sum accumulator rows kept in shared memory
 };
 
 __device__ __forceinline__ int pack_info(int status, int reason, int step) {

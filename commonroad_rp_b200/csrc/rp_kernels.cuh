@@ -14,6 +14,7 @@
 #include "rp_device.cuh"
 #include "rp_b200.h"
 #include "rp_fused.cuh"
+#include "rp_cand.cuh"
 
 namespace rp {
 

@@ -144,6 +144,15 @@ int rp_ctx_set_obstacles(rp_ctx* ctx, int n_static, const double* static_obb, in
                          const int32_t* dyn_t0, const int32_t* dyn_len, const double* dyn_obb,
                          int n_tri, const double* tris, double cell_size);
 
+/* Which kernel evaluates a4-a13 for the main launch.  Both give identical bits; they differ in schedule:
+ *   STEP_PARALLEL    one thread per (candidate, time step)  -- replanning-size bundles, state output, draw mode
+ *   CANDIDATE_MAJOR  one thread per candidate, sequential in time like reactive_planner.py:790-935 -- large
+ *                    bundles in select-only mode (falls back to STEP_PARALLEL for want_all_states / draw_all /
+ *                    N + 1 > 128)
+ *   AUTO             CANDIDATE_MAJOR from ~24k candidates up */
+enum rp_kernel_policy { RP_KERNEL_AUTO = 0, RP_KERNEL_STEP_PARALLEL = 1, RP_KERNEL_CANDIDATE_MAJOR = 2 };
+int rp_ctx_set_kernel_policy(rp_ctx* ctx, int policy);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* Grid form (FixedIntervalSampling.generate_trajectories_at_level, sampling.py:202-242): the three
  * ORDERED sample lists as the host's Python sets iterate them; traj_len[i] =

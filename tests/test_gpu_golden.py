@@ -46,6 +46,33 @@ def test_bundle_matches_reference_fixture(path):
     eng.close()
 
 
+@pytest.mark.parametrize("path", SYN, ids=[os.path.basename(p)[4:-4] for p in SYN])
+def test_bundle_matches_reference_fixture_candidate_major(path):
+    """the same fixtures through the candidate-major kernel (select-only mode: verdicts, costs, winner, counters)"""
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200._lib import REASON_NAMES
+    z = np.load(path)
+    prob = golden_io.unpack_problem(z)
+    eng = H.engine_for(prob)
+    g = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_CANDIDATE_MAJOR)
+    assert g["n"] == len(z["r_cost"])
+    assert np.array_equal(g["status"] == 3, ~z["r_kept"])
+    kin_ok = (g["status"] == 0) | (g["status"] == 2)
+    assert np.array_equal(kin_ok, z["r_kin_feasible"])
+    assert H.rel_err(z["r_cost"][kin_ok], g["cost"][kin_ok]) < RTOL
+    assert g["winner"] == int(z["r_winner"])
+    assert g["n_infeasible_kinematics"] == int(z["r_n_inf_kin"])
+    assert g["n_infeasible_collision"] == int(z["r_n_inf_col"])
+    for name, cnt in json.loads(str(z["r_reasons"])).items():
+        assert g["reason_counts"][REASON_NAMES.index(name)] == cnt, name
+    assert np.all(g["status"][z["r_label"] == 3] == 2)
+    if g["winner"] >= 0:
+        idx = list(z["r_state_idx"])
+        if g["winner"] in idx:
+            assert H.rel_err(z["r_states"][idx.index(g["winner"])], g["winner_states"]) < RTOL
+    eng.close()
+
+
 @pytest.mark.parametrize("path", CYC, ids=[os.path.basename(p)[4:-4] for p in CYC])
 def test_cyclic_replanning_matches_reference_fixture(path):
     from commonroad_rp_b200 import collision

@@ -51,3 +51,21 @@ def test_bundle_parity(case):
     g = H.run_engine_grid(eng, prob, want_all_states=True)
     H.assert_parity(o, g, prob, tag=str(case))
     eng.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+def test_bundle_parity_candidate_major(case):
+    """the candidate-major kernel (rp_cand.cuh; select-only mode) against the oracle, and bit-for-bit against
+    the step-parallel kernel (draw mode falls back to the step-parallel kernel by design)"""
+    from commonroad_rp_b200 import _lib
+    prob = _bundle(**case)
+    o = O.plan_grid(prob, want_states=True, full_collision=True)
+    eng = H.engine_for(prob)
+    g = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_CANDIDATE_MAJOR)
+    H.assert_parity(o, g, prob, tag="cand " + str(case))
+    g2 = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_STEP_PARALLEL)
+    assert np.array_equal(g["status"], g2["status"]) and np.array_equal(g["reason"], g2["reason"])
+    assert np.array_equal(g["step"], g2["step"])
+    assert np.array_equal(g["cost"].view(np.int64), g2["cost"].view(np.int64))       # identical bits, NaNs included
+    assert g["winner"] == g2["winner"]
+    eng.close()
