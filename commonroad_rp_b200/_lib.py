@@ -81,6 +81,7 @@ SIGNATURES = {
     "rp_fetch_coeffs": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "rp_solve_coeffs": (C.c_int, [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, _dp]),
     "rp_collide_poses": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, C.c_double, C.c_double, _bp]),
+    "rp_selftest_divide": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
     "rp_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rp_stage_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "rp_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -252,6 +253,13 @@ class Engine:
                                            _p(tl, _ip), _p(sk, _bp) if sk is not None else C.cast(None, _bp),
                                            C.byref(res)))
         return res
+
+    def selftest_divide(self, a, b):
+        """(shared-reciprocal quotient, plain a / b) as computed on the device."""
+        a, b = _f64(a).ravel(), _f64(b).ravel()
+        q1, q2 = np.empty_like(a), np.empty_like(a)
+        self._check(self._lib.rp_selftest_divide(self._ctx, len(a), _p(a, _dp), _p(b, _dp), _p(q1, _dp), _p(q2, _dp)))
+        return q1, q2
 
     def set_kernel_policy(self, policy):
         """KERNEL_AUTO / KERNEL_STEP_PARALLEL / KERNEL_CANDIDATE_MAJOR (identical results, different schedule)."""

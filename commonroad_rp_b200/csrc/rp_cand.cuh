@@ -162,6 +162,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
             continue;
         }
 
+        const LimitRcp Y = {rcp_refined(dt), rcp_refined(100000.0), rcp_refined(P.lim.wheelbase)};
         unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
         int ub = -1;
         // values of the current / last polynomial step (the extension reads them after step tl - 1)
@@ -200,11 +201,19 @@ cand_kernel(const __grid_constant__ PlanParams P) {
                 if (sv < -kEps) pre |= 2u;
 
                 // ---- orientation (:810-873) --------------------------------------------------------
+                // every division below is IEEE a / b (div_rcp, rp_device.cuh); divisors that serve several
+                // quotients get ONE refined reciprocal
                 double dp, dpp;
                 if (!low_vel) {
-                    if (sv > 0.001) dp = ddiv(dv, sv); else dp = 0.;
-                    const double ddot = da - dp * sa;
-                    if (sv > 0.001) dpp = ddiv(ddot, sv * sv); else dpp = 0.;
+                    if (sv > 0.001) {
+                        dp = div_rcp(dv, sv, rcp_refined(sv));
+                        const double ddot = da - dp * sa;
+                        const double sv2 = sv * sv;
+                        dpp = div_rcp(ddot, sv2, rcp_refined(sv2));
+                    } else {
+                        dp = 0.;
+                        dpp = 0.;
+                    }
                 } else {
                     dp = dv;
                     dpp = da;
@@ -214,8 +223,12 @@ cand_kernel(const __grid_constant__ PlanParams P) {
                 const int j0 = wrap ? R.n - 1 : ub - 1;
                 const int j1 = wrap ? 0 : ub;
                 const double p0 = R.pos[j0], p1 = R.pos[j1];
-                const double lam = ddiv(s - p0, p1 - p0);
-                const double th_ref = interpolate_angle(s, p0, p1, R.theta[j0], R.theta[j1]);
+                const double seg_len = p1 - p0;
+                const double y_seg = rcp_refined(seg_len);
+                const double lam = div_rcp(s - p0, seg_len, y_seg);
+                // interpolate_angle (utility/utils_coordinate_system.py:25-43)
+                const double th0 = R.theta[j0];
+                const double th_ref = make_valid_orientation(div_rcp((R.theta[j1] - th0) * (s - p0), seg_len, y_seg) + th0);
                 const bool carry = !(sv > 0.001) && !low_vel;
                 if (!carry) {
                     th_cl = atan(dp);                            // np.arctan2(dp, 1.0)
@@ -233,25 +246,51 @@ cand_kernel(const __grid_constant__ PlanParams P) {
                 const double oneKrD = (1 - k_r * d);
                 double cosT, tanT;
                 if (!carry) {
-                    cosT = 1.0 / sqrt(1.0 + dp * dp);
+                    const double hyp = sqrt(1.0 + dp * dp);
+                    cosT = div_rcp(1.0, hyp, rcp_refined(hyp));
                     tanT = dp;
                 } else {
                     cosT = cos(th_cl);
                     tanT = tan(th_cl);
                 }
-                const double q = ddiv(cosT, oneKrD);
+                const double y_cos = rcp_refined(cosT);
+                const double q = div_rcp(cosT, oneKrD, rcp_refined(oneKrD));
                 kappa = (dpp + (k_r * dp + k_r_d * d) * tanT) * cosT * (q * q) + q * k_r;
-                v = sv * ddiv(oneKrD, cosT);
-                a = ddiv(sa * oneKrD, cosT) + ddiv(sv * sv, cosT) * (oneKrD * tanT * (ddiv(kappa * oneKrD, cosT) - k_r) -
-                                                                    (k_r_d * d + k_r * dp));
+                v = sv * div_rcp(oneKrD, cosT, y_cos);
+                a = div_rcp(sa * oneKrD, cosT, y_cos) +
+                    div_rcp(sv * sv, cosT, y_cos) * (oneKrD * tanT * (div_rcp(kappa * oneKrD, cosT, y_cos) - k_r) -
+                                                     (k_r_d * d + k_r * dp));
 
                 // ---- limits (:971-1017) + projection (:908-917) --------------------------------------
-                const int r = check_constraints(P.lim, in.constraint_mask, dt, i, v, kappa, kap_prev, th_gl, th_prev, a);
+                const int r = check_constraints_rcp(P.lim, Y, in.constraint_mask, dt, i, v, kappa, kap_prev, th_gl, th_prev, a);
                 if (r != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)r;
-                const int ub_ps = R.same_s ? ub : upper_bound_guess(R.ps, R.n, s, P.ps_inv_step);
-                if (!project_to_cartesian(R, s, d, ub_ps, x, y)) {
-                    if (pbad == NONE) pbad = (unsigned)i;
-                    x = 0.; y = 0.;
+                {
+                    // project_to_cartesian (rp_device.cuh) with the segment reciprocal shared when both tables coincide
+                    const int n = R.n;
+                    bool ok = (s >= R.ps[0] && s <= R.ps[n - 1]) && (fabs(d) <= R.limit);
+                    if (ok) {
+                        const int ub_ps = R.same_s ? ub : upper_bound_guess(R.ps, n, s, P.ps_inv_step);
+                        int j = ub_ps - 1;
+                        if (j > n - 2) j = n - 2;
+                        double lam2;
+                        if (R.same_s && j == j0 && j1 == j0 + 1) {
+                            lam2 = lam;                          // same dividend, same divisor
+                        } else {
+                            const double sl = R.ps[j + 1] - R.ps[j];
+                            lam2 = div_rcp(s - R.ps[j], sl, rcp_refined(sl));
+                        }
+                        const double p0x = R.px[j], p0y = R.py[j];
+                        const double bx = p0x + lam2 * (R.px[j + 1] - p0x);
+                        const double by = p0y + lam2 * (R.py[j + 1] - p0y);
+                        const double n0x = R.nx[j], n0y = R.ny[j];
+                        const double nx = n0x + lam2 * (R.nx[j + 1] - n0x);
+                        const double ny = n0y + lam2 * (R.ny[j + 1] - n0y);
+                        x = bx + d * nx;
+                        y = by + d * ny;
+                    } else {
+                        if (pbad == NONE) pbad = (unsigned)i;
+                        x = 0.; y = 0.;
+                    }
                 }
                 th_prev = th_gl;
                 kap_prev = kappa;

@@ -99,7 +99,7 @@ struct rp_ctx {
     // obstacles (host copies; device tables rebuilt lazily when the vehicle or obstacles change)
     std::vector<double> h_static, h_dyn, h_tri;
     std::vector<int> h_dyn_t0, h_dyn_len;
-    double cell_size = 2.0;
+    double cell_size = 0.0;             // <= 0: automatic
     bool obstacles_dirty = true;
     DevBuf d_obb, d_tri, d_cell_start, d_cell_items, d_dyn_box, d_dyn_meta;
     rp::ObstacleTables obs{};
@@ -192,9 +192,11 @@ int build_obstacle_tables(rp_ctx* ctx) {
             gx0 = std::min(gx0, lo_x[q]); gx1 = std::max(gx1, hi_x[q]);
             gy0 = std::min(gy0, lo_y[q]); gy1 = std::max(gy1, hi_y[q]);
         }
-        double cell = ctx->cell_size > 0 ? ctx->cell_size : 2.0;
+        // default edge 0.5 m: with the ego circumradius folded into the lists, most poses on a free road land in an
+        // EMPTY cell (one 4-byte load); doubled until the table stays below 2^20 cells
+        double cell = ctx->cell_size > 0 ? ctx->cell_size : 0.5;
         double w = gx1 - gx0, h = gy1 - gy0;
-        while ((std::ceil(w / cell) + 1) * (std::ceil(h / cell) + 1) > 4.0e6) cell *= 2.0;
+        while ((std::ceil(w / cell) + 1) * (std::ceil(h / cell) + 1) > (ctx->cell_size > 0 ? 4.0e6 : 1048576.0)) cell *= 2.0;
         const int gnx = (int)std::ceil(w / cell) + 1, gny = (int)std::ceil(h / cell) + 1;
         const double inv = 1.0 / cell;
         std::vector<int> start((size_t)gnx * gny + 1, 0);
@@ -660,7 +662,7 @@ int rp_ctx_set_obstacles(rp_ctx* ctx, int n_static, const double* static_obb, in
     ctx->h_dyn_len.assign(dyn_len, dyn_len + n_dyn);
     ctx->h_dyn.assign(dyn_obb, dyn_obb + total * 5);
     ctx->h_tri.assign(tris, tris + (size_t)n_tri * 6);
-    ctx->cell_size = cell_size > 0 ? cell_size : 2.0;
+    ctx->cell_size = cell_size > 0 ? cell_size : 0.0;
     ctx->obstacles_dirty = true;
     return RP_OK;
 }
@@ -996,6 +998,40 @@ int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time
     rp::collide_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dp.as<double>(), dt.as<int>(), half_length,
                                                                  half_width, r_q, ctx->obs, dh.as<uint8_t>());
     cudaMemcpyAsync(hit, dh.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e));
+    return RP_OK;
+}
+
+namespace {
+__global__ void divide_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ q_shared,
+                              double* __restrict__ q_plain) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    q_shared[g] = rp::div_rcp(a[g], b[g], rp::rcp_refined(b[g]));
+    q_plain[g] = a[g] / b[g];
+}
+}  // namespace
+
+int rp_selftest_divide(rp_ctx* ctx, int n, const double* a, const double* b, double* q_shared, double* q_plain) {
+    if (int rc = bind(ctx)) return rc;
+    if (n < 0) return fail(RP_ERR_ARG, "negative count");
+    if (n == 0) return RP_OK;
+    if (!a || !b || !q_shared || !q_plain) return fail(RP_ERR_ARG, "null array");
+    DevBuf da, db, d1, d2;
+    int rc = RP_OK;
+    auto cleanup = [&]() { da.release(); db.release(); d1.release(); d2.release(); };
+    const size_t bytes = (size_t)n * sizeof(double);
+    if ((rc = da.ensure(bytes)) || (rc = db.ensure(bytes)) || (rc = d1.ensure(bytes)) || (rc = d2.ensure(bytes))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemcpyAsync(da.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    divide_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, da.as<double>(), db.as<double>(), d1.as<double>(), d2.as<double>());
+    cudaMemcpyAsync(q_shared, d1.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(q_plain, d2.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e));

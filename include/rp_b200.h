@@ -139,7 +139,8 @@ int rp_ctx_set_reference(rp_ctx* ctx, int n_pts, const double* ref_pos, const do
  *   static_obb[n_static][5]   = cx, cy, theta, half_length, half_width   (static obstacles + OBB road boundary)
  *   dynamic obstacle o: time indices dyn_t0[o] .. dyn_t0[o]+dyn_len[o]-1, boxes dyn_obb[sum(len)][5] concatenated
  *   tris[n_tri][6]            = x1, y1, x2, y2, x3, y3                   (triangulated road boundary)
- * cell_size: edge of the uniform broad-phase grid over the static primitives (<= 0: default 2 m). */
+ * cell_size: edge of the uniform broad-phase grid over the static primitives (<= 0: automatic, 0.5 m or the
+ * smallest power-of-two multiple that keeps the table below 2^20 cells). */
 int rp_ctx_set_obstacles(rp_ctx* ctx, int n_static, const double* static_obb, int n_dyn,
                          const int32_t* dyn_t0, const int32_t* dyn_len, const double* dyn_obb,
                          int n_tri, const double* tris, double cell_size);
@@ -208,6 +209,10 @@ int rp_solve_coeffs(rp_ctx* ctx, int n, const int32_t* kind, const double* x0, c
  * time_idx[n]; half extents from the arguments -> hit[n] (0/1) */
 int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time_idx,
                      double half_length, double half_width, uint8_t* hit);
+
+/* self-test of the kernels' division: q_shared[i] = the shared-reciprocal form used inside the kernels,
+ * q_plain[i] = a[i] / b[i] as the compiler emits it; the two must agree bit for bit for every input */
+int rp_selftest_divide(rp_ctx* ctx, int n, const double* a, const double* b, double* q_shared, double* q_plain);
 
 /* device timing of the last rp_grid_launch stages in milliseconds: [coeff, fused, argmin, winner] */
 int rp_last_stage_ms(rp_ctx* ctx, float* ms4);

@@ -69,3 +69,30 @@ def test_bundle_parity_candidate_major(case):
     assert np.array_equal(g["cost"].view(np.int64), g2["cost"].view(np.int64))       # identical bits, NaNs included
     assert g["winner"] == g2["winner"]
     eng.close()
+
+
+def test_shared_reciprocal_division_is_ieee_division():
+    """div_rcp(a, b, rcp_refined(b)) (rp_device.cuh) == a / b bit for bit: random operands over the full exponent
+    range, the operand classes the path produces (zeros, tiny, huge, denormal, inf, nan), and numpy's own quotient"""
+    from commonroad_rp_b200._lib import Engine
+    rng = np.random.default_rng(7)
+    n = 1 << 20
+    mant = lambda: rng.uniform(1.0, 2.0, n) * rng.choice([-1.0, 1.0], n)
+    a = np.concatenate([mant() * 2.0 ** rng.integers(-60, 60, n), mant() * 2.0 ** rng.integers(-1070, 1023, n),
+                        rng.normal(size=n), rng.uniform(-100, 100, n)])
+    b = np.concatenate([mant() * 2.0 ** rng.integers(-60, 60, n), mant() * 2.0 ** rng.integers(-1070, 1023, n),
+                        rng.choice([0.1, 100000.0, 2.5789, 1.0, 3.0], n), rng.uniform(0.5, 1.0, n)])
+    special = np.array([0.0, -0.0, 5e-324, -5e-324, 2.2250738585072014e-308, 1e-300, 1e-292, 1e-291, 1.0, -1.0, 3.0, 1e300,
+                        1.7976931348623157e308, 2.0 ** 1017, 2.0 ** 1016, np.inf, -np.inf, np.nan])
+    sa, sb = np.meshgrid(special, special)
+    a = np.concatenate([a, sa.ravel()])
+    b = np.concatenate([b, sb.ravel()])
+    eng = Engine(0)
+    q1, q2 = eng.selftest_divide(a, b)
+    eng.close()
+    same = (q1.view(np.int64) == q2.view(np.int64)) | (np.isnan(q1) & np.isnan(q2))
+    assert same.all(), (a[~same][:5], b[~same][:5], q1[~same][:5], q2[~same][:5])
+    with np.errstate(all="ignore"):
+        ref = a / b
+    same = (q1.view(np.int64) == ref.view(np.int64)) | (np.isnan(q1) & np.isnan(ref))
+    assert same.all(), (a[~same][:5], b[~same][:5], q1[~same][:5], ref[~same][:5])
