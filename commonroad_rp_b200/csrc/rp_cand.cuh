@@ -33,17 +33,30 @@ namespace rp {
 // cost accumulator rows kept in shared memory: acc[(row * 8 + j) * BLOCK + tid], numpy's 8 partial sums per np.sum
 constexpr int kAccRowsMax = 5;
 
-// dynamic obstacles staged [obstacle][field][step] exactly like fused_kernel; NaN-safe form of the circle reject
-// (this kernel checks speculatively, before the kinematic verdict of the candidate is known)
-__device__ __forceinline__ bool dyn_collides_staged_safe(const ObstacleTables& O, const double* __restrict__ stage,
-                                                         int Np1, int step, int tidx, double cx, double cy, double ca,
-                                                         double sa, double ahl, double ahw) {
-    for (int o = 0; o < O.n_dyn; ++o) {
-        const double* row = stage + (size_t)o * kDynFields * Np1 + step;
-        const double dx = row[0] - cx, dy = row[Np1] - cy;
-        if (!(dx * dx + dy * dy <= row[2 * Np1])) continue;
-        const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + (tidx - O.dyn_t0[o])) * kBoxStride;
-        if (obb_obb_overlap(cx, cy, ca, sa, ahl, ahw, b)) return true;
+// Dynamic obstacles of every time step staged as single-precision bounding circles, rows [step][obstacle] of
+// (cx, cy, squared reach, -) relative to the obstacle-table origin: all lanes of a warp are at the same step, so a row
+// is a shared-memory broadcast.  The pre-reject is conservative (reach inflated by the fp32 rounding bound,
+// build_obstacle_tables) and branch-free over the obstacles -- the circle tests of one step are independent
+// instructions, not a serial chain; survivors go to the exact fp64 SAT, which alone decides a hit.
+// An obstacle absent at a step is parked at 1e30 with zero reach (inf <= 0 is false).
+__device__ __forceinline__ bool dyn_collides_f32(const ObstacleTables& O, const float4* __restrict__ row, int tidx,
+                                                 double cx, double cy, double ca, double sa, double ahl, double ahw) {
+    const float ex = (float)(cx - O.org_x), ey = (float)(cy - O.org_y);
+    for (int base = 0; base < O.n_dyn; base += 32) {
+        const int cnt = min(32, O.n_dyn - base);
+        unsigned mask = 0u;
+#pragma unroll 8
+        for (int o = 0; o < cnt; ++o) {
+            const float4 r = row[base + o];
+            const float dx = r.x - ex, dy = r.y - ey;
+            if (dx * dx + dy * dy <= r.z) mask |= 1u << o;
+        }
+        while (mask) {
+            const int o = base + __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + (tidx - O.dyn_t0[o])) * kBoxStride;
+            if (obb_obb_overlap(cx, cy, ca, sa, ahl, ahw, b)) return true;
+        }
     }
     return false;
 }
@@ -78,22 +91,25 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         sp += n_arr * n;
     }
     const ObstacleTables& O = P.obs;
-    const double* dyn_stage = nullptr;
+    const float4* dyn_stage = nullptr;
     if (P.stage_dyn && O.n_dyn > 0) {
-        double* dst = sp;
+        if (reinterpret_cast<uintptr_t>(sp) & 8u) ++sp;  // 16-byte rows (the host's size includes the slack)
+        float4* dst = reinterpret_cast<float4*>(sp);
         const int total = Np1 * O.n_dyn;
         for (int q = tid; q < total; q += BLOCK) {
-            const int o = q / Np1, step = q - o * Np1;
+            const int step = q / O.n_dyn, o = q - step * O.n_dyn;
             const int kk = P.in.x0_time_step + step * P.in.factor - O.dyn_t0[o];
             const bool present = kk >= 0 && kk < O.dyn_len[o];
-            const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + (present ? kk : 0)) * kBoxStride;
-            double* row = dst + (size_t)o * kDynFields * Np1 + step;
-            row[0] = present ? b[0] : 1.0e300;
-            row[Np1] = present ? b[1] : 1.0e300;
-            row[2 * Np1] = present ? reach2(P.r_ego, b[6]) : 0.0;
+            float4 r = make_float4(1.0e30f, 1.0e30f, 0.0f, 0.0f);
+            if (present) {
+                const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + kk) * kBoxStride;
+                const float reach = (P.r_ego_f_up + (float)b[6]) * 1.000001f + O.dyn_margin;   // >= r_ego + r_obs + margin
+                r = make_float4((float)(b[0] - O.org_x), (float)(b[1] - O.org_y), reach * reach * 1.00001f, 0.0f);
+            }
+            dst[q] = r;
         }
         dyn_stage = dst;
-        sp += (size_t)total * kDynFields;
+        sp += (size_t)total * 2;                          // float4 = 2 doubles
     }
     double* const acc = sp + tid;                        // + (row * 8 + j) * BLOCK
     sp += (size_t)P.n_acc_rows * 8 * BLOCK;
@@ -347,11 +363,11 @@ cand_kernel(const __grid_constant__ PlanParams P) {
             }
 
             // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), speculative ---------------------
-            if (in.check_collision && col == NONE) {
+            if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u) {
                 const double ecx = px + P.wb_rear * cn;
                 const double ecy = py + P.wb_rear * sn;
                 const int tidx = in.x0_time_step + i * in.factor;
-                const bool hit = (dyn_stage ? dyn_collides_staged_safe(O, dyn_stage, Np1, i, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid)
+                const bool hit = (dyn_stage ? dyn_collides_f32(O, dyn_stage + (size_t)i * O.n_dyn, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid)
                                             : dyn_collides_global(O, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid, P.r_ego)) ||
                                  static_collides(O, ecx, ecy, cn, sn, P.half_len, P.half_wid);
                 if (hit) col = (unsigned)i;

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -101,7 +102,7 @@ struct rp_ctx {
     std::vector<int> h_dyn_t0, h_dyn_len;
     double cell_size = 0.0;             // <= 0: automatic
     bool obstacles_dirty = true;
-    DevBuf d_obb, d_tri, d_cell_start, d_cell_items, d_dyn_box, d_dyn_meta;
+    DevBuf d_obb, d_tri, d_cell_start, d_cell_items, d_dyn_box, d_dyn_meta, d_clr;
     rp::ObstacleTables obs{};
 
     // per-cycle
@@ -186,6 +187,43 @@ int build_obstacle_tables(rp_ctx* ctx) {
     O = rp::ObstacleTables{};
     O.n_obb = n_obb;
     O.n_tri = n_tri;
+    // ---- single-precision pre-reject frame ------------------------------------------------------------
+    // Positions are taken relative to the centre of everything's bounding box.  With M = the largest relative
+    // coordinate of an obstacle plus the largest reach plus 100 m, a relative coordinate rounds to fp32 with an
+    // error <= M * 2^-24, a difference of two with <= 3 * M * 2^-24, the distance with <= 1.5 * that, and the
+    // fp32 square / sum add <= 2^-21 relative.  margin = 1e-3 + 1e-6 * M (> 5 * M * 2^-24) metres on the reach and
+    // a factor 1.00001 on its square cover all of it, so a pair the exact test would accept is never rejected.
+    // An ego pose farther out than M is >= 100 m + reach away from every obstacle: far beyond any rounding.
+    double bx0 = 1e300, bx1 = -1e300, by0 = 1e300, by1 = -1e300, r_max = 0.0;
+    auto grow = [&](double x, double y, double r) {
+        bx0 = std::min(bx0, x - r); bx1 = std::max(bx1, x + r); by0 = std::min(by0, y - r); by1 = std::max(by1, y + r);
+        r_max = std::max(r_max, r);
+    };
+    for (int q = 0; q < n_obb; ++q) {
+        const double* sq = &ctx->h_static[(size_t)q * 5];
+        grow(sq[0], sq[1], std::sqrt(sq[3] * sq[3] + sq[4] * sq[4]));
+    }
+    for (int q = 0; q < n_tri; ++q) {
+        const double* t = &ctx->h_tri[(size_t)q * 6];
+        for (int c = 0; c < 3; ++c) grow(t[2 * c], t[2 * c + 1], 0.0);
+    }
+    for (size_t q = 0; q < ctx->h_dyn.size() / 5; ++q) {
+        const double* sq = &ctx->h_dyn[q * 5];
+        grow(sq[0], sq[1], std::sqrt(sq[3] * sq[3] + sq[4] * sq[4]));
+    }
+    if (bx0 > bx1) { bx0 = bx1 = by0 = by1 = 0.0; }
+    O.org_x = 0.5 * (bx0 + bx1);
+    O.org_y = 0.5 * (by0 + by1);
+    const double M = std::max(bx1 - bx0, by1 - by0) * 0.5 + (r_ego + r_max) + 100.0;
+    const bool f32_ok = M < 1.0e6;                       // beyond ~1000 km extent the pre-reject is switched off
+    const double margin = 1e-3 + 1e-6 * M;
+    auto r2_f32 = [&](double reach) -> float {           // squared fp32 reach, rounded up
+        if (!f32_ok) return std::numeric_limits<float>::infinity();
+        const double v = (reach + margin) * (reach + margin) * 1.00001;
+        return std::nextafterf((float)v, std::numeric_limits<float>::infinity());
+    };
+    O.dyn_margin = f32_ok ? (float)margin : std::numeric_limits<float>::infinity();
+    O.r_ego_f = (float)r_ego;
     if (n_prim > 0) {
         double gx0 = lo_x[0], gx1 = hi_x[0], gy0 = lo_y[0], gy1 = hi_y[0];
         for (int q = 1; q < n_prim; ++q) {
@@ -213,30 +251,67 @@ int build_obstacle_tables(rp_ctx* ctx) {
                 for (int ix = ix0; ix <= ix1; ++ix) ++start[(size_t)iy * gnx + ix + 1];
         }
         for (size_t q = 1; q < start.size(); ++q) start[q] += start[q - 1];
-        std::vector<int> items((size_t)std::max(start.back(), 1));
+        std::vector<rp::CellItem> items((size_t)std::max(start.back(), 1));
         std::vector<int> fill(start.begin(), start.end() - 1);
         for (int q = 0; q < n_prim; ++q) {
             int ix0, ix1, iy0, iy1;
             span(q, ix0, ix1, iy0, iy1);
+            rp::CellItem rec;
+            rec.id = q;
+            if (q < n_obb) {
+                const double* o = &obb[(size_t)q * rp::kBoxStride];
+                rec.cx = (float)(o[0] - O.org_x);
+                rec.cy = (float)(o[1] - O.org_y);
+                rec.r2 = r2_f32((r_ego + o[6]) * 1.000000001 + 1e-9);
+            } else {
+                const double* t = &ctx->h_tri[(size_t)(q - n_obb) * 6];
+                const double tx0 = std::min({t[0], t[2], t[4]}), tx1 = std::max({t[0], t[2], t[4]});
+                const double ty0 = std::min({t[1], t[3], t[5]}), ty1 = std::max({t[1], t[3], t[5]});
+                const double mx = 0.5 * (tx0 + tx1), my = 0.5 * (ty0 + ty1);
+                const double rt = 0.5 * std::sqrt((tx1 - tx0) * (tx1 - tx0) + (ty1 - ty0) * (ty1 - ty0));
+                rec.cx = (float)(mx - O.org_x);
+                rec.cy = (float)(my - O.org_y);
+                rec.r2 = r2_f32((r_ego + rt) * 1.000000001 + 1e-9);
+            }
             for (int iy = iy0; iy <= iy1; ++iy)
-                for (int ix = ix0; ix <= ix1; ++ix) items[(size_t)fill[(size_t)iy * gnx + ix]++] = q;
+                for (int ix = ix0; ix <= ix1; ++ix) items[(size_t)fill[(size_t)iy * gnx + ix]++] = rec;
         }
+        // clearance bitmask: cells touching a primitive's AABB inflated by the radius of the three covering circles
+        const double clr_off = 2.0 * hl / 3.0;
+        const double clr_r = std::sqrt((hl / 3.0) * (hl / 3.0) + hw * hw) * (1.0 + 1e-9) + 1e-6;
+        std::vector<unsigned> bits(((size_t)gnx * gny + 31) / 32 + 1, 0u);
+        for (int q = 0; q < n_prim; ++q) {
+            const double shrink = infl - clr_r;              // lo/hi carry the r_ego inflation
+            const int ix0 = std::max(0, (int)std::floor((lo_x[q] + shrink - gx0) * inv));
+            const int ix1 = std::min(gnx - 1, (int)std::floor((hi_x[q] - shrink - gx0) * inv));
+            const int iy0 = std::max(0, (int)std::floor((lo_y[q] + shrink - gy0) * inv));
+            const int iy1 = std::min(gny - 1, (int)std::floor((hi_y[q] - shrink - gy0) * inv));
+            for (int iy = iy0; iy <= iy1; ++iy)
+                for (int ix = ix0; ix <= ix1; ++ix) {
+                    const size_t c = (size_t)iy * gnx + ix;
+                    bits[c >> 5] |= 1u << (c & 31);
+                }
+        }
+        if (int rc = ctx->d_clr.ensure(bits.size() * sizeof(unsigned))) return rc;
+        RP_CUDA(cudaMemcpyAsync(ctx->d_clr.p, bits.data(), bits.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+        O.clr_bits = ctx->d_clr.as<unsigned>();
+        O.clr_off = clr_off;
         if (int rc = ctx->d_obb.ensure(obb.size() * sizeof(double))) return rc;
         if (int rc = ctx->d_tri.ensure(std::max<size_t>(ctx->h_tri.size(), 6) * sizeof(double))) return rc;
         if (int rc = ctx->d_cell_start.ensure(start.size() * sizeof(int))) return rc;
-        if (int rc = ctx->d_cell_items.ensure(items.size() * sizeof(int))) return rc;
+        if (int rc = ctx->d_cell_items.ensure(items.size() * sizeof(rp::CellItem))) return rc;
         RP_CUDA(cudaMemcpyAsync(ctx->d_obb.p, obb.data(), obb.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         if (n_tri)
             RP_CUDA(cudaMemcpyAsync(ctx->d_tri.p, ctx->h_tri.data(), ctx->h_tri.size() * sizeof(double),
                                     cudaMemcpyHostToDevice, ctx->stream));
         RP_CUDA(cudaMemcpyAsync(ctx->d_cell_start.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        RP_CUDA(cudaMemcpyAsync(ctx->d_cell_items.p, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RP_CUDA(cudaMemcpyAsync(ctx->d_cell_items.p, items.data(), items.size() * sizeof(rp::CellItem), cudaMemcpyHostToDevice, ctx->stream));
         RP_CUDA(cudaStreamSynchronize(ctx->stream));     // host vectors go out of scope
         O.obb = ctx->d_obb.as<double>();
         O.tri = ctx->d_tri.as<double>();
         O.gnx = gnx; O.gny = gny; O.gx0 = gx0; O.gy0 = gy0; O.inv_cell = inv;
         O.cell_start = ctx->d_cell_start.as<int>();
-        O.cell_items = ctx->d_cell_items.as<int>();
+        O.cell_items = ctx->d_cell_items.as<rp::CellItem>();
     }
     // dynamic obstacles
     const int n_dyn = (int)ctx->h_dyn_t0.size();
@@ -351,8 +426,9 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     G.n_segs = (int)segs.size();
     const size_t budget = (size_t)ctx->max_smem_optin;
     const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
-    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * rp::kDynFields * sizeof(double);
+    
     const size_t acc_bytes = (size_t)n_acc_rows * 8 * G.threads * sizeof(double);
+    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * sizeof(float4);       // fp32 circle rows
     const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 64;
     G.stage_dyn = (ctx->obs.n_dyn > 0 && dyn_bytes <= 32 * 1024) ? 1 : 0;
     G.smem = acc_bytes + fixed + (G.stage_dyn ? dyn_bytes : 0);
@@ -403,6 +479,7 @@ void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G, const rp::Segmen
     P.half_wid = 0.5 * ctx->veh.width;
     P.wb_rear = ctx->veh.wb_rear_axle;
     P.r_ego = std::sqrt(P.half_len * P.half_len + P.half_wid * P.half_wid);
+    P.r_ego_f_up = std::nextafterf((float)P.r_ego, std::numeric_limits<float>::infinity());
     const double* base = ctx->d_ref.as<double>();
     const int n = ctx->ref_n;
     P.ref.n = n;
@@ -576,7 +653,7 @@ int rp_ctx_destroy(rp_ctx* ctx) {
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all, &ctx->d_states_one,
                       &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best,
-                      &ctx->d_work})
+                      &ctx->d_work, &ctx->d_clr})
         b->release();
     ctx->h_stage.release();
     ctx->h_result.release();
@@ -995,8 +1072,10 @@ int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time
     }
     cudaMemcpyAsync(dp.p, pose, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(dt.p, time_idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    // the clearance bitmask is only valid for boxes inside the vehicle's own box
+    const int vehicle_box = (half_length <= 0.5 * ctx->veh.length && half_width <= 0.5 * ctx->veh.width) ? 1 : 0;
     rp::collide_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dp.as<double>(), dt.as<int>(), half_length,
-                                                                 half_width, r_q, ctx->obs, dh.as<uint8_t>());
+                                                                 half_width, r_q, ctx->obs, vehicle_box, dh.as<uint8_t>());
     cudaMemcpyAsync(hit, dh.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cleanup();

@@ -42,6 +42,7 @@ struct PlanParams {
     rp_plan_inputs in;
     Limits lim;
     double half_len, half_wid, wb_rear, r_ego;
+    float r_ego_f_up;            // r_ego rounded up to fp32 (single-precision pre-reject of rp_cand.cuh)
     RefTables ref;
     double ref_inv_step, ps_inv_step;     // (n-1) / (last - first): index guess of the segment lookup
     ObstacleTables obs;

@@ -264,13 +264,13 @@ __global__ void __launch_bounds__(256) count_before_kernel(const double* __restr
 
 // pycrcc.CollisionChecker.collide for a batch of ego boxes (rp_collide_poses)
 __global__ void collide_kernel(int n, const double* __restrict__ pose, const int* __restrict__ tidx, double hl,
-                               double hw, double r_ego, ObstacleTables O, uint8_t* __restrict__ hit) {
+                               double hw, double r_ego, ObstacleTables O, int vehicle_box, uint8_t* __restrict__ hit) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     double st, ct;
     sincos(pose[3 * g + 2], &st, &ct);
     const double cx = pose[3 * g], cy = pose[3 * g + 1];
-    hit[g] = (dyn_collides_global(O, tidx[g], cx, cy, ct, st, hl, hw, r_ego) || static_collides(O, cx, cy, ct, st, hl, hw)) ? 1 : 0;
+    hit[g] = (dyn_collides_global(O, tidx[g], cx, cy, ct, st, hl, hw, r_ego) || static_collides(O, cx, cy, ct, st, hl, hw, vehicle_box != 0)) ? 1 : 0;
 }
 
 }  // namespace rp
