@@ -294,6 +294,17 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=32, cycles=3):
             "note": "wall clock incl. H2D of every scenario's inputs and D2H of every result (host buffers)"}
 
 
+def ncu_record(kernel_name):
+    """Per-launch DRAM traffic and FP64-pipe activity of ``kernel_name`` from the committed ncu capture of this
+    same command (profiles/ncu_summary.json, written from `ncu --set full`); {} if there is none."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_summary.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(kernel_name, {})
+    except (OSError, ValueError):
+        return {}
+
+
 def cpu_port_rate(work, stride, workers, repeats=1):
     """The oracle port (reference algorithm restated, oracle/rp_oracle.py) on a sub-grid of the same
     workload: every ``stride``-th v and d sample.  Returns (candidates/s, description, seconds)."""
@@ -455,6 +466,7 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     res = eng.grid_result()
+    main_kernel = eng.last_main_kernel()
 
     # ---- end to end through the host-buffer API ----
     t_np, lon_np, d_np = np.array(work["t"]), np.array(work["lon"]), np.array(work["d"])
@@ -523,6 +535,9 @@ def main():
         return
 
     peaks, peak_kind = measured_peaks()
+    from commonroad_rp_b200 import _lib as _l
+    kernel_name = "rp::cand_kernel<128>" if main_kernel == _l.KERNEL_CANDIDATE_MAJOR else "rp::fused_kernel<256>"
+    ncu = ncu_record(kernel_name)
     value = n_total * args.steps / (total_ms * 1e-3)
     fused_mean_ms = float(np.mean(fused_ms))
     cand_steps_launch = count * Np1
@@ -546,8 +561,10 @@ def main():
         "gpu_launches": int((eng.launches_per_plan() + (2 if world > 1 else 0)) * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
-                     "kernel": "rp::fused_kernel<256>", "kernel_ms": fused_mean_ms,
+                     "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                     "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
+                     "fp64_pipe_active_pct_ncu": ncu.get("fp64_pipe_active_pct"),
+                     "kernel": kernel_name, "kernel_ms": fused_mean_ms,
                      "peak_source": "DFMA micro-benchmark measured in this run (FMA = 2 flop); "
                                     "algorithmic work = 200 flop per candidate-timestep (SURVEY 8d)",
                      "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_kind},
@@ -565,7 +582,7 @@ def main():
     if not args.no_cpu_baseline:
         line["p50_replanning_cycle_ms"]["cpu_port"] = replanning_latency_port()
         cores = 1
-        rate, desc, sec, n_s = cpu_port_rate(dense_workload(1), 8, cores)
+        rate, desc, sec, n_s = cpu_port_rate(dense_workload(1), 3, cores)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
                                 "seconds": sec}
     print(json.dumps(line))

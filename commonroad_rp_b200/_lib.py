@@ -86,6 +86,7 @@ SIGNATURES = {
     "rp_stage_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "rp_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "rp_launches_per_plan": (C.c_int, [C.c_void_p]),
+    "rp_last_main_kernel": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None
@@ -337,3 +338,7 @@ class Engine:
 
     def launches_per_plan(self):
         return int(self._lib.rp_launches_per_plan(self._ctx))
+
+    def last_main_kernel(self):
+        """KERNEL_STEP_PARALLEL or KERNEL_CANDIDATE_MAJOR: which schedule evaluated the last plan's main launch."""
+        return int(self._lib.rp_last_main_kernel(self._ctx))

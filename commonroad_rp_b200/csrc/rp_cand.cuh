@@ -33,9 +33,10 @@ namespace rp {
 // cost accumulator rows kept in shared memory: acc[(row * 8 + j) * BLOCK + tid], numpy's 8 partial sums per np.sum
 constexpr int kAccRowsMax = 5;
 
-// Dynamic obstacles of every time step staged as single-precision bounding circles, rows [step][obstacle] of
-// (cx, cy, squared reach, -) relative to the obstacle-table origin: all lanes of a warp are at the same step, so a row
-// is a shared-memory broadcast.  The pre-reject is conservative (reach inflated by the fp32 rounding bound,
+// Dynamic obstacles of every time step as single-precision bounding circles, rows [step][obstacle] of
+// (cx, cy, squared reach, -) relative to the obstacle-table origin, written once per launch by dyn_rows_kernel and
+// read through L1: all lanes of a warp are at the same step, so a row is one broadcast load, and one copy serves
+// every block of the SM (shared memory is left to the cost accumulators).  The pre-reject is conservative (reach inflated by the fp32 rounding bound,
 // build_obstacle_tables) and branch-free over the obstacles -- the circle tests of one step are independent
 // instructions, not a serial chain; survivors go to the exact fp64 SAT, which alone decides a hit.
 // An obstacle absent at a step is parked at 1e30 with zero reach (inf <= 0 is false).
@@ -68,6 +69,207 @@ __device__ __forceinline__ int upper_bound_from(const double* __restrict__ a, in
     return j;
 }
 
+// ---- one polynomial step of one candidate (reactive_planner.py:733-935 loop body) as straight-line code --------
+// Everything data-dependent that is cheap is a select, not a branch (standstill guards, the five ordered limit
+// checks, the projection-domain test), and the sixteen divisions go through Divider<EXACT>: shared refined
+// reciprocals with a sticky reject word (EXACT = false) or plain a / b (EXACT = true).  Large basic blocks let the
+// compiler interleave the independent FP64 chains -- the kernel is bound by FP64 dependency latency, not issue.
+// Remaining branches: low-velocity mode (launch-uniform), the reference-segment walk, the standstill carry (rare),
+// orientation folding (never taken on sane inputs), the second segment search when the tables differ.
+struct StepIn {
+    const double *cs, *cd;       // the candidate's longitudinal / lateral coefficients (re-read every step: L1-resident,
+                                 // the longitudinal row is a warp-wide broadcast; keeps 24 registers free)
+    double th_prev, kap_prev;
+    int i, ub;
+};
+struct StepOut {
+    double x, y, th_gl, th_cl, v, a, kappa, s, sv, d, dv;
+    int ub;
+    unsigned pre;        // pre-filter bits of this step (:796-805)
+    int reason;          // first violated limit of this step (R_NONE if none)
+    int proj_fail;       // projection domain left at this step (:911-917)
+    unsigned reject;     // sign bit set: a division left the fast path's window -> redo with EXACT = true
+};
+
+template <bool EXACT>
+__device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTables& R, const LimitRcp& Y, const StepIn& I) {
+    const rp_plan_inputs& in = P.in;
+    const bool low_vel = in.low_vel_mode != 0;
+    const double dt = in.dt;
+    const int i = I.i;
+    Divider<EXACT> D;
+    StepOut o;
+    double cs[6], cd[6];
+    {
+        const double2* a = reinterpret_cast<const double2*>(I.cs);
+        const double2* b = reinterpret_cast<const double2*>(I.cd);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double2 u = __ldg(a + q), w = __ldg(b + q);
+            cs[2 * q] = u.x; cs[2 * q + 1] = u.y; cd[2 * q] = w.x; cd[2 * q + 1] = w.y;
+        }
+    }
+    // ---- polynomial evaluation (reactive_planner.py:733-777) ---------------------------------------
+    const double tt = (double)i * dt;
+    const double t2 = tt * tt, t3 = t2 * tt, t4 = t2 * t2, t5 = t4 * tt;
+    const double s = poly_pos(cs, tt, t2, t3, t4, t5);
+    double sv = poly_vel(cs, tt, t2, t3, t4);
+    const double sa = poly_acc(cs, tt, t2, t3);
+    double d, dv, da;
+    if (!low_vel) {
+        d = poly_pos(cd, tt, t2, t3, t4, t5);
+        dv = poly_vel(cd, tt, t2, t3, t4);
+        da = poly_acc(cd, tt, t2, t3);
+    } else {
+        const double s1 = s - cs[0];
+        const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+        d = poly_pos(cd, s1, s2, s3, s4, s5);
+        dv = poly_vel(cd, s1, s2, s3, s4);
+        da = poly_acc(cd, s1, s2, s3);
+    }
+    sv = fabs(sv) < kEps ? 0.0 : sv;
+    dv = fabs(dv) < kEps ? 0.0 : dv;
+    o.pre = (fabs(sa) > P.lim.a_max ? 1u : 0u) | (sv < -kEps ? 2u : 0u);    // pre-filter (:796-805)
+
+    // ---- orientation (:810-873) ----------------------------------------------------------------------
+    const bool moving = sv > 0.001;
+    double dp, dpp;
+    if (!low_vel) {
+        const double svs = moving ? sv : 1.0;                   // guarded divisor: the quotient is discarded at standstill
+        const double dp_q = D.div(dv, svs, D.rcp(svs));
+        dp = moving ? dp_q : 0.;
+        const double ddot = da - dp * sa;
+        const double sv2 = svs * svs;
+        const double dpp_q = D.div(ddot, sv2, D.rcp(sv2));
+        dpp = moving ? dpp_q : 0.;
+    } else {
+        dp = dv;
+        dpp = da;
+    }
+    const int ub = I.ub < 0 ? upper_bound_guess(R.pos, R.n, s, P.ref_inv_step) : upper_bound_from(R.pos, R.n, s, I.ub);
+    const bool wrap = (ub == R.n) || (ub == 0);                 // s_idx == -1: python index wrap (App. B#8)
+    const int j0 = wrap ? R.n - 1 : ub - 1;
+    const int j1 = wrap ? 0 : ub;
+    const double p0 = R.pos[j0], p1 = R.pos[j1];
+    const double seg_len = p1 - p0;
+    const double y_seg = D.rcp(seg_len);
+    const double lam = D.div(s - p0, seg_len, y_seg);
+    // interpolate_angle (utility/utils_coordinate_system.py:25-43)
+    const double th0 = R.theta[j0];
+    double th_ref = D.div((R.theta[j1] - th0) * (s - p0), seg_len, y_seg) + th0;
+    if (th_ref > kTwoPi || th_ref < -kTwoPi) th_ref = make_valid_orientation(th_ref);
+    const bool carry = !moving && !low_vel;
+    double th_cl, th_gl, cosT, tanT;
+    if (!carry) {
+        th_cl = atan(dp);                                       // np.arctan2(dp, 1.0)
+        th_gl = th_cl + th_ref;
+        // theta_cl = atan(dp): cos(theta_cl) = 1 / sqrt(1 + dp^2), tan(theta_cl) = dp (<= 1 ulp from libm)
+        const double hyp = sqrt(1.0 + dp * dp);
+        cosT = D.div(1.0, hyp, D.rcp(hyp));
+        tanT = dp;
+    } else {
+        // standstill in high-velocity mode keeps the previous global orientation (:866-873)
+        th_gl = i > 0 ? I.th_prev : in.x0_orientation;
+        th_cl = th_gl - th_ref;
+        cosT = cos(th_cl);
+        tanT = tan(th_cl);
+    }
+
+    // ---- curvature, velocity, acceleration (:876-896) -------------------------------------------------
+    const double k0 = R.curv[j0], kd0 = R.curv_d[j0];
+    const double k_r = (R.curv[j1] - k0) * lam + k0;
+    const double k_r_d = (R.curv_d[j1] - kd0) * lam + kd0;
+    const double oneKrD = (1 - k_r * d);
+    const double y_cos = D.rcp(cosT);
+    const double q = D.div(cosT, oneKrD, D.rcp(oneKrD));
+    const double kappa = (dpp + (k_r * dp + k_r_d * d) * tanT) * cosT * (q * q) + q * k_r;
+    const double v = sv * D.div(oneKrD, cosT, y_cos);
+    const double a = D.div(sa * oneKrD, cosT, y_cos) +
+                     D.div(sv * sv, cosT, y_cos) * (oneKrD * tanT * (D.div(kappa * oneKrD, cosT, y_cos) - k_r) -
+                                                    (k_r_d * d + k_r * dp));
+
+    // ---- the five ordered limit checks (:971-1017), all evaluated, first violation selected ---------------
+    {
+        const Limits& L = P.lim;
+        const unsigned mask = in.constraint_mask;
+        const bool c_v = v < -kEps;
+        const bool c_k = fabs(kappa) > L.kappa_max;
+        const double yaw_q = D.div(th_gl - I.th_prev, dt, Y.y_dt);
+        const double yaw_rate = i > 0 ? yaw_q : 0.;
+        // round(np.float64, 5) == rint(x * 1e5) / 1e5   
+        const bool c_y = fabs(D.div(rint(yaw_rate * 100000.0), 100000.0, Y.y_1e5)) > L.kappa_max * v;
+        // cos(atan2(wb * kappa, 1))^2 == 1 / (1 + (wb * kappa)^2)  (see check_constraints)
+        const double tk = L.wheelbase * kappa;
+        const double kappa_dot_max = D.div(L.v_delta_max * (1.0 + tk * tk), L.wheelbase, Y.y_wb);
+        const double kd_q = D.div(kappa - I.kap_prev, dt, Y.y_dt);
+        const double kappa_dot = i > 0 ? kd_q : 0.;
+        const bool c_kd = fabs(kappa_dot) > kappa_dot_max;
+        const bool fast = v > L.v_switch;
+        const double vv = fast ? v : 1.0;
+        const double a_hi_q = D.div(L.a_max * L.v_switch, vv, D.rcp(vv));
+        const double a_hi = fast ? a_hi_q : L.a_max;
+        const bool c_a = !(-L.a_max <= a && a <= a_hi);
+        int r = R_NONE;
+        r = ((mask & C_ACCELERATION) && c_a) ? R_ACCELERATION : r;
+        r = ((mask & C_KAPPA_DOT) && c_kd) ? R_KAPPA_DOT : r;
+        r = ((mask & C_YAW_RATE) && c_y) ? R_YAW_RATE : r;
+        r = ((mask & C_KAPPA) && c_k) ? R_KAPPA : r;
+        r = ((mask & C_VELOCITY) && c_v) ? R_VELOCITY : r;
+        o.reason = r;
+    }
+
+    // ---- (s, d) -> (x, y) (:908-917; project_to_cartesian) -------------------------------------------------
+    {
+        const int n = R.n;
+        const bool ok = (s >= R.ps[0] && s <= R.ps[n - 1]) && (fabs(d) <= R.limit);
+        const int ub_ps = R.same_s ? ub : upper_bound_guess(R.ps, n, s, P.ps_inv_step);
+        int j = ub_ps - 1;
+        j = j > n - 2 ? n - 2 : j;
+        j = j < 0 ? 0 : j;                                      // only outside the domain (ok == false)
+        double lam2;
+        if (R.same_s && j == j0 && j1 == j0 + 1) {
+            lam2 = lam;                                         // same dividend, same divisor
+        } else {
+            const double sl = R.ps[j + 1] - R.ps[j];
+            lam2 = D.div(s - R.ps[j], sl, D.rcp(sl));
+        }
+        const double p0x = R.px[j], p0y = R.py[j];
+        const double bx = p0x + lam2 * (R.px[j + 1] - p0x);
+        const double by = p0y + lam2 * (R.py[j + 1] - p0y);
+        const double n0x = R.nx[j], n0y = R.ny[j];
+        const double nx = n0x + lam2 * (R.nx[j + 1] - n0x);
+        const double ny = n0y + lam2 * (R.ny[j + 1] - n0y);
+        o.x = ok ? bx + d * nx : 0.;
+        o.y = ok ? by + d * ny : 0.;
+        o.proj_fail = ok ? 0 : 1;
+    }
+    o.th_gl = th_gl; o.th_cl = th_cl; o.v = v; o.a = a; o.kappa = kappa; o.s = s; o.sv = sv; o.d = d; o.dv = dv;
+    o.ub = ub;
+    o.reject = D.reject;
+    return o;
+}
+
+// the rare exact redo: out of line, so its plain divisions (each with a slow-path call) stay out of the hot loop
+__device__ __noinline__ StepOut poly_step_exact(const PlanParams& P, const RefTables& R, const LimitRcp& Y, StepIn I) {
+    return poly_step<true>(P, R, Y, I);
+}
+
+// rows [step][obstacle] for the launch's time window x0.time_step + step * factor (reactive_planner.py:1040)
+__global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, int Np1, float r_ego_f_up, float4* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Np1 * O.n_dyn) return;
+    const int step = q / O.n_dyn, o = q - step * O.n_dyn;
+    const int kk = x0_time_step + step * factor - O.dyn_t0[o];
+    const bool present = kk >= 0 && kk < O.dyn_len[o];
+    float4 r = make_float4(1.0e30f, 1.0e30f, 0.0f, 0.0f);
+    if (present) {
+        const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + kk) * kBoxStride;
+        const float reach = (r_ego_f_up + (float)b[6]) * 1.000001f + O.dyn_margin;   // >= r_ego + r_obs + margin
+        r = make_float4((float)(b[0] - O.org_x), (float)(b[1] - O.org_y), reach * reach * 1.00001f, 0.0f);
+    }
+    out[q] = r;
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
@@ -75,7 +277,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
     const int Np1 = P.Np1;
     const int tid = threadIdx.x;
 
-    // ---- shared memory carve-up -----------------------------------------------------------------
+    // ---- shared memory: [reference tables (optional)] [np.sum accumulators] [v_mid] [limit reciprocals] [segments]
     double* sp = smem;
     RefTables R = P.ref;
     if (P.stage_ref) {
@@ -91,31 +293,21 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         sp += n_arr * n;
     }
     const ObstacleTables& O = P.obs;
-    const float4* dyn_stage = nullptr;
-    if (P.stage_dyn && O.n_dyn > 0) {
-        if (reinterpret_cast<uintptr_t>(sp) & 8u) ++sp;  // 16-byte rows (the host's size includes the slack)
-        float4* dst = reinterpret_cast<float4*>(sp);
-        const int total = Np1 * O.n_dyn;
-        for (int q = tid; q < total; q += BLOCK) {
-            const int step = q / O.n_dyn, o = q - step * O.n_dyn;
-            const int kk = P.in.x0_time_step + step * P.in.factor - O.dyn_t0[o];
-            const bool present = kk >= 0 && kk < O.dyn_len[o];
-            float4 r = make_float4(1.0e30f, 1.0e30f, 0.0f, 0.0f);
-            if (present) {
-                const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + kk) * kBoxStride;
-                const float reach = (P.r_ego_f_up + (float)b[6]) * 1.000001f + O.dyn_margin;   // >= r_ego + r_obs + margin
-                r = make_float4((float)(b[0] - O.org_x), (float)(b[1] - O.org_y), reach * reach * 1.00001f, 0.0f);
-            }
-            dst[q] = r;
-        }
-        dyn_stage = dst;
-        sp += (size_t)total * 2;                          // float4 = 2 doubles
-    }
     double* const acc = sp + tid;                        // + (row * 8 + j) * BLOCK
     sp += (size_t)P.n_acc_rows * 8 * BLOCK;
+    double* const s_vmid = sp + tid;
+    sp += BLOCK;
+    LimitRcp* const s_Y = reinterpret_cast<LimitRcp*>(sp);
+    sp += 4;
     Segment* const s_segs = reinterpret_cast<Segment*>(sp);
     for (int q = tid; q < P.n_segs; q += BLOCK) s_segs[q] = P.segs[q];
+    if (tid == 0) {
+        s_Y->y_dt = rcp_refined(P.in.dt);
+        s_Y->y_1e5 = rcp_refined(100000.0);
+        s_Y->y_wb = rcp_refined(P.lim.wheelbase);
+    }
     __syncthreads();
+    const LimitRcp& Y = *s_Y;
 
     const rp_plan_inputs& in = P.in;
     const bool low_vel = in.low_vel_mode != 0;
@@ -133,6 +325,14 @@ cand_kernel(const __grid_constant__ PlanParams P) {
     const int mid = Np1 / 2;
     const int lane = tid & 31;
 
+    // np.sum in time order: n < 8 plain loop from 0.; otherwise 8 accumulators over [0, n8)
+    // (shared memory), their pairwise tree, then the remainder added sequentially (registers).
+    auto tree = [&](int row) {
+        const double* r8 = acc + (size_t)row * 8 * BLOCK;
+        return ((r8[0] + r8[BLOCK]) + (r8[2 * BLOCK] + r8[3 * BLOCK])) +
+               ((r8[4 * BLOCK] + r8[5 * BLOCK]) + (r8[6 * BLOCK] + r8[7 * BLOCK]));
+    };
+
     for (;;) {
         int g = 0;
         if (lane == 0) g = atomicAdd(P.work_counter, 1);
@@ -147,169 +347,52 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         if (k >= s_segs[lo].k_end) continue;
 
         // ---- candidate decode (sampling.py:202-242 enumeration order) ----------------------------
-        double cs[6], cd[6];
+        StepIn I;
         int tl;
         bool filtered;
-        {
-            const double *pl, *pt;
-            if (P.mode == 0) {
-                const int per_t = P.n_lon * P.n_d;
-                const int it = k / per_t;
-                const int rem = k - it * per_t;
-                const int il = rem / P.n_d;
-                const int id = rem - il * P.n_d;
-                pl = P.lon_coef + (size_t)(it * P.n_lon + il) * 6;
-                pt = P.lat_coef + (size_t)(low_vel ? k : it * P.n_d + id) * 6;
-                tl = P.traj_len[it];
-                filtered = (in.lon_mode == RP_STOPPING) && !(in.x0_lon[0] < P.lon_samples[il]);
-            } else {
-                pl = P.lon_coef + (size_t)k * 6;
-                pt = P.lat_coef + (size_t)k * 6;
-                tl = P.traj_len[k];
-                filtered = P.skip != nullptr && P.skip[k] != 0;
-            }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) { cs[q] = pl[q]; cd[q] = pt[q]; }
-            if (tl > Np1) tl = Np1;
+        if (P.mode == 0) {
+            const int per_t = P.n_lon * P.n_d;
+            const int it = k / per_t;
+            const int rem = k - it * per_t;
+            const int il = rem / P.n_d;
+            const int id = rem - il * P.n_d;
+            I.cs = P.lon_coef + (size_t)(it * P.n_lon + il) * 6;
+            I.cd = P.lat_coef + (size_t)(low_vel ? k : it * P.n_d + id) * 6;
+            tl = P.traj_len[it];
+            filtered = (in.lon_mode == RP_STOPPING) && !(in.x0_lon[0] < P.lon_samples[il]);
+        } else {
+            I.cs = P.lon_coef + (size_t)k * 6;
+            I.cd = P.lat_coef + (size_t)k * 6;
+            tl = P.traj_len[k];
+            filtered = P.skip != nullptr && P.skip[k] != 0;
         }
+        if (tl > Np1) tl = Np1;
         if (filtered) {
             P.info[k] = pack_info(ST_FILTERED, R_NONE, -1);
             if (P.cost) P.cost[k] = __longlong_as_double(0x7ff8000000000000LL);
             continue;
         }
 
-        const LimitRcp Y = {rcp_refined(dt), rcp_refined(100000.0), rcp_refined(P.lim.wheelbase)};
         unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
         int ub = -1;
         // values of the current / last polynomial step (the extension reads them after step tl - 1)
         double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
         double cn = 1., sn = 0.;                       // cos / sin of th_gl
-        double th_prev = 0., kap_prev = 0.;
         double ax = 0., ay = 0.;                       // np.cumsum of the extension increments
         double res_a = 0., res_d = 0., res_th = 0., res_v = 0., res_s = 0.;   // np.sum results
-        double v_mid = 0.;
 
         for (int i = 0; i < Np1; ++i) {
             double px, py;                             // rear-axle position of this step
             double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
             if (i < tl) {
-                // ---- polynomial evaluation (reactive_planner.py:733-777) ---------------------------
-                const double tt = (double)i * dt;
-                const double t2 = tt * tt, t3 = t2 * tt, t4 = t2 * t2, t5 = t4 * tt;
-                s = poly_pos(cs, tt, t2, t3, t4, t5);
-                sv = poly_vel(cs, tt, t2, t3, t4);
-                const double sa = poly_acc(cs, tt, t2, t3);
-                double da;
-                if (!low_vel) {
-                    d = poly_pos(cd, tt, t2, t3, t4, t5);
-                    dv = poly_vel(cd, tt, t2, t3, t4);
-                    da = poly_acc(cd, tt, t2, t3);
-                } else {
-                    const double s1 = s - cs[0];
-                    const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
-                    d = poly_pos(cd, s1, s2, s3, s4, s5);
-                    dv = poly_vel(cd, s1, s2, s3, s4);
-                    da = poly_acc(cd, s1, s2, s3);
-                }
-                if (fabs(sv) < kEps) sv = 0.0;
-                if (fabs(dv) < kEps) dv = 0.0;
-                if (fabs(sa) > P.lim.a_max) pre |= 1u;   // pre-filter (:796-805); this kernel never runs draw mode
-                if (sv < -kEps) pre |= 2u;
-
-                // ---- orientation (:810-873) --------------------------------------------------------
-                // every division below is IEEE a / b (div_rcp, rp_device.cuh); divisors that serve several
-                // quotients get ONE refined reciprocal
-                double dp, dpp;
-                if (!low_vel) {
-                    if (sv > 0.001) {
-                        dp = div_rcp(dv, sv, rcp_refined(sv));
-                        const double ddot = da - dp * sa;
-                        const double sv2 = sv * sv;
-                        dpp = div_rcp(ddot, sv2, rcp_refined(sv2));
-                    } else {
-                        dp = 0.;
-                        dpp = 0.;
-                    }
-                } else {
-                    dp = dv;
-                    dpp = da;
-                }
-                ub = ub < 0 ? upper_bound_guess(R.pos, R.n, s, P.ref_inv_step) : upper_bound_from(R.pos, R.n, s, ub);
-                const bool wrap = (ub == R.n) || (ub == 0);      // s_idx == -1: python index wrap (App. B#8)
-                const int j0 = wrap ? R.n - 1 : ub - 1;
-                const int j1 = wrap ? 0 : ub;
-                const double p0 = R.pos[j0], p1 = R.pos[j1];
-                const double seg_len = p1 - p0;
-                const double y_seg = rcp_refined(seg_len);
-                const double lam = div_rcp(s - p0, seg_len, y_seg);
-                // interpolate_angle (utility/utils_coordinate_system.py:25-43)
-                const double th0 = R.theta[j0];
-                const double th_ref = make_valid_orientation(div_rcp((R.theta[j1] - th0) * (s - p0), seg_len, y_seg) + th0);
-                const bool carry = !(sv > 0.001) && !low_vel;
-                if (!carry) {
-                    th_cl = atan(dp);                            // np.arctan2(dp, 1.0)
-                    th_gl = th_cl + th_ref;
-                } else {
-                    // standstill in high-velocity mode keeps the previous global orientation (:866-873)
-                    th_gl = i > 0 ? th_prev : in.x0_orientation;
-                    th_cl = th_gl - th_ref;
-                }
-
-                // ---- curvature, velocity, acceleration (:876-896) -----------------------------------
-                const double k0 = R.curv[j0], kd0 = R.curv_d[j0];
-                const double k_r = (R.curv[j1] - k0) * lam + k0;
-                const double k_r_d = (R.curv_d[j1] - kd0) * lam + kd0;
-                const double oneKrD = (1 - k_r * d);
-                double cosT, tanT;
-                if (!carry) {
-                    const double hyp = sqrt(1.0 + dp * dp);
-                    cosT = div_rcp(1.0, hyp, rcp_refined(hyp));
-                    tanT = dp;
-                } else {
-                    cosT = cos(th_cl);
-                    tanT = tan(th_cl);
-                }
-                const double y_cos = rcp_refined(cosT);
-                const double q = div_rcp(cosT, oneKrD, rcp_refined(oneKrD));
-                kappa = (dpp + (k_r * dp + k_r_d * d) * tanT) * cosT * (q * q) + q * k_r;
-                v = sv * div_rcp(oneKrD, cosT, y_cos);
-                a = div_rcp(sa * oneKrD, cosT, y_cos) +
-                    div_rcp(sv * sv, cosT, y_cos) * (oneKrD * tanT * (div_rcp(kappa * oneKrD, cosT, y_cos) - k_r) -
-                                                     (k_r_d * d + k_r * dp));
-
-                // ---- limits (:971-1017) + projection (:908-917) --------------------------------------
-                const int r = check_constraints_rcp(P.lim, Y, in.constraint_mask, dt, i, v, kappa, kap_prev, th_gl, th_prev, a);
-                if (r != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)r;
-                {
-                    // project_to_cartesian (rp_device.cuh) with the segment reciprocal shared when both tables coincide
-                    const int n = R.n;
-                    bool ok = (s >= R.ps[0] && s <= R.ps[n - 1]) && (fabs(d) <= R.limit);
-                    if (ok) {
-                        const int ub_ps = R.same_s ? ub : upper_bound_guess(R.ps, n, s, P.ps_inv_step);
-                        int j = ub_ps - 1;
-                        if (j > n - 2) j = n - 2;
-                        double lam2;
-                        if (R.same_s && j == j0 && j1 == j0 + 1) {
-                            lam2 = lam;                          // same dividend, same divisor
-                        } else {
-                            const double sl = R.ps[j + 1] - R.ps[j];
-                            lam2 = div_rcp(s - R.ps[j], sl, rcp_refined(sl));
-                        }
-                        const double p0x = R.px[j], p0y = R.py[j];
-                        const double bx = p0x + lam2 * (R.px[j + 1] - p0x);
-                        const double by = p0y + lam2 * (R.py[j + 1] - p0y);
-                        const double n0x = R.nx[j], n0y = R.ny[j];
-                        const double nx = n0x + lam2 * (R.nx[j + 1] - n0x);
-                        const double ny = n0y + lam2 * (R.ny[j + 1] - n0y);
-                        x = bx + d * nx;
-                        y = by + d * ny;
-                    } else {
-                        if (pbad == NONE) pbad = (unsigned)i;
-                        x = 0.; y = 0.;
-                    }
-                }
-                th_prev = th_gl;
-                kap_prev = kappa;
+                I.i = i; I.ub = ub; I.th_prev = th_gl; I.kap_prev = kappa;
+                StepOut o = poly_step<false>(P, R, Y, I);
+                if (o.reject & 0x80000000u) o = poly_step_exact(P, R, Y, I);
+                pre |= o.pre;
+                if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
+                if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
+                x = o.x; y = o.y; th_gl = o.th_gl; th_cl = o.th_cl; v = o.v; a = o.a; kappa = o.kappa;
+                s = o.s; sv = o.sv; d = o.d; dv = o.dv; ub = o.ub;
                 if (in.check_collision || i == tl - 1) sincos(th_gl, &sn, &cn);
                 px = x; py = y;
                 c_a = a; c_v = v; c_s = s; c_d = d; c_th = th_cl;
@@ -327,15 +410,14 @@ cand_kernel(const __grid_constant__ PlanParams P) {
                 c_th = th_cl;
             }
 
-            // ---- cost terms in numpy's np.sum order (cost_function.py:51-71) ---------
+            // ---- cost terms in numpy's np.sum order (cost_function.py:51-71) ------------------------------
             if (costed) {
                 const double t0 = w_a * c_a, t3 = 0.25 * (des_d - c_d), t4 = 0.25 * fabs(c_th);
-                double q0 = t0 * t0, q3 = t3 * t3, q4 = t4 * t4, q1 = 0., q2 = 0.;
+                const double q0 = t0 * t0, q3 = t3 * t3, q4 = t4 * t4;
+                double q1 = 0., q2 = 0.;
                 if (use_v) { const double t1 = 5 * (c_v - in.desired_speed); q1 = t1 * t1; }
                 if (use_s) { const double t2 = 0.25 * (in.desired_s - c_s); q2 = t2 * t2; }
-                if (Np1 < 8) {
-                    res_a += q0; res_d += q3; res_th += q4; res_v += q1; res_s += q2;
-                } else if (i < n8) {
+                if (Np1 >= 8 && i < n8) {
                     double* ap = acc + (size_t)(i & 7) * BLOCK;
                     if (i < 8) {
                         ap[0] = q0; ap[8 * BLOCK] = q3; ap[16 * BLOCK] = q4;
@@ -347,19 +429,14 @@ cand_kernel(const __grid_constant__ PlanParams P) {
                         if (use_s) ap[row_s * 8 * BLOCK] += q2;
                     }
                 } else {
-                    if (i == n8) {
-                        auto tree = [&](int row) {
-                            const double* r8 = acc + (size_t)row * 8 * BLOCK;
-                            return ((r8[0] + r8[BLOCK]) + (r8[2 * BLOCK] + r8[3 * BLOCK])) +
-                                   ((r8[4 * BLOCK] + r8[5 * BLOCK]) + (r8[6 * BLOCK] + r8[7 * BLOCK]));
-                        };
+                    if (Np1 >= 8 && i == n8) {
                         res_a = tree(0); res_d = tree(1); res_th = tree(2);
                         if (use_v) res_v = tree(row_v);
                         if (use_s) res_s = tree(row_s);
                     }
                     res_a += q0; res_d += q3; res_th += q4; res_v += q1; res_s += q2;
                 }
-                if (i == mid) v_mid = c_v;                       // v[int(len(v) / 2)]
+                if (i == mid) s_vmid[0] = c_v;                   // v[int(len(v) / 2)]
             }
 
             // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), speculative ---------------------
@@ -367,8 +444,8 @@ cand_kernel(const __grid_constant__ PlanParams P) {
                 const double ecx = px + P.wb_rear * cn;
                 const double ecy = py + P.wb_rear * sn;
                 const int tidx = in.x0_time_step + i * in.factor;
-                const bool hit = (dyn_stage ? dyn_collides_f32(O, dyn_stage + (size_t)i * O.n_dyn, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid)
-                                            : dyn_collides_global(O, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid, P.r_ego)) ||
+                const bool hit = (P.dyn_rows ? dyn_collides_f32(O, P.dyn_rows + (size_t)i * O.n_dyn, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid)
+                                             : dyn_collides_global(O, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid, P.r_ego)) ||
                                  static_collides(O, ecx, ecy, cn, sn, P.half_len, P.half_wid);
                 if (hit) col = (unsigned)i;
             }
@@ -395,11 +472,6 @@ cand_kernel(const __grid_constant__ PlanParams P) {
             status = ST_FEASIBLE;
             if (costed) {
                 if (Np1 >= 8 && n8 == Np1) {                       // no remainder: the tree was not taken in the loop
-                    auto tree = [&](int row) {
-                        const double* r8 = acc + (size_t)row * 8 * BLOCK;
-                        return ((r8[0] + r8[BLOCK]) + (r8[2 * BLOCK] + r8[3 * BLOCK])) +
-                               ((r8[4 * BLOCK] + r8[5 * BLOCK]) + (r8[6 * BLOCK] + r8[7 * BLOCK]));
-                    };
                     res_a = tree(0); res_d = tree(1); res_th = tree(2);
                     if (use_v) res_v = tree(row_v);
                     if (use_s) res_s = tree(row_s);
@@ -407,7 +479,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
                 double costs = 0.0;
                 costs += res_a;
                 if (!fs && in.has_desired_speed) {
-                    const double e1 = v - in.desired_speed, e2 = v_mid - in.desired_speed;
+                    const double e1 = v - in.desired_speed, e2 = s_vmid[0] - in.desired_speed;
                     costs += res_v + (50 * (e1 * e1)) + (100 * (e2 * e2));
                 }
                 if (!fs && in.has_desired_s) {

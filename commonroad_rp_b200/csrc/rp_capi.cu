@@ -125,7 +125,7 @@ struct rp_ctx {
     Geometry main_geom{}, index_geom{}, cand_geom{};
     bool main_is_cand = false;          // geometry in main_geom/d_segs belongs to the candidate-major kernel
     int kernel_policy = RP_KERNEL_AUTO;
-    DevBuf d_work;
+    DevBuf d_work, d_dyn_rows;
     int index_geom_np1 = -1, index_geom_count = -1;
     long long index_geom_tables = -1;
     double ref_inv_step = 1.0, ps_inv_step = 1.0;
@@ -427,11 +427,10 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     const size_t budget = (size_t)ctx->max_smem_optin;
     const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
     
-    const size_t acc_bytes = (size_t)n_acc_rows * 8 * G.threads * sizeof(double);
-    const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * sizeof(float4);       // fp32 circle rows
-    const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 64;
-    G.stage_dyn = (ctx->obs.n_dyn > 0 && dyn_bytes <= 32 * 1024) ? 1 : 0;
-    G.smem = acc_bytes + fixed + (G.stage_dyn ? dyn_bytes : 0);
+    const size_t acc_bytes = (size_t)(n_acc_rows * 8 + 1) * G.threads * sizeof(double);    // + v_mid
+    const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 128;
+    G.stage_dyn = 0;                                   // dynamic-obstacle rows are read through L1 (dyn_rows_kernel)
+    G.smem = acc_bytes + fixed;
     G.stage_ref = (env_stage_ref && G.smem + ref_bytes <= budget / 3) ? 1 : 0;
     if (G.stage_ref) G.smem += ref_bytes;
     if (G.smem > budget) return fail(RP_ERR_ARG, "candidate-major kernel: shared-memory need exceeds the SM");
@@ -653,7 +652,7 @@ int rp_ctx_destroy(rp_ctx* ctx) {
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all, &ctx->d_states_one,
                       &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best,
-                      &ctx->d_work, &ctx->d_clr})
+                      &ctx->d_work, &ctx->d_clr, &ctx->d_dyn_rows})
         b->release();
     ctx->h_stage.release();
     ctx->h_result.release();
@@ -854,6 +853,14 @@ static int launch_plan(rp_ctx* ctx) {
             RP_CUDA(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(int), ctx->stream));
             P.work_counter = ctx->d_work.as<int>();
             P.n_acc_rows = cand_acc_rows(ctx->in);
+            P.dyn_rows = nullptr;
+            if (ctx->obs.n_dyn > 0 && ctx->in.check_collision) {
+                const int total = Np1 * ctx->obs.n_dyn;
+                if (int rc = ctx->d_dyn_rows.ensure((size_t)total * sizeof(float4))) return rc;
+                rp::dyn_rows_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->obs, ctx->in.x0_time_step, ctx->in.factor, Np1,
+                                                                                   P.r_ego_f_up, ctx->d_dyn_rows.as<float4>());
+                P.dyn_rows = ctx->d_dyn_rows.as<float4>();
+            }
             const Geometry& G = ctx->main_geom;
             rp::cand_kernel<RP_CAND_THREADS><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
             RP_CUDA(cudaGetLastError());
@@ -1198,9 +1205,15 @@ int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double
     return RP_OK;
 }
 
+int rp_last_main_kernel(rp_ctx* ctx) {
+    if (!ctx) return 0;
+    return ctx->main_is_cand ? RP_KERNEL_CANDIDATE_MAJOR : RP_KERNEL_STEP_PARALLEL;
+}
+
 int rp_launches_per_plan(rp_ctx* ctx) {
     if (!ctx) return 0;
-    return ctx->mode == 0 ? 6 : 5;     // coeff, fused, argmin partial / merge / count, winner states
+    // coeff, fused, argmin partial / merge / count, winner states (+ the dynamic-obstacle rows of the candidate-major kernel)
+    return (ctx->mode == 0 ? 6 : 5) + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
 }
 
 }  // extern "C"

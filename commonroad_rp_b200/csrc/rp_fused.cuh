@@ -57,6 +57,7 @@ struct PlanParams {
     // ---- candidate-major kernel (rp_cand.cuh) ----
     int* work_counter;           // chunk dispenser (zeroed before the launch)
     int n_acc_rows;              // np.sum accumulator rows kept in shared memory
+    const float4* dyn_rows;      // [Np1][n_dyn] single-precision circles of the launch's time window (null: none staged)
 };
 
 __device__ __forceinline__ int pack_info(int status, int reason, int step) {

@@ -220,6 +220,8 @@ int rp_last_stage_ms(rp_ctx* ctx, float* ms4);
 int rp_stage_ms(rp_ctx* ctx, int back, float* ms4);
 /* measurement aid: FP64 FMA peak of the device in TFLOP/s from a DFMA micro-benchmark (roofline denominator) */
 int rp_measure_fp64_peak(rp_ctx* ctx, double* tflops);
+/* which kernel evaluated the main launch of the last plan: RP_KERNEL_STEP_PARALLEL or RP_KERNEL_CANDIDATE_MAJOR */
+int rp_last_main_kernel(rp_ctx* ctx);
 /* number of kernels rp_grid_launch enqueues (for bench.py's gpu_launches) */
 int rp_launches_per_plan(rp_ctx* ctx);
 

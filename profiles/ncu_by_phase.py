@@ -64,7 +64,7 @@ def main():
             o = (toks[1] if toks[0].startswith("@") else toks[0]).split(".")[0]
             op[o] += int(r[ix["Instructions Executed"]]); ops[o] += int(r[ix["# Samples"]])
         ti, ts = sum(op.values()) or 1, sum(ops.values()) or 1
-        print("\nopcode      instr%  samples%   (%d SASS instructions in the kernel)" % len(data))
+        print("\nopcode      instr%%  samples%%   (%d SASS instructions in the kernel)" % len(data))
         for o, c in op.most_common(16):
             print("%-10s %6.1f%% %6.1f%%" % (o, 100 * c / ti, 100 * ops[o] / ts))
 
