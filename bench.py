@@ -250,7 +250,7 @@ def replanning_latency_port(name="ZAM_Over-1_1", max_cycles=6):
             "scenario": "%s, N=%d" % (name, meta["N"]), "api": "oracle port, single process"}
 
 
-def scenario_batch_rate(device, stream_handle, n_scenarios=32, cycles=3):
+def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3):
     """BASELINE configs[4] shape on one rank: independent seeded scenarios, default level-3 grid at N = 60
     (29 t x 17 v x 18 d = 8 874 candidates each), one resident device context per scenario, launches
     enqueued back to back (commonroad_rp_b200.parallel.ScenarioBatch).  Returns candidates/s."""
@@ -278,20 +278,35 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=32, cycles=3):
         j = int(np.argmax(co.ref_pos > s0)) - 1
         inputs = Engine.make_inputs([s0, s_dot0, 0.0], [d0, 0.0, 0.0], float(co.ref_theta[j]), 0, s_dot0 < 4.0,
                                     "velocity_keeping", N_HORIZON, DT, desired_speed=s_dot0)
-        cycle.append((inputs, t, lon, d))
+        from commonroad_rp_b200._lib import traj_len_of
+        cycle.append((inputs, np.asarray(t, dtype=np.float64), np.asarray(lon, dtype=np.float64), np.asarray(d, dtype=np.float64),
+                      np.asarray([traj_len_of(x, DT) for x in t], dtype=np.int32)))
         n_cand += len(t) * len(lon) * len(d)
-    batch.plan(cycle)                                   # warm-up (allocations, geometry)
+    for _ in range(2):
+        batch.plan(cycle)                               # warm-up (allocations, geometry)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    dev_ms = []
     for _ in range(cycles):
         res = batch.plan(cycle)
+        dev_ms.append(batch.batch.last_ms()[0])
     torch.cuda.synchronize()
     dt_s = (time.perf_counter() - t0) / cycles
     n_win = sum(1 for r in res if r.winner >= 0)
+    batch.plan_one_by_one(cycle)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(cycles):
+        batch.plan_one_by_one(cycle)
+    torch.cuda.synchronize()
+    one_s = (time.perf_counter() - t1) / cycles
     batch.close()
     return {"value": n_cand / dt_s, "unit": UNIT, "scenarios": n_scenarios, "candidates_per_scenario": n_cand // n_scenarios,
-            "ms_per_cycle_of_all_scenarios": 1e3 * dt_s, "scenarios_with_winner": n_win,
-            "note": "wall clock incl. H2D of every scenario's inputs and D2H of every result (host buffers)"}
+            "ms_per_cycle_of_all_scenarios": 1e3 * dt_s, "device_ms_per_cycle": float(np.mean(dev_ms)),
+            "device_value": n_cand / (float(np.mean(dev_ms)) * 1e-3), "scenarios_with_winner": n_win,
+            "one_launch_chain_per_scenario": {"value": n_cand / one_s, "ms_per_cycle_of_all_scenarios": 1e3 * one_s},
+            "note": "rp_batch_*: one H2D, four launches, one D2H per cycle of all scenarios; wall clock incl. host "
+                    "staging of every scenario's inputs (host buffers) and D2H of every result"}
 
 
 def ncu_record(kernel_name):

@@ -81,6 +81,14 @@ SIGNATURES = {
     "rp_fetch_coeffs": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "rp_solve_coeffs": (C.c_int, [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, _dp]),
     "rp_collide_poses": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, C.c_double, C.c_double, _bp]),
+    "rp_batch_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rp_batch_destroy": (C.c_int, [C.c_void_p]),
+    "rp_batch_size": (C.c_int, [C.c_void_p]),
+    "rp_batch_set_inputs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PlanInputs), C.c_int, _dp, _ip, C.c_int, _dp, C.c_int, _dp]),
+    "rp_batch_launch": (C.c_int, [C.c_void_p]),
+    "rp_batch_results": (C.c_int, [C.c_void_p, C.POINTER(PlanResult)]),
+    "rp_batch_fetch_candidates": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, _ip, _ip]),
+    "rp_batch_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "rp_selftest_divide": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
     "rp_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rp_stage_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
@@ -342,3 +350,65 @@ class Engine:
     def last_main_kernel(self):
         """KERNEL_STEP_PARALLEL or KERNEL_CANDIDATE_MAJOR: which schedule evaluated the last plan's main launch."""
         return int(self._lib.rp_last_main_kernel(self._ctx))
+
+
+class Batch:
+    """Independent scenarios (``Engine`` objects of one device) evaluated by ONE set of launches per replanning
+    cycle (rp_batch_* in include/rp_b200.h; BASELINE configs[4])."""
+
+    def __init__(self, engines, stream=None):
+        self._lib = load_library()
+        self.engines = list(engines)
+        arr = (C.c_void_p * len(self.engines))(*[e._ctx for e in self.engines])
+        self._b = C.c_void_p()
+        self._check(self._lib.rp_batch_create(arr, len(self.engines), C.c_void_p(stream) if stream else None, C.byref(self._b)))
+        self._n_cand = [0] * len(self.engines)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.rp_last_error()
+            raise RpError("rp_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+    def __len__(self):
+        return len(self.engines)
+
+    def set_inputs(self, k, inputs, t, lon, d, traj_len=None):
+        t, lon, d = _f64(t), _f64(lon), _f64(d)
+        if traj_len is None:
+            traj_len = [traj_len_of(tt, inputs.dt) for tt in t]
+        tl = _i32(traj_len)
+        self._n_cand[k] = t.size * lon.size * d.size
+        self._check(self._lib.rp_batch_set_inputs(self._b, int(k), C.byref(inputs), t.size, _p(t, _dp), _p(tl, _ip),
+                                                  lon.size, _p(lon, _dp), d.size, _p(d, _dp)))
+
+    def launch(self):
+        self._check(self._lib.rp_batch_launch(self._b))
+
+    def results(self):
+        out = (PlanResult * len(self.engines))()
+        self._check(self._lib.rp_batch_results(self._b, out))
+        return list(out)
+
+    def fetch_candidates(self, k):
+        n = self._n_cand[k]
+        cost = np.empty(n, dtype=np.float64)
+        status, reason, step = (np.empty(n, dtype=np.int32) for _ in range(3))
+        self._check(self._lib.rp_batch_fetch_candidates(self._b, int(k), _p(cost, _dp), _p(status, _ip), _p(reason, _ip), _p(step, _ip)))
+        return cost, status, reason, step
+
+    def last_ms(self):
+        """(device milliseconds of the last launch, candidates it evaluated)"""
+        ms, n = C.c_float(), C.c_longlong()
+        self._check(self._lib.rp_batch_last_ms(self._b, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def close(self):
+        if self._b:
+            self._lib.rp_batch_destroy(self._b)
+            self._b = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -270,11 +270,207 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
     out[q] = r;
 }
 
+// ---- one candidate through the whole horizon (the per-lane body of both kernels below) ----------------------
+// acc: this thread's accumulator column (+ (row * 8 + j) * BLOCK), s_vmid: this thread's parked v[mid] slot
+template <int BLOCK>
+__device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k,
+                                           double* __restrict__ acc, double* __restrict__ s_vmid) {
+    const int Np1 = P.Np1;
+    const ObstacleTables& O = P.obs;
+    const rp_plan_inputs& in = P.in;
+    const bool low_vel = in.low_vel_mode != 0;
+    const double dt = in.dt;
+    const unsigned NONE = 0xFFFFFFFFu;
+    const bool fs = in.cost_kind == RP_COST_FAILSAFE;
+    const bool costed = in.cost_kind != RP_COST_NONE;
+    const double w_a = fs ? 1.0 : in.w_a;
+    const double des_d = fs ? 0.0 : in.desired_d;
+    const bool use_v = costed && !fs && in.has_desired_speed;
+    const bool use_s = costed && !fs && in.has_desired_s;
+    // accumulator rows: 0 acceleration, 1 lateral offset, 2 orientation, then velocity / position when used
+    const int row_v = 3, row_s = use_v ? 4 : 3;
+    const int n8 = Np1 - (Np1 & 7);                      // numpy: elements [8, n8) go to the 8 accumulators
+    const int mid = Np1 / 2;
+    // np.sum in time order (SURVEY App. B#5): n < 8 plain loop from 0.; otherwise 8 accumulators over [0, n8)
+    // (shared memory), their pairwise tree, then the remainder added sequentially (registers).
+    auto tree = [&](int row) {
+        const double* r8 = acc + (size_t)row * 8 * BLOCK;
+        return ((r8[0] + r8[BLOCK]) + (r8[2 * BLOCK] + r8[3 * BLOCK])) +
+               ((r8[4 * BLOCK] + r8[5 * BLOCK]) + (r8[6 * BLOCK] + r8[7 * BLOCK]));
+    };
+
+    // ---- candidate decode (sampling.py:202-242 enumeration order) ----------------------------
+    StepIn I;
+    int tl;
+    bool filtered;
+    if (P.mode == 0) {
+        const int per_t = P.n_lon * P.n_d;
+        const int it = k / per_t;
+        const int rem = k - it * per_t;
+        const int il = rem / P.n_d;
+        const int id = rem - il * P.n_d;
+        I.cs = P.lon_coef + (size_t)(it * P.n_lon + il) * 6;
+        I.cd = P.lat_coef + (size_t)(low_vel ? k : it * P.n_d + id) * 6;
+        tl = P.traj_len[it];
+        filtered = (in.lon_mode == RP_STOPPING) && !(in.x0_lon[0] < P.lon_samples[il]);
+    } else {
+        I.cs = P.lon_coef + (size_t)k * 6;
+        I.cd = P.lat_coef + (size_t)k * 6;
+        tl = P.traj_len[k];
+        filtered = P.skip != nullptr && P.skip[k] != 0;
+    }
+    if (tl > Np1) tl = Np1;
+    if (filtered) {
+        P.info[k] = pack_info(ST_FILTERED, R_NONE, -1);
+        if (P.cost) P.cost[k] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+
+    unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
+    int ub = -1;
+    // values of the current / last polynomial step (the extension reads them after step tl - 1)
+    double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
+    double cn = 1., sn = 0.;                       // cos / sin of th_gl
+    double ax = 0., ay = 0.;                       // np.cumsum of the extension increments
+    double res_a = 0., res_d = 0., res_th = 0., res_v = 0., res_s = 0.;   // np.sum results
+
+    for (int i = 0; i < Np1; ++i) {
+        double px, py;                             // rear-axle position of this step
+        double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
+        if (i < tl) {
+            I.i = i; I.ub = ub; I.th_prev = th_gl; I.kap_prev = kappa;
+            StepOut o = poly_step<false>(P, R, Y, I);
+            if (o.reject & 0x80000000u) o = poly_step_exact(P, R, Y, I);
+            pre |= o.pre;
+            if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
+            if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
+            x = o.x; y = o.y; th_gl = o.th_gl; th_cl = o.th_cl; v = o.v; a = o.a; kappa = o.kappa;
+            s = o.s; sv = o.sv; d = o.d; dv = o.dv; ub = o.ub;
+            if (in.check_collision || i == tl - 1) sincos(th_gl, &sn, &cn);
+            px = x; py = y;
+            c_a = a; c_v = v; c_s = s; c_d = d; c_th = th_cl;
+        } else {
+            // ---- horizon extension (trajectories.py:168-197, :302-332) ---------------------------
+            const double tau = (double)(i - tl + 1) * dt;      // np.arange(1, steps + 1) * dt
+            double v_tmp = v + tau * a;
+            v_tmp = v_tmp * (v_tmp >= 0 ? 1.0 : 0.0);
+            const double ix = dt * v_tmp * cn, iy = dt * v_tmp * sn;
+            if (i == tl) { ax = ix; ay = iy; } else { ax += ix; ay += iy; }   // np.cumsum: sequential adds
+            px = x + ax; py = y + ay;
+            c_a = a; c_v = v_tmp;
+            c_s = s + tau * sv;                                // curvilinear tail (App. B#7)
+            c_d = d + tau * dv;
+            c_th = th_cl;
+        }
+
+        // ---- cost terms in numpy's np.sum order (cost_function.py:51-71) ------------------------------
+        if (costed) {
+            const double t0 = w_a * c_a, t3 = 0.25 * (des_d - c_d), t4 = 0.25 * fabs(c_th);
+            const double q0 = t0 * t0, q3 = t3 * t3, q4 = t4 * t4;
+            double q1 = 0., q2 = 0.;
+            if (use_v) { const double t1 = 5 * (c_v - in.desired_speed); q1 = t1 * t1; }
+            if (use_s) { const double t2 = 0.25 * (in.desired_s - c_s); q2 = t2 * t2; }
+            if (Np1 >= 8 && i < n8) {
+                double* ap = acc + (size_t)(i & 7) * BLOCK;
+                if (i < 8) {
+                    ap[0] = q0; ap[8 * BLOCK] = q3; ap[16 * BLOCK] = q4;
+                    if (use_v) ap[row_v * 8 * BLOCK] = q1;
+                    if (use_s) ap[row_s * 8 * BLOCK] = q2;
+                } else {
+                    ap[0] += q0; ap[8 * BLOCK] += q3; ap[16 * BLOCK] += q4;
+                    if (use_v) ap[row_v * 8 * BLOCK] += q1;
+                    if (use_s) ap[row_s * 8 * BLOCK] += q2;
+                }
+            } else {
+                if (Np1 >= 8 && i == n8) {
+                    res_a = tree(0); res_d = tree(1); res_th = tree(2);
+                    if (use_v) res_v = tree(row_v);
+                    if (use_s) res_s = tree(row_s);
+                }
+                res_a += q0; res_d += q3; res_th += q4; res_v += q1; res_s += q2;
+            }
+            if (i == mid) s_vmid[0] = c_v;                   // v[int(len(v) / 2)]
+        }
+
+        // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), speculative ---------------------
+        if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u) {
+            const double ecx = px + P.wb_rear * cn;
+            const double ecy = py + P.wb_rear * sn;
+            const int tidx = in.x0_time_step + i * in.factor;
+            const bool hit = (P.dyn_rows ? dyn_collides_f32(O, P.dyn_rows + (size_t)i * O.n_dyn, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid)
+                                         : dyn_collides_global(O, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid, P.r_ego)) ||
+                             static_collides(O, ecx, ecy, cn, sn, P.half_len, P.half_wid);
+            if (hit) col = (unsigned)i;
+        }
+        if (i == Np1 - 1) {                                   // park the end values for the terminal terms
+            v = c_v; s = c_s; d = c_d; th_cl = c_th;
+        }
+    }
+
+    // ---- per-candidate verdict --------------------------------------------------------------------
+    int status, reason = R_NONE, step = -1;
+    double cost = __longlong_as_double(0x7ff8000000000000LL);   // NaN
+    if (pre != 0u) {
+        status = ST_KINEMATIC;
+        reason = (pre & 1u) ? R_ACCELERATION : R_VELOCITY;
+    } else if (bad != NONE) {
+        status = ST_KINEMATIC;
+        reason = (int)(bad & 0xFFu);
+        step = (int)(bad >> 8);
+    } else if (pbad != NONE) {
+        status = ST_KINEMATIC;
+        reason = R_PROJECTION;
+        step = (int)pbad;
+    } else {
+        status = ST_FEASIBLE;
+        if (costed) {
+            if (Np1 >= 8 && n8 == Np1) {                       // no remainder: the tree was not taken in the loop
+                res_a = tree(0); res_d = tree(1); res_th = tree(2);
+                if (use_v) res_v = tree(row_v);
+                if (use_s) res_s = tree(row_s);
+            }
+            double costs = 0.0;
+            costs += res_a;
+            if (!fs && in.has_desired_speed) {
+                const double e1 = v - in.desired_speed, e2 = s_vmid[0] - in.desired_speed;
+                costs += res_v + (50 * (e1 * e1)) + (100 * (e2 * e2));
+            }
+            if (!fs && in.has_desired_s) {
+                const double e = 20 * (in.desired_s - s);
+                costs += res_s + e * e;
+            }
+            {
+                const double e = 20 * (des_d - d);
+                costs += res_d + e * e;
+            }
+            {
+                const double e = 5 * fabs(th_cl);
+                costs += res_th + e * e;
+            }
+            cost = costs;
+        }
+        if (col != NONE) { status = ST_COLLISION; step = (int)col; }
+    }
+    P.info[k] = pack_info(status, reason, step);
+    if (P.cost) P.cost[k] = cost;
+}
+
+// locate chunk g of 32 candidates in the segment table (sorted by traj_len, longest first); -1: past the end
+__device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs, int n_segs, int g, int lane) {
+    int lo = 0, hi = n_segs - 1;
+    while (lo < hi) {
+        const int m = (lo + hi + 1) >> 1;
+        if (segs[m].g_begin <= g) lo = m; else hi = m - 1;
+    }
+    const int k = segs[lo].k_begin + (g - segs[lo].g_begin) * 32 + lane;
+    return k < segs[lo].k_end ? k : -1;
+}
+
+// ---- one bundle: persistent grid, warps draw chunks of 32 candidates from a counter -----------------------------
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
-    const int Np1 = P.Np1;
     const int tid = threadIdx.x;
 
     // ---- shared memory: [reference tables (optional)] [np.sum accumulators] [v_mid] [limit reciprocals] [segments]
@@ -292,7 +488,6 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         R.ps = R.same_s ? R.pos : base + 8 * n;
         sp += n_arr * n;
     }
-    const ObstacleTables& O = P.obs;
     double* const acc = sp + tid;                        // + (row * 8 + j) * BLOCK
     sp += (size_t)P.n_acc_rows * 8 * BLOCK;
     double* const s_vmid = sp + tid;
@@ -307,199 +502,65 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         s_Y->y_wb = rcp_refined(P.lim.wheelbase);
     }
     __syncthreads();
-    const LimitRcp& Y = *s_Y;
-
-    const rp_plan_inputs& in = P.in;
-    const bool low_vel = in.low_vel_mode != 0;
-    const double dt = in.dt;
-    const unsigned NONE = 0xFFFFFFFFu;
-    const bool fs = in.cost_kind == RP_COST_FAILSAFE;
-    const bool costed = in.cost_kind != RP_COST_NONE;
-    const double w_a = fs ? 1.0 : in.w_a;
-    const double des_d = fs ? 0.0 : in.desired_d;
-    const bool use_v = costed && !fs && in.has_desired_speed;
-    const bool use_s = costed && !fs && in.has_desired_s;
-    // accumulator rows: 0 acceleration, 1 lateral offset, 2 orientation, then velocity / position when used
-    const int row_v = 3, row_s = use_v ? 4 : 3;
-    const int n8 = Np1 - (Np1 & 7);                      // numpy: elements [8, n8) go to the 8 accumulators
-    const int mid = Np1 / 2;
     const int lane = tid & 31;
-
-    // np.sum in time order (SURVEY App. B#5): n < 8 plain loop from 0.; otherwise 8 accumulators over [0, n8)
-    // (shared memory), their pairwise tree, then the remainder added sequentially (registers).
-    auto tree = [&](int row) {
-        const double* r8 = acc + (size_t)row * 8 * BLOCK;
-        return ((r8[0] + r8[BLOCK]) + (r8[2 * BLOCK] + r8[3 * BLOCK])) +
-               ((r8[4 * BLOCK] + r8[5 * BLOCK]) + (r8[6 * BLOCK] + r8[7 * BLOCK]));
-    };
-
     for (;;) {
         int g = 0;
         if (lane == 0) g = atomicAdd(P.work_counter, 1);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= P.n_groups) break;
-        int lo = 0, hi = P.n_segs - 1;
+        const int k = chunk_candidate(s_segs, P.n_segs, g, lane);
+        if (k >= 0) cand_march<BLOCK>(P, R, *s_Y, k, acc, s_vmid);
+    }
+}
+
+// ---- a batch of independent scenarios (BASELINE configs[4]): ONE launch over all (scenario, chunk) pairs --------
+// params[sc] is the scenario's PlanParams in device memory (its own tables, samples, coefficients, verdict arrays),
+// chunk_prefix[sc] the index of its first chunk in the global queue.  Scenario-static data is read through L1; the
+// limit reciprocals are per warp (dt / wheelbase may differ between scenarios).
+struct BatchTable {
+    const PlanParams* params;
+    const int* chunk_prefix;     // [n_scenarios + 1]
+    int n_scenarios;
+    int n_acc_rows;              // max over the scenarios (sizes shared memory)
+    int* work_counter;
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
+cand_batch_kernel(const __grid_constant__ BatchTable B) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* sp = smem;
+    double* const acc = sp + tid;
+    sp += (size_t)B.n_acc_rows * 8 * BLOCK;
+    double* const s_vmid = sp + tid;
+    sp += BLOCK;
+    LimitRcp* const s_Y = reinterpret_cast<LimitRcp*>(sp) + warp;
+    const int total = B.chunk_prefix[B.n_scenarios];
+    int sc_cached = -1;
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(B.work_counter, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= total) break;
+        int lo = 0, hi = B.n_scenarios - 1;              // last scenario with chunk_prefix[sc] <= g
         while (lo < hi) {
             const int m = (lo + hi + 1) >> 1;
-            if (s_segs[m].g_begin <= g) lo = m; else hi = m - 1;
+            if (B.chunk_prefix[m] <= g) lo = m; else hi = m - 1;
         }
-        const int k = s_segs[lo].k_begin + (g - s_segs[lo].g_begin) * 32 + lane;
-        if (k >= s_segs[lo].k_end) continue;
-
-        // ---- candidate decode (sampling.py:202-242 enumeration order) ----------------------------
-        StepIn I;
-        int tl;
-        bool filtered;
-        if (P.mode == 0) {
-            const int per_t = P.n_lon * P.n_d;
-            const int it = k / per_t;
-            const int rem = k - it * per_t;
-            const int il = rem / P.n_d;
-            const int id = rem - il * P.n_d;
-            I.cs = P.lon_coef + (size_t)(it * P.n_lon + il) * 6;
-            I.cd = P.lat_coef + (size_t)(low_vel ? k : it * P.n_d + id) * 6;
-            tl = P.traj_len[it];
-            filtered = (in.lon_mode == RP_STOPPING) && !(in.x0_lon[0] < P.lon_samples[il]);
-        } else {
-            I.cs = P.lon_coef + (size_t)k * 6;
-            I.cd = P.lat_coef + (size_t)k * 6;
-            tl = P.traj_len[k];
-            filtered = P.skip != nullptr && P.skip[k] != 0;
+        const PlanParams& P = B.params[lo];
+        if (lo != sc_cached) {                           // warp-uniform
+            __syncwarp();
+            if (lane == 0) {
+                s_Y->y_dt = rcp_refined(P.in.dt);
+                s_Y->y_1e5 = rcp_refined(100000.0);
+                s_Y->y_wb = rcp_refined(P.lim.wheelbase);
+            }
+            __syncwarp();
+            sc_cached = lo;
         }
-        if (tl > Np1) tl = Np1;
-        if (filtered) {
-            P.info[k] = pack_info(ST_FILTERED, R_NONE, -1);
-            if (P.cost) P.cost[k] = __longlong_as_double(0x7ff8000000000000LL);
-            continue;
-        }
-
-        unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
-        int ub = -1;
-        // values of the current / last polynomial step (the extension reads them after step tl - 1)
-        double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
-        double cn = 1., sn = 0.;                       // cos / sin of th_gl
-        double ax = 0., ay = 0.;                       // np.cumsum of the extension increments
-        double res_a = 0., res_d = 0., res_th = 0., res_v = 0., res_s = 0.;   // np.sum results
-
-        for (int i = 0; i < Np1; ++i) {
-            double px, py;                             // rear-axle position of this step
-            double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
-            if (i < tl) {
-                I.i = i; I.ub = ub; I.th_prev = th_gl; I.kap_prev = kappa;
-                StepOut o = poly_step<false>(P, R, Y, I);
-                if (o.reject & 0x80000000u) o = poly_step_exact(P, R, Y, I);
-                pre |= o.pre;
-                if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
-                if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
-                x = o.x; y = o.y; th_gl = o.th_gl; th_cl = o.th_cl; v = o.v; a = o.a; kappa = o.kappa;
-                s = o.s; sv = o.sv; d = o.d; dv = o.dv; ub = o.ub;
-                if (in.check_collision || i == tl - 1) sincos(th_gl, &sn, &cn);
-                px = x; py = y;
-                c_a = a; c_v = v; c_s = s; c_d = d; c_th = th_cl;
-            } else {
-                // ---- horizon extension (trajectories.py:168-197, :302-332) ---------------------------
-                const double tau = (double)(i - tl + 1) * dt;      // np.arange(1, steps + 1) * dt
-                double v_tmp = v + tau * a;
-                v_tmp = v_tmp * (v_tmp >= 0 ? 1.0 : 0.0);
-                const double ix = dt * v_tmp * cn, iy = dt * v_tmp * sn;
-                if (i == tl) { ax = ix; ay = iy; } else { ax += ix; ay += iy; }   // np.cumsum: sequential adds
-                px = x + ax; py = y + ay;
-                c_a = a; c_v = v_tmp;
-                c_s = s + tau * sv;                                // curvilinear tail (App. B#7)
-                c_d = d + tau * dv;
-                c_th = th_cl;
-            }
-
-            // ---- cost terms in numpy's np.sum order (cost_function.py:51-71) ------------------------------
-            if (costed) {
-                const double t0 = w_a * c_a, t3 = 0.25 * (des_d - c_d), t4 = 0.25 * fabs(c_th);
-                const double q0 = t0 * t0, q3 = t3 * t3, q4 = t4 * t4;
-                double q1 = 0., q2 = 0.;
-                if (use_v) { const double t1 = 5 * (c_v - in.desired_speed); q1 = t1 * t1; }
-                if (use_s) { const double t2 = 0.25 * (in.desired_s - c_s); q2 = t2 * t2; }
-                if (Np1 >= 8 && i < n8) {
-                    double* ap = acc + (size_t)(i & 7) * BLOCK;
-                    if (i < 8) {
-                        ap[0] = q0; ap[8 * BLOCK] = q3; ap[16 * BLOCK] = q4;
-                        if (use_v) ap[row_v * 8 * BLOCK] = q1;
-                        if (use_s) ap[row_s * 8 * BLOCK] = q2;
-                    } else {
-                        ap[0] += q0; ap[8 * BLOCK] += q3; ap[16 * BLOCK] += q4;
-                        if (use_v) ap[row_v * 8 * BLOCK] += q1;
-                        if (use_s) ap[row_s * 8 * BLOCK] += q2;
-                    }
-                } else {
-                    if (Np1 >= 8 && i == n8) {
-                        res_a = tree(0); res_d = tree(1); res_th = tree(2);
-                        if (use_v) res_v = tree(row_v);
-                        if (use_s) res_s = tree(row_s);
-                    }
-                    res_a += q0; res_d += q3; res_th += q4; res_v += q1; res_s += q2;
-                }
-                if (i == mid) s_vmid[0] = c_v;                   // v[int(len(v) / 2)]
-            }
-
-            // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), speculative ---------------------
-            if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u) {
-                const double ecx = px + P.wb_rear * cn;
-                const double ecy = py + P.wb_rear * sn;
-                const int tidx = in.x0_time_step + i * in.factor;
-                const bool hit = (P.dyn_rows ? dyn_collides_f32(O, P.dyn_rows + (size_t)i * O.n_dyn, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid)
-                                             : dyn_collides_global(O, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid, P.r_ego)) ||
-                                 static_collides(O, ecx, ecy, cn, sn, P.half_len, P.half_wid);
-                if (hit) col = (unsigned)i;
-            }
-            if (i == Np1 - 1) {                                   // park the end values for the terminal terms
-                v = c_v; s = c_s; d = c_d; th_cl = c_th;
-            }
-        }
-
-        // ---- per-candidate verdict --------------------------------------------------------------------
-        int status, reason = R_NONE, step = -1;
-        double cost = __longlong_as_double(0x7ff8000000000000LL);   // NaN
-        if (pre != 0u) {
-            status = ST_KINEMATIC;
-            reason = (pre & 1u) ? R_ACCELERATION : R_VELOCITY;
-        } else if (bad != NONE) {
-            status = ST_KINEMATIC;
-            reason = (int)(bad & 0xFFu);
-            step = (int)(bad >> 8);
-        } else if (pbad != NONE) {
-            status = ST_KINEMATIC;
-            reason = R_PROJECTION;
-            step = (int)pbad;
-        } else {
-            status = ST_FEASIBLE;
-            if (costed) {
-                if (Np1 >= 8 && n8 == Np1) {                       // no remainder: the tree was not taken in the loop
-                    res_a = tree(0); res_d = tree(1); res_th = tree(2);
-                    if (use_v) res_v = tree(row_v);
-                    if (use_s) res_s = tree(row_s);
-                }
-                double costs = 0.0;
-                costs += res_a;
-                if (!fs && in.has_desired_speed) {
-                    const double e1 = v - in.desired_speed, e2 = s_vmid[0] - in.desired_speed;
-                    costs += res_v + (50 * (e1 * e1)) + (100 * (e2 * e2));
-                }
-                if (!fs && in.has_desired_s) {
-                    const double e = 20 * (in.desired_s - s);
-                    costs += res_s + e * e;
-                }
-                {
-                    const double e = 20 * (des_d - d);
-                    costs += res_d + e * e;
-                }
-                {
-                    const double e = 5 * fabs(th_cl);
-                    costs += res_th + e * e;
-                }
-                cost = costs;
-            }
-            if (col != NONE) { status = ST_COLLISION; step = (int)col; }
-        }
-        P.info[k] = pack_info(status, reason, step);
-        if (P.cost) P.cost[k] = cost;
+        const int k = chunk_candidate(P.segs, P.n_segs, g - B.chunk_prefix[lo], lane);
+        if (k >= 0) cand_march<BLOCK>(P, P.ref, *s_Y, k, acc, s_vmid);
     }
 }
 

@@ -1217,3 +1217,276 @@ int rp_launches_per_plan(rp_ctx* ctx) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Batch of independent scenarios (BASELINE configs[4]): every scenario keeps its own context (device-resident
+// reference / obstacle tables); one replanning cycle of ALL of them is one host->device copy, four launches
+// (coefficients, dynamic-obstacle rows, candidate-major evaluation over a global (scenario, chunk) queue,
+// one arg-min block per scenario) and one device->host copy.
+// =====================================================================================================
+struct rp_batch {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    std::vector<rp_ctx*> ctxs;
+    struct Slot {
+        rp_plan_inputs in{};
+        std::vector<double> t, lon, d;
+        std::vector<int> traj_len;
+        bool set = false;
+    };
+    std::vector<Slot> slots;
+    PinBuf h_stage, h_results;
+    DevBuf d_stage, d_lon_coef, d_lat_coef, d_cost, d_info, d_dyn_rows, d_results, d_work;
+    cudaEvent_t ev_stage = nullptr, ev_results = nullptr, ev0 = nullptr, ev1 = nullptr;
+    bool stage_pending = false, launched = false;
+    long long total_cand = 0;
+    int smem_granted = 0;
+};
+
+extern "C" {
+
+int rp_batch_create(rp_ctx* const* ctxs, int n, void* stream, rp_batch** out) {
+    if (!out) return fail(RP_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (n < 1 || !ctxs) return fail(RP_ERR_ARG, "a batch needs at least one context");
+    for (int k = 0; k < n; ++k) {
+        if (!ctxs[k]) return fail(RP_ERR_ARG, "null context in batch");
+        if (ctxs[k]->device != ctxs[0]->device) return fail(RP_ERR_ARG, "all contexts of a batch must live on one device");
+    }
+    RP_CUDA(cudaSetDevice(ctxs[0]->device));
+    rp_batch* b = new rp_batch();
+    b->device = ctxs[0]->device;
+    b->stream = stream ? static_cast<cudaStream_t>(stream) : ctxs[0]->stream;
+    b->num_sms = ctxs[0]->num_sms;
+    b->ctxs.assign(ctxs, ctxs + n);
+    b->slots.resize(n);
+    cudaEventCreateWithFlags(&b->ev_stage, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&b->ev_results, cudaEventDisableTiming);
+    cudaEventCreate(&b->ev0);
+    cudaEventCreate(&b->ev1);
+    *out = b;
+    return RP_OK;
+}
+
+int rp_batch_destroy(rp_batch* b) {
+    if (!b) return RP_OK;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    for (DevBuf* q : {&b->d_stage, &b->d_lon_coef, &b->d_lat_coef, &b->d_cost, &b->d_info, &b->d_dyn_rows, &b->d_results, &b->d_work})
+        q->release();
+    b->h_stage.release();
+    b->h_results.release();
+    for (cudaEvent_t e : {b->ev_stage, b->ev_results, b->ev0, b->ev1})
+        if (e) cudaEventDestroy(e);
+    delete b;
+    return RP_OK;
+}
+
+int rp_batch_size(rp_batch* b) { return b ? (int)b->ctxs.size() : 0; }
+
+int rp_batch_set_inputs(rp_batch* b, int k, const rp_plan_inputs* in, int n_t, const double* t, const int32_t* traj_len,
+                        int n_lon, const double* lon, int n_d, const double* d) {
+    if (!b) return fail(RP_ERR_ARG, "null batch");
+    if (k < 0 || k >= (int)b->ctxs.size()) return fail(RP_ERR_ARG, "scenario index out of range");
+    if (int rc = check_inputs(in)) return rc;
+    if (n_t < 0 || n_lon < 0 || n_d < 0) return fail(RP_ERR_ARG, "negative sample count");
+    if ((n_t && (!t || !traj_len)) || (n_lon && !lon) || (n_d && !d)) return fail(RP_ERR_ARG, "null sample array");
+    if ((long long)n_t * n_lon * n_d > 0x7fffffffLL / 8) return fail(RP_ERR_ARG, "bundle too large");
+    if (in->want_all_states || in->draw_all) return fail(RP_ERR_ARG, "a batch runs in select-only mode (no draw_all / want_all_states)");
+    if (in->N + 1 > 128) return fail(RP_ERR_ARG, "a batch supports N + 1 <= 128");
+    for (int q = 0; q < n_t; ++q)
+        if (traj_len[q] < 1 || traj_len[q] > in->N + 1) return fail(RP_ERR_ARG, "traj_len out of [1, N+1]");
+    rp_batch::Slot& s = b->slots[k];
+    s.in = *in;
+    s.t.assign(t, t + n_t);
+    s.lon.assign(lon, lon + n_lon);
+    s.d.assign(d, d + n_d);
+    s.traj_len.assign(traj_len, traj_len + n_t);
+    s.set = true;
+    return RP_OK;
+}
+
+int rp_batch_launch(rp_batch* b) {
+    if (!b) return fail(RP_ERR_ARG, "null batch");
+    RP_CUDA(cudaSetDevice(b->device));
+    const int n = (int)b->ctxs.size();
+    // ---- layout of the staging buffer: params | chunk_prefix | per scenario: t, lon, d, traj_len, segments -------
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    size_t off = align16((size_t)n * sizeof(PlanParams));
+    const size_t off_prefix = off;
+    off = align16(off + (size_t)(n + 1) * sizeof(int));
+    std::vector<size_t> off_samples(n), off_segs(n);
+    std::vector<std::vector<rp::Segment>> segs(n);
+    std::vector<int> prefix(n + 1, 0);
+    std::vector<size_t> off_lon(n), off_lat(n), off_cand(n), off_rows(n);
+    size_t n_lon_tot = 0, n_lat_tot = 0, n_cand_tot = 0, n_rows_tot = 0;
+    int max_sys = 0, max_rows = 0, acc_rows = 0;
+    for (int k = 0; k < n; ++k) {
+        rp_ctx* c = b->ctxs[k];
+        const rp_batch::Slot& s = b->slots[k];
+        if (!s.set) return fail(RP_ERR_STATE, "rp_batch_set_inputs missing for a scenario");
+        if (int rc = check_ready(c)) return rc;
+        const int n_t = (int)s.t.size(), n_lon = (int)s.lon.size(), n_d = (int)s.d.size();
+        const int Np1 = s.in.N + 1;
+        off_samples[k] = off;
+        off = align16(off + (size_t)(n_t + n_lon + n_d) * sizeof(double) + (size_t)n_t * sizeof(int));
+        const int per_t = n_lon * n_d;
+        for (int it = 0; it < n_t && per_t > 0; ++it)
+            segs[k].push_back(rp::Segment{it * per_t, (it + 1) * per_t, std::max(1, std::min(s.traj_len[it], Np1)), 32, 0});
+        if (segs[k].empty()) segs[k].push_back(rp::Segment{0, 0, Np1, 32, 0});
+        std::stable_sort(segs[k].begin(), segs[k].end(), [](const rp::Segment& x, const rp::Segment& y) { return x.tl > y.tl; });
+        int groups = 0;
+        for (auto& sg : segs[k]) {
+            sg.g_begin = groups;
+            groups += (sg.k_end - sg.k_begin + 31) / 32;
+        }
+        prefix[k + 1] = prefix[k] + groups;
+        off_segs[k] = off;
+        off = align16(off + segs[k].size() * sizeof(rp::Segment));
+        const int n_cand = n_t * per_t;
+        const int n_lon_sys = n_t * n_lon, n_lat_sys = s.in.low_vel_mode ? n_cand : n_t * n_d;
+        off_lon[k] = n_lon_tot; off_lat[k] = n_lat_tot; off_cand[k] = n_cand_tot; off_rows[k] = n_rows_tot;
+        n_lon_tot += (size_t)n_lon_sys; n_lat_tot += (size_t)n_lat_sys; n_cand_tot += (size_t)n_cand;
+        const int rows = (c->obs.n_dyn > 0 && s.in.check_collision) ? Np1 * c->obs.n_dyn : 0;
+        n_rows_tot += (size_t)rows;
+        max_sys = std::max(max_sys, n_lon_sys + n_lat_sys);
+        max_rows = std::max(max_rows, rows);
+        acc_rows = std::max(acc_rows, cand_acc_rows(s.in));
+    }
+    const size_t stage_bytes = off;
+    if (int rc = b->h_stage.ensure(stage_bytes)) return rc;
+    if (int rc = b->d_stage.ensure(stage_bytes)) return rc;
+    if (int rc = b->d_lon_coef.ensure(std::max<size_t>(n_lon_tot, 1) * 6 * sizeof(double))) return rc;
+    if (int rc = b->d_lat_coef.ensure(std::max<size_t>(n_lat_tot, 1) * 6 * sizeof(double))) return rc;
+    if (int rc = b->d_cost.ensure(std::max<size_t>(n_cand_tot, 1) * sizeof(double))) return rc;
+    if (int rc = b->d_info.ensure(std::max<size_t>(n_cand_tot, 1) * sizeof(int))) return rc;
+    if (int rc = b->d_dyn_rows.ensure(std::max<size_t>(n_rows_tot, 1) * sizeof(float4))) return rc;
+    if (int rc = b->d_results.ensure((size_t)n * sizeof(rp::PlanResultDev))) return rc;
+    if (int rc = b->h_results.ensure((size_t)n * sizeof(rp::PlanResultDev))) return rc;
+    if (int rc = b->d_work.ensure(sizeof(int))) return rc;
+    if (b->stage_pending) RP_CUDA(cudaEventSynchronize(b->ev_stage));          // last copy out of the pinned buffer
+    char* hs = static_cast<char*>(b->h_stage.p);
+    const char* ds = static_cast<const char*>(b->d_stage.p);
+    std::memcpy(hs + off_prefix, prefix.data(), prefix.size() * sizeof(int));
+    PlanParams* hp = reinterpret_cast<PlanParams*>(hs);
+    Geometry G{};
+    G.stage_ref = 0; G.stage_dyn = 0; G.Cmax = 32;
+    for (int k = 0; k < n; ++k) {
+        rp_ctx* c = b->ctxs[k];
+        const rp_batch::Slot& s = b->slots[k];
+        const int n_t = (int)s.t.size(), n_lon = (int)s.lon.size(), n_d = (int)s.d.size();
+        char* p = hs + off_samples[k];
+        if (n_t) std::memcpy(p, s.t.data(), (size_t)n_t * 8);
+        if (n_lon) std::memcpy(p + (size_t)n_t * 8, s.lon.data(), (size_t)n_lon * 8);
+        if (n_d) std::memcpy(p + (size_t)(n_t + n_lon) * 8, s.d.data(), (size_t)n_d * 8);
+        if (n_t) std::memcpy(p + (size_t)(n_t + n_lon + n_d) * 8, s.traj_len.data(), (size_t)n_t * 4);
+        std::memcpy(hs + off_segs[k], segs[k].data(), segs[k].size() * sizeof(rp::Segment));
+        // the scenario's context describes its tables; the cycle's inputs come from the slot
+        c->in = s.in;
+        c->mode = 0;
+        c->n_t = n_t; c->n_lon = n_lon; c->n_d = n_d;
+        c->n_cand = n_t * n_lon * n_d;
+        c->have_plan = false;
+        G.n_segs = (int)segs[k].size();
+        G.n_groups = prefix[k + 1] - prefix[k];
+        PlanParams P{};
+        fill_common(c, P, G, reinterpret_cast<const rp::Segment*>(ds + off_segs[k]));
+        const char* dsamp = ds + off_samples[k];
+        P.t_samples = reinterpret_cast<const double*>(dsamp);
+        P.lon_samples = reinterpret_cast<const double*>(dsamp + (size_t)n_t * 8);
+        P.d_samples = reinterpret_cast<const double*>(dsamp + (size_t)(n_t + n_lon) * 8);
+        P.traj_len = reinterpret_cast<const int*>(dsamp + (size_t)(n_t + n_lon + n_d) * 8);
+        P.skip = nullptr;
+        P.lon_coef = b->d_lon_coef.as<double>() + off_lon[k] * 6;
+        P.lat_coef = b->d_lat_coef.as<double>() + off_lat[k] * 6;
+        P.index = nullptr;
+        P.cost = b->d_cost.as<double>() + off_cand[k];
+        P.info = b->d_info.as<int>() + off_cand[k];
+        P.states = nullptr;
+        P.best_bits = nullptr;
+        P.work_counter = nullptr;
+        P.n_acc_rows = cand_acc_rows(s.in);
+        P.dyn_rows = (c->obs.n_dyn > 0 && s.in.check_collision) ? b->d_dyn_rows.as<float4>() + off_rows[k] : nullptr;
+        hp[k] = P;
+    }
+    RP_CUDA(cudaMemcpyAsync(b->d_stage.p, b->h_stage.p, stage_bytes, cudaMemcpyHostToDevice, b->stream));
+    RP_CUDA(cudaEventRecord(b->ev_stage, b->stream));
+    b->stage_pending = true;
+    RP_CUDA(cudaMemsetAsync(b->d_work.p, 0, sizeof(int), b->stream));
+    cudaEventRecord(b->ev0, b->stream);
+    const PlanParams* dparams = reinterpret_cast<const PlanParams*>(ds);
+    if (max_sys > 0) rp::coeff_batch_kernel<<<dim3((max_sys + 127) / 128, n), 128, 0, b->stream>>>(dparams);
+    if (max_rows > 0) rp::dyn_rows_batch_kernel<<<dim3((max_rows + 127) / 128, n), 128, 0, b->stream>>>(dparams);
+    if (prefix[n] > 0) {
+        rp::BatchTable T{};
+        T.params = dparams;
+        T.chunk_prefix = reinterpret_cast<const int*>(ds + off_prefix);
+        T.n_scenarios = n;
+        T.n_acc_rows = acc_rows;
+        T.work_counter = b->d_work.as<int>();
+        const int threads = RP_CAND_THREADS;
+        const size_t smem = (size_t)(acc_rows * 8 + 1) * threads * sizeof(double) + (size_t)(threads / 32) * sizeof(rp::LimitRcp) + 64;
+        if ((int)smem > b->smem_granted) {
+            RP_CUDA(cudaFuncSetAttribute(rp::cand_batch_kernel<RP_CAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            b->smem_granted = (int)smem;
+        }
+        int occ = 0;
+        RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::cand_batch_kernel<RP_CAND_THREADS>, threads, smem));
+        if (occ < 1) return fail(RP_ERR_CUDA, "batch kernel does not fit on an SM");
+        const int wpb = threads / 32;
+        const int grid = std::max(1, std::min((prefix[n] + wpb - 1) / wpb, occ * b->num_sms));
+        rp::cand_batch_kernel<RP_CAND_THREADS><<<grid, threads, smem, b->stream>>>(T);
+    }
+    rp::argmin_batch_kernel<<<n, 256, 0, b->stream>>>(dparams, b->d_results.as<rp::PlanResultDev>());
+    RP_CUDA(cudaGetLastError());
+    cudaEventRecord(b->ev1, b->stream);
+    b->total_cand = (long long)n_cand_tot;
+    b->launched = true;
+    return RP_OK;
+}
+
+int rp_batch_results(rp_batch* b, rp_plan_result* out) {
+    if (!b || !out) return fail(RP_ERR_ARG, "null argument");
+    if (!b->launched) return fail(RP_ERR_STATE, "no batch launched");
+    RP_CUDA(cudaSetDevice(b->device));
+    const int n = (int)b->ctxs.size();
+    RP_CUDA(cudaMemcpyAsync(b->h_results.p, b->d_results.p, (size_t)n * sizeof(rp::PlanResultDev), cudaMemcpyDeviceToHost, b->stream));
+    RP_CUDA(cudaEventRecord(b->ev_results, b->stream));
+    RP_CUDA(cudaEventSynchronize(b->ev_results));
+    const rp::PlanResultDev* h = static_cast<const rp::PlanResultDev*>(b->h_results.p);
+    for (int k = 0; k < n; ++k) out[k] = h[k].r;
+    return RP_OK;
+}
+
+int rp_batch_fetch_candidates(rp_batch* b, int k, double* cost, int32_t* status, int32_t* reason, int32_t* step) {
+    if (!b) return fail(RP_ERR_ARG, "null batch");
+    if (!b->launched) return fail(RP_ERR_STATE, "no batch launched");
+    if (k < 0 || k >= (int)b->ctxs.size()) return fail(RP_ERR_ARG, "scenario index out of range");
+    RP_CUDA(cudaSetDevice(b->device));
+    const PlanParams* hp = reinterpret_cast<const PlanParams*>(b->h_stage.p);
+    const int n = hp[k].n_cand;
+    if (n == 0) return RP_OK;
+    if (cost) RP_CUDA(cudaMemcpyAsync(cost, hp[k].cost, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    std::vector<int> info(n);
+    RP_CUDA(cudaMemcpyAsync(info.data(), hp[k].info, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    RP_CUDA(cudaStreamSynchronize(b->stream));
+    for (int q = 0; q < n; ++q) {
+        if (status) status[q] = info[q] & 0xFF;
+        if (reason) reason[q] = (info[q] >> 8) & 0xFF;
+        if (step) step[q] = ((info[q] >> 16) & 0xFFFF) - 1;
+    }
+    return RP_OK;
+}
+
+int rp_batch_last_ms(rp_batch* b, float* ms, long long* n_candidates) {
+    if (!b || !ms) return fail(RP_ERR_ARG, "null argument");
+    if (!b->launched) return fail(RP_ERR_STATE, "no batch launched");
+    RP_CUDA(cudaSetDevice(b->device));
+    RP_CUDA(cudaEventSynchronize(b->ev1));
+    RP_CUDA(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    if (n_candidates) *n_candidates = b->total_cand;
+    return RP_OK;
+}
+
+}  // extern "C"

@@ -31,6 +31,8 @@ struct PlanParams {
     int n_cand;                  // size of the enumeration space
     const int* index;            // index mode: candidate id per slot (negative = empty slot); else null
     const double* lon_samples;   // grid: [n_lon] (filter_goals_behind in stopping mode)
+    const double* t_samples;     // grid: [n_t], [n_d]: read by the batch coefficient kernel only
+    const double* d_samples;
     const int* traj_len;         // grid: [n_t], list: [n_cand]
     const double* lon_coef;      // grid: [n_t*n_lon][6], list: [n_cand][6]
     const double* lat_coef;      // grid: [n_t*n_d][6] (or [n_cand][6] in low-velocity mode), list: [n_cand][6]

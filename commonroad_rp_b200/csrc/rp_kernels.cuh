@@ -28,14 +28,14 @@ struct PlanResultDev {
 // the lateral ones.  In low-velocity mode the lateral parameter range is the longitudinal end
 // position (sampling.py:229-234), so a lateral thread first redoes its longitudinal solve.
 // ------------------------------------------------------------------------------------------------
-__global__ void coeff_kernel(int n_t, int n_lon, int n_d, int low_vel, int lon_mode, const double* __restrict__ t,
-                             const double* __restrict__ lon, const double* __restrict__ d, const double x0s,
-                             const double x0sd, const double x0sdd, const double x0d, const double x0dd,
-                             const double x0ddd, double* __restrict__ lon_coef, double* __restrict__ lat_coef,
-                             double* __restrict__ lat_tau) {
+__device__ __forceinline__ void coeff_thread(int gid, int n_t, int n_lon, int n_d, int low_vel, int lon_mode,
+                                             const double* __restrict__ t, const double* __restrict__ lon,
+                                             const double* __restrict__ d, const double x0s, const double x0sd,
+                                             const double x0sdd, const double x0d, const double x0dd, const double x0ddd,
+                                             double* __restrict__ lon_coef, double* __restrict__ lat_coef,
+                                             double* __restrict__ lat_tau) {
     const int n_lon_sys = n_t * n_lon;
     const int n_lat_sys = low_vel ? n_t * n_lon * n_d : n_t * n_d;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_lon_sys + n_lat_sys) return;
     double c[6];
     if (gid < n_lon_sys) {
@@ -69,7 +69,42 @@ __global__ void coeff_kernel(int n_t, int n_lon, int n_d, int low_vel, int lon_m
     solve_quintic(x0d, x0dd, x0ddd, d[id], 0.0, 0.0, tau, c);
 #pragma unroll
     for (int k = 0; k < 6; ++k) lat_coef[(size_t)q * 6 + k] = c[k];
-    lat_tau[q] = tau;
+    if (lat_tau) lat_tau[q] = tau;
+}
+
+__global__ void coeff_kernel(int n_t, int n_lon, int n_d, int low_vel, int lon_mode, const double* __restrict__ t,
+                             const double* __restrict__ lon, const double* __restrict__ d, const double x0s,
+                             const double x0sd, const double x0sdd, const double x0d, const double x0dd,
+                             const double x0ddd, double* __restrict__ lon_coef, double* __restrict__ lat_coef,
+                             double* __restrict__ lat_tau) {
+    coeff_thread(blockIdx.x * blockDim.x + threadIdx.x, n_t, n_lon, n_d, low_vel, lon_mode, t, lon, d, x0s, x0sd, x0sdd, x0d,
+                 x0dd, x0ddd, lon_coef, lat_coef, lat_tau);
+}
+
+// ---- batch of independent scenarios (blockIdx.y = scenario; see cand_batch_kernel) --------------------------------
+__global__ void coeff_batch_kernel(const PlanParams* __restrict__ params) {
+    const PlanParams& P = params[blockIdx.y];
+    const rp_plan_inputs& in = P.in;
+    coeff_thread(blockIdx.x * blockDim.x + threadIdx.x, P.n_t, P.n_lon, P.n_d, in.low_vel_mode, in.lon_mode, P.t_samples,
+                 P.lon_samples, P.d_samples, in.x0_lon[0], in.x0_lon[1], in.x0_lon[2], in.x0_lat[0], in.x0_lat[1], in.x0_lat[2],
+                 const_cast<double*>(P.lon_coef), const_cast<double*>(P.lat_coef), nullptr);
+}
+
+__global__ void dyn_rows_batch_kernel(const PlanParams* __restrict__ params) {
+    const PlanParams& P = params[blockIdx.y];
+    const ObstacleTables& O = P.obs;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P.dyn_rows == nullptr || q >= P.Np1 * O.n_dyn) return;
+    const int step = q / O.n_dyn, o = q - step * O.n_dyn;
+    const int kk = P.in.x0_time_step + step * P.in.factor - O.dyn_t0[o];
+    const bool present = kk >= 0 && kk < O.dyn_len[o];
+    float4 r = make_float4(1.0e30f, 1.0e30f, 0.0f, 0.0f);
+    if (present) {
+        const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + kk) * kBoxStride;
+        const float reach = (P.r_ego_f_up + (float)b[6]) * 1.000001f + O.dyn_margin;
+        r = make_float4((float)(b[0] - O.org_x), (float)(b[1] - O.org_y), reach * reach * 1.00001f, 0.0f);
+    }
+    const_cast<float4*>(P.dyn_rows)[q] = r;
 }
 
 // generic batched solve (rp_solve_coeffs)
@@ -223,6 +258,90 @@ __global__ void __launch_bounds__(256) count_before_result_kernel(const double* 
     }
     local = warp_sum(local);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&out->r.n_infeasible_collision, local);
+}
+
+// one block per scenario of a batch: arg-min, counters and the colliders ranked before the winner in one launch
+__global__ void __launch_bounds__(256) argmin_batch_kernel(const PlanParams* __restrict__ params, PlanResultDev* __restrict__ results) {
+    __shared__ double w_cost[8];
+    __shared__ int w_idx[8];
+    __shared__ int s_counts[16];
+    __shared__ double s_wc;
+    __shared__ int s_wi, s_before;
+    const PlanParams& P = params[blockIdx.x];
+    const double* __restrict__ cost = P.cost;
+    const int* __restrict__ info = P.info;
+    const int n = P.n_cand;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 16) s_counts[tid] = 0;
+    if (tid == 0) s_before = 0;
+    __syncthreads();
+    double bc = __longlong_as_double(0x7ff0000000000000LL);
+    int bi = 0x7fffffff;
+    int l_feas = 0, l_colt = 0, l_filt = 0;
+    int l_reason[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = tid; k < n; k += blockDim.x) {
+        const int w = info[k];
+        const int st = w & 0xFF;
+        if (st == ST_FEASIBLE) {
+            ++l_feas;
+            const double cc = cost[k];
+            if (lex_less(cc, k, bc, bi)) { bc = cc; bi = k; }
+        } else if (st == ST_COLLISION) {
+            ++l_feas;
+            ++l_colt;
+        } else if (st == ST_UNCHECKED) {
+            ++l_feas;
+        } else if (st == ST_KINEMATIC) {
+            const int r = (w >> 8) & 0x7;
+#pragma unroll
+            for (int z = 0; z < 8; ++z) l_reason[z] += (r == z) ? 1 : 0;
+        } else {
+            ++l_filt;
+        }
+    }
+    warp_lexmin(bc, bi);
+    if (lane == 0) { w_cost[warp] = bc; w_idx[warp] = bi; }
+    l_feas = warp_sum(l_feas); l_colt = warp_sum(l_colt); l_filt = warp_sum(l_filt);
+#pragma unroll
+    for (int z = 0; z < 8; ++z) l_reason[z] = warp_sum(l_reason[z]);
+    if (lane == 0) {
+        atomicAdd(&s_counts[0], l_feas);
+        atomicAdd(&s_counts[2], l_colt);
+        atomicAdd(&s_counts[3], l_filt);
+#pragma unroll
+        for (int z = 0; z < 8; ++z) atomicAdd(&s_counts[8 + z], l_reason[z]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        bc = lane < 8 ? w_cost[lane] : __longlong_as_double(0x7ff0000000000000LL);
+        bi = lane < 8 ? w_idx[lane] : 0x7fffffff;
+        warp_lexmin(bc, bi);
+        if (lane == 0) { s_wc = bc; s_wi = bi; }
+    }
+    __syncthreads();
+    const bool none = s_wi == 0x7fffffff;
+    if (s_counts[2] > 0) {                      // colliders ranked before the winner (all of them without a winner)
+        const double wc = s_wc;
+        const int wi = s_wi;
+        int local = 0;
+        for (int k = tid; k < n; k += blockDim.x)
+            if ((info[k] & 0xFF) == ST_COLLISION && (none || lex_less(cost[k], k, wc, wi))) ++local;
+        local = warp_sum(local);
+        if (lane == 0 && local) atomicAdd(&s_before, local);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        rp_plan_result& r = results[blockIdx.x].r;
+        r.winner = none ? -1 : s_wi;
+        r.winner_cost = none ? __longlong_as_double(0x7ff8000000000000LL) : s_wc;
+        r.n_candidates = n;
+        r.n_feasible = s_counts[0];
+        r.n_infeasible_kinematics = n - s_counts[3] - s_counts[0];
+        r.n_infeasible_collision = s_before;
+        r.n_collision_total = s_counts[2];
+        for (int z = 0; z < 8; ++z) r.reason_counts[z] = s_counts[8 + z];
+        results[blockIdx.x].n_filtered = s_counts[3];
+    }
 }
 
 // ---- multi-GPU bundle shards: each rank owns a contiguous tile of the enumeration space --------

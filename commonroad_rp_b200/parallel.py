@@ -39,11 +39,10 @@ def global_argmin(engine, rec: torch.Tensor, world: int, group=None):
 
 
 class ScenarioBatch:
-    """Independent scenarios evaluated back to back (BASELINE config 5: scenario-major sharding, no exchange
-    on the data path).  Every scenario keeps its own device context (reference tables, obstacle tables,
-    verdict buffers stay resident); a replanning cycle uploads all inputs, enqueues all launches without
-    any host synchronisation in between, and only then collects the results, so the kernels of consecutive
-    scenarios run back to back on the stream while the host is already enqueueing the next ones."""
+    """Independent scenarios evaluated together (BASELINE config 5: scenario-major sharding, no exchange on the data
+    path).  Every scenario keeps its own device context (reference tables, obstacle tables stay resident); a
+    replanning cycle of ALL scenarios is one host->device copy, four kernel launches over a global (scenario, chunk)
+    work queue and one device->host copy (``_lib.Batch`` / rp_batch_* of the C-ABI)."""
 
     def __init__(self, device=None, stream=None):
         from commonroad_rp_b200._device import current_device_and_stream
@@ -53,6 +52,7 @@ class ScenarioBatch:
             stream = st if stream is None else stream
         self.device, self.stream = device, stream
         self.engines = []
+        self._batch = None
 
     def add_scenario(self, vehicle, coordinate_system, collision_checker):
         """vehicle: VehicleConfiguration; coordinate_system: CoordinateSystem; collision_checker:
@@ -66,29 +66,50 @@ class ScenarioBatch:
                           tb["path_s"], tb["path_normals"], tb["proj_limit"])
         collision_checker.upload(eng)
         self.engines.append(eng)
+        if self._batch is not None:
+            self._batch.close()
+            self._batch = None
         return len(self.engines) - 1
 
     def __len__(self):
         return len(self.engines)
 
+    @property
+    def batch(self):
+        if self._batch is None:
+            from commonroad_rp_b200._lib import Batch
+            self._batch = Batch(self.engines, self.stream)
+        return self._batch
+
     def upload(self, cycle_inputs):
-        """cycle_inputs[k] = (rp_plan_inputs, t, lon, d) of scenario k."""
-        for eng, (inputs, t, lon, d) in zip(self.engines, cycle_inputs):
-            eng.grid_upload(inputs, t, lon, d)
+        """cycle_inputs[k] = (rp_plan_inputs, t, lon, d[, traj_len]) of scenario k."""
+        b = self.batch
+        for k, item in enumerate(cycle_inputs):
+            b.set_inputs(k, *item)
 
     def launch(self):
-        for eng in self.engines:
-            eng.grid_launch()
+        self.batch.launch()
 
     def results(self):
-        return [eng.grid_result() for eng in self.engines]
+        return self.batch.results()
 
     def plan(self, cycle_inputs):
         self.upload(cycle_inputs)
         self.launch()
         return self.results()
 
+    def plan_one_by_one(self, cycle_inputs):
+        """the same cycle as one launch chain per scenario (what the batch replaces; kept for comparison)"""
+        for eng, item in zip(self.engines, cycle_inputs):
+            eng.grid_upload(*item)
+        for eng in self.engines:
+            eng.grid_launch()
+        return [eng.grid_result() for eng in self.engines]
+
     def close(self):
+        if self._batch is not None:
+            self._batch.close()
+            self._batch = None
         for eng in self.engines:
             eng.close()
         self.engines = []

@@ -191,6 +191,25 @@ int rp_set_candidate_range(rp_ctx* ctx, int first, int count);
 int rp_export_record_dev(rp_ctx* ctx, double* dev_dst4);
 int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double* dev_out1);
 
+/* ---- batches of independent scenarios (reactive_planner.py has no counterpart: one ReactivePlanner per scenario
+ * and process; BASELINE configs[4]) ------------------------------------------------------------------------------
+ * A batch groups contexts of ONE device -- each with its own vehicle, reference and obstacle tables -- and
+ * evaluates one replanning cycle of all of them with one host->device copy, four launches (no per-scenario launch)
+ * and one device->host copy.  Select-only mode (no draw_all / want_all_states), N + 1 <= 128.  stream: as in
+ * rp_ctx_create (NULL: the first context's stream).  The contexts stay usable on their own between batch cycles. */
+typedef struct rp_batch rp_batch;
+int rp_batch_create(rp_ctx* const* ctxs, int n, void* stream, rp_batch** out);
+int rp_batch_destroy(rp_batch* b);
+int rp_batch_size(rp_batch* b);
+/* inputs of scenario k for the next rp_batch_launch (same arguments as rp_grid_upload; host side only) */
+int rp_batch_set_inputs(rp_batch* b, int k, const rp_plan_inputs* in, int n_t, const double* t, const int32_t* traj_len,
+                        int n_lon, const double* lon, int n_d, const double* d);
+int rp_batch_launch(rp_batch* b);                              /* asynchronous on the batch's stream */
+int rp_batch_results(rp_batch* b, rp_plan_result* out);        /* out[rp_batch_size]; synchronises */
+int rp_batch_fetch_candidates(rp_batch* b, int k, double* cost, int32_t* status, int32_t* reason, int32_t* step);
+/* device time of the last rp_batch_launch (its four launches) and the candidates it evaluated */
+int rp_batch_last_ms(rp_batch* b, float* ms, long long* n_candidates);
+
 /* ---- results of the last plan call ----------------------------------------------------------- */
 /* 14 x (N+1) state rows (rp_state_row order) of candidate idx; available for the winner always,
  * for every candidate when want_all_states was set.  Other indices are re-evaluated on demand. */

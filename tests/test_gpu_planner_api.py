@@ -311,27 +311,32 @@ def test_lazy_collision_mode_is_exact_for_reference_outputs():
 
 
 def test_scenario_batch_equals_individual_plans():
-    """config-5 shape: independent seeded scenarios evaluated back to back give what each gives alone"""
+    """config-5 shape: independent seeded scenarios (different paths, obstacles, horizons, sample levels) evaluated
+    by ONE set of launches give, candidate by candidate, what each scenario gives alone"""
     from commonroad_rp_b200 import _lib, collision
     from commonroad_rp_b200.parallel import ScenarioBatch
     from commonroad_rp_b200.utility.config import VehicleConfiguration
     from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
     veh = VehicleConfiguration()
     batch = ScenarioBatch()
-    cycle, single = [], []
+    cycle, single, arrays = [], [], []
     keys = ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes", "boundary_tris")
-    for sid in range(6):
+    for sid in range(7):
         scn, s_dot0, d0 = synthetic.scenario_seeded(sid)
         co = CoordinateSystem(scn["ref_path"])
         cc = collision.checker_from_arrays(**{k: scn[k] for k in keys})
         batch.add_scenario(veh, co, cc)
+        N = (20, 30, 20, 60, 20, 25, 20)[sid]
+        level = (2, 1, 3, 2, 2, 2, 1)[sid]
+        if sid == 5:
+            s_dot0 = 2.0                       # low-velocity mode: one lateral system per candidate
         lo = max(0.0, s_dot0 - 0.125 * 2.0 * veh.a_max)
-        t, lon, dset = H.level_sets(2, 0.4, 2.0, 0.1, lo, max(lo + 5.0, s_dot0 + 2))
+        t, lon, dset = H.level_sets(level, 0.4, N * 0.1, 0.1, lo, max(lo + 5.0, s_dot0 + 2))
         d = [float(x) for x in dset.union({d0})]
         s0 = float(co.ref_pos[10])
         j = int(np.argmax(co.ref_pos > s0)) - 1
-        inputs = _lib.Engine.make_inputs([s0, s_dot0, 0.0], [d0, 0.0, 0.0], float(co.ref_theta[j]), 0, s_dot0 < 4.0,
-                                         "velocity_keeping", 20, 0.1, desired_speed=s_dot0)
+        inputs = _lib.Engine.make_inputs([s0, s_dot0, 0.0], [d0, 0.0, 0.0], float(co.ref_theta[j]), 3 * sid, s_dot0 < 4.0,
+                                         "velocity_keeping", N, 0.1, desired_speed=s_dot0)
         cycle.append((inputs, t, lon, d))
         eng = _lib.Engine(0)
         eng.set_vehicle(veh.length, veh.width, veh.wb_rear_axle, veh.wheelbase, veh.a_max, veh.v_switch, veh.delta_max,
@@ -341,12 +346,26 @@ def test_scenario_batch_equals_individual_plans():
                           tb["path_normals"], tb["proj_limit"])
         cc.upload(eng)
         r = eng.plan_grid(inputs, t, lon, d)
-        single.append((r.winner, r.winner_cost, r.n_infeasible_kinematics, r.n_infeasible_collision))
+        single.append((r.winner, r.winner_cost, r.n_infeasible_kinematics, r.n_infeasible_collision, r.n_feasible,
+                       r.n_collision_total, list(r.reason_counts)))
+        arrays.append(eng.fetch_candidates())
         eng.close()
+    same = lambda a, b: (a == b) or (np.isnan(a) and np.isnan(b))
     for rep in range(2):                      # second cycle reuses the resident tables and staging buffers
-        got = [(r.winner, r.winner_cost, r.n_infeasible_kinematics, r.n_infeasible_collision) for r in batch.plan(cycle)]
+        res = batch.plan(cycle)
+        got = [(r.winner, r.winner_cost, r.n_infeasible_kinematics, r.n_infeasible_collision, r.n_feasible,
+                r.n_collision_total, list(r.reason_counts)) for r in res]
         assert [g[0] for g in got] == [s[0] for s in single]
         assert all(g[2:] == s[2:] for g, s in zip(got, single))
-        assert all((g[1] == s[1]) or (np.isnan(g[1]) and np.isnan(s[1])) for g, s in zip(got, single))
+        assert all(same(g[1], s[1]) for g, s in zip(got, single))
+        for k in range(len(cycle)):
+            cost, status, reason, step = batch.batch.fetch_candidates(k)
+            c0, st0, r0, sp0 = arrays[k]
+            assert np.array_equal(status, st0) and np.array_equal(reason, r0) and np.array_equal(step, sp0), k
+            assert np.array_equal(cost.view(np.int64), c0.view(np.int64)), k          # identical bits
+    one = batch.plan_one_by_one(cycle)
+    assert [r.winner for r in one] == [s[0] for s in single]
     assert len({g[0] for g in got}) > 1       # the scenarios really differ
+    ms, n = batch.batch.last_ms()
+    assert ms > 0 and n == sum(len(c[1]) * len(c[2]) * len(c[3]) for c in cycle)
     batch.close()
