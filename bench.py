@@ -250,7 +250,7 @@ def replanning_latency_port(name="ZAM_Over-1_1", max_cycles=6):
             "scenario": "%s, N=%d" % (name, meta["N"]), "api": "oracle port, single process"}
 
 
-def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3):
+def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0, world=1):
     """BASELINE configs[4] shape on one rank: independent seeded scenarios, default level-3 grid at N = 60
     (29 t x 17 v x 18 d = 8 874 candidates each), one resident device context per scenario, launches
     enqueued back to back (commonroad_rp_b200.parallel.ScenarioBatch).  Returns candidates/s."""
@@ -266,7 +266,7 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3):
     keys = ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes", "boundary_tris")
     batch = ScenarioBatch(device, stream_handle)
     cycle, n_cand = [], 0
-    for sid in range(n_scenarios):
+    for sid in range(rank * n_scenarios, (rank + 1) * n_scenarios):       # scenario-major shards: no exchange on the data path
         scn, s_dot0, d0 = synthetic.scenario_seeded(sid)
         co = CoordinateSystem(scn["ref_path"])
         batch.add_scenario(cfg.vehicle, co, collision.checker_from_arrays(**{k: scn[k] for k in keys}))
@@ -285,6 +285,9 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3):
     for _ in range(2):
         batch.plan(cycle)                               # warm-up (allocations, geometry)
     torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     t0 = time.perf_counter()
     dev_ms = []
     for _ in range(cycles):
@@ -293,6 +296,14 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3):
     torch.cuda.synchronize()
     dt_s = (time.perf_counter() - t0) / cycles
     n_win = sum(1 for r in res if r.winner >= 0)
+    n_local = n_cand
+    if world > 1:                                       # whole job: all ranks' scenarios / slowest rank
+        agg = torch.tensor([dt_s, float(np.mean(dev_ms))], dtype=torch.float64, device="cuda:%d" % device)
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([float(n_cand), float(n_win)], dtype=torch.float64, device="cuda:%d" % device)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dt_s, dev_ms = float(agg[0].item()), [float(agg[1].item())]
+        n_cand, n_win, n_scenarios = int(cnt[0].item()), int(cnt[1].item()), n_scenarios * world
     batch.plan_one_by_one(cycle)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -304,7 +315,7 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3):
     return {"value": n_cand / dt_s, "unit": UNIT, "scenarios": n_scenarios, "candidates_per_scenario": n_cand // n_scenarios,
             "ms_per_cycle_of_all_scenarios": 1e3 * dt_s, "device_ms_per_cycle": float(np.mean(dev_ms)),
             "device_value": n_cand / (float(np.mean(dev_ms)) * 1e-3), "scenarios_with_winner": n_win,
-            "one_launch_chain_per_scenario": {"value": n_cand / one_s, "ms_per_cycle_of_all_scenarios": 1e3 * one_s},
+            "one_launch_chain_per_scenario": {"value": n_local / one_s, "ms_per_cycle_of_one_ranks_scenarios": 1e3 * one_s},
             "note": "rp_batch_*: one H2D, four launches, one D2H per cycle of all scenarios; wall clock incl. host "
                     "staging of every scenario's inputs (host buffers) and D2H of every result"}
 
@@ -544,6 +555,7 @@ def main():
         lazy_res = eng.grid_result()
         assert lazy_res.winner == res.winner and lazy_res.n_infeasible_collision == res.n_infeasible_collision
 
+    scen = scenario_batch_rate(local_rank, stream.cuda_stream, rank=rank, world=world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -593,7 +605,7 @@ def main():
                                         "frac": gbs / peaks.get("hbm_gbs"), "traffic": None, "kernel_ms": full,
                                         "peak_source": peak_kind + " (MEASURED_PEAKS.json)"}
     line["p50_replanning_cycle_ms"] = replanning_latency_b200()
-    line["scenario_batch"] = scenario_batch_rate(local_rank, stream.cuda_stream)
+    line["scenario_batch"] = scen
     if not args.no_cpu_baseline:
         line["p50_replanning_cycle_ms"]["cpu_port"] = replanning_latency_port()
         cores = 1

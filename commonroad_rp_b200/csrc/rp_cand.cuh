@@ -62,10 +62,17 @@ __device__ __forceinline__ bool dyn_collides_f32(const ObstacleTables& O, const 
     return false;
 }
 
-// first index with a[idx] > x, walking from a guess (the previous step's answer); identical to upper_bound()
-__device__ __forceinline__ int upper_bound_from(const double* __restrict__ a, int n, double x, int j) {
-    while (j < n && a[j] <= x) ++j;
-    while (j > 0 && a[j - 1] > x) --j;
+// first index with a[idx] > x (identical to upper_bound()), from the O(1) guess of a uniform table; returns the
+// bracketing values lo = a[idx - 1] (-inf if idx == 0) and hi = a[idx] (+inf if idx == n) it verified the guess with
+__device__ __forceinline__ int locate_segment(const double* __restrict__ a, int n, double x, double inv_step, double& lo,
+                                              double& hi) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double f = (x - a[0]) * inv_step;
+    int j = f > 0.0 ? (f < (double)(n - 1) ? (int)f + 1 : n) : 0;
+    hi = j < n ? a[j] : inf;
+    lo = j > 0 ? a[j - 1] : -inf;
+    while (hi <= x) { lo = hi; ++j; hi = j < n ? a[j] : inf; }
+    while (lo > x) { hi = lo; --j; lo = j > 0 ? a[j - 1] : -inf; }
     return j;
 }
 
@@ -80,11 +87,10 @@ struct StepIn {
     const double *cs, *cd;       // the candidate's longitudinal / lateral coefficients (re-read every step: L1-resident,
                                  // the longitudinal row is a warp-wide broadcast; keeps 24 registers free)
     double th_prev, kap_prev;
-    int i, ub;
+    int i;
 };
 struct StepOut {
     double x, y, th_gl, th_cl, v, a, kappa, s, sv, d, dv;
-    int ub;
     unsigned pre;        // pre-filter bits of this step (:796-805)
     int reason;          // first violated limit of this step (R_NONE if none)
     int proj_fail;       // projection domain left at this step (:911-917)
@@ -146,11 +152,14 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
         dp = dv;
         dpp = da;
     }
-    const int ub = I.ub < 0 ? upper_bound_guess(R.pos, R.n, s, P.ref_inv_step) : upper_bound_from(R.pos, R.n, s, I.ub);
+    // reference segment (:835): first index with ref_pos > s, from an O(1) guess on the near-uniform table; the two
+    // loads that verify the guess ARE ref_pos[j0], ref_pos[j1]
+    double p0, p1;
+    const int ub = locate_segment(R.pos, R.n, s, P.ref_inv_step, p0, p1);
     const bool wrap = (ub == R.n) || (ub == 0);                 // s_idx == -1: python index wrap (App. B#8)
     const int j0 = wrap ? R.n - 1 : ub - 1;
     const int j1 = wrap ? 0 : ub;
-    const double p0 = R.pos[j0], p1 = R.pos[j1];
+    if (wrap) { p0 = R.pos[j0]; p1 = R.pos[j1]; }
     const double seg_len = p1 - p0;
     const double y_seg = D.rcp(seg_len);
     const double lam = D.div(s - p0, seg_len, y_seg);
@@ -165,7 +174,7 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
         th_gl = th_cl + th_ref;
         // theta_cl = atan(dp): cos(theta_cl) = 1 / sqrt(1 + dp^2), tan(theta_cl) = dp (<= 1 ulp from libm)
         const double hyp = sqrt(1.0 + dp * dp);
-        cosT = D.div(1.0, hyp, D.rcp(hyp));
+        cosT = D.div_nz(1.0, hyp, D.rcp(hyp));
         tanT = dp;
     } else {
         // standstill in high-velocity mode keeps the previous global orientation (:866-873)
@@ -181,9 +190,9 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
     const double k_r_d = (R.curv_d[j1] - kd0) * lam + kd0;
     const double oneKrD = (1 - k_r * d);
     const double y_cos = D.rcp(cosT);
-    const double q = D.div(cosT, oneKrD, D.rcp(oneKrD));
+    const double q = D.div_nz(cosT, oneKrD, D.rcp(oneKrD));
     const double kappa = (dpp + (k_r * dp + k_r_d * d) * tanT) * cosT * (q * q) + q * k_r;
-    const double v = sv * D.div(oneKrD, cosT, y_cos);
+    const double v = sv * D.div_nz(oneKrD, cosT, y_cos);
     const double a = D.div(sa * oneKrD, cosT, y_cos) +
                      D.div(sv * sv, cosT, y_cos) * (oneKrD * tanT * (D.div(kappa * oneKrD, cosT, y_cos) - k_r) -
                                                     (k_r_d * d + k_r * dp));
@@ -200,13 +209,13 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
         const bool c_y = fabs(D.div(rint(yaw_rate * 100000.0), 100000.0, Y.y_1e5)) > L.kappa_max * v;
         // cos(atan2(wb * kappa, 1))^2 == 1 / (1 + (wb * kappa)^2)  (see check_constraints)
         const double tk = L.wheelbase * kappa;
-        const double kappa_dot_max = D.div(L.v_delta_max * (1.0 + tk * tk), L.wheelbase, Y.y_wb);
+        const double kappa_dot_max = D.div_nz(L.v_delta_max * (1.0 + tk * tk), L.wheelbase, Y.y_wb);
         const double kd_q = D.div(kappa - I.kap_prev, dt, Y.y_dt);
         const double kappa_dot = i > 0 ? kd_q : 0.;
         const bool c_kd = fabs(kappa_dot) > kappa_dot_max;
         const bool fast = v > L.v_switch;
         const double vv = fast ? v : 1.0;
-        const double a_hi_q = D.div(L.a_max * L.v_switch, vv, D.rcp(vv));
+        const double a_hi_q = D.div_nz(L.a_max * L.v_switch, vv, D.rcp(vv));
         const double a_hi = fast ? a_hi_q : L.a_max;
         const bool c_a = !(-L.a_max <= a && a <= a_hi);
         int r = R_NONE;
@@ -244,7 +253,6 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
         o.proj_fail = ok ? 0 : 1;
     }
     o.th_gl = th_gl; o.th_cl = th_cl; o.v = v; o.a = a; o.kappa = kappa; o.s = s; o.sv = sv; o.d = d; o.dv = dv;
-    o.ub = ub;
     o.reject = D.reject;
     return o;
 }
@@ -327,7 +335,6 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     }
 
     unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
-    int ub = -1;
     // values of the current / last polynomial step (the extension reads them after step tl - 1)
     double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
     double cn = 1., sn = 0.;                       // cos / sin of th_gl
@@ -338,14 +345,14 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         double px, py;                             // rear-axle position of this step
         double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
         if (i < tl) {
-            I.i = i; I.ub = ub; I.th_prev = th_gl; I.kap_prev = kappa;
+            I.i = i; I.th_prev = th_gl; I.kap_prev = kappa;
             StepOut o = poly_step<false>(P, R, Y, I);
             if (o.reject & 0x80000000u) o = poly_step_exact(P, R, Y, I);
             pre |= o.pre;
             if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
             if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
             x = o.x; y = o.y; th_gl = o.th_gl; th_cl = o.th_cl; v = o.v; a = o.a; kappa = o.kappa;
-            s = o.s; sv = o.sv; d = o.d; dv = o.dv; ub = o.ub;
+            s = o.s; sv = o.sv; d = o.d; dv = o.dv;
             if (in.check_collision || i == tl - 1) sincos(th_gl, &sn, &cn);
             px = x; py = y;
             c_a = a; c_v = v; c_s = s; c_d = d; c_th = th_cl;
@@ -497,9 +504,9 @@ cand_kernel(const __grid_constant__ PlanParams P) {
     Segment* const s_segs = reinterpret_cast<Segment*>(sp);
     for (int q = tid; q < P.n_segs; q += BLOCK) s_segs[q] = P.segs[q];
     if (tid == 0) {
-        s_Y->y_dt = rcp_refined(P.in.dt);
-        s_Y->y_1e5 = rcp_refined(100000.0);
-        s_Y->y_wb = rcp_refined(P.lim.wheelbase);
+        s_Y->y_dt = rcp_window(P.in.dt);
+        s_Y->y_1e5 = rcp_window(100000.0);
+        s_Y->y_wb = rcp_window(P.lim.wheelbase);
     }
     __syncthreads();
     const int lane = tid & 31;
@@ -552,9 +559,9 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
         if (lo != sc_cached) {                           // warp-uniform
             __syncwarp();
             if (lane == 0) {
-                s_Y->y_dt = rcp_refined(P.in.dt);
-                s_Y->y_1e5 = rcp_refined(100000.0);
-                s_Y->y_wb = rcp_refined(P.lim.wheelbase);
+                s_Y->y_dt = rcp_window(P.in.dt);
+                s_Y->y_1e5 = rcp_window(100000.0);
+                s_Y->y_wb = rcp_window(P.lim.wheelbase);
             }
             __syncwarp();
             sc_cached = lo;

@@ -292,9 +292,15 @@ int build_obstacle_tables(rp_ctx* ctx) {
                     bits[c >> 5] |= 1u << (c & 31);
                 }
         }
+        // second half of the buffer: occupancy bits (cell list non-empty)
+        const size_t n_words = bits.size();
+        bits.resize(2 * n_words, 0u);
+        for (size_t c = 0; c + 1 < start.size(); ++c)
+            if (start[c + 1] > start[c]) bits[n_words + (c >> 5)] |= 1u << (c & 31);
         if (int rc = ctx->d_clr.ensure(bits.size() * sizeof(unsigned))) return rc;
         RP_CUDA(cudaMemcpyAsync(ctx->d_clr.p, bits.data(), bits.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
         O.clr_bits = ctx->d_clr.as<unsigned>();
+        O.occ_bits = ctx->d_clr.as<unsigned>() + n_words;
         O.clr_off = clr_off;
         if (int rc = ctx->d_obb.ensure(obb.size() * sizeof(double))) return rc;
         if (int rc = ctx->d_tri.ensure(std::max<size_t>(ctx->h_tri.size(), 6) * sizeof(double))) return rc;
