@@ -89,6 +89,8 @@ SIGNATURES = {
     "rp_batch_results": (C.c_int, [C.c_void_p, C.POINTER(PlanResult)]),
     "rp_batch_fetch_candidates": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, _ip, _ip]),
     "rp_batch_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
+    "rp_initial_states": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, _dp, _dp, _ip]),
+    "rp_batch_initial_states": (C.c_int, [C.c_void_p, _dp, _ip, _dp, _dp, _ip]),
     "rp_selftest_divide": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
     "rp_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rp_stage_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
@@ -263,6 +265,17 @@ class Engine:
                                            C.byref(res)))
         return res
 
+    def initial_states(self, x0, low_vel_mode):
+        """Cartesian rear-axle states x0[n][6] = (x, y, orientation, velocity, acceleration, steering_angle) ->
+        (x_0_lon[n][3], x_0_lat[n][3], status[n]) on the device (reactive_planner.py:446-512)."""
+        x0 = _f64(x0).reshape(-1, 6)
+        lv = _i32(np.broadcast_to(np.asarray(low_vel_mode, dtype=np.int32), (x0.shape[0],)))
+        lon, lat = np.empty((x0.shape[0], 3)), np.empty((x0.shape[0], 3))
+        status = np.empty(x0.shape[0], dtype=np.int32)
+        self._check(self._lib.rp_initial_states(self._ctx, x0.shape[0], _p(x0, _dp), _p(lv, _ip), _p(lon, _dp), _p(lat, _dp),
+                                                _p(status, _ip)))
+        return lon, lat, status
+
     def selftest_divide(self, a, b):
         """(shared-reciprocal quotient, plain a / b) as computed on the device."""
         a, b = _f64(a).ravel(), _f64(b).ravel()
@@ -395,6 +408,16 @@ class Batch:
         status, reason, step = (np.empty(n, dtype=np.int32) for _ in range(3))
         self._check(self._lib.rp_batch_fetch_candidates(self._b, int(k), _p(cost, _dp), _p(status, _ip), _p(reason, _ip), _p(step, _ip)))
         return cost, status, reason, step
+
+    def initial_states(self, x0, low_vel_mode):
+        """one Cartesian state per scenario, x0[n_scenarios][6] -> (x_0_lon, x_0_lat, status), each scenario against its
+        own reference tables (the batched reset() of SURVEY 8f rank 1)"""
+        n = len(self.engines)
+        x0 = _f64(x0).reshape(n, 6)
+        lv = _i32(np.broadcast_to(np.asarray(low_vel_mode, dtype=np.int32), (n,)))
+        lon, lat, status = np.empty((n, 3)), np.empty((n, 3)), np.empty(n, dtype=np.int32)
+        self._check(self._lib.rp_batch_initial_states(self._b, _p(x0, _dp), _p(lv, _ip), _p(lon, _dp), _p(lat, _dp), _p(status, _ip)))
+        return lon, lat, status
 
     def last_ms(self):
         """(device milliseconds of the last launch, candidates it evaluated)"""

@@ -1496,3 +1496,74 @@ int rp_batch_last_ms(rp_batch* b, float* ms, long long* n_candidates) {
 }
 
 }  // extern "C"
+
+// ---- Cartesian -> curvilinear initial states on the device ---------------------------------------
+namespace {
+int run_initial_states(int device, cudaStream_t stream, int n, const double* x0, const int32_t* low_vel,
+                       const std::vector<rp::InitFrame>& frames, double* out_lon, double* out_lat, int32_t* status) {
+    RP_CUDA(cudaSetDevice(device));
+    DevBuf dx, dl, df, do1, do2, ds;
+    int rc = RP_OK;
+    auto cleanup = [&]() { dx.release(); dl.release(); df.release(); do1.release(); do2.release(); ds.release(); };
+    if ((rc = dx.ensure((size_t)n * 48)) || (rc = dl.ensure((size_t)n * 4)) || (rc = df.ensure(frames.size() * sizeof(rp::InitFrame))) ||
+        (rc = do1.ensure((size_t)n * 24)) || (rc = do2.ensure((size_t)n * 24)) || (rc = ds.ensure((size_t)n * 4))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemcpyAsync(dx.p, x0, (size_t)n * 48, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(dl.p, low_vel, (size_t)n * 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(df.p, frames.data(), frames.size() * sizeof(rp::InitFrame), cudaMemcpyHostToDevice, stream);
+    rp::initial_states_kernel<<<n, 128, 0, stream>>>(n, dx.as<double>(), dl.as<int>(), df.as<rp::InitFrame>(),
+                                                     frames.size() > 1 ? 1 : 0, do1.as<double>(), do2.as<double>(), ds.as<int>());
+    cudaMemcpyAsync(out_lon, do1.p, (size_t)n * 24, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(out_lat, do2.p, (size_t)n * 24, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(status, ds.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e));
+    return RP_OK;
+}
+
+rp::InitFrame frame_of(rp_ctx* ctx) {
+    rp::InitFrame F{};
+    const double* base = ctx->d_ref.as<double>();
+    const int n = ctx->ref_n;
+    F.ref.n = n;
+    F.ref.same_s = ctx->ref_same_s;
+    F.ref.limit = ctx->ref_limit;
+    F.ref.pos = base; F.ref.theta = base + n; F.ref.curv = base + 2 * n; F.ref.curv_d = base + 3 * n;
+    F.ref.px = base + 4 * n; F.ref.py = base + 5 * n; F.ref.nx = base + 6 * n; F.ref.ny = base + 7 * n;
+    F.ref.ps = base + 8 * n;
+    F.wheelbase = ctx->veh.wheelbase;
+    return F;
+}
+}  // namespace
+
+extern "C" {
+
+int rp_initial_states(rp_ctx* ctx, int n, const double* x0, const int32_t* low_vel_mode, double* out_lon, double* out_lat,
+                      int32_t* status) {
+    if (int rc = bind(ctx)) return rc;
+    if (n < 0) return fail(RP_ERR_ARG, "negative count");
+    if (n == 0) return RP_OK;
+    if (!x0 || !low_vel_mode || !out_lon || !out_lat || !status) return fail(RP_ERR_ARG, "null array");
+    if (!ctx->have_vehicle) return fail(RP_ERR_STATE, "vehicle parameters not set");
+    if (!ctx->have_ref) return fail(RP_ERR_STATE, "reference tables not set");
+    std::vector<rp::InitFrame> frames{frame_of(ctx)};
+    return run_initial_states(ctx->device, ctx->stream, n, x0, low_vel_mode, frames, out_lon, out_lat, status);
+}
+
+int rp_batch_initial_states(rp_batch* b, const double* x0, const int32_t* low_vel_mode, double* out_lon, double* out_lat,
+                            int32_t* status) {
+    if (!b) return fail(RP_ERR_ARG, "null batch");
+    if (!x0 || !low_vel_mode || !out_lon || !out_lat || !status) return fail(RP_ERR_ARG, "null array");
+    std::vector<rp::InitFrame> frames;
+    for (rp_ctx* c : b->ctxs) {
+        if (!c->have_vehicle || !c->have_ref) return fail(RP_ERR_STATE, "vehicle / reference tables not set for a scenario");
+        frames.push_back(frame_of(c));
+    }
+    if (frames.size() == 1) frames.push_back(frames[0]);      // stride 1 addressing
+    return run_initial_states(b->device, b->stream, (int)b->ctxs.size(), x0, low_vel_mode, frames, out_lon, out_lat, status);
+}
+
+}  // extern "C"

@@ -381,6 +381,130 @@ __global__ void __launch_bounds__(256) count_before_kernel(const double* __restr
     if (threadIdx.x == 0) atomicAdd(out, (double)total);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cartesian initial state -> curvilinear (lon, lat) initial states, batched.
+//   pycrccosy convert_to_curvilinear_coords as restated in oracle/third_party.py (:188-221): per segment the foot
+//   parameter of the pseudo-normal map solves a quadratic; the solution with the smallest |d| wins (first in
+//   (segment, root) order on ties); then reactive_planner.py:446-512 in the reference's operation order.
+// One block per state: threads scan the segments, a lexicographic (|d|, 2 j + root) block minimum picks the foot.
+// status: 0 ok, 1 outside the projection domain (the reference raises ValueError), 2 negative s_dot (Exception).
+// ------------------------------------------------------------------------------------------------
+struct InitFrame {
+    RefTables ref;
+    double wheelbase;
+};
+
+__global__ void __launch_bounds__(128) initial_states_kernel(int n_states, const double* __restrict__ x0,
+                                                             const int* __restrict__ low_vel,
+                                                             const InitFrame* __restrict__ frames, int frame_stride,
+                                                             double* __restrict__ out_lon, double* __restrict__ out_lat,
+                                                             int* __restrict__ status) {
+    __shared__ double w_key[4], w_s[4], w_d[4];
+    __shared__ int w_ord[4];
+    const int st = blockIdx.x;
+    if (st >= n_states) return;
+    const InitFrame& F = frames[(size_t)st * frame_stride];
+    const RefTables& R = F.ref;
+    const double px = x0[6 * st], py = x0[6 * st + 1];
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double best_key = inf, best_s = 0., best_d = 0.;
+    int best_ord = 0x7fffffff;
+    for (int j = threadIdx.x; j < R.n - 1; j += blockDim.x) {
+        const double p0x = R.px[j], p0y = R.py[j];
+        const double ex = R.px[j + 1] - p0x, ey = R.py[j + 1] - p0y;
+        const double mx = R.nx[j], my = R.ny[j];
+        const double dnx = R.nx[j + 1] - mx, dny = R.ny[j + 1] - my;
+        const double ax = px - p0x, ay = py - p0y;
+        const double qa = -(ex * dny - ey * dnx);
+        const double qb = (ax * dny - ay * dnx) - (ex * my - ey * mx);
+        const double qc = ax * my - ay * mx;
+        double roots[2];
+        int n_roots = 0;
+        if (fabs(qa) < 1e-14) {
+            if (fabs(qb) > 0.0) roots[n_roots++] = -qc / qb;
+        } else {
+            const double disc = qb * qb - 4.0 * qa * qc;
+            if (disc >= 0.0) {
+                const double sq = sqrt(disc);
+                roots[0] = (-qb + sq) / (2.0 * qa);
+                roots[1] = (-qb - sq) / (2.0 * qa);
+                n_roots = 2;
+            }
+        }
+        for (int r = 0; r < n_roots; ++r) {
+            double lam = roots[r];
+            if (!(-1e-12 <= lam && lam <= 1.0 + 1e-12)) continue;
+            lam = fmin(fmax(lam, 0.0), 1.0);
+            const double bx = p0x + lam * ex, by = p0y + lam * ey;
+            const double pnx = mx + lam * dnx, pny = my + lam * dny;
+            const double dd = ((px - bx) * pnx + (py - by) * pny) / (pnx * pnx + pny * pny);
+            const int ord = 2 * j + r;
+            if (fabs(dd) <= R.limit && (fabs(dd) < best_key || (fabs(dd) == best_key && ord < best_ord))) {
+                best_key = fabs(dd);
+                best_ord = ord;
+                best_d = dd;
+                best_s = R.ps[j] + lam * (R.ps[j + 1] - R.ps[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ok = __shfl_down_sync(0xffffffffu, best_key, off);
+        const int oo = __shfl_down_sync(0xffffffffu, best_ord, off);
+        const double os = __shfl_down_sync(0xffffffffu, best_s, off);
+        const double od = __shfl_down_sync(0xffffffffu, best_d, off);
+        if (ok < best_key || (ok == best_key && oo < best_ord)) { best_key = ok; best_ord = oo; best_s = os; best_d = od; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { w_key[warp] = best_key; w_ord[warp] = best_ord; w_s[warp] = best_s; w_d[warp] = best_d; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        if (w_key[w] < best_key || (w_key[w] == best_key && w_ord[w] < best_ord)) {
+            best_key = w_key[w]; best_ord = w_ord[w]; best_s = w_s[w]; best_d = w_d[w];
+        }
+    double* lon = out_lon + 3 * st;
+    double* lat = out_lat + 3 * st;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (best_ord == 0x7fffffff) {
+        status[st] = 1;
+        lon[0] = lon[1] = lon[2] = lat[0] = lat[1] = lat[2] = nan;
+        return;
+    }
+    // ---- reactive_planner.py:465-512 ----------------------------------------------------------------
+    const double s = best_s, d = best_d;
+    const double orientation = x0[6 * st + 2], velocity = x0[6 * st + 3], acceleration = x0[6 * st + 4];
+    const double steering = x0[6 * st + 5];
+    const int ub = upper_bound(R.pos, R.n, s);               // np.argmax(ref_pos > s) (0 if none)
+    const int ub_np = ub == R.n ? 0 : ub;
+    const int i0 = ub_np == 0 ? R.n - 1 : ub_np - 1;          // s_idx = argmax - 1, python index wrap for -1
+    const int i1 = ub_np == 0 ? 0 : ub_np;                    // s_idx + 1
+    const double s_lambda = (s - R.pos[i0]) / (R.pos[i1] - R.pos[i0]);
+    const double theta_cl = orientation - interpolate_angle(s, R.pos[i0], R.pos[i1], R.theta[i0], R.theta[i1]);
+    const double kr = (R.curv[i1] - R.curv[i0]) * s_lambda + R.curv[i0];
+    const double kr_d = (R.curv_d[i1] - R.curv_d[i0]) * s_lambda + R.curv_d[i0];
+    const double kappa_0 = tan(steering) / F.wheelbase;
+    const double one_krd = 1 - kr * d;
+    const double tan_t = tan(theta_cl), cos_t = cos(theta_cl);
+    const double d_p = one_krd * tan_t;
+    const double d_pp = -(kr_d * d + kr * d_p) * tan_t + (one_krd / (cos_t * cos_t)) * (kappa_0 * one_krd / cos_t - kr);
+    const double s_velocity = velocity * cos_t / one_krd;
+    double s_acceleration = acceleration;
+    s_acceleration -= (s_velocity * s_velocity / cos_t) * (one_krd * tan_t * (kappa_0 * one_krd / cos_t - kr) - (kr_d * d + kr * d_p));
+    s_acceleration /= (one_krd / cos_t);
+    double d_velocity, d_acceleration;
+    if (low_vel[st]) {
+        d_velocity = d_p;
+        d_acceleration = d_pp;
+    } else {
+        d_velocity = velocity * sin(theta_cl);
+        d_acceleration = s_acceleration * d_p + s_velocity * s_velocity * d_pp;
+    }
+    lon[0] = s; lon[1] = s_velocity; lon[2] = s_acceleration;
+    lat[0] = d; lat[1] = d_velocity; lat[2] = d_acceleration;
+    status[st] = s_velocity < 0 ? 2 : 0;
+}
+
 // pycrcc.CollisionChecker.collide for a batch of ego boxes (rp_collide_poses)
 __global__ void collide_kernel(int n, const double* __restrict__ pose, const int* __restrict__ tidx, double hl,
                                double hw, double r_ego, ObstacleTables O, int vehicle_box, uint8_t* __restrict__ hit) {

@@ -322,8 +322,8 @@ class ReactivePlanner(object):
             self._infeasible_reason_dict[constraint] = 0
 
     # ------------------------------------------------------------------ device tables
-    def _sync_device_tables(self):
-        """Upload vehicle / reference / obstacle tables when they changed since the last cycle."""
+    def _sync_frame_tables(self):
+        """Upload vehicle / reference tables when they changed since the last cycle."""
         eng = self.engine
         vp = self.vehicle_params
         vkey = (vp.length, vp.width, vp.wb_rear_axle, vp.wheelbase, vp.a_max, vp.v_switch, vp.delta_max, vp.v_delta_max)
@@ -336,6 +336,11 @@ class ReactivePlanner(object):
             eng.set_reference(tb["ref_pos"], tb["ref_theta"], tb["ref_curv"], tb["ref_curv_d"], tb["path_xy"],
                               tb["path_s"], tb["path_normals"], tb["proj_limit"])
             self._uploaded_co = self._co
+
+    def _sync_device_tables(self):
+        """Upload vehicle / reference / obstacle tables when they changed since the last cycle."""
+        self._sync_frame_tables()
+        eng = self.engine
         cc_key = (id(self._cc), self._cc.version)
         if self._uploaded_cc != cc_key:
             self._cc.upload(eng)
@@ -511,42 +516,22 @@ class ReactivePlanner(object):
 
     # ------------------------------------------------------------------ host glue around the hot path
     def _compute_initial_states(self, x_0: ReactivePlannerState) -> (np.ndarray, np.ndarray):
-        """Cartesian initial state -> curvilinear (lon, lat) initial states (reference :446-512; once per
-        cycle, host)."""
+        """Cartesian initial state -> curvilinear (lon, lat) initial states (reference :446-512) on the device:
+        the pseudo-normal projection over all path segments and the Frenet derivative formulas are one kernel
+        (rp_initial_states); errors are raised exactly as the reference raises them."""
         if not self._co:
             return None
-        try:
-            s, d = self._co.convert_to_curvilinear_coords(x_0.position[0], x_0.position[1])
-        except ValueError:
+        self._sync_frame_tables()
+        lon, lat, status = self.engine.initial_states(
+            [x_0.position[0], x_0.position[1], x_0.orientation, x_0.velocity, x_0.acceleration, x_0.steering_angle],
+            self._low_vel_mode)
+        if status[0] == 1:
             logger.critical("Initial state could not be transformed.")
             raise ValueError("Initial state could not be transformed.")
-        co = self._co
-        s_idx = np.argmax(co.ref_pos > s) - 1
-        s_lambda = (s - co.ref_pos[s_idx]) / (co.ref_pos[s_idx + 1] - co.ref_pos[s_idx])
-        ref_theta = np.unwrap(co.ref_theta)
-        theta_cl = x_0.orientation - interpolate_angle(s, co.ref_pos[s_idx], co.ref_pos[s_idx + 1], ref_theta[s_idx],
-                                                       ref_theta[s_idx + 1])
-        kr = (co.ref_curv[s_idx + 1] - co.ref_curv[s_idx]) * s_lambda + co.ref_curv[s_idx]
-        kr_d = (co.ref_curv_d[s_idx + 1] - co.ref_curv_d[s_idx]) * s_lambda + co.ref_curv_d[s_idx]
-        kappa_0 = np.tan(x_0.steering_angle) / self.vehicle_params.wheelbase
-        one_krd = 1 - kr * d
-        tan_t, cos_t = np.tan(theta_cl), math.cos(theta_cl)
-        d_p = one_krd * tan_t
-        d_pp = -(kr_d * d + kr * d_p) * tan_t + (one_krd / (cos_t ** 2)) * (kappa_0 * one_krd / cos_t - kr)
-        s_velocity = x_0.velocity * cos_t / one_krd
-        if s_velocity < 0:
+        if status[0] == 2:
             raise Exception("Initial state or reference incorrect! Curvilinear velocity is negative which indicates"
                             "that the ego vehicle is not driving in the same direction as specified by the reference")
-        s_acceleration = x_0.acceleration
-        s_acceleration -= (s_velocity ** 2 / cos_t) * (one_krd * tan_t * (kappa_0 * one_krd / cos_t - kr) -
-                                                       (kr_d * d + kr * d_p))
-        s_acceleration /= (one_krd / cos_t)
-        if self._low_vel_mode:
-            d_velocity, d_acceleration = d_p, d_pp
-        else:
-            d_velocity = x_0.velocity * math.sin(theta_cl)
-            d_acceleration = s_acceleration * d_p + s_velocity ** 2 * d_pp
-        return [s, s_velocity, s_acceleration], [d, d_velocity, d_acceleration]
+        return [float(v) for v in lon[0]], [float(v) for v in lat[0]]
 
     def _compute_trajectory_pair(self, trajectory: TrajectorySample) -> Tuple[Trajectory, Trajectory, List, List]:
         """Optimal sample -> (Cartesian Trajectory, curvilinear Trajectory, lon list, lat list)

@@ -219,6 +219,18 @@ int rp_fetch_candidates(rp_ctx* ctx, double* cost, int32_t* status, int32_t* rea
 /* coefficients as solved on the device: lon[n][6], lat[n][6], delta_tau_lat[n] */
 int rp_fetch_coeffs(rp_ctx* ctx, double* coeffs_lon, double* coeffs_lat, double* delta_tau_lat);
 
+/* ---- the step before the path ------------------------------------------------ */
+/* ReactivePlanner._compute_initial_states (reactive_planner.py:446-512) incl. pycrccosy's
+ * convert_to_curvilinear_coords, batched: x0[n][6] = x, y, orientation, velocity, acceleration, steering_angle of the
+ * rear-axle state; low_vel_mode[n] (d derivatives w.r.t. arc length instead of time, :498-505) ->
+ * out_lon[n][3] = s, s_dot, s_ddot; out_lat[n][3] = d, d_dot, d_ddot; status[n]: 0 ok, 1 outside the projection
+ * domain (the reference raises ValueError, :459-461), 2 negative s_dot (the reference raises Exception, :489-491). */
+int rp_initial_states(rp_ctx* ctx, int n, const double* x0, const int32_t* low_vel_mode, double* out_lon, double* out_lat,
+                      int32_t* status);
+/* the same for one state per scenario of a batch (each against its own reference tables): arrays of rp_batch_size rows */
+int rp_batch_initial_states(rp_batch* b, const double* x0, const int32_t* low_vel_mode, double* out_lon, double* out_lat,
+                            int32_t* status);
+
 /* ---- stand-alone pieces ---------------------------------------------------------------------- */
 /* batched coefficient solve (polynomial_trajectory.py:292-360): kind 0 = quartic
  * (x_d = target velocity in xd[i][0]), 1 = quintic; x0[n][3], xd[n][3], tau[n] -> coeffs[n][6] */

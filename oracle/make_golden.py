@@ -217,12 +217,50 @@ def make_cyclic(name, route, yaml, max_cycles):
                                              [[lv["winner"] for lv in r["levels"]] for r in records]))
 
 
+def make_initial_states():
+    """the reference's own ``_compute_initial_states`` (reactive_planner.py:446-512) on the Cartesian
+    states of every recorded replanning cycle, in high- and low-velocity mode -> tests/golden/init_states.npz.
+    (The x0_lon / x0_lat of the cyclic fixtures are NOT that: from cycle 1 on run_planner.py hands reset() the previous
+    optimal trajectory's curvilinear states.)"""
+    ref_root = ref_shims.REFERENCE_ROOT
+    arrays = {}
+    for name, kw in CYC_CASES.items():
+        z = np.load(os.path.join(OUT, "cyc_%s.npz" % name))
+        meta = json.loads(str(z["meta"]))
+        sc = scenario_xml.load(os.path.join(ref_root, "example_scenarios", name + ".xml"))
+        scn = dict(sc["scn"])
+        scn["ref_path"] = scenario_xml.route_centerline(sc["lanelets"], kw["route"])
+        planner = H.build_planner(scn, N=meta["N"], dt=meta["dt"], t_min=meta["t_min"],
+                                  low_vel_mode_threshold=meta["low_vel_mode_threshold"], draw_traj_set=False)
+        from commonroad_rp.state import ReactivePlannerState        # importable once the shims are installed
+        xs, out = [], {"lon_hv": [], "lat_hv": [], "lon_lv": [], "lat_lv": []}
+        for ci in range(meta["n_cycles"]):
+            x = z["c%d_x0" % ci]
+            x0 = ReactivePlannerState(time_step=int(x[7]), position=np.array([x[0], x[1]]), orientation=x[2], velocity=x[3],
+                                      acceleration=x[4], yaw_rate=x[5], steering_angle=x[6])
+            xs.append(x)
+            for tag, flag in (("hv", False), ("lv", True)):
+                planner._low_vel_mode = flag
+                lon, lat = planner._compute_initial_states(x0)
+                out["lon_" + tag].append(np.array(lon, dtype=np.float64))
+                out["lat_" + tag].append(np.array(lat, dtype=np.float64))
+        arrays[name + "_x0"] = np.stack(xs)
+        for k, v in out.items():
+            arrays[name + "_" + k] = np.stack(v)
+        print("init_states %s: %d states" % (name, len(xs)))
+    np.savez_compressed(os.path.join(OUT, "init_states.npz"), **arrays)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "init":
+        make_initial_states()
+        return
     for name, kw in SYN_CASES.items():
         make_synthetic(name, **kw)
     for name, kw in CYC_CASES.items():
         make_cyclic(name, **kw)
+    make_initial_states()
 
 
 if __name__ == "__main__":

@@ -142,6 +142,38 @@ def interpolate_angle(x, x1, x2, y1, y2):
 # ------------------------------------------------------------------------------------------------
 # a7: constraint checks at step i (reactive_planner.py:971-1017); returns reason code or 0
 # ------------------------------------------------------------------------------------------------
+def initial_states(x0, low_vel_mode, ref, ccosy, wheelbase):
+    """ReactivePlanner._compute_initial_states (reactive_planner.py:446-512): Cartesian rear-axle state
+    x0 = (x, y, orientation, velocity, acceleration, steering_angle) -> ([s, s_dot, s_ddot], [d, d_dot, d_ddot]).
+    ``ccosy`` restates pycrccosy's convert_to_curvilinear_coords (oracle/third_party.py); raises like the reference."""
+    px, py, orientation, velocity, acceleration, steering_angle = [float(v) for v in x0]
+    s, d = ccosy.convert_to_curvilinear_coords(px, py)                       # ValueError outside the domain (:459-461)
+    ref_pos, ref_curv, ref_curv_d = ref["ref_pos"], ref["ref_curv"], ref["ref_curv_d"]
+    s_idx = np.argmax(ref_pos > s) - 1                                       # :464
+    s_lambda = (s - ref_pos[s_idx]) / (ref_pos[s_idx + 1] - ref_pos[s_idx])
+    ref_theta = np.unwrap(ref["ref_theta"])                                  # :469
+    theta_cl = orientation - interpolate_angle(s, ref_pos[s_idx], ref_pos[s_idx + 1], ref_theta[s_idx], ref_theta[s_idx + 1])
+    kr = (ref_curv[s_idx + 1] - ref_curv[s_idx]) * s_lambda + ref_curv[s_idx]
+    kr_d = (ref_curv_d[s_idx + 1] - ref_curv_d[s_idx]) * s_lambda + ref_curv_d[s_idx]
+    kappa_0 = np.tan(steering_angle) / wheelbase                             # :480
+    d_p = (1 - kr * d) * np.tan(theta_cl)                                    # :483
+    d_pp = -(kr_d * d + kr * d_p) * np.tan(theta_cl) + ((1 - kr * d) / (math.cos(theta_cl) ** 2)) * (
+        kappa_0 * (1 - kr * d) / math.cos(theta_cl) - kr)
+    s_velocity = velocity * math.cos(theta_cl) / (1 - kr * d)                # :488
+    if s_velocity < 0:
+        raise Exception("Initial state or reference incorrect! Curvilinear velocity is negative")
+    s_acceleration = acceleration                                            # :493-497
+    s_acceleration -= (s_velocity ** 2 / math.cos(theta_cl)) * (
+        (1 - kr * d) * np.tan(theta_cl) * (kappa_0 * (1 - kr * d) / (math.cos(theta_cl)) - kr) - (kr_d * d + kr * d_p))
+    s_acceleration /= ((1 - kr * d) / (math.cos(theta_cl)))
+    if low_vel_mode:                                                         # :500-507
+        d_velocity, d_acceleration = d_p, d_pp
+    else:
+        d_velocity = velocity * math.sin(theta_cl)
+        d_acceleration = s_acceleration * d_p + s_velocity ** 2 * d_pp
+    return [s, s_velocity, s_acceleration], [d, d_velocity, d_acceleration]
+
+
 def check_constraints(v, kappa_gl, theta_gl, a, i, veh, dt, constraints):
     if "velocity" in constraints:
         if v[i] < -_EPS:

@@ -150,3 +150,67 @@ def test_cyclic_replanning_matches_reference_fixture(path):
             got = np.array([[s.position[0], s.position[1], s.velocity, s.acceleration] for s in cart.state_list]).T
             assert H.rel_err(ws[[0, 1, 3, 4]], got) < RTOL, "cycle %d" % ci
             assert H.rel_err(ws[[7, 10, 11]], np.array(lon_list).T) < RTOL and H.rel_err(ws[[8, 12, 13]], np.array(lat_list).T) < RTOL
+
+
+def _frame_engine(z):
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200.utility.config import VehicleConfiguration
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    veh = VehicleConfiguration()
+    co = CoordinateSystem(z["ref_path_raw"])
+    eng = _lib.Engine(0)
+    eng.set_vehicle(veh.length, veh.width, veh.wb_rear_axle, veh.wheelbase, veh.a_max, veh.v_switch, veh.delta_max,
+                    veh.v_delta_max, veh.kappa_max)
+    tb = co.device_tables()
+    eng.set_reference(tb["ref_pos"], tb["ref_theta"], tb["ref_curv"], tb["ref_curv_d"], tb["path_xy"], tb["path_s"],
+                      tb["path_normals"], tb["proj_limit"])
+    return eng, co
+
+
+@pytest.mark.parametrize("path", CYC, ids=[os.path.basename(p)[4:-4] for p in CYC])
+def test_initial_states_match_reference_fixture(path):
+    """the device's Cartesian -> curvilinear initial states (rp_initial_states) against the
+    reference's own _compute_initial_states (:446-512) evaluated on the Cartesian state of every recorded replanning
+    cycle, in high- and low-velocity mode (tests/golden/init_states.npz, oracle/make_golden.py init)"""
+    z = np.load(path)
+    g = np.load(os.path.join(GOLDEN, "init_states.npz"))
+    name = json.loads(str(z["meta"]))["name"]
+    eng, co = _frame_engine(z)
+    x = g[name + "_x0"]
+    n = len(x)
+    x0 = x[:, [0, 1, 2, 3, 4, 6]]                               # x, y, orientation, velocity, acceleration, steering_angle
+    for tag, flag in (("hv", 0), ("lv", 1)):
+        lon, lat, status = eng.initial_states(x0, np.full(n, flag, dtype=np.int32))
+        assert not status.any()
+        assert H.rel_err(g[name + "_lon_" + tag], lon) < RTOL, (tag, H.rel_err(g[name + "_lon_" + tag], lon))
+        assert H.rel_err(g[name + "_lat_" + tag], lat) < RTOL, (tag, H.rel_err(g[name + "_lat_" + tag], lat))
+    # the host-side frame (CoordinateSystem.convert_to_curvilinear_coords) agrees, and error cases map to status codes
+    s_d = co.convert_to_curvilinear_coords(x0[0, 0], x0[0, 1])
+    assert H.rel_err(s_d, [lon[0, 0], lat[0, 0]]) < RTOL
+    far = x0[:1].copy()
+    far[0, :2] += 1.0e4
+    assert eng.initial_states(far, [0])[2][0] == 1                   # outside the projection domain
+    back = x0[:1].copy()
+    back[0, 2] += np.pi
+    assert eng.initial_states(back, [0])[2][0] == 2                  # driving against the reference: negative s_dot
+    eng.close()
+
+
+def test_batched_initial_states_over_scenarios():
+    """one state per scenario, each against its own reference tables, in one launch (rp_batch_initial_states)"""
+    from commonroad_rp_b200 import _lib
+    g = np.load(os.path.join(GOLDEN, "init_states.npz"))
+    zs = [np.load(p) for p in CYC]
+    names = [json.loads(str(z["meta"]))["name"] for z in zs]
+    pairs = [_frame_engine(z) for z in zs]
+    batch = _lib.Batch([e for e, _ in pairs])
+    x0 = np.stack([g[nm + "_x0"][2][[0, 1, 2, 3, 4, 6]] for nm in names])
+    lon, lat, status = batch.initial_states(x0, 0)
+    assert not status.any()
+    for k, nm in enumerate(names):
+        assert H.rel_err(g[nm + "_lon_hv"][2], lon[k]) < RTOL and H.rel_err(g[nm + "_lat_hv"][2], lat[k]) < RTOL
+        single = pairs[k][0].initial_states(x0[k], [0])
+        assert np.array_equal(single[0][0], lon[k]) and np.array_equal(single[1][0], lat[k])
+    batch.close()
+    for e, _ in pairs:
+        e.close()

@@ -47,3 +47,24 @@ def test_oracle_matches_reference_fixture(path):
 def test_fixtures_cover_the_branches():
     names = {os.path.basename(p)[4:-4] for p in SYN}
     assert {"lowvel", "standstill_carry", "draw_all", "stopping", "lvl2_N60", "dense_small"} <= names
+
+
+def test_oracle_initial_states_match_reference_vectors():
+    """the oracle's restatement of _compute_initial_states (reactive_planner.py:446-512) against
+    the reference's own outputs on the Cartesian states of every recorded replanning cycle (init_states.npz)"""
+    g = np.load(os.path.join(GOLDEN, "init_states.npz"))
+    wheelbase = O.vehicle_dict()["wheelbase"]
+    n_checked = 0
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "cyc_*.npz"))):
+        z = np.load(path)
+        name = json.loads(str(z["meta"]))["name"]
+        ref, ccosy, _ = O.reference_tables(z["ref_path_raw"])
+        frame = O._ArrayCCosy(ccosy)
+        for row, x in enumerate(g[name + "_x0"]):
+            for tag, flag in (("hv", False), ("lv", True)):
+                lon, lat = O.initial_states(x[[0, 1, 2, 3, 4, 6]], flag, ref, frame, wheelbase)
+                assert _close(lon, g[name + "_lon_" + tag][row]) and _close(lat, g[name + "_lat_" + tag][row]), (name, row, tag)
+                n_checked += 1
+    assert n_checked >= 60
+    with pytest.raises(ValueError):
+        O.initial_states([1e6, 1e6, 0, 1, 0, 0], False, ref, frame, wheelbase)
