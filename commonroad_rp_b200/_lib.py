@@ -41,6 +41,7 @@ class PlanInputs(C.Structure):
         ("cost_kind", C.c_int32), ("has_desired_speed", C.c_int32), ("has_desired_s", C.c_int32),
         ("desired_speed", C.c_double), ("desired_s", C.c_double), ("desired_d", C.c_double), ("w_a", C.c_double),
         ("want_all_states", C.c_int32), ("check_collision", C.c_int32),
+        ("continuous_collision_check", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -195,7 +196,7 @@ class Engine:
     def make_inputs(x0_lon, x0_lat, x0_orientation, x0_time_step, low_vel_mode, lon_mode, N, dt, factor=1,
                     draw_all=False, constraints=("velocity", "acceleration", "kappa", "kappa_dot", "yaw_rate"),
                     cost_kind=COST_DEFAULT, desired_speed=None, desired_s=None, desired_d=0.0, w_a=5.0,
-                    want_all_states=False, check_collision=True):
+                    want_all_states=False, check_collision=True, continuous_collision_check=False):
         pi = PlanInputs()
         pi.x0_lon[:] = [float(v) for v in x0_lon]
         pi.x0_lat[:] = [float(v) for v in x0_lat]
@@ -220,6 +221,7 @@ class Engine:
         pi.w_a = float(w_a)
         pi.want_all_states = int(bool(want_all_states))
         pi.check_collision = int(check_collision) if not isinstance(check_collision, bool) else int(check_collision)
+        pi.continuous_collision_check = int(bool(continuous_collision_check))
         return pi
 
     def _grid_args(self, inputs, t, lon, d, traj_len):

@@ -73,6 +73,38 @@ class TimeVariantCollisionObject:
         return self._shapes[k] if 0 <= k < len(self._shapes) else None
 
 
+def obb_sum_hull(a: RectOBB, b: RectOBB) -> RectOBB:
+    """The OBB-sum hull of two consecutive boxes (continuous collision check, reference :240-241, :1049-1058): the
+    tight box along ``a``'s axes that encloses both.  commonroad_dc is not installable here, so this follows
+    SURVEY.md App. D#2 / oracle/third_party.py (parity unpinned); the device builds the ego's hulls with the same
+    expressions (continuous_check_kernel)."""
+    ca, sa = math.cos(a.orientation), math.sin(a.orientation)
+    cb, sb = math.cos(b.orientation), math.sin(b.orientation)
+    dx, dy = b.cx - a.cx, b.cy - a.cy
+    u0 = dx * ca + dy * sa
+    v0 = -dx * sa + dy * ca
+    c = ca * cb + sa * sb
+    s = ca * sb - sa * cb
+    eu = b.r_x * abs(c) + b.r_y * abs(s)
+    ev = b.r_x * abs(s) + b.r_y * abs(c)
+    umin, umax = min(-a.r_x, u0 - eu), max(a.r_x, u0 + eu)
+    vmin, vmax = min(-a.r_y, v0 - ev), max(a.r_y, v0 + ev)
+    um, vm = 0.5 * (umin + umax), 0.5 * (vmin + vmax)
+    return RectOBB(0.5 * (umax - umin), 0.5 * (vmax - vmin), a.orientation, a.cx + um * ca - vm * sa, a.cy + um * sa + vm * ca)
+
+
+def trajectory_preprocess_obb_sum(tvo: "TimeVariantCollisionObject"):
+    """``commonroad_dc.collision.trajectory_queries.trajectory_preprocess_obb_sum``: n boxes -> n - 1 hull boxes
+    (steps k, k + 1) from the same start index; returns (object, error code) like the original."""
+    out = TimeVariantCollisionObject(tvo.time_start_idx())
+    shapes = [tvo.obstacle_at_time(k) for k in range(tvo.time_start_idx(), tvo.time_end_idx() + 1)]
+    for k in range(len(shapes) - 1):
+        if not isinstance(shapes[k], RectOBB) or not isinstance(shapes[k + 1], RectOBB):
+            return None, -1
+        out.append_obstacle(obb_sum_hull(shapes[k], shapes[k + 1]))
+    return out, 0
+
+
 class CollisionChecker:
     """Set of static shapes, shape groups and time-variant objects."""
 

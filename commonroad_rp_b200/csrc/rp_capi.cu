@@ -890,6 +890,13 @@ static int launch_plan(rp_ctx* ctx) {
     if (count > 0) {
         if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one.as<double>())) return rc;
     }
+    if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision) {
+        if (ctx->range_count >= 0) return fail(RP_ERR_ARG, "continuous collision check is not available for sharded bundles");
+        rp::continuous_check_kernel<<<1, 128, 0, ctx->stream>>>(ctx->obs, ctx->d_states_one.as<double>(), Np1, ctx->in.x0_time_step,
+                                                                0.5 * ctx->veh.length, 0.5 * ctx->veh.width, ctx->veh.wb_rear_axle,
+                                                                dres, ctx->d_info.as<int>());
+        RP_CUDA(cudaGetLastError());
+    }
     cudaEventRecord(ctx->ev[4], ctx->stream);
     ++ctx->n_launches;
     ctx->have_plan = true;
@@ -1300,6 +1307,7 @@ int rp_batch_set_inputs(rp_batch* b, int k, const rp_plan_inputs* in, int n_t, c
     if ((n_t && (!t || !traj_len)) || (n_lon && !lon) || (n_d && !d)) return fail(RP_ERR_ARG, "null sample array");
     if ((long long)n_t * n_lon * n_d > 0x7fffffffLL / 8) return fail(RP_ERR_ARG, "bundle too large");
     if (in->want_all_states || in->draw_all) return fail(RP_ERR_ARG, "a batch runs in select-only mode (no draw_all / want_all_states)");
+    if (in->continuous_collision_check) return fail(RP_ERR_ARG, "a batch does not run the continuous collision check");
     if (in->N + 1 > 128) return fail(RP_ERR_ARG, "a batch supports N + 1 <= 128");
     for (int q = 0; q < n_t; ++q)
         if (traj_len[q] < 1 || traj_len[q] > in->N + 1) return fail(RP_ERR_ARG, "traj_len out of [1, N+1]");

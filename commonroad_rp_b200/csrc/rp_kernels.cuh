@@ -505,6 +505,64 @@ __global__ void __launch_bounds__(128) initial_states_kernel(int n_states, const
     status[st] = s_velocity < 0 ? 2 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// the continuous collision check of the selected candidate (reactive_planner.py:1049-1058).
+// Hull k = OBB-sum of the ego boxes at steps k, k + 1 (oracle/third_party.py obb_sum_hull: tight box along the
+// first box's axes), tested at time index x0.time_step + k against every dynamic box of that index and every static
+// primitive (brute force: one trajectory, <= N hulls; the broad-phase grid is sized for the vehicle box, not hulls).
+// A hit relabels the winner, counts it and leaves the cycle without a trajectory -- the reference breaks out of its
+// candidate loop there.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) continuous_check_kernel(ObstacleTables O, const double* __restrict__ st, int Np1,
+                                                               int x0_time_step, double half_len, double half_wid,
+                                                               double wb_rear, PlanResultDev* res, int* __restrict__ info) {
+    __shared__ int s_hit;
+    const int winner = res->r.winner;
+    if (winner < 0) return;
+    if (threadIdx.x == 0) s_hit = 0;
+    __syncthreads();
+    const double* X = st;
+    const double* Y = st + Np1;
+    const double* TH = st + 2 * Np1;
+    bool hit = false;
+    for (int i = threadIdx.x; i < Np1 - 1 && !hit; i += blockDim.x) {
+        double sa, ca, sb, cb;
+        sincos(TH[i], &sa, &ca);
+        sincos(TH[i + 1], &sb, &cb);
+        const double acx = X[i] + wb_rear * ca, acy = Y[i] + wb_rear * sa;
+        const double bcx = X[i + 1] + wb_rear * cb, bcy = Y[i + 1] + wb_rear * sb;
+        const double dx = bcx - acx, dy = bcy - acy;
+        const double u0 = dx * ca + dy * sa;
+        const double v0 = -dx * sa + dy * ca;
+        const double c = ca * cb + sa * sb;
+        const double s = ca * sb - sa * cb;
+        const double eu = half_len * fabs(c) + half_wid * fabs(s);
+        const double ev = half_len * fabs(s) + half_wid * fabs(c);
+        const double umin = fmin(-half_len, u0 - eu), umax = fmax(half_len, u0 + eu);
+        const double vmin = fmin(-half_wid, v0 - ev), vmax = fmax(half_wid, v0 + ev);
+        const double um = 0.5 * (umin + umax), vm = 0.5 * (vmin + vmax);
+        const double hcx = acx + um * ca - vm * sa, hcy = acy + um * sa + vm * ca;
+        const double hl = 0.5 * (umax - umin), hw = 0.5 * (vmax - vmin);
+        const int tidx = x0_time_step + i;
+        for (int o = 0; o < O.n_dyn && !hit; ++o) {
+            const int k = tidx - O.dyn_t0[o];
+            if (k < 0 || k >= O.dyn_len[o]) continue;
+            hit = obb_obb_overlap(hcx, hcy, ca, sa, hl, hw, O.dyn_box + (size_t)(O.dyn_off[o] + k) * kBoxStride);
+        }
+        for (int q = 0; q < O.n_obb && !hit; ++q) hit = obb_obb_overlap(hcx, hcy, ca, sa, hl, hw, O.obb + (size_t)q * kBoxStride);
+        for (int q = 0; q < O.n_tri && !hit; ++q) hit = obb_triangle_overlap(hcx, hcy, ca, sa, hl, hw, O.tri + (size_t)q * 6);
+    }
+    if (hit) atomicOr(&s_hit, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_hit) {
+        info[winner] = pack_info(ST_COLLISION, R_NONE, -1);
+        res->r.winner = -1;
+        res->r.winner_cost = __longlong_as_double(0x7ff8000000000000LL);
+        res->r.n_infeasible_collision += 1;
+        res->r.n_collision_total += 1;
+    }
+}
+
 // pycrcc.CollisionChecker.collide for a batch of ego boxes (rp_collide_poses)
 __global__ void collide_kernel(int n, const double* __restrict__ pose, const int* __restrict__ tidx, double hl,
                                double hw, double r_ego, ObstacleTables O, int vehicle_box, uint8_t* __restrict__ hit) {

@@ -203,14 +203,17 @@ class ReactivePlanner(object):
         if collision_checker is None:
             assert scenario is not None, '<ReactivePlanner.set collision checker>: Please provide a CommonRoad ' \
                                          'scenario OR a CollisionChecker object to the planner.'
-            if self.config.planning.continuous_collision_check:
-                raise NotImplementedError("continuous collision checking is not part of the GPU path yet "
-                                          "(SURVEY.md section 8f, rank 2)")
             cc_scenario = rpc.CollisionChecker()
             for co in scenario.static_obstacles:
                 cc_scenario.add_collision_object(rpc.create_collision_object(co))
             for co in scenario.dynamic_obstacles:
-                cc_scenario.add_collision_object(rpc.create_collision_object(co))
+                tvo = rpc.create_collision_object(co)
+                if self.config.planning.continuous_collision_check:
+                    tvo, err = rpc.trajectory_preprocess_obb_sum(tvo)
+                    if err == -1:
+                        raise Exception("Invalid input for trajectory_preprocess_obb_sum: dynamic "
+                                        "obstacle elements overlap")
+                cc_scenario.add_collision_object(tvo)
             if road_boundary_obstacle is None:
                 _, road_boundary_sg = rpc.create_road_boundary_obstacle(scenario)
                 cc_scenario.add_collision_object(road_boundary_sg)
@@ -356,7 +359,9 @@ class ReactivePlanner(object):
             desired_d=cost_spec["desired_d"], w_a=cost_spec["w_a"], want_all_states=want_all_states,
             # the reference's collision pass is lazy (:1031-1063); full flags only when every trajectory is kept
             check_collision=_lib.COLLISION_ALL if (want_all_states or cost_spec["cost_kind"] == _lib.COST_NONE)
-            else _lib.COLLISION_LAZY)
+            else _lib.COLLISION_LAZY,
+            # reference :1049-1058 (the hull check of the first discretely collision-free candidate, on the device)
+            continuous_collision_check=bool(p.continuous_collision_check) and cost_spec["cost_kind"] != _lib.COST_NONE)
 
     def _device_cost_spec(self):
         """Fused device cost for the built-in cost functions; None for user subclasses that bring their own
@@ -444,6 +449,9 @@ class ReactivePlanner(object):
                                               "x_0_lat": np.asarray(self.x_0_cl[1], dtype=np.float64)}
         cost_spec = self._device_cost_spec()
         generic_cost = cost_spec is None
+        if generic_cost and self.config.planning.continuous_collision_check:
+            raise NotImplementedError("continuous collision check with a user-defined cost function: the hull check runs "
+                                      "on the device right after the device-side selection (built-in cost functions)")
         if generic_cost:
             cost_spec = {"cost_kind": _lib.COST_NONE, "desired_speed": None, "desired_s": None, "desired_d": 0.0, "w_a": 1.0}
         want_all = bool(self._draw_traj_set or generic_cost)

@@ -99,3 +99,16 @@ def scenario_seeded(scenario_id):
     d0 = rng.uniform(-1.0, 1.0)
     scn = make_scenario(seed=int(scenario_id), amplitude=amplitude, wavelength=wavelength)
     return scn, float(s_dot0), float(d0)
+
+
+def add_crossing_obstacle(scn, speed=40.0, phase=2.0, x_c=24.0, y_path=0.0, n_steps=40, size=(1.0, 1.0)):
+    """A small box crossing the road along +y at x = x_c with ``speed`` m/s: consecutive discrete poses straddle the
+    ego, so only the continuous collision check (OBB-sum hulls of consecutive poses) sees it."""
+    k = np.arange(n_steps)
+    y = y_path - 6.0 + speed * 0.1 * (k - 10) + phase
+    st = np.stack([np.full(n_steps, x_c), y, np.full(n_steps, np.pi / 2)], axis=1)
+    out = dict(scn)
+    out["dyn_t0"] = list(scn["dyn_t0"]) + [0]
+    out["dyn_states"] = list(scn["dyn_states"]) + [st]
+    out["dyn_lw"] = [tuple(x) for x in scn["dyn_lw"]] + [tuple(size)]
+    return out

@@ -101,6 +101,12 @@ typedef struct rp_plan_inputs {
                                     reference's cost-ordered pass (:1031-1063): candidates costlier than the best
                                     collision-free one found so far are not visited.  Winner and
                                     n_infeasible_collision are identical in modes 1 and 2.              */
+    int32_t continuous_collision_check;   /* config.planning.continuous_collision_check (:1049-1058): the first discretely
+                                    collision-free candidate in cost order is re-checked with the OBB-sum hulls of its
+                                    consecutive poses (time indices x0_time_step + i); a hit ends the level without a
+                                    trajectory, as the reference's `break` does.  The caller uploads dynamic obstacles
+                                    already replaced by their hulls (:240-241). */
+    int32_t reserved_;
 } rp_plan_inputs;
 
 typedef struct rp_plan_result {

@@ -42,6 +42,9 @@ SYN_CASES = {
     "straight": dict(seed=7, level=2, N=20, amplitude=0.0, static_offset=1.0),
     "time_offset": dict(seed=8, level=1, N=20, time_step=30),
     "dense_small": dict(seed=0, level=1, N=60, dense=(6, 9, 9)),
+    # continuous collision check (reactive_planner.py:240-241, :1049-1058): OBB-sum hulls of consecutive poses
+    "continuous_pass": dict(seed=0, level=2, N=20, amplitude=0.0, continuous=True, crossing=(40.0, 1.0)),
+    "continuous_hit": dict(seed=0, level=2, N=20, amplitude=0.0, continuous=True, crossing=(40.0, 2.0)),
 }
 
 
@@ -61,9 +64,13 @@ def reference_result_arrays(r, rng):
 
 
 def make_synthetic(name, seed, level, N, s_dot0=15.0, d0=0.3, mode="velocity_keeping", desired_s=None, draw=False,
-                   amplitude=20.0, static_offset=0.0, time_step=0, low_vel_threshold=4.0, dense=None):
+                   amplitude=20.0, static_offset=0.0, time_step=0, low_vel_threshold=4.0, dense=None, continuous=False,
+                   factor=1, crossing=None):
     scn = synthetic.make_scenario(seed=seed, amplitude=amplitude, static_offset=static_offset)
-    p = H.build_planner(scn, N=N, longitudinal_mode=mode, draw_traj_set=draw, low_vel_mode_threshold=low_vel_threshold)
+    if crossing is not None:
+        scn = synthetic.add_crossing_obstacle(scn, speed=crossing[0], phase=crossing[1])
+    p = H.build_planner(scn, N=N, longitudinal_mode=mode, draw_traj_set=draw, low_vel_mode_threshold=low_vel_threshold,
+                        continuous_collision_check=continuous, factor=factor)
     s0 = float(p.coordinate_system.ref_pos[10])
     H.set_initial_state(p, [s0, s_dot0, 0.0], [d0, 0.0, 0.0], time_step=time_step)
     if mode == "stopping":
@@ -255,6 +262,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "init":
         make_initial_states()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "only":
+        for name in sys.argv[2:]:
+            make_synthetic(name, **SYN_CASES[name])
         return
     for name, kw in SYN_CASES.items():
         make_synthetic(name, **kw)

@@ -23,7 +23,8 @@ def scenario_stub(scn):
 
 
 def build_planner(scn, N=20, dt=0.1, t_min=0.4, low_vel_mode_threshold=4.0, longitudinal_mode="velocity_keeping",
-                  draw_traj_set=False, constraints=None, factor=1, d_min=-3.0, d_max=3.0, smooth_reference=True):
+                  draw_traj_set=False, constraints=None, factor=1, d_min=-3.0, d_max=3.0, smooth_reference=True,
+                  continuous_collision_check=False):
     """Reference ReactivePlanner with multiproc off (canonical enumeration order, SURVEY App. B#10)."""
     ref_shims.install()
     from commonroad_rp.reactive_planner import ReactivePlanner
@@ -36,6 +37,7 @@ def build_planner(scn, N=20, dt=0.1, t_min=0.4, low_vel_mode_threshold=4.0, long
     cfg.planning.planning_horizon = dt * N
     cfg.planning.low_vel_mode_threshold = low_vel_mode_threshold
     cfg.planning.factor = factor
+    cfg.planning.continuous_collision_check = bool(continuous_collision_check)
     if constraints is not None:
         cfg.planning.constraints_to_check = list(constraints)
     cfg.sampling.t_min = t_min
@@ -157,6 +159,7 @@ def problem_from_planner(planner, level, scn):
         "low_vel_mode": bool(planner.x_0.velocity < cfg.planning.low_vel_mode_threshold),
         "dt": planner.dt, "N": planner.N, "factor": cfg.planning.factor,
         "draw_all": bool(planner._draw_traj_set),
+        "continuous": bool(cfg.planning.continuous_collision_check),
         "constraints": tuple(cfg.planning.constraints_to_check),
         "cost": {"kind": kind, "desired_speed": getattr(cf, "desired_speed", None),
                  "desired_s": getattr(cf, "desired_s", None), "desired_d": getattr(cf, "desired_d", 0.0),

@@ -141,7 +141,8 @@ def _create_road_boundary_obstacle(scenario, *a, **k):
 
 
 def _trajectory_preprocess_obb_sum(tvo):
-    raise NotImplementedError("continuous collision check is out of scope (SURVEY 8f#2)")
+    """commonroad_dc ... trajectory_preprocess_obb_sum (reactive_planner.py:241, :1053) -> oracle/third_party.py"""
+    return tp.trajectory_preprocess_obb_sum(tvo)
 
 
 _BEHAVIOUR = {

@@ -415,8 +415,9 @@ def evaluate_cost(states, cost):
 # ------------------------------------------------------------------------------------------------
 # a13: ego-vs-obstacle check of one candidate (reactive_planner.py:1026-1046)
 # ------------------------------------------------------------------------------------------------
-def build_checker(obst):
-    """pycrcc.CollisionChecker as set_collision_checker builds it (reactive_planner.py:234-251)."""
+def build_checker(obst, continuous=False):
+    """pycrcc.CollisionChecker as set_collision_checker builds it (reactive_planner.py:234-251); with the
+    continuous collision check every dynamic obstacle is replaced by its OBB-sum hulls (:240-241)."""
     cc = tp.CollisionChecker()
     for cx, cy, th, l, w in np.asarray(obst.get("static_boxes", np.zeros((0, 5)))).reshape(-1, 5):
         cc.add_collision_object(tp.RectOBB(0.5 * l, 0.5 * w, th, cx, cy))
@@ -424,6 +425,8 @@ def build_checker(obst):
         tvo = tp.TimeVariantCollisionObject(int(t0))
         for cx, cy, th in np.asarray(st).reshape(-1, 3):
             tvo.append_obstacle(tp.RectOBB(0.5 * lw[0], 0.5 * lw[1], th, cx, cy))
+        if continuous:
+            tvo, err = tp.trajectory_preprocess_obb_sum(tvo)
         cc.add_collision_object(tvo)
     sg = tp.ShapeGroup()
     for cx, cy, th, hl, hw in np.asarray(obst.get("boundary_boxes", np.zeros((0, 5)))).reshape(-1, 5):
@@ -450,6 +453,20 @@ def candidate_collides(states, prob, checker):
     return -1
 
 
+def candidate_collides_continuous(states, prob, checker):
+    """The additional continuous check (reactive_planner.py:1049-1058): the OBB-sum hulls of consecutive ego boxes,
+    time indices x_0.time_step + i (no ``factor`` here), against the checker."""
+    veh = prob["vehicle"]
+    x, y, theta = states[0], states[1], states[2]
+    pos1 = x + veh["wb_rear_axle"] * np.cos(theta)
+    pos2 = y + veh["wb_rear_axle"] * np.sin(theta)
+    ego = tp.TimeVariantCollisionObject(prob["x0_time_step"])
+    for i in range(len(pos1)):
+        ego.append_obstacle(tp.RectOBB(0.5 * veh["length"], 0.5 * veh["width"], theta[i], pos1[i], pos2[i]))
+    ego, err = tp.trajectory_preprocess_obb_sum(ego)
+    return checker.collide(ego)
+
+
 # ------------------------------------------------------------------------------------------------
 # a12-a14: whole bundle (reactive_planner.py:1065-1136)
 # ------------------------------------------------------------------------------------------------
@@ -461,7 +478,8 @@ def plan_candidates(coeffs_lon, coeffs_lat, delta_tau, prob, goal_behind=None, w
     n = len(delta_tau)
     N = prob["N"]
     ccosy = _ccosy_from(prob)
-    checker = build_checker(prob["obstacles"])
+    continuous = bool(prob.get("continuous", False))
+    checker = build_checker(prob["obstacles"], continuous)
     status = np.zeros(n, dtype=np.int32)
     reason = np.zeros(n, dtype=np.int32)
     bad_step = np.full(n, -1, dtype=np.int32)
@@ -508,7 +526,16 @@ def plan_candidates(coeffs_lon, coeffs_lat, delta_tau, prob, goal_behind=None, w
             winner = k
             if not full_collision:
                 break
+    continuous_hit = False
+    if continuous and winner >= 0 and candidate_collides_continuous(all_states[winner], prob, checker):
+        # the first discretely collision-free candidate fails the continuous check: the reference counts it, labels
+        # it and BREAKS OUT OF THE CANDIDATE LOOP (:1054-1058) -- no trajectory at this level
+        status[winner] = ST_COLLISION
+        n_inf_col += 1
+        winner = -1
+        continuous_hit = True
     return {
+        "continuous_hit": continuous_hit,
         "n": n, "status": status, "reason": reason, "bad_step": bad_step, "cost": cost,
         "collide_step": collide_step, "states": states, "winner": int(winner),
         "n_infeasible_kinematics": int(n_inf_kin), "n_infeasible_collision": int(n_inf_col),

@@ -300,6 +300,38 @@ class TimeVariantCollisionObject:
         return None
 
 
+def obb_sum_hull(a, b):
+    """commonroad_dc's "OBB sum hull" of two consecutive boxes (trajectory_preprocess_obb_sum; continuous collision
+    check, reactive_planner.py:240-241, :1049-1058).  PARITY UNPINNED: the package is not installed and the reference
+    ships no vectors; restated as the tight box ALONG THE FIRST BOX'S AXES enclosing both boxes."""
+    ca, sa = math.cos(a.orientation), math.sin(a.orientation)
+    cb, sb = math.cos(b.orientation), math.sin(b.orientation)
+    dx = b.cx - a.cx
+    dy = b.cy - a.cy
+    u0 = dx * ca + dy * sa
+    v0 = -dx * sa + dy * ca
+    c = ca * cb + sa * sb
+    s = ca * sb - sa * cb
+    eu = b.r_x * abs(c) + b.r_y * abs(s)
+    ev = b.r_x * abs(s) + b.r_y * abs(c)
+    umin, umax = min(-a.r_x, u0 - eu), max(a.r_x, u0 + eu)
+    vmin, vmax = min(-a.r_y, v0 - ev), max(a.r_y, v0 + ev)
+    um, vm = 0.5 * (umin + umax), 0.5 * (vmin + vmax)
+    return RectOBB(0.5 * (umax - umin), 0.5 * (vmax - vmin), a.orientation, a.cx + um * ca - vm * sa, a.cy + um * sa + vm * ca)
+
+
+def trajectory_preprocess_obb_sum(tvo):
+    """commonroad_dc.collision.trajectory_queries.trajectory_preprocess_obb_sum: a time-variant object of n boxes ->
+    one of n - 1 hull boxes (steps k, k + 1) starting at the same time index; (object, error code)."""
+    out = TimeVariantCollisionObject(tvo.time_start_idx())
+    obs = tvo._obstacles
+    for k in range(len(obs) - 1):
+        if not isinstance(obs[k], RectOBB) or not isinstance(obs[k + 1], RectOBB):
+            return None, -1
+        out.append_obstacle(obb_sum_hull(obs[k], obs[k + 1]))
+    return out, 0
+
+
 def obb_obb_overlap(a, b):
     """4-axis SAT on two oriented boxes; separated iff gap > 0 on some axis."""
     ca, sa = math.cos(a.orientation), math.sin(a.orientation)

@@ -10,6 +10,7 @@ def pack_problem(prob, prefix="p_"):
     out = {}
     meta = {k: prob[k] for k in ("x0_orientation", "x0_time_step", "lon_mode", "low_vel_mode", "dt", "N", "factor")}
     meta["draw_all"] = bool(prob.get("draw_all", False))
+    meta["continuous"] = bool(prob.get("continuous", False))
     meta["constraints"] = list(prob["constraints"])
     meta["cost"] = prob["cost"]
     meta["vehicle"] = prob["vehicle"]
@@ -55,6 +56,7 @@ def unpack_problem(z, prefix="p_"):
     prob = {k: meta[k] for k in ("x0_orientation", "x0_time_step", "lon_mode", "low_vel_mode", "dt", "N", "factor",
                                  "draw_all", "cost", "vehicle")}
     prob["constraints"] = tuple(meta["constraints"])
+    prob["continuous"] = bool(meta.get("continuous", False))
     for k in ("t", "lon", "d", "x0_lon", "x0_lat"):
         prob[k] = z[prefix + k]
     prob["ref"] = {k: z[prefix + "ref_" + k] for k in ("ref_pos", "ref_theta", "ref_curv", "ref_curv_d")}

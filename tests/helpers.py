@@ -55,8 +55,9 @@ def make_problem(scn, t, lon, d, x0_lon, x0_lat, N=20, dt=0.1, lon_mode="velocit
     }
 
 
-def obstacle_arrays(obst):
-    """scenario-dict obstacles -> the C-ABI's (static_obb, dyn_t0, dyn_boxes, tris)."""
+def obstacle_arrays(obst, continuous=False):
+    """scenario-dict obstacles -> the C-ABI's (static_obb, dyn_t0, dyn_boxes, tris); with the continuous collision
+    check the dynamic obstacles are uploaded as their OBB-sum hulls (reference :240-241)."""
     sb = np.asarray(obst.get("static_boxes", np.zeros((0, 5))), dtype=np.float64).reshape(-1, 5)
     static = np.stack([sb[:, 0], sb[:, 1], sb[:, 2], 0.5 * sb[:, 3], 0.5 * sb[:, 4]], axis=1)
     bb = np.asarray(obst.get("boundary_boxes", np.zeros((0, 5))), dtype=np.float64).reshape(-1, 5)
@@ -64,8 +65,15 @@ def obstacle_arrays(obst):
     dyn_boxes = []
     for st, lw in zip(obst.get("dyn_states", ()), obst.get("dyn_lw", ())):
         st = np.asarray(st, dtype=np.float64).reshape(-1, 3)
-        dyn_boxes.append(np.concatenate([st, np.full((len(st), 1), 0.5 * lw[0]), np.full((len(st), 1), 0.5 * lw[1])],
-                                        axis=1))
+        boxes = np.concatenate([st, np.full((len(st), 1), 0.5 * lw[0]), np.full((len(st), 1), 0.5 * lw[1])], axis=1)
+        if continuous:
+            from commonroad_rp_b200 import collision
+            tvo = collision.TimeVariantCollisionObject(0)
+            for cx, cy, th, hl, hw in boxes:
+                tvo.append_obstacle(collision.RectOBB(hl, hw, th, cx, cy))
+            hull, err = collision.trajectory_preprocess_obb_sum(tvo)
+            boxes = np.asarray([hull.obstacle_at_time(k).row() for k in range(len(boxes) - 1)], dtype=np.float64).reshape(-1, 5)
+        dyn_boxes.append(boxes)
     tris = np.asarray(obst.get("boundary_tris", np.zeros((0, 6))), dtype=np.float64).reshape(-1, 6)
     return static, np.asarray(obst.get("dyn_t0", ()), dtype=np.int32), dyn_boxes, tris
 
@@ -79,7 +87,7 @@ def engine_for(prob, device=0, stream=None):
     r, c = prob["ref"], prob["ccosy"]
     eng.set_reference(r["ref_pos"], r["ref_theta"], r["ref_curv"], r["ref_curv_d"], c["path"], c["S"], c["normals"],
                       c["limit"])
-    static, t0, dyn_boxes, tris = obstacle_arrays(prob["obstacles"])
+    static, t0, dyn_boxes, tris = obstacle_arrays(prob["obstacles"], prob.get("continuous", False))
     eng.set_obstacles(static, t0, dyn_boxes, tris)
     return eng
 
@@ -93,7 +101,8 @@ def inputs_for(prob, want_all_states=False, check_collision=True):
         prob["lon_mode"], prob["N"], prob["dt"], factor=prob["factor"], draw_all=prob.get("draw_all", False),
         constraints=prob["constraints"], cost_kind=kind, desired_speed=cost.get("desired_speed"),
         desired_s=cost.get("desired_s"), desired_d=cost.get("desired_d", 0.0), w_a=cost.get("w_a", 5),
-        want_all_states=want_all_states, check_collision=check_collision)
+        want_all_states=want_all_states, check_collision=check_collision,
+        continuous_collision_check=prob.get("continuous", False))
 
 
 def run_engine_grid(eng, prob, want_all_states=True, kernel=None):

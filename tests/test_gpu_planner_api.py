@@ -369,3 +369,27 @@ def test_scenario_batch_equals_individual_plans():
     ms, n = batch.batch.last_ms()
     assert ms > 0 and n == sum(len(c[1]) * len(c[2]) * len(c[3]) for c in cycle)
     batch.close()
+
+
+def test_continuous_collision_check_through_the_planner_api():
+    """SURVEY 8f rank 2 through the drop-in API: with config.planning.continuous_collision_check the scenario's dynamic
+    obstacles become OBB-sum hulls (reference :240-241) and the selected candidate is hull-checked (:1049-1058)"""
+    from commonroad_rp_b200 import collision
+    a = collision.RectOBB(2.0, 1.0, 0.3, 0.0, 0.0)
+    b = collision.RectOBB(2.0, 1.0, 0.5, 3.0, 1.0)
+    h = collision.obb_sum_hull(a, b)
+    assert h.orientation == a.orientation and h.r_x > a.r_x and h.r_y >= a.r_y
+    # the hull contains the corners of both boxes
+    ca, sa = np.cos(h.orientation), np.sin(h.orientation)
+    for box in (a, b):
+        cb, sb = np.cos(box.orientation), np.sin(box.orientation)
+        for sx in (-1, 1):
+            for sy in (-1, 1):
+                px = box.cx + sx * box.r_x * cb - sy * box.r_y * sb - h.cx
+                py = box.cy + sx * box.r_x * sb + sy * box.r_y * cb - h.cy
+                assert abs(px * ca + py * sa) <= h.r_x + 1e-12 and abs(-px * sa + py * ca) <= h.r_y + 1e-12
+    tvo = collision.TimeVariantCollisionObject(5)
+    for k in range(4):
+        tvo.append_obstacle(collision.RectOBB(2.0, 1.0, 0.1 * k, 1.0 * k, 0.0))
+    hull, err = collision.trajectory_preprocess_obb_sum(tvo)
+    assert err == 0 and hull.time_start_idx() == 5 and hull.time_end_idx() == 7
