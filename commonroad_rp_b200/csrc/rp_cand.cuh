@@ -97,61 +97,46 @@ struct StepOut {
     unsigned reject;     // sign bit set: a division left the fast path's window -> redo with EXACT = true
 };
 
+// Everything of a step that depends on the LONGITUDINAL polynomial alone: s, s_dot, s_ddot, the reference segment and
+// what is interpolated on it, the projection base point, two reciprocals.  In a grid bundle it is identical for all
+// candidates of one (t, lon) pair -- a whole warp when n_d is a multiple of 32 -- which is what cand_kernel<.., true>
+// exploits (rows computed once per 32 steps by the warp, lane = step, and broadcast from shared memory).
+struct LonRow {
+    double s, sv, sa;            // sv after the eps clamp
+    double y_sv, y_sv2;          // refined reciprocals of the guarded s_dot and its square
+    double th_ref, k_r, k_r_d;   // reference heading / curvature / curvature rate at s
+    double bx, by, nx, ny;       // frame base point and interpolated pseudo-normal: (x, y) = b + d * n
+    unsigned flags;
+};
+enum : unsigned { LR_PRE = 3u, LR_MOVING = 4u, LR_OK_S = 8u, LR_REJECT = 16u };
+constexpr int kLonRowDoubles = 12;
+
 template <bool EXACT>
-__device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTables& R, const LimitRcp& Y, const StepIn& I) {
-    const rp_plan_inputs& in = P.in;
-    const bool low_vel = in.low_vel_mode != 0;
-    const double dt = in.dt;
-    const int i = I.i;
+__device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables& R, const double* __restrict__ cs_ptr, int i) {
     Divider<EXACT> D;
-    StepOut o;
-    double cs[6], cd[6];
+    LonRow o;
+    double cs[6];
     {
-        const double2* a = reinterpret_cast<const double2*>(I.cs);
-        const double2* b = reinterpret_cast<const double2*>(I.cd);
+        const double2* a = reinterpret_cast<const double2*>(cs_ptr);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            const double2 u = __ldg(a + q), w = __ldg(b + q);
-            cs[2 * q] = u.x; cs[2 * q + 1] = u.y; cd[2 * q] = w.x; cd[2 * q + 1] = w.y;
+            const double2 u = __ldg(a + q);
+            cs[2 * q] = u.x; cs[2 * q + 1] = u.y;
         }
     }
     // ---- polynomial evaluation (reactive_planner.py:733-777) ---------------------------------------
-    const double tt = (double)i * dt;
+    const double tt = (double)i * P.in.dt;
     const double t2 = tt * tt, t3 = t2 * tt, t4 = t2 * t2, t5 = t4 * tt;
     const double s = poly_pos(cs, tt, t2, t3, t4, t5);
     double sv = poly_vel(cs, tt, t2, t3, t4);
     const double sa = poly_acc(cs, tt, t2, t3);
-    double d, dv, da;
-    if (!low_vel) {
-        d = poly_pos(cd, tt, t2, t3, t4, t5);
-        dv = poly_vel(cd, tt, t2, t3, t4);
-        da = poly_acc(cd, tt, t2, t3);
-    } else {
-        const double s1 = s - cs[0];
-        const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
-        d = poly_pos(cd, s1, s2, s3, s4, s5);
-        dv = poly_vel(cd, s1, s2, s3, s4);
-        da = poly_acc(cd, s1, s2, s3);
-    }
     sv = fabs(sv) < kEps ? 0.0 : sv;
-    dv = fabs(dv) < kEps ? 0.0 : dv;
-    o.pre = (fabs(sa) > P.lim.a_max ? 1u : 0u) | (sv < -kEps ? 2u : 0u);    // pre-filter (:796-805)
-
-    // ---- orientation (:810-873) ----------------------------------------------------------------------
+    unsigned flags = (fabs(sa) > P.lim.a_max ? 1u : 0u) | (sv < -kEps ? 2u : 0u);    // pre-filter (:796-805)
     const bool moving = sv > 0.001;
-    double dp, dpp;
-    if (!low_vel) {
-        const double svs = moving ? sv : 1.0;                   // guarded divisor: the quotient is discarded at standstill
-        const double dp_q = D.div(dv, svs, D.rcp(svs));
-        dp = moving ? dp_q : 0.;
-        const double ddot = da - dp * sa;
-        const double sv2 = svs * svs;
-        const double dpp_q = D.div(ddot, sv2, D.rcp(sv2));
-        dpp = moving ? dpp_q : 0.;
-    } else {
-        dp = dv;
-        dpp = da;
-    }
+    flags |= moving ? LR_MOVING : 0u;
+    const double svs = moving ? sv : 1.0;                       // guarded divisor: quotients are discarded at standstill
+    o.y_sv = D.rcp(svs);
+    o.y_sv2 = D.rcp(svs * svs);
     // reference segment (:835): first index with ref_pos > s, from an O(1) guess on the near-uniform table; the two
     // loads that verify the guess ARE ref_pos[j0], ref_pos[j1]
     double p0, p1;
@@ -167,6 +152,89 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
     const double th0 = R.theta[j0];
     double th_ref = D.div((R.theta[j1] - th0) * (s - p0), seg_len, y_seg) + th0;
     if (th_ref > kTwoPi || th_ref < -kTwoPi) th_ref = make_valid_orientation(th_ref);
+    const double k0 = R.curv[j0], kd0 = R.curv_d[j0];
+    o.k_r = (R.curv[j1] - k0) * lam + k0;
+    o.k_r_d = (R.curv_d[j1] - kd0) * lam + kd0;
+    // ---- base of (s, d) -> (x, y) (:908-917; project_to_cartesian) ----------------------------------------
+    {
+        const int n = R.n;
+        flags |= (s >= R.ps[0] && s <= R.ps[n - 1]) ? LR_OK_S : 0u;
+        const int ub_ps = R.same_s ? ub : upper_bound_guess(R.ps, n, s, P.ps_inv_step);
+        int j = ub_ps - 1;
+        j = j > n - 2 ? n - 2 : j;
+        j = j < 0 ? 0 : j;                                      // only outside the domain
+        double lam2;
+        if (R.same_s && j == j0 && j1 == j0 + 1) {
+            lam2 = lam;                                         // same dividend, same divisor
+        } else {
+            const double sl = R.ps[j + 1] - R.ps[j];
+            lam2 = D.div(s - R.ps[j], sl, D.rcp(sl));
+        }
+        const double p0x = R.px[j], p0y = R.py[j];
+        o.bx = p0x + lam2 * (R.px[j + 1] - p0x);
+        o.by = p0y + lam2 * (R.py[j + 1] - p0y);
+        const double n0x = R.nx[j], n0y = R.ny[j];
+        o.nx = n0x + lam2 * (R.nx[j + 1] - n0x);
+        o.ny = n0y + lam2 * (R.ny[j + 1] - n0y);
+    }
+    o.s = s; o.sv = sv; o.sa = sa; o.th_ref = th_ref;
+    o.flags = flags | ((D.reject & 0x80000000u) ? LR_REJECT : 0u);
+    return o;
+}
+
+// the candidate's own part of the step, given the longitudinal row
+template <bool EXACT>
+__device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables& R, const LimitRcp& Y, const LonRow& L,
+                                            const double* __restrict__ cd_ptr, double cs0, double th_prev, double kap_prev,
+                                            int i) {
+    const rp_plan_inputs& in = P.in;
+    const bool low_vel = in.low_vel_mode != 0;
+    const double dt = in.dt;
+    Divider<EXACT> D;
+    StepOut o;
+    double cd[6];
+    {
+        const double2* b = reinterpret_cast<const double2*>(cd_ptr);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double2 w = __ldg(b + q);
+            cd[2 * q] = w.x; cd[2 * q + 1] = w.y;
+        }
+    }
+    const double s = L.s, sv = L.sv, sa = L.sa;
+    double d, dv, da;
+    if (!low_vel) {
+        const double tt = (double)i * dt;
+        const double t2 = tt * tt, t3 = t2 * tt, t4 = t2 * t2, t5 = t4 * tt;
+        d = poly_pos(cd, tt, t2, t3, t4, t5);
+        dv = poly_vel(cd, tt, t2, t3, t4);
+        da = poly_acc(cd, tt, t2, t3);
+    } else {
+        const double s1 = s - cs0;                              // s - s[0]; s[0] == c0 exactly
+        const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+        d = poly_pos(cd, s1, s2, s3, s4, s5);
+        dv = poly_vel(cd, s1, s2, s3, s4);
+        da = poly_acc(cd, s1, s2, s3);
+    }
+    dv = fabs(dv) < kEps ? 0.0 : dv;
+    o.pre = L.flags & LR_PRE;
+
+    // ---- orientation (:810-873) ----------------------------------------------------------------------
+    const bool moving = (L.flags & LR_MOVING) != 0u;
+    double dp, dpp;
+    if (!low_vel) {
+        const double svs = moving ? sv : 1.0;
+        const double dp_q = D.div(dv, svs, L.y_sv);
+        dp = moving ? dp_q : 0.;
+        const double ddot = da - dp * sa;
+        const double sv2 = svs * svs;
+        const double dpp_q = D.div(ddot, sv2, L.y_sv2);
+        dpp = moving ? dpp_q : 0.;
+    } else {
+        dp = dv;
+        dpp = da;
+    }
+    const double th_ref = L.th_ref;
     const bool carry = !moving && !low_vel;
     double th_cl, th_gl, cosT, tanT;
     if (!carry) {
@@ -178,16 +246,14 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
         tanT = dp;
     } else {
         // standstill in high-velocity mode keeps the previous global orientation (:866-873)
-        th_gl = i > 0 ? I.th_prev : in.x0_orientation;
+        th_gl = i > 0 ? th_prev : in.x0_orientation;
         th_cl = th_gl - th_ref;
         cosT = cos(th_cl);
         tanT = tan(th_cl);
     }
 
     // ---- curvature, velocity, acceleration (:876-896) -------------------------------------------------
-    const double k0 = R.curv[j0], kd0 = R.curv_d[j0];
-    const double k_r = (R.curv[j1] - k0) * lam + k0;
-    const double k_r_d = (R.curv_d[j1] - kd0) * lam + kd0;
+    const double k_r = L.k_r, k_r_d = L.k_r_d;
     const double oneKrD = (1 - k_r * d);
     const double y_cos = D.rcp(cosT);
     const double q = D.div_nz(cosT, oneKrD, D.rcp(oneKrD));
@@ -199,25 +265,25 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
 
     // ---- the five ordered limit checks (:971-1017), all evaluated, first violation selected ---------------
     {
-        const Limits& L = P.lim;
+        const Limits& Lm = P.lim;
         const unsigned mask = in.constraint_mask;
         const bool c_v = v < -kEps;
-        const bool c_k = fabs(kappa) > L.kappa_max;
-        const double yaw_q = D.div(th_gl - I.th_prev, dt, Y.y_dt);
+        const bool c_k = fabs(kappa) > Lm.kappa_max;
+        const double yaw_q = D.div(th_gl - th_prev, dt, Y.y_dt);
         const double yaw_rate = i > 0 ? yaw_q : 0.;
         // round(np.float64, 5) == rint(x * 1e5) / 1e5   
-        const bool c_y = fabs(D.div(rint(yaw_rate * 100000.0), 100000.0, Y.y_1e5)) > L.kappa_max * v;
+        const bool c_y = fabs(D.div(rint(yaw_rate * 100000.0), 100000.0, Y.y_1e5)) > Lm.kappa_max * v;
         // cos(atan2(wb * kappa, 1))^2 == 1 / (1 + (wb * kappa)^2)  (see check_constraints)
-        const double tk = L.wheelbase * kappa;
-        const double kappa_dot_max = D.div_nz(L.v_delta_max * (1.0 + tk * tk), L.wheelbase, Y.y_wb);
-        const double kd_q = D.div(kappa - I.kap_prev, dt, Y.y_dt);
+        const double tk = Lm.wheelbase * kappa;
+        const double kappa_dot_max = D.div_nz(Lm.v_delta_max * (1.0 + tk * tk), Lm.wheelbase, Y.y_wb);
+        const double kd_q = D.div(kappa - kap_prev, dt, Y.y_dt);
         const double kappa_dot = i > 0 ? kd_q : 0.;
         const bool c_kd = fabs(kappa_dot) > kappa_dot_max;
-        const bool fast = v > L.v_switch;
+        const bool fast = v > Lm.v_switch;
         const double vv = fast ? v : 1.0;
-        const double a_hi_q = D.div_nz(L.a_max * L.v_switch, vv, D.rcp(vv));
-        const double a_hi = fast ? a_hi_q : L.a_max;
-        const bool c_a = !(-L.a_max <= a && a <= a_hi);
+        const double a_hi_q = D.div_nz(Lm.a_max * Lm.v_switch, vv, D.rcp(vv));
+        const double a_hi = fast ? a_hi_q : Lm.a_max;
+        const bool c_a = !(-Lm.a_max <= a && a <= a_hi);
         int r = R_NONE;
         r = ((mask & C_ACCELERATION) && c_a) ? R_ACCELERATION : r;
         r = ((mask & C_KAPPA_DOT) && c_kd) ? R_KAPPA_DOT : r;
@@ -226,35 +292,20 @@ __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTable
         r = ((mask & C_VELOCITY) && c_v) ? R_VELOCITY : r;
         o.reason = r;
     }
-
-    // ---- (s, d) -> (x, y) (:908-917; project_to_cartesian) -------------------------------------------------
-    {
-        const int n = R.n;
-        const bool ok = (s >= R.ps[0] && s <= R.ps[n - 1]) && (fabs(d) <= R.limit);
-        const int ub_ps = R.same_s ? ub : upper_bound_guess(R.ps, n, s, P.ps_inv_step);
-        int j = ub_ps - 1;
-        j = j > n - 2 ? n - 2 : j;
-        j = j < 0 ? 0 : j;                                      // only outside the domain (ok == false)
-        double lam2;
-        if (R.same_s && j == j0 && j1 == j0 + 1) {
-            lam2 = lam;                                         // same dividend, same divisor
-        } else {
-            const double sl = R.ps[j + 1] - R.ps[j];
-            lam2 = D.div(s - R.ps[j], sl, D.rcp(sl));
-        }
-        const double p0x = R.px[j], p0y = R.py[j];
-        const double bx = p0x + lam2 * (R.px[j + 1] - p0x);
-        const double by = p0y + lam2 * (R.py[j + 1] - p0y);
-        const double n0x = R.nx[j], n0y = R.ny[j];
-        const double nx = n0x + lam2 * (R.nx[j + 1] - n0x);
-        const double ny = n0y + lam2 * (R.ny[j + 1] - n0y);
-        o.x = ok ? bx + d * nx : 0.;
-        o.y = ok ? by + d * ny : 0.;
-        o.proj_fail = ok ? 0 : 1;
-    }
+    // ---- (s, d) -> (x, y) ---------------------------------------------------------------------------------
+    const bool ok = (L.flags & LR_OK_S) && (fabs(d) <= R.limit);
+    o.x = ok ? L.bx + d * L.nx : 0.;
+    o.y = ok ? L.by + d * L.ny : 0.;
+    o.proj_fail = ok ? 0 : 1;
     o.th_gl = th_gl; o.th_cl = th_cl; o.v = v; o.a = a; o.kappa = kappa; o.s = s; o.sv = sv; o.d = d; o.dv = dv;
-    o.reject = D.reject;
+    o.reject = D.reject | ((L.flags & LR_REJECT) ? 0x80000000u : 0u);
     return o;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTables& R, const LimitRcp& Y, const StepIn& I) {
+    const LonRow L = lon_part<EXACT>(P, R, I.cs, I.i);
+    return lat_part<EXACT>(P, R, Y, L, I.cd, __ldg(I.cs), I.th_prev, I.kap_prev, I.i);
 }
 
 // the rare exact redo: out of line, so its plain divisions (each with a slow-path call) stay out of the hot loop
@@ -280,9 +331,13 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 
 // ---- one candidate through the whole horizon (the per-lane body of both kernels below) ----------------------
 // acc: this thread's accumulator column (+ (row * 8 + j) * BLOCK), s_vmid: this thread's parked v[mid] slot
-template <int BLOCK>
+// SHARED_LON: all 32 lanes of the warp are candidates of one (t, lon) pair (grid bundle, n_d a multiple of 32): the
+// longitudinal rows of 32 consecutive steps are computed by the warp at once (lane = step) into `rows`
+// ([field][32] doubles + [32] flag words of this warp's shared memory) and broadcast from there.
+template <int BLOCK, bool SHARED_LON>
 __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k,
-                                           double* __restrict__ acc, double* __restrict__ s_vmid) {
+                                           double* __restrict__ acc, double* __restrict__ s_vmid,
+                                           double* __restrict__ rows) {
     const int Np1 = P.Np1;
     const ObstacleTables& O = P.obs;
     const rp_plan_inputs& in = P.in;
@@ -335,6 +390,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     }
 
     unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
+    const double cs0 = SHARED_LON ? __ldg(I.cs) : 0.;
     // values of the current / last polynomial step (the extension reads them after step tl - 1)
     double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
     double cn = 1., sn = 0.;                       // cos / sin of th_gl
@@ -346,7 +402,30 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
         if (i < tl) {
             I.i = i; I.th_prev = th_gl; I.kap_prev = kappa;
-            StepOut o = poly_step<false>(P, R, Y, I);
+            StepOut o;
+            if (SHARED_LON) {
+                const int lane = threadIdx.x & 31;
+                unsigned* rflags = reinterpret_cast<unsigned*>(rows + kLonRowDoubles * 32);
+                if ((i & 31) == 0) {
+                    __syncwarp();
+                    if (i + lane < tl) {
+                        const LonRow w = lon_part<false>(P, R, I.cs, i + lane);
+                        double* c = rows + lane;
+                        c[0] = w.s; c[32] = w.sv; c[64] = w.sa; c[96] = w.y_sv; c[128] = w.y_sv2; c[160] = w.th_ref;
+                        c[192] = w.k_r; c[224] = w.k_r_d; c[256] = w.bx; c[288] = w.by; c[320] = w.nx; c[352] = w.ny;
+                        rflags[lane] = w.flags;
+                    }
+                    __syncwarp();
+                }
+                const double* c = rows + (i & 31);
+                LonRow L;
+                L.s = c[0]; L.sv = c[32]; L.sa = c[64]; L.y_sv = c[96]; L.y_sv2 = c[128]; L.th_ref = c[160];
+                L.k_r = c[192]; L.k_r_d = c[224]; L.bx = c[256]; L.by = c[288]; L.nx = c[320]; L.ny = c[352];
+                L.flags = rflags[i & 31];
+                o = lat_part<false>(P, R, Y, L, I.cd, cs0, th_gl, kappa, i);
+            } else {
+                o = poly_step<false>(P, R, Y, I);
+            }
             if (o.reject & 0x80000000u) o = poly_step_exact(P, R, Y, I);
             pre |= o.pre;
             if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
@@ -474,7 +553,7 @@ __device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs,
 }
 
 // ---- one bundle: persistent grid, warps draw chunks of 32 candidates from a counter -----------------------------
-template <int BLOCK>
+template <int BLOCK, bool SHARED_LON>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
@@ -501,6 +580,8 @@ cand_kernel(const __grid_constant__ PlanParams P) {
     sp += BLOCK;
     LimitRcp* const s_Y = reinterpret_cast<LimitRcp*>(sp);
     sp += 4;
+    double* const s_rows = sp + (size_t)(tid >> 5) * (kLonRowDoubles * 32 + 16);   // this warp's longitudinal rows
+    if (SHARED_LON) sp += (size_t)(BLOCK / 32) * (kLonRowDoubles * 32 + 16);
     Segment* const s_segs = reinterpret_cast<Segment*>(sp);
     for (int q = tid; q < P.n_segs; q += BLOCK) s_segs[q] = P.segs[q];
     if (tid == 0) {
@@ -516,7 +597,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= P.n_groups) break;
         const int k = chunk_candidate(s_segs, P.n_segs, g, lane);
-        if (k >= 0) cand_march<BLOCK>(P, R, *s_Y, k, acc, s_vmid);
+        if (k >= 0) cand_march<BLOCK, SHARED_LON>(P, R, *s_Y, k, acc, s_vmid, s_rows);
     }
 }
 
@@ -567,7 +648,7 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
             sc_cached = lo;
         }
         const int k = chunk_candidate(P.segs, P.n_segs, g - B.chunk_prefix[lo], lane);
-        if (k >= 0) cand_march<BLOCK>(P, P.ref, *s_Y, k, acc, s_vmid);
+        if (k >= 0) cand_march<BLOCK, false>(P, P.ref, *s_Y, k, acc, s_vmid, nullptr);
     }
 }
 

@@ -1,4 +1,6 @@
 """GPU parity: the CUDA path, called through the C-ABI, against the oracle on the same seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -96,3 +98,25 @@ def test_shared_reciprocal_division_is_ieee_division():
         ref = a / b
     same = (q1.view(np.int64) == ref.view(np.int64)) | (np.isnan(q1) & np.isnan(ref))
     assert same.all(), (a[~same][:5], b[~same][:5], q1[~same][:5], ref[~same][:5])
+
+
+@pytest.mark.parametrize("low_vel", [False, True], ids=["high_vel", "low_vel"])
+def test_warp_shared_longitudinal_rows(low_vel):
+    """n_d a multiple of 32: the candidate-major kernel computes the (t, lon)-invariant part of a step once per warp
+    (cand_kernel<128, true>) -- same bits as the per-lane form and the step-parallel kernel, parity with the oracle"""
+    from commonroad_rp_b200 import _lib
+    prob = _bundle(seed=2, level=1, N=40, s_dot0=3.0 if low_vel else 12.0, low_vel=low_vel, t_min=0.8)
+    d0 = float(prob["x0_lat"][0])
+    rng = np.random.default_rng(5)
+    d = np.concatenate([[d0], rng.uniform(-3.0, 3.0, 63)])
+    prob["d"] = np.array([float(x) for x in set(d)])                  # 64 lateral targets, d0 among them
+    assert len(prob["d"]) == 64
+    o = O.plan_grid(prob, want_states=True, full_collision=True)
+    eng = H.engine_for(prob)
+    g = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_CANDIDATE_MAJOR)
+    H.assert_parity(o, g, prob, tag="shared-lon")
+    g2 = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_STEP_PARALLEL)
+    assert np.array_equal(g["status"], g2["status"]) and np.array_equal(g["reason"], g2["reason"])
+    assert np.array_equal(g["step"], g2["step"])
+    assert np.array_equal(g["cost"].view(np.int64), g2["cost"].view(np.int64))
+    eng.close()
