@@ -398,7 +398,7 @@ def run_reference_arm(args, rank, world):
         "cand_timesteps_per_sec": value * (N_HORIZON + 1), "gpu_launches": 0,
         "p50_replanning_cycle_ms": replanning_latency_port(),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -612,10 +612,30 @@ def main():
         rate, desc, sec, n_s = cpu_port_rate(dense_workload(1), 3, cores)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
                                 "seconds": sec}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Everything native libraries print on fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE JSON line is
+    written to the real stdout by ``emit``."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 if __name__ == "__main__":
+    capture_stdout()
     main()

@@ -77,6 +77,7 @@ SIGNATURES = {
     "rp_ctx_set_kernel_policy": (C.c_int, [C.c_void_p, C.c_int]),
     "rp_export_record_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rp_count_colliders_before_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rp_merge_records_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "rp_fetch_states": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "rp_fetch_candidates": (C.c_int, [C.c_void_p, _dp, _ip, _ip, _ip]),
     "rp_fetch_coeffs": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
@@ -294,6 +295,10 @@ class Engine:
 
     def export_record_dev(self, dev_ptr):
         self._check(self._lib.rp_export_record_dev(self._ctx, C.c_void_p(int(dev_ptr))))
+
+    def merge_records_dev(self, dev_gathered_ptr, world, dev_winner_ptr, dev_totals_ptr):
+        self._check(self._lib.rp_merge_records_dev(self._ctx, C.c_void_p(int(dev_gathered_ptr)), int(world),
+                                                   C.c_void_p(int(dev_winner_ptr)), C.c_void_p(int(dev_totals_ptr))))
 
     def count_colliders_before_dev(self, dev_winner_ptr, dev_out_ptr):
         self._check(self._lib.rp_count_colliders_before_dev(self._ctx, C.c_void_p(int(dev_winner_ptr)),

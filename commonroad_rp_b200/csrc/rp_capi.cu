@@ -1212,6 +1212,14 @@ int rp_export_record_dev(rp_ctx* ctx, double* dev_dst4) {
     return RP_OK;
 }
 
+int rp_merge_records_dev(rp_ctx* ctx, const double* dev_gathered, int world, double* dev_winner2, double* dev_totals2) {
+    if (int rc = bind(ctx)) return rc;
+    if (!dev_gathered || !dev_winner2 || !dev_totals2 || world < 1) return fail(RP_ERR_ARG, "invalid merge arguments");
+    rp::merge_records_kernel<<<1, 32, 0, ctx->stream>>>(dev_gathered, world, dev_winner2, dev_totals2);
+    RP_CUDA(cudaGetLastError());
+    return RP_OK;
+}
+
 int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double* dev_out1) {
     if (int rc = bind(ctx)) return rc;
     if (!dev_winner2 || !dev_out1) return fail(RP_ERR_ARG, "null device pointer");

@@ -356,6 +356,31 @@ __global__ void export_record_kernel(const PlanResultDev* __restrict__ res, doub
     dst[3] = (double)res->r.n_feasible;
 }
 
+// lexicographic min on (cost, enumeration index) over the ranks' gathered records [world][4] and the summed counters:
+// winner[2] = [cost, index] (+inf = none), totals[2] = [n_infeasible_kinematics, n_feasible]; one warp
+__global__ void merge_records_kernel(const double* __restrict__ gathered, int world, double* __restrict__ winner,
+                                     double* __restrict__ totals) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double bc = inf, bi = inf, kin = 0., feas = 0.;
+    for (int r = threadIdx.x; r < world; r += 32) {
+        const double c = gathered[4 * r], i = gathered[4 * r + 1];
+        if (c < bc || (c == bc && i < bi)) { bc = c; bi = i; }
+        kin += gathered[4 * r + 2];
+        feas += gathered[4 * r + 3];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double oc = __shfl_down_sync(0xffffffffu, bc, off), oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+        kin += __shfl_down_sync(0xffffffffu, kin, off);
+        feas += __shfl_down_sync(0xffffffffu, feas, off);
+    }
+    if (threadIdx.x == 0) {
+        winner[0] = bc; winner[1] = bi;
+        totals[0] = kin; totals[1] = feas;
+    }
+}
+
 // colliders of this shard ranked before the GLOBAL winner (lazy collision count, App. B#12)
 __global__ void __launch_bounds__(256) count_before_kernel(const double* __restrict__ cost, const int* __restrict__ info,
                                                            int first, int count, const double* __restrict__ winner,

@@ -195,6 +195,9 @@ int rp_set_candidate_range(rp_ctx* ctx, int first, int count);
  * rp_count_colliders_before_dev writes to dev_out1 how many of this shard's colliding candidates rank
  * before the GLOBAL winner dev_winner2 = [cost, index] (lazy collision count, reactive_planner.py:1031-1063). */
 int rp_export_record_dev(rp_ctx* ctx, double* dev_dst4);
+/* merge of the all-gathered records dev_gathered[world][4]: dev_winner2 = lexicographic min on (cost, index),
+ * dev_totals2 = [sum n_infeasible_kinematics, sum n_feasible] */
+int rp_merge_records_dev(rp_ctx* ctx, const double* dev_gathered, int world, double* dev_winner2, double* dev_totals2);
 int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double* dev_out1);
 
 /* ---- batches of independent scenarios (reactive_planner.py has no counterpart: one ReactivePlanner per scenario

@@ -393,3 +393,29 @@ def test_continuous_collision_check_through_the_planner_api():
         tvo.append_obstacle(collision.RectOBB(2.0, 1.0, 0.1 * k, 1.0 * k, 0.0))
     hull, err = collision.trajectory_preprocess_obb_sum(tvo)
     assert err == 0 and hull.time_start_idx() == 5 and hull.time_end_idx() == 7
+
+
+def test_merge_records_kernel_matches_host_merge():
+    """the one-warp merge of the all-gathered shard records (multi-GPU arg-min) against the torch reference"""
+    import torch
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200.parallel import merge_records
+    eng = _lib.Engine(0)
+    inf = float("inf")
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 8, 40):
+        g = rng.uniform(0, 10, (world, 4))
+        g[:, 1] = rng.integers(0, 1000, world)
+        g[:, 2:] = rng.integers(0, 50, (world, 2))
+        if world > 2:
+            g[1, 0] = g[0, 0]                 # cost tie: lowest index wins
+            g[2] = [inf, inf, 3, 0]           # a shard without a feasible candidate
+        gathered = torch.tensor(g, dtype=torch.float64, device="cuda:0")
+        winner = torch.empty(2, dtype=torch.float64, device="cuda:0")
+        totals = torch.empty(2, dtype=torch.float64, device="cuda:0")
+        torch.cuda.synchronize()
+        eng.merge_records_dev(gathered.data_ptr(), world, winner.data_ptr(), totals.data_ptr())
+        eng.synchronize()
+        w, t = merge_records(gathered)
+        assert torch.equal(w.cpu(), winner.cpu()) and torch.equal(t.cpu(), totals.cpu())
+    eng.close()
