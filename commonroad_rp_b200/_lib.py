@@ -93,7 +93,7 @@ SIGNATURES = {
     "rp_batch_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "rp_initial_states": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, _dp, _dp, _ip]),
     "rp_batch_initial_states": (C.c_int, [C.c_void_p, _dp, _ip, _dp, _dp, _ip]),
-    "rp_selftest_divide": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
+    "rp_selftest_divide": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip]),
     "rp_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rp_stage_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "rp_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -280,11 +280,13 @@ class Engine:
         return lon, lat, status
 
     def selftest_divide(self, a, b):
-        """(shared-reciprocal quotient, plain a / b) as computed on the device."""
+        """(shared-reciprocal quotient as the kernels form it, plain a / b, 1 where the range check fell back to the plain
+        division) as computed on the device."""
         a, b = _f64(a).ravel(), _f64(b).ravel()
         q1, q2 = np.empty_like(a), np.empty_like(a)
-        self._check(self._lib.rp_selftest_divide(self._ctx, len(a), _p(a, _dp), _p(b, _dp), _p(q1, _dp), _p(q2, _dp)))
-        return q1, q2
+        rej = np.empty(len(a), dtype=np.int32)
+        self._check(self._lib.rp_selftest_divide(self._ctx, len(a), _p(a, _dp), _p(b, _dp), _p(q1, _dp), _p(q2, _dp), _p(rej, _ip)))
+        return q1, q2, rej
 
     def set_kernel_policy(self, policy):
         """KERNEL_AUTO / KERNEL_STEP_PARALLEL / KERNEL_CANDIDATE_MAJOR (identical results, different schedule)."""

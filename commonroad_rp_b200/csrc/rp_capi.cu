@@ -1117,32 +1117,41 @@ int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time
 
 namespace {
 __global__ void divide_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ q_shared,
-                              double* __restrict__ q_plain) {
+                              double* __restrict__ q_plain, int* __restrict__ rejected) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
-    q_shared[g] = rp::div_rcp(a[g], b[g], rp::rcp_refined(b[g]));
+    // exactly what poly_step does: fast quotient with a sticky reject word, plain division on reject
+    unsigned reject = 0u;
+    double q = rp::div_fast<true>(a[g], b[g], rp::rcp_window(b[g]), reject);
+    const bool rej = (reject & 0x80000000u) != 0u;
+    if (rej) q = a[g] / b[g];
+    q_shared[g] = q;
     q_plain[g] = a[g] / b[g];
+    if (rejected) rejected[g] = rej ? 1 : 0;
 }
 }  // namespace
 
-int rp_selftest_divide(rp_ctx* ctx, int n, const double* a, const double* b, double* q_shared, double* q_plain) {
+int rp_selftest_divide(rp_ctx* ctx, int n, const double* a, const double* b, double* q_shared, double* q_plain, int32_t* rejected) {
     if (int rc = bind(ctx)) return rc;
     if (n < 0) return fail(RP_ERR_ARG, "negative count");
     if (n == 0) return RP_OK;
     if (!a || !b || !q_shared || !q_plain) return fail(RP_ERR_ARG, "null array");
-    DevBuf da, db, d1, d2;
+    DevBuf da, db, d1, d2, d3;
     int rc = RP_OK;
-    auto cleanup = [&]() { da.release(); db.release(); d1.release(); d2.release(); };
+    auto cleanup = [&]() { da.release(); db.release(); d1.release(); d2.release(); d3.release(); };
     const size_t bytes = (size_t)n * sizeof(double);
-    if ((rc = da.ensure(bytes)) || (rc = db.ensure(bytes)) || (rc = d1.ensure(bytes)) || (rc = d2.ensure(bytes))) {
+    if ((rc = da.ensure(bytes)) || (rc = db.ensure(bytes)) || (rc = d1.ensure(bytes)) || (rc = d2.ensure(bytes)) ||
+        (rc = d3.ensure((size_t)n * sizeof(int)))) {
         cleanup();
         return rc;
     }
     cudaMemcpyAsync(da.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, ctx->stream);
-    divide_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, da.as<double>(), db.as<double>(), d1.as<double>(), d2.as<double>());
+    divide_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, da.as<double>(), db.as<double>(), d1.as<double>(), d2.as<double>(),
+                                                             d3.as<int>());
     cudaMemcpyAsync(q_shared, d1.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(q_plain, d2.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rejected) cudaMemcpyAsync(rejected, d3.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e));

@@ -250,9 +250,12 @@ int rp_solve_coeffs(rp_ctx* ctx, int n, const int32_t* kind, const double* x0, c
 int rp_collide_poses(rp_ctx* ctx, int n, const double* pose, const int32_t* time_idx,
                      double half_length, double half_width, uint8_t* hit);
 
-/* self-test of the kernels' division: q_shared[i] = the shared-reciprocal form used inside the kernels,
- * q_plain[i] = a[i] / b[i] as the compiler emits it; the two must agree bit for bit for every input */
-int rp_selftest_divide(rp_ctx* ctx, int n, const double* a, const double* b, double* q_shared, double* q_plain);
+/* self-test of the kernels' division: q_shared[i] = what the candidate-major kernel computes (quotient from a shared
+ * refined reciprocal with a range check, plain division when the check rejects), q_plain[i] = a[i] / b[i] as the
+ * compiler emits it -- the two must agree bit for bit for every input; rejected[i] (may be NULL) = 1 where the range
+ * check sent the pair to the plain division */
+int rp_selftest_divide(rp_ctx* ctx, int n, const double* a, const double* b, double* q_shared, double* q_plain,
+                       int32_t* rejected);
 
 /* device timing of the last rp_grid_launch stages in milliseconds: [coeff, fused, argmin, winner] */
 int rp_last_stage_ms(rp_ctx* ctx, float* ms4);

@@ -90,8 +90,17 @@ def test_shared_reciprocal_division_is_ieee_division():
     a = np.concatenate([a, sa.ravel()])
     b = np.concatenate([b, sb.ravel()])
     eng = Engine(0)
-    q1, q2 = eng.selftest_divide(a, b)
+    q1, q2, rej = eng.selftest_divide(a, b)
+    # operands of the path's magnitudes never leave the fast form -- zero dividends of either sign included
+    az = np.concatenate([np.zeros(8), -np.zeros(8), rng.normal(size=4096), np.rint(rng.normal(size=4096) * 0.4)])
+    bz = rng.choice([0.1, 100000.0, 2.5789, -0.7, 15.0], len(az))
+    z1, z2, zrej = eng.selftest_divide(az, bz)
     eng.close()
+    assert not zrej.any()
+    assert np.array_equal(z1.view(np.int64), z2.view(np.int64))
+    with np.errstate(all="ignore"):
+        assert np.array_equal(z1.view(np.int64), (az / bz).view(np.int64))
+    assert rej[:n].sum() == 0                                       # |a|, |b| in [2^-60, 2^60]
     same = (q1.view(np.int64) == q2.view(np.int64)) | (np.isnan(q1) & np.isnan(q2))
     assert same.all(), (a[~same][:5], b[~same][:5], q1[~same][:5], q2[~same][:5])
     with np.errstate(all="ignore"):
