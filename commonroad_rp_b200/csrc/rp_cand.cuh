@@ -24,10 +24,10 @@
 namespace rp {
 
 #ifndef RP_CAND_THREADS
-#define RP_CAND_THREADS 128
+#define RP_CAND_THREADS 512
 #endif
 #ifndef RP_CAND_MIN_BLOCKS
-#define RP_CAND_MIN_BLOCKS 4
+#define RP_CAND_MIN_BLOCKS 1
 #endif
 
 // cost accumulator rows kept in shared memory: acc[(row * 8 + j) * BLOCK + tid], numpy's 8 partial sums per np.sum
@@ -91,6 +91,7 @@ struct StepIn {
 };
 struct StepOut {
     double x, y, th_gl, th_cl, v, a, kappa, s, sv, d, dv;
+    double cn, sn;       // cos / sin of th_gl
     unsigned pre;        // pre-filter bits of this step (:796-805)
     int reason;          // first violated limit of this step (R_NONE if none)
     int proj_fail;       // projection domain left at this step (:911-917)
@@ -105,11 +106,12 @@ struct LonRow {
     double s, sv, sa;            // sv after the eps clamp
     double y_sv, y_sv2;          // refined reciprocals of the guarded s_dot and its square
     double th_ref, k_r, k_r_d;   // reference heading / curvature / curvature rate at s
+    double c_ref, s_ref;         // cos / sin of th_ref
     double bx, by, nx, ny;       // frame base point and interpolated pseudo-normal: (x, y) = b + d * n
     unsigned flags;
 };
 enum : unsigned { LR_PRE = 3u, LR_MOVING = 4u, LR_OK_S = 8u, LR_REJECT = 16u };
-constexpr int kLonRowDoubles = 12;
+constexpr int kLonRowDoubles = 14;
 
 template <bool EXACT>
 __device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables& R, const double* __restrict__ cs_ptr, int i) {
@@ -178,6 +180,7 @@ __device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables&
         o.ny = n0y + lam2 * (R.ny[j + 1] - n0y);
     }
     o.s = s; o.sv = sv; o.sa = sa; o.th_ref = th_ref;
+    sincos(th_ref, &o.s_ref, &o.c_ref);
     o.flags = flags | ((D.reject & 0x80000000u) ? LR_REJECT : 0u);
     return o;
 }
@@ -244,12 +247,14 @@ __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables
         const double hyp = sqrt(1.0 + dp * dp);
         cosT = D.div_nz(1.0, hyp, D.rcp(hyp));
         tanT = dp;
+        heading_cos_sin(cosT, tanT, L.c_ref, L.s_ref, o.cn, o.sn);
     } else {
         // standstill in high-velocity mode keeps the previous global orientation (:866-873)
         th_gl = i > 0 ? th_prev : in.x0_orientation;
         th_cl = th_gl - th_ref;
         cosT = cos(th_cl);
         tanT = tan(th_cl);
+        sincos(th_gl, &o.sn, &o.cn);
     }
 
     // ---- curvature, velocity, acceleration (:876-896) -------------------------------------------------
@@ -413,6 +418,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
                         double* c = rows + lane;
                         c[0] = w.s; c[32] = w.sv; c[64] = w.sa; c[96] = w.y_sv; c[128] = w.y_sv2; c[160] = w.th_ref;
                         c[192] = w.k_r; c[224] = w.k_r_d; c[256] = w.bx; c[288] = w.by; c[320] = w.nx; c[352] = w.ny;
+                        c[384] = w.c_ref; c[416] = w.s_ref;
                         rflags[lane] = w.flags;
                     }
                     __syncwarp();
@@ -421,6 +427,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
                 LonRow L;
                 L.s = c[0]; L.sv = c[32]; L.sa = c[64]; L.y_sv = c[96]; L.y_sv2 = c[128]; L.th_ref = c[160];
                 L.k_r = c[192]; L.k_r_d = c[224]; L.bx = c[256]; L.by = c[288]; L.nx = c[320]; L.ny = c[352];
+                L.c_ref = c[384]; L.s_ref = c[416];
                 L.flags = rflags[i & 31];
                 o = lat_part<false>(P, R, Y, L, I.cd, cs0, th_gl, kappa, i);
             } else {
@@ -432,7 +439,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
             x = o.x; y = o.y; th_gl = o.th_gl; th_cl = o.th_cl; v = o.v; a = o.a; kappa = o.kappa;
             s = o.s; sv = o.sv; d = o.d; dv = o.dv;
-            if (in.check_collision || i == tl - 1) sincos(th_gl, &sn, &cn);
+            cn = o.cn; sn = o.sn;
             px = x; py = y;
             c_a = a; c_v = v; c_s = s; c_d = d; c_th = th_cl;
         } else {

@@ -294,7 +294,7 @@ fused_kernel(const __grid_constant__ PlanParams P) {
         }
 
         // ---- curvature, velocity, acceleration (reactive_planner.py:876-896) -----------------------
-        double kappa = 0., v = 0., a = 0.;
+        double kappa = 0., v = 0., a = 0., cn = 1., sn = 0.;
         if (act) {
             const double k0 = R.curv[j0], kd0 = R.curv_d[j0];
             const double k_r = (R.curv[j1] - k0) * lam + k0;
@@ -305,10 +305,17 @@ fused_kernel(const __grid_constant__ PlanParams P) {
                 // theta_cl = atan(dp): cos(theta_cl) = 1 / sqrt(1 + dp^2), tan(theta_cl) = dp (<= 1 ulp from libm)
                 cosT = 1.0 / sqrt(1.0 + dp * dp);
                 tanT = dp;
+                double s_ref, c_ref;
+                sincos(th_ref, &s_ref, &c_ref);
+                heading_cos_sin(cosT, tanT, c_ref, s_ref, cn, sn);
             } else {
                 cosT = cos(th_cl);
                 tanT = tan(th_cl);
+                sincos(th_gl, &sn, &cn);
             }
+            // cos / sin of the heading for the collision phase: the head of the (tail-only) increment rows is free
+            scratch[4 * Np1 + i] = cn;
+            scratch[5 * Np1 + i] = sn;
             const double q = ddiv(cosT, oneKrD);
             kappa = (dpp + (k_r * dp + k_r_d * d) * tanT) * cosT * (q * q) + q * k_r;
             v = sv * ddiv(oneKrD, cosT);
@@ -350,8 +357,6 @@ fused_kernel(const __grid_constant__ PlanParams P) {
                 s_last[0] = x; s_last[1] = y; s_last[2] = th_gl; s_last[3] = v; s_last[4] = a; s_last[5] = kappa;
                 s_last[6] = kdot; s_last[7] = s; s_last[8] = d; s_last[9] = th_cl; s_last[10] = sv; s_last[11] = sa;
                 s_last[12] = dv; s_last[13] = da;
-                double sn, cn;
-                sincos(th_gl, &sn, &cn);
                 s_last[14] = cn; s_last[15] = sn;
             }
             if (costed) {
@@ -521,9 +526,9 @@ fused_kernel(const __grid_constant__ PlanParams P) {
                 if (!(fl[F_STATE] & S_KINOK)) continue;
                 if (lazy && fl[F_GATE] == 0u) continue;
                 const double* sc = slots + (size_t)c2 * per_slot;
-                const double th2 = sc[i2];
-                double st, ct;
-                sincos(th2, &st, &ct);
+                const bool tail = i2 >= (int)fl[F_TL];
+                const double ct = tail ? sc[kRows * Np1 + 14] : sc[4 * Np1 + i2];
+                const double st = tail ? sc[kRows * Np1 + 15] : sc[5 * Np1 + i2];
                 const double ecx = sc[2 * Np1 + i2] + P.wb_rear * ct;
                 const double ecy = sc[3 * Np1 + i2] + P.wb_rear * st;
                 const int tidx = in.x0_time_step + i2 * in.factor;
