@@ -496,14 +496,16 @@ def main():
 
     # ---- end to end through the host-buffer API ----
     t_np, lon_np, d_np = np.array(work["t"]), np.array(work["lon"]), np.array(work["d"])
+    from commonroad_rp_b200._lib import traj_len_of
+    tl_np = np.array([traj_len_of(x, DT) for x in t_np], dtype=np.int32)        # an input array of rp_plan_grid
     for _ in range(2):
-        r = eng.plan_grid(inputs, t_np, lon_np, d_np)
+        r = eng.plan_grid(inputs, t_np, lon_np, d_np, tl_np)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e2e_t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = eng.plan_grid(inputs, t_np, lon_np, d_np)
+        r = eng.plan_grid(inputs, t_np, lon_np, d_np, tl_np)
         if world > 1:
             global_argmin(eng, rec, world)
         if r.winner >= 0:

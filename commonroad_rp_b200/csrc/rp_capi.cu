@@ -112,13 +112,20 @@ struct rp_ctx {
     bool have_inputs = false, have_plan = false, states_all_valid = false;
     DevBuf d_samples;                   // t | lon | d (doubles) then traj_len (ints)
     DevBuf d_lon_coef, d_lat_coef, d_lat_tau, d_skip;
-    DevBuf d_cost, d_info, d_states_all, d_states_one, d_result, d_index;
+    DevBuf d_cost, d_info, d_states_all, d_result, d_index;
     PinBuf h_stage, h_result;
+    // the result block: [PlanResultDev, padded to kResBytes][winner states 14 x (N+1)] -- ONE device->host copy per cycle
+    static constexpr size_t kResBytes = 256;
+    size_t res_states_bytes = 0;          // bytes of winner states in the block of the last launch
+    bool h_states_valid = false;          // the pinned copy holds the last launch's winner states
+    double* d_states_one() const { return reinterpret_cast<double*>(static_cast<char*>(d_result.p) + kResBytes); }
     size_t off_t = 0, off_lon = 0, off_d = 0, off_len = 0;
 
     // fused-kernel work decomposition (segments of equal traj_len)
     std::vector<int> h_traj_len;
     bool segs_dirty = true;
+    bool geom_key_valid = false;        // shape of the inputs the current work decomposition was built for
+    int geom_key_mode = -1, geom_key_n[9] = {};
     long long tables_version = 0;
     DevBuf d_segs, d_segs_index, d_argmin, d_best;
     PinBuf h_segs, h_segs_index;
@@ -652,7 +659,8 @@ int rp_ctx_create(int device, void* stream, rp_ctx** out) {
     cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_segs, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_result, cudaEventDisableTiming);
-    if (ctx->d_result.ensure(sizeof(rp::PlanResultDev)) || ctx->h_result.ensure(sizeof(rp::PlanResultDev)) ||
+    static_assert(sizeof(rp::PlanResultDev) <= rp_ctx::kResBytes, "result block header too small");
+    if (ctx->d_result.ensure(rp_ctx::kResBytes) || ctx->h_result.ensure(rp_ctx::kResBytes) ||
         ctx->d_index.ensure(sizeof(int))) {
         rp_ctx_destroy(ctx);
         return RP_ERR_NOMEM;
@@ -667,7 +675,7 @@ int rp_ctx_destroy(rp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->d_ref, &ctx->d_obb, &ctx->d_tri, &ctx->d_cell_start, &ctx->d_cell_items, &ctx->d_dyn_box,
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
-                      &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all, &ctx->d_states_one,
+                      &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all,
                       &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best,
                       &ctx->d_work, &ctx->d_clr, &ctx->d_dyn_rows})
         b->release();
@@ -809,8 +817,22 @@ int rp_grid_upload(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double*
         RP_CUDA(cudaEventRecord(ctx->ev_stage, ctx->stream));
         ctx->stage_pending = true;
     }
-    ctx->h_traj_len.assign(traj_len, traj_len + n_t);
-    ctx->segs_dirty = true;
+    // the work decomposition depends on the grid's shape, the horizon and what selects the kernel -- not on the sample
+    // values: consecutive replanning cycles of one planner reuse it
+    const bool same_shape = ctx->geom_key_valid && ctx->geom_key_mode == 0 && ctx->geom_key_n[0] == n_t && ctx->geom_key_n[1] == n_lon &&
+                            ctx->geom_key_n[2] == n_d && ctx->geom_key_n[3] == in->N && ctx->geom_key_n[4] == in->want_all_states &&
+                            ctx->geom_key_n[5] == in->draw_all && ctx->geom_key_n[6] == in->cost_kind &&
+                            ctx->geom_key_n[7] == in->has_desired_speed && ctx->geom_key_n[8] == in->has_desired_s &&
+                            ctx->h_traj_len.size() == (size_t)n_t && std::equal(traj_len, traj_len + n_t, ctx->h_traj_len.begin());
+    if (!same_shape) {
+        ctx->h_traj_len.assign(traj_len, traj_len + n_t);
+        ctx->segs_dirty = true;
+        ctx->geom_key_valid = true;
+        ctx->geom_key_mode = 0;
+        const int key[9] = {n_t, n_lon, n_d, in->N, in->want_all_states, in->draw_all, in->cost_kind, in->has_desired_speed,
+                            in->has_desired_s};
+        std::copy(key, key + 9, ctx->geom_key_n);
+    }
     ctx->have_inputs = true;
     ctx->have_plan = false;
     return RP_OK;
@@ -827,7 +849,13 @@ static int launch_plan(rp_ctx* ctx) {
     }
     if (int rc = ctx->d_cost.ensure((size_t)std::max(n, 1) * sizeof(double))) return rc;
     if (int rc = ctx->d_info.ensure((size_t)std::max(n, 1) * sizeof(int))) return rc;
-    if (int rc = ctx->d_states_one.ensure((size_t)14 * Np1 * sizeof(double))) return rc;
+    ctx->res_states_bytes = (size_t)14 * Np1 * sizeof(double);
+    ctx->h_states_valid = false;
+    if (ctx->d_result.cap < rp_ctx::kResBytes + ctx->res_states_bytes) {
+        RP_CUDA(cudaStreamSynchronize(ctx->stream));           // a previous result copy may still read the old block
+        if (int rc = ctx->d_result.ensure(rp_ctx::kResBytes + ctx->res_states_bytes)) return rc;
+        if (int rc = ctx->h_result.ensure(rp_ctx::kResBytes + ctx->res_states_bytes)) return rc;
+    }
     ctx->states_all_valid = false;
     if (ctx->in.want_all_states) {
         if (int rc = ctx->d_states_all.ensure((size_t)std::max(n, 1) * 14 * Np1 * sizeof(double))) return rc;
@@ -900,11 +928,11 @@ static int launch_plan(rp_ctx* ctx) {
     cudaEventRecord(ctx->ev[3], ctx->stream);
     // winner's 14 x (N+1) state block; the winner index never leaves the device
     if (count > 0) {
-        if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one.as<double>())) return rc;
+        if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one())) return rc;
     }
     if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision) {
         if (ctx->range_count >= 0) return fail(RP_ERR_ARG, "continuous collision check is not available for sharded bundles");
-        rp::continuous_check_kernel<<<1, 128, 0, ctx->stream>>>(ctx->obs, ctx->d_states_one.as<double>(), Np1, ctx->in.x0_time_step,
+        rp::continuous_check_kernel<<<1, 128, 0, ctx->stream>>>(ctx->obs, ctx->d_states_one(), Np1, ctx->in.x0_time_step,
                                                                 0.5 * ctx->veh.length, 0.5 * ctx->veh.width, ctx->veh.wb_rear_axle,
                                                                 dres, ctx->d_info.as<int>());
         RP_CUDA(cudaGetLastError());
@@ -925,9 +953,12 @@ int rp_grid_result(rp_ctx* ctx, rp_plan_result* out) {
     if (int rc = bind(ctx)) return rc;
     if (!out) return fail(RP_ERR_ARG, "null result");
     if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
-    RP_CUDA(cudaMemcpyAsync(ctx->h_result.p, ctx->d_result.p, sizeof(rp::PlanResultDev), cudaMemcpyDeviceToHost, ctx->stream));
+    // result and winner states in ONE copy: rp_fetch_states(winner) is then served from the pinned block
+    RP_CUDA(cudaMemcpyAsync(ctx->h_result.p, ctx->d_result.p, rp_ctx::kResBytes + ctx->res_states_bytes, cudaMemcpyDeviceToHost,
+                            ctx->stream));
     RP_CUDA(cudaEventRecord(ctx->ev_result, ctx->stream));
     RP_CUDA(cudaEventSynchronize(ctx->ev_result));
+    ctx->h_states_valid = true;
     *out = static_cast<rp::PlanResultDev*>(ctx->h_result.p)->r;
     return RP_OK;
 }
@@ -949,6 +980,7 @@ int rp_plan_list(rp_ctx* ctx, const rp_plan_inputs* in, int n_cand, const double
         if (traj_len[q] < 1 || traj_len[q] > in->N + 1) return fail(RP_ERR_ARG, "traj_len out of [1, N+1]");
     ctx->in = *in;
     ctx->mode = 1;
+    ctx->geom_key_valid = false;
     ctx->n_t = ctx->n_lon = ctx->n_d = 0;
     ctx->n_cand = n_cand;
     ctx->off_len = 0;
@@ -985,17 +1017,21 @@ int rp_fetch_states(rp_ctx* ctx, int idx, double* out) {
         RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_all.as<double>() + (size_t)idx * 14 * (ctx->in.N + 1), bytes,
                                 cudaMemcpyDeviceToHost, ctx->stream));
     } else {
-        RP_CUDA(cudaMemcpyAsync(ctx->h_result.p, ctx->d_result.p, sizeof(rp::PlanResultDev), cudaMemcpyDeviceToHost, ctx->stream));
-        RP_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (hres->r.winner != idx) {
-            // lazily re-evaluate one candidate (TrajectorySample views of non-winners)
-            RP_CUDA(cudaMemcpyAsync(ctx->d_index.p, &idx, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            if (int rc = ctx->d_states_all.ensure(bytes)) return rc;
-            if (int rc = launch_states_for_index(ctx, ctx->d_index.as<int>(), 1, ctx->d_states_all.as<double>())) return rc;
-            RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_all.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        } else {
-            RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_one.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!ctx->h_states_valid) {
+            RP_CUDA(cudaMemcpyAsync(ctx->h_result.p, ctx->d_result.p, rp_ctx::kResBytes + ctx->res_states_bytes, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+            RP_CUDA(cudaStreamSynchronize(ctx->stream));
+            ctx->h_states_valid = true;
         }
+        if (hres->r.winner == idx) {
+            std::memcpy(out, static_cast<const char*>(ctx->h_result.p) + rp_ctx::kResBytes, bytes);
+            return RP_OK;
+        }
+        // lazily re-evaluate one candidate (TrajectorySample views of non-winners)
+        RP_CUDA(cudaMemcpyAsync(ctx->d_index.p, &idx, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (int rc = ctx->d_states_all.ensure(bytes)) return rc;
+        if (int rc = launch_states_for_index(ctx, ctx->d_index.as<int>(), 1, ctx->d_states_all.as<double>())) return rc;
+        RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_all.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     RP_CUDA(cudaStreamSynchronize(ctx->stream));
     return RP_OK;
