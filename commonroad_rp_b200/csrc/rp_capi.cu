@@ -625,6 +625,9 @@ int launch_states_for_index(rp_ctx* ctx, const int* d_index, int count, double* 
     P.in.draw_all = 1;          // produce states whatever the verdict was
     P.in.check_collision = 0;
     P.in.cost_kind = RP_COST_NONE;
+    // a handful of candidates: nothing to amortise a staging pass over (tables through L1, no collision phase)
+    P.stage_dyn = 0;
+    if (count <= 4) P.stage_ref = 0;
     return launch_fused(ctx, P, ctx->index_geom);
 }
 
