@@ -565,7 +565,7 @@ def main():
 
     peaks, peak_kind = measured_peaks()
     from commonroad_rp_b200 import _lib as _l
-    kernel_name = "rp::cand_kernel<512, true>" if main_kernel == _l.KERNEL_CANDIDATE_MAJOR else "rp::fused_kernel<256>"
+    kernel_name = "rp::cand_kernel<512>" if main_kernel == _l.KERNEL_CANDIDATE_MAJOR else "rp::fused_kernel<256>"
     ncu = ncu_record(kernel_name)
     value = n_total * args.steps / (total_ms * 1e-3)
     fused_mean_ms = float(np.mean(fused_ms))

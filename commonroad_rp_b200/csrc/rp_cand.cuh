@@ -100,8 +100,8 @@ struct StepOut {
 
 // Everything of a step that depends on the LONGITUDINAL polynomial alone: s, s_dot, s_ddot, the reference segment and
 // what is interpolated on it, the projection base point, two reciprocals.  In a grid bundle it is identical for all
-// candidates of one (t, lon) pair -- a whole warp when n_d is a multiple of 32 -- which is what cand_kernel<.., true>
-// exploits (rows computed once per 32 steps by the warp, lane = step, and broadcast from shared memory).
+// candidates of one (t, lon) pair -- a whole warp when n_d is a multiple of 32 -- which is what cand_march
+// exploits (rows computed cooperatively by the warp and read back from shared memory).
 struct LonRow {
     double s, sv, sa;            // sv after the eps clamp
     double y_sv, y_sv2;          // refined reciprocals of the guarded s_dot and its square
@@ -336,11 +336,18 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 
 // ---- one candidate through the whole horizon (the per-lane body of both kernels below) ----------------------
 // acc: this thread's accumulator column (+ (row * 8 + j) * BLOCK), s_vmid: this thread's parked v[mid] slot
-// SHARED_LON: all 32 lanes of the warp are candidates of one (t, lon) pair (grid bundle, n_d a multiple of 32): the
-// longitudinal rows of 32 consecutive steps are computed by the warp at once (lane = step) into `rows`
-// ([field][32] doubles + [32] flag words of this warp's shared memory) and broadcast from there.
-template <int BLOCK, bool SHARED_LON>
-__device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k,
+// The warp evaluates the longitudinal rows cooperatively.  Its 32 lanes hold G distinct longitudinal polynomials
+// ("groups": grid bundle -> the distinct lon samples among 32 consecutive candidates of one t, G = 1 when n_d is a
+// multiple of 32; list form -> one per lane, G = 32).  Every W = 32 / G steps the warp computes the rows of the next
+// W steps of all groups at once -- lane q does (group q / W, step base + q % W) -- into `rows` ([field][32] doubles +
+// [32] flag words of this warp's shared memory); each lane then reads the row of its own group.  The (t, lon)-
+// invariant part of a step therefore costs G / 32 of a per-lane evaluation.
+// ALL 32 lanes of the warp call this function; lanes without a candidate (valid == false) mirror the chunk's last
+// candidate and write nothing.
+// ONE_GROUP: the host guarantees G == 1 for every chunk (grid form, n_d a multiple of 32, aligned shard): the group
+// arithmetic folds away at compile time.
+template <int BLOCK, bool ONE_GROUP>
+__device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k, bool valid,
                                            double* __restrict__ acc, double* __restrict__ s_vmid,
                                            double* __restrict__ rows) {
     const int Np1 = P.Np1;
@@ -367,10 +374,12 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
                ((r8[4 * BLOCK] + r8[5 * BLOCK]) + (r8[6 * BLOCK] + r8[7 * BLOCK]));
     };
 
-    // ---- candidate decode (sampling.py:202-242 enumeration order) ----------------------------
+    // ---- candidate decode (sampling.py:202-242 enumeration order) + the warp's longitudinal groups -------------
+    const int lane = threadIdx.x & 31;
     StepIn I;
-    int tl;
+    int tl, grp, G;
     bool filtered;
+    const double* cs_group0;                             // grid form: coefficients of group 0 (group g: + 6 g)
     if (P.mode == 0) {
         const int per_t = P.n_lon * P.n_d;
         const int it = k / per_t;
@@ -381,21 +390,35 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         I.cd = P.lat_coef + (size_t)(low_vel ? k : it * P.n_d + id) * 6;
         tl = P.traj_len[it];
         filtered = (in.lon_mode == RP_STOPPING) && !(in.x0_lon[0] < P.lon_samples[il]);
+        if (ONE_GROUP) {
+            grp = 0;
+            G = 1;
+            cs_group0 = I.cs;
+        } else {
+            const int il0 = __shfl_sync(0xffffffffu, il, 0);
+            grp = il - il0;
+            G = __shfl_sync(0xffffffffu, grp, 31) + 1;   // lanes are consecutive candidates of one t: il is monotone
+            cs_group0 = P.lon_coef + (size_t)(it * P.n_lon + il0) * 6;
+        }
     } else {
         I.cs = P.lon_coef + (size_t)k * 6;
         I.cd = P.lat_coef + (size_t)k * 6;
         tl = P.traj_len[k];
         filtered = P.skip != nullptr && P.skip[k] != 0;
+        grp = lane;
+        G = 32;
+        cs_group0 = nullptr;
     }
     if (tl > Np1) tl = Np1;
-    if (filtered) {
-        P.info[k] = pack_info(ST_FILTERED, R_NONE, -1);
-        if (P.cost) P.cost[k] = __longlong_as_double(0x7ff8000000000000LL);
-        return;
-    }
+    const int tl_warp = P.mode == 0 ? tl : __reduce_max_sync(0xffffffffu, tl);
+    const int W = ONE_GROUP ? 32 : 32 / G;               // steps per refresh of the rows
+    const int item_g = ONE_GROUP ? 0 : lane / W;         // the (group, step offset) this lane computes
+    const int item_w = ONE_GROUP ? lane : lane - item_g * W;
+    unsigned* const rflags = reinterpret_cast<unsigned*>(rows + kLonRowDoubles * 32);
+    int row_base = 0, row_next = 0;
 
     unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
-    const double cs0 = SHARED_LON ? __ldg(I.cs) : 0.;
+    const double cs0 = low_vel ? __ldg(I.cs) : 0.;
     // values of the current / last polynomial step (the extension reads them after step tl - 1)
     double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
     double cn = 1., sn = 0.;                       // cos / sin of th_gl
@@ -405,34 +428,35 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     for (int i = 0; i < Np1; ++i) {
         double px, py;                             // rear-axle position of this step
         double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
+        if (i == row_next && i < tl_warp) {            // warp-uniform: refresh the rows of steps i .. i + W - 1
+            __syncwarp();
+            if (item_g < G) {
+                const int step = i + item_w;
+                // grid form: every group has the chunk's traj_len; list form: W == 1, the item is the lane's own candidate
+                if (step < tl) {
+                    const double* cs_item = P.mode == 0 ? cs_group0 + (size_t)item_g * 6 : I.cs;
+                    const LonRow w = lon_part<false>(P, R, cs_item, step);
+                    double* c = rows + lane;
+                    c[0] = w.s; c[32] = w.sv; c[64] = w.sa; c[96] = w.y_sv; c[128] = w.y_sv2; c[160] = w.th_ref;
+                    c[192] = w.k_r; c[224] = w.k_r_d; c[256] = w.bx; c[288] = w.by; c[320] = w.nx; c[352] = w.ny;
+                    c[384] = w.c_ref; c[416] = w.s_ref;
+                    rflags[lane] = w.flags;
+                }
+            }
+            __syncwarp();
+            row_base = i;
+            row_next = i + W;
+        }
         if (i < tl) {
             I.i = i; I.th_prev = th_gl; I.kap_prev = kappa;
-            StepOut o;
-            if (SHARED_LON) {
-                const int lane = threadIdx.x & 31;
-                unsigned* rflags = reinterpret_cast<unsigned*>(rows + kLonRowDoubles * 32);
-                if ((i & 31) == 0) {
-                    __syncwarp();
-                    if (i + lane < tl) {
-                        const LonRow w = lon_part<false>(P, R, I.cs, i + lane);
-                        double* c = rows + lane;
-                        c[0] = w.s; c[32] = w.sv; c[64] = w.sa; c[96] = w.y_sv; c[128] = w.y_sv2; c[160] = w.th_ref;
-                        c[192] = w.k_r; c[224] = w.k_r_d; c[256] = w.bx; c[288] = w.by; c[320] = w.nx; c[352] = w.ny;
-                        c[384] = w.c_ref; c[416] = w.s_ref;
-                        rflags[lane] = w.flags;
-                    }
-                    __syncwarp();
-                }
-                const double* c = rows + (i & 31);
-                LonRow L;
-                L.s = c[0]; L.sv = c[32]; L.sa = c[64]; L.y_sv = c[96]; L.y_sv2 = c[128]; L.th_ref = c[160];
-                L.k_r = c[192]; L.k_r_d = c[224]; L.bx = c[256]; L.by = c[288]; L.nx = c[320]; L.ny = c[352];
-                L.c_ref = c[384]; L.s_ref = c[416];
-                L.flags = rflags[i & 31];
-                o = lat_part<false>(P, R, Y, L, I.cd, cs0, th_gl, kappa, i);
-            } else {
-                o = poly_step<false>(P, R, Y, I);
-            }
+            const int item = grp * W + (i - row_base);
+            const double* c = rows + item;
+            LonRow L;
+            L.s = c[0]; L.sv = c[32]; L.sa = c[64]; L.y_sv = c[96]; L.y_sv2 = c[128]; L.th_ref = c[160];
+            L.k_r = c[192]; L.k_r_d = c[224]; L.bx = c[256]; L.by = c[288]; L.nx = c[320]; L.ny = c[352];
+            L.c_ref = c[384]; L.s_ref = c[416];
+            L.flags = rflags[item];
+            StepOut o = lat_part<false>(P, R, Y, L, I.cd, cs0, th_gl, kappa, i);
             if (o.reject & 0x80000000u) o = poly_step_exact(P, R, Y, I);
             pre |= o.pre;
             if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
@@ -503,7 +527,10 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     // ---- per-candidate verdict --------------------------------------------------------------------
     int status, reason = R_NONE, step = -1;
     double cost = __longlong_as_double(0x7ff8000000000000LL);   // NaN
-    if (pre != 0u) {
+    if (!valid) return;                                  // mirror lane: it only helped with the rows
+    if (filtered) {
+        status = ST_FILTERED;                            // filter_goals_behind (trajectories.py:545-550)
+    } else if (pre != 0u) {
         status = ST_KINEMATIC;
         reason = (pre & 1u) ? R_ACCELERATION : R_VELOCITY;
     } else if (bad != NONE) {
@@ -548,19 +575,21 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     if (P.cost) P.cost[k] = cost;
 }
 
-// locate chunk g of 32 candidates in the segment table (sorted by traj_len, longest first); -1: past the end
-__device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs, int n_segs, int g, int lane) {
+// locate chunk g of 32 candidates in the segment table (sorted by traj_len, longest first): the lane's candidate,
+// clamped to the chunk's last one for lanes past the end of the segment (valid = false: mirror lanes)
+__device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs, int n_segs, int g, int lane, bool& valid) {
     int lo = 0, hi = n_segs - 1;
     while (lo < hi) {
         const int m = (lo + hi + 1) >> 1;
         if (segs[m].g_begin <= g) lo = m; else hi = m - 1;
     }
     const int k = segs[lo].k_begin + (g - segs[lo].g_begin) * 32 + lane;
-    return k < segs[lo].k_end ? k : -1;
+    valid = k < segs[lo].k_end;
+    return valid ? k : segs[lo].k_end - 1;
 }
 
 // ---- one bundle: persistent grid, warps draw chunks of 32 candidates from a counter -----------------------------
-template <int BLOCK, bool SHARED_LON>
+template <int BLOCK, bool ONE_GROUP>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
@@ -588,7 +617,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
     LimitRcp* const s_Y = reinterpret_cast<LimitRcp*>(sp);
     sp += 4;
     double* const s_rows = sp + (size_t)(tid >> 5) * (kLonRowDoubles * 32 + 16);   // this warp's longitudinal rows
-    if (SHARED_LON) sp += (size_t)(BLOCK / 32) * (kLonRowDoubles * 32 + 16);
+    sp += (size_t)(BLOCK / 32) * (kLonRowDoubles * 32 + 16);
     Segment* const s_segs = reinterpret_cast<Segment*>(sp);
     for (int q = tid; q < P.n_segs; q += BLOCK) s_segs[q] = P.segs[q];
     if (tid == 0) {
@@ -603,8 +632,9 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         if (lane == 0) g = atomicAdd(P.work_counter, 1);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= P.n_groups) break;
-        const int k = chunk_candidate(s_segs, P.n_segs, g, lane);
-        if (k >= 0) cand_march<BLOCK, SHARED_LON>(P, R, *s_Y, k, acc, s_vmid, s_rows);
+        bool valid;
+        const int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
+        cand_march<BLOCK, ONE_GROUP>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 
@@ -631,6 +661,8 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
     double* const s_vmid = sp + tid;
     sp += BLOCK;
     LimitRcp* const s_Y = reinterpret_cast<LimitRcp*>(sp) + warp;
+    sp += (size_t)(BLOCK / 32) * 3;
+    double* const s_rows = sp + (size_t)warp * (kLonRowDoubles * 32 + 16);
     const int total = B.chunk_prefix[B.n_scenarios];
     int sc_cached = -1;
     for (;;) {
@@ -654,8 +686,9 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
             __syncwarp();
             sc_cached = lo;
         }
-        const int k = chunk_candidate(P.segs, P.n_segs, g - B.chunk_prefix[lo], lane);
-        if (k >= 0) cand_march<BLOCK, false>(P, P.ref, *s_Y, k, acc, s_vmid, nullptr);
+        bool valid;
+        const int k = chunk_candidate(P.segs, P.n_segs, g - B.chunk_prefix[lo], lane, valid);
+        cand_march<BLOCK, false>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 

@@ -130,7 +130,7 @@ struct rp_ctx {
     DevBuf d_segs, d_segs_index, d_argmin, d_best;
     PinBuf h_segs, h_segs_index;
     Geometry main_geom{}, index_geom{}, cand_geom{};
-    bool main_is_cand = false, main_shared_lon = false;          // geometry in main_geom/d_segs belongs to the candidate-major kernel
+    bool main_is_cand = false, main_one_group = false;          // geometry in main_geom/d_segs belongs to the candidate-major kernel
     int kernel_policy = RP_KERNEL_AUTO;
     DevBuf d_work, d_dyn_rows;
     int index_geom_np1 = -1, index_geom_count = -1;
@@ -423,14 +423,7 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
 
 // Launch geometry of the candidate-major kernel (rp_cand.cuh): segments sorted by traj_len, longest first,
 // cut into chunks of 32 candidates that the warps of a persistent grid draw from a counter.
-// the warp-cooperative longitudinal rows need every chunk of 32 to be one (t, lon) pair: grid form, n_d a multiple of
-// 32, shard boundaries on multiples of 32
-bool cand_shared_lon(const rp_ctx* ctx, int first, int count) {
-    static const int env = std::getenv("RP_CAND_SHARED_LON") ? std::atoi(std::getenv("RP_CAND_SHARED_LON")) : 1;
-    return env && ctx->mode == 0 && ctx->n_d > 0 && ctx->n_d % 32 == 0 && first % 32 == 0 && count % 32 == 0;
-}
-
-int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, int n_acc_rows, bool shared_lon) {
+int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, int n_acc_rows) {
     static const int env_stage_ref = std::getenv("RP_CAND_STAGE_REF") ? std::atoi(std::getenv("RP_CAND_STAGE_REF")) : 0;
     std::stable_sort(segs.begin(), segs.end(), [](const rp::Segment& a, const rp::Segment& b) { return a.tl > b.tl; });
     G.big = false;
@@ -449,7 +442,7 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     
     const size_t acc_bytes = (size_t)(n_acc_rows * 8 + 1) * G.threads * sizeof(double);    // + v_mid
     const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 128 +
-                         (shared_lon ? (size_t)(G.threads / 32) * (rp::kLonRowDoubles * 32 + 16) * sizeof(double) : 0);
+                         (size_t)(G.threads / 32) * (rp::kLonRowDoubles * 32 + 16) * sizeof(double);     // the warps' longitudinal rows
     G.stage_dyn = 0;                                   // dynamic-obstacle rows are read through L1 (dyn_rows_kernel)
     G.smem = acc_bytes + fixed;
     G.stage_ref = (env_stage_ref && G.smem + ref_bytes <= budget / 3) ? 1 : 0;
@@ -463,8 +456,7 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
         granted = (int)G.smem;
     }
     int occ = 0;
-    if (shared_lon) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::cand_kernel<RP_CAND_THREADS, true>, G.threads, G.smem));
-    else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::cand_kernel<RP_CAND_THREADS, false>, G.threads, G.smem));
+    RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::cand_kernel<RP_CAND_THREADS, false>, G.threads, G.smem));
     if (occ < 1) return fail(RP_ERR_CUDA, "candidate-major kernel does not fit on an SM");
     const int warps_per_block = G.threads / 32;
     G.grid = std::max(1, std::min((G.n_groups + warps_per_block - 1) / warps_per_block, occ * ctx->num_sms));
@@ -563,8 +555,9 @@ int prepare_main_geometry(rp_ctx* ctx, int first, int count) {
     ctx->main_is_cand = use_cand_kernel(ctx, count);
     if (ctx->main_is_cand) {
         // (list form: one segment in list order; traj_len varies per candidate, lanes diverge on i < tl only)
-        ctx->main_shared_lon = cand_shared_lon(ctx, first, count);
-        if (int rc = plan_cand_geometry(ctx, Np1, segs, ctx->main_geom, cand_acc_rows(ctx->in), ctx->main_shared_lon)) return rc;
+        // one longitudinal group per chunk of 32: grid form, n_d a multiple of 32, shard boundaries on multiples of 32
+        ctx->main_one_group = ctx->mode == 0 && ctx->n_d > 0 && ctx->n_d % 32 == 0 && first % 32 == 0 && count % 32 == 0;
+        if (int rc = plan_cand_geometry(ctx, Np1, segs, ctx->main_geom, cand_acc_rows(ctx->in))) return rc;
     } else if (int rc = plan_geometry(ctx, Np1, segs, ctx->main_geom)) return rc;
     const size_t bytes = segs.size() * sizeof(rp::Segment);
     if (int rc = ctx->h_segs.ensure(bytes)) return rc;
@@ -910,7 +903,7 @@ static int launch_plan(rp_ctx* ctx) {
                 P.dyn_rows = ctx->d_dyn_rows.as<float4>();
             }
             const Geometry& G = ctx->main_geom;
-            if (ctx->main_shared_lon) rp::cand_kernel<RP_CAND_THREADS, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+            if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
             else rp::cand_kernel<RP_CAND_THREADS, false><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
             RP_CUDA(cudaGetLastError());
         } else if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
@@ -1508,7 +1501,8 @@ int rp_batch_launch(rp_batch* b) {
         T.n_acc_rows = acc_rows;
         T.work_counter = b->d_work.as<int>();
         const int threads = RP_CAND_THREADS;
-        const size_t smem = (size_t)(acc_rows * 8 + 1) * threads * sizeof(double) + (size_t)(threads / 32) * sizeof(rp::LimitRcp) + 64;
+        const size_t smem = (size_t)(acc_rows * 8 + 1) * threads * sizeof(double) + (size_t)(threads / 32) * sizeof(rp::LimitRcp) +
+                            (size_t)(threads / 32) * (rp::kLonRowDoubles * 32 + 16) * sizeof(double) + 64;
         if ((int)smem > b->smem_granted) {
             RP_CUDA(cudaFuncSetAttribute(rp::cand_batch_kernel<RP_CAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             b->smem_granted = (int)smem;
