@@ -129,3 +129,33 @@ def test_warp_shared_longitudinal_rows(low_vel):
     assert np.array_equal(g["step"], g2["step"])
     assert np.array_equal(g["cost"].view(np.int64), g2["cost"].view(np.int64))
     eng.close()
+
+
+@pytest.mark.parametrize("mode", ["velocity_keeping", "stopping"])
+def test_list_form_candidate_major(mode):
+    """rp_plan_list through the candidate-major kernel (every lane its own longitudinal polynomial and traj_len,
+    filter_goals_behind as skip flags): identical, candidate by candidate, to the grid form of the same bundle"""
+    from commonroad_rp_b200 import _lib
+    kw = dict(seed=6, level=2, N=30, lon_mode="stopping", s_dot0=8.0, desired_s=24.0) if mode == "stopping" \
+        else dict(seed=2, level=2, N=40, s_dot0=12.0)
+    prob = _bundle(**kw)
+    eng = H.engine_for(prob)
+    g = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_CANDIDATE_MAJOR)
+    n_t, n_lon, n_d = len(prob["t"]), len(prob["lon"]), len(prob["d"])
+    cl = np.repeat(g["coeffs_lon"].reshape(n_t, n_lon, 1, 6), n_d, axis=2).reshape(-1, 6) if g["coeffs_lon"].shape[0] != g["n"] \
+        else g["coeffs_lon"]
+    ct = g["coeffs_lat"]
+    tl = np.repeat([_lib.traj_len_of(t, prob["dt"]) for t in prob["t"]], n_lon * n_d).astype(np.int32)
+    skip = (g["status"] == 3).astype(np.uint8)
+    # shuffle the list so that lanes of a warp get different polynomials AND different traj_len
+    perm = np.random.default_rng(1).permutation(g["n"])
+    eng.set_kernel_policy(_lib.KERNEL_CANDIDATE_MAJOR)
+    res = eng.plan_list(H.inputs_for(prob), cl[perm], ct[perm], tl[perm], skip[perm])
+    cost, status, reason, step = eng.fetch_candidates()
+    assert np.array_equal(status, g["status"][perm]) and np.array_equal(reason, g["reason"][perm])
+    assert np.array_equal(step, g["step"][perm])
+    assert np.array_equal(cost.view(np.int64), g["cost"][perm].view(np.int64))
+    assert res.n_infeasible_kinematics == g["n_infeasible_kinematics"]
+    if g["winner"] >= 0:
+        assert res.winner_cost == g["winner_cost"]
+    eng.close()
