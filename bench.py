@@ -34,6 +34,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_CAND_STEP = 200.0      # SURVEY.md section 8d "ALGORITHMIC work per unit"
+SELECT_BYTES_PER_CAND = 13 * 8 + 16          # select-only: 13 doubles in, (cost f64, info i32, padding) out per candidate
 STATE_BYTES_PER_CAND_STEP = 112.0
 METRIC = "candidate_trajectories_per_sec"
 UNIT = "candidates/s"
@@ -598,6 +599,13 @@ def main():
                                     "algorithmic work = 200 flop per candidate-timestep (SURVEY 8d)",
                      "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_kind},
     }
+    # the same kernel against the HBM roofline (the contract's other bound): select-only mode moves 13 doubles in and
+    # 16 bytes out per candidate -- two orders of magnitude below the copy bandwidth, the path is FP64-bound
+    sel_bytes = count * SELECT_BYTES_PER_CAND
+    line["roofline_hbm"] = {"bound": "hbm", "achieved": sel_bytes / (fused_mean_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
+                            "unit": "GB/s", "frac": sel_bytes / (fused_mean_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs"),
+                            "traffic": ncu.get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": sel_bytes,
+                            "peak_source": peak_kind + " (MEASURED_PEAKS.json)"}
     if lazy_ms is not None:
         line["lazy_collision"] = {"value": n_total / (lazy_ms * 1e-3), "unit": UNIT, "ms_per_step": lazy_ms,
                                   "note": "check_collision=2: same winner / counters, costlier candidates not visited"}
