@@ -557,8 +557,15 @@ int prepare_main_geometry(rp_ctx* ctx, int first, int count) {
         // (list form: one segment in list order; traj_len varies per candidate, lanes diverge on i < tl only)
         // one longitudinal group per chunk of 32: grid form, n_d a multiple of 32, shard boundaries on multiples of 32
         ctx->main_one_group = ctx->mode == 0 && ctx->n_d > 0 && ctx->n_d % 32 == 0 && first % 32 == 0 && count % 32 == 0;
-        if (int rc = plan_cand_geometry(ctx, Np1, segs, ctx->main_geom, cand_acc_rows(ctx->in))) return rc;
-    } else if (int rc = plan_geometry(ctx, Np1, segs, ctx->main_geom)) return rc;
+        std::vector<rp::Segment> sorted = segs;
+        if (plan_cand_geometry(ctx, Np1, sorted, ctx->main_geom, cand_acc_rows(ctx->in)) == RP_OK) {
+            segs.swap(sorted);
+        } else {
+            ctx->main_is_cand = false;          // e.g. a segment table too long for its shared memory: the other schedule
+        }
+    }
+    if (!ctx->main_is_cand)
+        if (int rc = plan_geometry(ctx, Np1, segs, ctx->main_geom)) return rc;
     const size_t bytes = segs.size() * sizeof(rp::Segment);
     if (int rc = ctx->h_segs.ensure(bytes)) return rc;
     if (int rc = ctx->d_segs.ensure(bytes)) return rc;

@@ -545,19 +545,25 @@ class ReactivePlanner(object):
         """Optimal sample -> (Cartesian Trajectory, curvilinear Trajectory, lon list, lat list)
         (reference :514-568)."""
         ca, cu = trajectory.cartesian, trajectory.curvilinear
-        cart_list, cl_list, lon_list, lat_list = [], [], [], []
         factor = self.config.planning.factor
+        n = len(ca.x)
+        theta = ca.theta
         steering = np.arctan2(self.vehicle_params.wheelbase * ca.kappa, 1.0)
-        for i in range(len(ca.x)):
-            ts = self.x_0.time_step + factor * i
-            yaw_rate = (ca.theta[i] - ca.theta[i - 1]) / self.dt if i > 0 else self.x_0.yaw_rate
-            cart_list.append(ReactivePlannerState(time_step=ts, position=np.array([ca.x[i], ca.y[i]]),
-                                                  orientation=ca.theta[i], velocity=ca.v[i], acceleration=ca.a[i],
-                                                  yaw_rate=yaw_rate, steering_angle=steering[i]))
-            cl_list.append(CustomState(time_step=ts, position=np.array([cu.s[i], cu.d[i]]), velocity=ca.v[i],
-                                       acceleration=ca.a[i], orientation=ca.theta[i], yaw_rate=ca.kappa[i]))
-            lon_list.append([cu.s[i], cu.s_dot[i], cu.s_ddot[i]])
-            lat_list.append([cu.d[i], cu.d_dot[i], cu.d_ddot[i]])
+        # element-wise the same arithmetic as the reference's per-state loop (:520-556), built once as arrays
+        yaw_rate = np.empty(n)
+        yaw_rate[0] = self.x_0.yaw_rate
+        yaw_rate[1:] = (theta[1:] - theta[:-1]) / self.dt
+        pos_cart = np.stack([ca.x, ca.y], axis=1)
+        pos_curv = np.stack([cu.s, cu.d], axis=1)
+        t0 = self.x_0.time_step
+        cart_list = [ReactivePlannerState(time_step=t0 + factor * i, position=pos_cart[i], orientation=th, velocity=vel,
+                                          acceleration=acc, yaw_rate=yr, steering_angle=st)
+                     for i, (th, vel, acc, yr, st) in enumerate(zip(theta, ca.v, ca.a, yaw_rate, steering))]
+        cl_list = [CustomState(time_step=t0 + factor * i, position=pos_curv[i], velocity=vel, acceleration=acc,
+                               orientation=th, yaw_rate=kap)
+                   for i, (vel, acc, th, kap) in enumerate(zip(ca.v, ca.a, theta, ca.kappa))]
+        lon_list = np.stack([cu.s, cu.s_dot, cu.s_ddot], axis=1).tolist()
+        lat_list = np.stack([cu.d, cu.d_dot, cu.d_ddot], axis=1).tolist()
         cart_traj = shift_orientation(Trajectory(self.x_0.time_step, cart_list),
                                       interval_start=self.x_0.orientation - np.pi,
                                       interval_end=self.x_0.orientation + np.pi)
