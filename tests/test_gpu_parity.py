@@ -159,3 +159,31 @@ def test_list_form_candidate_major(mode):
     if g["winner"] >= 0:
         assert res.winner_cost == g["winner_cost"]
     eng.close()
+
+
+@pytest.mark.parametrize("kernel", ["step_parallel", "candidate_major"])
+def test_edge_cases_no_obstacles_no_check_empty_bundle(kernel):
+    """no obstacle tables at all, collision check switched off, and an empty bundle -- through both schedules"""
+    from commonroad_rp_b200 import _lib
+    pol = _lib.KERNEL_STEP_PARALLEL if kernel == "step_parallel" else _lib.KERNEL_CANDIDATE_MAJOR
+    prob = _bundle(seed=0, level=2, N=20)
+    empty = {"static_boxes": np.zeros((0, 5)), "dyn_t0": [], "dyn_states": [], "dyn_lw": np.zeros((0, 2)),
+             "boundary_boxes": np.zeros((0, 5)), "boundary_tris": np.zeros((0, 6))}
+    free = dict(prob, obstacles=empty)
+    o = O.plan_grid(free, want_states=True, full_collision=True)
+    eng = H.engine_for(free)
+    g = H.run_engine_grid(eng, free, want_all_states=False, kernel=pol)
+    H.assert_parity(o, g, free, tag="no obstacles " + kernel)
+    assert g["n_collision_total"] == 0
+    eng.close()
+    # collision check off on a scenario WITH obstacles: same verdicts as the obstacle-free scenario
+    eng = H.engine_for(prob)
+    eng.set_kernel_policy(pol)
+    res = eng.plan_grid(H.inputs_for(prob, check_collision=0), prob["t"], prob["lon"], prob["d"])
+    cost, status, reason, step = eng.fetch_candidates()
+    assert np.array_equal(status, g["status"]) and np.array_equal(cost.view(np.int64), g["cost"].view(np.int64))
+    assert res.winner == g["winner"]
+    # empty bundle
+    res = eng.plan_grid(H.inputs_for(prob), [], prob["lon"], prob["d"])
+    assert res.winner == -1 and res.n_candidates == 0 and res.n_feasible == 0
+    eng.close()
