@@ -411,6 +411,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-states", action="store_true", help="also time the full-state (HBM-heavy) variant")
+    ap.add_argument("--scenarios", type=int, default=64,
+                    help="independent scenarios PER RANK of the scenario-batch leg (BASELINE configs[4]: 512 per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -558,7 +560,7 @@ def main():
         lazy_res = eng.grid_result()
         assert lazy_res.winner == res.winner and lazy_res.n_infeasible_collision == res.n_infeasible_collision
 
-    scen = scenario_batch_rate(local_rank, stream.cuda_stream, rank=rank, world=world)
+    scen = scenario_batch_rate(local_rank, stream.cuda_stream, n_scenarios=args.scenarios, rank=rank, world=world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
