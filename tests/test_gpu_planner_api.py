@@ -363,6 +363,8 @@ def test_scenario_batch_equals_individual_plans():
             c0, st0, r0, sp0 = arrays[k]
             assert np.array_equal(status, st0) and np.array_equal(reason, r0) and np.array_equal(step, sp0), k
             assert np.array_equal(cost.view(np.int64), c0.view(np.int64)), k          # identical bits
+    packed = _lib.Batch.pack(cycle)           # all scenarios' inputs in one call
+    assert [r.winner for r in batch.plan(packed)] == [s[0] for s in single]
     one = batch.plan_one_by_one(cycle)
     assert [r.winner for r in one] == [s[0] for s in single]
     assert len({g[0] for g in got}) > 1       # the scenarios really differ
