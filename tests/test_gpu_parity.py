@@ -187,3 +187,40 @@ def test_edge_cases_no_obstacles_no_check_empty_bundle(kernel):
     res = eng.plan_grid(H.inputs_for(prob), [], prob["lon"], prob["d"])
     assert res.winner == -1 and res.n_candidates == 0 and res.n_feasible == 0
     eng.close()
+
+
+def _shifted(scn, ox, oy):
+    out = dict(scn)
+    out["ref_path"] = np.asarray(scn["ref_path"], dtype=np.float64) + [ox, oy]
+    sb = np.array(scn["static_boxes"], dtype=np.float64).reshape(-1, 5)
+    sb[:, 0] += ox; sb[:, 1] += oy
+    out["static_boxes"] = sb
+    bb = np.array(scn["boundary_boxes"], dtype=np.float64).reshape(-1, 5)
+    bb[:, 0] += ox; bb[:, 1] += oy
+    out["boundary_boxes"] = bb
+    out["dyn_states"] = [np.asarray(s, dtype=np.float64) + [ox, oy, 0.0] for s in scn["dyn_states"]]
+    return out
+
+
+@pytest.mark.parametrize("kernel", ["step_parallel", "candidate_major"])
+def test_utm_sized_coordinates(kernel):
+    """the single-precision collision pre-rejects work on positions relative to the obstacle table's own origin: a
+    scenario moved to UTM-sized coordinates (4e5, 5.2e6) gives the verdicts of the oracle evaluated there"""
+    from commonroad_rp_b200 import _lib
+    scn = _shifted(synthetic.make_scenario(seed=2), 4.0e5, 5.2e6)
+    dt, N, s_dot0, d0 = 0.1, 30, 12.0, 0.3
+    lo = max(0.0, s_dot0 - 0.125 * N * dt * 11.5)
+    t, lon, dset = H.level_sets(2, 0.4, N * dt, dt, lo, max(lo + 5.0, s_dot0 + 2))
+    d = [float(x) for x in dset.union({d0})]
+    tables = O.reference_tables(scn["ref_path"])
+    s0 = float(tables[0]["ref_pos"][10])
+    prob = H.make_problem(scn, t, lon, d, [s0, s_dot0, 0.0], [d0, 0.0, 0.0], N=N, dt=dt, desired_speed=s_dot0, tables=tables)
+    o = O.plan_grid(prob, want_states=True, full_collision=True)
+    assert (o["status"] == O.ST_COLLISION).any()
+    eng = H.engine_for(prob)
+    g = H.run_engine_grid(eng, prob, want_all_states=False,
+                          kernel=_lib.KERNEL_STEP_PARALLEL if kernel == "step_parallel" else _lib.KERNEL_CANDIDATE_MAJOR)
+    # flags, reasons, steps, winner and counters exact; costs 1e-9.  Positions of magnitude 5e6 carry ~1e-9 absolute
+    # rounding, so the states are compared with that absolute floor (helpers.rel_err scales by max(|a|, |b|, 1)).
+    H.assert_parity(o, g, prob, tag="utm " + kernel)
+    eng.close()
