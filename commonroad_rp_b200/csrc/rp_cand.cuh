@@ -1,23 +1,25 @@
-// rp_cand.cuh -- the candidate-major form of the fused path (a4-a13 of SURVEY.md section 8a) for LARGE bundles
-// in select-only mode: one thread per candidate, marching through the horizon sequentially.
+// rp_cand.cuh -- the candidate-major form of the fused path (a4-a13 of SURVEY.md section 8a) for LARGE bundles and
+// batches of scenarios in select-only mode: one thread per candidate, marching through the horizon sequentially.
 // (reactive_planner.py:715-1063, cost_function.py:51-92, trajectories.py:168-332)
 //
 // Why a second mapping.  fused_kernel (rp_fused.cuh) gives every (candidate, step) pair a thread; that is what a
 // 120-3000 candidate replanning bundle needs to fill 148 SMs, but it pays ~12 block barriers per group, exchanges
 // every sequential-in-time quantity (theta[i-1], kappa[i-1], standstill carry, cumsum, numpy's summation order)
 // through shared-memory rows and re-derives indices per element: ~2200 warp instructions per candidate-timestep of
-// which 27 % are FP64.  A bundle of >= ~30 000 candidates fills the machine with candidates alone, and then the
-// reference's own loop structure is the cheapest one: everything sequential-in-time lives in registers, the
-// reference-segment lookup advances incrementally (s is monotone up to the eps clamp), there are no barriers, and
-// lanes of a warp (adjacent candidates of one sampled t) share traj_len, the dynamic obstacles of the step
-// (shared-memory broadcast) and the longitudinal polynomial.
+// which 27 % are FP64.  A bundle of >= ~25 000 candidates fills the machine with candidates alone, and then the
+// reference's own loop structure is the cheapest one: everything sequential-in-time lives in registers, there are
+// no barriers, and the lanes of a warp (adjacent candidates of one sampled t) share traj_len, the dynamic
+// obstacles of the step (one broadcast load per obstacle) and -- computed ONCE per warp, see cand_march -- everything
+// that depends on the longitudinal polynomial alone.  ~720 warp instructions per 32 candidate-timesteps.
 //
-// The arithmetic is expression-for-expression the one of fused_kernel (same rp_device.cuh functions), so both
-// kernels give identical bits; only the schedule differs.  Not handled here (the host routes these to fused_kernel):
-// state output, draw mode, index mode, N + 1 > 128 (numpy's recursive pairwise split).
+// The arithmetic is expression-for-expression the one of fused_kernel (same rp_device.cuh functions; divisions are
+// IEEE quotients in both), so both kernels give identical bits; only the schedule differs.  Not handled here (the
+// host routes these to fused_kernel): state output, draw mode, index mode, N + 1 > 128 (numpy's recursive pairwise
+// split), and bundles too small to fill the machine (one march of a warp is ~0.18 ms whatever the load).
 //
 // Work distribution: the host sorts the segments (one per sampled t) by traj_len, longest first, and cuts them
-// into chunks of 32 candidates; warps of a persistent grid draw chunks from a global counter.
+// into chunks of 32 candidates; warps of a persistent grid (one 512-thread block per SM) draw chunks from a global
+// counter.  cand_batch_kernel does the same over the chunks of MANY scenarios (rp_batch_*).
 #pragma once
 #include "rp_fused.cuh"
 
@@ -30,14 +32,11 @@ namespace rp {
 #define RP_CAND_MIN_BLOCKS 1
 #endif
 
-// cost accumulator rows kept in shared memory: acc[(row * 8 + j) * BLOCK + tid], numpy's 8 partial sums per np.sum
-constexpr int kAccRowsMax = 5;
-
 // Dynamic obstacles of every time step as single-precision bounding circles, rows [step][obstacle] of
 // (cx, cy, squared reach, -) relative to the obstacle-table origin, written once per launch by dyn_rows_kernel and
 // read through L1: all lanes of a warp are at the same step, so a row is one broadcast load, and one copy serves
-// every block of the SM (shared memory is left to the cost accumulators).  The pre-reject is conservative (reach inflated by the fp32 rounding bound,
-// build_obstacle_tables) and branch-free over the obstacles -- the circle tests of one step are independent
+// every block of the SM (shared memory is left to the cost accumulators).  The pre-reject is conservative (reach
+// inflated by the fp32 rounding bound, build_obstacle_tables) and branch-free over the obstacles -- the circle tests of one step are independent
 // instructions, not a serial chain; survivors go to the exact fp64 SAT, which alone decides a hit.
 // An obstacle absent at a step is parked at 1e30 with zero reach (inf <= 0 is false).
 __device__ __forceinline__ bool dyn_collides_f32(const ObstacleTables& O, const float4* __restrict__ row, int tidx,
