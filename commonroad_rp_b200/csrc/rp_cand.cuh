@@ -39,17 +39,29 @@ namespace rp {
 // inflated by the fp32 rounding bound, build_obstacle_tables) and branch-free over the obstacles -- the circle tests of one step are independent
 // instructions, not a serial chain; survivors go to the exact fp64 SAT, which alone decides a hit.
 // An obstacle absent at a step is parked at 1e30 with zero reach (inf <= 0 is false).
+// `relevant`: bit o clear = obstacle o (< 32) was already excluded for this step by the row-level line test (lon_part).
 __device__ __forceinline__ bool dyn_collides_f32(const ObstacleTables& O, const float4* __restrict__ row, int tidx,
-                                                 double cx, double cy, double ca, double sa, double ahl, double ahw) {
+                                                 double cx, double cy, double ca, double sa, double ahl, double ahw,
+                                                 unsigned relevant) {
     const float ex = (float)(cx - O.org_x), ey = (float)(cy - O.org_y);
     for (int base = 0; base < O.n_dyn; base += 32) {
         const int cnt = min(32, O.n_dyn - base);
         unsigned mask = 0u;
+        if (base == 0 && relevant != 0xffffffffu) {
+            for (unsigned todo = relevant; todo;) {             // warp-uniform: the lanes share the row
+                const int o = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const float4 r = row[o];
+                const float dx = r.x - ex, dy = r.y - ey;
+                if (dx * dx + dy * dy <= r.z) mask |= 1u << o;
+            }
+        } else {
 #pragma unroll 8
-        for (int o = 0; o < cnt; ++o) {
-            const float4 r = row[base + o];
-            const float dx = r.x - ex, dy = r.y - ey;
-            if (dx * dx + dy * dy <= r.z) mask |= 1u << o;
+            for (int o = 0; o < cnt; ++o) {
+                const float4 r = row[base + o];
+                const float dx = r.x - ex, dy = r.y - ey;
+                if (dx * dx + dy * dy <= r.z) mask |= 1u << o;
+            }
         }
         while (mask) {
             const int o = base + __ffs(mask) - 1;
@@ -108,9 +120,11 @@ struct LonRow {
     double c_ref, s_ref;         // cos / sin of th_ref
     double bx, by, nx, ny;       // frame base point and interpolated pseudo-normal: (x, y) = b + d * n
     unsigned flags;
+    unsigned dynmask;            // dynamic obstacles of this step that can reach ANY pose on the lateral line b + d * n
 };
 enum : unsigned { LR_PRE = 3u, LR_MOVING = 4u, LR_OK_S = 8u, LR_REJECT = 16u };
 constexpr int kLonRowDoubles = 14;
+constexpr int kWarpRowDoubles = kLonRowDoubles * 32 + 32;     // + [32] flag words + [32] dynamic-obstacle masks
 
 template <bool EXACT>
 __device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables& R, const double* __restrict__ cs_ptr, int i) {
@@ -180,6 +194,25 @@ __device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables&
     }
     o.s = s; o.sv = sv; o.sa = sa; o.th_ref = th_ref;
     sincos(th_ref, &o.s_ref, &o.c_ref);
+    // Dynamic obstacles that matter at this step for ANY candidate sharing this longitudinal motion: the rear axle of
+    // every such candidate lies on the line b + d * n, its box centre within wb_rear of that, so an obstacle whose
+    // centre is farther than (reach + wb_rear + margin) from the LINE cannot touch any of them.  Conservative, single
+    // precision (row.w carries that radius, dyn_rows_kernel); the lanes test only the surviving obstacles.
+    o.dynmask = 0xffffffffu;
+    if (P.dyn_rows != nullptr && P.obs.n_dyn <= 32) {
+        const ObstacleTables& O = P.obs;
+        const float4* row = P.dyn_rows + (size_t)i * O.n_dyn;
+        const float fbx = (float)(o.bx - O.org_x), fby = (float)(o.by - O.org_y), fnx = (float)o.nx, fny = (float)o.ny;
+        const float n2 = (fnx * fnx + fny * fny) * 1.0001f;
+        unsigned m = 0u;
+        for (int q = 0; q < O.n_dyn; ++q) {
+            const float4 r = row[q];
+            const float dx = r.x - fbx, dy = r.y - fby;
+            const float cr = dx * fny - dy * fnx;
+            if (cr * cr <= r.w * r.w * n2) m |= 1u << q;
+        }
+        o.dynmask = m;
+    }
     o.flags = flags | ((D.reject & 0x80000000u) ? LR_REJECT : 0u);
     return o;
 }
@@ -318,7 +351,8 @@ __device__ __noinline__ StepOut poly_step_exact(const PlanParams& P, const RefTa
 }
 
 // rows [step][obstacle] for the launch's time window x0.time_step + step * factor (reactive_planner.py:1040)
-__global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, int Np1, float r_ego_f_up, float4* __restrict__ out) {
+__global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, int Np1, float r_ego_f_up, float wb_rear_f_up,
+                                float4* __restrict__ out) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Np1 * O.n_dyn) return;
     const int step = q / O.n_dyn, o = q - step * O.n_dyn;
@@ -328,7 +362,9 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
     if (present) {
         const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + kk) * kBoxStride;
         const float reach = (r_ego_f_up + (float)b[6]) * 1.000001f + O.dyn_margin;   // >= r_ego + r_obs + margin
-        r = make_float4((float)(b[0] - O.org_x), (float)(b[1] - O.org_y), reach * reach * 1.00001f, 0.0f);
+        // .w: radius of the row-level test against the lateral LINE of the rear-axle positions (lon_part)
+        r = make_float4((float)(b[0] - O.org_x), (float)(b[1] - O.org_y), reach * reach * 1.00001f,
+                        (reach + wb_rear_f_up) * 1.0001f + 1.0e-3f);
     }
     out[q] = r;
 }
@@ -426,6 +462,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
 
     for (int i = 0; i < Np1; ++i) {
         double px, py;                             // rear-axle position of this step
+        unsigned heavy_dynmask = 0xffffffffu;      // polynomial steps: the obstacles that can reach this step's lateral line
         double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
         if (i == row_next && i < tl_warp) {            // warp-uniform: refresh the rows of steps i .. i + W - 1
             __syncwarp();
@@ -440,6 +477,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
                     c[192] = w.k_r; c[224] = w.k_r_d; c[256] = w.bx; c[288] = w.by; c[320] = w.nx; c[352] = w.ny;
                     c[384] = w.c_ref; c[416] = w.s_ref;
                     rflags[lane] = w.flags;
+                    rflags[32 + lane] = w.dynmask;
                 }
             }
             __syncwarp();
@@ -455,6 +493,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             L.k_r = c[192]; L.k_r_d = c[224]; L.bx = c[256]; L.by = c[288]; L.nx = c[320]; L.ny = c[352];
             L.c_ref = c[384]; L.s_ref = c[416];
             L.flags = rflags[item];
+            heavy_dynmask = rflags[32 + item];
             StepOut o = lat_part<false>(P, R, Y, L, I.cd, cs0, th_gl, kappa, i);
             if (o.reject & 0x80000000u) o = poly_step_exact(P, R, Y, I);
             pre |= o.pre;
@@ -513,7 +552,8 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             const double ecx = px + P.wb_rear * cn;
             const double ecy = py + P.wb_rear * sn;
             const int tidx = in.x0_time_step + i * in.factor;
-            const bool hit = (P.dyn_rows ? dyn_collides_f32(O, P.dyn_rows + (size_t)i * O.n_dyn, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid)
+            const bool hit = (P.dyn_rows ? dyn_collides_f32(O, P.dyn_rows + (size_t)i * O.n_dyn, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid,
+                                                               i < tl ? heavy_dynmask : 0xffffffffu)
                                          : dyn_collides_global(O, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid, P.r_ego)) ||
                              static_collides(O, ecx, ecy, cn, sn, P.half_len, P.half_wid);
             if (hit) col = (unsigned)i;
@@ -615,8 +655,8 @@ cand_kernel(const __grid_constant__ PlanParams P) {
     sp += BLOCK;
     LimitRcp* const s_Y = reinterpret_cast<LimitRcp*>(sp);
     sp += 4;
-    double* const s_rows = sp + (size_t)(tid >> 5) * (kLonRowDoubles * 32 + 16);   // this warp's longitudinal rows
-    sp += (size_t)(BLOCK / 32) * (kLonRowDoubles * 32 + 16);
+    double* const s_rows = sp + (size_t)(tid >> 5) * kWarpRowDoubles;   // this warp's longitudinal rows
+    sp += (size_t)(BLOCK / 32) * kWarpRowDoubles;
     Segment* const s_segs = reinterpret_cast<Segment*>(sp);
     for (int q = tid; q < P.n_segs; q += BLOCK) s_segs[q] = P.segs[q];
     if (tid == 0) {
@@ -661,7 +701,7 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
     sp += BLOCK;
     LimitRcp* const s_Y = reinterpret_cast<LimitRcp*>(sp) + warp;
     sp += (size_t)(BLOCK / 32) * 3;
-    double* const s_rows = sp + (size_t)warp * (kLonRowDoubles * 32 + 16);
+    double* const s_rows = sp + (size_t)warp * kWarpRowDoubles;
     const int total = B.chunk_prefix[B.n_scenarios];
     int sc_cached = -1;
     for (;;) {

@@ -442,7 +442,7 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     
     const size_t acc_bytes = (size_t)(n_acc_rows * 8 + 1) * G.threads * sizeof(double);    // + v_mid
     const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 128 +
-                         (size_t)(G.threads / 32) * (rp::kLonRowDoubles * 32 + 16) * sizeof(double);     // the warps' longitudinal rows
+                         (size_t)(G.threads / 32) * rp::kWarpRowDoubles * sizeof(double);     // the warps' longitudinal rows
     G.stage_dyn = 0;                                   // dynamic-obstacle rows are read through L1 (dyn_rows_kernel)
     G.smem = acc_bytes + fixed;
     G.stage_ref = (env_stage_ref && G.smem + ref_bytes <= budget / 3) ? 1 : 0;
@@ -494,6 +494,7 @@ void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G, const rp::Segmen
     P.wb_rear = ctx->veh.wb_rear_axle;
     P.r_ego = std::sqrt(P.half_len * P.half_len + P.half_wid * P.half_wid);
     P.r_ego_f_up = std::nextafterf((float)P.r_ego, std::numeric_limits<float>::infinity());
+    P.wb_rear_f_up = std::nextafterf((float)std::fabs(P.wb_rear), std::numeric_limits<float>::infinity());
     const double* base = ctx->d_ref.as<double>();
     const int n = ctx->ref_n;
     P.ref.n = n;
@@ -906,7 +907,7 @@ static int launch_plan(rp_ctx* ctx) {
                 const int total = Np1 * ctx->obs.n_dyn;
                 if (int rc = ctx->d_dyn_rows.ensure((size_t)total * sizeof(float4))) return rc;
                 rp::dyn_rows_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->obs, ctx->in.x0_time_step, ctx->in.factor, Np1,
-                                                                                   P.r_ego_f_up, ctx->d_dyn_rows.as<float4>());
+                                                                                   P.r_ego_f_up, P.wb_rear_f_up, ctx->d_dyn_rows.as<float4>());
                 P.dyn_rows = ctx->d_dyn_rows.as<float4>();
             }
             const Geometry& G = ctx->main_geom;
@@ -1525,7 +1526,7 @@ int rp_batch_launch(rp_batch* b) {
         T.work_counter = b->d_work.as<int>();
         const int threads = RP_CAND_THREADS;
         const size_t smem = (size_t)(acc_rows * 8 + 1) * threads * sizeof(double) + (size_t)(threads / 32) * sizeof(rp::LimitRcp) +
-                            (size_t)(threads / 32) * (rp::kLonRowDoubles * 32 + 16) * sizeof(double) + 64;
+                            (size_t)(threads / 32) * rp::kWarpRowDoubles * sizeof(double) + 64;
         if ((int)smem > b->smem_granted) {
             RP_CUDA(cudaFuncSetAttribute(rp::cand_batch_kernel<RP_CAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             b->smem_granted = (int)smem;

@@ -45,6 +45,7 @@ struct PlanParams {
     Limits lim;
     double half_len, half_wid, wb_rear, r_ego;
     float r_ego_f_up;            // r_ego rounded up to fp32 (single-precision pre-reject of rp_cand.cuh)
+    float wb_rear_f_up;          // |wb_rear| rounded up to fp32
     RefTables ref;
     double ref_inv_step, ps_inv_step;     // (n-1) / (last - first): index guess of the segment lookup
     ObstacleTables obs;

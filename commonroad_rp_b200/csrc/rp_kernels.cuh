@@ -102,7 +102,8 @@ __global__ void dyn_rows_batch_kernel(const PlanParams* __restrict__ params) {
     if (present) {
         const double* b = O.dyn_box + (size_t)(O.dyn_off[o] + kk) * kBoxStride;
         const float reach = (P.r_ego_f_up + (float)b[6]) * 1.000001f + O.dyn_margin;
-        r = make_float4((float)(b[0] - O.org_x), (float)(b[1] - O.org_y), reach * reach * 1.00001f, 0.0f);
+        r = make_float4((float)(b[0] - O.org_x), (float)(b[1] - O.org_y), reach * reach * 1.00001f,
+                        (reach + P.wb_rear_f_up) * 1.0001f + 1.0e-3f);
     }
     const_cast<float4*>(P.dyn_rows)[q] = r;
 }
