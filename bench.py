@@ -612,7 +612,10 @@ def main():
                             "peak_source": peak_kind + " (MEASURED_PEAKS.json)"}
     if lazy_ms is not None:
         line["lazy_collision"] = {"value": n_total / (lazy_ms * 1e-3), "unit": UNIT, "ms_per_step": lazy_ms,
-                                  "note": "check_collision=2: same winner / counters, costlier candidates not visited"}
+                                  "note": "check_collision=2 (the reference's lazy semantics): same winner / counters.  The "
+                                          "step-parallel kernel skips candidates costlier than the best collision-free one so far; "
+                                          "the candidate-major kernel (this bundle size) checks speculatively while it marches, so "
+                                          "both modes cost the same there"}
     if full is not None:
         gbs = cand_steps_launch * STATE_BYTES_PER_CAND_STEP / (full * 1e-3) / 1e9
         line["roofline_full_states"] = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",

@@ -224,3 +224,41 @@ def test_utm_sized_coordinates(kernel):
     # rounding, so the states are compared with that absolute floor (helpers.rel_err scales by max(|a|, |b|, 1)).
     H.assert_parity(o, g, prob, tag="utm " + kernel)
     eng.close()
+
+
+def test_schedules_identical_on_randomised_bundles():
+    """kernel-vs-kernel identity (status, reason, step, cost bits, winner, counters) on randomised bundles: horizons,
+    sampling levels, initial speeds incl. low-velocity and standstill-carry regimes, stopping mode, time offsets,
+    straight and tight reference paths -- no oracle involved, so the bundles can be many"""
+    from commonroad_rp_b200 import _lib
+    rng = np.random.default_rng(2026)
+    n_checked = 0
+    for trial in range(24):
+        N = int(rng.choice([12, 20, 33, 47, 60]))
+        level = int(rng.choice([1, 2, 3]))
+        regime = trial % 4
+        kw = dict(seed=int(rng.integers(0, 50)), level=level, N=N, d0=float(rng.uniform(-1.0, 1.0)),
+                  amplitude=float(rng.choice([0.0, 10.0, 20.0])), wavelength=float(rng.choice([25.0, 40.0, 80.0])),
+                  x0_time_step=int(rng.integers(0, 40)), t_min=float(rng.choice([0.2, 0.4, 1.0])))
+        if regime == 0:
+            kw.update(s_dot0=float(rng.uniform(6.0, 22.0)))
+        elif regime == 1:
+            kw.update(s_dot0=float(rng.uniform(0.5, 3.5)), low_vel=True)
+        elif regime == 2:
+            kw.update(s_dot0=float(rng.uniform(0.2, 1.5)), low_vel=False)            # standstill carry branch
+        else:
+            kw.update(lon_mode="stopping", s_dot0=float(rng.uniform(4.0, 10.0)), desired_s=float(rng.uniform(15.0, 40.0)))
+        kw["t_min"] = min(kw["t_min"], N * 0.1)
+        prob = _bundle(**kw)
+        eng = H.engine_for(prob)
+        a = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_CANDIDATE_MAJOR)
+        b = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_STEP_PARALLEL)
+        eng.close()
+        tag = str(kw)
+        assert np.array_equal(a["status"], b["status"]), tag
+        assert np.array_equal(a["reason"], b["reason"]) and np.array_equal(a["step"], b["step"]), tag
+        assert np.array_equal(a["cost"].view(np.int64), b["cost"].view(np.int64)), tag
+        assert a["winner"] == b["winner"] and a["n_infeasible_collision"] == b["n_infeasible_collision"], tag
+        assert a["reason_counts"] == b["reason_counts"] and a["n_collision_total"] == b["n_collision_total"], tag
+        n_checked += a["n"]
+    assert n_checked > 10000
