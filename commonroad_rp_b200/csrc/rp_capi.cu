@@ -130,7 +130,7 @@ struct rp_ctx {
     DevBuf d_segs, d_segs_index, d_argmin, d_best;
     PinBuf h_segs, h_segs_index;
     Geometry main_geom{}, index_geom{}, cand_geom{};
-    bool main_is_cand = false, main_one_group = false;          // geometry in main_geom/d_segs belongs to the candidate-major kernel
+    bool main_is_cand = false, main_one_group = false, small_path_last = false;          // geometry in main_geom/d_segs belongs to the candidate-major kernel
     int kernel_policy = RP_KERNEL_AUTO;
     DevBuf d_work, d_dyn_rows;
     int index_geom_np1 = -1, index_geom_count = -1;
@@ -864,6 +864,14 @@ static int launch_plan(rp_ctx* ctx) {
     if (ctx->in.want_all_states) {
         if (int rc = ctx->d_states_all.ensure((size_t)std::max(n, 1) * 14 * Np1 * sizeof(double))) return rc;
     }
+    // replanning-size bundles: the main launch writes the states of every kept candidate (a few MB at most) and ONE
+    // block selects the winner and gathers its states -- 3 launches per cycle instead of 6
+    static const int env_small = std::getenv("RP_SMALL_PATH") ? std::atoi(std::getenv("RP_SMALL_PATH")) : 1;
+    const bool small_path = env_small && count > 0 && (long long)n * Np1 <= 262144 && !use_cand_kernel(ctx, count);
+    ctx->small_path_last = small_path;
+    if (small_path && !ctx->in.want_all_states) {
+        if (int rc = ctx->d_states_all.ensure((size_t)n * 14 * Np1 * sizeof(double))) return rc;
+    }
     ctx->ev = ctx->ev_ring[ctx->n_launches % rp_ctx::kEvRing];
     cudaEventRecord(ctx->ev[0], ctx->stream);
     if (ctx->mode == 0 && n > 0) {
@@ -890,7 +898,7 @@ static int launch_plan(rp_ctx* ctx) {
         P.index = nullptr;
         P.cost = ctx->d_cost.as<double>();
         P.info = ctx->d_info.as<int>();
-        P.states = ctx->in.want_all_states ? ctx->d_states_all.as<double>() : nullptr;
+        P.states = (ctx->in.want_all_states || small_path) ? ctx->d_states_all.as<double>() : nullptr;
         P.states_by_slot = 0;
         if (ctx->in.check_collision == 2) {
             if (int rc = ctx->d_best.ensure(sizeof(unsigned long long))) return rc;
@@ -919,7 +927,10 @@ static int launch_plan(rp_ctx* ctx) {
     }
     cudaEventRecord(ctx->ev[2], ctx->stream);
     rp::PlanResultDev* dres = ctx->d_result.as<rp::PlanResultDev>();
-    {
+    if (small_path) {
+        rp::select_small_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count,
+                                                            ctx->d_states_all.as<double>(), Np1, dres, ctx->d_states_one());
+    } else {
         if (int rc = ctx->d_argmin.ensure(sizeof(rp::ArgminScratch))) return rc;
         rp::ArgminScratch* sc = ctx->d_argmin.as<rp::ArgminScratch>();
         RP_CUDA(cudaMemsetAsync(sc, 0, sizeof(int) * 16, ctx->stream));
@@ -931,7 +942,7 @@ static int launch_plan(rp_ctx* ctx) {
     RP_CUDA(cudaGetLastError());
     cudaEventRecord(ctx->ev[3], ctx->stream);
     // winner's 14 x (N+1) state block; the winner index never leaves the device
-    if (count > 0) {
+    if (count > 0 && !small_path) {
         if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one())) return rc;
     }
     if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision) {
@@ -1295,6 +1306,7 @@ int rp_last_main_kernel(rp_ctx* ctx) {
 int rp_launches_per_plan(rp_ctx* ctx) {
     if (!ctx) return 0;
     // coeff, fused, argmin partial / merge / count, winner states (+ the dynamic-obstacle rows of the candidate-major kernel)
+    if (ctx->small_path_last) return ctx->mode == 0 ? 3 : 2;      // coeff, fused (states of every kept candidate), select
     return (ctx->mode == 0 ? 6 : 5) + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
 }
 

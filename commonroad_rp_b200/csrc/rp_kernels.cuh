@@ -261,17 +261,16 @@ __global__ void __launch_bounds__(256) count_before_result_kernel(const double* 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&out->r.n_infeasible_collision, local);
 }
 
-// one block per scenario of a batch: arg-min, counters and the colliders ranked before the winner in one launch
-__global__ void __launch_bounds__(256) argmin_batch_kernel(const PlanParams* __restrict__ params, PlanResultDev* __restrict__ results) {
+// The whole selection of ONE bundle (or shard [first, first + count)) by ONE block: lexicographic arg-min on
+// (cost, enumeration index) over feasible, collision-free candidates, the cycle's counters, and the colliders ranked
+// before the winner.  Used per scenario of a batch and for replanning-size bundles (one launch instead of three).
+__device__ __forceinline__ void block_select(const double* __restrict__ cost, const int* __restrict__ info, int first,
+                                             int count, PlanResultDev* __restrict__ out) {
     __shared__ double w_cost[8];
     __shared__ int w_idx[8];
     __shared__ int s_counts[16];
     __shared__ double s_wc;
     __shared__ int s_wi, s_before;
-    const PlanParams& P = params[blockIdx.x];
-    const double* __restrict__ cost = P.cost;
-    const int* __restrict__ info = P.info;
-    const int n = P.n_cand;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) s_counts[tid] = 0;
     if (tid == 0) s_before = 0;
@@ -280,7 +279,8 @@ __global__ void __launch_bounds__(256) argmin_batch_kernel(const PlanParams* __r
     int bi = 0x7fffffff;
     int l_feas = 0, l_colt = 0, l_filt = 0;
     int l_reason[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = tid; k < n; k += blockDim.x) {
+    for (int q = tid; q < count; q += blockDim.x) {
+        const int k = first + q;
         const int w = info[k];
         const int st = w & 0xFF;
         if (st == ST_FEASIBLE) {
@@ -325,24 +325,45 @@ __global__ void __launch_bounds__(256) argmin_batch_kernel(const PlanParams* __r
         const double wc = s_wc;
         const int wi = s_wi;
         int local = 0;
-        for (int k = tid; k < n; k += blockDim.x)
+        for (int q = tid; q < count; q += blockDim.x) {
+            const int k = first + q;
             if ((info[k] & 0xFF) == ST_COLLISION && (none || lex_less(cost[k], k, wc, wi))) ++local;
+        }
         local = warp_sum(local);
         if (lane == 0 && local) atomicAdd(&s_before, local);
         __syncthreads();
     }
     if (tid == 0) {
-        rp_plan_result& r = results[blockIdx.x].r;
+        rp_plan_result& r = out->r;
         r.winner = none ? -1 : s_wi;
         r.winner_cost = none ? __longlong_as_double(0x7ff8000000000000LL) : s_wc;
-        r.n_candidates = n;
+        r.n_candidates = count;
         r.n_feasible = s_counts[0];
-        r.n_infeasible_kinematics = n - s_counts[3] - s_counts[0];
+        r.n_infeasible_kinematics = count - s_counts[3] - s_counts[0];
         r.n_infeasible_collision = s_before;
         r.n_collision_total = s_counts[2];
         for (int z = 0; z < 8; ++z) r.reason_counts[z] = s_counts[8 + z];
-        results[blockIdx.x].n_filtered = s_counts[3];
+        out->n_filtered = s_counts[3];
     }
+    __syncthreads();
+}
+
+// one block per scenario of a batch
+__global__ void __launch_bounds__(256) argmin_batch_kernel(const PlanParams* __restrict__ params, PlanResultDev* __restrict__ results) {
+    const PlanParams& P = params[blockIdx.x];
+    block_select(P.cost, P.info, 0, P.n_cand, results + blockIdx.x);
+}
+
+// replanning-size bundle: selection + the winner's 14 x (N + 1) state block gathered from the states the main launch
+// wrote for every kept candidate -- one launch instead of partial / merge / count / winner-state re-evaluation
+__global__ void __launch_bounds__(256) select_small_kernel(const double* __restrict__ cost, const int* __restrict__ info, int first,
+                                                           int count, const double* __restrict__ states_all, int Np1,
+                                                           PlanResultDev* __restrict__ out, double* __restrict__ states_one) {
+    block_select(cost, info, first, count, out);
+    const int winner = out->r.winner;           // written by thread 0 before the closing barrier of block_select
+    if (winner < 0) return;
+    const double* src = states_all + (size_t)winner * 14 * Np1;
+    for (int q = threadIdx.x; q < 14 * Np1; q += blockDim.x) states_one[q] = src[q];
 }
 
 // ---- multi-GPU bundle shards: each rank owns a contiguous tile of the enumeration space --------
