@@ -21,7 +21,7 @@ import numpy as np
 
 from commonroad_rp_b200 import _lib
 from commonroad_rp_b200 import collision as rpc
-from commonroad_rp_b200._compat import CustomState, InputState, Trajectory
+from commonroad_rp_b200._compat import HAVE_COMMONROAD_IO, CustomState, InputState, Trajectory
 from commonroad_rp_b200.cost_function import CostFunction, DefaultCostFunction
 from commonroad_rp_b200.polynomial_trajectory import QuarticTrajectory, QuinticTrajectory
 from commonroad_rp_b200.sampling import (PositionSampling, SamplingSpace, TimeSampling, VelocitySampling,
@@ -556,12 +556,30 @@ class ReactivePlanner(object):
         pos_cart = np.stack([ca.x, ca.y], axis=1)
         pos_curv = np.stack([cu.s, cu.d], axis=1)
         t0 = self.x_0.time_step
-        cart_list = [ReactivePlannerState(time_step=t0 + factor * i, position=pos_cart[i], orientation=th, velocity=vel,
-                                          acceleration=acc, yaw_rate=yr, steering_angle=st)
-                     for i, (th, vel, acc, yr, st) in enumerate(zip(theta, ca.v, ca.a, yaw_rate, steering))]
-        cl_list = [CustomState(time_step=t0 + factor * i, position=pos_curv[i], velocity=vel, acceleration=acc,
-                               orientation=th, yaw_rate=kap)
-                   for i, (vel, acc, th, kap) in enumerate(zip(ca.v, ca.a, theta, ca.kappa))]
+        th_l, v_l, a_l = theta.tolist(), ca.v.tolist(), ca.a.tolist()
+        if HAVE_COMMONROAD_IO:
+            cart_list = [ReactivePlannerState(time_step=t0 + factor * i, position=pos_cart[i], orientation=th, velocity=vel,
+                                              acceleration=acc, yaw_rate=yr, steering_angle=st)
+                         for i, (th, vel, acc, yr, st) in enumerate(zip(th_l, v_l, a_l, yaw_rate.tolist(), steering.tolist()))]
+            cl_list = [CustomState(time_step=t0 + factor * i, position=pos_curv[i], velocity=vel, acceleration=acc,
+                                   orientation=th, yaw_rate=kap)
+                       for i, (vel, acc, th, kap) in enumerate(zip(v_l, a_l, th_l, ca.kappa.tolist()))]
+        else:
+            # the package's own plain state classes: fill the instance dictionaries directly (42 objects per cycle)
+            cart_list, cl_list = [], []
+            new_rs, new_cs = ReactivePlannerState.__new__, CustomState.__new__
+            p_cart, p_curv = list(pos_cart), list(pos_curv)
+            for i, (th, vel, acc, yr, st, kap) in enumerate(zip(th_l, v_l, a_l, yaw_rate.tolist(), steering.tolist(),
+                                                                 ca.kappa.tolist())):
+                ts = t0 + factor * i
+                o = new_rs(ReactivePlannerState)
+                o.__dict__ = {"time_step": ts, "position": p_cart[i], "steering_angle": st, "velocity": vel, "orientation": th,
+                              "acceleration": acc, "yaw_rate": yr}
+                cart_list.append(o)
+                c = new_cs(CustomState)
+                c.__dict__ = {"time_step": ts, "position": p_curv[i], "velocity": vel, "acceleration": acc, "orientation": th,
+                              "yaw_rate": kap}
+                cl_list.append(c)
         lon_list = np.stack([cu.s, cu.s_dot, cu.s_ddot], axis=1).tolist()
         lat_list = np.stack([cu.d, cu.d_dot, cu.d_ddot], axis=1).tolist()
         cart_traj = shift_orientation(Trajectory(self.x_0.time_step, cart_list),
