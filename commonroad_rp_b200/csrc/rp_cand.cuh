@@ -351,9 +351,8 @@ __device__ __noinline__ StepOut poly_step_exact(const PlanParams& P, const RefTa
 }
 
 // rows [step][obstacle] for the launch's time window x0.time_step + step * factor (reactive_planner.py:1040)
-__global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, int Np1, float r_ego_f_up, float wb_rear_f_up,
-                                float4* __restrict__ out) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void dyn_rows_thread(int q, const ObstacleTables& O, int x0_time_step, int factor, int Np1,
+                                                float r_ego_f_up, float wb_rear_f_up, float4* __restrict__ out) {
     if (q >= Np1 * O.n_dyn) return;
     const int step = q / O.n_dyn, o = q - step * O.n_dyn;
     const int kk = x0_time_step + step * factor - O.dyn_t0[o];
@@ -367,6 +366,11 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
                         (reach + wb_rear_f_up) * 1.0001f + 1.0e-3f);
     }
     out[q] = r;
+}
+
+__global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, int Np1, float r_ego_f_up, float wb_rear_f_up,
+                                float4* __restrict__ out) {
+    dyn_rows_thread(blockIdx.x * blockDim.x + threadIdx.x, O, x0_time_step, factor, Np1, r_ego_f_up, wb_rear_f_up, out);
 }
 
 // ---- one candidate through the whole horizon (the per-lane body of both kernels below) ----------------------

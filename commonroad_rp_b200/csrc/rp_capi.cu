@@ -874,6 +874,15 @@ static int launch_plan(rp_ctx* ctx) {
     }
     ctx->ev = ctx->ev_ring[ctx->n_launches % rp_ctx::kEvRing];
     cudaEventRecord(ctx->ev[0], ctx->stream);
+    // dynamic-obstacle rows of the candidate-major kernel ride along with the coefficient solve (one launch)
+    const bool cand_main = count > 0 && use_cand_kernel(ctx, count);
+    const int dyn_total = (cand_main && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? Np1 * ctx->obs.n_dyn : 0;
+    if (dyn_total > 0)
+        if (int rc = ctx->d_dyn_rows.ensure((size_t)dyn_total * sizeof(float4))) return rc;
+    const double hl_ = 0.5 * ctx->veh.length, hw_ = 0.5 * ctx->veh.width;
+    const float r_ego_f_up = std::nextafterf((float)std::sqrt(hl_ * hl_ + hw_ * hw_), std::numeric_limits<float>::infinity());
+    const float wb_rear_f_up = std::nextafterf((float)std::fabs(ctx->veh.wb_rear_axle), std::numeric_limits<float>::infinity());
+    bool dyn_rows_done = false;         // the prep launch ran: coefficients, dynamic-obstacle rows, scratch words reset
     if (ctx->mode == 0 && n > 0) {
         const int n_lon_sys = ctx->n_t * ctx->n_lon;
         const int n_lat_sys = ctx->in.low_vel_mode ? n : ctx->n_t * ctx->n_d;
@@ -881,14 +890,28 @@ static int launch_plan(rp_ctx* ctx) {
         if (int rc = ctx->d_lat_coef.ensure((size_t)n_lat_sys * 6 * sizeof(double))) return rc;
         if (int rc = ctx->d_lat_tau.ensure((size_t)n_lat_sys * sizeof(double))) return rc;
         const char* sb = static_cast<const char*>(ctx->d_samples.p);
-        const int total = n_lon_sys + n_lat_sys;
-        rp::coeff_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(
-            ctx->n_t, ctx->n_lon, ctx->n_d, ctx->in.low_vel_mode, ctx->in.lon_mode,
-            reinterpret_cast<const double*>(sb + ctx->off_t), reinterpret_cast<const double*>(sb + ctx->off_lon),
-            reinterpret_cast<const double*>(sb + ctx->off_d), ctx->in.x0_lon[0], ctx->in.x0_lon[1], ctx->in.x0_lon[2],
-            ctx->in.x0_lat[0], ctx->in.x0_lat[1], ctx->in.x0_lat[2], ctx->d_lon_coef.as<double>(),
-            ctx->d_lat_coef.as<double>(), ctx->d_lat_tau.as<double>());
+        rp::PrepArgs A{};
+        A.n_t = ctx->n_t; A.n_lon = ctx->n_lon; A.n_d = ctx->n_d; A.low_vel = ctx->in.low_vel_mode; A.lon_mode = ctx->in.lon_mode;
+        A.t = reinterpret_cast<const double*>(sb + ctx->off_t);
+        A.lon = reinterpret_cast<const double*>(sb + ctx->off_lon);
+        A.d = reinterpret_cast<const double*>(sb + ctx->off_d);
+        A.x0s = ctx->in.x0_lon[0]; A.x0sd = ctx->in.x0_lon[1]; A.x0sdd = ctx->in.x0_lon[2];
+        A.x0d = ctx->in.x0_lat[0]; A.x0dd = ctx->in.x0_lat[1]; A.x0ddd = ctx->in.x0_lat[2];
+        A.lon_coef = ctx->d_lon_coef.as<double>(); A.lat_coef = ctx->d_lat_coef.as<double>(); A.lat_tau = ctx->d_lat_tau.as<double>();
+        A.n_coeff_blocks = (n_lon_sys + n_lat_sys + 127) / 128;
+        A.obs = ctx->obs;
+        A.x0_time_step = ctx->in.x0_time_step; A.factor = ctx->in.factor; A.Np1 = Np1;
+        A.r_ego_f_up = r_ego_f_up; A.wb_rear_f_up = wb_rear_f_up;
+        A.dyn_rows = ctx->d_dyn_rows.as<float4>();
+        if (int rc = ctx->d_argmin.ensure(sizeof(rp::ArgminScratch))) return rc;
+        if (int rc = ctx->d_work.ensure(sizeof(int))) return rc;
+        if (int rc = ctx->d_best.ensure(sizeof(unsigned long long))) return rc;
+        A.argmin_counts = reinterpret_cast<int*>(ctx->d_argmin.p);
+        A.work_counter = ctx->d_work.as<int>();
+        A.best_bits = ctx->d_best.as<unsigned long long>();
+        rp::prep_kernel<<<A.n_coeff_blocks + (dyn_total + 127) / 128, 128, 0, ctx->stream>>>(A);
         RP_CUDA(cudaGetLastError());
+        dyn_rows_done = true;
     }
     cudaEventRecord(ctx->ev[1], ctx->stream);
     if (count > 0) {
@@ -902,20 +925,21 @@ static int launch_plan(rp_ctx* ctx) {
         P.states_by_slot = 0;
         if (ctx->in.check_collision == 2) {
             if (int rc = ctx->d_best.ensure(sizeof(unsigned long long))) return rc;
-            RP_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, sizeof(unsigned long long), ctx->stream));   // ~1.4e306
+            if (!dyn_rows_done)             // (the prep launch of the grid form resets the per-cycle scratch words)
+                RP_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, sizeof(unsigned long long), ctx->stream));   // ~1.4e306
             P.best_bits = ctx->d_best.as<unsigned long long>();
         }
         if (ctx->main_is_cand) {
             if (int rc = ctx->d_work.ensure(sizeof(int))) return rc;
-            RP_CUDA(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(int), ctx->stream));
+            if (!dyn_rows_done) RP_CUDA(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(int), ctx->stream));
             P.work_counter = ctx->d_work.as<int>();
             P.n_acc_rows = cand_acc_rows(ctx->in);
             P.dyn_rows = nullptr;
-            if (ctx->obs.n_dyn > 0 && ctx->in.check_collision) {
-                const int total = Np1 * ctx->obs.n_dyn;
-                if (int rc = ctx->d_dyn_rows.ensure((size_t)total * sizeof(float4))) return rc;
-                rp::dyn_rows_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->obs, ctx->in.x0_time_step, ctx->in.factor, Np1,
-                                                                                   P.r_ego_f_up, P.wb_rear_f_up, ctx->d_dyn_rows.as<float4>());
+            if (dyn_total > 0) {
+                if (!dyn_rows_done)         // list form: no coefficient launch to ride along with
+                    rp::dyn_rows_kernel<<<(dyn_total + 127) / 128, 128, 0, ctx->stream>>>(ctx->obs, ctx->in.x0_time_step, ctx->in.factor,
+                                                                                           Np1, P.r_ego_f_up, P.wb_rear_f_up,
+                                                                                           ctx->d_dyn_rows.as<float4>());
                 P.dyn_rows = ctx->d_dyn_rows.as<float4>();
             }
             const Geometry& G = ctx->main_geom;
@@ -933,7 +957,7 @@ static int launch_plan(rp_ctx* ctx) {
     } else {
         if (int rc = ctx->d_argmin.ensure(sizeof(rp::ArgminScratch))) return rc;
         rp::ArgminScratch* sc = ctx->d_argmin.as<rp::ArgminScratch>();
-        RP_CUDA(cudaMemsetAsync(sc, 0, sizeof(int) * 16, ctx->stream));
+        if (!dyn_rows_done) RP_CUDA(cudaMemsetAsync(sc, 0, sizeof(int) * 16, ctx->stream));
         const int nb = std::max(1, std::min(512, std::min(2 * ctx->num_sms, (count + 255) / 256)));
         rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc);
         rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres);
@@ -1307,7 +1331,9 @@ int rp_launches_per_plan(rp_ctx* ctx) {
     if (!ctx) return 0;
     // coeff, fused, argmin partial / merge / count, winner states (+ the dynamic-obstacle rows of the candidate-major kernel)
     if (ctx->small_path_last) return ctx->mode == 0 ? 3 : 2;      // coeff, fused (states of every kept candidate), select
-    return (ctx->mode == 0 ? 6 : 5) + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
+    // prep (coefficients + dynamic-obstacle rows), main kernel, argmin partial / merge / count, winner states; the list
+    // form has no coefficient solve but, for the candidate-major kernel, its own dynamic-obstacle rows launch
+    return ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
 }
 
 }  // extern "C"

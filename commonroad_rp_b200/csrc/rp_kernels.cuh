@@ -81,6 +81,38 @@ __global__ void coeff_kernel(int n_t, int n_lon, int n_d, int low_vel, int lon_m
                  x0dd, x0ddd, lon_coef, lat_coef, lat_tau);
 }
 
+// coefficient solves and the dynamic-obstacle rows of the candidate-major kernel are independent: one launch, the first
+// n_coeff_blocks blocks solve, the rest write rows
+struct PrepArgs {
+    int n_t, n_lon, n_d, low_vel, lon_mode;
+    const double *t, *lon, *d;
+    double x0s, x0sd, x0sdd, x0d, x0dd, x0ddd;
+    double *lon_coef, *lat_coef, *lat_tau;
+    int n_coeff_blocks;
+    ObstacleTables obs;
+    int x0_time_step, factor, Np1;
+    float r_ego_f_up, wb_rear_f_up;
+    float4* dyn_rows;
+    // per-cycle scratch words this launch resets for the kernels after it (instead of separate memset nodes)
+    int* argmin_counts;                 // [16]
+    int* work_counter;                  // chunk dispenser of the candidate-major kernel (may be null)
+    unsigned long long* best_bits;      // lazy collision bound of the step-parallel kernel (may be null)
+};
+
+__global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ PrepArgs A) {
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 16 && A.argmin_counts) A.argmin_counts[threadIdx.x] = 0;
+        if (threadIdx.x == 16 && A.work_counter) *A.work_counter = 0;
+        if (threadIdx.x == 17 && A.best_bits) *A.best_bits = 0x7f7f7f7f7f7f7f7fULL;     // ~1.4e306
+    }
+    if ((int)blockIdx.x < A.n_coeff_blocks)
+        coeff_thread(blockIdx.x * blockDim.x + threadIdx.x, A.n_t, A.n_lon, A.n_d, A.low_vel, A.lon_mode, A.t, A.lon, A.d, A.x0s,
+                     A.x0sd, A.x0sdd, A.x0d, A.x0dd, A.x0ddd, A.lon_coef, A.lat_coef, A.lat_tau);
+    else
+        dyn_rows_thread((blockIdx.x - A.n_coeff_blocks) * blockDim.x + threadIdx.x, A.obs, A.x0_time_step, A.factor, A.Np1,
+                        A.r_ego_f_up, A.wb_rear_f_up, A.dyn_rows);
+}
+
 // ---- batch of independent scenarios (blockIdx.y = scenario; see cand_batch_kernel) --------------------------------
 __global__ void coeff_batch_kernel(const PlanParams* __restrict__ params) {
     const PlanParams& P = params[blockIdx.y];
