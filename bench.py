@@ -178,6 +178,8 @@ def replanning_latency_b200(name="ZAM_Over-1_1", repeats=5):
     cfg.planning.time_steps_computation = meta["N"]
     cfg.planning.low_vel_mode_threshold = meta["low_vel_mode_threshold"]
     cfg.sampling.t_min = meta["t_min"]
+    cfg.debug.draw_traj_set = meta.get("draw_traj_set", False)       # DEU_Test's YAML keeps every trajectory for plotting
+    cfg.debug.save_plots = meta.get("draw_traj_set", False)
 
     class _Empty:
         static_obstacles, dynamic_obstacles = (), ()
@@ -622,6 +624,9 @@ def main():
                                         "frac": gbs / peaks.get("hbm_gbs"), "traffic": None, "kernel_ms": full,
                                         "peak_source": peak_kind + " (MEASURED_PEAKS.json)"}
     line["p50_replanning_cycle_ms"] = replanning_latency_b200()
+    line["p50_replanning_cycle_ms"]["other_bundled_scenarios"] = {
+        name: {k: v for k, v in replanning_latency_b200(name, repeats=3).items() if k in ("p50_ms", "p95_ms", "cycles")}
+        for name in ("ZAM_Tjunction-1_42_T-1", "DEU_Test-1_1_T-1")}
     line["scenario_batch"] = scen
     if not args.no_cpu_baseline:
         line["p50_replanning_cycle_ms"]["cpu_port"] = replanning_latency_port()

@@ -12,6 +12,8 @@ calls.  There is no CPU fallback: without the CUDA library or a device, ``plan()
 ``config.debug.multiproc`` / ``num_workers`` are accepted and ignored (the reference forks workers over
 candidate chunks, :1084-1111; here every (candidate, time step) pair is a GPU thread).
 """
+import collections.abc
+import copy
 import logging
 import math
 import time
@@ -32,6 +34,32 @@ from commonroad_rp_b200.trajectories import (CartesianSample, CurviLinearSample,
 from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration, VehicleConfiguration
 from commonroad_rp_b200.utility.general import retrieve_desired_velocity_from_pp, shift_orientation
 from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem, interpolate_angle
+
+class _LazyViews(collections.abc.Sequence):
+    """``stored_trajectories`` in draw mode: a read-only sequence of TrajectorySample views on the device results of
+    the cycle, each created (and cached) on first access.  ``copy.deepcopy`` gives a plain list of materialised copies."""
+
+    def __init__(self, make, order):
+        self._make, self._order, self._cache = make, order, {}
+
+    def __len__(self):
+        return len(self._order)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError("trajectory index out of range")
+        view = self._cache.get(i)
+        if view is None:
+            view = self._cache[i] = self._make(int(self._order[i]))
+        return view
+
+    def __deepcopy__(self, memo):
+        return [copy.deepcopy(v, memo) for v in self]
+
 
 logger = logging.getLogger("RP_LOGGER")
 
@@ -487,9 +515,11 @@ class ReactivePlanner(object):
             self._infeasible_reason_dict[constraint] = int(res.reason_counts[_lib.REASON_NAMES.index(constraint)])
 
         if self._draw_traj_set:
-            status = arrays["status"]
-            order = [k for k in range(dev["n"]) if status[k] in (0, 2, 4)] + [k for k in range(dev["n"]) if status[k] == 1]
-            self.stored_trajectories = [self._view(trajectory_bundle, k, arrays) for k in order]
+            # feasible candidates first, then the kinematically infeasible ones (reference :1121-1128); the views are
+            # created when they are looked at (plotting), not 3 000 Python objects per cycle up front
+            status = np.asarray(arrays["status"])
+            order = np.concatenate([np.nonzero(np.isin(status, (0, 2, 4)))[0], np.nonzero(status == 1)[0]])
+            self.stored_trajectories = _LazyViews(lambda k: self._view(trajectory_bundle, k, arrays), order)
 
         if winner < 0:
             return None
