@@ -603,6 +603,9 @@ def main():
                      "kernel": kernel_name, "kernel_ms": fused_mean_ms,
                      "peak_source": "DFMA micro-benchmark measured in this run (FMA = 2 flop); "
                                     "algorithmic work = 200 flop per candidate-timestep (SURVEY 8d)",
+                     # the path multiplies and adds separately (--fmad=false: the reference's IEEE operation order decides
+                     # flags bit-exactly), one flop per FP64 issue slot: the attainable ceiling is half the FMA peak
+                     "frac_of_unfused_ceiling": 2.0 * achieved_tf / fp64_peak if fp64_peak else None,
                      "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_kind},
     }
     # the same kernel against the HBM roofline (the contract's other bound): select-only mode moves 13 doubles in and
