@@ -414,6 +414,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: the arg-min exchange of the sharded bundle -- stores into peer-mapped mailboxes over NVLink "
+                         "(rp_peer_*) or an NCCL all-gather + all-reduce")
     ap.add_argument("--full-states", action="store_true", help="also time the full-state (HBM-heavy) variant")
     ap.add_argument("--scenarios", type=int, default=64,
                     help="independent scenarios PER RANK of the scenario-batch leg (BASELINE configs[4]: 512 per GPU)")
@@ -453,13 +456,17 @@ def main():
         eng.set_candidate_range(first, count)
     Np1 = N_HORIZON + 1
 
-    from commonroad_rp_b200.parallel import global_argmin
+    from commonroad_rp_b200.parallel import PeerExchange, global_argmin
     rec = torch.zeros(4, dtype=torch.float64, device=dev)
+    peer = PeerExchange(eng, dev) if (world > 1 and args.exchange == "peer") else None
+
+    def exchange():
+        return peer.argmin() if peer is not None else global_argmin(eng, rec, world)
 
     def step_device():
         eng.grid_launch()
         if world > 1:
-            return global_argmin(eng, rec, world)
+            return exchange()
         return None
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -500,6 +507,16 @@ def main():
     total_ms = float(total_ms.item())
     res = eng.grid_result()
     main_kernel = eng.last_main_kernel()
+    exchange_check = None
+    if peer is not None:
+        # the peer-memory exchange against the NCCL one on the same launch: identical winner / totals / count
+        peer.check()
+        got = [x.clone() for x in peer.argmin()]
+        want = [x.clone() for x in global_argmin(eng, rec, world)]
+        torch.cuda.synchronize()
+        peer.check()
+        exchange_check = all(torch.equal(a, b) for a, b in zip(got, want))
+        assert exchange_check, "peer-memory exchange differs from the NCCL exchange: %r vs %r" % (got, want)
 
     # ---- end to end through the host-buffer API ----
     t_np, lon_np, d_np = np.array(work["t"]), np.array(work["lon"]), np.array(work["d"])
@@ -514,7 +531,7 @@ def main():
     for _ in range(args.steps):
         r = eng.plan_grid(inputs, t_np, lon_np, d_np, tl_np)
         if world > 1:
-            global_argmin(eng, rec, world)
+            exchange()
         if r.winner >= 0:
             eng.fetch_states(r.winner)
     torch.cuda.synchronize()
@@ -583,7 +600,8 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "dense sampling sweep 64 d x %d v x 32 t, 60-step horizon (BASELINE configs[3]%s)"
-                               % (64 * n_gpus, "" if n_gpus == 1 else "; v grid scaled with N, bundle sharded t-major, NCCL arg-min"),
+                               % (64 * n_gpus, "" if n_gpus == 1 else "; v grid scaled with N, bundle sharded t-major, arg-min exchange: " +
+                                  ("stores into peer-mapped mailboxes over NVLink (rp_peer_*)" if peer is not None else "NCCL")),
                    "candidates_per_cycle": n_total, "time_steps": Np1, "l2": "flushed between timed iterations (256 MiB fill)",
                    "mode": "select-only (winner states materialised), fmad off for parity"},
         "cand_timesteps_per_sec": value * Np1,
@@ -591,6 +609,7 @@ def main():
         "stage_ms": {"coeff": float(stage_ms[0]), "fused": float(stage_ms[1]), "argmin": float(stage_ms[2]),
                      "winner_states": float(stage_ms[3])},
         "winner": int(res.winner), "n_feasible": int(res.n_feasible),
+        "exchange": None if world == 1 else {"kind": "peer" if peer is not None else "nccl", "equals_nccl": exchange_check},
         "e2e": {"value": n_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "rp_plan_grid + rp_fetch_states (host buffers)"},

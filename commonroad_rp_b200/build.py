@@ -6,8 +6,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "rp_capi.cu")
 OUT = os.path.join(HERE, "librp_b200.so")
-DEPS = [SRC, os.path.join(HERE, "csrc", "rp_kernels.cuh"), os.path.join(HERE, "csrc", "rp_fused.cuh"), os.path.join(HERE, "csrc", "rp_device.cuh"),
-        os.path.join(ROOT, "include", "rp_b200.h")]
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("rp_kernels.cuh", "rp_fused.cuh", "rp_cand.cuh", "rp_device.cuh")] + \
+       [os.path.join(ROOT, "include", "rp_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               # the reference evaluates every expression as separate IEEE multiplies/adds: no contraction

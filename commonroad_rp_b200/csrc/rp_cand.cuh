@@ -458,6 +458,13 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
 
     unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
     const double cs0 = low_vel ? __ldg(I.cs) : 0.;
+    // lazy collision mode (check_collision == 2, the reference's cost-ordered pass :1031-1063 in parallel form): every
+    // cost term is a square, so the running sum is a lower bound of the final cost; once it exceeds the best
+    // collision-free cost any candidate has published so far, this candidate can be neither the winner nor a collider
+    // ranked before it, and its remaining poses are not checked (status RP_FEASIBLE_UNCHECKED unless it already hit)
+    const bool lazy = in.check_collision == 2 && costed && P.best_bits != nullptr;
+    double cost_lb = 0.;
+    bool gated = false;
     // values of the current / last polynomial step (the extension reads them after step tl - 1)
     double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
     double cn = 1., sn = 0.;                       // cos / sin of th_gl
@@ -529,6 +536,13 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             double q1 = 0., q2 = 0.;
             if (use_v) { const double t1 = 5 * (c_v - in.desired_speed); q1 = t1 * t1; }
             if (use_s) { const double t2 = 0.25 * (in.desired_s - c_s); q2 = t2 * t2; }
+            if (lazy) {
+                cost_lb += (q0 + q3) + (q4 + (q1 + q2));
+                if ((i & 7) == 7 && !gated) {
+                    const unsigned long long best = *reinterpret_cast<volatile unsigned long long*>(P.best_bits);
+                    gated = cost_lb * (1.0 - 1.0e-9) > __longlong_as_double((long long)best);
+                }
+            }
             if (Np1 >= 8 && i < n8) {
                 double* ap = acc + (size_t)(i & 7) * BLOCK;
                 if (i < 8) {
@@ -552,7 +566,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         }
 
         // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), speculative ---------------------
-        if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u) {
+        if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u && !gated) {
             const double ecx = px + P.wb_rear * cn;
             const double ecy = py + P.wb_rear * sn;
             const int tidx = in.x0_time_step + i * in.factor;
@@ -612,7 +626,17 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             }
             cost = costs;
         }
-        if (col != NONE) { status = ST_COLLISION; step = (int)col; }
+        if (col != NONE) {
+            status = ST_COLLISION;
+            step = (int)col;
+        } else if (lazy) {
+            if (gated) {
+                status = ST_UNCHECKED;
+            } else if (cost == cost) {                         // collision-free over the whole horizon: tighten the bound
+                const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);     // costs are >= 0
+                if (cb < *reinterpret_cast<volatile unsigned long long*>(P.best_bits)) atomicMin(P.best_bits, cb);
+            }
+        }
     }
     P.info[k] = pack_info(status, reason, step);
     if (P.cost) P.cost[k] = cost;

@@ -142,6 +142,13 @@ struct rp_ctx {
     cudaEvent_t ev_stage = nullptr, ev_segs = nullptr, ev_result = nullptr;
     bool stage_pending = false, segs_pending = false;
 
+    // multi-GPU exchange over peer-mapped memory (rp_peer_*)
+    rp::PeerMailbox* peer_mine = nullptr;           // cudaMalloc'ed, exported through CUDA IPC
+    void* peer_opened[rp::kMaxPeers] = {};          // the other ranks' mailboxes (cudaIpcOpenMemHandle)
+    rp::PeerTable peer_table{};
+    bool peer_ready = false;
+    unsigned long long peer_epoch = 0;
+
     static constexpr int kEvRing = 64;
     cudaEvent_t ev_ring[kEvRing][5] = {};
     cudaEvent_t* ev = ev_ring[0];       // event set of the launch in flight
@@ -677,6 +684,7 @@ int rp_ctx_destroy(rp_ctx* ctx) {
     if (!ctx) return RP_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    rp_peer_close(ctx);
     for (DevBuf* b : {&ctx->d_ref, &ctx->d_obb, &ctx->d_tri, &ctx->d_cell_start, &ctx->d_cell_items, &ctx->d_dyn_box,
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all,
@@ -1319,6 +1327,88 @@ int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double
     rp::count_before_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first,
                                                               count, dev_winner2, dev_out1);
     RP_CUDA(cudaGetLastError());
+    return RP_OK;
+}
+
+int rp_peer_create(rp_ctx* ctx, unsigned char* handle64) {
+    if (int rc = bind(ctx)) return rc;
+    if (!handle64) return fail(RP_ERR_ARG, "null handle buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!ctx->peer_mine) {
+        void* p = nullptr;
+        RP_CUDA(cudaMalloc(&p, sizeof(rp::PeerMailbox)));
+        ctx->peer_mine = static_cast<rp::PeerMailbox*>(p);
+    }
+    RP_CUDA(cudaMemset(ctx->peer_mine, 0, sizeof(rp::PeerMailbox)));
+    RP_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    RP_CUDA(cudaIpcGetMemHandle(&h, ctx->peer_mine));
+    std::memcpy(handle64, &h, 64);
+    ctx->peer_ready = false;
+    ctx->peer_epoch = 0;
+    return RP_OK;
+}
+
+int rp_peer_open(rp_ctx* ctx, int rank, int world, const unsigned char* handles) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ctx->peer_mine) return fail(RP_ERR_STATE, "rp_peer_create must precede rp_peer_open");
+    if (!handles || world < 1 || world > rp::kMaxPeers || rank < 0 || rank >= world) return fail(RP_ERR_ARG, "invalid peer arguments");
+    for (int r = 0; r < rp::kMaxPeers; ++r)
+        if (ctx->peer_opened[r]) { cudaIpcCloseMemHandle(ctx->peer_opened[r]); ctx->peer_opened[r] = nullptr; }
+    ctx->peer_table = rp::PeerTable{};
+    ctx->peer_table.rank = rank;
+    ctx->peer_table.world = world;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { ctx->peer_table.box[r] = ctx->peer_mine; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        RP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_opened[r] = p;
+        ctx->peer_table.box[r] = static_cast<rp::PeerMailbox*>(p);
+    }
+    ctx->peer_ready = true;
+    return RP_OK;
+}
+
+int rp_peer_argmin(rp_ctx* ctx, double* dev_winner2, double* dev_totals2, double* dev_before1) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ctx->peer_ready) return fail(RP_ERR_STATE, "rp_peer_open must precede rp_peer_argmin");
+    if (!dev_winner2 || !dev_totals2 || !dev_before1) return fail(RP_ERR_ARG, "null device pointer");
+    if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
+    const int n = ctx->n_cand;
+    int first = 0, count = n;
+    if (ctx->range_count >= 0) {
+        first = std::min(ctx->range_first, n);
+        count = std::min(ctx->range_count, n - first);
+    }
+    const unsigned long long epoch = ++ctx->peer_epoch;
+    rp::peer_merge_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_table, epoch, ctx->d_result.as<rp::PlanResultDev>(), dev_winner2,
+                                                     dev_totals2);
+    const int blocks = std::max(1, std::min(ctx->num_sms, (count + 255) / 256));
+    rp::peer_count_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->peer_table, epoch, ctx->d_cost.as<double>(), ctx->d_info.as<int>(),
+                                                           first, count, dev_winner2, dev_before1);
+    RP_CUDA(cudaGetLastError());
+    return RP_OK;
+}
+
+int rp_peer_status(rp_ctx* ctx) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ctx->peer_mine) return fail(RP_ERR_STATE, "no peer mailbox");
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    int err = 0;
+    RP_CUDA(cudaMemcpy(&err, &ctx->peer_mine->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return fail(RP_ERR_STATE, "peer exchange: a wait on another rank timed out");
+    return RP_OK;
+}
+
+int rp_peer_close(rp_ctx* ctx) {
+    if (!ctx) return RP_OK;
+    cudaSetDevice(ctx->device);
+    for (int r = 0; r < rp::kMaxPeers; ++r)
+        if (ctx->peer_opened[r]) { cudaIpcCloseMemHandle(ctx->peer_opened[r]); ctx->peer_opened[r] = nullptr; }
+    if (ctx->peer_mine) { cudaFree(ctx->peer_mine); ctx->peer_mine = nullptr; }
+    ctx->peer_ready = false;
     return RP_OK;
 }
 

@@ -460,6 +460,138 @@ __global__ void __launch_bounds__(256) count_before_kernel(const double* __restr
     if (threadIdx.x == 0) atomicAdd(out, (double)total);
 }
 
+// ---- the same exchange over peer-mapped memory (NVLink / NVSwitch, CUDA IPC) instead of two NCCL collectives ------
+// Every rank owns one PeerMailbox that all ranks of the box have mapped.  Per cycle ("epoch"):
+//   peer_merge_kernel (one warp): lane r stores this shard's record into rank r's mailbox, fences, then raises its
+//     flag there; the warp waits until every rank's flag in its OWN mailbox shows the epoch and merges the records
+//     (the same lexicographic min / sums as merge_records_kernel) -- every rank ends up with the global winner.
+//   peer_count_kernel: the shard's colliders ranked before the global winner; the last block to finish exchanges
+//     the shard counts the same way and sums them in rank order (integers in doubles: exact).
+// Slots are double-buffered by epoch parity: a rank can be at most one phase ahead of the slowest one, because it
+// cannot leave a phase before all ranks have written that phase's flags.  Waits are bounded (kPeerSpinCycles);
+// a timeout sets PeerMailbox::error and the host call that follows reports it.
+constexpr int kMaxPeers = 16;
+constexpr long long kPeerSpinCycles = 4000000000LL;             // ~2 s at 1.9 GHz
+struct PeerMailbox {
+    double rec[2][kMaxPeers][4];
+    unsigned long long flag1[2][kMaxPeers];
+    double cnt[2][kMaxPeers];
+    unsigned long long flag2[2][kMaxPeers];
+    int local_count;                    // this rank only: colliders before the winner, accumulated over the blocks
+    unsigned int ticket;                // this rank only: blocks of peer_count_kernel that have finished
+    int error;                          // this rank only: a wait timed out (a peer never arrived)
+    int pad;
+};
+struct PeerTable {
+    PeerMailbox* box[kMaxPeers];
+    int rank, world;
+};
+
+__device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsigned long long epoch) {
+    const volatile unsigned long long* f = flag;
+    const long long t0 = clock64();
+    while (*f != epoch) {
+        if (clock64() - t0 > kPeerSpinCycles) return false;
+        __nanosleep(64);
+    }
+    __threadfence_system();
+    return true;
+}
+
+__global__ void __launch_bounds__(32) peer_merge_kernel(const __grid_constant__ PeerTable T, unsigned long long epoch,
+                                                        const PlanResultDev* __restrict__ res,
+                                                        double* __restrict__ winner, double* __restrict__ totals) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const int lane = threadIdx.x, par = (int)(epoch & 1ULL);
+    PeerMailbox* const mine = T.box[T.rank];
+    if (lane == 0) { mine->local_count = 0; mine->ticket = 0u; }
+    bool ok = true;
+    if (lane < T.world) {
+        const bool has = res->r.winner >= 0;
+        PeerMailbox* const dst = T.box[lane];
+        double* r = dst->rec[par][T.rank];
+        r[0] = has ? res->r.winner_cost : inf;
+        r[1] = has ? (double)res->r.winner : inf;
+        r[2] = (double)res->r.n_infeasible_kinematics;
+        r[3] = (double)res->r.n_feasible;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(&dst->flag1[par][T.rank]) = epoch;
+        ok = peer_wait(&mine->flag1[par][lane], epoch);
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+        if (lane == 0) { mine->error = 1; winner[0] = inf; winner[1] = inf; totals[0] = 0.; totals[1] = 0.; }
+        return;
+    }
+    double bc = inf, bi = inf, kin = 0., feas = 0.;
+    if (lane < T.world) {
+        const volatile double* g = mine->rec[par][lane];
+        bc = g[0]; bi = g[1]; kin = g[2]; feas = g[3];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double oc = __shfl_down_sync(0xffffffffu, bc, off), oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+        kin += __shfl_down_sync(0xffffffffu, kin, off);
+        feas += __shfl_down_sync(0xffffffffu, feas, off);
+    }
+    if (lane == 0) {
+        winner[0] = bc; winner[1] = bi;
+        totals[0] = kin; totals[1] = feas;
+    }
+}
+
+__global__ void __launch_bounds__(256) peer_count_kernel(const __grid_constant__ PeerTable T, unsigned long long epoch,
+                                                         const double* __restrict__ cost, const int* __restrict__ info,
+                                                         int first, int count, const double* __restrict__ winner,
+                                                         double* __restrict__ out) {
+    __shared__ int total;
+    __shared__ unsigned int s_ticket;
+    PeerMailbox* const mine = T.box[T.rank];
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    const double wc = winner[0];
+    const double wi = winner[1];
+    const bool none = !(wi < __longlong_as_double(0x7ff0000000000000LL));
+    int local = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const int k = first + q;
+        if ((info[k] & 0xFF) == ST_COLLISION) {
+            const double c = cost[k];
+            if (none || c < wc || (c == wc && (double)k < wi)) ++local;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&total, local);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (total) atomicAdd(&mine->local_count, total);
+        __threadfence();
+        s_ticket = atomicAdd(&mine->ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1 || threadIdx.x >= 32) return;
+    // ---- last block, first warp: exchange the shard counts -----------------------------------------------------
+    const int lane = threadIdx.x, par = (int)(epoch & 1ULL);
+    bool ok = true;
+    if (lane < T.world) {
+        const double mine_cnt = (double)*reinterpret_cast<volatile int*>(&mine->local_count);
+        PeerMailbox* const dst = T.box[lane];
+        dst->cnt[par][T.rank] = mine_cnt;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(&dst->flag2[par][T.rank]) = epoch;
+        ok = peer_wait(&mine->flag2[par][lane], epoch);
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+        if (lane == 0) { mine->error = 1; out[0] = 0.; }
+        return;
+    }
+    double sum = lane < T.world ? *reinterpret_cast<const volatile double*>(&mine->cnt[par][lane]) : 0.;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
+    if (lane == 0) out[0] = sum;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Cartesian initial state -> curvilinear (lon, lat) initial states, batched.
 //   pycrccosy convert_to_curvilinear_coords as restated in oracle/third_party.py (:188-221): per segment the foot

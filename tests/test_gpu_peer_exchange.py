@@ -1,0 +1,100 @@
+"""Multi-GPU arg-min exchange over peer-mapped memory (rp_peer_*): sharded bundles give the result of the
+unsharded plan.  world = 1 runs in-process; world = 2 runs two processes -- on two GPUs when the box has them, else
+both on cuda:0 (CUDA IPC between processes of one device; the kernels of the two ranks time-slice)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem():
+    from tests.test_gpu_parity import _bundle
+    return _bundle(seed=3, level=3, N=30, s_dot0=11.0)
+
+
+def _reference_result(prob, eng):
+    from commonroad_rp_b200 import _lib
+    r = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
+    return r.winner, r.winner_cost, r.n_infeasible_kinematics, r.n_feasible, r.n_infeasible_collision
+
+
+def test_peer_exchange_world_1():
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200.parallel import PeerExchange
+    prob = _problem()
+    eng = H.engine_for(prob)
+    want = _reference_result(prob, eng)
+    ex = PeerExchange(eng, torch.device("cuda", 0), rank=0, world=1)
+    for _ in range(3):                                      # epochs advance, slots alternate
+        eng.grid_upload(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
+        eng.grid_launch()
+        winner, totals, before = ex.argmin()
+        ex.check()
+        got = (int(winner[1].item()), winner[0].item(), int(totals[0].item()), int(totals[1].item()), int(before.item()))
+        assert got == want
+    ex.close()
+    eng.close()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_dev, out_q):
+    import torch.distributed as dist
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200.parallel import PeerExchange, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = rank % n_dev
+    torch.cuda.set_device(dev)
+    prob = _problem()
+    eng = H.engine_for(prob, device=dev, stream=torch.cuda.current_stream().cuda_stream)
+    n = len(prob["t"]) * len(prob["lon"]) * len(prob["d"])
+    ex = PeerExchange(eng, torch.device("cuda", dev))
+    got = []
+    for cycle in range(3):
+        first, count = shard_range(n, (rank + cycle) % world, world)     # the shards change hands between cycles
+        eng.set_candidate_range(first, count)
+        eng.grid_upload(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
+        eng.grid_launch()
+        winner, totals, before = ex.argmin()
+        ex.check()
+        got.append((int(winner[1].item()), winner[0].item(), int(totals[0].item()), int(totals[1].item()), int(before.item())))
+    out_q.put((rank, got))
+    dist.barrier()
+    ex.close()
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_two_ranks_equal_the_unsharded_plan():
+    import torch.multiprocessing as mp
+    prob = _problem()
+    eng = H.engine_for(prob)
+    want = _reference_result(prob, eng)
+    eng.close()
+    world, n_dev = 2, torch.cuda.device_count()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_dev, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank in range(world):
+        for got in results[rank]:
+            assert got == want, (rank, got, want)

@@ -287,9 +287,13 @@ def test_lazy_collision_mode_is_exact_for_reference_outputs():
     must equal full checking."""
     from commonroad_rp_b200 import _lib
     from tests.test_gpu_parity import _bundle
-    for case in (dict(seed=2, level=2, N=60, s_dot0=12.0), dict(seed=1, level=3, N=20, d0=-0.4), dict(seed=0, level=1, N=20)):
+    cases = (dict(seed=2, level=2, N=60, s_dot0=12.0), dict(seed=1, level=3, N=20, d0=-0.4), dict(seed=0, level=1, N=20))
+    # both schedules: the step-parallel kernel gates whole candidates, the candidate-major kernel stops checking the
+    # remaining poses of a candidate once its partial cost exceeds the bound
+    for case, kernel in [(c, k) for c in cases for k in (_lib.KERNEL_STEP_PARALLEL, _lib.KERNEL_CANDIDATE_MAJOR)]:
         prob = _bundle(**case)
         eng = H.engine_for(prob)
+        eng.set_kernel_policy(kernel)
         full = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
         cost_f, status_f, _, step_f = eng.fetch_candidates()
         lazy = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_LAZY), prob["t"], prob["lon"], prob["d"])
