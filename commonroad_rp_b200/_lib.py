@@ -80,8 +80,6 @@ SIGNATURES = {
     "rp_merge_records_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "rp_peer_create": (C.c_int, [C.c_void_p, C.c_char_p]),
     "rp_peer_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
-    "rp_peer_argmin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "rp_peer_status": (C.c_int, [C.c_void_p]),
     "rp_peer_close": (C.c_int, [C.c_void_p]),
     "rp_fetch_states": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "rp_fetch_candidates": (C.c_int, [C.c_void_p, _dp, _ip, _ip, _ip]),
@@ -325,13 +323,6 @@ class Engine:
         if len(handles) != 64 * int(world):
             raise RpError("peer_open: expected %d handle bytes, got %d" % (64 * int(world), len(handles)))
         self._check(self._lib.rp_peer_open(self._ctx, int(rank), int(world), handles))
-
-    def peer_argmin(self, dev_winner_ptr, dev_totals_ptr, dev_before_ptr):
-        self._check(self._lib.rp_peer_argmin(self._ctx, C.c_void_p(int(dev_winner_ptr)), C.c_void_p(int(dev_totals_ptr)),
-                                             C.c_void_p(int(dev_before_ptr))))
-
-    def peer_status(self):
-        self._check(self._lib.rp_peer_status(self._ctx))
 
     def peer_close(self):
         self._check(self._lib.rp_peer_close(self._ctx))

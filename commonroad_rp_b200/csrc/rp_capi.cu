@@ -146,7 +146,7 @@ struct rp_ctx {
     rp::PeerMailbox* peer_mine = nullptr;           // cudaMalloc'ed, exported through CUDA IPC
     void* peer_opened[rp::kMaxPeers] = {};          // the other ranks' mailboxes (cudaIpcOpenMemHandle)
     rp::PeerTable peer_table{};
-    bool peer_ready = false;
+    bool peer_ready = false, peer_mode_last = false;
     unsigned long long peer_epoch = 0;
 
     static constexpr int kEvRing = 64;
@@ -875,7 +875,10 @@ static int launch_plan(rp_ctx* ctx) {
     // replanning-size bundles: the main launch writes the states of every kept candidate (a few MB at most) and ONE
     // block selects the winner and gathers its states -- 3 launches per cycle instead of 6
     static const int env_small = std::getenv("RP_SMALL_PATH") ? std::atoi(std::getenv("RP_SMALL_PATH")) : 1;
-    const bool small_path = env_small && count > 0 && (long long)n * Np1 <= 262144 && !use_cand_kernel(ctx, count);
+    // sharded bundle with an open peer group: the selection chain ends with the exchange over peer-mapped memory
+    const bool peer_mode = ctx->peer_ready && ctx->range_count >= 0;
+    ctx->peer_mode_last = peer_mode;
+    const bool small_path = env_small && !peer_mode && count > 0 && (long long)n * Np1 <= 262144 && !use_cand_kernel(ctx, count);
     ctx->small_path_last = small_path;
     if (small_path && !ctx->in.want_all_states) {
         if (int rc = ctx->d_states_all.ensure((size_t)n * 14 * Np1 * sizeof(double))) return rc;
@@ -969,12 +972,19 @@ static int launch_plan(rp_ctx* ctx) {
         const int nb = std::max(1, std::min(512, std::min(2 * ctx->num_sms, (count + 255) / 256)));
         rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc);
         rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres);
-        rp::count_before_result_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, dres);
+        if (peer_mode) {
+            const unsigned long long epoch = ++ctx->peer_epoch;
+            rp::peer_merge_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_table, epoch, dres);
+            rp::peer_count_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->peer_table, epoch, ctx->d_cost.as<double>(), ctx->d_info.as<int>(),
+                                                               first, count, dres);
+        } else {
+            rp::count_before_result_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, dres);
+        }
     }
     RP_CUDA(cudaGetLastError());
     cudaEventRecord(ctx->ev[3], ctx->stream);
     // winner's 14 x (N+1) state block; the winner index never leaves the device
-    if (count > 0 && !small_path) {
+    if ((count > 0 || peer_mode) && !small_path) {          // peer mode: the GLOBAL winner, on every rank
         if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one())) return rc;
     }
     if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision) {
@@ -1007,6 +1017,8 @@ int rp_grid_result(rp_ctx* ctx, rp_plan_result* out) {
     RP_CUDA(cudaEventSynchronize(ctx->ev_result));
     ctx->h_states_valid = true;
     *out = static_cast<rp::PlanResultDev*>(ctx->h_result.p)->r;
+    if (ctx->peer_mode_last && static_cast<rp::PlanResultDev*>(ctx->h_result.p)->peer_error)
+        return fail(RP_ERR_STATE, "peer exchange: a wait on another rank timed out (did every rank launch this cycle?)");
     return RP_OK;
 }
 
@@ -1371,37 +1383,6 @@ int rp_peer_open(rp_ctx* ctx, int rank, int world, const unsigned char* handles)
     return RP_OK;
 }
 
-int rp_peer_argmin(rp_ctx* ctx, double* dev_winner2, double* dev_totals2, double* dev_before1) {
-    if (int rc = bind(ctx)) return rc;
-    if (!ctx->peer_ready) return fail(RP_ERR_STATE, "rp_peer_open must precede rp_peer_argmin");
-    if (!dev_winner2 || !dev_totals2 || !dev_before1) return fail(RP_ERR_ARG, "null device pointer");
-    if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
-    const int n = ctx->n_cand;
-    int first = 0, count = n;
-    if (ctx->range_count >= 0) {
-        first = std::min(ctx->range_first, n);
-        count = std::min(ctx->range_count, n - first);
-    }
-    const unsigned long long epoch = ++ctx->peer_epoch;
-    rp::peer_merge_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_table, epoch, ctx->d_result.as<rp::PlanResultDev>(), dev_winner2,
-                                                     dev_totals2);
-    const int blocks = std::max(1, std::min(ctx->num_sms, (count + 255) / 256));
-    rp::peer_count_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->peer_table, epoch, ctx->d_cost.as<double>(), ctx->d_info.as<int>(),
-                                                           first, count, dev_winner2, dev_before1);
-    RP_CUDA(cudaGetLastError());
-    return RP_OK;
-}
-
-int rp_peer_status(rp_ctx* ctx) {
-    if (int rc = bind(ctx)) return rc;
-    if (!ctx->peer_mine) return fail(RP_ERR_STATE, "no peer mailbox");
-    RP_CUDA(cudaStreamSynchronize(ctx->stream));
-    int err = 0;
-    RP_CUDA(cudaMemcpy(&err, &ctx->peer_mine->error, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err) return fail(RP_ERR_STATE, "peer exchange: a wait on another rank timed out");
-    return RP_OK;
-}
-
 int rp_peer_close(rp_ctx* ctx) {
     if (!ctx) return RP_OK;
     cudaSetDevice(ctx->device);
@@ -1421,6 +1402,8 @@ int rp_launches_per_plan(rp_ctx* ctx) {
     if (!ctx) return 0;
     // coeff, fused, argmin partial / merge / count, winner states (+ the dynamic-obstacle rows of the candidate-major kernel)
     if (ctx->small_path_last) return ctx->mode == 0 ? 3 : 2;      // coeff, fused (states of every kept candidate), select
+    if (ctx->peer_mode_last)        // prep, main kernel, argmin partial / merge, peer merge / count, winner states
+        return ctx->mode == 0 ? 7 : 6 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
     // prep (coefficients + dynamic-obstacle rows), main kernel, argmin partial / merge / count, winner states; the list
     // form has no coefficient solve but, for the candidate-major kernel, its own dynamic-obstacle rows launch
     return ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);

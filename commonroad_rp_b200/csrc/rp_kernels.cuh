@@ -21,6 +21,7 @@ namespace rp {
 struct PlanResultDev {
     rp_plan_result r;
     int n_filtered;
+    int peer_error;        // multi-GPU exchange over peer-mapped memory: a wait on another rank timed out
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -461,26 +462,28 @@ __global__ void __launch_bounds__(256) count_before_kernel(const double* __restr
 }
 
 // ---- the same exchange over peer-mapped memory (NVLink / NVSwitch, CUDA IPC) instead of two NCCL collectives ------
-// Every rank owns one PeerMailbox that all ranks of the box have mapped.  Per cycle ("epoch"):
-//   peer_merge_kernel (one warp): lane r stores this shard's record into rank r's mailbox, fences, then raises its
-//     flag there; the warp waits until every rank's flag in its OWN mailbox shows the epoch and merges the records
-//     (the same lexicographic min / sums as merge_records_kernel) -- every rank ends up with the global winner.
-//   peer_count_kernel: the shard's colliders ranked before the global winner; the last block to finish exchanges
-//     the shard counts the same way and sums them in rank order (integers in doubles: exact).
+// Every rank owns one PeerMailbox that all ranks of the box have mapped.  When a peer group is open and the bundle is
+// sharded, the selection chain of rp_grid_launch is argmin_partial -> argmin_merge (the shard's result) ->
+//   peer_merge_kernel (one warp): lane r stores this shard's record (best cost, best index, the counters) into rank
+//     r's mailbox, fences, then raises its flag there; the warp waits until every rank's flag in its OWN mailbox shows
+//     the cycle's epoch and merges the records -- lexicographic min on (cost, index), summed counters -- INTO the
+//     result block: every rank ends up with the global result, and the winner-state launch that follows materialises
+//     the GLOBAL winner on every rank (each rank holds all coefficient systems and tables).
+//   peer_count_kernel: the shard's colliders ranked before the global winner; the last block to finish exchanges the
+//     shard counts the same way and sums them (integers in doubles: exact) into n_infeasible_collision.
 // Slots are double-buffered by epoch parity: a rank can be at most one phase ahead of the slowest one, because it
-// cannot leave a phase before all ranks have written that phase's flags.  Waits are bounded (kPeerSpinCycles);
-// a timeout sets PeerMailbox::error and the host call that follows reports it.
+// cannot leave a phase before all ranks have written that phase's flags.  Waits are bounded (kPeerSpinCycles); a
+// timeout sets PlanResultDev::peer_error, which rp_grid_result reports.
 constexpr int kMaxPeers = 16;
-constexpr long long kPeerSpinCycles = 4000000000LL;             // ~2 s at 1.9 GHz
+constexpr int kPeerRecord = 16;          // cost, index, n_kin, n_feasible, n_collision_total, n_candidates, n_filtered, reasons[8]
+constexpr long long kPeerSpinCycles = 16000000000LL;            // ~8 s at 1.9 GHz
 struct PeerMailbox {
-    double rec[2][kMaxPeers][4];
+    double rec[2][kMaxPeers][kPeerRecord];
     unsigned long long flag1[2][kMaxPeers];
     double cnt[2][kMaxPeers];
     unsigned long long flag2[2][kMaxPeers];
     int local_count;                    // this rank only: colliders before the winner, accumulated over the blocks
     unsigned int ticket;                // this rank only: blocks of peer_count_kernel that have finished
-    int error;                          // this rank only: a wait timed out (a peer never arrived)
-    int pad;
 };
 struct PeerTable {
     PeerMailbox* box[kMaxPeers];
@@ -498,70 +501,93 @@ __device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsign
     return true;
 }
 
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+}
+
 __global__ void __launch_bounds__(32) peer_merge_kernel(const __grid_constant__ PeerTable T, unsigned long long epoch,
-                                                        const PlanResultDev* __restrict__ res,
-                                                        double* __restrict__ winner, double* __restrict__ totals) {
+                                                        PlanResultDev* __restrict__ res) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const int lane = threadIdx.x, par = (int)(epoch & 1ULL);
     PeerMailbox* const mine = T.box[T.rank];
-    if (lane == 0) { mine->local_count = 0; mine->ticket = 0u; }
+    if (lane == 0) { mine->local_count = 0; mine->ticket = 0u; res->peer_error = 0; }
     bool ok = true;
     if (lane < T.world) {
-        const bool has = res->r.winner >= 0;
+        const rp_plan_result r0 = res->r;
+        const bool has = r0.winner >= 0;
         PeerMailbox* const dst = T.box[lane];
         double* r = dst->rec[par][T.rank];
-        r[0] = has ? res->r.winner_cost : inf;
-        r[1] = has ? (double)res->r.winner : inf;
-        r[2] = (double)res->r.n_infeasible_kinematics;
-        r[3] = (double)res->r.n_feasible;
+        r[0] = has ? r0.winner_cost : inf;
+        r[1] = has ? (double)r0.winner : inf;
+        r[2] = (double)r0.n_infeasible_kinematics;
+        r[3] = (double)r0.n_feasible;
+        r[4] = (double)r0.n_collision_total;
+        r[5] = (double)r0.n_candidates;
+        r[6] = (double)res->n_filtered;
+#pragma unroll
+        for (int z = 0; z < 8; ++z) r[7 + z] = (double)r0.reason_counts[z];
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long*>(&dst->flag1[par][T.rank]) = epoch;
         ok = peer_wait(&mine->flag1[par][lane], epoch);
     }
     if (!__all_sync(0xffffffffu, ok)) {
-        if (lane == 0) { mine->error = 1; winner[0] = inf; winner[1] = inf; totals[0] = 0.; totals[1] = 0.; }
+        if (lane == 0) { res->peer_error = 1; res->r.winner = -1; }
         return;
     }
-    double bc = inf, bi = inf, kin = 0., feas = 0.;
+    double bc = inf, bi = inf, sums[kPeerRecord - 2];
+#pragma unroll
+    for (int z = 0; z < kPeerRecord - 2; ++z) sums[z] = 0.;
     if (lane < T.world) {
         const volatile double* g = mine->rec[par][lane];
-        bc = g[0]; bi = g[1]; kin = g[2]; feas = g[3];
+        bc = g[0]; bi = g[1];
+#pragma unroll
+        for (int z = 0; z < kPeerRecord - 3; ++z) sums[z] = g[2 + z];
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const double oc = __shfl_down_sync(0xffffffffu, bc, off), oi = __shfl_down_sync(0xffffffffu, bi, off);
         if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
-        kin += __shfl_down_sync(0xffffffffu, kin, off);
-        feas += __shfl_down_sync(0xffffffffu, feas, off);
     }
+#pragma unroll
+    for (int z = 0; z < kPeerRecord - 3; ++z) sums[z] = warp_sum_f64(sums[z]);
     if (lane == 0) {
-        winner[0] = bc; winner[1] = bi;
-        totals[0] = kin; totals[1] = feas;
+        const bool has_winner = bi < inf;
+        rp_plan_result& r = res->r;
+        r.winner = has_winner ? (int)bi : -1;
+        r.winner_cost = has_winner ? bc : __longlong_as_double(0x7ff8000000000000LL);
+        r.n_infeasible_kinematics = (int)sums[0];
+        r.n_feasible = (int)sums[1];
+        r.n_collision_total = (int)sums[2];
+        r.n_candidates = (int)sums[3];
+        res->n_filtered = (int)sums[4];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) r.reason_counts[z] = (int)sums[5 + z];
+        r.n_infeasible_collision = 0;                  // filled by peer_count_kernel
     }
 }
 
 __global__ void __launch_bounds__(256) peer_count_kernel(const __grid_constant__ PeerTable T, unsigned long long epoch,
                                                          const double* __restrict__ cost, const int* __restrict__ info,
-                                                         int first, int count, const double* __restrict__ winner,
-                                                         double* __restrict__ out) {
+                                                         int first, int count, PlanResultDev* res) {
     __shared__ int total;
     __shared__ unsigned int s_ticket;
     PeerMailbox* const mine = T.box[T.rank];
+    if (res->peer_error) return;                     // (uniform over the grid: set before this launch started)
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
-    const double wc = winner[0];
-    const double wi = winner[1];
-    const bool none = !(wi < __longlong_as_double(0x7ff0000000000000LL));
+    const int wi = res->r.winner;
+    const double wc = res->r.winner_cost;
+    const bool none = wi < 0;
     int local = 0;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
         const int k = first + q;
         if ((info[k] & 0xFF) == ST_COLLISION) {
-            const double c = cost[k];
-            if (none || c < wc || (c == wc && (double)k < wi)) ++local;
+            if (none || lex_less(cost[k], k, wc, wi)) ++local;
         }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+    local = warp_sum(local);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&total, local);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -583,13 +609,12 @@ __global__ void __launch_bounds__(256) peer_count_kernel(const __grid_constant__
         ok = peer_wait(&mine->flag2[par][lane], epoch);
     }
     if (!__all_sync(0xffffffffu, ok)) {
-        if (lane == 0) { mine->error = 1; out[0] = 0.; }
+        if (lane == 0) res->peer_error = 1;
         return;
     }
     double sum = lane < T.world ? *reinterpret_cast<const volatile double*>(&mine->cnt[par][lane]) : 0.;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
-    if (lane == 0) out[0] = sum;
+    sum = warp_sum_f64(sum);
+    if (lane == 0) res->r.n_infeasible_collision = (int)sum;
 }
 
 // ------------------------------------------------------------------------------------------------

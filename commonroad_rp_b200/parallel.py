@@ -52,11 +52,13 @@ def global_argmin(engine, rec: torch.Tensor, world: int, group=None):
 
 class PeerExchange:
     """The arg-min exchange of a sharded bundle over peer-mapped memory (NVLink / NVSwitch) instead of NCCL: every rank
-    owns a small mailbox all ranks of the box map through CUDA IPC; per cycle two kernels store the shard record and
-    the shard's collider count straight into the peers' mailboxes and merge what arrived (rp_peer_* of the C-ABI).
-    ``torch.distributed`` is used once, at set-up, to hand the 64-byte IPC handles around."""
+    owns a small mailbox all ranks of the box map through CUDA IPC.  While the group is open and the engine has a
+    candidate range, ``engine.grid_launch()`` itself ends with two kernels that store the shard's record and collider
+    count straight into the peers' mailboxes and merge what arrived (rp_peer_* of the C-ABI); ``engine.grid_result()``
+    then returns the GLOBAL result on every rank.  ``torch.distributed`` is used once, at set-up, to hand the 64-byte
+    IPC handles around."""
 
-    def __init__(self, engine, device, rank=None, world=None, group=None):
+    def __init__(self, engine, rank=None, world=None, group=None):
         self.engine = engine
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -70,19 +72,6 @@ class PeerExchange:
         engine.peer_open(self.rank, self.world, handles)
         if self.world > 1:
             dist.barrier(group=group)           # every mailbox exists and is zeroed before the first store into it
-        self.winner = torch.empty(2, dtype=torch.float64, device=device)
-        self.totals = torch.empty(2, dtype=torch.float64, device=device)
-        self.before = torch.empty(1, dtype=torch.float64, device=device)
-
-    def argmin(self):
-        """After ``engine.grid_launch()`` on every rank; returns device tensors (winner[2], totals[2],
-        n_collision_before[1]) like ``global_argmin``."""
-        self.engine.peer_argmin(self.winner.data_ptr(), self.totals.data_ptr(), self.before.data_ptr())
-        return self.winner, self.totals, self.before
-
-    def check(self):
-        """Synchronises; raises if a wait on another rank timed out."""
-        self.engine.peer_status()
 
     def close(self):
         self.engine.peer_close()

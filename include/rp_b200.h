@@ -202,20 +202,18 @@ int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double
 
 /* The same exchange over peer-mapped memory instead of NCCL (one process per GPU of ONE box, NVLink / NVSwitch):
  * the reference gathers its workers' results through fork + pickle (reactive_planner.py:1084-1111); here every rank
- * owns a small mailbox that all ranks map through CUDA IPC, and two kernels per cycle store the shard records / shard
- * collider counts straight into the peers' mailboxes and merge them -- no collective call on the data path.
+ * owns a small mailbox that all ranks map through CUDA IPC.  While a peer group is open and a candidate range is set,
+ * rp_grid_launch / rp_plan_grid end with two kernels that store the shard's record and the shard's collider count
+ * straight into the peers' mailboxes and merge what arrived -- no collective call on the data path -- and
+ * rp_grid_result returns the GLOBAL result on every rank (winner, cost, all counters; rp_fetch_states(winner) the
+ * global winner's states).  Every rank must launch the same cycles; a rank that never arrives makes the others'
+ * rp_grid_result fail with RP_ERR_STATE after ~8 s instead of hanging.
  *   rp_peer_create  allocates this rank's mailbox and returns its 64-byte CUDA IPC handle in handle64;
  *   rp_peer_open    maps the mailboxes of all ranks (handles[world][64] in rank order, e.g. from one all-gather at
- *                   set-up); every rank must have returned from rp_peer_create before any rank calls rp_peer_argmin;
- *   rp_peer_argmin  after rp_grid_launch on EVERY rank (same number of calls on every rank): dev_winner2 = global
- *                   [cost, index] (+inf = none), dev_totals2 = [sum n_infeasible_kinematics, sum n_feasible],
- *                   dev_before1 = colliders of all shards ranked before the global winner; asynchronous on the stream;
- *   rp_peer_status  0, or RP_ERR_STATE after a wait on a peer timed out (~2 s; a rank that never arrived);
- *   rp_peer_close   unmaps / frees (also done by rp_ctx_destroy). */
+ *                   set-up); every rank must have returned from rp_peer_create before any rank launches a cycle;
+ *   rp_peer_close   unmaps / frees (also done by rp_ctx_destroy); launches go back to shard-local results. */
 int rp_peer_create(rp_ctx* ctx, unsigned char* handle64);
 int rp_peer_open(rp_ctx* ctx, int rank, int world, const unsigned char* handles);
-int rp_peer_argmin(rp_ctx* ctx, double* dev_winner2, double* dev_totals2, double* dev_before1);
-int rp_peer_status(rp_ctx* ctx);
 int rp_peer_close(rp_ctx* ctx);
 
 /* ---- batches of independent scenarios (reactive_planner.py has no counterpart: one ReactivePlanner per scenario

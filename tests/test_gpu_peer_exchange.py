@@ -21,7 +21,12 @@ def _problem():
 def _reference_result(prob, eng):
     from commonroad_rp_b200 import _lib
     r = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
-    return r.winner, r.winner_cost, r.n_infeasible_kinematics, r.n_feasible, r.n_infeasible_collision
+    return _as_tuple(r), eng.fetch_states(r.winner)
+
+
+def _as_tuple(r):
+    return (r.winner, r.winner_cost, r.n_candidates, r.n_feasible, r.n_infeasible_kinematics, r.n_infeasible_collision,
+            r.n_collision_total, tuple(r.reason_counts))
 
 
 def test_peer_exchange_world_1():
@@ -29,15 +34,14 @@ def test_peer_exchange_world_1():
     from commonroad_rp_b200.parallel import PeerExchange
     prob = _problem()
     eng = H.engine_for(prob)
-    want = _reference_result(prob, eng)
-    ex = PeerExchange(eng, torch.device("cuda", 0), rank=0, world=1)
+    want, want_states = _reference_result(prob, eng)
+    n = want[2]
+    ex = PeerExchange(eng, rank=0, world=1)
+    eng.set_candidate_range(0, n)
     for _ in range(3):                                      # epochs advance, slots alternate
-        eng.grid_upload(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
-        eng.grid_launch()
-        winner, totals, before = ex.argmin()
-        ex.check()
-        got = (int(winner[1].item()), winner[0].item(), int(totals[0].item()), int(totals[1].item()), int(before.item()))
-        assert got == want
+        r = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
+        assert _as_tuple(r) == want
+        assert np.array_equal(eng.fetch_states(r.winner), want_states)
     ex.close()
     eng.close()
 
@@ -50,7 +54,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n_dev, out_q):
+def _worker(rank, world, port, n_dev, kernel, out_q):
     import torch.distributed as dist
     from commonroad_rp_b200 import _lib
     from commonroad_rp_b200.parallel import PeerExchange, shard_range
@@ -60,17 +64,15 @@ def _worker(rank, world, port, n_dev, out_q):
     torch.cuda.set_device(dev)
     prob = _problem()
     eng = H.engine_for(prob, device=dev, stream=torch.cuda.current_stream().cuda_stream)
+    eng.set_kernel_policy(kernel)
     n = len(prob["t"]) * len(prob["lon"]) * len(prob["d"])
-    ex = PeerExchange(eng, torch.device("cuda", dev))
+    ex = PeerExchange(eng)
     got = []
     for cycle in range(3):
         first, count = shard_range(n, (rank + cycle) % world, world)     # the shards change hands between cycles
         eng.set_candidate_range(first, count)
-        eng.grid_upload(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
-        eng.grid_launch()
-        winner, totals, before = ex.argmin()
-        ex.check()
-        got.append((int(winner[1].item()), winner[0].item(), int(totals[0].item()), int(totals[1].item()), int(before.item())))
+        r = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
+        got.append((_as_tuple(r), eng.fetch_states(r.winner)))
     out_q.put((rank, got))
     dist.barrier()
     ex.close()
@@ -78,17 +80,18 @@ def _worker(rank, world, port, n_dev, out_q):
     dist.destroy_process_group()
 
 
-def test_peer_exchange_two_ranks_equal_the_unsharded_plan():
+@pytest.mark.parametrize("kernel", [1, 2])          # _lib.KERNEL_STEP_PARALLEL, _lib.KERNEL_CANDIDATE_MAJOR
+def test_peer_exchange_two_ranks_equal_the_unsharded_plan(kernel):
     import torch.multiprocessing as mp
     prob = _problem()
     eng = H.engine_for(prob)
-    want = _reference_result(prob, eng)
+    want, want_states = _reference_result(prob, eng)
     eng.close()
     world, n_dev = 2, torch.cuda.device_count()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_dev, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_dev, kernel, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=240) for _ in range(world))
@@ -96,5 +99,6 @@ def test_peer_exchange_two_ranks_equal_the_unsharded_plan():
         p.join(timeout=120)
         assert p.exitcode == 0
     for rank in range(world):
-        for got in results[rank]:
+        for got, states in results[rank]:
             assert got == want, (rank, got, want)
+            assert np.array_equal(states, want_states)
