@@ -66,6 +66,8 @@ SIGNATURES = {
     "rp_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "rp_ctx_set_vehicle": (C.c_int, [C.c_void_p, C.POINTER(VehicleParams)]),
     "rp_ctx_set_reference": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
+    "rp_ctx_set_reference_polyline": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_double, C.c_double]),
+    "rp_ctx_get_reference": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "rp_ctx_set_obstacles": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int, _ip, _ip, _dp, C.c_int, _dp, C.c_double]),
     "rp_plan_grid": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _ip, C.c_int, _dp, C.c_int, _dp,
                                C.POINTER(PlanResult)]),
@@ -183,6 +185,27 @@ class Engine:
         n = arrs[0].shape[0]
         assert all(a.shape[0] == n for a in arrs), "reference arrays must have equal length"
         self._check(self._lib.rp_ctx_set_reference(self._ctx, n, *[_p(a, _dp) for a in arrs], float(proj_limit)))
+
+    def set_reference_polyline(self, xy, proj_limit=20.0, eps2=1e-4):
+        """Reference tables derived on the device from the (smoothed, de-duplicated) polyline xy[n][2]."""
+        xy = _f64(xy).reshape(-1, 2)
+        self._check(self._lib.rp_ctx_set_reference_polyline(self._ctx, len(xy), _p(xy, _dp), float(proj_limit),
+                                                            float(eps2)))
+
+    def get_reference(self):
+        """The context's reference tables as a dict with the keys of ``CoordinateSystem.device_tables()``."""
+        n = C.c_int(0)
+        self._check(self._lib.rp_ctx_get_reference(self._ctx, 0, C.byref(n), None, None, None, None, None, None, None))
+        n = n.value
+        a = {k: np.empty(n, dtype=np.float64) for k in ("ref_pos", "ref_theta", "ref_curv", "ref_curv_d", "path_s")}
+        xy, nm = np.empty((n, 2), dtype=np.float64), np.empty((n, 2), dtype=np.float64)
+        m = C.c_int(0)
+        self._check(self._lib.rp_ctx_get_reference(
+            self._ctx, n, C.byref(m), _p(a["ref_pos"], _dp), _p(a["ref_theta"], _dp),
+            _p(a["ref_curv"], _dp), _p(a["ref_curv_d"], _dp), _p(xy, _dp), _p(a["path_s"], _dp),
+            _p(nm, _dp)))
+        a["path_xy"], a["path_normals"] = xy, nm
+        return a
 
     def set_obstacles(self, static_obb=None, dyn_t0=None, dyn_boxes=None, tris=None, cell_size=0.0):
         """static_obb (n,5): cx, cy, theta, half_len, half_wid.  dyn_boxes: list of (K_i,5) arrays."""

@@ -757,6 +757,68 @@ int rp_ctx_set_reference(rp_ctx* ctx, int n, const double* ref_pos, const double
     return RP_OK;
 }
 
+int rp_ctx_set_reference_polyline(rp_ctx* ctx, int n_pts, const double* xy, double proj_limit, double eps2) {
+    if (int rc = bind(ctx)) return rc;
+    if (n_pts < 3 || !xy) return fail(RP_ERR_ARG, "reference polyline needs at least 3 points");
+    if (!(eps2 > 0) || !(proj_limit > 0)) return fail(RP_ERR_ARG, "eps2 and proj_limit must be positive");
+    for (int q = 1; q < n_pts; ++q)
+        if (xy[2 * q] == xy[2 * q - 2] && xy[2 * q + 1] == xy[2 * q - 1])
+            return fail(RP_ERR_ARG, "reference polyline has a repeated vertex");
+    const int n = n_pts + 2;
+    DevBuf d_xy, d_scratch;
+    if (int rc = d_xy.ensure((size_t)n_pts * 2 * sizeof(double))) return rc;
+    if (int rc = d_scratch.ensure((size_t)n * 4 * sizeof(double))) { d_xy.release(); return rc; }
+    if (int rc = ctx->d_ref.ensure((size_t)9 * n * sizeof(double))) { d_xy.release(); d_scratch.release(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(d_xy.p, xy, (size_t)n_pts * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        rp::ref_tables_kernel<<<1, 256, 0, ctx->stream>>>(n_pts, d_xy.as<double>(), eps2, ctx->d_ref.as<double>(), d_scratch.as<double>());
+        e = cudaGetLastError();
+    }
+    double ends[2] = {0., 0.};           // ref_pos[0], ref_pos[n - 1]: the O(1) segment guess needs their span on the host
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[0], ctx->d_ref.as<double>(), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[1], ctx->d_ref.as<double>() + (n - 1), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    d_xy.release();
+    d_scratch.release();
+    if (e != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e));
+    if (!(ends[1] > ends[0])) return fail(RP_ERR_ARG, "degenerate reference polyline");
+    ctx->ref_n = n;
+    ctx->ref_same_s = 1;                 // the frame's arc length IS ref_pos (utils_coordinate_system.py:113)
+    ctx->ref_limit = proj_limit;
+    ctx->ref_inv_step = (double)(n - 1) / (ends[1] - ends[0]);
+    ctx->ps_inv_step = ctx->ref_inv_step;
+    ctx->segs_dirty = true;
+    ++ctx->tables_version;
+    ctx->have_ref = true;
+    return RP_OK;
+}
+
+int rp_ctx_get_reference(rp_ctx* ctx, int capacity, int* n_pts, double* ref_pos, double* ref_theta, double* ref_curv,
+                         double* ref_curv_d, double* path_xy, double* path_s, double* path_normal_xy) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ctx->have_ref) return fail(RP_ERR_STATE, "reference tables not set");
+    if (!n_pts) return fail(RP_ERR_ARG, "null n_pts");
+    const int n = ctx->ref_n;
+    *n_pts = n;
+    if (capacity <= 0) return RP_OK;                       // size query
+    if (capacity < n) return fail(RP_ERR_ARG, "reference buffers too small");
+    std::vector<double> pack((size_t)9 * n);
+    RP_CUDA(cudaMemcpyAsync(pack.data(), ctx->d_ref.p, pack.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
+    // (layout of d_ref: pos | theta | curv | curv_d | px | py | nx | ny | ps; ps is omitted when it equals pos)
+    auto col = [&](int a) { return &pack[(size_t)a * n]; };
+    if (ref_pos) std::memcpy(ref_pos, col(0), n * sizeof(double));
+    if (ref_theta) std::memcpy(ref_theta, col(1), n * sizeof(double));
+    if (ref_curv) std::memcpy(ref_curv, col(2), n * sizeof(double));
+    if (ref_curv_d) std::memcpy(ref_curv_d, col(3), n * sizeof(double));
+    for (int q = 0; q < n; ++q) {
+        if (path_xy) { path_xy[2 * q] = col(4)[q]; path_xy[2 * q + 1] = col(5)[q]; }
+        if (path_normal_xy) { path_normal_xy[2 * q] = col(6)[q]; path_normal_xy[2 * q + 1] = col(7)[q]; }
+    }
+    if (path_s) std::memcpy(path_s, col(8), n * sizeof(double));
+    return RP_OK;
+}
+
 int rp_ctx_set_obstacles(rp_ctx* ctx, int n_static, const double* static_obb, int n_dyn, const int32_t* dyn_t0,
                          const int32_t* dyn_len, const double* dyn_obb, int n_tri, const double* tris,
                          double cell_size) {

@@ -461,6 +461,129 @@ __global__ void __launch_bounds__(256) count_before_kernel(const double* __restr
     if (threadIdx.x == 0) atomicAdd(out, (double)total);
 }
 
+// ------------------------------------------------------------------------------------------------
+// reference polyline -> the nine device tables, on the device (one block per path).
+//   utils_coordinate_system.py:113-118 (ref_pos / ref_curv / ref_theta / ref_curv_d from the frame's stored polyline)
+//   and the frame construction of pycrccosy as restated in oracle/third_party.py:126-145 (two extension vertices eps2
+//   beyond the ends, per-vertex pseudo-normals from the normalised chords p[i+1] - p[i-1]);
+//   commonroad_dc.geometry.util compute_pathlength / orientation / curvature_from_polyline (third_party.py:44-70);
+//   np.gradient with non-uniform spacing (second-order interior, first-order edges), np.cumsum and np.unwrap in
+//   numpy's operation order (the two scans are sequential in one thread; everything else is one thread per vertex).
+// in:  xy[n_in][2] (smoothed, de-duplicated reference), out: 9 SoA arrays of n = n_in + 2 doubles
+//      [pos | theta | curv | curv_d | px | py | nx | ny | ps], scratch: 4 arrays of n doubles.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double np_gradient_at(const double* __restrict__ f, const double* __restrict__ x, int n, int i,
+                                                 bool uniform) {
+    if (i == 0) return (f[1] - f[0]) / (x[1] - x[0]);
+    if (i == n - 1) return (f[n - 1] - f[n - 2]) / (x[n - 1] - x[n - 2]);
+    const double dx1 = x[i] - x[i - 1], dx2 = x[i + 1] - x[i];
+    if (uniform) return (f[i + 1] - f[i - 1]) / (2. * dx1);
+    const double a = -(dx2) / (dx1 * (dx1 + dx2));
+    const double b = (dx2 - dx1) / (dx1 * dx2);
+    const double c = dx1 / (dx2 * (dx1 + dx2));
+    return a * f[i - 1] + b * f[i] + c * f[i + 1];
+}
+
+__global__ void __launch_bounds__(256) ref_tables_kernel(int n_in, const double* __restrict__ xy, double eps2,
+                                                         double* __restrict__ out, double* __restrict__ scratch) {
+    const int n = n_in + 2;
+    double* pos = out;
+    double* theta = out + n;
+    double* curv = out + 2 * (size_t)n;
+    double* curv_d = out + 3 * (size_t)n;
+    double* px = out + 4 * (size_t)n;
+    double* py = out + 5 * (size_t)n;
+    double* nx = out + 6 * (size_t)n;
+    double* ny = out + 7 * (size_t)n;
+    double* ps = out + 8 * (size_t)n;
+    double* xd = scratch;
+    double* yd = scratch + n;
+    double* seg = scratch + 2 * (size_t)n;
+    double* th_raw = scratch + 3 * (size_t)n;
+    __shared__ int s_uniform;
+    const int tid = threadIdx.x, T = blockDim.x;
+    // ---- the frame's stored polyline: the input plus one vertex eps2 beyond each end --------------------------
+    for (int i = tid; i < n; i += T) {
+        double x, y;
+        if (i == 0) {
+            const double hx = xy[2] - xy[0], hy = xy[3] - xy[1];
+            const double nrm = sqrt(hx * hx + hy * hy);
+            x = xy[0] - eps2 * hx / nrm; y = xy[1] - eps2 * hy / nrm;
+        } else if (i == n - 1) {
+            const double* e = xy + 2 * (size_t)(n_in - 1);
+            const double tx = e[0] - e[-2], ty = e[1] - e[-1];
+            const double nrm = sqrt(tx * tx + ty * ty);
+            x = e[0] + eps2 * tx / nrm; y = e[1] + eps2 * ty / nrm;
+        } else {
+            x = xy[2 * (size_t)(i - 1)]; y = xy[2 * (size_t)(i - 1) + 1];
+        }
+        px[i] = x; py[i] = y;
+    }
+    __syncthreads();
+    // ---- segment lengths, raw orientations, pseudo-normals ----------------------------------------------------
+    for (int i = tid; i < n; i += T) {
+        if (i < n - 1) {
+            const double dx = px[i + 1] - px[i], dy = py[i + 1] - py[i];
+            seg[i] = sqrt(dx * dx + dy * dy);
+            th_raw[i] = atan2(dy, dx);
+        }
+        const int lo = i == 0 ? 0 : i - 1, hi = i == n - 1 ? n - 1 : i + 1;
+        const double cx = px[hi] - px[lo], cy = py[hi] - py[lo];
+        const double nrm = sqrt(cx * cx + cy * cy);
+        nx[i] = -(cy / nrm);
+        ny[i] = cx / nrm;
+    }
+    __syncthreads();
+    // ---- np.cumsum / np.unwrap: sequential, numpy's order -------------------------------------------------------
+    if (tid == 0) {
+        double acc = 0.;
+        pos[0] = 0.;
+        for (int i = 0; i < n - 1; ++i) {
+            acc = i == 0 ? seg[0] : acc + seg[i];
+            pos[i + 1] = acc;
+        }
+        int uni = 1;
+        const double d0 = pos[1] - pos[0];
+        for (int i = 1; i < n - 1 && uni; ++i) uni = (pos[i + 1] - pos[i]) == d0;
+        s_uniform = uni;
+    }
+    if (tid == 32) {
+        th_raw[n - 1] = th_raw[n - 2];                      // compute_orientation_from_polyline repeats the last value
+        const double pi = 3.141592653589793, two_pi = 6.283185307179586;
+        theta[0] = th_raw[0];
+        double corr = 0.;
+        bool first = true;
+        for (int i = 1; i < n; ++i) {
+            const double dd = th_raw[i] - th_raw[i - 1];
+            // np.mod(dd + pi, 2 pi) - pi with Python's sign convention (result has the sign of the divisor)
+            double m = fmod(dd + pi, two_pi);
+            if (m != 0. && m < 0.) m += two_pi;
+            double ddmod = m - pi;
+            if (ddmod == -pi && dd > 0.) ddmod = pi;
+            double ph = ddmod - dd;
+            if (fabs(dd) < pi) ph = 0.;
+            corr = first ? ph : corr + ph;
+            first = false;
+            theta[i] = th_raw[i] + corr;
+        }
+    }
+    __syncthreads();
+    const bool uniform = s_uniform != 0;
+    for (int i = tid; i < n; i += T) {
+        ps[i] = pos[i];
+        xd[i] = np_gradient_at(px, pos, n, i, uniform);
+        yd[i] = np_gradient_at(py, pos, n, i, uniform);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += T) {
+        const double xdd = np_gradient_at(xd, pos, n, i, uniform);
+        const double ydd = np_gradient_at(yd, pos, n, i, uniform);
+        curv[i] = (xd[i] * ydd - xdd * yd[i]) / pow(xd[i] * xd[i] + yd[i] * yd[i], 1.5);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += T) curv_d[i] = np_gradient_at(curv, pos, n, i, uniform);
+}
+
 // ---- the same exchange over peer-mapped memory (NVLink / NVSwitch, CUDA IPC) instead of two NCCL collectives ------
 // Every rank owns one PeerMailbox that all ranks of the box have mapped.  When a peer group is open and the bundle is
 // sharded, the selection chain of rp_grid_launch is argmin_partial -> argmin_merge (the shard's result) ->

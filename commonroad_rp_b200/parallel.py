@@ -93,16 +93,22 @@ class ScenarioBatch:
         self.engines = []
         self._batch = None
 
-    def add_scenario(self, vehicle, coordinate_system, collision_checker):
-        """vehicle: VehicleConfiguration; coordinate_system: CoordinateSystem; collision_checker:
+    def add_scenario(self, vehicle, coordinate_system, collision_checker, proj_limit=20.0):
+        """vehicle: VehicleConfiguration; coordinate_system: CoordinateSystem, or the (smoothed, de-duplicated)
+        reference polyline as an (n, 2) array -- its tables are then derived on the device (rp_ctx_set_reference_polyline:
+        what CoordinateSystem.__init__ computes with numpy, utils_coordinate_system.py:101-118); collision_checker:
         collision.CollisionChecker.  Returns the scenario's index."""
+        import numpy as np
         from commonroad_rp_b200._lib import Engine
         eng = Engine(self.device, self.stream)
         eng.set_vehicle(vehicle.length, vehicle.width, vehicle.wb_rear_axle, vehicle.wheelbase, vehicle.a_max,
                         vehicle.v_switch, vehicle.delta_max, vehicle.v_delta_max, vehicle.kappa_max)
-        tb = coordinate_system.device_tables()
-        eng.set_reference(tb["ref_pos"], tb["ref_theta"], tb["ref_curv"], tb["ref_curv_d"], tb["path_xy"],
-                          tb["path_s"], tb["path_normals"], tb["proj_limit"])
+        if isinstance(coordinate_system, np.ndarray):
+            eng.set_reference_polyline(coordinate_system, proj_limit)
+        else:
+            tb = coordinate_system.device_tables()
+            eng.set_reference(tb["ref_pos"], tb["ref_theta"], tb["ref_curv"], tb["ref_curv_d"], tb["path_xy"],
+                              tb["path_s"], tb["path_normals"], tb["proj_limit"])
         collision_checker.upload(eng)
         self.engines.append(eng)
         if self._batch is not None:

@@ -141,6 +141,18 @@ int rp_ctx_set_reference(rp_ctx* ctx, int n_pts, const double* ref_pos, const do
                          const double* ref_curv, const double* ref_curv_d, const double* path_xy,
                          const double* path_s, const double* path_normal_xy, double proj_limit);
 
+/* The same tables DERIVED ON THE DEVICE from the (smoothed, de-duplicated) reference polyline xy[n_pts][2] -- what
+ * CoordinateSystem.__init__ does on the host (utility/utils_coordinate_system.py:101-118: frame construction with one
+ * extension vertex eps2 beyond each end and per-vertex pseudo-normals, then compute_pathlength / orientation (+ np.unwrap)
+ * / curvature_from_polyline and np.gradient for the curvature rate, in numpy's operation order).  The context then
+ * holds n_pts + 2 table rows.  For batches of thousands of scenarios the per-scenario host numpy pass is the set-up
+ * cost this replaces. */
+int rp_ctx_set_reference_polyline(rp_ctx* ctx, int n_pts, const double* xy, double proj_limit, double eps2);
+/* read the context's reference tables back (any of the array pointers may be NULL); capacity = rows the buffers hold;
+ * capacity <= 0: only *n_pts is written (size query) */
+int rp_ctx_get_reference(rp_ctx* ctx, int capacity, int* n_pts, double* ref_pos, double* ref_theta, double* ref_curv,
+                         double* ref_curv_d, double* path_xy, double* path_s, double* path_normal_xy);
+
 /* pycrcc.CollisionChecker content (reactive_planner.py:234-251):
  *   static_obb[n_static][5]   = cx, cy, theta, half_length, half_width   (static obstacles + OBB road boundary)
  *   dynamic obstacle o: time indices dyn_t0[o] .. dyn_t0[o]+dyn_len[o]-1, boxes dyn_obb[sum(len)][5] concatenated

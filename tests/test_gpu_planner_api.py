@@ -425,3 +425,49 @@ def test_merge_records_kernel_matches_host_merge():
         w, t = merge_records(gathered)
         assert torch.equal(w.cpu(), winner.cpu()) and torch.equal(t.cpu(), totals.cpu())
     eng.close()
+
+
+def test_reference_tables_derived_on_the_device():
+    """rp_ctx_set_reference_polyline derives the nine reference tables from the smoothed polyline on
+    the device (CoordinateSystem.__init__, utils_coordinate_system.py:101-118 + the frame construction); they equal the
+    oracle's numpy derivation, and a bundle planned on them gives the same verdicts as on uploaded tables."""
+    from tests.test_gpu_parity import _bundle
+    u = np.linspace(0.0, 1.0, 160)
+    paths = {
+        "sine": synthetic.sine_path(20.0, 40.0, 300),
+        "straight": synthetic.sine_path(0.0, 40.0, 120),
+        # a left-hand loop of 1.5 turns: the heading crosses +-pi twice (np.unwrap)
+        "loop": np.stack([(30.0 + 25.0 * u) * np.cos(3.0 * np.pi * u), (30.0 + 25.0 * u) * np.sin(3.0 * np.pi * u)], axis=1),
+    }
+    prob = _bundle(seed=2, level=2, N=30, s_dot0=12.0)
+    eng = H.engine_for(prob)
+    for name, raw in paths.items():
+        ref, ccosy, _ = O.reference_tables(raw)
+        polyline = np.asarray(ccosy["path"])[1:-1]                   # the smoothed reference without its extension vertices
+        eng.set_reference_polyline(polyline, ccosy["limit"], 1e-4)
+        got = eng.get_reference()
+        assert len(got["ref_pos"]) == len(polyline) + 2
+        for key, want in (("ref_pos", ref["ref_pos"]), ("ref_theta", ref["ref_theta"]), ("ref_curv", ref["ref_curv"]),
+                          ("ref_curv_d", ref["ref_curv_d"]), ("path_xy", ccosy["path"]), ("path_s", ccosy["S"]),
+                          ("path_normals", ccosy["normals"])):
+            # the curvature rate at the two extension vertices divides a curvature difference by eps2 = 1e-4: a last-bit
+            # difference in pow() / the vertex norm is amplified 1e4 times there (interior rows agree to ~1e-13)
+            tol = 1e-8 if key == "ref_curv_d" else 1e-9
+            assert H.rel_err(want, got[key]) < tol, (name, key, H.rel_err(want, got[key]))
+            if key == "ref_curv_d":
+                assert H.rel_err(want[2:-2], got[key][2:-2]) < 1e-10, (name, key)
+        if name == "loop":
+            assert np.ptp(ref["ref_theta"]) > 2.0 * np.pi               # the case really unwraps
+    eng.close()
+    # the same bundle on uploaded tables and on device-derived tables
+    eng_a, eng_b = H.engine_for(prob), H.engine_for(prob)
+    eng_b.set_reference_polyline(np.asarray(prob["ccosy"]["path"])[1:-1], prob["ccosy"]["limit"], 1e-4)
+    ra = H.run_engine_grid(eng_a, prob, want_all_states=False)
+    rb = H.run_engine_grid(eng_b, prob, want_all_states=False)
+    assert ra["winner"] == rb["winner"] and np.array_equal(ra["status"], rb["status"])
+    assert np.array_equal(ra["reason"], rb["reason"]) and np.array_equal(ra["step"], rb["step"])
+    kin = ra["status"] != 1
+    assert H.rel_err(ra["cost"][kin], rb["cost"][kin]) < 1e-9
+    assert H.rel_err(ra["winner_states"], rb["winner_states"]) < 1e-9
+    eng_a.close()
+    eng_b.close()
