@@ -385,7 +385,7 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 // candidate and write nothing.
 // ONE_GROUP: the host guarantees G == 1 for every chunk (grid form, n_d a multiple of 32, aligned shard): the group
 // arithmetic folds away at compile time.
-template <int BLOCK, bool ONE_GROUP>
+template <int BLOCK, bool ONE_GROUP, bool LAZY, int PF>
 __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k, bool valid,
                                            double* __restrict__ acc, double* __restrict__ s_vmid,
                                            double* __restrict__ rows) {
@@ -462,7 +462,8 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     // cost term is a square, so the running sum is a lower bound of the final cost; once it exceeds the best
     // collision-free cost any candidate has published so far, this candidate can be neither the winner nor a collider
     // ranked before it, and its remaining poses are not checked (status RP_FEASIBLE_UNCHECKED unless it already hit)
-    const bool lazy = in.check_collision == 2 && costed && P.best_bits != nullptr;
+    // LAZY is a compile-time switch: the gate's running sum and flag cost the full-checking path ~3 % if merely branched over
+    const bool lazy = LAZY && in.check_collision == 2 && costed && P.best_bits != nullptr;
     double cost_lb = 0.;
     bool gated = false;
     // values of the current / last polynomial step (the extension reads them after step tl - 1)
@@ -536,7 +537,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             double q1 = 0., q2 = 0.;
             if (use_v) { const double t1 = 5 * (c_v - in.desired_speed); q1 = t1 * t1; }
             if (use_s) { const double t2 = 0.25 * (in.desired_s - c_s); q2 = t2 * t2; }
-            if (lazy) {
+            if (LAZY && lazy) {
                 cost_lb += (q0 + q3) + (q4 + (q1 + q2));
                 if ((i & 7) == 7 && !gated) {
                     const unsigned long long best = *reinterpret_cast<volatile unsigned long long*>(P.best_bits);
@@ -566,14 +567,14 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         }
 
         // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), speculative ---------------------
-        if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u && !gated) {
+        if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u && !(LAZY && gated)) {
             const double ecx = px + P.wb_rear * cn;
             const double ecy = py + P.wb_rear * sn;
             const int tidx = in.x0_time_step + i * in.factor;
             const bool hit = (P.dyn_rows ? dyn_collides_f32(O, P.dyn_rows + (size_t)i * O.n_dyn, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid,
                                                                i < tl ? heavy_dynmask : 0xffffffffu)
                                          : dyn_collides_global(O, tidx, ecx, ecy, cn, sn, P.half_len, P.half_wid, P.r_ego)) ||
-                             static_collides(O, ecx, ecy, cn, sn, P.half_len, P.half_wid);
+                             static_collides<PF>(O, ecx, ecy, cn, sn, P.half_len, P.half_wid);
             if (hit) col = (unsigned)i;
         }
         if (i == Np1 - 1) {                                   // park the end values for the terminal terms
@@ -629,7 +630,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         if (col != NONE) {
             status = ST_COLLISION;
             step = (int)col;
-        } else if (lazy) {
+        } else if (LAZY && lazy) {
             if (gated) {
                 status = ST_UNCHECKED;
             } else if (cost == cost) {                         // collision-free over the whole horizon: tighten the bound
@@ -656,7 +657,7 @@ __device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs,
 }
 
 // ---- one bundle: persistent grid, warps draw chunks of 32 candidates from a counter -----------------------------
-template <int BLOCK, bool ONE_GROUP>
+template <int BLOCK, bool ONE_GROUP, bool LAZY = false>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
@@ -701,7 +702,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         if (g >= P.n_groups) break;
         bool valid;
         const int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
-        cand_march<BLOCK, ONE_GROUP>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, ONE_GROUP, LAZY, 2>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 
@@ -755,7 +756,7 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
         }
         bool valid;
         const int k = chunk_candidate(P.segs, P.n_segs, g - B.chunk_prefix[lo], lane, valid);
-        cand_march<BLOCK, false>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, false, false, 1>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 
