@@ -470,7 +470,6 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
     double cn = 1., sn = 0.;                       // cos / sin of th_gl
     double ax = 0., ay = 0.;                       // np.cumsum of the extension increments
-    double res_a = 0., res_d = 0., res_th = 0., res_v = 0., res_s = 0.;   // np.sum results
 
     for (int i = 0; i < Np1; ++i) {
         double px, py;                             // rear-axle position of this step
@@ -556,12 +555,21 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
                     if (use_s) ap[row_s * 8 * BLOCK] += q2;
                 }
             } else {
+                // remainder of np.sum (or the plain loop of n < 8): the running results live in slot 0 of each row --
+                // five doubles that would otherwise sit in registers through the whole march
                 if (Np1 >= 8 && i == n8) {
-                    res_a = tree(0); res_d = tree(1); res_th = tree(2);
-                    if (use_v) res_v = tree(row_v);
-                    if (use_s) res_s = tree(row_s);
+                    const double ta = tree(0), td = tree(1), tt = tree(2);
+                    acc[0] = ta; acc[8 * BLOCK] = td; acc[16 * BLOCK] = tt;
+                    if (use_v) { const double tv = tree(row_v); acc[row_v * 8 * BLOCK] = tv; }
+                    if (use_s) { const double ts = tree(row_s); acc[row_s * 8 * BLOCK] = ts; }
+                } else if (Np1 < 8 && i == 0) {
+                    acc[0] = 0.; acc[8 * BLOCK] = 0.; acc[16 * BLOCK] = 0.;
+                    if (use_v) acc[row_v * 8 * BLOCK] = 0.;
+                    if (use_s) acc[row_s * 8 * BLOCK] = 0.;
                 }
-                res_a += q0; res_d += q3; res_th += q4; res_v += q1; res_s += q2;
+                acc[0] += q0; acc[8 * BLOCK] += q3; acc[16 * BLOCK] += q4;
+                if (use_v) acc[row_v * 8 * BLOCK] += q1;
+                if (use_s) acc[row_s * 8 * BLOCK] += q2;
             }
             if (i == mid) s_vmid[0] = c_v;                   // v[int(len(v) / 2)]
         }
@@ -602,10 +610,15 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     } else {
         status = ST_FEASIBLE;
         if (costed) {
+            double res_a, res_d, res_th, res_v = 0., res_s = 0.;     // np.sum results
             if (Np1 >= 8 && n8 == Np1) {                       // no remainder: the tree was not taken in the loop
                 res_a = tree(0); res_d = tree(1); res_th = tree(2);
                 if (use_v) res_v = tree(row_v);
                 if (use_s) res_s = tree(row_s);
+            } else {
+                res_a = acc[0]; res_d = acc[8 * BLOCK]; res_th = acc[16 * BLOCK];
+                if (use_v) res_v = acc[row_v * 8 * BLOCK];
+                if (use_s) res_s = acc[row_s * 8 * BLOCK];
             }
             double costs = 0.0;
             costs += res_a;
