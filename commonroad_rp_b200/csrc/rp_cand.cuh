@@ -385,7 +385,7 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 // candidate and write nothing.
 // ONE_GROUP: the host guarantees G == 1 for every chunk (grid form, n_d a multiple of 32, aligned shard): the group
 // arithmetic folds away at compile time.
-template <int BLOCK, bool ONE_GROUP, bool LAZY, int PF>
+template <int BLOCK, bool ONE_GROUP, int PF>
 __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k, bool valid,
                                            double* __restrict__ acc, double* __restrict__ s_vmid,
                                            double* __restrict__ rows) {
@@ -458,14 +458,10 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
 
     unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
     const double cs0 = low_vel ? __ldg(I.cs) : 0.;
-    // lazy collision mode (check_collision == 2, the reference's cost-ordered pass :1031-1063 in parallel form): every
-    // cost term is a square, so the running sum is a lower bound of the final cost; once it exceeds the best
-    // collision-free cost any candidate has published so far, this candidate can be neither the winner nor a collider
-    // ranked before it, and its remaining poses are not checked (status RP_FEASIBLE_UNCHECKED unless it already hit)
-    // LAZY is a compile-time switch: the gate's running sum and flag cost the full-checking path ~3 % if merely branched over
-    const bool lazy = LAZY && in.check_collision == 2 && costed && P.best_bits != nullptr;
-    double cost_lb = 0.;
-    bool gated = false;
+    // (check_collision == 2, the reference's lazy pass: this schedule checks every feasible candidate while it marches.
+    // A gate on the running cost -- skip the remaining poses once the partial cost exceeds the best collision-free
+    // cost published so far -- was measured: the first wave of candidates finishes before any bound exists, and the
+    // running sum costs the march more than the skipped checks of the second wave save: 0.360 vs 0.353 ms.)
     // values of the current / last polynomial step (the extension reads them after step tl - 1)
     double x = 0., y = 0., th_gl = 0., v = 0., a = 0., kappa = 0., s = 0., sv = 0., d = 0., dv = 0., th_cl = 0.;
     double cn = 1., sn = 0.;                       // cos / sin of th_gl
@@ -536,13 +532,6 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             double q1 = 0., q2 = 0.;
             if (use_v) { const double t1 = 5 * (c_v - in.desired_speed); q1 = t1 * t1; }
             if (use_s) { const double t2 = 0.25 * (in.desired_s - c_s); q2 = t2 * t2; }
-            if (LAZY && lazy) {
-                cost_lb += (q0 + q3) + (q4 + (q1 + q2));
-                if ((i & 7) == 7 && !gated) {
-                    const unsigned long long best = *reinterpret_cast<volatile unsigned long long*>(P.best_bits);
-                    gated = cost_lb * (1.0 - 1.0e-9) > __longlong_as_double((long long)best);
-                }
-            }
             if (Np1 >= 8 && i < n8) {
                 double* ap = acc + (size_t)(i & 7) * BLOCK;
                 if (i < 8) {
@@ -575,7 +564,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         }
 
         // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), speculative ---------------------
-        if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u && !(LAZY && gated)) {
+        if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u) {
             const double ecx = px + P.wb_rear * cn;
             const double ecy = py + P.wb_rear * sn;
             const int tidx = in.x0_time_step + i * in.factor;
@@ -640,17 +629,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             }
             cost = costs;
         }
-        if (col != NONE) {
-            status = ST_COLLISION;
-            step = (int)col;
-        } else if (LAZY && lazy) {
-            if (gated) {
-                status = ST_UNCHECKED;
-            } else if (cost == cost) {                         // collision-free over the whole horizon: tighten the bound
-                const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);     // costs are >= 0
-                if (cb < *reinterpret_cast<volatile unsigned long long*>(P.best_bits)) atomicMin(P.best_bits, cb);
-            }
-        }
+        if (col != NONE) { status = ST_COLLISION; step = (int)col; }
     }
     P.info[k] = pack_info(status, reason, step);
     if (P.cost) P.cost[k] = cost;
@@ -670,7 +649,7 @@ __device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs,
 }
 
 // ---- one bundle: persistent grid, warps draw chunks of 32 candidates from a counter -----------------------------
-template <int BLOCK, bool ONE_GROUP, bool LAZY = false>
+template <int BLOCK, bool ONE_GROUP>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
@@ -715,7 +694,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         if (g >= P.n_groups) break;
         bool valid;
         const int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
-        cand_march<BLOCK, ONE_GROUP, LAZY, 2>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, ONE_GROUP, 2>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 
@@ -769,7 +748,7 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
         }
         bool valid;
         const int k = chunk_candidate(P.segs, P.n_segs, g - B.chunk_prefix[lo], lane, valid);
-        cand_march<BLOCK, false, false, 1>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, false, 1>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 

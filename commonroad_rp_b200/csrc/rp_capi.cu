@@ -458,10 +458,8 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     static int g_granted[64] = {};
     int& granted = g_granted[ctx->device & 63];
     if ((int)G.smem > granted) {
-        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         granted = (int)G.smem;
     }
     int occ = 0;
@@ -1018,14 +1016,8 @@ static int launch_plan(rp_ctx* ctx) {
                 P.dyn_rows = ctx->d_dyn_rows.as<float4>();
             }
             const Geometry& G = ctx->main_geom;
-            const bool lazy_gate = ctx->in.check_collision == 2 && ctx->in.cost_kind != RP_COST_NONE;     // compile-time variant
-            if (ctx->main_one_group) {
-                if (lazy_gate) rp::cand_kernel<RP_CAND_THREADS, true, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
-                else rp::cand_kernel<RP_CAND_THREADS, true, false><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
-            } else {
-                if (lazy_gate) rp::cand_kernel<RP_CAND_THREADS, false, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
-                else rp::cand_kernel<RP_CAND_THREADS, false, false><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
-            }
+            if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+            else rp::cand_kernel<RP_CAND_THREADS, false><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
             RP_CUDA(cudaGetLastError());
         } else if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
         ctx->states_all_valid = ctx->in.want_all_states != 0;

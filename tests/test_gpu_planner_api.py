@@ -288,8 +288,8 @@ def test_lazy_collision_mode_is_exact_for_reference_outputs():
     from commonroad_rp_b200 import _lib
     from tests.test_gpu_parity import _bundle
     cases = (dict(seed=2, level=2, N=60, s_dot0=12.0), dict(seed=1, level=3, N=20, d0=-0.4), dict(seed=0, level=1, N=20))
-    # both schedules: the step-parallel kernel gates whole candidates, the candidate-major kernel stops checking the
-    # remaining poses of a candidate once its partial cost exceeds the bound
+    # both schedules: the step-parallel kernel gates whole candidates, the candidate-major kernel checks every feasible
+    # candidate while it marches (no RP_FEASIBLE_UNCHECKED there) -- the reference outputs are the same
     for case, kernel in [(c, k) for c in cases for k in (_lib.KERNEL_STEP_PARALLEL, _lib.KERNEL_CANDIDATE_MAJOR)]:
         prob = _bundle(**case)
         eng = H.engine_for(prob)
