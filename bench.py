@@ -479,7 +479,18 @@ def main():
         eng.grid_launch()
         w_, t_, b_ = global_argmin(eng, rec, world)
         nccl_ref = w_.tolist() + t_.tolist() + b_.tolist()
-        peer = PeerExchange(eng)
+        # (a box without CUDA IPC / peer access between its GPUs: every rank falls back to the NCCL form together)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            peer = PeerExchange(eng)
+        except Exception as exc:                                      # noqa: BLE001
+            print("[bench] peer-memory exchange unavailable on rank %d: %s" % (rank, exc), file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if peer is not None:
+                peer.close()
+            peer = None
     fp64_peak = eng.measure_fp64_peak()
     # clocks are sampled from the warm-up to the end of the e2e loop (the same kernels throughout);
     # nvidia-smi needs a few hundred ms to start, so keep the GPU under this load until it reports

@@ -59,19 +59,40 @@ class PeerExchange:
     IPC handles around."""
 
     def __init__(self, engine, rank=None, world=None, group=None):
+        from commonroad_rp_b200._lib import RpError
         self.engine = engine
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
-        handle = engine.peer_create()
+        # every step that can fail on one rank is followed by an exchange of its outcome, so that the ranks either all
+        # open the group or all raise (a rank that raised alone would leave the others waiting in a collective)
+        try:
+            handle, err = engine.peer_create(), None
+        except RpError as exc:
+            handle, err = None, str(exc)
         if self.world > 1:
             every = [None] * self.world
             dist.all_gather_object(every, handle, group=group)          # set-up only; any backend
-            handles = b"".join(every)
         else:
-            handles = handle
-        engine.peer_open(self.rank, self.world, handles)
+            every = [handle]
+        if any(h is None for h in every):
+            engine.peer_close()
+            raise RpError("peer mailbox could not be created on rank(s) %s%s"
+                          % ([r for r, h in enumerate(every) if h is None], ": " + err if err else ""))
+        try:
+            engine.peer_open(self.rank, self.world, b"".join(every))
+            err = None
+        except RpError as exc:
+            err = str(exc)
         if self.world > 1:
-            dist.barrier(group=group)           # every mailbox exists and is zeroed before the first store into it
+            # (doubles as the barrier: every mailbox exists and is zeroed before the first store into it)
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+        else:
+            oks = [err is None]
+        if not all(oks):
+            engine.peer_close()
+            raise RpError("peer mailboxes could not be mapped on rank(s) %s%s"
+                          % ([r for r, ok in enumerate(oks) if not ok], ": " + err if err else ""))
 
     def close(self):
         self.engine.peer_close()

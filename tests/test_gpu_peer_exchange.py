@@ -102,3 +102,60 @@ def test_peer_exchange_two_ranks_equal_the_unsharded_plan(kernel):
         for got, states in results[rank]:
             assert got == want, (rank, got, want)
             assert np.array_equal(states, want_states)
+
+
+def _worker_timeout(rank, world, port, n_dev, out_q):
+    import time
+    import torch.distributed as dist
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200.parallel import PeerExchange
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = rank % n_dev
+    torch.cuda.set_device(dev)
+    prob = _problem()
+    eng = H.engine_for(prob, device=dev, stream=torch.cuda.current_stream().cuda_stream)
+    n = len(prob["t"]) * len(prob["lon"]) * len(prob["d"])
+    ex = PeerExchange(eng)
+    if rank == 0:                                            # rank 1 never launches its shard
+        eng.set_candidate_range(0, n // 2)
+        t0 = time.perf_counter()
+        try:
+            eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
+            outcome = "no error"
+        except _lib.RpError as exc:
+            outcome = str(exc)
+        waited = time.perf_counter() - t0
+        ex.close()
+        eng.set_candidate_range(0, -1)                       # the context keeps working afterwards
+        r = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
+        out_q.put((outcome, waited, _as_tuple(r)))
+    dist.barrier()
+    if rank != 0:
+        ex.close()
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_missing_rank_times_out_instead_of_hanging():
+    """A peer group of two where the second rank never launches: the first rank's result call fails with an error after
+    the bounded wait (~8 s) -- the kernel does not spin forever -- and the context keeps working afterwards."""
+    import torch.multiprocessing as mp
+    prob = _problem()
+    eng = H.engine_for(prob)
+    want, _ = _reference_result(prob, eng)
+    eng.close()
+    world, n_dev = 2, torch.cuda.device_count()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_timeout, args=(r, world, port, n_dev, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outcome, waited, after = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert "timed out" in outcome, outcome
+    assert waited < 60.0
+    assert after == want
