@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -415,6 +416,8 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
     // the attribute is a per-function maximum: only ever raise it (main and index launches share the kernel)
     // (per device, shared by all contexts of the process: the attribute belongs to the function, not the context)
     static int g_granted[64][2] = {};
+    static std::mutex g_granted_mutex;                      // distinct contexts may plan from distinct threads
+    std::lock_guard<std::mutex> granted_lock(g_granted_mutex);
     int& granted = g_granted[ctx->device & 63][G.big ? 1 : 0];
     if ((int)G.smem > granted) {
         if (G.big) RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
@@ -456,6 +459,8 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     if (G.stage_ref) G.smem += ref_bytes;
     if (G.smem > budget) return fail(RP_ERR_ARG, "candidate-major kernel: shared-memory need exceeds the SM");
     static int g_granted[64] = {};
+    static std::mutex g_granted_mutex;
+    std::lock_guard<std::mutex> granted_lock(g_granted_mutex);
     int& granted = g_granted[ctx->device & 63];
     if ((int)G.smem > granted) {
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
@@ -765,6 +770,7 @@ int rp_ctx_set_reference_polyline(rp_ctx* ctx, int n_pts, const double* xy, doub
         if (xy[2 * q] == xy[2 * q - 2] && xy[2 * q + 1] == xy[2 * q - 1])
             return fail(RP_ERR_ARG, "reference polyline has a repeated vertex");
     const int n = n_pts + 2;
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));           // launches in flight may still read the old tables
     DevBuf d_xy, d_scratch;
     if (int rc = d_xy.ensure((size_t)n_pts * 2 * sizeof(double))) return rc;
     if (int rc = d_scratch.ensure((size_t)n * 4 * sizeof(double))) { d_xy.release(); return rc; }
