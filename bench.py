@@ -526,8 +526,24 @@ def main():
     if world > 1:
         dist.barrier()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    # per-kernel durations (stage_ms, roofline.kernel_ms): the same K steps once more with the library's stage events
+    # on -- five CUDA event records per launch, which cost the cycle ~15 us and are therefore off (the library's
+    # default) in the timed region above
+    eng.set_stage_timing(True)
+    ev_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        ev_starts[k].record(stream)
+        step_device()
+        ev_stops[k].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    step_ms_events = [s.elapsed_time(e) for s, e in zip(ev_starts, ev_stops)]
     fused_ms = [eng.stage_ms(back)[1] for back in range(min(args.steps, 64))]
     stage_ms = np.mean([eng.stage_ms(back) for back in range(min(args.steps, 64))], axis=0)
+    eng.set_stage_timing(False)
     total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -572,6 +588,7 @@ def main():
     full = None
     if args.full_states and world == 1:
         fin = make_inputs(work, want_all_states=True)
+        eng.set_stage_timing(True)
         eng.grid_upload(fin, work["t"], work["lon"], work["d"])
         for _ in range(3):
             eng.grid_launch()
@@ -583,6 +600,7 @@ def main():
             torch.cuda.synchronize()
             ms.append(eng.stage_ms(0)[1])
         full = float(np.mean(ms))
+        eng.set_stage_timing(False)
 
     # lazy collision pass (the reference's own semantics, reactive_planner.py:1031-1063): same winner and
     # counters, candidates costlier than the best collision-free one so far are not visited
@@ -630,8 +648,10 @@ def main():
                    "mode": "select-only (winner states materialised), fmad off for parity"},
         "cand_timesteps_per_sec": value * Np1,
         "p50_cycle_ms": float(np.median(step_ms)),
+        "ms_per_step_with_stage_events": float(np.mean(step_ms_events)),
         "stage_ms": {"coeff": float(stage_ms[0]), "fused": float(stage_ms[1]), "argmin": float(stage_ms[2]),
-                     "winner_states": float(stage_ms[3])},
+                     "winner_states": float(stage_ms[3]),
+                     "note": "second pass of the same K steps with the library's stage events on (ms_per_step_with_stage_events)"},
         "winner": int(res.winner), "n_feasible": int(res.n_feasible),
         "exchange": None if world == 1 else {"kind": "peer" if peer is not None else "nccl", "equals_nccl": exchange_check},
         "e2e": {"value": n_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),

@@ -4,6 +4,7 @@ There is deliberately NO CPU fallback: if the CUDA library is missing or a call 
 exception is raised.  ``Engine`` is a thin owner of one ``rp_ctx`` (one CUDA device + stream).
 """
 import ctypes as C
+import functools
 import os
 
 import numpy as np
@@ -102,6 +103,7 @@ SIGNATURES = {
     "rp_selftest_divide": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip]),
     "rp_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rp_stage_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "rp_ctx_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "rp_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "rp_launches_per_plan": (C.c_int, [C.c_void_p]),
     "rp_last_main_kernel": (C.c_int, [C.c_void_p]),
@@ -138,9 +140,15 @@ def _p(a, t):
     return a.ctypes.data_as(t) if a is not None and a.size else C.cast(None, t)
 
 
-def traj_len_of(delta_tau, dt):
-    """len(np.arange(0, np.round(delta_tau + dt, 5), dt))  (reactive_planner.py:733, :748)."""
+@functools.lru_cache(maxsize=8192)
+def _traj_len_cached(delta_tau, dt):
     return len(np.arange(0, np.round(delta_tau + dt, 5), dt))
+
+
+def traj_len_of(delta_tau, dt):
+    """len(np.arange(0, np.round(delta_tau + dt, 5), dt))  (reactive_planner.py:733, :748).  The sampled horizons of a
+    level repeat every replanning cycle, so the numpy expression is evaluated once per distinct (delta_tau, dt)."""
+    return _traj_len_cached(float(delta_tau), float(dt))
 
 
 class Engine:
@@ -394,6 +402,10 @@ class Engine:
         self._check(self._lib.rp_collide_poses(self._ctx, pose.shape[0], _p(pose, _dp), _p(ti, _ip),
                                                float(half_length), float(half_width), _p(hit, _bp)))
         return hit.astype(bool)
+
+    def set_stage_timing(self, on=True):
+        """CUDA-event stage timing of the launches that follow (``stage_ms``); off by default."""
+        self._check(self._lib.rp_ctx_set_stage_timing(self._ctx, int(bool(on))))
 
     def last_stage_ms(self):
         ms = (C.c_float * 4)()

@@ -153,6 +153,9 @@ struct rp_ctx {
     static constexpr int kEvRing = 64;
     cudaEvent_t ev_ring[kEvRing][5] = {};
     cudaEvent_t* ev = ev_ring[0];       // event set of the launch in flight
+    bool ev_recorded[kEvRing] = {};     // the launch that last used the slot ran with stage timing on
+    bool stage_timing = false;          // rp_ctx_set_stage_timing: five event records per launch cost a replanning-size
+                                        // cycle 16 of its 82 us, so they are opt-in
     long long n_launches = 0;
 };
 
@@ -952,7 +955,8 @@ static int launch_plan(rp_ctx* ctx) {
         if (int rc = ctx->d_states_all.ensure((size_t)n * 14 * Np1 * sizeof(double))) return rc;
     }
     ctx->ev = ctx->ev_ring[ctx->n_launches % rp_ctx::kEvRing];
-    cudaEventRecord(ctx->ev[0], ctx->stream);
+    ctx->ev_recorded[ctx->n_launches % rp_ctx::kEvRing] = ctx->stage_timing;
+    if (ctx->stage_timing) cudaEventRecord(ctx->ev[0], ctx->stream);
     // dynamic-obstacle rows of the candidate-major kernel ride along with the coefficient solve (one launch)
     const bool cand_main = count > 0 && use_cand_kernel(ctx, count);
     const int dyn_total = (cand_main && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? Np1 * ctx->obs.n_dyn : 0;
@@ -992,7 +996,7 @@ static int launch_plan(rp_ctx* ctx) {
         RP_CUDA(cudaGetLastError());
         dyn_rows_done = true;
     }
-    cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (ctx->stage_timing) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (count > 0) {
         if (int rc = prepare_main_geometry(ctx, first, count)) return rc;
         PlanParams P{};
@@ -1028,7 +1032,7 @@ static int launch_plan(rp_ctx* ctx) {
         } else if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
         ctx->states_all_valid = ctx->in.want_all_states != 0;
     }
-    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (ctx->stage_timing) cudaEventRecord(ctx->ev[2], ctx->stream);
     rp::PlanResultDev* dres = ctx->d_result.as<rp::PlanResultDev>();
     if (small_path) {
         rp::select_small_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count,
@@ -1050,7 +1054,7 @@ static int launch_plan(rp_ctx* ctx) {
         }
     }
     RP_CUDA(cudaGetLastError());
-    cudaEventRecord(ctx->ev[3], ctx->stream);
+    if (ctx->stage_timing) cudaEventRecord(ctx->ev[3], ctx->stream);
     // winner's 14 x (N+1) state block; the winner index never leaves the device
     if ((count > 0 || peer_mode) && !small_path) {          // peer mode: the GLOBAL winner, on every rank
         if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one())) return rc;
@@ -1062,7 +1066,7 @@ static int launch_plan(rp_ctx* ctx) {
                                                                 dres, ctx->d_info.as<int>());
         RP_CUDA(cudaGetLastError());
     }
-    cudaEventRecord(ctx->ev[4], ctx->stream);
+    if (ctx->stage_timing) cudaEventRecord(ctx->ev[4], ctx->stream);
     ++ctx->n_launches;
     ctx->have_plan = true;
     return RP_OK;
@@ -1325,13 +1329,21 @@ int rp_stage_ms(rp_ctx* ctx, int back, float* ms4) {
     if (int rc = bind(ctx)) return rc;
     if (!ms4) return fail(RP_ERR_ARG, "null output");
     if (back < 0 || back >= rp_ctx::kEvRing || back >= ctx->n_launches) return fail(RP_ERR_STATE, "no such launch in the event ring");
-    cudaEvent_t* ev = ctx->ev_ring[(ctx->n_launches - 1 - back) % rp_ctx::kEvRing];
+    const int slot = (int)((ctx->n_launches - 1 - back) % rp_ctx::kEvRing);
+    if (!ctx->ev_recorded[slot]) return fail(RP_ERR_STATE, "that launch ran without stage timing (rp_ctx_set_stage_timing)");
+    cudaEvent_t* ev = ctx->ev_ring[slot];
     RP_CUDA(cudaEventSynchronize(ev[4]));
     for (int q = 0; q < 4; ++q) RP_CUDA(cudaEventElapsedTime(&ms4[q], ev[q], ev[q + 1]));
     return RP_OK;
 }
 
 int rp_last_stage_ms(rp_ctx* ctx, float* ms4) { return rp_stage_ms(ctx, 0, ms4); }
+
+int rp_ctx_set_stage_timing(rp_ctx* ctx, int on) {
+    if (!ctx) return fail(RP_ERR_ARG, "null context");
+    ctx->stage_timing = on != 0;
+    return RP_OK;
+}
 
 // FP64 pipe peak by a DFMA micro-benchmark (the roofline denominator SURVEY 8d asks to measure)
 namespace {

@@ -583,24 +583,36 @@ class ReactivePlanner(object):
         yaw_rate = np.empty(n)
         yaw_rate[0] = self.x_0.yaw_rate
         yaw_rate[1:] = (theta[1:] - theta[:-1]) / self.dt
-        pos_cart = np.stack([ca.x, ca.y], axis=1)
-        pos_curv = np.stack([cu.s, cu.d], axis=1)
         t0 = self.x_0.time_step
-        th_l, v_l, a_l = theta.tolist(), ca.v.tolist(), ca.a.tolist()
+        if getattr(trajectory, "_rows_untouched", None) is not None and trajectory._rows_untouched():
+            # device result: the 14 rows are views of one block -- one transpose / tolist per group instead of one per row
+            block = trajectory._state_block[0]
+            rows = block.tolist()
+            th_l, v_l, a_l, kap_l = rows[2], rows[3], rows[4], rows[5]
+            pos_cart = np.ascontiguousarray(block[0:2].T)
+            pos_curv = np.ascontiguousarray(block[7:9].T)
+            lon_list = [list(r) for r in zip(rows[7], rows[10], rows[11])]
+            lat_list = [list(r) for r in zip(rows[8], rows[12], rows[13])]
+        else:
+            pos_cart = np.stack([ca.x, ca.y], axis=1)
+            pos_curv = np.stack([cu.s, cu.d], axis=1)
+            th_l, v_l, a_l, kap_l = theta.tolist(), ca.v.tolist(), ca.a.tolist(), ca.kappa.tolist()
+            lon_list = np.stack([cu.s, cu.s_dot, cu.s_ddot], axis=1).tolist()
+            lat_list = np.stack([cu.d, cu.d_dot, cu.d_ddot], axis=1).tolist()
         if HAVE_COMMONROAD_IO:
             cart_list = [ReactivePlannerState(time_step=t0 + factor * i, position=pos_cart[i], orientation=th, velocity=vel,
                                               acceleration=acc, yaw_rate=yr, steering_angle=st)
                          for i, (th, vel, acc, yr, st) in enumerate(zip(th_l, v_l, a_l, yaw_rate.tolist(), steering.tolist()))]
             cl_list = [CustomState(time_step=t0 + factor * i, position=pos_curv[i], velocity=vel, acceleration=acc,
                                    orientation=th, yaw_rate=kap)
-                       for i, (vel, acc, th, kap) in enumerate(zip(v_l, a_l, th_l, ca.kappa.tolist()))]
+                       for i, (vel, acc, th, kap) in enumerate(zip(v_l, a_l, th_l, kap_l))]
         else:
             # the package's own plain state classes: fill the instance dictionaries directly (42 objects per cycle)
             cart_list, cl_list = [], []
             new_rs, new_cs = ReactivePlannerState.__new__, CustomState.__new__
             p_cart, p_curv = list(pos_cart), list(pos_curv)
             for i, (th, vel, acc, yr, st, kap) in enumerate(zip(th_l, v_l, a_l, yaw_rate.tolist(), steering.tolist(),
-                                                                 ca.kappa.tolist())):
+                                                                 kap_l)):
                 ts = t0 + factor * i
                 o = new_rs(ReactivePlannerState)
                 o.__dict__ = {"time_step": ts, "position": p_cart[i], "steering_angle": st, "velocity": vel, "orientation": th,
@@ -610,8 +622,6 @@ class ReactivePlanner(object):
                 c.__dict__ = {"time_step": ts, "position": p_curv[i], "velocity": vel, "acceleration": acc, "orientation": th,
                               "yaw_rate": kap}
                 cl_list.append(c)
-        lon_list = np.stack([cu.s, cu.s_dot, cu.s_ddot], axis=1).tolist()
-        lat_list = np.stack([cu.d, cu.d_dot, cu.d_ddot], axis=1).tolist()
         cart_traj = shift_orientation(Trajectory(self.x_0.time_step, cart_list),
                                       interval_start=self.x_0.orientation - np.pi,
                                       interval_end=self.x_0.orientation + np.pi)

@@ -181,16 +181,28 @@ class TrajectorySample(Sample):
 
     def _set_states(self, st: np.ndarray):
         n = st.shape[1]
-        self._cartesian = CartesianSample(st[0], st[1], st[2], st[3], st[4], st[5], st[6], current_time_step=n)
-        self._curvilinear = CurviLinearSample(st[7], st[8], st[9], current_time_step=n, ss=st[10], sss=st[11],
-                                              dd=st[12], ddd=st[13])
+        r = tuple(st)                     # the 14 row views handed to the two samples
+        self._state_block = (st, r)       # output packing reads the block whole while the samples still hold these rows
+        self._cartesian = CartesianSample(r[0], r[1], r[2], r[3], r[4], r[5], r[6], current_time_step=n)
+        self._curvilinear = CurviLinearSample(r[7], r[8], r[9], current_time_step=n, ss=r[10], sss=r[11],
+                                              dd=r[12], ddd=r[13])
+
+    def _rows_untouched(self) -> bool:
+        """True while cartesian / curvilinear still hold exactly the row views of the device block."""
+        blk = getattr(self, "_state_block", None)
+        if blk is None or self._cartesian is None or self._curvilinear is None:
+            return False
+        r, ca, cu = blk[1], self._cartesian, self._curvilinear
+        return (ca.x is r[0] and ca.y is r[1] and ca.theta is r[2] and ca.v is r[3] and ca.a is r[4] and ca.kappa is r[5]
+                and cu.s is r[7] and cu.d is r[8] and cu.s_dot is r[10] and cu.s_ddot is r[11] and cu.d_dot is r[12]
+                and cu.d_ddot is r[13])
 
     def __deepcopy__(self, memo):
         import copy
         self._materialise_if_available()
         new = TrajectorySample.__new__(TrajectorySample)
         for k, v in self.__dict__.items():
-            setattr(new, k, None if k == "_backing" else copy.deepcopy(v, memo))
+            setattr(new, k, None if k in ("_backing", "_state_block") else copy.deepcopy(v, memo))
         if self._backing is not None:
             new._cost = self.cost
             new._label = self.feasibility_label

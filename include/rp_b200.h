@@ -295,6 +295,9 @@ int rp_selftest_divide(rp_ctx* ctx, int n, const double* a, const double* b, dou
 int rp_last_stage_ms(rp_ctx* ctx, float* ms4);
 /* the same for the launch `back` launches ago (0 = last; the context keeps the last 64) */
 int rp_stage_ms(rp_ctx* ctx, int back, float* ms4);
+/* stage timing is opt-in (off by default): the five event records per launch cost a replanning-size cycle 16 of its
+ * 82 us.  rp_last_stage_ms / rp_stage_ms fail with RP_ERR_STATE for launches made while it was off. */
+int rp_ctx_set_stage_timing(rp_ctx* ctx, int on);
 /* measurement aid: FP64 FMA peak of the device in TFLOP/s from a DFMA micro-benchmark (roofline denominator) */
 int rp_measure_fp64_peak(rp_ctx* ctx, double* tflops);
 /* which kernel evaluated the main launch of the last plan: RP_KERNEL_STEP_PARALLEL or RP_KERNEL_CANDIDATE_MAJOR */

@@ -23,6 +23,7 @@ def main():
     torch.cuda.set_stream(stream)
     work = bench.dense_workload(1)
     eng = bench.make_engine(work, 0, stream.cuda_stream)
+    eng.set_stage_timing(True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     out = {}
     for mode in (1, 2, 0):

@@ -22,6 +22,7 @@ def main():
     torch.cuda.set_stream(stream)
     work = bench.dense_workload(1)
     eng = bench.make_engine(work, 0, stream.cuda_stream)
+    eng.set_stage_timing(True)
     t_all = np.array(work["t"])
     for mode, t_one in [(m, t) for m in (1, 0) for t in (t_all.min(), 4.5, t_all.max())]:
         inp = bench.make_inputs(work, check_collision=mode)
