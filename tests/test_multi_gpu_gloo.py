@@ -71,3 +71,72 @@ def test_two_rank_argmin_equals_single_rank():
     assert totals == [float((status == 1).sum()), float((status != 1).sum())]
     idx = np.arange(n)
     assert before == float(((status == 2) & ((cost < cost[k]) | ((cost == cost[k]) & (idx < k)))).sum())
+
+
+# ---- PeerExchange set-up is collective-safe: the ranks either all open the group or all raise ------------------
+class _FakeEngine:
+    """Stands in for _lib.Engine on a box without a GPU: records the calls, fails where told to."""
+
+    def __init__(self, fail_create=False, fail_open=False):
+        self.fail_create, self.fail_open = fail_create, fail_open
+        self.opened = None
+        self.closed = 0
+
+    def peer_create(self):
+        from commonroad_rp_b200._lib import RpError
+        if self.fail_create:
+            raise RpError("no mailbox")
+        return bytes(range(64))
+
+    def peer_open(self, rank, world, handles):
+        from commonroad_rp_b200._lib import RpError
+        if self.fail_open:
+            raise RpError("cannot map")
+        self.opened = (rank, world, len(handles))
+
+    def peer_close(self):
+        self.closed += 1
+
+
+def _peer_worker(rank, world, port, mode, out_q):
+    from commonroad_rp_b200._lib import RpError
+    from commonroad_rp_b200.parallel import PeerExchange
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeEngine(fail_create=(mode == "create" and rank == 1), fail_open=(mode == "open" and rank == 0))
+    try:
+        PeerExchange(eng)
+        outcome = "opened"
+    except RpError as exc:
+        outcome = "raised: %s" % exc
+    out_q.put((rank, outcome, eng.opened, eng.closed))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_peer_setup(mode):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return got
+
+
+def test_peer_exchange_setup_opens_on_every_rank():
+    got = _run_peer_setup("ok")
+    assert [g[1] for g in got] == ["opened", "opened"]
+    assert [g[2] for g in got] == [(0, 2, 128), (1, 2, 128)]
+
+
+def test_peer_exchange_setup_fails_on_every_rank_together():
+    for mode, word in (("create", "created"), ("open", "mapped")):
+        got = _run_peer_setup(mode)
+        assert all(g[1].startswith("raised") and word in g[1] for g in got), got
+        assert all(g[3] >= 1 for g in got)                 # every rank released what it had
