@@ -1466,6 +1466,7 @@ int rp_peer_open(rp_ctx* ctx, int rank, int world, const unsigned char* handles)
 int rp_peer_close(rp_ctx* ctx) {
     if (!ctx) return RP_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->peer_mine) cudaStreamSynchronize(ctx->stream);        // a cycle in flight still stores into the mailboxes
     for (int r = 0; r < rp::kMaxPeers; ++r)
         if (ctx->peer_opened[r]) { cudaIpcCloseMemHandle(ctx->peer_opened[r]); ctx->peer_opened[r] = nullptr; }
     if (ctx->peer_mine) { cudaFree(ctx->peer_mine); ctx->peer_mine = nullptr; }
