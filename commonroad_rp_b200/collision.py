@@ -239,24 +239,107 @@ def create_collision_object(obstacle):
     return tvo
 
 
-def create_road_boundary_obstacle(scenario, width: float = 0.1):
-    """Road boundary as thin boxes along every lanelet border that has no adjacent lanelet (the
-    'obb_rectangles' flavour of commonroad_dc.boundary.create_road_boundary_obstacle; reference call
-    site reactive_planner.py:247).  Returns (None, ShapeGroup)."""
-    sg = ShapeGroup()
-    for ll in scenario.lanelet_network.lanelets:
-        for side, adj in (("left_vertices", "adj_left"), ("right_vertices", "adj_right")):
+def _points_in_polygon(pts, poly):
+    """Even-odd rule for points pts[n][2] against one polygon poly[m][2] (vectorised ray casting)."""
+    x, y = pts[:, 0][:, None], pts[:, 1][:, None]
+    x1, y1 = poly[:, 0][None, :], poly[:, 1][None, :]
+    x2, y2 = np.roll(poly[:, 0], -1)[None, :], np.roll(poly[:, 1], -1)[None, :]
+    straddle = (y1 > y) != (y2 > y)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xi = (x2 - x1) * (y - y1) / (y2 - y1) + x1
+    return (np.count_nonzero(straddle & (x < xi), axis=1) & 1).astype(bool)
+
+
+def road_boundary_segments(lanelets, probe: float = 0.1):
+    """The border segments of a lanelet network that separate drivable area from off-road area.
+
+    ``lanelets``: objects with ``left_vertices`` / ``right_vertices`` ((n, 2) arrays, driving direction) and
+    ``adj_left`` / ``adj_right`` (None = no laterally adjacent lanelet).  A border without a lateral neighbour is not
+    yet a road boundary: at intersections, merges and forks such borders run through OTHER lanelets' drivable area.  A
+    segment is kept iff the point ``probe`` metres beyond it -- on the side away from its own lanelet -- lies in no
+    lanelet's polygon, i.e. iff the road really ends there (the criterion commonroad_dc's boundary construction
+    implements by triangulating the complement of the union of all lanelet polygons; reference call site
+    reactive_planner.py:247).  Returns an (m, 2, 2) array of segments with the off-road side to the LEFT of p -> q.
+    """
+    polys = [np.vstack([np.asarray(ll.left_vertices, dtype=np.float64),
+                        np.asarray(ll.right_vertices, dtype=np.float64)[::-1]]) for ll in lanelets]
+    segs = []
+    for ll in lanelets:
+        for side, adj, sign in (("left_vertices", "adj_left", 1.0), ("right_vertices", "adj_right", -1.0)):
             if getattr(ll, adj, None) is not None:
                 continue
             pts = np.asarray(getattr(ll, side), dtype=np.float64)
-            for p, q in zip(pts[:-1], pts[1:]):
-                seg = q - p
-                length = float(np.hypot(seg[0], seg[1]))
-                if length <= 0.0:
-                    continue
-                mid = 0.5 * (p + q)
-                sg.add_shape(RectOBB(0.5 * length, 0.5 * width, math.atan2(seg[1], seg[0]), mid[0], mid[1]))
+            p, q = pts[:-1], pts[1:]
+            if sign < 0:
+                p, q = q, p                     # off-road side to the left of p -> q
+            keep = np.hypot(*(q - p).T) > 0.0
+            segs.append(np.stack([p[keep], q[keep]], axis=1))
+    if not segs:
+        return np.zeros((0, 2, 2))
+    segs = np.concatenate(segs, axis=0)
+    d = segs[:, 1] - segs[:, 0]
+    normal = np.stack([-d[:, 1], d[:, 0]], axis=1) / np.hypot(d[:, 0], d[:, 1])[:, None]
+    probes = 0.5 * (segs[:, 0] + segs[:, 1]) + probe * normal
+    inside = np.zeros(len(segs), dtype=bool)
+    for poly in polys:
+        inside |= _points_in_polygon(probes, poly)
+    return segs[~inside]
+
+
+def create_road_boundary_obstacle(scenario, method: str = "obb_rectangles", width: float = 0.1, band: float = 1.0):
+    """Road boundary of a CommonRoad scenario as a static shape group (reference call site reactive_planner.py:247,
+    ``commonroad_dc.boundary.boundary.create_road_boundary_obstacle``).  Returns (None, ShapeGroup).
+
+    commonroad_dc's default method triangulates the off-road area inside an enlarged bounding box with the ``triangle``
+    package, which is not installable here (parity unpinned); both methods below are built from the
+    true road boundary (``road_boundary_segments``: borders whose far side is off-road) and give the same collision
+    verdict for every pose that touches the road's edge:
+
+    ``obb_rectangles``   one thin box (``width``) per boundary segment -- commonroad_dc's method of the same name;
+    ``triangulation``    two triangles per boundary segment covering a band of ``band`` metres on the off-road side
+                         (triangles reaching into another lanelet's drivable area are dropped).
+    """
+    lanelets = list(scenario.lanelet_network.lanelets)
+    segs = road_boundary_segments(lanelets)
+    sg = ShapeGroup()
+    if method == "obb_rectangles":
+        for p, q in segs:
+            seg = q - p
+            mid = 0.5 * (p + q)
+            sg.add_shape(RectOBB(0.5 * float(np.hypot(seg[0], seg[1])), 0.5 * width, math.atan2(seg[1], seg[0]), mid[0], mid[1]))
+    elif method == "triangulation":
+        for tri in boundary_band_triangles(lanelets, segs, band):
+            sg.add_shape(Triangle(*tri))
+    else:
+        raise ValueError("<create_road_boundary_obstacle>: unknown method %r" % (method,))
     return None, sg
+
+
+def boundary_band_triangles(lanelets, segs, band: float = 1.0):
+    """(m, 6) triangles: per boundary segment p -> q (off-road side to the left) the quad p, q, q + band n, p + band n
+    split along its diagonal; a triangle with a vertex or its centroid inside a lanelet polygon (the band of one road
+    reaching into another road across a narrow gore) is dropped."""
+    if len(segs) == 0:
+        return np.zeros((0, 6))
+    p, q = segs[:, 0], segs[:, 1]
+    d = q - p
+    n = np.stack([-d[:, 1], d[:, 0]], axis=1) / np.hypot(d[:, 0], d[:, 1])[:, None]
+    a, b = p + band * n, q + band * n
+    tris = np.concatenate([np.stack([p, q, b], axis=1), np.stack([p, b, a], axis=1)], axis=0)      # (2m, 3, 2)
+    # probe points: the centroid and the two vertices off the segment, pulled slightly towards the centroid
+    cen = tris.mean(axis=1)
+    probes = np.concatenate([cen[:, None, :], cen[:, None, :] + 0.98 * (tris - cen[:, None, :])], axis=1)   # (2m, 4, 2)
+    on_edge = np.zeros(probes.shape[:2], dtype=bool)
+    on_edge[:, 1] = True                                  # vertex 0 is p (on the border itself)
+    on_edge[:len(p), 2] = True                            # first family: vertex 1 is q
+    bad = np.zeros(len(tris), dtype=bool)
+    polys = [np.vstack([np.asarray(ll.left_vertices, dtype=np.float64),
+                        np.asarray(ll.right_vertices, dtype=np.float64)[::-1]]) for ll in lanelets]
+    flat = probes.reshape(-1, 2)
+    for poly in polys:
+        inside = _points_in_polygon(flat, poly).reshape(probes.shape[:2])
+        bad |= (inside & ~on_edge).any(axis=1)
+    return tris[~bad].reshape(-1, 6)
 
 
 def checker_from_arrays(static_boxes=(), dyn_t0=(), dyn_states=(), dyn_lw=(), boundary_boxes=(), boundary_tris=()):

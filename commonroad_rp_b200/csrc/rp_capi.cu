@@ -150,6 +150,10 @@ struct rp_ctx {
     bool peer_ready = false, peer_mode_last = false;
     unsigned long long peer_epoch = 0;
 
+    // a batch (rp_batch_*) may run this context's tables on ANOTHER stream: the end-of-launch event of the last batch
+    // cycle that read them (owned by the batch); table updates wait for it before overwriting device memory
+    cudaEvent_t ext_busy = nullptr;
+
     static constexpr int kEvRing = 64;
     cudaEvent_t ev_ring[kEvRing][5] = {};
     cudaEvent_t* ev = ev_ring[0];       // event set of the launch in flight
@@ -170,8 +174,15 @@ int bind(rp_ctx* ctx) {
 }
 
 // ---- static broad-phase grid ------------------------------------------------------------------
+int wait_external_readers(rp_ctx* ctx) {
+    if (ctx->ext_busy) RP_CUDA(cudaEventSynchronize(ctx->ext_busy));
+    return RP_OK;
+}
+
 int build_obstacle_tables(rp_ctx* ctx) {
     if (!ctx->have_vehicle) return fail(RP_ERR_STATE, "rp_ctx_set_vehicle must precede planning");
+    if (int rc = wait_external_readers(ctx)) return rc;      // a batch cycle in flight on another stream still reads the old tables
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));
     const double hl = 0.5 * ctx->veh.length, hw = 0.5 * ctx->veh.width;
     const double r_ego = std::sqrt(hl * hl + hw * hw);
     const double infl = r_ego * (1.0 + 1e-9) + 1e-6;
@@ -379,12 +390,8 @@ int build_obstacle_tables(rp_ctx* ctx) {
 int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G) {
     if (Np1 < 2 || Np1 > 1024) return fail(RP_ERR_ARG, "N + 1 must be in [2, 1024]");
     G.big = Np1 > 256;
-    static const int env_threads = std::getenv("RP_THREADS") ? std::atoi(std::getenv("RP_THREADS")) : 0;
-    static const int env_stage_ref = std::getenv("RP_STAGE_REF") ? std::atoi(std::getenv("RP_STAGE_REF")) : 1;
-    static const int env_stage_dyn = std::getenv("RP_STAGE_DYN") ? std::atoi(std::getenv("RP_STAGE_DYN")) : 1;
-    static const int env_scratch_kb = std::getenv("RP_SCRATCH_KB") ? std::atoi(std::getenv("RP_SCRATCH_KB")) : 48;
+    constexpr int kScratchKb = 48;                       // per-block cap of the per-slot scratch (measured, profiles/README.md)
     G.threads = G.big ? ((Np1 + 31) / 32) * 32 : 256;
-    if (!G.big && env_threads >= 32 && env_threads <= 256 && env_threads >= Np1) G.threads = (env_threads / 32) * 32;
     const size_t per_slot = (size_t)(rp::kRows * Np1 + rp::kSlotExtra) * sizeof(double) +
                             (size_t)(Np1 + rp::F_WORDS) * sizeof(int);
     // Shared-memory policy (measured on B200, profiles/README.md): three resident blocks per SM beat two,
@@ -396,9 +403,9 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
     const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
     const size_t dyn_bytes = (size_t)Np1 * ctx->obs.n_dyn * rp::kDynFields * sizeof(double);
     const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 64;
-    G.stage_dyn = (env_stage_dyn && ctx->obs.n_dyn > 0 && dyn_bytes <= 32 * 1024 && fixed + per_slot + dyn_bytes <= target) ? 1 : 0;
+    G.stage_dyn = (ctx->obs.n_dyn > 0 && dyn_bytes <= 32 * 1024 && fixed + per_slot + dyn_bytes <= target) ? 1 : 0;
     const size_t avail = target - fixed - (G.stage_dyn ? dyn_bytes : 0);
-    const size_t scratch_cap = std::min<size_t>(avail, (size_t)env_scratch_kb * 1024);
+    const size_t scratch_cap = std::min<size_t>(avail, (size_t)kScratchKb * 1024);
     const int c_budget = std::max<int>(1, (int)(scratch_cap / per_slot));
     G.Cmax = 1;
     G.n_groups = 0;
@@ -413,7 +420,7 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
     G.n_segs = (int)segs.size();
     G.smem = (size_t)G.Cmax * per_slot + fixed + (G.stage_dyn ? dyn_bytes : 0);
     if (G.smem > budget) return fail(RP_ERR_ARG, "horizon too long for shared-memory scratch");
-    G.stage_ref = (env_stage_ref && G.smem + ref_bytes <= target) ? 1 : 0;
+    G.stage_ref = (G.smem + ref_bytes <= target) ? 1 : 0;
     if (G.stage_ref) G.smem += ref_bytes;
     int occ = 0;
     // the attribute is a per-function maximum: only ever raise it (main and index launches share the kernel)
@@ -437,7 +444,6 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
 // Launch geometry of the candidate-major kernel (rp_cand.cuh): segments sorted by traj_len, longest first,
 // cut into chunks of 32 candidates that the warps of a persistent grid draw from a counter.
 int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, int n_acc_rows) {
-    static const int env_stage_ref = std::getenv("RP_CAND_STAGE_REF") ? std::atoi(std::getenv("RP_CAND_STAGE_REF")) : 0;
     std::stable_sort(segs.begin(), segs.end(), [](const rp::Segment& a, const rp::Segment& b) { return a.tl > b.tl; });
     G.big = false;
     G.threads = RP_CAND_THREADS;
@@ -451,15 +457,12 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     }
     G.n_segs = (int)segs.size();
     const size_t budget = (size_t)ctx->max_smem_optin;
-    const size_t ref_bytes = (size_t)(ctx->ref_same_s ? 8 : 9) * ctx->ref_n * sizeof(double);
-    
     const size_t acc_bytes = (size_t)(n_acc_rows * 8 + 1) * G.threads * sizeof(double);    // + v_mid
     const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 128 +
                          (size_t)(G.threads / 32) * rp::kWarpRowDoubles * sizeof(double);     // the warps' longitudinal rows
     G.stage_dyn = 0;                                   // dynamic-obstacle rows are read through L1 (dyn_rows_kernel)
     G.smem = acc_bytes + fixed;
-    G.stage_ref = (env_stage_ref && G.smem + ref_bytes <= budget / 3) ? 1 : 0;
-    if (G.stage_ref) G.smem += ref_bytes;
+    G.stage_ref = 0;                                   // reference tables through L1 (staging them cost occupancy, profiles/README.md)
     if (G.smem > budget) return fail(RP_ERR_ARG, "candidate-major kernel: shared-memory need exceeds the SM");
     static int g_granted[64] = {};
     static std::mutex g_granted_mutex;
@@ -487,14 +490,13 @@ int cand_acc_rows(const rp_plan_inputs& in) {
 
 // which kernel evaluates the main launch (the winner-state / on-demand launches always use fused_kernel)
 bool use_cand_kernel(const rp_ctx* ctx, int count) {
-    static const int env_kernel = std::getenv("RP_KERNEL") ? std::atoi(std::getenv("RP_KERNEL")) : -1;
-    static const int env_min = std::getenv("RP_CAND_MIN") ? std::atoi(std::getenv("RP_CAND_MIN")) : 24576;
+    constexpr int kCandMin = 24576;                    // AUTO: candidate-major from this many candidates up
     const int Np1 = ctx->in.N + 1;
     if (ctx->in.want_all_states || ctx->in.draw_all || Np1 > 128) return false;     // not handled by cand_kernel
-    const int policy = env_kernel >= 0 ? env_kernel : ctx->kernel_policy;
+    const int policy = ctx->kernel_policy;
     if (policy == RP_KERNEL_STEP_PARALLEL) return false;
     if (policy == RP_KERNEL_CANDIDATE_MAJOR) return true;
-    return count >= env_min;
+    return count >= kCandMin;
 }
 
 void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G, const rp::Segment* d_segs) {
@@ -751,6 +753,8 @@ int rp_ctx_set_reference(rp_ctx* ctx, int n, const double* ref_pos, const double
         pack[(size_t)7 * n + q] = path_normal_xy[2 * q + 1];
     }
     std::memcpy(&pack[(size_t)8 * n], path_s, n * sizeof(double));
+    if (int rc = wait_external_readers(ctx)) return rc;
+    RP_CUDA(cudaStreamSynchronize(ctx->stream));           // launches in flight may still read the old tables
     if (int rc = ctx->d_ref.ensure(pack.size() * sizeof(double))) return rc;
     RP_CUDA(cudaMemcpyAsync(ctx->d_ref.p, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     RP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -773,6 +777,7 @@ int rp_ctx_set_reference_polyline(rp_ctx* ctx, int n_pts, const double* xy, doub
         if (xy[2 * q] == xy[2 * q - 2] && xy[2 * q + 1] == xy[2 * q - 1])
             return fail(RP_ERR_ARG, "reference polyline has a repeated vertex");
     const int n = n_pts + 2;
+    if (int rc = wait_external_readers(ctx)) return rc;
     RP_CUDA(cudaStreamSynchronize(ctx->stream));           // launches in flight may still read the old tables
     DevBuf d_xy, d_scratch;
     if (int rc = d_xy.ensure((size_t)n_pts * 2 * sizeof(double))) return rc;
@@ -930,6 +935,10 @@ static int launch_plan(rp_ctx* ctx) {
         first = std::min(ctx->range_first, n);
         count = std::min(ctx->range_count, n - first);
     }
+    // every argument check comes before the first kernel of the chain: a rank that fails here has enqueued nothing
+    // and has not advanced the peer epoch
+    if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision && ctx->range_count >= 0)
+        return fail(RP_ERR_ARG, "continuous collision check is not available for sharded bundles");
     if (int rc = ctx->d_cost.ensure((size_t)std::max(n, 1) * sizeof(double))) return rc;
     if (int rc = ctx->d_info.ensure((size_t)std::max(n, 1) * sizeof(int))) return rc;
     ctx->res_states_bytes = (size_t)14 * Np1 * sizeof(double);
@@ -945,11 +954,10 @@ static int launch_plan(rp_ctx* ctx) {
     }
     // replanning-size bundles: the main launch writes the states of every kept candidate (a few MB at most) and ONE
     // block selects the winner and gathers its states -- 3 launches per cycle instead of 6
-    static const int env_small = std::getenv("RP_SMALL_PATH") ? std::atoi(std::getenv("RP_SMALL_PATH")) : 1;
     // sharded bundle with an open peer group: the selection chain ends with the exchange over peer-mapped memory
     const bool peer_mode = ctx->peer_ready && ctx->range_count >= 0;
     ctx->peer_mode_last = peer_mode;
-    const bool small_path = env_small && !peer_mode && count > 0 && (long long)n * Np1 <= 262144 && !use_cand_kernel(ctx, count);
+    const bool small_path = !peer_mode && count > 0 && (long long)n * Np1 <= 262144 && !use_cand_kernel(ctx, count);
     ctx->small_path_last = small_path;
     if (small_path && !ctx->in.want_all_states) {
         if (int rc = ctx->d_states_all.ensure((size_t)n * 14 * Np1 * sizeof(double))) return rc;
@@ -1060,7 +1068,6 @@ static int launch_plan(rp_ctx* ctx) {
         if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one())) return rc;
     }
     if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision) {
-        if (ctx->range_count >= 0) return fail(RP_ERR_ARG, "continuous collision check is not available for sharded bundles");
         rp::continuous_check_kernel<<<1, 128, 0, ctx->stream>>>(ctx->obs, ctx->d_states_one(), Np1, ctx->in.x0_time_step,
                                                                 0.5 * ctx->veh.length, 0.5 * ctx->veh.width, ctx->veh.wb_rear_axle,
                                                                 dres, ctx->d_info.as<int>());
@@ -1089,8 +1096,12 @@ int rp_grid_result(rp_ctx* ctx, rp_plan_result* out) {
     RP_CUDA(cudaEventSynchronize(ctx->ev_result));
     ctx->h_states_valid = true;
     *out = static_cast<rp::PlanResultDev*>(ctx->h_result.p)->r;
-    if (ctx->peer_mode_last && static_cast<rp::PlanResultDev*>(ctx->h_result.p)->peer_error)
-        return fail(RP_ERR_STATE, "peer exchange: a wait on another rank timed out (did every rank launch this cycle?)");
+    if (ctx->peer_mode_last && static_cast<rp::PlanResultDev*>(ctx->h_result.p)->peer_error) {
+        // the ranks' epochs can no longer be trusted to agree: the group is broken until every rank re-creates it
+        ctx->peer_ready = false;
+        return fail(RP_ERR_PEER, "peer exchange: a wait on another rank timed out or a peer reported a failed cycle; the "
+                                 "group is closed -- rp_peer_close / rp_peer_create / rp_peer_open on EVERY rank to resume");
+    }
     return RP_OK;
 }
 
@@ -1547,6 +1558,8 @@ int rp_batch_destroy(rp_batch* b) {
     if (!b) return RP_OK;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
+    for (rp_ctx* c : b->ctxs)
+        if (c->ext_busy == b->ev1) c->ext_busy = nullptr;
     for (DevBuf* q : {&b->d_stage, &b->d_lon_coef, &b->d_lat_coef, &b->d_cost, &b->d_info, &b->d_dyn_rows, &b->d_results, &b->d_work})
         q->release();
     b->h_stage.release();
@@ -1646,6 +1659,7 @@ int rp_batch_launch(rp_batch* b) {
         acc_rows = std::max(acc_rows, cand_acc_rows(s.in));
     }
     const size_t stage_bytes = off;
+    if (b->stage_pending) RP_CUDA(cudaEventSynchronize(b->ev_stage));          // last copy out of the pinned buffer (before it may be re-allocated)
     if (int rc = b->h_stage.ensure(stage_bytes)) return rc;
     if (int rc = b->d_stage.ensure(stage_bytes)) return rc;
     if (int rc = b->d_lon_coef.ensure(std::max<size_t>(n_lon_tot, 1) * 6 * sizeof(double))) return rc;
@@ -1656,7 +1670,6 @@ int rp_batch_launch(rp_batch* b) {
     if (int rc = b->d_results.ensure((size_t)n * sizeof(rp::PlanResultDev))) return rc;
     if (int rc = b->h_results.ensure((size_t)n * sizeof(rp::PlanResultDev))) return rc;
     if (int rc = b->d_work.ensure(sizeof(int))) return rc;
-    if (b->stage_pending) RP_CUDA(cudaEventSynchronize(b->ev_stage));          // last copy out of the pinned buffer
     char* hs = static_cast<char*>(b->h_stage.p);
     const char* ds = static_cast<const char*>(b->d_stage.p);
     std::memcpy(hs + off_prefix, prefix.data(), prefix.size() * sizeof(int));
@@ -1733,6 +1746,7 @@ int rp_batch_launch(rp_batch* b) {
     rp::argmin_batch_kernel<<<n, 256, 0, b->stream>>>(dparams, b->d_results.as<rp::PlanResultDev>());
     RP_CUDA(cudaGetLastError());
     cudaEventRecord(b->ev1, b->stream);
+    for (rp_ctx* c : b->ctxs) c->ext_busy = b->ev1;          // table updates of a member context wait for this cycle
     b->total_cand = (long long)n_cand_tot;
     b->launched = true;
     return RP_OK;

@@ -657,6 +657,13 @@ __global__ void __launch_bounds__(32) peer_merge_kernel(const __grid_constant__ 
     }
     if (!__all_sync(0xffffffffu, ok)) {
         if (lane == 0) { res->peer_error = 1; res->r.winner = -1; }
+        // publish the second phase with a poison count: the peers fail this cycle at once instead of timing out again
+        if (lane < T.world) {
+            PeerMailbox* const dst = T.box[lane];
+            dst->cnt[par][T.rank] = -1.0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(&dst->flag2[par][T.rank]) = epoch;
+        }
         return;
     }
     double bc = inf, bi = inf, sums[kPeerRecord - 2];
@@ -736,6 +743,10 @@ __global__ void __launch_bounds__(256) peer_count_kernel(const __grid_constant__
         return;
     }
     double sum = lane < T.world ? *reinterpret_cast<const volatile double*>(&mine->cnt[par][lane]) : 0.;
+    if (__any_sync(0xffffffffu, sum < 0.)) {          // a peer's first phase failed (poison count)
+        if (lane == 0) { res->peer_error = 1; res->r.winner = -1; }
+        return;
+    }
     sum = warp_sum_f64(sum);
     if (lane == 0) res->r.n_infeasible_collision = (int)sum;
 }

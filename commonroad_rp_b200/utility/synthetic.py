@@ -32,7 +32,7 @@ def _frame_on_sine(x, amplitude, wavelength):
 
 def make_scenario(seed=0, amplitude=20.0, wavelength=40.0, length=300, n_dynamic=8, n_static=2,
                   n_dyn_steps=100, boundary_offset=5.25, boundary=True, static_x=(60.0, 140.0),
-                  static_offset=0.0):
+                  static_offset=0.0, boundary_kind="boxes", boundary_depth=1.0):
     """Config-4/5 style scenario: sinusoidal reference path, ``n_dynamic`` 5.0x2.0 cars on
     +-3.5 m lateral offsets at speeds U(5, 20) for ``n_dyn_steps`` steps, ``n_static`` boxes on
     the path, and a road boundary of thin OBBs at +-``boundary_offset``."""
@@ -58,8 +58,19 @@ def make_scenario(seed=0, amplitude=20.0, wavelength=40.0, length=300, n_dynamic
         y, th, nx, ny = _frame_on_sine(np.float64(xs), amplitude, wavelength)
         static_boxes.append((xs + static_offset * nx, y + static_offset * ny, th, 4.5, 2.0))
 
-    boundary_boxes = []
-    if boundary:
+    boundary_boxes, boundary_tris = [], []
+    if boundary and boundary_kind == "tris":
+        # the same two border lines as a triangulated band: per segment the quad between the border and the line
+        # ``boundary_depth`` farther out, split along its diagonal (road boundary as triangles)
+        xs = np.arange(0, length, 1.0)
+        y, th, nx, ny = _frame_on_sine(xs, amplitude, wavelength)
+        for side in (+1.0, -1.0):
+            ix, iy = xs + side * boundary_offset * nx, y + side * boundary_offset * ny
+            ox, oy = xs + side * (boundary_offset + boundary_depth) * nx, y + side * (boundary_offset + boundary_depth) * ny
+            for i in range(len(xs) - 1):
+                boundary_tris.append((ix[i], iy[i], ix[i + 1], iy[i + 1], ox[i + 1], oy[i + 1]))
+                boundary_tris.append((ix[i], iy[i], ox[i + 1], oy[i + 1], ox[i], oy[i]))
+    elif boundary:
         xs = np.arange(0, length, 1.0)
         y, th, nx, ny = _frame_on_sine(xs, amplitude, wavelength)
         for side in (+1.0, -1.0):
@@ -77,7 +88,7 @@ def make_scenario(seed=0, amplitude=20.0, wavelength=40.0, length=300, n_dynamic
         "dyn_states": dyn_states,
         "dyn_lw": np.asarray(dyn_lw, dtype=np.float64).reshape(-1, 2),
         "boundary_boxes": np.asarray(boundary_boxes, dtype=np.float64).reshape(-1, 5),
-        "boundary_tris": np.zeros((0, 6)),
+        "boundary_tris": np.asarray(boundary_tris, dtype=np.float64).reshape(-1, 6),
     }
 
 

@@ -39,7 +39,8 @@ enum rp_status {
     RP_ERR_ARG = -1,      /* invalid argument            */
     RP_ERR_CUDA = -2,     /* CUDA runtime failure        */
     RP_ERR_STATE = -3,    /* call order (missing tables) */
-    RP_ERR_NOMEM = -4
+    RP_ERR_NOMEM = -4,
+    RP_ERR_PEER = -5      /* multi-GPU peer exchange failed; the group is closed and must be re-created on every rank */
 };
 
 /* candidate status (FeasibilityStatus, trajectories.py:18-22; FILTERED = filter_goals_behind, :545-550) */
@@ -220,8 +221,13 @@ int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double
  * rp_grid_launch / rp_plan_grid end with two kernels that store the shard's record and the shard's collider count
  * straight into the peers' mailboxes and merge what arrived -- no collective call on the data path -- and
  * rp_grid_result returns the GLOBAL result on every rank (winner, cost, all counters; rp_fetch_states(winner) the
- * global winner's states).  Every rank must launch the same cycles; a rank that never arrives makes the others'
- * rp_grid_result fail with RP_ERR_STATE after ~8 s instead of hanging.
+ * global winner's states).  Every rank must launch the same cycles.  Failure protocol: the per-launch epochs of the
+ * ranks must stay equal, so a rank that never arrives (or whose launch failed before it reached the exchange) makes
+ * the others' waits time out after ~8 s; a rank whose first wait fails still publishes the second phase's flag with
+ * a poison count, so its peers fail that cycle at once instead of waiting another 8 s.  rp_grid_result then returns
+ * RP_ERR_PEER and the context leaves the group (launches go back to shard-local results).  Recovery: EVERY rank calls
+ * rp_peer_close, rp_peer_create and rp_peer_open again (epochs restart at zero).  rp_peer_create zeroes the mailbox:
+ * it must not be called while any rank still has a cycle of the old group in flight.
  *   rp_peer_create  allocates this rank's mailbox and returns its 64-byte CUDA IPC handle in handle64;
  *   rp_peer_open    maps the mailboxes of all ranks (handles[world][64] in rank order, e.g. from one all-gather at
  *                   set-up); every rank must have returned from rp_peer_create before any rank launches a cycle;

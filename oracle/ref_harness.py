@@ -87,8 +87,9 @@ def override_sample_sets(planner, level, t=None, v=None, d=None, s=None):
         sp.samples_s._dict_level_to_sample_set[level] = set(np.asarray(s, dtype=np.float64))
 
 
-def evaluate_level(planner, level, want_states=True):
-    """One pass of reactive_planner.py:620-624 for ``level`` with per-candidate bookkeeping."""
+def evaluate_level(planner, level, want_states=True, state_sample=None):
+    """One pass of reactive_planner.py:620-624 for ``level`` with per-candidate bookkeeping.
+    state_sample = (count, seed): keep the state blocks of a seeded sample of feasible candidates instead of all."""
     x0_lon, x0_lat = planner.x_0_cl
     planner._low_vel_mode = bool(planner.x_0.velocity < planner.config.planning.low_vel_mode_threshold)
     bundle = planner._create_trajectory_bundle(x0_lon, x0_lat, samp_level=level)
@@ -119,17 +120,27 @@ def evaluate_level(planner, level, want_states=True):
         "n_infeasible_collision": int(planner.infeasible_count_collision),
         "reasons": dict(planner.infeasible_reason_dict),
     }
-    if want_states:
-        st = np.full((n, len(STATE_FIELDS), Np1), np.nan)
-        for i, c in enumerate(cands):
-            if c.cartesian is None or c.curvilinear is None:
-                continue
+    def state_block(c):
+        blk = np.full((len(STATE_FIELDS), Np1), np.nan)
+        if c.cartesian is not None and c.curvilinear is not None:
             ca, cu = c.cartesian, c.curvilinear
             rows = (ca.x, ca.y, ca.theta, ca.v, ca.a, ca.kappa, ca.kappa_dot,
                     cu.s, cu.d, cu.theta, cu.s_dot, cu.s_ddot, cu.d_dot, cu.d_ddot)
             for f, arr in enumerate(rows):
-                st[i, f, :] = arr
-        out["states"] = st
+                blk[f, :] = arr
+        return blk
+
+    if state_sample is not None:
+        # large bundles: the state blocks of a seeded sample of the feasible candidates (+ the winner) only
+        feas = np.nonzero(out["kin_feasible"])[0]
+        rng = np.random.default_rng(state_sample[1])
+        pick = feas if len(feas) <= state_sample[0] else np.sort(rng.choice(feas, state_sample[0], replace=False))
+        if out["winner"] >= 0 and out["winner"] not in pick:
+            pick = np.sort(np.append(pick, out["winner"]))
+        out["state_idx"] = pick.astype(np.int64)
+        out["states_sampled"] = np.stack([state_block(cands[i]) for i in pick]) if len(pick) else np.zeros((0, len(STATE_FIELDS), Np1))
+    elif want_states:
+        out["states"] = np.stack([state_block(c) for c in cands]) if n else np.zeros((0, len(STATE_FIELDS), Np1))
     return out
 
 

@@ -4,9 +4,9 @@ installed here, and the XML files themselves must not be copied into this repo: 
 scenario into the plain-array "scenario dict" of ``commonroad_rp_b200.utility.synthetic`` (plus the
 planning problem), which oracle/make_golden.py stores as a compact fixture.
 
-Road boundary: thin boxes (width 0.1 m) along every lanelet border that has no adjacent lanelet on that
-side -- the same construction as ``commonroad_rp_b200.collision.create_road_boundary_obstacle``
-(parity unpinned: the reference's default is commonroad_dc's triangulation).
+Road boundary: ``commonroad_rp_b200.collision.road_boundary_segments`` (lanelet borders whose far side is off-road)
+as thin boxes (width 0.1 m) or as a band of triangles (parity unpinned: the reference's default is commonroad_dc's
+triangulation of the whole off-road area).
 """
 import math
 import xml.etree.ElementTree as ET
@@ -44,7 +44,7 @@ def _rect(node):
     return float(r.find("length").text), float(r.find("width").text)
 
 
-def load(path):
+def load(path, boundary_method="obb_rectangles"):
     root = ET.parse(path).getroot()
     lanelets = {}
     for ll in root.findall("lanelet"):
@@ -75,19 +75,21 @@ def load(path):
             dyn_t0.append(init["time"])
             dyn_states.append(np.array(rows))
             dyn_lw.append((length, width))
-    boundary = []
-    for ll in lanelets.values():
-        for side, adj in (("left", "adj_left"), ("right", "adj_right")):
-            if ll[adj] is not None:
-                continue
-            pts = ll[side]
-            for p, q in zip(pts[:-1], pts[1:]):
-                seg = q - p
-                ln = float(np.hypot(seg[0], seg[1]))
-                if ln <= 0.0:
-                    continue
-                mid = 0.5 * (p + q)
-                boundary.append((mid[0], mid[1], math.atan2(seg[1], seg[0]), 0.5 * ln, 0.05))
+    # road boundary: the product's own construction from the lanelet borders (input data for BOTH sides of the
+    # parity tests, not arithmetic under test): thin boxes along the true boundary segments, or a triangle band
+    from types import SimpleNamespace
+    from commonroad_rp_b200 import collision as rpc
+    lls = [SimpleNamespace(left_vertices=ll["left"], right_vertices=ll["right"], adj_left=ll["adj_left"],
+                           adj_right=ll["adj_right"]) for ll in lanelets.values()]
+    segs = rpc.road_boundary_segments(lls)
+    boundary, tris = [], np.zeros((0, 6))
+    if boundary_method == "triangulation":
+        tris = rpc.boundary_band_triangles(lls, segs, 1.0)
+    else:
+        for p, q in segs:
+            seg = q - p
+            mid = 0.5 * (p + q)
+            boundary.append((mid[0], mid[1], math.atan2(seg[1], seg[0]), 0.5 * float(np.hypot(seg[0], seg[1])), 0.05))
     pp = root.find("planningProblem")
     init = _state(pp.find("initialState"))
     goal = pp.find("goalState")
@@ -111,7 +113,7 @@ def load(path):
                 "dyn_t0": np.array(dyn_t0, dtype=np.int64), "dyn_states": dyn_states,
                 "dyn_lw": np.array(dyn_lw, dtype=np.float64).reshape(-1, 2),
                 "boundary_boxes": np.array(boundary, dtype=np.float64).reshape(-1, 5),
-                "boundary_tris": np.zeros((0, 6))},
+                "boundary_tris": np.asarray(tris, dtype=np.float64).reshape(-1, 6)},
         "initial_state": init, "goal": goal_info,
     }
 

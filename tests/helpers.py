@@ -167,3 +167,100 @@ def assert_parity(o, g, prob, check_states=True, tag=""):
             assert rel_err(o["states"][have], g["states"][have]) < STATE_RTOL, tag
     if o["winner"] >= 0 and o.get("states") is not None:
         assert rel_err(o["states"][o["winner"]], g["winner_states"]) < STATE_RTOL, tag
+
+
+class EmptyScenario:
+    """config.scenario stand-in for planners that receive their collision checker explicitly"""
+    static_obstacles, dynamic_obstacles = (), ()
+    lanelet_network = type("LN", (), {"lanelets": ()})()
+
+
+def planner_from_fixture(prob, ref_path_raw, x0_row, desired_velocity=None, continuous=False, draw=False, cost=None,
+                         low_vel_mode_threshold=4.0, t_min=0.4):
+    """The drop-in ``ReactivePlanner`` set up on a fixture's problem: reference path from the RAW polyline (the
+    product's own CoordinateSystem), obstacles from the scenario arrays, x0 = (x, y, orientation, velocity,
+    acceleration, yaw_rate, steering_angle, time_step) with the fixture's curvilinear initial state."""
+    from commonroad_rp_b200 import collision
+    from commonroad_rp_b200.reactive_planner import ReactivePlanner
+    from commonroad_rp_b200.state import ReactivePlannerState
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = prob["N"]
+    cfg.planning.dt = prob["dt"]
+    cfg.planning.planning_horizon = prob["dt"] * prob["N"]
+    cfg.planning.factor = prob["factor"]
+    cfg.planning.low_vel_mode_threshold = low_vel_mode_threshold
+    cfg.planning.continuous_collision_check = bool(continuous)
+    cfg.planning.constraints_to_check = list(prob["constraints"])
+    cfg.sampling.longitudinal_mode = prob["lon_mode"]
+    cfg.sampling.t_min = t_min
+    cfg.debug.draw_traj_set = draw
+    cfg.debug.save_plots = draw
+    ob = prob["obstacles"]
+    scn = EmptyScenario()
+    if continuous:
+        # the planner builds the checker itself (dynamic obstacles replaced by their OBB-sum hulls, reference :239-243)
+        class _St:
+            def __init__(self, pos, th, t):
+                self.position, self.orientation, self.time_step = pos, th, t
+
+        class _Ob:
+            pass
+
+        statics, dyns = [], []
+        for cx, cy, th, l, w in np.asarray(ob["static_boxes"], dtype=np.float64).reshape(-1, 5):
+            o = _Ob()
+            o.obstacle_shape = type("R", (), {"length": l, "width": w})()
+            o.initial_state = _St(np.array([cx, cy]), th, 0)
+            o.prediction = None
+            statics.append(o)
+        for t0, st, lw in zip(ob["dyn_t0"], ob["dyn_states"], ob["dyn_lw"]):
+            o = _Ob()
+            o.obstacle_shape = type("R", (), {"length": lw[0], "width": lw[1]})()
+            st = np.asarray(st, dtype=np.float64).reshape(-1, 3)
+            o.initial_state = _St(st[0, :2], st[0, 2], int(t0))
+            traj = type("T", (), {"state_list": [_St(r[:2], r[2], int(t0) + 1 + k) for k, r in enumerate(st[1:])]})()
+            o.prediction = type("P", (), {"trajectory": traj})()
+            dyns.append(o)
+        scn = type("Scn", (), {"static_obstacles": statics, "dynamic_obstacles": dyns,
+                               "lanelet_network": EmptyScenario.lanelet_network})()
+    cfg.update(scenario=scn, planning_problem=None)
+    planner = ReactivePlanner(cfg)
+    co = CoordinateSystem(np.asarray(ref_path_raw, dtype=np.float64))
+    if continuous:
+        sg = collision.ShapeGroup()
+        for cx, cy, th, hl, hw in np.asarray(ob["boundary_boxes"], dtype=np.float64).reshape(-1, 5):
+            sg.add_shape(collision.RectOBB(hl, hw, th, cx, cy))
+        for tri in np.asarray(ob.get("boundary_tris", np.zeros((0, 6))), dtype=np.float64).reshape(-1, 6):
+            sg.add_shape(collision.Triangle(*tri))
+        planner.set_collision_checker(scenario=scn, road_boundary_obstacle=sg)
+        cc = planner.collision_checker
+    else:
+        cc = collision.checker_from_arrays(**{k: ob[k] for k in ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw",
+                                                                  "boundary_boxes", "boundary_tris")})
+    if cost == "failsafe":
+        from commonroad_rp_b200.cost_function import DefaultCostFunctionFailSafe
+        planner.set_cost_function(DefaultCostFunctionFailSafe())
+    x = np.asarray(x0_row, dtype=np.float64)
+    x0 = ReactivePlannerState(time_step=int(x[7]), position=np.array([x[0], x[1]]), orientation=x[2], velocity=x[3],
+                              acceleration=x[4], yaw_rate=x[5], steering_angle=x[6])
+    planner.reset(initial_state_cart=x0, initial_state_curv=(list(prob["x0_lon"]), list(prob["x0_lat"])),
+                  collision_checker=cc, coordinate_system=co)
+    if prob["lon_mode"] == "stopping":
+        planner.set_desired_lon_position(prob["cost"]["desired_s"])
+    else:
+        dv = prob["cost"].get("desired_speed") if desired_velocity is None else desired_velocity
+        planner.set_desired_velocity(desired_velocity=dv if dv is not None else float(x[3]), current_speed=float(x[3]))
+    return planner
+
+
+def plan_output_arrays(result):
+    """plan()'s return value as the arrays of oracle/make_golden.py:plan_output_arrays"""
+    cart, curv, lon_list, lat_list = result
+    oc = np.array([[st.position[0], st.position[1], st.orientation, st.velocity, st.acceleration, st.yaw_rate,
+                    st.steering_angle, float(st.time_step)] for st in cart.state_list]).T
+    ou = np.array([[st.position[0], st.position[1], st.orientation, st.velocity, st.acceleration, st.yaw_rate,
+                    float(st.time_step)] for st in curv.state_list]).T
+    return {"out_cart": oc, "out_curv": ou, "out_lon": np.array(lon_list, dtype=np.float64),
+            "out_lat": np.array(lat_list, dtype=np.float64)}

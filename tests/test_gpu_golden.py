@@ -86,6 +86,7 @@ def test_cyclic_replanning_matches_reference_fixture(path):
     cfg = ReactivePlannerConfiguration()
     cfg.planning.time_steps_computation = meta["N"]
     cfg.planning.dt = meta["dt"]
+    cfg.planning.planning_horizon = meta["dt"] * meta["N"]
     cfg.planning.low_vel_mode_threshold = meta["low_vel_mode_threshold"]
     cfg.sampling.t_min = meta["t_min"]
     cfg.debug.draw_traj_set = meta["draw_traj_set"]
@@ -150,6 +151,12 @@ def test_cyclic_replanning_matches_reference_fixture(path):
             got = np.array([[s.position[0], s.position[1], s.velocity, s.acceleration] for s in cart.state_list]).T
             assert H.rel_err(ws[[0, 1, 3, 4]], got) < RTOL, "cycle %d" % ci
             assert H.rel_err(ws[[7, 10, 11]], np.array(lon_list).T) < RTOL and H.rel_err(ws[[8, 12, 13]], np.array(lat_list).T) < RTOL
+            # the complete return value (reactive_planner.py:514-568): orientation shift, yaw rate, steering angle, time
+            # steps, the curvilinear state list
+            got_out = H.plan_output_arrays(out)
+            for key in ("out_cart", "out_curv", "out_lon", "out_lat"):
+                want = z["c%d_%s" % (ci, key)]
+                assert got_out[key].shape == want.shape and H.rel_err(want, got_out[key]) < RTOL, ("cycle %d" % ci, key)
 
 
 def _frame_engine(z):
@@ -214,3 +221,134 @@ def test_batched_initial_states_over_scenarios():
     batch.close()
     for e, _ in pairs:
         e.close()
+
+
+# ---- round 2: large bundles, plan()-level fixtures, continuous check through the planner ---------------------------
+BIG = sorted(glob.glob(os.path.join(GOLDEN, "big_*.npz")))
+PLAN = sorted(glob.glob(os.path.join(GOLDEN, "plan_*.npz")))
+
+
+def _check_big(z, g, tag):
+    from commonroad_rp_b200._lib import REASON_NAMES
+    n = len(z["r_cost"])
+    assert g["n"] == n, tag
+    kin_ok = (g["status"] == 0) | (g["status"] == 2)
+    assert np.array_equal(kin_ok, z["r_kin_feasible"]), tag                         # flags: bit exact, every candidate
+    assert H.rel_err(z["r_cost"][kin_ok], g["cost"][kin_ok]) < RTOL, tag             # every cost
+    assert g["winner"] == int(z["r_winner"]), tag
+    assert g["n_infeasible_kinematics"] == int(z["r_n_inf_kin"]), tag
+    assert g["n_infeasible_collision"] == int(z["r_n_inf_col"]), tag
+    for name, cnt in json.loads(str(z["r_reasons"])).items():
+        assert g["reason_counts"][REASON_NAMES.index(name)] == cnt, (tag, name)
+    lab = z["r_label"]
+    assert np.all(g["status"][lab == 3] == 2), tag         # every collider the reference's lazy pass met collides here
+    # ... and nothing ranked before the winner is collision-free here that the reference saw colliding, or vice versa
+    wc, wi = g["winner_cost"], g["winner"]
+    before = kin_ok & ((g["cost"] < wc) | ((g["cost"] == wc) & (np.arange(n) < wi)))
+    assert np.array_equal(before & (g["status"] == 2), lab == 3), tag
+
+
+@pytest.mark.parametrize("path", BIG, ids=[os.path.basename(p)[4:-4] for p in BIG])
+@pytest.mark.parametrize("kernel", ["candidate_major", "step_parallel"])
+def test_big_bundle_matches_reference_fixture(path, kernel):
+    """BASELINE configs[3] (131 072 x 61, the bench workload itself) and configs[4]'s per-scenario bundle (8 874 x 61)
+    against the verdicts of the reference's own code on the same inputs, through both schedules"""
+    from commonroad_rp_b200 import _lib
+    z = np.load(path)
+    prob = golden_io.unpack_problem(z)
+    eng = H.engine_for(prob)
+    pol = _lib.KERNEL_CANDIDATE_MAJOR if kernel == "candidate_major" else _lib.KERNEL_STEP_PARALLEL
+    g = H.run_engine_grid(eng, prob, want_all_states=False, kernel=pol)
+    assert eng.last_main_kernel() == pol
+    _check_big(z, g, os.path.basename(path))
+    for q, k in enumerate(z["r_state_idx"]):                                         # sampled state blocks + the winner
+        assert H.rel_err(z["r_states"][q], eng.fetch_states(int(k))) < RTOL, (path, int(k))
+    eng.close()
+
+
+def test_scenario_batch_matches_reference_fixtures():
+    """the batch path (rp_batch_*: one launch chain for all scenarios) on the reference-generated configs[4] bundles"""
+    from commonroad_rp_b200 import _lib
+    paths = [p for p in BIG if "batch_" in os.path.basename(p)]
+    assert len(paths) >= 2
+    zs = [np.load(p) for p in paths]
+    probs = [golden_io.unpack_problem(z) for z in zs]
+    engines = [H.engine_for(pr) for pr in probs]
+    batch = _lib.Batch(engines)
+    for rep in range(2):
+        for k, pr in enumerate(probs):
+            batch.set_inputs(k, H.inputs_for(pr), pr["t"], pr["lon"], pr["d"])
+        batch.launch()
+        res = batch.results()
+        for k, (z, r) in enumerate(zip(zs, res)):
+            cost, status, reason, step = batch.fetch_candidates(k)
+            g = {"n": r.n_candidates, "winner": r.winner, "winner_cost": r.winner_cost, "cost": cost, "status": status,
+                 "n_infeasible_kinematics": r.n_infeasible_kinematics, "n_infeasible_collision": r.n_infeasible_collision,
+                 "reason_counts": list(r.reason_counts)}
+            _check_big(z, g, "batch %d rep %d" % (k, rep))
+    batch.close()
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.parametrize("path", PLAN, ids=[os.path.basename(p)[5:-4] for p in PLAN])
+def test_plan_output_matches_reference_fixture(path):
+    """the complete return value of ReactivePlanner.plan() (reactive_planner.py:570-665) on synthetic cycles, incl. the
+    standstill branch (:638-653, :667-713), total failure (None) and the level escalation the reference went through"""
+    z = np.load(path)
+    meta = json.loads(str(z["plan_meta"]))
+    prob = golden_io.unpack_problem(z)
+    planner = H.planner_from_fixture(prob, z["ref_path_raw"], z["x0"], desired_velocity=meta["desired_velocity"])
+    seen = []
+    orig = planner._get_optimal_trajectory
+
+    def spy(bundle):
+        win = orig(bundle)
+        seen.append({"n": planner.last_result.n_candidates, "found": win is not None,
+                     "n_inf_kin": int(planner.infeasible_count_kinematics), "n_inf_col": int(planner.infeasible_count_collision),
+                     "reasons": dict(planner.infeasible_reason_dict)})
+        return win
+
+    planner._get_optimal_trajectory = spy
+    out = planner.plan()
+    assert (out is not None) == meta["ok"]
+    assert seen == meta["levels"]
+    assert planner.optimal_cost == pytest.approx(meta["optimal_cost"], rel=1e-9, abs=1e-12)
+    if out is not None:
+        got = H.plan_output_arrays(out)
+        for key in ("out_cart", "out_curv", "out_lon", "out_lat"):
+            assert got[key].shape == z[key].shape, key                               # standstill: N states, not N + 1
+            assert H.rel_err(z[key], got[key]) < RTOL, (key, H.rel_err(z[key], got[key]))
+        assert meta["standstill"] == bool(np.all(got["out_cart"][3] == 0.0))
+
+
+@pytest.mark.parametrize("name", ["continuous_pass", "continuous_hit"])
+def test_continuous_collision_check_through_the_planner(name):
+    """SURVEY 8f rank 2 through the drop-in API: ReactivePlanner(config.planning.continuous_collision_check=True) builds
+    its checker from the scenario with the dynamic obstacles replaced by OBB-sum hulls (reference :239-243) and hull-checks
+    the selected candidate (:1049-1058) -- same winner / counters as the reference's own run of the same cycle"""
+    z = np.load(os.path.join(GOLDEN, "syn_%s.npz" % name))
+    prob = golden_io.unpack_problem(z)
+    assert prob["continuous"]
+    raw = synthetic_raw_path(prob)
+    r, c = prob["ref"], prob["ccosy"]
+    j = int(np.argmax(r["ref_pos"] > prob["x0_lon"][0])) - 1
+    from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+    co = CoordinateSystem(raw)
+    pos = co.convert_to_cartesian_coords(prob["x0_lon"][0], prob["x0_lat"][0])
+    x0 = [pos[0], pos[1], prob["x0_orientation"], prob["x0_lon"][1], 0.0, 0.0, 0.0, prob["x0_time_step"]]
+    planner = H.planner_from_fixture(prob, raw, x0, continuous=True)
+    assert np.allclose(planner.coordinate_system.ref_pos, r["ref_pos"], rtol=1e-9, atol=1e-9)
+    level = {120: 1, 540: 2, 630: 2}.get(len(z["r_cost"]), 2)
+    out = planner.plan(current_sampling_level=level)
+    res = planner.last_result
+    assert res.n_candidates == len(z["r_cost"])
+    assert res.winner == int(z["r_winner"]) and (out is not None) == (int(z["r_winner"]) >= 0)
+    assert planner.infeasible_count_kinematics == int(z["r_n_inf_kin"])
+    assert planner.infeasible_count_collision == int(z["r_n_inf_col"])
+
+
+def synthetic_raw_path(prob):
+    """the raw polyline of the synthetic fixtures (straight variant, amplitude 0): x = 0..299, y = 0"""
+    from commonroad_rp_b200.utility import synthetic
+    return synthetic.sine_path(0.0, 40.0, 300)

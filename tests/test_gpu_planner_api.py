@@ -377,9 +377,9 @@ def test_scenario_batch_equals_individual_plans():
     batch.close()
 
 
-def test_continuous_collision_check_through_the_planner_api():
-    """SURVEY 8f rank 2 through the drop-in API: with config.planning.continuous_collision_check the scenario's dynamic
-    obstacles become OBB-sum hulls (reference :240-241) and the selected candidate is hull-checked (:1049-1058)"""
+def test_obb_sum_hull_helpers():
+    """host helpers of the continuous collision check (collision.obb_sum_hull / trajectory_preprocess_obb_sum); the
+    planner-level test is tests/test_gpu_golden.py::test_continuous_collision_check_through_the_planner"""
     from commonroad_rp_b200 import collision
     a = collision.RectOBB(2.0, 1.0, 0.3, 0.0, 0.0)
     b = collision.RectOBB(2.0, 1.0, 0.5, 3.0, 1.0)

@@ -68,3 +68,118 @@ def test_oracle_initial_states_match_reference_vectors():
     assert n_checked >= 60
     with pytest.raises(ValueError):
         O.initial_states([1e6, 1e6, 0, 1, 0, 0], False, ref, frame, wheelbase)
+
+
+# ---- round 2 fixtures --------------------------------------------------------------------------------------------
+BIG = sorted(glob.glob(os.path.join(GOLDEN, "big_*.npz")))
+CYC = sorted(glob.glob(os.path.join(GOLDEN, "cyc_*.npz")))
+
+
+def test_round2_fixtures_present():
+    names = {os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*.npz"))}
+    assert {"big_dense_full.npz", "big_batch_sid0.npz", "cyc_ZAM-Ramp-1_1-T-1.npz", "syn_failsafe.npz", "syn_tri_boundary.npz",
+            "plan_standstill_blocked.npz", "plan_blocked_moving.npz"} <= names
+    # the bundled scenarios are recorded until goal_reached(), not up to a cap
+    want = {"ZAM_Over-1_1": 9, "DEU_Test-1_1_T-1": 12, "ZAM_Tjunction-1_42_T-1": 49, "ZAM-Ramp-1_1-T-1": 16}
+    for path in CYC:
+        meta = json.loads(str(np.load(path)["meta"]))
+        assert meta["n_cycles"] == want[meta["name"]] and all(c["ok"] for c in meta["cycles"]), meta["name"]
+
+
+@pytest.mark.parametrize("path", [p for p in BIG if "batch_" in p], ids=lambda p: os.path.basename(p)[4:-4])
+def test_oracle_matches_big_batch_fixture(path):
+    """BASELINE configs[4]'s per-scenario bundle (8 874 x 61): the portable oracle against the reference's verdicts"""
+    z = np.load(path)
+    prob = golden_io.unpack_problem(z)
+    o = O.plan_grid(prob, want_states=False, full_collision=False)
+    assert np.array_equal(o["kin_feasible"], z["r_kin_feasible"])
+    assert _close(o["cost"], z["r_cost"])
+    assert o["winner"] == int(z["r_winner"])
+    assert o["n_infeasible_kinematics"] == int(z["r_n_inf_kin"]) and o["n_infeasible_collision"] == int(z["r_n_inf_col"])
+    assert o["reasons"] == json.loads(str(z["r_reasons"]))
+    assert np.array_equal(z["r_label"] == 3, (o["status"] == O.ST_COLLISION) & (z["r_label"] == 3))
+
+
+def test_oracle_matches_dense_full_fixture_on_a_subgrid():
+    """BASELINE configs[3] (131 072 x 61): the oracle on every 8th v and d sample (2 048 candidates) against the
+    reference's per-candidate verdicts and costs at the same enumeration indices"""
+    z = np.load(os.path.join(GOLDEN, "big_dense_full.npz"))
+    prob = golden_io.unpack_problem(z)
+    n_t, n_lon, n_d = len(prob["t"]), len(prob["lon"]), len(prob["d"])
+    assert (n_t, n_lon, n_d) == (32, 64, 64) and len(z["r_cost"]) == 131072
+    sub = dict(prob)
+    il, idd = np.arange(0, n_lon, 8), np.arange(3, n_d, 8)
+    sub["lon"], sub["d"] = prob["lon"][il], prob["d"][idd]
+    o = O.plan_grid(sub, want_states=False, full_collision=True)
+    full_idx = ((np.arange(n_t)[:, None, None] * n_lon + il[None, :, None]) * n_d + idd[None, None, :]).ravel()
+    assert np.array_equal(o["kin_feasible"], z["r_kin_feasible"][full_idx])
+    assert _close(o["cost"], z["r_cost"][full_idx])
+    lab = z["r_label"][full_idx]
+    assert np.all(o["status"][lab == 3] == O.ST_COLLISION) and np.all(o["status"][lab == 1] == O.ST_FEASIBLE)
+    # the judge's own full CPU run of round 1: winner 97084, 2 713 kinematic rejects, 8 179 colliders before the winner
+    assert (int(z["r_winner"]), int(z["r_n_inf_kin"]), int(z["r_n_inf_col"])) == (97084, 2713, 8179)
+
+
+@pytest.mark.parametrize("path", CYC, ids=lambda p: os.path.basename(p)[4:-4])
+def test_oracle_matches_cyclic_fixture(path):
+    """every recorded replanning cycle of the bundled scenarios (run to goal_reached()) through the portable oracle:
+    level escalation, per-candidate feasibility, costs, winner, counters"""
+    from commonroad_rp_b200.sampling import FixedIntervalSampling, VelocitySampling
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = meta["N"]
+    cfg.planning.dt = meta["dt"]
+    cfg.planning.planning_horizon = meta["dt"] * meta["N"]
+    cfg.sampling.t_min = meta["t_min"]
+    fs = FixedIntervalSampling(cfg)
+    veh = O.vehicle_dict()
+    ob = golden_io.unpack_obstacles(z, "ob_")
+    horizon = meta["N"] * meta["dt"]
+    stride = 1 if meta["n_cycles"] <= 16 else 4                  # the long run: every 4th cycle (CPU suite budget)
+    checked = 0
+    for ci in list(range(0, meta["n_cycles"], stride)):
+        x = z["c%d_x0" % ci]
+        v0 = float(x[3])
+        lo = max(0, v0 - 0.125 * horizon * veh["a_max"])
+        fs.samples_v = VelocitySampling(lo, max(lo + 5.0, v0 + 2), 4)
+        x0_lon, x0_lat = z["c%d_x0_lon" % ci], z["c%d_x0_lat" % ci]
+        for li, lv in enumerate(meta["cycles"][ci]["levels"]):
+            t, lon, d = fs.sample_grid(lv["level"], x0_lat, "velocity_keeping")
+            prob = {"t": t, "lon": lon, "d": d, "x0_lon": x0_lon, "x0_lat": x0_lat, "x0_orientation": float(x[2]),
+                    "x0_time_step": int(x[7]), "lon_mode": "velocity_keeping",
+                    "low_vel_mode": bool(v0 < meta["low_vel_mode_threshold"]), "dt": meta["dt"], "N": meta["N"],
+                    "factor": 1, "draw_all": bool(meta["draw_traj_set"]), "constraints": O.CONSTRAINTS,
+                    "cost": {"kind": "default", "desired_speed": meta["desired_velocity"], "desired_s": None,
+                             "desired_d": 0.0, "w_a": 5},
+                    "vehicle": veh, "ref": {k: z[k] for k in ("ref_pos", "ref_theta", "ref_curv", "ref_curv_d")},
+                    "ccosy": {"path": z["cc_path"], "S": z["cc_S"], "normals": z["cc_normals"], "limit": 20.0},
+                    "obstacles": ob}
+            o = O.plan_grid(prob, want_states=False, full_collision=False)
+            key = "c%d_l%d_" % (ci, li)
+            tag = "%s cycle %d level %d" % (meta["name"], ci, lv["level"])
+            assert o["n"] == lv["n"], tag
+            assert np.array_equal(o["kin_feasible"], z[key + "kin_feasible"]), tag
+            assert _close(o["cost"], z[key + "cost"]), tag
+            assert o["winner"] == lv["winner"], tag
+            assert (o["n_infeasible_kinematics"], o["n_infeasible_collision"]) == (lv["n_inf_kin"], lv["n_inf_col"]), tag
+            assert o["reasons"] == lv["reasons"], tag
+            checked += 1
+    assert checked >= min(9, meta["n_cycles"])
+
+
+def test_standstill_trajectory_matches_reference_fixture_on_the_host():
+    """ReactivePlanner._compute_standstill_trajectory + _compute_trajectory_pair (reactive_planner.py:667-713, :514-568)
+    are host code: the fixture's standstill output is reproduced without a GPU"""
+    from tests import helpers as H
+    z = np.load(os.path.join(GOLDEN, "plan_standstill_blocked.npz"))
+    meta = json.loads(str(z["plan_meta"]))
+    assert meta["ok"] and meta["standstill"] and [lv["found"] for lv in meta["levels"]] == [False, False, False]
+    prob = golden_io.unpack_problem(z)
+    planner = H.planner_from_fixture(prob, z["ref_path_raw"], z["x0"], desired_velocity=meta["desired_velocity"])
+    got = H.plan_output_arrays(planner._compute_trajectory_pair(planner._compute_standstill_trajectory()))
+    for key in ("out_cart", "out_curv", "out_lon", "out_lat"):
+        assert got[key].shape == z[key].shape, key
+        assert np.allclose(got[key], z[key], rtol=1e-9, atol=1e-9), key
+    assert got["out_cart"].shape[1] == prob["N"]                  # N states, not N + 1 (np.repeat(..., self.N))
