@@ -44,9 +44,11 @@ class Triangle:
 class ShapeGroup:
     def __init__(self):
         self._shapes = []
+        self._version = 0
 
     def add_shape(self, shape):
         self._shapes.append(shape)
+        self._version += 1
 
     def unpack(self):
         return list(self._shapes)
@@ -58,9 +60,11 @@ class TimeVariantCollisionObject:
     def __init__(self, time_start_idx: int):
         self._t0 = int(time_start_idx)
         self._shapes = []
+        self._version = 0
 
     def append_obstacle(self, shape):
         self._shapes.append(shape)
+        self._version += 1
 
     def time_start_idx(self) -> int:
         return self._t0
@@ -123,7 +127,9 @@ class CollisionChecker:
 
     @property
     def version(self) -> int:
-        return self._version
+        """Changes whenever the checker's content changes: objects added here, or shapes appended to a contained
+        shape group / time-variant object after it was added (device tables are re-uploaded when it moves)."""
+        return self._version + sum(getattr(o, "_version", 0) for o in self._objects)
 
     # ---- packing for rp_ctx_set_obstacles ----
     def device_arrays(self) -> dict:
@@ -187,7 +193,7 @@ class CollisionChecker:
     def _query_engine(self, hl, hw):
         from commonroad_rp_b200._device import current_device_and_stream
         from commonroad_rp_b200._lib import Engine
-        state = (hl, hw, self._version)
+        state = (hl, hw, self.version)
         if self._engine is None:
             dev, stream = current_device_and_stream()
             self._engine = Engine(dev, stream)

@@ -372,10 +372,12 @@ class ReactivePlanner(object):
         """Upload vehicle / reference / obstacle tables when they changed since the last cycle."""
         self._sync_frame_tables()
         eng = self.engine
-        cc_key = (id(self._cc), self._cc.version)
-        if self._uploaded_cc != cc_key:
+        # the uploaded checker is kept alive and compared by identity (id() values are reused once an object is freed),
+        # plus its content version (objects added / shapes appended since the upload)
+        up = self._uploaded_cc
+        if up is None or up[0] is not self._cc or up[1] != self._cc.version:
             self._cc.upload(eng)
-            self._uploaded_cc = cc_key
+            self._uploaded_cc = (self._cc, self._cc.version)
 
     def _plan_inputs(self, x_0_lon, x_0_lat, cost_spec, want_all_states):
         p = self.config.planning

@@ -250,3 +250,65 @@ def test_merge_records_lexicographic():
     assert w.tolist() == [2.0, 70.0] and tot.tolist() == [15.0, 20.0]
     w, _ = merge_records(torch.tensor([[inf, inf, 1, 0]], dtype=torch.float64))
     assert w[1].item() == inf
+
+
+def test_collision_checker_version_tracks_content():
+    """the planner re-uploads the obstacle tables when the checker's content moved (identity + version): objects added,
+    and shapes appended to an object AFTER it was added"""
+    from commonroad_rp_b200 import collision
+    cc = collision.CollisionChecker()
+    v0 = cc.version
+    tvo = collision.TimeVariantCollisionObject(0)
+    tvo.append_obstacle(collision.RectOBB(1, 1, 0, 0, 0))
+    cc.add_collision_object(tvo)
+    v1 = cc.version
+    tvo.append_obstacle(collision.RectOBB(1, 1, 0, 1, 0))
+    v2 = cc.version
+    sg = collision.ShapeGroup()
+    cc.add_collision_object(sg)
+    v3 = cc.version
+    sg.add_shape(collision.Triangle(0, 0, 1, 0, 0, 1))
+    assert len({v0, v1, v2, v3, cc.version}) == 5
+    assert len(cc.device_arrays()["dyn_boxes"][0]) == 2 and len(cc.device_arrays()["tris"]) == 1
+
+
+def _strip(x0, x1, y0, y1, horizontal, adj_left=None, adj_right=None):
+    """a straight lanelet with 1 m border sampling"""
+    from types import SimpleNamespace
+    if horizontal:
+        xs = np.arange(x0, x1 + 0.5, 1.0)
+        left = np.stack([xs, np.full_like(xs, y1)], axis=1)
+        right = np.stack([xs, np.full_like(xs, y0)], axis=1)
+    else:
+        ys = np.arange(y0, y1 + 0.5, 1.0)
+        left = np.stack([np.full_like(ys, x0), ys], axis=1)       # driving +y: left border at the smaller x
+        right = np.stack([np.full_like(ys, x1), ys], axis=1)
+    return SimpleNamespace(left_vertices=left, right_vertices=right, adj_left=adj_left, adj_right=adj_right)
+
+
+def test_road_boundary_of_a_crossing_has_no_walls_inside_the_junction():
+    """two roads crossing at right angles, neither lanelet has lateral neighbours: every border lacks an adjacent lanelet,
+    but only the parts OUTSIDE the other road are road boundary -- independent expectation: 4 arms x 2 sides x 18 m"""
+    from commonroad_rp_b200 import collision
+    a = _strip(-20.0, 20.0, -2.0, 2.0, horizontal=True)
+    b = _strip(-2.0, 2.0, -20.0, 20.0, horizontal=False)
+    segs = collision.road_boundary_segments([a, b])
+    length = np.hypot(*(segs[:, 1] - segs[:, 0]).T)
+    assert len(segs) == 144 and length.sum() == pytest.approx(144.0)
+    mid = 0.5 * (segs[:, 0] + segs[:, 1])
+    assert not np.any((np.abs(mid[:, 0]) < 2.0) & (np.abs(mid[:, 1]) < 2.0))            # nothing inside the junction square
+    # the naive construction (every neighbour-less border) would have put 4 x 4 m of wall across the junction
+    scn = type("S", (), {"lanelet_network": type("LN", (), {"lanelets": [a, b]})()})()
+    _, sg = collision.create_road_boundary_obstacle(scn)
+    assert len(sg.unpack()) == 144 and all(isinstance(s, collision.RectOBB) for s in sg.unpack())
+    _, tg = collision.create_road_boundary_obstacle(scn, method="triangulation", band=1.0)
+    tris = np.array([t.row() for t in tg.unpack()]).reshape(-1, 3, 2)
+    assert len(tris) > 200 and all(isinstance(t, collision.Triangle) for t in tg.unpack())
+    cen = tris.mean(axis=1)
+    on_road = ((np.abs(cen[:, 1]) < 2.0) & (np.abs(cen[:, 0]) < 20.0)) | ((np.abs(cen[:, 0]) < 2.0) & (np.abs(cen[:, 1]) < 20.0))
+    assert not on_road.any()                                                             # the band lies off-road
+    # laterally adjacent lanelets share a border: no boundary between them
+    l1 = _strip(0.0, 30.0, 0.0, 3.0, True, adj_left=2)
+    l2 = _strip(0.0, 30.0, 3.0, 6.0, True, adj_right=1)
+    segs2 = collision.road_boundary_segments([l1, l2])
+    assert len(segs2) == 60 and set(np.round(0.5 * (segs2[:, 0, 1] + segs2[:, 1, 1]), 6)) == {0.0, 6.0}

@@ -115,7 +115,10 @@ def test_oracle_matches_dense_full_fixture_on_a_subgrid():
     assert np.array_equal(o["kin_feasible"], z["r_kin_feasible"][full_idx])
     assert _close(o["cost"], z["r_cost"][full_idx])
     lab = z["r_label"][full_idx]
-    assert np.all(o["status"][lab == 3] == O.ST_COLLISION) and np.all(o["status"][lab == 1] == O.ST_FEASIBLE)
+    # label 3 = colliders the reference's lazy pass met; label 1 = kinematically feasible (collision state unknown
+    # unless it is the winner)
+    assert (lab == 3).any() and np.all(o["status"][lab == 3] == O.ST_COLLISION)
+    assert np.all(np.isin(o["status"][lab == 1], (O.ST_FEASIBLE, O.ST_COLLISION)))
     # the judge's own full CPU run of round 1: winner 97084, 2 713 kinematic rejects, 8 179 colliders before the winner
     assert (int(z["r_winner"]), int(z["r_n_inf_kin"]), int(z["r_n_inf_col"])) == (97084, 2713, 8179)
 
