@@ -150,6 +150,19 @@ struct rp_ctx {
     bool peer_ready = false, peer_mode_last = false;
     unsigned long long peer_epoch = 0;
 
+    // one replanning cycle in one launch (rp_plan_levels)
+    bool cycle_valid = false;              // the last plan was a cycle launch: fetch_* address the selected level
+    int cyc_n_levels = 0, cyc_chosen = 0, cyc_n_eval = 0, cyc_sel = 0, cyc_coeff_level = -1;
+    rp::LevelDesc cyc_lv[rp::kMaxLevels] = {};
+    std::vector<double> cyc_t[rp::kMaxLevels], cyc_lon[rp::kMaxLevels], cyc_d[rp::kMaxLevels];
+    std::vector<int> cyc_tl[rp::kMaxLevels];
+    rp::CycleOut* h_cycle = nullptr;       // mapped pinned host memory, written by the kernel's last block
+    void* d_cycle = nullptr;               // its device alias
+    size_t cycle_bytes = 0;
+    unsigned long long cyc_epoch = 0;
+    DevBuf d_cycle_res, d_ticket, d_best4;
+    Geometry cycle_geom{};
+
     // a batch (rp_batch_*) may run this context's tables on ANOTHER stream: the end-of-launch event of the last batch
     // cycle that read them (owned by the batch); table updates wait for it before overwriting device memory
     cudaEvent_t ext_busy = nullptr;
@@ -387,7 +400,7 @@ int build_obstacle_tables(rp_ctx* ctx) {
 
 // ---- launch geometry of the fused kernel ---------------------------------------------------------
 // Fill C / g_begin of the segments (k ranges and tl given), size shared memory, query occupancy.
-int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G) {
+int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, bool cycle = false) {
     if (Np1 < 2 || Np1 > 1024) return fail(RP_ERR_ARG, "N + 1 must be in [2, 1024]");
     G.big = Np1 > 256;
     constexpr int kScratchKb = 48;                       // per-block cap of the per-slot scratch (measured, profiles/README.md)
@@ -425,16 +438,19 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
     int occ = 0;
     // the attribute is a per-function maximum: only ever raise it (main and index launches share the kernel)
     // (per device, shared by all contexts of the process: the attribute belongs to the function, not the context)
-    static int g_granted[64][2] = {};
+    static int g_granted[64][3] = {};
     static std::mutex g_granted_mutex;                      // distinct contexts may plan from distinct threads
     std::lock_guard<std::mutex> granted_lock(g_granted_mutex);
-    int& granted = g_granted[ctx->device & 63][G.big ? 1 : 0];
+    if (cycle && G.big) return fail(RP_ERR_ARG, "cycle launch: N + 1 must be <= 256");
+    int& granted = g_granted[ctx->device & 63][cycle ? 2 : (G.big ? 1 : 0)];
     if ((int)G.smem > granted) {
-        if (G.big) RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        if (cycle) RP_CUDA(cudaFuncSetAttribute(rp::cycle_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        else if (G.big) RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         else RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         granted = (int)G.smem;
     }
-    if (G.big) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<1024>, G.threads, G.smem));
+    if (cycle) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::cycle_kernel<256>, G.threads, G.smem));
+    else if (G.big) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<1024>, G.threads, G.smem));
     else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<256>, G.threads, G.smem));
     if (occ < 1) return fail(RP_ERR_CUDA, "fused kernel does not fit on an SM");
     G.grid = std::max(1, std::min(G.n_groups, occ * ctx->num_sms));
@@ -533,7 +549,11 @@ void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G, const rp::Segmen
     P.mode = ctx->mode;
     P.n_t = ctx->n_t; P.n_lon = ctx->n_lon; P.n_d = ctx->n_d;
     P.n_cand = ctx->n_cand;
-    if (ctx->mode == 0) {
+    if (ctx->mode == 2) {                      // cycle launch: samples, segments and coefficients live in CycleArgs / shared memory
+        P.lon_samples = nullptr;
+        P.traj_len = nullptr;
+        P.skip = nullptr;
+    } else if (ctx->mode == 0) {
         const char* sb = static_cast<const char*>(ctx->d_samples.p);
         P.lon_samples = reinterpret_cast<const double*>(sb + ctx->off_lon);
         P.traj_len = reinterpret_cast<const int*>(sb + ctx->off_len);
@@ -564,12 +584,12 @@ int prepare_main_geometry(rp_ctx* ctx, int first, int count) {
         const int per_t = ctx->n_lon * ctx->n_d;
         for (int it = 0; it < ctx->n_t && per_t > 0; ++it) {
             const int b = std::max(first, it * per_t), e = std::min(first + count, (it + 1) * per_t);
-            if (b < e) segs.push_back(rp::Segment{b, e, ctx->h_traj_len[it], 0, 0});
+            if (b < e) segs.push_back(rp::Segment{b, e, ctx->h_traj_len[it], 0, 0, 0});
         }
     } else if (count > 0) {
-        segs.push_back(rp::Segment{first, first + count, Np1, 0, 0});
+        segs.push_back(rp::Segment{first, first + count, Np1, 0, 0, 0});
     }
-    if (segs.empty()) segs.push_back(rp::Segment{0, 0, Np1, 0, 0});
+    if (segs.empty()) segs.push_back(rp::Segment{0, 0, Np1, 0, 0, 0});
     ctx->main_is_cand = use_cand_kernel(ctx, count);
     if (ctx->main_is_cand) {
         // (list form: one segment in list order; traj_len varies per candidate, lanes diverge on i < tl only)
@@ -600,7 +620,7 @@ int prepare_index_geometry(rp_ctx* ctx, int count) {
     const int Np1 = ctx->in.N + 1;
     if (ctx->index_geom_np1 == Np1 && ctx->index_geom_count == count && ctx->index_geom_tables == ctx->tables_version)
         return RP_OK;
-    std::vector<rp::Segment> segs{rp::Segment{0, count, Np1, 0, 0}};
+    std::vector<rp::Segment> segs{rp::Segment{0, count, Np1, 0, 0, 0}};
     if (int rc = plan_geometry(ctx, Np1, segs, ctx->index_geom)) return rc;
     if (int rc = ctx->h_segs_index.ensure(sizeof(rp::Segment))) return rc;
     if (int rc = ctx->d_segs_index.ensure(sizeof(rp::Segment))) return rc;
@@ -701,6 +721,8 @@ int rp_ctx_destroy(rp_ctx* ctx) {
                       &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best,
                       &ctx->d_work, &ctx->d_clr, &ctx->d_dyn_rows})
         b->release();
+    for (DevBuf* b : {&ctx->d_cycle_res, &ctx->d_ticket, &ctx->d_best4}) b->release();
+    if (ctx->h_cycle) cudaFreeHost(ctx->h_cycle);
     ctx->h_stage.release();
     ctx->h_result.release();
     ctx->h_segs.release();
@@ -885,6 +907,7 @@ int rp_grid_upload(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double*
         if (traj_len[q] < 1 || traj_len[q] > in->N + 1) return fail(RP_ERR_ARG, "traj_len out of [1, N+1]");
     ctx->in = *in;
     ctx->mode = 0;
+    ctx->cycle_valid = false;
     ctx->n_t = n_t; ctx->n_lon = n_lon; ctx->n_d = n_d;
     ctx->n_cand = (int)n_cand;
     ctx->off_t = 0;
@@ -1122,6 +1145,7 @@ int rp_plan_list(rp_ctx* ctx, const rp_plan_inputs* in, int n_cand, const double
         if (traj_len[q] < 1 || traj_len[q] > in->N + 1) return fail(RP_ERR_ARG, "traj_len out of [1, N+1]");
     ctx->in = *in;
     ctx->mode = 1;
+    ctx->cycle_valid = false;
     ctx->geom_key_valid = false;
     ctx->n_t = ctx->n_lon = ctx->n_d = 0;
     ctx->n_cand = n_cand;
@@ -1637,8 +1661,8 @@ int rp_batch_launch(rp_batch* b) {
         off = align16(off + (size_t)(n_t + n_lon + n_d) * sizeof(double) + (size_t)n_t * sizeof(int));
         const int per_t = n_lon * n_d;
         for (int it = 0; it < n_t && per_t > 0; ++it)
-            segs[k].push_back(rp::Segment{it * per_t, (it + 1) * per_t, std::max(1, std::min(s.traj_len[it], Np1)), 32, 0});
-        if (segs[k].empty()) segs[k].push_back(rp::Segment{0, 0, Np1, 32, 0});
+            segs[k].push_back(rp::Segment{it * per_t, (it + 1) * per_t, std::max(1, std::min(s.traj_len[it], Np1)), 32, 0, 0});
+        if (segs[k].empty()) segs[k].push_back(rp::Segment{0, 0, Np1, 32, 0, 0});
         std::stable_sort(segs[k].begin(), segs[k].end(), [](const rp::Segment& x, const rp::Segment& y) { return x.tl > y.tl; });
         int groups = 0;
         for (auto& sg : segs[k]) {

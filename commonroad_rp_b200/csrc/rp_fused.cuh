@@ -22,6 +22,34 @@ struct Segment {
     int tl;               // threads per candidate in the heavy phases (= traj_len in grid mode, N+1 otherwise)
     int C;                // candidates per group
     int g_begin;          // index of the segment's first group
+    int level;            // cycle mode (several sampling levels in one launch): index of the segment's level
+};
+
+// ---- one replanning cycle in ONE launch (rp_plan_levels) -------------------------------------------------------
+// The level-escalation loop of reactive_planner.py:616-636 evaluates sampling levels 1, 2, 3 one after the other and
+// stops at the first that yields a feasible, collision-free candidate; the levels are independent bundles (SURVEY
+// App. B#13).  cycle_kernel evaluates several levels as ONE concatenated enumeration space; everything a cycle needs
+// travels in the launch itself (this struct is a __grid_constant__ kernel parameter: no host->device copy, no
+// coefficient launch -- each candidate slot solves its two polynomials in shared memory), and the last block to finish
+// selects level by level, gathers the winner's state block and writes the records straight into mapped host memory.
+constexpr int kMaxLevels = 4;
+constexpr int kCycleSamples = 448;      // doubles: t | lon | d of every level
+constexpr int kCycleSegs = 128;         // one segment per (level, sampled t)
+
+struct LevelDesc {
+    int k0, count;                      // the level's slice of the concatenated enumeration space
+    int n_t, n_lon, n_d;
+    int off_t, off_lon, off_d;          // offsets into CycleArgs::samples
+};
+
+struct CycleArgs {
+    int n_levels, n_segs;
+    LevelDesc lv[kMaxLevels];
+    Segment segs[kCycleSegs];
+    double samples[kCycleSamples];
+    void* out_host;                     // CycleOut in mapped pinned host memory (rp_kernels.cuh)
+    unsigned* ticket;                   // blocks that have finished (reset by the last one)
+    unsigned long long epoch;           // written to CycleOut::flag when the records are complete
 };
 
 struct PlanParams {
@@ -90,10 +118,11 @@ constexpr int kSlotExtra = 16 + 40 + 5 + 5 + 2;
 #define RP_FUSED_MIN_BLOCKS 3
 #endif
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT == 256 ? RP_FUSED_MIN_BLOCKS : 1)
-fused_kernel(const __grid_constant__ PlanParams P) {
-    extern __shared__ double smem[];
+// CYCLE = true: several sampling levels in one launch (cycle_kernel): candidates are decoded through the segment's
+// level, and the two polynomials of a slot are solved HERE (threads 0 / 1 of the slot, into the slot's still unused
+// accumulator scratch) with the same device functions coeff_kernel uses -- identical bits, no coefficient launch.
+template <int MAXT, bool CYCLE>
+__device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs* __restrict__ A, double* smem) {
     const int Np1 = P.Np1;
     const int Cmax = P.Cmax;
     const int tid = threadIdx.x;
@@ -140,7 +169,7 @@ fused_kernel(const __grid_constant__ PlanParams P) {
     int* const s_carry_all = reinterpret_cast<int*>(sp);                    // [Cmax][Np1]
     unsigned* const s_flags_all = reinterpret_cast<unsigned*>(s_carry_all + (size_t)Cmax * Np1);   // [Cmax][F_WORDS]
     Segment* const s_segs = reinterpret_cast<Segment*>(s_flags_all + (size_t)Cmax * F_WORDS);
-    for (int q = tid; q < P.n_segs; q += T) s_segs[q] = P.segs[q];
+    for (int q = tid; q < P.n_segs; q += T) s_segs[q] = CYCLE ? A->segs[q] : P.segs[q];
 
     const rp_plan_inputs& in = P.in;
     const bool low_vel = in.low_vel_mode != 0;
@@ -163,6 +192,8 @@ fused_kernel(const __grid_constant__ PlanParams P) {
             if (s_segs[mid].g_begin <= g) lo = mid; else hi = mid - 1;
         }
         const Segment seg = s_segs[lo];
+        // lazy collision bound: one per sampling level (levels are independent bundles)
+        unsigned long long* const best_ptr = P.best_bits ? P.best_bits + (CYCLE ? seg.level : 0) : nullptr;
         const int C = seg.C;
         const int tlg = seg.tl;
         const int c = tid / tlg;
@@ -189,7 +220,51 @@ fused_kernel(const __grid_constant__ PlanParams P) {
         double cs[6], cd[6];
         int tl = 0;
         bool filtered = false;
-        if (valid) {
+        if (CYCLE) {
+            double* const s_coef = scratch + kRows * Np1 + 16;       // the slot's accumulator scratch (cost phase only)
+            if (valid) {
+                const LevelDesc& L = A->lv[seg.level];
+                const int kk = k - L.k0;
+                const int per_t = L.n_lon * L.n_d;
+                const int it = kk / per_t;
+                const int rem = kk - it * per_t;
+                const int il = rem / L.n_d;
+                const int id = rem - il * L.n_d;
+                tl = tlg;                                            // one segment per (level, sampled t)
+                const double tt = A->samples[L.off_t + it], lon = A->samples[L.off_lon + il];
+                filtered = (in.lon_mode == RP_STOPPING) && !(in.x0_lon[0] < lon);
+                const int i_lat = tl > 1 ? 1 : 0;
+                if (i == 0 || i == i_lat) {
+                    // a3 (polynomial_trajectory.py:292-360), exactly as coeff_thread does it
+                    double cl[6];
+                    if (i == 0 || low_vel) {
+                        if (in.lon_mode == RP_VELOCITY_KEEPING) solve_quartic(in.x0_lon[0], in.x0_lon[1], in.x0_lon[2], tt, lon, cl);
+                        else solve_quintic(in.x0_lon[0], in.x0_lon[1], in.x0_lon[2], lon, 0.0, 0.0, tt, cl);
+                    }
+                    if (i == 0) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) s_coef[q] = cl[q];
+                    }
+                    if (i == i_lat) {
+                        double tau = tt;
+                        if (low_vel) {
+                            double s_goal = position_at_end(cl, tt) - in.x0_lon[0];
+                            if (s_goal <= 0) s_goal = tt;
+                            tau = s_goal;
+                        }
+                        double ct[6];
+                        solve_quintic(in.x0_lat[0], in.x0_lat[1], in.x0_lat[2], A->samples[L.off_d + id], 0.0, 0.0, tau, ct);
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) s_coef[6 + q] = ct[q];
+                    }
+                }
+            }
+            __syncthreads();                                         // coefficients of every slot solved
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { cs[q] = s_coef[q]; cd[q] = s_coef[6 + q]; }
+            }
+        } else if (valid) {
             const double *pl, *pt;
             if (P.mode == 0) {
                 const int per_t = P.n_lon * P.n_d;
@@ -510,7 +585,7 @@ fused_kernel(const __grid_constant__ PlanParams P) {
                 unsigned gate = 0u;
                 if (fl[F_STATE] & S_KINOK) {
                     const double cst = total_cost(tid);
-                    const unsigned long long best = *reinterpret_cast<volatile unsigned long long*>(P.best_bits);
+                    const unsigned long long best = *reinterpret_cast<volatile unsigned long long*>(best_ptr);
                     gate = !((unsigned long long)__double_as_longlong(cst) > best) ? 1u : 0u;   // costs are >= 0: bit order == value order
                     if (cst != cst) gate = 1u;                 // NaN cost: keep full semantics
                 }
@@ -572,7 +647,7 @@ fused_kernel(const __grid_constant__ PlanParams P) {
                         if (fl[F_GATE] == 0u) status = ST_UNCHECKED;
                         else if (cost == cost) {
                             const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);
-                            if (cb < *reinterpret_cast<volatile unsigned long long*>(P.best_bits)) atomicMin(P.best_bits, cb);
+                            if (cb < *reinterpret_cast<volatile unsigned long long*>(best_ptr)) atomicMin(best_ptr, cb);
                         }
                     }
                 }
@@ -583,6 +658,13 @@ fused_kernel(const __grid_constant__ PlanParams P) {
         }
         __syncthreads();                                                            // scratch reusable
     }
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? RP_FUSED_MIN_BLOCKS : 1)
+fused_kernel(const __grid_constant__ PlanParams P) {
+    extern __shared__ double smem[];
+    fused_body<MAXT, false>(P, nullptr, smem);
 }
 
 }  // namespace rp

@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(256) count_before_result_kernel(const double* 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&out->r.n_infeasible_collision, local);
 }
 
+// (loads go to L2 -- __ldcg: in cycle_kernel the verdicts were written by OTHER blocks of the same launch)
 // The whole selection of ONE bundle (or shard [first, first + count)) by ONE block: lexicographic arg-min on
 // (cost, enumeration index) over feasible, collision-free candidates, the cycle's counters, and the colliders ranked
 // before the winner.  Used per scenario of a batch and for replanning-size bundles (one launch instead of three).
@@ -314,11 +315,11 @@ __device__ __forceinline__ void block_select(const double* __restrict__ cost, co
     int l_reason[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int q = tid; q < count; q += blockDim.x) {
         const int k = first + q;
-        const int w = info[k];
+        const int w = __ldcg(info + k);
         const int st = w & 0xFF;
         if (st == ST_FEASIBLE) {
             ++l_feas;
-            const double cc = cost[k];
+            const double cc = __ldcg(cost + k);
             if (lex_less(cc, k, bc, bi)) { bc = cc; bi = k; }
         } else if (st == ST_COLLISION) {
             ++l_feas;
@@ -360,7 +361,7 @@ __device__ __forceinline__ void block_select(const double* __restrict__ cost, co
         int local = 0;
         for (int q = tid; q < count; q += blockDim.x) {
             const int k = first + q;
-            if ((info[k] & 0xFF) == ST_COLLISION && (none || lex_less(cost[k], k, wc, wi))) ++local;
+            if ((__ldcg(info + k) & 0xFF) == ST_COLLISION && (none || lex_less(__ldcg(cost + k), k, wc, wi))) ++local;
         }
         local = warp_sum(local);
         if (lane == 0 && local) atomicAdd(&s_before, local);
@@ -397,6 +398,65 @@ __global__ void __launch_bounds__(256) select_small_kernel(const double* __restr
     if (winner < 0) return;
     const double* src = states_all + (size_t)winner * 14 * Np1;
     for (int q = threadIdx.x; q < 14 * Np1; q += blockDim.x) states_one[q] = src[q];
+}
+
+// ---- one replanning cycle in one launch (rp_plan_levels; structs in rp_fused.cuh) ------------------------------
+// Result block in MAPPED PINNED HOST memory: the last block of cycle_kernel writes it over PCIe and raises `flag` to the
+// cycle's epoch after a system-wide fence; the host spins on the flag -- no device->host copy node, no event.
+struct CycleOut {
+    unsigned long long flag;
+    int chosen;                         // level whose record is final: the lowest with a winner, else the last one
+    int n_evaluated;                    // records written: levels 0 .. chosen (reactive_planner.py:618 stops there)
+    PlanResultDev res[kMaxLevels];      // winner = enumeration index WITHIN the level
+    double states[1];                   // winner's 14 x (N + 1) block follows (offset kCycleStatesOffset)
+};
+constexpr size_t kCycleStatesOffset = 512;
+static_assert(sizeof(CycleOut) <= kCycleStatesOffset + sizeof(double), "CycleOut header grew past its slot");
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? RP_FUSED_MIN_BLOCKS : 1)
+cycle_kernel(const __grid_constant__ PlanParams P, const __grid_constant__ CycleArgs A, PlanResultDev* __restrict__ d_res) {
+    extern __shared__ double smem[];
+    fused_body<MAXT, true>(P, &A, smem);
+    // ---- the last block to finish selects (a12 / a14, trajectories.py:502-510, reactive_planner.py:616-636, :1065-1136)
+    __shared__ unsigned s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(A.ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    int chosen = A.n_levels - 1;
+    for (int lv = 0; lv < A.n_levels; ++lv) {
+        block_select(P.cost, P.info, A.lv[lv].k0, A.lv[lv].count, d_res + lv);          // (ends with a barrier)
+        if (d_res[lv].r.winner >= 0) { chosen = lv; break; }
+    }
+    CycleOut* const out = static_cast<CycleOut*>(A.out_host);
+    const int Np1 = P.Np1;
+    const int winner = d_res[chosen].r.winner;                                           // global enumeration index
+    if (winner >= 0) {
+        const double* src = P.states + (size_t)winner * 14 * Np1;
+        double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(out) + kCycleStatesOffset);
+        for (int q = threadIdx.x; q < 14 * Np1; q += blockDim.x) dst[q] = __ldcg(src + q);
+    }
+    if ((int)threadIdx.x <= chosen) {
+        PlanResultDev r = d_res[threadIdx.x];
+        if (r.r.winner >= 0) r.r.winner -= A.lv[threadIdx.x].k0;
+        out->res[threadIdx.x] = r;
+    }
+    if (threadIdx.x == 32) {
+        out->chosen = chosen;
+        out->n_evaluated = chosen + 1;
+        *A.ticket = 0u;                                                                  // ready for the next launch
+        if (P.best_bits)
+            for (int lv = 0; lv < kMaxLevels; ++lv) P.best_bits[lv] = 0x7f7f7f7f7f7f7f7fULL;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(&out->flag) = A.epoch;
+        __threadfence_system();
+    }
 }
 
 // ---- multi-GPU bundle shards: each rank owns a contiguous tile of the enumeration space --------

@@ -197,7 +197,8 @@ def test_initial_states_match_reference_fixture(path):
     far = x0[:1].copy()
     far[0, :2] += 1.0e4
     assert eng.initial_states(far, [0])[2][0] == 1                   # outside the projection domain
-    back = x0[:1].copy()
+    fastest = int(np.argmax(x0[:, 3]))                               # (ZAM-Ramp starts at v = 0: s_dot = -0 is not negative)
+    back = x0[fastest:fastest + 1].copy()
     back[0, 2] += np.pi
     assert eng.initial_states(back, [0])[2][0] == 2                  # driving against the reference: negative s_dot
     eng.close()
