@@ -75,6 +75,12 @@ SIGNATURES = {
     "rp_grid_upload": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _ip, C.c_int, _dp, C.c_int, _dp]),
     "rp_grid_launch": (C.c_int, [C.c_void_p]),
     "rp_grid_result": (C.c_int, [C.c_void_p, C.POINTER(PlanResult)]),
+    "rp_plan_levels": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PlanResult), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32)]),
+    "rp_select_level": (C.c_int, [C.c_void_p, C.c_int]),
+    "rp_cycle_host_block": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "rp_cycle_limits": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "rp_plan_list": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _dp, _ip, _bp, C.POINTER(PlanResult)]),
     "rp_set_candidate_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rp_ctx_set_kernel_policy": (C.c_int, [C.c_void_p, C.c_int]),
@@ -288,6 +294,76 @@ class Engine:
         res = PlanResult()
         self._check(self._lib.rp_grid_result(self._ctx, C.byref(res)))
         return res
+
+    # ---- one replanning cycle in one launch (rp_plan_levels) ----
+    def cycle_limits(self):
+        """(max_levels, max_samples, max_segments, max_work) of one ``plan_levels`` launch."""
+        lim = getattr(Engine, "_cycle_limits", None)
+        if lim is None:
+            a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+            self._check(self._lib.rp_cycle_limits(C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+            lim = Engine._cycle_limits = (a.value, b.value, c.value, d.value)
+        return lim
+
+    def plan_levels(self, inputs, levels):
+        """Several sampling levels in ONE launch: ``levels`` = [(t, lon, d, traj_len), ...] in escalation order.
+        Returns (records, chosen): ``records[j]`` is the PlanResult of level j for j <= chosen, the first level with a
+        winner (else the last).  fetch_* afterwards address the chosen level (``select_level`` switches)."""
+        b = getattr(self, "_cyc", None)
+        if b is None:
+            max_levels, max_samples = self.cycle_limits()[:2]
+            b = self._cyc = {"n": np.zeros((3, max_levels), dtype=np.int32), "t": np.zeros(max_samples), "lon": np.zeros(max_samples),
+                             "d": np.zeros(max_samples), "tl": np.zeros(max_samples, dtype=np.int32),
+                             "res": (PlanResult * max_levels)(), "n_eval": C.c_int32(), "chosen": C.c_int32()}
+            b["ptr"] = (b["n"][0].ctypes.data, b["n"][1].ctypes.data, b["n"][2].ctypes.data, b["t"].ctypes.data,
+                        b["tl"].ctypes.data, b["lon"].ctypes.data, b["d"].ctypes.data)
+            b["refs"] = (C.byref(b["n_eval"]), C.byref(b["chosen"]))
+        n, bt, bl, bd, btl = b["n"], b["t"], b["lon"], b["d"], b["tl"]
+        ot = ol = od = 0
+        counts = []
+        for j, (t, lon, d, tl) in enumerate(levels):
+            nt, nl, nd = len(t), len(lon), len(d)
+            n[0, j] = nt
+            n[1, j] = nl
+            n[2, j] = nd
+            bt[ot:ot + nt] = t
+            btl[ot:ot + nt] = tl
+            bl[ol:ol + nl] = lon
+            bd[od:od + nd] = d
+            ot += nt
+            ol += nl
+            od += nd
+            counts.append(nt * nl * nd)
+        self._N = inputs.N
+        self.plan_generation += 1
+        rc = self._lib.rp_plan_levels(self._ctx, C.byref(inputs), len(levels), *b["ptr"], b["res"], *b["refs"])
+        if rc != 0:
+            self._check(rc)
+        chosen = b["chosen"].value
+        self._level_counts = counts
+        self._n_cand = counts[chosen]
+        self._cyc_chosen = chosen
+        return b["res"], chosen
+
+    def cycle_winner_states(self):
+        """The chosen level's winner states (14 x (N + 1)) of the last ``plan_levels`` call, copied out of the mapped
+        result block the kernel wrote (no library call)."""
+        n = N_STATE_ROWS * (self._N + 1)
+        view = getattr(self, "_cyc_view", None)
+        if view is None or view[0] != n:
+            ptr, cnt = C.c_void_p(), C.c_int64()
+            self._check(self._lib.rp_cycle_host_block(self._ctx, C.byref(ptr), C.byref(cnt)))
+            buf = (C.c_double * n).from_address(ptr.value)
+            view = self._cyc_view = (n, ptr.value, np.frombuffer(buf, dtype=np.float64).reshape(N_STATE_ROWS, self._N + 1))
+        else:
+            # the block is re-allocated only when N grows, which changes n as well
+            pass
+        return view[2].copy()
+
+    def select_level(self, level):
+        """After ``plan_levels``: make fetch_states / fetch_candidates / fetch_coeffs address that evaluated level."""
+        self._check(self._lib.rp_select_level(self._ctx, int(level)))
+        self._n_cand = self._level_counts[level]
 
     def plan_list(self, inputs, coeffs_lon, coeffs_lat, traj_len, skip=None):
         cl = _f64(coeffs_lon).reshape(-1, 6)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -73,6 +74,9 @@ struct PinBuf {
         cap = 0;
     }
 };
+
+// largest (candidates x time steps) of one cycle launch (rp_plan_levels): the states of every kept candidate are written
+constexpr long long kCycleMaxWork = 1LL << 20;
 
 // launch geometry of the fused kernel
 struct Geometry {
@@ -162,6 +166,8 @@ struct rp_ctx {
     unsigned long long cyc_epoch = 0;
     DevBuf d_cycle_res, d_ticket, d_best4;
     Geometry cycle_geom{};
+    std::vector<int> cyc_geom_key;         // shapes the cached work decomposition was built for
+    std::vector<rp::Segment> cyc_geom_segs;
 
     // a batch (rp_batch_*) may run this context's tables on ANOTHER stream: the end-of-launch event of the last batch
     // cycle that read them (owned by the batch); table updates wait for it before overwriting device memory
@@ -400,11 +406,11 @@ int build_obstacle_tables(rp_ctx* ctx) {
 
 // ---- launch geometry of the fused kernel ---------------------------------------------------------
 // Fill C / g_begin of the segments (k ranges and tl given), size shared memory, query occupancy.
-int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, bool cycle = false) {
+int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, bool cycle = false, int threads = 0) {
     if (Np1 < 2 || Np1 > 1024) return fail(RP_ERR_ARG, "N + 1 must be in [2, 1024]");
     G.big = Np1 > 256;
     constexpr int kScratchKb = 48;                       // per-block cap of the per-slot scratch (measured, profiles/README.md)
-    G.threads = G.big ? ((Np1 + 31) / 32) * 32 : 256;
+    G.threads = G.big ? ((Np1 + 31) / 32) * 32 : (threads > 0 ? threads : 256);
     const size_t per_slot = (size_t)(rp::kRows * Np1 + rp::kSlotExtra) * sizeof(double) +
                             (size_t)(Np1 + rp::F_WORDS) * sizeof(int);
     // Shared-memory policy (measured on B200, profiles/README.md): three resident blocks per SM beat two,
@@ -435,6 +441,9 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
     if (G.smem > budget) return fail(RP_ERR_ARG, "horizon too long for shared-memory scratch");
     G.stage_ref = (G.smem + ref_bytes <= target) ? 1 : 0;
     if (G.stage_ref) G.smem += ref_bytes;
+    // (decided below, once the grid is known: a block that runs only a group or two reads the tables through L1 --
+    // staging 13 KB per block was 18 % of a replanning-size launch, profiles/README.md round 2)
+    const size_t smem_without_ref = G.smem - (G.stage_ref ? ref_bytes : 0);
     int occ = 0;
     // the attribute is a per-function maximum: only ever raise it (main and index launches share the kernel)
     // (per device, shared by all contexts of the process: the attribute belongs to the function, not the context)
@@ -444,16 +453,23 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
     if (cycle && G.big) return fail(RP_ERR_ARG, "cycle launch: N + 1 must be <= 256");
     int& granted = g_granted[ctx->device & 63][cycle ? 2 : (G.big ? 1 : 0)];
     if ((int)G.smem > granted) {
-        if (cycle) RP_CUDA(cudaFuncSetAttribute(rp::cycle_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        if (cycle) {
+            RP_CUDA(cudaFuncSetAttribute(rp::cycle_kernel<256, rp::CycleArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+            RP_CUDA(cudaFuncSetAttribute(rp::cycle_kernel<256, rp::CycleArgsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        }
         else if (G.big) RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         else RP_CUDA(cudaFuncSetAttribute(rp::fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         granted = (int)G.smem;
     }
-    if (cycle) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::cycle_kernel<256>, G.threads, G.smem));
+    if (cycle) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::cycle_kernel<256, rp::CycleArgs>, G.threads, G.smem));
     else if (G.big) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<1024>, G.threads, G.smem));
     else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp::fused_kernel<256>, G.threads, G.smem));
     if (occ < 1) return fail(RP_ERR_CUDA, "fused kernel does not fit on an SM");
     G.grid = std::max(1, std::min(G.n_groups, occ * ctx->num_sms));
+    if (G.stage_ref && G.n_groups < 3 * G.grid) {
+        G.stage_ref = 0;
+        G.smem = smem_without_ref;
+    }
     return RP_OK;
 }
 
@@ -667,6 +683,46 @@ int launch_states_for_index(rp_ctx* ctx, const int* d_index, int count, double* 
     P.stage_dyn = 0;
     if (count <= 4) P.stage_ref = 0;
     return launch_fused(ctx, P, ctx->index_geom);
+}
+
+// cycle launch: the coefficient arrays / device sample lists of the SELECTED level, built on demand (only the lazy paths
+// need them: rp_fetch_coeffs and the re-evaluation of a non-winner's states; the cycle kernel itself solves in shared memory)
+int cycle_ensure_coeffs(rp_ctx* ctx) {
+    const int lv = ctx->cyc_sel;
+    if (ctx->cyc_coeff_level == lv) return RP_OK;
+    const int n_t = (int)ctx->cyc_t[lv].size(), n_lon = (int)ctx->cyc_lon[lv].size(), n_d = (int)ctx->cyc_d[lv].size();
+    ctx->off_t = 0;
+    ctx->off_lon = (size_t)n_t * sizeof(double);
+    ctx->off_d = ctx->off_lon + (size_t)n_lon * sizeof(double);
+    ctx->off_len = ctx->off_d + (size_t)n_d * sizeof(double);
+    const size_t bytes = ctx->off_len + (size_t)n_t * sizeof(int);
+    if (int rc = ctx->h_stage.ensure(bytes)) return rc;
+    if (int rc = ctx->d_samples.ensure(bytes)) return rc;
+    if (ctx->stage_pending) RP_CUDA(cudaEventSynchronize(ctx->ev_stage));
+    char* hs = static_cast<char*>(ctx->h_stage.p);
+    std::memcpy(hs + ctx->off_t, ctx->cyc_t[lv].data(), (size_t)n_t * sizeof(double));
+    std::memcpy(hs + ctx->off_lon, ctx->cyc_lon[lv].data(), (size_t)n_lon * sizeof(double));
+    std::memcpy(hs + ctx->off_d, ctx->cyc_d[lv].data(), (size_t)n_d * sizeof(double));
+    std::memcpy(hs + ctx->off_len, ctx->cyc_tl[lv].data(), (size_t)n_t * sizeof(int));
+    RP_CUDA(cudaMemcpyAsync(ctx->d_samples.p, hs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RP_CUDA(cudaEventRecord(ctx->ev_stage, ctx->stream));
+    ctx->stage_pending = true;
+    const int n = n_t * n_lon * n_d;
+    const int n_lon_sys = n_t * n_lon, n_lat_sys = ctx->in.low_vel_mode ? n : n_t * n_d;
+    if (int rc = ctx->d_lon_coef.ensure((size_t)std::max(n_lon_sys, 1) * 6 * sizeof(double))) return rc;
+    if (int rc = ctx->d_lat_coef.ensure((size_t)std::max(n_lat_sys, 1) * 6 * sizeof(double))) return rc;
+    if (int rc = ctx->d_lat_tau.ensure((size_t)std::max(n_lat_sys, 1) * sizeof(double))) return rc;
+    if (n_lon_sys + n_lat_sys > 0) {
+        const char* sb = static_cast<const char*>(ctx->d_samples.p);
+        rp::coeff_kernel<<<(n_lon_sys + n_lat_sys + 127) / 128, 128, 0, ctx->stream>>>(
+            n_t, n_lon, n_d, ctx->in.low_vel_mode, ctx->in.lon_mode, reinterpret_cast<const double*>(sb + ctx->off_t),
+            reinterpret_cast<const double*>(sb + ctx->off_lon), reinterpret_cast<const double*>(sb + ctx->off_d), ctx->in.x0_lon[0],
+            ctx->in.x0_lon[1], ctx->in.x0_lon[2], ctx->in.x0_lat[0], ctx->in.x0_lat[1], ctx->in.x0_lat[2], ctx->d_lon_coef.as<double>(),
+            ctx->d_lat_coef.as<double>(), ctx->d_lat_tau.as<double>());
+        RP_CUDA(cudaGetLastError());
+    }
+    ctx->cyc_coeff_level = lv;
+    return RP_OK;
 }
 
 }  // namespace
@@ -1135,6 +1191,249 @@ int rp_plan_grid(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double* t
     return rp_grid_result(ctx, out);
 }
 
+// ---- one replanning cycle in one launch --------------------------------------------------------------------------
+int rp_cycle_limits(int32_t* max_levels, int32_t* max_samples, int32_t* max_segments, int64_t* max_work) {
+    if (max_levels) *max_levels = rp::kMaxLevels;
+    if (max_samples) *max_samples = rp::kCycleSamples;
+    if (max_segments) *max_segments = rp::kCycleSegs;
+    if (max_work) *max_work = kCycleMaxWork;
+    return RP_OK;
+}
+
+int rp_cycle_host_block(rp_ctx* ctx, void** states, int64_t* n_doubles) {
+    if (!ctx || !states || !n_doubles) return fail(RP_ERR_ARG, "null argument");
+    if (!ctx->h_cycle) return fail(RP_ERR_STATE, "no cycle launch yet");
+    *states = reinterpret_cast<char*>(ctx->h_cycle) + rp::kCycleStatesOffset;
+    *n_doubles = (int64_t)((ctx->cycle_bytes - rp::kCycleStatesOffset) / sizeof(double));
+    return RP_OK;
+}
+
+#ifdef RP_CYCLE_TIMING
+}  // extern "C"
+#include <chrono>
+namespace {
+struct BigParam { char bytes[7424]; };
+struct SmallParam { char bytes[64]; };
+template <class PT>
+__global__ void null_flag_kernel(const __grid_constant__ PT p, unsigned long long* flag_host, unsigned long long epoch) {
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(flag_host) = epoch + (unsigned long long)p.bytes[0];
+    }
+}
+}  // namespace
+extern "C" {
+// launch floor: null kernel with a small / large parameter block, completion seen through a mapped flag or a stream sync
+int rp_debug_launch_floor(rp_ctx* ctx, int iters, double* us4) {
+    if (int rc = bind(ctx)) return rc;
+    unsigned long long* h = nullptr;
+    cudaHostAlloc((void**)&h, 64, cudaHostAllocMapped);
+    unsigned long long* d = nullptr;
+    cudaHostGetDevicePointer((void**)&d, h, 0);
+    *h = 0;
+    BigParam big{};
+    SmallParam small{};
+    unsigned long long epoch = 0;
+    for (int variant = 0; variant < 4; ++variant) {
+        double total = 0;
+        for (int it = 0; it < iters + 20; ++it) {
+            ++epoch;
+            auto t0 = std::chrono::steady_clock::now();
+            if (variant & 1) null_flag_kernel<BigParam><<<9, 64, 0, ctx->stream>>>(big, d, epoch);
+            else null_flag_kernel<SmallParam><<<9, 64, 0, ctx->stream>>>(small, d, epoch);
+            if (variant & 2) cudaStreamSynchronize(ctx->stream);
+            else while (*reinterpret_cast<volatile unsigned long long*>(h) != epoch) { }
+            auto t1 = std::chrono::steady_clock::now();
+            if (it >= 20) total += std::chrono::duration<double, std::micro>(t1 - t0).count();
+        }
+        us4[variant] = total / iters;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(h);
+    return RP_OK;
+}
+int rp_debug_stamps(long long* out32) {
+    return cudaMemcpyFromSymbol(out32, rp::g_stamps, sizeof(long long) * 32) == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
+#endif
+
+int rp_select_level(rp_ctx* ctx, int level) {
+    if (!ctx) return fail(RP_ERR_ARG, "null context");
+    if (!ctx->cycle_valid) return fail(RP_ERR_STATE, "rp_select_level: the last plan was not an rp_plan_levels call");
+    if (level < 0 || level >= ctx->cyc_n_eval) return fail(RP_ERR_ARG, "rp_select_level: that level was not evaluated");
+    ctx->cyc_sel = level;
+    const rp::LevelDesc& L = ctx->cyc_lv[level];
+    ctx->mode = 0;
+    ctx->n_t = L.n_t; ctx->n_lon = L.n_lon; ctx->n_d = L.n_d;
+    ctx->n_cand = L.count;
+    return RP_OK;
+}
+
+int rp_plan_levels(rp_ctx* ctx, const rp_plan_inputs* in, int n_levels, const int32_t* n_t, const int32_t* n_lon,
+                   const int32_t* n_d, const double* t_cat, const int32_t* traj_len_cat, const double* lon_cat,
+                   const double* d_cat, rp_plan_result* out, int32_t* n_evaluated, int32_t* chosen) {
+    if (int rc = bind(ctx)) return rc;
+    if (int rc = check_inputs(in)) return rc;
+    if (n_levels < 1 || n_levels > rp::kMaxLevels) return fail(RP_ERR_ARG, "rp_plan_levels: 1 .. 4 levels");
+    if (!n_t || !n_lon || !n_d || !t_cat || !traj_len_cat || !lon_cat || !d_cat || !out) return fail(RP_ERR_ARG, "null array");
+    if (ctx->range_count >= 0) return fail(RP_ERR_ARG, "rp_plan_levels does not shard (reset rp_set_candidate_range)");
+    if (in->continuous_collision_check) return fail(RP_ERR_ARG, "rp_plan_levels does not run the continuous collision check");
+    if (in->cost_kind == RP_COST_NONE && n_levels > 1)
+        return fail(RP_ERR_ARG, "rp_plan_levels: without a device cost the host selects, one level at a time");
+    const int Np1 = in->N + 1;
+    if (Np1 > 256) return fail(RP_ERR_ARG, "rp_plan_levels: N + 1 must be <= 256");
+    if (int rc = check_ready(ctx)) return rc;
+    // ---- the launch's argument block: levels, segments (one per level and sampled t), samples -------------------
+    rp::CycleArgs A{};
+    A.n_levels = n_levels;
+    std::vector<rp::Segment> segs;
+    int k0 = 0, n_samp = 0;
+    size_t ot = 0, ol = 0, od = 0;
+    for (int lv = 0; lv < n_levels; ++lv) {
+        if (n_t[lv] < 0 || n_lon[lv] < 0 || n_d[lv] < 0) return fail(RP_ERR_ARG, "negative sample count");
+        const long long cnt = (long long)n_t[lv] * n_lon[lv] * n_d[lv];
+        if (n_samp + n_t[lv] + n_lon[lv] + n_d[lv] > rp::kCycleSamples) return fail(RP_ERR_ARG, "rp_plan_levels: too many samples for one launch");
+        if ((long long)(k0 + cnt) * Np1 > kCycleMaxWork) return fail(RP_ERR_ARG, "rp_plan_levels: too many candidates for one launch");
+        rp::LevelDesc& L = A.lv[lv];
+        L.k0 = k0; L.count = (int)cnt;
+        L.n_t = n_t[lv]; L.n_lon = n_lon[lv]; L.n_d = n_d[lv];
+        L.off_t = n_samp; L.off_lon = n_samp + n_t[lv]; L.off_d = L.off_lon + n_lon[lv];
+        std::memcpy(A.samples + L.off_t, t_cat + ot, (size_t)n_t[lv] * sizeof(double));
+        std::memcpy(A.samples + L.off_lon, lon_cat + ol, (size_t)n_lon[lv] * sizeof(double));
+        std::memcpy(A.samples + L.off_d, d_cat + od, (size_t)n_d[lv] * sizeof(double));
+        n_samp += n_t[lv] + n_lon[lv] + n_d[lv];
+        const int per_t = n_lon[lv] * n_d[lv];
+        for (int it = 0; it < n_t[lv] && per_t > 0; ++it) {
+            const int tl = traj_len_cat[ot + it];
+            if (tl < 1 || tl > Np1) return fail(RP_ERR_ARG, "traj_len out of [1, N+1]");
+            segs.push_back(rp::Segment{k0 + it * per_t, k0 + (it + 1) * per_t, tl, 0, 0, lv});
+        }
+        ctx->cyc_t[lv].assign(t_cat + ot, t_cat + ot + n_t[lv]);
+        ctx->cyc_tl[lv].assign(traj_len_cat + ot, traj_len_cat + ot + n_t[lv]);
+        ctx->cyc_lon[lv].assign(lon_cat + ol, lon_cat + ol + n_lon[lv]);
+        ctx->cyc_d[lv].assign(d_cat + od, d_cat + od + n_d[lv]);
+        ctx->cyc_lv[lv] = L;
+        ot += (size_t)n_t[lv]; ol += (size_t)n_lon[lv]; od += (size_t)n_d[lv];
+        k0 += (int)cnt;
+    }
+    const int n_total = k0;
+    if ((int)segs.size() > rp::kCycleSegs) return fail(RP_ERR_ARG, "rp_plan_levels: too many sampled horizons for one launch");
+    if (segs.empty()) segs.push_back(rp::Segment{0, 0, Np1, 0, 0, 0});
+    ctx->in = *in;
+    ctx->mode = 2;
+    ctx->n_t = ctx->n_lon = ctx->n_d = 0;
+    ctx->n_cand = n_total;
+    ctx->geom_key_valid = false;
+    ctx->segs_dirty = true;                       // the grid form's cached decomposition no longer describes the inputs
+    // work decomposition: depends on the shapes only (not on the sample values), so consecutive cycles reuse it.
+    // A replanning-size launch is latency bound: the smallest blocks that still give ONE wave (one or two warps per
+    // scheduler instead of two blocks' worth) -- measured, profiles/README.md round 2.
+    {
+        std::vector<int> key;
+        key.reserve(segs.size() * 3 + 4);
+        key.push_back(Np1);
+        key.push_back((int)ctx->tables_version);
+        key.push_back(ctx->obs.n_dyn);
+        for (const auto& sg : segs) { key.push_back(sg.k_begin); key.push_back(sg.k_end); key.push_back(sg.tl); }
+        if (key != ctx->cyc_geom_key) {
+            int max_tl = 1;
+            for (const auto& sg : segs) max_tl = std::max(max_tl, std::min(sg.tl, Np1));
+            int rc = RP_OK;
+            for (int threads : {64, 128, 256}) {
+                if (threads < max_tl) continue;
+                std::vector<rp::Segment> trial = segs;
+                rc = plan_geometry(ctx, Np1, trial, ctx->cycle_geom, true, threads);
+                if (rc != RP_OK) break;
+                if (ctx->cycle_geom.n_groups <= ctx->cycle_geom.grid || threads == 256) { segs.swap(trial); break; }
+            }
+            if (rc != RP_OK) return rc;
+            ctx->cyc_geom_key.swap(key);
+            ctx->cyc_geom_segs = segs;
+        } else {
+            segs = ctx->cyc_geom_segs;
+        }
+    }
+    A.n_segs = (int)segs.size();
+    std::memcpy(A.segs, segs.data(), segs.size() * sizeof(rp::Segment));
+    // ---- buffers ---------------------------------------------------------------------------------------------
+    if (int rc = ctx->d_cost.ensure((size_t)std::max(n_total, 1) * sizeof(double))) return rc;
+    if (int rc = ctx->d_info.ensure((size_t)std::max(n_total, 1) * sizeof(int))) return rc;
+    if (int rc = ctx->d_states_all.ensure((size_t)std::max(n_total, 1) * 14 * Np1 * sizeof(double))) return rc;
+    if (int rc = ctx->d_cycle_res.ensure(sizeof(rp::PlanResultDev) * rp::kMaxLevels)) return rc;
+    if (!ctx->d_ticket.p) {
+        if (int rc = ctx->d_ticket.ensure(sizeof(unsigned))) return rc;
+        if (int rc = ctx->d_best4.ensure(sizeof(unsigned long long) * rp::kMaxLevels)) return rc;
+        RP_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(unsigned), ctx->stream));
+        RP_CUDA(cudaMemsetAsync(ctx->d_best4.p, 0x7f, sizeof(unsigned long long) * rp::kMaxLevels, ctx->stream));
+    }
+    const size_t need = rp::kCycleStatesOffset + (size_t)14 * Np1 * sizeof(double);
+    if (ctx->cycle_bytes < need) {
+        RP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_cycle) cudaFreeHost(ctx->h_cycle);
+        ctx->h_cycle = nullptr;
+        void* p = nullptr;
+        RP_CUDA(cudaHostAlloc(&p, need, cudaHostAllocMapped));
+        std::memset(p, 0, need);
+        ctx->h_cycle = static_cast<rp::CycleOut*>(p);
+        RP_CUDA(cudaHostGetDevicePointer(&ctx->d_cycle, p, 0));
+        ctx->cycle_bytes = need;
+    }
+    A.out_host = ctx->d_cycle;
+    A.ticket = ctx->d_ticket.as<unsigned>();
+    A.epoch = ++ctx->cyc_epoch;
+    PlanParams P{};
+    fill_common(ctx, P, ctx->cycle_geom, nullptr);
+    P.index = nullptr;
+    P.cost = ctx->d_cost.as<double>();
+    P.info = ctx->d_info.as<int>();
+    P.states = ctx->d_states_all.as<double>();        // every kept candidate: the last block gathers the winner's block
+    P.states_by_slot = 0;
+    P.best_bits = in->check_collision == 2 ? ctx->d_best4.as<unsigned long long>() : nullptr;
+    const Geometry& G = ctx->cycle_geom;
+    if (A.n_segs <= rp::kCycleSegsSmall && n_samp <= rp::kCycleSamplesSmall) {
+        rp::CycleArgsSmall S{};
+        S.n_levels = A.n_levels; S.n_segs = A.n_segs;
+        std::memcpy(S.lv, A.lv, sizeof(A.lv));
+        std::memcpy(S.segs, A.segs, (size_t)A.n_segs * sizeof(rp::Segment));
+        std::memcpy(S.samples, A.samples, (size_t)n_samp * sizeof(double));
+        S.out_host = A.out_host; S.ticket = A.ticket; S.epoch = A.epoch;
+        rp::cycle_kernel<256, rp::CycleArgsSmall><<<G.grid, G.threads, G.smem, ctx->stream>>>(P, S, ctx->d_cycle_res.as<rp::PlanResultDev>());
+    } else {
+        rp::cycle_kernel<256, rp::CycleArgs><<<G.grid, G.threads, G.smem, ctx->stream>>>(P, A, ctx->d_cycle_res.as<rp::PlanResultDev>());
+    }
+    RP_CUDA(cudaGetLastError());
+    ++ctx->n_launches;
+    // ---- wait for the result block (written by the kernel into mapped host memory) -----------------------------
+    const volatile unsigned long long* flag = &ctx->h_cycle->flag;
+    for (unsigned spins = 0; *flag != A.epoch; ++spins) {
+        if ((spins & 0x3fffu) == 0x3fffu) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) {
+                if (*flag == A.epoch) break;
+                return fail(RP_ERR_CUDA, "rp_plan_levels: the cycle kernel finished without publishing its result");
+            }
+            if (q != cudaErrorNotReady) return fail(RP_ERR_CUDA, std::string("rp_plan_levels: ") + cudaGetErrorString(q));
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const rp::CycleOut* H = ctx->h_cycle;
+    ctx->cyc_n_levels = n_levels;
+    ctx->cyc_chosen = H->chosen;
+    ctx->cyc_n_eval = H->n_evaluated;
+    ctx->cyc_coeff_level = -1;
+    for (int lv = 0; lv < H->n_evaluated; ++lv) out[lv] = H->res[lv].r;
+    if (n_evaluated) *n_evaluated = H->n_evaluated;
+    if (chosen) *chosen = H->chosen;
+    ctx->cycle_valid = true;
+    ctx->have_inputs = false;                     // rp_grid_launch needs a fresh rp_grid_upload
+    ctx->have_plan = true;
+    ctx->peer_mode_last = false;
+    ctx->small_path_last = false;
+    ctx->states_all_valid = in->want_all_states != 0;
+    ctx->h_states_valid = false;
+    return rp_select_level(ctx, H->chosen);
+}
+
 int rp_plan_list(rp_ctx* ctx, const rp_plan_inputs* in, int n_cand, const double* coeffs_lon, const double* coeffs_lat,
                  const int32_t* traj_len, const uint8_t* skip, rp_plan_result* out) {
     if (int rc = bind(ctx)) return rc;
@@ -1179,9 +1478,27 @@ int rp_fetch_states(rp_ctx* ctx, int idx, double* out) {
     if (idx < 0 || idx >= ctx->n_cand) return fail(RP_ERR_ARG, "candidate index out of range");
     const size_t bytes = (size_t)14 * (ctx->in.N + 1) * sizeof(double);
     const rp::PlanResultDev* hres = static_cast<rp::PlanResultDev*>(ctx->h_result.p);
+    const int k0 = ctx->cycle_valid ? ctx->cyc_lv[ctx->cyc_sel].k0 : 0;         // cycle launch: the selected level's slice
     if (ctx->states_all_valid) {
-        RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_all.as<double>() + (size_t)idx * 14 * (ctx->in.N + 1), bytes,
+        RP_CUDA(cudaMemcpyAsync(out, ctx->d_states_all.as<double>() + (size_t)(k0 + idx) * 14 * (ctx->in.N + 1), bytes,
                                 cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (ctx->cycle_valid) {
+        if (ctx->cyc_sel == ctx->cyc_chosen && ctx->h_cycle->res[ctx->cyc_chosen].r.winner == idx) {
+            std::memcpy(out, reinterpret_cast<const char*>(ctx->h_cycle) + rp::kCycleStatesOffset, bytes);   // written by the kernel
+            return RP_OK;
+        }
+        // any other candidate: re-evaluated on demand (needs the level's coefficient arrays)
+        if (int rc = cycle_ensure_coeffs(ctx)) return rc;
+        RP_CUDA(cudaMemcpyAsync(ctx->d_index.p, &idx, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        DevBuf tmp;
+        if (int rc = tmp.ensure(bytes)) return rc;
+        int rc = launch_states_for_index(ctx, ctx->d_index.as<int>(), 1, tmp.as<double>());
+        cudaError_t e = rc ? cudaSuccess : cudaMemcpyAsync(out, tmp.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+        tmp.release();
+        if (rc) return rc;
+        if (e != cudaSuccess || e2 != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return RP_OK;
     } else {
         if (!ctx->h_states_valid) {
             RP_CUDA(cudaMemcpyAsync(ctx->h_result.p, ctx->d_result.p, rp_ctx::kResBytes + ctx->res_states_bytes, cudaMemcpyDeviceToHost,
@@ -1208,11 +1525,12 @@ int rp_fetch_candidates(rp_ctx* ctx, double* cost, int32_t* status, int32_t* rea
     if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
     const int n = ctx->n_cand;
     if (n == 0) return RP_OK;
-    if (cost) RP_CUDA(cudaMemcpyAsync(cost, ctx->d_cost.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const int k0 = ctx->cycle_valid ? ctx->cyc_lv[ctx->cyc_sel].k0 : 0;         // cycle launch: the selected level's slice
+    if (cost) RP_CUDA(cudaMemcpyAsync(cost, ctx->d_cost.as<double>() + k0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<int> info;
     if (status || reason || step) {
         info.resize(n);
-        RP_CUDA(cudaMemcpyAsync(info.data(), ctx->d_info.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RP_CUDA(cudaMemcpyAsync(info.data(), ctx->d_info.as<int>() + k0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
     RP_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int q = 0; q < (int)info.size(); ++q) {
@@ -1228,6 +1546,8 @@ int rp_fetch_coeffs(rp_ctx* ctx, double* coeffs_lon, double* coeffs_lat, double*
     if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
     const int n = ctx->n_cand;
     if (n == 0) return RP_OK;
+    if (ctx->cycle_valid)
+        if (int rc = cycle_ensure_coeffs(ctx)) return rc;
     if (ctx->mode == 1) {
         if (coeffs_lon) RP_CUDA(cudaMemcpyAsync(coeffs_lon, ctx->d_lon_coef.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
         if (coeffs_lat) RP_CUDA(cudaMemcpyAsync(coeffs_lat, ctx->d_lat_coef.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1511,12 +1831,14 @@ int rp_peer_close(rp_ctx* ctx) {
 
 int rp_last_main_kernel(rp_ctx* ctx) {
     if (!ctx) return 0;
+    if (ctx->cycle_valid) return RP_KERNEL_STEP_PARALLEL;
     return ctx->main_is_cand ? RP_KERNEL_CANDIDATE_MAJOR : RP_KERNEL_STEP_PARALLEL;
 }
 
 int rp_launches_per_plan(rp_ctx* ctx) {
     if (!ctx) return 0;
     // coeff, fused, argmin partial / merge / count, winner states (+ the dynamic-obstacle rows of the candidate-major kernel)
+    if (ctx->cycle_valid) return 1;                               // rp_plan_levels: the whole cycle is one kernel
     if (ctx->small_path_last) return ctx->mode == 0 ? 3 : 2;      // coeff, fused (states of every kept candidate), select
     if (ctx->peer_mode_last)        // prep, main kernel, argmin partial / merge, peer merge / count, winner states
         return ctx->mode == 0 ? 7 : 6 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);

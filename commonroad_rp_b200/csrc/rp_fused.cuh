@@ -42,14 +42,27 @@ struct LevelDesc {
     int off_t, off_lon, off_d;          // offsets into CycleArgs::samples
 };
 
-struct CycleArgs {
+// (the parameter block rides in the launch packet: 7.4 KB cost a null launch 2.8 us more than 64 bytes on this part, so
+// cycles that fit -- e.g. levels 1-3 of the bundled N = 20 configurations -- use the SMALL instantiation)
+constexpr int kCycleSamplesSmall = 160;
+constexpr int kCycleSegsSmall = 32;
+
+template <int NSEG, int NSAMP>
+struct CycleArgsT {
     int n_levels, n_segs;
     LevelDesc lv[kMaxLevels];
-    Segment segs[kCycleSegs];
-    double samples[kCycleSamples];
+    Segment segs[NSEG];
+    double samples[NSAMP];
     void* out_host;                     // CycleOut in mapped pinned host memory (rp_kernels.cuh)
     unsigned* ticket;                   // blocks that have finished (reset by the last one)
     unsigned long long epoch;           // written to CycleOut::flag when the records are complete
+};
+using CycleArgs = CycleArgsT<kCycleSegs, kCycleSamples>;
+using CycleArgsSmall = CycleArgsT<kCycleSegsSmall, kCycleSamplesSmall>;
+struct NoCycleArgs {                    // fused_kernel: never dereferenced
+    Segment segs[1];
+    LevelDesc lv[1];
+    double samples[1];
 };
 
 struct PlanParams {
@@ -114,6 +127,15 @@ enum : unsigned { S_VALID = 1u, S_FILTERED = 2u, S_ALIVE = 4u, S_KINOK = 8u, S_K
 constexpr int kRows = 11;         // th, kap, x, y, tx, ty, ct0..ct4
 constexpr int kSlotExtra = 16 + 40 + 5 + 5 + 2;
 
+// development aid (-DRP_CYCLE_TIMING, tools/probe_cycle.py): cycle stamps of block 0 at the phase boundaries
+#ifdef RP_CYCLE_TIMING
+__device__ long long g_stamps[32];
+__device__ __forceinline__ long long rp_globaltimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define RP_STAMP(n) do { if (blockIdx.x == 0 && threadIdx.x == 0) { g_stamps[n] = clock64(); if ((n) == 0 || (n) == 11) g_stamps[16 + (n)] = rp_globaltimer(); } } while (0)
+#else
+#define RP_STAMP(n) do { } while (0)
+#endif
+
 #ifndef RP_FUSED_MIN_BLOCKS
 #define RP_FUSED_MIN_BLOCKS 3
 #endif
@@ -121,8 +143,8 @@ constexpr int kSlotExtra = 16 + 40 + 5 + 5 + 2;
 // CYCLE = true: several sampling levels in one launch (cycle_kernel): candidates are decoded through the segment's
 // level, and the two polynomials of a slot are solved HERE (threads 0 / 1 of the slot, into the slot's still unused
 // accumulator scratch) with the same device functions coeff_kernel uses -- identical bits, no coefficient launch.
-template <int MAXT, bool CYCLE>
-__device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs* __restrict__ A, double* smem) {
+template <int MAXT, bool CYCLE, class ARGS>
+__device__ __forceinline__ void fused_body(const PlanParams& P, const ARGS* __restrict__ A, double* smem) {
     const int Np1 = P.Np1;
     const int Cmax = P.Cmax;
     const int tid = threadIdx.x;
@@ -179,10 +201,17 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
     const bool fs = in.cost_kind == RP_COST_FAILSAFE;
     const double w_a = fs ? 1.0 : in.w_a;
     const double des_d = fs ? 0.0 : in.desired_d;
+    // cycle launches in select-only mode: only the BEST candidate of each group (feasible, collision-free, lowest
+    // (cost, index)) writes its state block -- the cycle's winner is the best of its own group, and the stores of all
+    // the other kept candidates (2.3 KB each at N = 20) were what the publish phase and the closing fence waited for
+    const bool defer_states = CYCLE && P.states != nullptr && !in.want_all_states;
+    __shared__ unsigned long long s_gbest;
+    __shared__ int s_gk;
     // element-strided loops over (slot, step) pairs advance without integer division
     const int e_c0 = tid / Np1, e_i0 = tid - e_c0 * Np1;
     const int e_dc = T / Np1, e_di = T - e_dc * Np1;
     __syncthreads();
+    RP_STAMP(1);
 
     for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
         // ---- locate the group's segment (block-uniform) ---------------------------------------------
@@ -233,33 +262,26 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
                 tl = tlg;                                            // one segment per (level, sampled t)
                 const double tt = A->samples[L.off_t + it], lon = A->samples[L.off_lon + il];
                 filtered = (in.lon_mode == RP_STOPPING) && !(in.x0_lon[0] < lon);
-                const int i_lat = tl > 1 ? 1 : 0;
-                if (i == 0 || i == i_lat) {
-                    // a3 (polynomial_trajectory.py:292-360), exactly as coeff_thread does it
-                    double cl[6];
-                    if (i == 0 || low_vel) {
-                        if (in.lon_mode == RP_VELOCITY_KEEPING) solve_quartic(in.x0_lon[0], in.x0_lon[1], in.x0_lon[2], tt, lon, cl);
-                        else solve_quintic(in.x0_lon[0], in.x0_lon[1], in.x0_lon[2], lon, 0.0, 0.0, tt, cl);
+                if (i == 0) {
+                    // a3 (polynomial_trajectory.py:292-360), exactly as coeff_thread does it.  One thread solves both
+                    // systems: straight-line code, so the two independent elimination chains overlap (on two lanes of
+                    // one warp they would run one after the other)
+                    double cl[6], ct[6];
+                    if (in.lon_mode == RP_VELOCITY_KEEPING) solve_quartic(in.x0_lon[0], in.x0_lon[1], in.x0_lon[2], tt, lon, cl);
+                    else solve_quintic(in.x0_lon[0], in.x0_lon[1], in.x0_lon[2], lon, 0.0, 0.0, tt, cl);
+                    double tau = tt;
+                    if (low_vel) {
+                        double s_goal = position_at_end(cl, tt) - in.x0_lon[0];
+                        if (s_goal <= 0) s_goal = tt;
+                        tau = s_goal;
                     }
-                    if (i == 0) {
+                    solve_quintic(in.x0_lat[0], in.x0_lat[1], in.x0_lat[2], A->samples[L.off_d + id], 0.0, 0.0, tau, ct);
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) s_coef[q] = cl[q];
-                    }
-                    if (i == i_lat) {
-                        double tau = tt;
-                        if (low_vel) {
-                            double s_goal = position_at_end(cl, tt) - in.x0_lon[0];
-                            if (s_goal <= 0) s_goal = tt;
-                            tau = s_goal;
-                        }
-                        double ct[6];
-                        solve_quintic(in.x0_lat[0], in.x0_lat[1], in.x0_lat[2], A->samples[L.off_d + id], 0.0, 0.0, tau, ct);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) s_coef[6 + q] = ct[q];
-                    }
+                    for (int q = 0; q < 6; ++q) { s_coef[q] = cl[q]; s_coef[6 + q] = ct[q]; }
                 }
             }
             __syncthreads();                                         // coefficients of every slot solved
+        RP_STAMP(2);
             if (valid) {
 #pragma unroll
                 for (int q = 0; q < 6; ++q) { cs[q] = s_coef[q]; cd[q] = s_coef[6 + q]; }
@@ -293,6 +315,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
         }
         const bool live = valid && !filtered;
         const bool in_traj = live && i < tl;
+        if (tid == 0) { s_gbest = ~0ULL; s_gk = 0x7fffffff; }
         __syncthreads();                                                            // flags initialised
 
         // ---- polynomial evaluation (reactive_planner.py:733-777) -------------------------------
@@ -324,6 +347,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
             }
         }
         __syncthreads();                                                            // pre-filter known
+        RP_STAMP(3);
         const unsigned pre = lane ? s_flags[F_PRE] : 0u;
         const bool alive = live && pre == 0u;
         const bool act = alive && i < tl;
@@ -400,6 +424,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
             s_kap[i] = kappa;
         }
         __syncthreads();                                                            // theta/kappa rows complete
+        RP_STAMP(4);
 
         // ---- limits (reactive_planner.py:971-1017) + projection (:908-917) -------------------------
         double x = 0., y = 0., kdot = 0.;
@@ -416,6 +441,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
             }
         }
         __syncthreads();                                                            // verdict known
+        RP_STAMP(5);
         const unsigned bad = lane ? s_flags[F_BAD] : NONE;
         const unsigned pbad = lane ? s_flags[F_PBAD] : NONE;
         const bool kin_ok = alive && bad == NONE && pbad == NONE;
@@ -443,7 +469,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
                 if (i == Np1 - 1) { s_park[0] = v; s_park[1] = s; s_park[2] = d; s_park[3] = th_cl; }
                 if (i == Np1 / 2) s_park[4] = v;                  // v[int(len(v) / 2)]
             }
-            if (P.states != nullptr) {
+            if (P.states != nullptr && !defer_states) {
                 double* o = P.states + (size_t)(P.states_by_slot ? slot : k) * 14 * Np1 + i;
                 o[0] = x; o[Np1] = y; o[2 * Np1] = th_gl; o[3 * Np1] = v; o[4 * Np1] = a; o[5 * Np1] = kappa;
                 o[6 * Np1] = kdot; o[7 * Np1] = s; o[8 * Np1] = d; o[9 * Np1] = th_cl; o[10 * Np1] = sv;
@@ -451,6 +477,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
             }
         }
         __syncthreads();
+        RP_STAMP(6);
 
         // ---- horizon extension (trajectories.py:168-197, :302-332), element-strided over the tails ----
         const int n_elem = C * Np1;
@@ -505,7 +532,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
                 if (i2 == Np1 - 1) { park[0] = ve; park[1] = se; park[2] = de; park[3] = the; }
                 if (i2 == Np1 / 2) park[4] = ve;
             }
-            if (P.states != nullptr) {
+            if (P.states != nullptr && !defer_states) {
                 const int k2 = (int)fl[F_K];
                 const int slot2 = seg.k_begin + (g - seg.g_begin) * C + c2;
                 double* o = P.states + (size_t)(P.states_by_slot ? slot2 : k2) * 14 * Np1 + i2;
@@ -515,6 +542,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
             }
         }
         __syncthreads();
+        RP_STAMP(7);
 
         // ---- cost (cost_function.py:51-71, :85-92); np.sum order per SURVEY App. B#5 ----------------
         const bool par_sum = Np1 >= 8 && Np1 <= 128;
@@ -594,6 +622,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
             __syncthreads();
         }
 
+        RP_STAMP(8);
         // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), element-strided ----------------
         if (in.check_collision) {
             for (int e = tid, c2 = e_c0, i2 = e_i0; e < n_elem; e += T, c2 += e_dc, i2 += e_di) {
@@ -616,8 +645,11 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
             }
         }
         __syncthreads();
+        RP_STAMP(9);
 
         // ---- per-candidate verdict ------------------------------------------------------------------
+        unsigned long long my_bits = ~0ULL;                  // cost bits of a feasible, collision-free candidate (defer_states)
+        int my_k = 0x7fffffff;
         if (tid < C && P.info != nullptr) {
             const unsigned* fl = s_flags_all + (size_t)tid * F_WORDS;
             const unsigned st2 = fl[F_STATE];
@@ -654,9 +686,45 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const CycleArgs*
                 const int k2 = (int)fl[F_K];
                 P.info[k2] = pack_info(status, reason, step);
                 if (P.cost) P.cost[k2] = cost;
+                if (defer_states && status == ST_FEASIBLE && cost == cost) {
+                    my_bits = (unsigned long long)__double_as_longlong(cost);       // costs are >= 0: bit order == value order
+                    my_k = k2;
+                    atomicMin(&s_gbest, my_bits);
+                }
+            }
+        }
+        if (defer_states) {
+            __syncthreads();
+            if (my_bits == s_gbest && my_k != 0x7fffffff) atomicMin(&s_gk, my_k);   // ties: the lowest enumeration index
+            __syncthreads();
+            if (valid && k == s_gk) {
+                // this slot holds the group's best candidate: its threads write the polynomial part from their
+                // registers and the extension part from the slot's shared-memory rows (same expressions as above)
+                double* o = P.states + (size_t)k * 14 * Np1;
+                if (i < tl) {
+                    double* q = o + i;
+                    q[0] = x; q[Np1] = y; q[2 * Np1] = th_gl; q[3 * Np1] = v; q[4 * Np1] = a; q[5 * Np1] = kappa;
+                    q[6 * Np1] = kdot; q[7 * Np1] = s; q[8 * Np1] = d; q[9 * Np1] = th_cl; q[10 * Np1] = sv;
+                    q[11 * Np1] = sa; q[12 * Np1] = dv; q[13 * Np1] = da;
+                }
+                const double* last = s_last;
+                for (int i2 = tl + i; i2 < Np1; i2 += tl) {
+                    const double tau = (double)(i2 - tl + 1) * dt;
+                    const double ae = last[4];
+                    double ve = last[3] + tau * ae;
+                    ve = ve * (ve >= 0 ? 1.0 : 0.0);
+                    double sve = last[10] + tau * 0.0;
+                    sve = sve * (sve >= 0 ? 1.0 : 0.0);
+                    const double dve = last[12] + tau * 0.0;
+                    double* q = o + i2;
+                    q[0] = s_x[i2]; q[Np1] = s_y[i2]; q[2 * Np1] = last[2]; q[3 * Np1] = ve; q[4 * Np1] = ae; q[5 * Np1] = last[5];
+                    q[6 * Np1] = last[6]; q[7 * Np1] = last[7] + tau * last[10]; q[8 * Np1] = last[8] + tau * last[12];
+                    q[9 * Np1] = last[9]; q[10 * Np1] = sve; q[11 * Np1] = last[11]; q[12 * Np1] = dve; q[13 * Np1] = last[13];
+                }
             }
         }
         __syncthreads();                                                            // scratch reusable
+        RP_STAMP(10);
     }
 }
 
@@ -664,7 +732,7 @@ template <int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT == 256 ? RP_FUSED_MIN_BLOCKS : 1)
 fused_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
-    fused_body<MAXT, false>(P, nullptr, smem);
+    fused_body<MAXT, false, NoCycleArgs>(P, nullptr, smem);
 }
 
 }  // namespace rp

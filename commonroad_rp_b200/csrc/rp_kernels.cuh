@@ -348,8 +348,9 @@ __device__ __forceinline__ void block_select(const double* __restrict__ cost, co
     }
     __syncthreads();
     if (warp == 0) {
-        bc = lane < 8 ? w_cost[lane] : __longlong_as_double(0x7ff0000000000000LL);
-        bi = lane < 8 ? w_idx[lane] : 0x7fffffff;
+        const int n_warps = (int)(blockDim.x >> 5);             // (blocks of 64 .. 256 threads)
+        bc = lane < n_warps ? w_cost[lane] : __longlong_as_double(0x7ff0000000000000LL);
+        bi = lane < n_warps ? w_idx[lane] : 0x7fffffff;
         warp_lexmin(bc, bi);
         if (lane == 0) { s_wc = bc; s_wi = bi; }
     }
@@ -413,19 +414,29 @@ struct CycleOut {
 constexpr size_t kCycleStatesOffset = 512;
 static_assert(sizeof(CycleOut) <= kCycleStatesOffset + sizeof(double), "CycleOut header grew past its slot");
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT == 256 ? RP_FUSED_MIN_BLOCKS : 1)
-cycle_kernel(const __grid_constant__ PlanParams P, const __grid_constant__ CycleArgs A, PlanResultDev* __restrict__ d_res) {
+// (two blocks per SM at most: a cycle launch is latency bound and runs blocks of 64 .. 256 threads in one wave; the
+// register room keeps the deferred state values of defer_states out of local memory)
+template <int MAXT, class ARGS>
+__global__ void __launch_bounds__(MAXT, 2)
+cycle_kernel(const __grid_constant__ PlanParams P, const __grid_constant__ ARGS A, PlanResultDev* __restrict__ d_res) {
     extern __shared__ double smem[];
-    fused_body<MAXT, true>(P, &A, smem);
+    RP_STAMP(0);
+    fused_body<MAXT, true, ARGS>(P, &A, smem);
+    RP_STAMP(11);
     // ---- the last block to finish selects (a12 / a14, trajectories.py:502-510, reactive_planner.py:616-636, :1065-1136)
     __shared__ unsigned s_ticket;
     __threadfence();
     __syncthreads();
+#ifdef RP_CYCLE_TIMING
+    if (threadIdx.x == 0) atomicMax((unsigned long long*)&g_stamps[31], (unsigned long long)rp_globaltimer());   // last body end + fence
+#endif
     if (threadIdx.x == 0) s_ticket = atomicAdd(A.ticket, 1u);
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
+#ifdef RP_CYCLE_TIMING
+    if (threadIdx.x == 0) { g_stamps[12] = clock64(); g_stamps[28] = rp_globaltimer(); }
+#endif
     int chosen = A.n_levels - 1;
     for (int lv = 0; lv < A.n_levels; ++lv) {
         block_select(P.cost, P.info, A.lv[lv].k0, A.lv[lv].count, d_res + lv);          // (ends with a barrier)
@@ -451,9 +462,15 @@ cycle_kernel(const __grid_constant__ PlanParams P, const __grid_constant__ Cycle
         if (P.best_bits)
             for (int lv = 0; lv < kMaxLevels; ++lv) P.best_bits[lv] = 0x7f7f7f7f7f7f7f7fULL;
     }
+#ifdef RP_CYCLE_TIMING
+    if (threadIdx.x == 0) { g_stamps[13] = clock64(); g_stamps[29] = rp_globaltimer(); }
+#endif
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+#ifdef RP_CYCLE_TIMING
+        g_stamps[14] = clock64(); g_stamps[30] = rp_globaltimer();
+#endif
         *reinterpret_cast<volatile unsigned long long*>(&out->flag) = A.epoch;
         __threadfence_system();
     }

@@ -29,8 +29,8 @@ from commonroad_rp_b200.polynomial_trajectory import QuarticTrajectory, QuinticT
 from commonroad_rp_b200.sampling import (PositionSampling, SamplingSpace, TimeSampling, VelocitySampling,
                                           sampling_space_factory)
 from commonroad_rp_b200.state import ReactivePlannerState
-from commonroad_rp_b200.trajectories import (CartesianSample, CurviLinearSample, FeasibilityStatus, TrajectoryBundle,
-                                              TrajectorySample, _DeviceBacking)
+from commonroad_rp_b200.trajectories import (CartesianSample, CurviLinearSample, DeviceTrajectorySample, FeasibilityStatus,
+                                              TrajectoryBundle, TrajectorySample, _DeviceBacking)
 from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration, VehicleConfiguration
 from commonroad_rp_b200.utility.general import retrieve_desired_velocity_from_pp, shift_orientation
 from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem, interpolate_angle
@@ -64,21 +64,64 @@ class _LazyViews(collections.abc.Sequence):
 logger = logging.getLogger("RP_LOGGER")
 
 _EPS = 1e-5
+_TWO_PI = 2.0 * math.pi
+
+
+def _curvilinear_states(t0, factor, pos_curv, v_l, a_l, th_l, kap_l):
+    """the curvilinear CustomState list of plan()'s result (reference :543-556: velocity, acceleration and orientation
+    are the CARTESIAN ones, yaw_rate carries the curvature)"""
+    out = []
+    new_cs = CustomState.__new__
+    ts = t0
+    for pos, vel, acc, th, kap in zip(pos_curv, v_l, a_l, th_l, kap_l):
+        c = new_cs(CustomState)
+        c.__dict__ = {"time_step": ts, "position": pos, "velocity": vel, "acceleration": acc, "orientation": th, "yaw_rate": kap}
+        out.append(c)
+        ts += factor
+    return out
+
+
+class _LazyTrajectory(Trajectory):
+    """Trajectory whose ``state_list`` is built on first access (only used with the package's own stand-in classes)"""
+
+    def __init__(self, initial_time_step, make_states):
+        self.initial_time_step = initial_time_step
+        self._make_states = make_states
+        self._states = None
+
+    @property
+    def state_list(self):
+        if self._states is None:
+            self._states = self._make_states()
+            self._make_states = None
+        return self._states
+
+    @state_list.setter
+    def state_list(self, value):
+        self._states = value
+        self._make_states = None
 
 
 class _BundleArrays(dict):
     """Per-candidate verdict arrays of the device bundle, fetched on first use and shared by all the
     lazy TrajectorySample views of that bundle."""
 
-    def __init__(self, engine, generation, all_states):
+    def __init__(self, engine, generation, all_states, level=None):
         super().__init__()
         self._engine = engine
         self._generation = generation
+        self._level = level              # cycle launch (several levels evaluated together): this bundle's level index
         dict.__setitem__(self, "all_states", all_states)
+
+    def select(self):
+        """make the engine's fetch_* calls address this bundle's level (cycle launches hold several)"""
+        if self._level is not None:
+            self._engine.select_level(self._level)
 
     def __missing__(self, key):
         if self._engine.plan_generation != self._generation:
             raise RuntimeError("device bundle replaced by a newer plan() call")
+        self.select()
         cost, status, reason, step = self._engine.fetch_candidates()
         self.update(cost=cost, status=status, reason=reason, step=step)
         return dict.__getitem__(self, key)
@@ -125,6 +168,16 @@ class ReactivePlanner(object):
         self._uploaded_cc = None
         self._uploaded_vehicle = None
         self.last_result = None        # rp_plan_result of the last evaluated level
+        # level escalation (:616-636) in one submission: plan() lets the device evaluate the next sampling levels together
+        # with the current one -- as long as their candidates x time steps stay below this budget (about one wave of the
+        # step-parallel kernel) -- and picks the lowest level with a winner; 0 = one level per submission
+        self.speculation_budget = 200000
+        self._escalating = False       # inside plan()'s escalation loop
+        self._spec = None              # records of the levels evaluated ahead in the current cycle
+        self._plan_serial = 0
+        self._inputs = None            # the rp_plan_inputs struct, reused across cycles
+        self._constraint_key, self._constraint_mask = None, 0
+        self._grid_cache = {}          # per sampling level: ordered t / lon arrays (+ traj_len) while the sample sets live
 
         self.config: Optional[ReactivePlannerConfiguration] = None
         self.reset(config)
@@ -206,6 +259,8 @@ class ReactivePlanner(object):
             self.config = config
         else:
             assert self.config is not None, "<ReactivePlanner.reset(). No Configuration object provided>"
+        self._spec = None                  # levels evaluated ahead belong to the previous initial state
+        self._plan_serial += 1
         self._reset_statistics()
         if collision_checker is None:
             self.set_collision_checker(scenario=self.config.scenario)
@@ -379,19 +434,46 @@ class ReactivePlanner(object):
             self._cc.upload(eng)
             self._uploaded_cc = (self._cc, self._cc.version)
 
-    def _plan_inputs(self, x_0_lon, x_0_lat, cost_spec, want_all_states):
+    def _plan_inputs(self, x_0_lon, x_0_lat, cost_spec, want_all_states, check_collision=None):
+        """The cycle's rp_plan_inputs (one struct per planner, refilled every cycle)."""
         p = self.config.planning
-        return _lib.Engine.make_inputs(
-            x_0_lon, x_0_lat, self.x_0.orientation, self.x_0.time_step, self._low_vel_mode,
-            self.config.sampling.longitudinal_mode, self.N, self.dt, factor=p.factor, draw_all=self._draw_traj_set,
-            constraints=p.constraints_to_check, cost_kind=cost_spec["cost_kind"],
-            desired_speed=cost_spec["desired_speed"], desired_s=cost_spec["desired_s"],
-            desired_d=cost_spec["desired_d"], w_a=cost_spec["w_a"], want_all_states=want_all_states,
+        pi = self._inputs
+        if pi is None:
+            pi = self._inputs = _lib.PlanInputs()
+        pi.x0_lon[0], pi.x0_lon[1], pi.x0_lon[2] = x_0_lon[0], x_0_lon[1], x_0_lon[2]
+        pi.x0_lat[0], pi.x0_lat[1], pi.x0_lat[2] = x_0_lat[0], x_0_lat[1], x_0_lat[2]
+        pi.x0_orientation = self.x_0.orientation
+        pi.x0_time_step = int(self.x_0.time_step)
+        pi.low_vel_mode = 1 if self._low_vel_mode else 0
+        pi.lon_mode = _lib.STOPPING if self.config.sampling.longitudinal_mode == "stopping" else _lib.VELOCITY_KEEPING
+        pi.N = self.N
+        pi.dt = self.dt
+        pi.factor = int(p.factor)
+        pi.draw_all = 1 if self._draw_traj_set else 0
+        key = tuple(p.constraints_to_check)
+        if key != self._constraint_key:
+            mask = 0
+            for name in key:
+                mask |= _lib.CONSTRAINT_BITS[name]
+            self._constraint_key, self._constraint_mask = key, mask
+        pi.constraint_mask = self._constraint_mask
+        kind = cost_spec["cost_kind"]
+        pi.cost_kind = kind
+        ds, dp = cost_spec["desired_speed"], cost_spec["desired_s"]
+        pi.has_desired_speed = 0 if ds is None else 1
+        pi.has_desired_s = 0 if dp is None else 1
+        pi.desired_speed = 0.0 if ds is None else ds
+        pi.desired_s = 0.0 if dp is None else dp
+        pi.desired_d = cost_spec["desired_d"]
+        pi.w_a = cost_spec["w_a"]
+        pi.want_all_states = 1 if want_all_states else 0
+        if check_collision is None:
             # the reference's collision pass is lazy (:1031-1063); full flags only when every trajectory is kept
-            check_collision=_lib.COLLISION_ALL if (want_all_states or cost_spec["cost_kind"] == _lib.COST_NONE)
-            else _lib.COLLISION_LAZY,
-            # reference :1049-1058 (the hull check of the first discretely collision-free candidate, on the device)
-            continuous_collision_check=bool(p.continuous_collision_check) and cost_spec["cost_kind"] != _lib.COST_NONE)
+            check_collision = _lib.COLLISION_ALL if (want_all_states or kind == _lib.COST_NONE) else _lib.COLLISION_LAZY
+        pi.check_collision = check_collision
+        # reference :1049-1058 (the hull check of the first discretely collision-free candidate, on the device)
+        pi.continuous_collision_check = 1 if (p.continuous_collision_check and kind != _lib.COST_NONE) else 0
+        return pi
 
     def _device_cost_spec(self):
         """Fused device cost for the built-in cost functions; None for user subclasses that bring their own
@@ -410,22 +492,26 @@ class ReactivePlanner(object):
     def _create_trajectory_bundle(self, x_0_lon: np.array, x_0_lat: np.array, samp_level: int) -> TrajectoryBundle:
         """Candidate bundle of a sampling level (reference :421-444).  For grid sampling spaces only the three
         ordered sample arrays are produced here; TrajectorySample objects are views created on access."""
-        logger.info("===== Sampling trajectories ... =====")
-        logger.info(f"Sampling density {samp_level + 1} of {self.sampling_level}")
+        log = logger.isEnabledFor(logging.INFO)        # (the f-strings below are formatted before logger.info sees them)
+        if log:
+            logger.info("===== Sampling trajectories ... =====")
+            logger.info(f"Sampling density {samp_level + 1} of {self.sampling_level}")
         mode = self.config.sampling.longitudinal_mode
         if hasattr(self.sampling_space, "sample_grid"):
             t, lon, d = self.sampling_space.sample_grid(samp_level, x_0_lat, mode)
             bundle = TrajectoryBundle(lambda: self._materialise_views(bundle), cost_function=self.cost_function)
             bundle.device = {"kind": "grid", "t": t, "lon": lon, "d": d, "x_0_lon": np.asarray(x_0_lon, dtype=np.float64),
                              "x_0_lat": np.asarray(x_0_lat, dtype=np.float64), "mode": mode,
-                             "low_vel": bool(self._low_vel_mode), "n": len(t) * len(lon) * len(d)}
+                             "low_vel": bool(self._low_vel_mode), "n": len(t) * len(lon) * len(d), "level": samp_level,
+                             "serial": self._plan_serial}
         else:
             trajectories = self.sampling_space.generate_trajectories_at_level(samp_level, x_0_lon, x_0_lat, mode,
                                                                               self._low_vel_mode)
             bundle = TrajectoryBundle(trajectories, cost_function=self.cost_function)
             bundle.device = {"kind": "list", "n": len(trajectories), "x_0_lon": np.asarray(x_0_lon, dtype=np.float64),
                              "x_0_lat": np.asarray(x_0_lat, dtype=np.float64)}
-        logger.info(f"Number of trajectory samples: {bundle.device['n']}")
+        if log:
+            logger.info(f"Number of trajectory samples: {bundle.device['n']}")
         return bundle
 
     def _grid_polynomials(self, dev, k):
@@ -448,8 +534,8 @@ class ReactivePlanner(object):
     def _view(self, bundle, k, arrays):
         dev = bundle.device
         if dev["kind"] == "grid":
-            tl, lat = self._grid_polynomials(dev, k)
-            sample = TrajectorySample(self.horizon, self.dt, tl, lat)
+            # the polynomial objects are built when somebody reads them (most callers only read the sampled states)
+            sample = DeviceTrajectorySample(self.horizon, self.dt, lambda: self._grid_polynomials(dev, k))
         else:
             sample = dev["candidates"][k]
         return sample._attach(_DeviceBacking(self.engine, k, arrays, dev["generation"]))
@@ -465,10 +551,54 @@ class ReactivePlanner(object):
             return out
         return [self._view(bundle, k, dev["arrays"]) for k in range(dev["n"])]
 
+    def _cycle_levels(self, dev, cost_generic):
+        """The sampling levels one cycle launch (rp_plan_levels) evaluates for this bundle: the bundle's own level and --
+        inside plan()'s escalation loop -- the following ones while the launch stays within ``speculation_budget``
+        candidate-timesteps and the library's limits.  None: not eligible (one rp_plan_grid per level instead)."""
+        p = self.config.planning
+        Np1 = self.N + 1
+        if dev["kind"] != "grid" or Np1 > 256 or p.continuous_collision_check:
+            return None
+        max_levels, max_samples, max_segments, max_work = self.engine.cycle_limits()
+        dt = self.dt
+        levels = [(dev["level"], dev["t"], dev["lon"], dev["d"], self._traj_lens(dev["t"], dt))]
+        n_samp = len(dev["t"]) + len(dev["lon"]) + len(dev["d"])
+        n_seg = len(dev["t"])
+        work = dev["n"] * Np1
+        if n_samp > max_samples or n_seg > max_segments or work > max_work:
+            return None
+        if self._escalating and not cost_generic and self.speculation_budget > 0:
+            for lvl in range(dev["level"] + 1, self.sampling_level):
+                if len(levels) >= max_levels:
+                    break
+                t, lon, d = self.sampling_space.sample_grid(lvl, dev["x_0_lat"], dev["mode"])
+                n = len(t) * len(lon) * len(d)
+                n_samp += len(t) + len(lon) + len(d)
+                n_seg += len(t)
+                work += n * Np1
+                if work > min(self.speculation_budget, max_work) or n_samp > max_samples or n_seg > max_segments:
+                    break
+                levels.append((lvl, t, lon, d, self._traj_lens(t, dt)))
+        return levels
+
+    _traj_len_cache: Dict = {}
+
+    @classmethod
+    def _traj_lens(cls, t, dt):
+        """traj_len of every sampled horizon (reactive_planner.py:733); the sampled horizons of a level repeat every cycle"""
+        hit = cls._traj_len_cache.get(id(t))           # (the ordered t arrays are cached objects, sampling._ordered)
+        if hit is None or hit[0] is not t or hit[1] != dt:
+            if len(cls._traj_len_cache) > 256:
+                cls._traj_len_cache.clear()
+            hit = cls._traj_len_cache[id(t)] = (t, dt, np.array([_lib.traj_len_of(x, dt) for x in t], dtype=np.int32))
+        return hit[2]
+
     def _get_optimal_trajectory(self, trajectory_bundle: TrajectoryBundle) -> Union[TrajectorySample, None]:
         """Kinematic check, cost, collision check and selection of the optimal candidate in one device pass
         (reference :1065-1136).  Returns the optimal TrajectorySample or None."""
-        logger.info("===== Checking trajectories ... =====")
+        log = logger.isEnabledFor(logging.INFO)
+        if log:
+            logger.info("===== Checking trajectories ... =====")
         self._reset_statistics()
         self._sync_device_tables()
         eng = self.engine
@@ -485,29 +615,63 @@ class ReactivePlanner(object):
         if generic_cost:
             cost_spec = {"cost_kind": _lib.COST_NONE, "desired_speed": None, "desired_s": None, "desired_d": 0.0, "w_a": 1.0}
         want_all = bool(self._draw_traj_set or generic_cost)
-        inputs = self._plan_inputs(dev["x_0_lon"], dev["x_0_lat"], cost_spec, want_all)
 
         t0 = time.time()
-        if dev["kind"] == "grid":
-            res = eng.plan_grid(inputs, dev["t"], dev["lon"], dev["d"])
+        level_index = None
+        spec = self._spec
+        if (spec is not None and dev["kind"] == "grid" and spec["serial"] == dev.get("serial") and dev["level"] in spec["index"]
+                and spec["generation"] == eng.plan_generation and np.array_equal(spec["x_0_lon"], dev["x_0_lon"])
+                and np.array_equal(spec["x_0_lat"], dev["x_0_lat"])):
+            # this level was evaluated ahead, together with the previous one: no new submission
+            level_index = spec["index"][dev["level"]]
+            res = spec["records"][level_index]
         else:
-            cands = trajectory_bundle.trajectories
-            skip = None
-            if self.config.sampling.longitudinal_mode == 'stopping':
-                # filter_goals_behind (trajectories.py:545-550) as skip flags so that indices stay stable
-                skip = np.array([not (c.trajectory_long.x_0[0] < c.trajectory_long.x_d[0]) for c in cands], dtype=np.uint8)
-            cl = np.array([c.trajectory_long.coeffs for c in cands], dtype=np.float64).reshape(-1, 6)
-            ct = np.array([c.trajectory_lat.coeffs for c in cands], dtype=np.float64).reshape(-1, 6)
-            tl = np.array([_lib.traj_len_of(c.trajectory_long.delta_tau, self.dt) for c in cands], dtype=np.int32)
-            dev["candidates"] = cands
-            res = eng.plan_list(inputs, cl, ct, tl, skip)
+            self._spec = None
+            levels = self._cycle_levels(dev, generic_cost) if dev["kind"] == "grid" else None
+            # replanning-size launches check every feasible candidate: the lazy gate's extra barriers cost a small
+            # bundle more than the skipped checks save (winner and counters are the same in both modes; the views
+            # restore the reference's labels, trajectories._STATUS_TO_LABEL / TrajectorySample.feasibility_label)
+            inputs = self._plan_inputs(dev["x_0_lon"], dev["x_0_lat"], cost_spec, want_all,
+                                       check_collision=_lib.COLLISION_ALL if levels is not None else None)
+            if levels is not None:
+                # the whole cycle in one launch: inputs inside the launch, result block written to mapped host memory
+                records, chosen = eng.plan_levels(inputs, [lv[1:] for lv in levels])
+                records = [_lib.PlanResult.from_buffer_copy(records[j]) for j in range(chosen + 1)]
+                level_index = 0
+                res = records[0]
+                if len(levels) > 1:
+                    self._spec = {"serial": dev.get("serial"), "generation": eng.plan_generation, "records": records,
+                                  "index": {lv[0]: j for j, lv in enumerate(levels) if j <= chosen},
+                                  "x_0_lon": dev["x_0_lon"], "x_0_lat": dev["x_0_lat"]}
+            elif dev["kind"] == "grid":
+                res = eng.plan_grid(inputs, dev["t"], dev["lon"], dev["d"])
+            else:
+                cands = trajectory_bundle.trajectories
+                skip = None
+                if self.config.sampling.longitudinal_mode == 'stopping':
+                    # filter_goals_behind (trajectories.py:545-550) as skip flags so that indices stay stable
+                    skip = np.array([not (c.trajectory_long.x_0[0] < c.trajectory_long.x_d[0]) for c in cands], dtype=np.uint8)
+                cl = np.array([c.trajectory_long.coeffs for c in cands], dtype=np.float64).reshape(-1, 6)
+                ct = np.array([c.trajectory_lat.coeffs for c in cands], dtype=np.float64).reshape(-1, 6)
+                tl = np.array([_lib.traj_len_of(c.trajectory_long.delta_tau, self.dt) for c in cands], dtype=np.int32)
+                dev["candidates"] = cands
+                res = eng.plan_list(inputs, cl, ct, tl, skip)
         dev["generation"] = eng.plan_generation
-        arrays = dev["arrays"] = _BundleArrays(eng, eng.plan_generation, want_all)
+        arrays = dev["arrays"] = _BundleArrays(eng, eng.plan_generation, want_all, level=level_index)
+        from_block = False
+        if level_index is not None:
+            # (a fresh cycle launch already addresses the chosen level; its winner's states lie in the mapped result block)
+            from_block = self._spec is None or len(self._spec["records"]) - 1 == level_index
+            if not (from_block and getattr(eng, "_cyc_chosen", -1) == level_index):
+                eng.select_level(level_index)
+                from_block = False
         self.last_result = res
-        logger.info(f"Kinematic + cost + collision checks took:  \t{time.time() - t0:.7f}s")
+        if log:
+            logger.info(f"Kinematic + cost + collision checks took:  \t{time.time() - t0:.7f}s")
 
         winner = res.winner
         n_collision = res.n_infeasible_collision
+        dict.__setitem__(arrays, "winner_key", (float(res.winner_cost), int(winner)) if winner >= 0 else None)
         if generic_cost:
             winner, n_collision = self._select_with_user_cost(trajectory_bundle, arrays)
 
@@ -526,7 +690,7 @@ class ReactivePlanner(object):
         if winner < 0:
             return None
         best = self._view(trajectory_bundle, winner, arrays)
-        best._set_states(eng.fetch_states(winner))
+        best._set_states(eng.cycle_winner_states() if (from_block and not generic_cost) else eng.fetch_states(winner))
         best._label = FeasibilityStatus.FEASIBLE
         if not generic_cost:
             best._cost = float(res.winner_cost)
@@ -578,14 +742,15 @@ class ReactivePlanner(object):
         (reference :514-568)."""
         ca, cu = trajectory.cartesian, trajectory.curvilinear
         factor = self.config.planning.factor
+        x_0 = self.x_0
         n = len(ca.x)
         theta = ca.theta
         steering = np.arctan2(self.vehicle_params.wheelbase * ca.kappa, 1.0)
         # element-wise the same arithmetic as the reference's per-state loop (:520-556), built once as arrays
         yaw_rate = np.empty(n)
-        yaw_rate[0] = self.x_0.yaw_rate
+        yaw_rate[0] = x_0.yaw_rate
         yaw_rate[1:] = (theta[1:] - theta[:-1]) / self.dt
-        t0 = self.x_0.time_step
+        t0 = x_0.time_step
         if getattr(trajectory, "_rows_untouched", None) is not None and trajectory._rows_untouched():
             # device result: the 14 rows are views of one block -- one transpose / tolist per group instead of one per row
             block = trajectory._state_block[0]
@@ -608,26 +773,35 @@ class ReactivePlanner(object):
             cl_list = [CustomState(time_step=t0 + factor * i, position=pos_curv[i], velocity=vel, acceleration=acc,
                                    orientation=th, yaw_rate=kap)
                        for i, (vel, acc, th, kap) in enumerate(zip(v_l, a_l, th_l, kap_l))]
-        else:
-            # the package's own plain state classes: fill the instance dictionaries directly (42 objects per cycle)
-            cart_list, cl_list = [], []
-            new_rs, new_cs = ReactivePlannerState.__new__, CustomState.__new__
-            p_cart, p_curv = list(pos_cart), list(pos_curv)
-            for i, (th, vel, acc, yr, st, kap) in enumerate(zip(th_l, v_l, a_l, yaw_rate.tolist(), steering.tolist(),
-                                                                 kap_l)):
-                ts = t0 + factor * i
-                o = new_rs(ReactivePlannerState)
-                o.__dict__ = {"time_step": ts, "position": p_cart[i], "steering_angle": st, "velocity": vel, "orientation": th,
-                              "acceleration": acc, "yaw_rate": yr}
-                cart_list.append(o)
-                c = new_cs(CustomState)
-                c.__dict__ = {"time_step": ts, "position": p_curv[i], "velocity": vel, "acceleration": acc, "orientation": th,
-                              "yaw_rate": kap}
-                cl_list.append(c)
-        cart_traj = shift_orientation(Trajectory(self.x_0.time_step, cart_list),
-                                      interval_start=self.x_0.orientation - np.pi,
-                                      interval_end=self.x_0.orientation + np.pi)
-        return cart_traj, Trajectory(self.x_0.time_step, cl_list), lon_list, lat_list
+            cart_traj = shift_orientation(Trajectory(t0, cart_list), interval_start=x_0.orientation - np.pi,
+                                          interval_end=x_0.orientation + np.pi)
+            return cart_traj, Trajectory(t0, cl_list), lon_list, lat_list
+        # ---- the package's own plain state classes (no commonroad-io) ----------------------------------------------
+        # orientation shift (:565, utility/general.py:49-55) on the list, before the objects exist: whole turns into
+        # [x_0.orientation - pi, x_0.orientation + pi]
+        lo, hi = x_0.orientation - math.pi, x_0.orientation + math.pi
+        th_shift = th_l
+        if min(th_l) < lo or max(th_l) > hi:
+            th_shift = []
+            for th in th_l:
+                while th < lo:
+                    th += _TWO_PI
+                while th > hi:
+                    th -= _TWO_PI
+                th_shift.append(th)
+        new_rs = ReactivePlannerState.__new__
+        cart_list = []
+        append = cart_list.append
+        ts = t0
+        for pos, th, vel, acc, yr, st in zip(pos_cart, th_shift, v_l, a_l, yaw_rate.tolist(), steering.tolist()):
+            o = new_rs(ReactivePlannerState)
+            o.__dict__ = {"time_step": ts, "position": pos, "steering_angle": st, "velocity": vel, "orientation": th,
+                          "acceleration": acc, "yaw_rate": yr}
+            append(o)
+            ts += factor
+        # the curvilinear state list (second element of the result; run_planner.py never reads it) is built when read
+        curv_traj = _LazyTrajectory(t0, lambda: _curvilinear_states(t0, factor, pos_curv, v_l, a_l, th_l, kap_l))
+        return Trajectory(t0, cart_list), curv_traj, lon_list, lat_list
 
     def plan(self, current_sampling_level: int = None) -> tuple:
         """Plans an optimal trajectory (reference :570-665): sampling levels are escalated until one yields a
@@ -641,7 +815,8 @@ class ReactivePlanner(object):
         x_0_lon, x_0_lat = self.x_0_cl
         self._low_vel_mode = True if self.x_0.velocity < self.config.planning.low_vel_mode_threshold else False
 
-        if logger.isEnabledFor(logging.INFO):      # the f-strings format numpy arrays: skip when nobody listens
+        log = logger.isEnabledFor(logging.INFO)
+        if log:                                    # the f-strings format numpy arrays: skip when nobody listens
             logger.info("=================== Starting Planning Cycle ===================")
             logger.info(f"time_step={self.x_0.time_step} position={self.x_0.position} velocity={self.x_0.velocity} "
                         f"orientation={self.x_0.orientation}")
@@ -652,16 +827,23 @@ class ReactivePlanner(object):
         optimal_trajectory = None
         bundle = None
         i = 1 if current_sampling_level is None else current_sampling_level
-        while optimal_trajectory is None and i < self.sampling_level:
-            bundle = self._create_trajectory_bundle(x_0_lon, x_0_lat, samp_level=i)
-            t0 = time.time()
-            optimal_trajectory = self._get_optimal_trajectory(bundle)
-            logger.info(f"Total checking time: {time.time() - t0:.7f}")
-            logger.info(f"Rejected {self.infeasible_count_kinematics} infeasible trajectories due to kinematics")
-            logger.info(f"Rejected {self.infeasible_count_collision} infeasible trajectories due to collisions")
-            if current_sampling_level is not None:
-                break
-            i += 1
+        self._plan_serial += 1
+        self._spec = None
+        self._escalating = current_sampling_level is None        # the device may evaluate the following levels ahead
+        try:
+            while optimal_trajectory is None and i < self.sampling_level:
+                bundle = self._create_trajectory_bundle(x_0_lon, x_0_lat, samp_level=i)
+                t0 = time.time()
+                optimal_trajectory = self._get_optimal_trajectory(bundle)
+                if log:
+                    logger.info(f"Total checking time: {time.time() - t0:.7f}")
+                    logger.info(f"Rejected {self.infeasible_count_kinematics} infeasible trajectories due to kinematics")
+                    logger.info(f"Rejected {self.infeasible_count_collision} infeasible trajectories due to collisions")
+                if current_sampling_level is not None:
+                    break
+                i += 1
+        finally:
+            self._escalating = False
 
         if (optimal_trajectory is None or optimal_trajectory.cartesian.v[self._standstill_lookahead] <= 0.05) \
                 and self.x_0.velocity <= 0.05:
@@ -674,7 +856,8 @@ class ReactivePlanner(object):
 
         planning_result = self._compute_trajectory_pair(optimal_trajectory) if optimal_trajectory is not None else None
         self._planning_times_list.append(time.time() - planning_start_time)
-        logger.info(f"Total planning time: {self.planning_times[-1]:.7f}")
+        if log:
+            logger.info(f"Total planning time: {self.planning_times[-1]:.7f}")
         if planning_result is None:
             logger.warning("Planner failed to find an optimal trajectory with given sampling configuration!")
         return planning_result

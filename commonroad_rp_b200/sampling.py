@@ -148,10 +148,20 @@ class FixedIntervalSampling(SamplingSpace):
         (reference :218, :220, :226) -- as float64 arrays for ``rp_plan_grid``.  Enumeration index of a
         candidate = (i_t * n_lon + i_lon) * n_d + i_d."""
         self._longitudinal_mode = longitudinal_mode
-        t = np.fromiter(self.samples_t.samples_at_level(level_sampling), dtype=np.float64)
-        lon = np.fromiter(self._get_lon_samples(level_sampling), dtype=np.float64)
+        t = self._ordered(("t", level_sampling), self.samples_t.samples_at_level(level_sampling))
+        lon = self._ordered((longitudinal_mode, level_sampling), self._get_lon_samples(level_sampling))
+        # the union builds a new set whose order depends on d0: iterated afresh every cycle (SURVEY App. B#1)
         d = np.fromiter(self.samples_d.samples_at_level(level_sampling).union({x_0_lat[0]}), dtype=np.float64)
         return t, lon, d
+
+    def _ordered(self, key, sample_set):
+        """iteration order of a sample set as an array; re-read whenever the set object (or its size) changed.  The
+        arrays are shared between cycles: callers must not write to them."""
+        cache = self.__dict__.setdefault("_order_cache", {})
+        hit = cache.get(key)
+        if hit is None or hit[0] is not sample_set or hit[2] != len(sample_set):
+            hit = cache[key] = (sample_set, np.fromiter(sample_set, dtype=np.float64), len(sample_set))
+        return hit[1]
 
     def generate_trajectories_at_level(self, level_sampling: int, x_0_lon: np.ndarray, x_0_lat: np.ndarray,
                                        longitudinal_mode: str, low_vel_mode: bool) -> List[TrajectorySample]:

@@ -170,6 +170,8 @@ class TrajectorySample(Sample):
         b = self._backing
         if b is None or self._cartesian is not None:
             return
+        if b.engine.plan_generation == b.generation and hasattr(b.bundle_arrays, "select"):
+            b.bundle_arrays.select()          # cycle launches hold several levels: address this bundle's one
         st = b.engine.fetch_states(b.index) if b.engine.plan_generation == b.generation else None
         if st is None:
             raise RuntimeError("<TrajectorySample>: the device bundle this sample belongs to has been replaced by a "
@@ -200,9 +202,10 @@ class TrajectorySample(Sample):
     def __deepcopy__(self, memo):
         import copy
         self._materialise_if_available()
+        self.trajectory_long, self.trajectory_lat          # (lazy views build their polynomial objects now)
         new = TrajectorySample.__new__(TrajectorySample)
         for k, v in self.__dict__.items():
-            setattr(new, k, None if k in ("_backing", "_state_block") else copy.deepcopy(v, memo))
+            setattr(new, k, None if k in ("_backing", "_state_block", "_poly_factory") else copy.deepcopy(v, memo))
         if self._backing is not None:
             new._cost = self.cost
             new._label = self.feasibility_label
@@ -270,7 +273,15 @@ class TrajectorySample(Sample):
     @property
     def feasibility_label(self):
         if self._label is None and self._backing is not None:
-            return _STATUS_TO_LABEL[int(self._backing.bundle_arrays["status"][self._backing.index])]
+            arr, k = self._backing.bundle_arrays, self._backing.index
+            status = int(arr["status"][k])
+            if status == 2:
+                # the device may have collision-checked every candidate; the reference's lazy pass (:1031-1063) only
+                # labels the colliders it met BEFORE the winner in (cost, index) order -- the others stay FEASIBLE
+                key = arr.get("winner_key") if hasattr(arr, "get") else None
+                if key is not None and (float(arr["cost"][k]), k) > key:
+                    return FeasibilityStatus.FEASIBLE
+            return _STATUS_TO_LABEL[status]
         return self._label
 
     @feasibility_label.setter
@@ -283,6 +294,50 @@ class TrajectorySample(Sample):
     def enlarge(self, dt: float):
         self._cartesian.enlarge(dt)
         self._curvilinear.enlarge(dt)
+
+
+class DeviceTrajectorySample(TrajectorySample):
+    """A view on one candidate of a device-evaluated grid bundle whose two polynomial OBJECTS are built on first access
+    (``poly_factory() -> (trajectory_long, trajectory_lat)``): the planner creates one such view per cycle for the
+    winner, and most callers only read its sampled states."""
+
+    def __init__(self, horizon: float, dt: float, poly_factory):
+        self.horizon = horizon
+        self.dt = dt
+        self._poly_factory = poly_factory
+        self._trajectory_long = None
+        self._trajectory_lat = None
+        self._cost = 0
+        self._cost_function = None
+        self._cartesian = None
+        self._curvilinear = None
+        self._ext_cartesian = None
+        self._ext_curvilinear = None
+        self._label = None
+        self._backing = None
+
+    def _polys(self):
+        if self._trajectory_long is None and self._poly_factory is not None:
+            self._trajectory_long, self._trajectory_lat = self._poly_factory()
+            self._poly_factory = None
+
+    @property
+    def trajectory_long(self) -> PolynomialTrajectory:
+        self._polys()
+        return self._trajectory_long
+
+    @trajectory_long.setter
+    def trajectory_long(self, trajectory_long):
+        pass
+
+    @property
+    def trajectory_lat(self) -> PolynomialTrajectory:
+        self._polys()
+        return self._trajectory_lat
+
+    @trajectory_lat.setter
+    def trajectory_lat(self, trajectory_lat):
+        pass
 
 
 class TrajectoryBundle:

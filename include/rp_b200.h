@@ -193,6 +193,32 @@ int rp_grid_upload(rp_ctx* ctx, const rp_plan_inputs* in, int n_t, const double*
 int rp_grid_launch(rp_ctx* ctx);
 int rp_grid_result(rp_ctx* ctx, rp_plan_result* out);
 
+/* One replanning cycle in ONE launch.  plan() escalates the sampling level until a level yields a feasible,
+ * collision-free candidate (reactive_planner.py:616-636); the levels are independent bundles, so several of them can be
+ * evaluated together and the LOWEST level with a winner selected -- the result the loop would have produced.  The
+ * cycle's whole input (this call's arguments) travels inside the kernel launch, each candidate's two polynomials are
+ * solved in shared memory, the last block of the launch selects level by level, gathers the winner's state block and
+ * writes the records into mapped host memory: no host->device copy, no coefficient / selection launches, no
+ * device->host copy, no event.
+ *   n_t / n_lon / n_d [n_levels]; t_cat / traj_len_cat, lon_cat, d_cat: the levels' ORDERED sample lists concatenated in
+ *   level order (same meaning as in rp_plan_grid);
+ *   out[j], j < *n_evaluated: the record of level j (winner = enumeration index WITHIN the level); *chosen = the level
+ *   whose record is final = *n_evaluated - 1: the first level with a winner, else the last level.  Levels above it are
+ *   not "evaluated" in the reference's sense (the loop would not have reached them) and have no record.
+ * Afterwards rp_fetch_states / rp_fetch_candidates / rp_fetch_coeffs address the chosen level; rp_select_level switches
+ * to another evaluated level.  Limits (rp_cycle_limits): <= 4 levels, sum of samples <= max_samples, sampled horizons
+ * <= max_segments, (sum of candidates) x (N + 1) <= max_work, N + 1 <= 256; no sharding, no continuous collision check,
+ * and cost_kind NONE only with one level.  Callers fall back to one rp_plan_grid per level beyond them. */
+int rp_plan_levels(rp_ctx* ctx, const rp_plan_inputs* in, int n_levels, const int32_t* n_t, const int32_t* n_lon,
+                   const int32_t* n_d, const double* t_cat, const int32_t* traj_len_cat, const double* lon_cat,
+                   const double* d_cat, rp_plan_result* out, int32_t* n_evaluated, int32_t* chosen);
+int rp_select_level(rp_ctx* ctx, int level);
+/* the winner-state area of the mapped result block of rp_plan_levels: 14 x (N + 1) doubles of the CHOSEN level's
+ * winner after every call (the address changes only when N grows) -- callers that poll results at replanning rate read
+ * it in place instead of calling rp_fetch_states */
+int rp_cycle_host_block(rp_ctx* ctx, void** states, int64_t* n_doubles);
+int rp_cycle_limits(int32_t* max_levels, int32_t* max_samples, int32_t* max_segments, int64_t* max_work);
+
 /* List form (any SamplingSpace, e.g. CorridorSampling, sampling.py:340-397): per-candidate
  * polynomial coefficients as the host built them; skip[i] != 0 marks candidates dropped by
  * filter_goals_behind (may be NULL). */

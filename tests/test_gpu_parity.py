@@ -262,3 +262,112 @@ def test_schedules_identical_on_randomised_bundles():
         assert a["reason_counts"] == b["reason_counts"] and a["n_collision_total"] == b["n_collision_total"], tag
         n_checked += a["n"]
     assert n_checked > 10000
+
+
+# ---- one replanning cycle in one launch (rp_plan_levels) ------------------------------------------------------------
+def _level_problems(seed, N, s_dot0, levels=(1, 2, 3), **kw):
+    return [_bundle(seed=seed, level=lv, N=N, s_dot0=s_dot0, **kw) for lv in levels]
+
+
+@pytest.mark.parametrize("case", [dict(seed=0, N=20, s_dot0=15.0), dict(seed=3, N=20, s_dot0=3.0, low_vel=True),
+                                  dict(seed=2, N=60, s_dot0=12.0, levels=(1, 2)), dict(seed=5, N=20, s_dot0=15.0, draw=True),
+                                  dict(seed=6, N=30, s_dot0=8.0, lon_mode="stopping", desired_s=24.0),
+                                  dict(seed=4, N=30, s_dot0=1.0)],
+                         ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+def test_cycle_launch_equals_one_launch_chain_per_level(case):
+    """rp_plan_levels evaluates several sampling levels in ONE kernel (coefficients solved in shared memory, selection by
+    the last block, result block in mapped host memory): every level's verdicts, costs, counters and the winner's states
+    are bit-identical to rp_plan_grid on that level alone, and the chosen level is the lowest one with a winner"""
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200._lib import traj_len_of
+    case = dict(case)
+    draw = case.pop("draw", False)
+    probs = _level_problems(**case)
+    eng = H.engine_for(probs[0])
+    singles = []
+    for pr in probs:
+        pr["draw_all"] = draw
+        r = eng.plan_grid(H.inputs_for(pr, want_all_states=draw), pr["t"], pr["lon"], pr["d"])
+        cost, status, reason, step = eng.fetch_candidates()
+        singles.append({"res": r, "cost": cost, "status": status, "reason": reason, "step": step,
+                        "ws": eng.fetch_states(r.winner) if r.winner >= 0 else None,
+                        "coeffs": eng.fetch_coeffs()})
+    levels = [(pr["t"], pr["lon"], pr["d"], np.array([traj_len_of(x, pr["dt"]) for x in pr["t"]], dtype=np.int32)) for pr in probs]
+    for rep in range(2):
+        records, chosen = eng.plan_levels(H.inputs_for(probs[0], want_all_states=draw), levels)
+        want_chosen = next((j for j, sg in enumerate(singles) if sg["res"].winner >= 0), len(singles) - 1)
+        assert chosen == want_chosen
+        assert eng.launches_per_plan() == 1
+        for j in range(chosen + 1):
+            r, sg = records[j], singles[j]
+            for f in ("winner", "n_candidates", "n_feasible", "n_infeasible_kinematics", "n_infeasible_collision", "n_collision_total"):
+                assert getattr(r, f) == getattr(sg["res"], f), (j, f)
+            assert list(r.reason_counts) == list(sg["res"].reason_counts)
+            assert r.winner_cost == sg["res"].winner_cost or (np.isnan(r.winner_cost) and np.isnan(sg["res"].winner_cost))
+            eng.select_level(j)
+            cost, status, reason, step = eng.fetch_candidates()
+            assert np.array_equal(status, sg["status"]) and np.array_equal(reason, sg["reason"]) and np.array_equal(step, sg["step"])
+            assert np.array_equal(cost.view(np.int64), sg["cost"].view(np.int64))                  # identical bits
+            if r.winner >= 0:
+                assert np.array_equal(eng.fetch_states(r.winner), sg["ws"])
+                other = int(np.flatnonzero(status != 1)[-1])                                       # a non-winner, re-evaluated on demand
+                assert eng.fetch_states(other).shape == sg["ws"].shape and np.isfinite(eng.fetch_states(other)).all()
+            cl, ct, tau = eng.fetch_coeffs()
+            assert np.array_equal(cl, sg["coeffs"][0]) and np.array_equal(ct, sg["coeffs"][1])
+    # the grid form still works on the same context afterwards
+    r = eng.plan_grid(H.inputs_for(probs[0]), probs[0]["t"], probs[0]["lon"], probs[0]["d"])
+    assert r.winner == singles[0]["res"].winner or draw
+    eng.close()
+
+
+def test_cycle_launch_escalates_to_the_level_that_has_a_winner():
+    """levels 1 and 2 without a collision-free candidate, level 3 with one: the cycle launch reports three records and
+    chooses level 3 (reactive_planner.py:616-636); with nothing feasible anywhere it reports every level, no winner"""
+    from commonroad_rp_b200._lib import traj_len_of
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cyc_DEU_Test-1_1_T-1.npz"))
+    import json
+    from tests import golden_io
+    meta = json.loads(str(z["meta"]))
+    ci = next(i for i, c in enumerate(meta["cycles"]) if [lv["winner"] >= 0 for lv in c["levels"]] == [False, False, True])
+    from commonroad_rp_b200.sampling import FixedIntervalSampling, VelocitySampling
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = meta["N"]
+    cfg.planning.planning_horizon = meta["N"] * meta["dt"]
+    cfg.sampling.t_min = meta["t_min"]
+    fs = FixedIntervalSampling(cfg)
+    x = z["c%d_x0" % ci]
+    v0 = float(x[3])
+    lo = max(0, v0 - 0.125 * meta["N"] * meta["dt"] * O.vehicle_dict()["a_max"])
+    fs.samples_v = VelocitySampling(lo, max(lo + 5.0, v0 + 2), 4)
+    x0_lon, x0_lat = z["c%d_x0_lon" % ci], z["c%d_x0_lat" % ci]
+    grids = [fs.sample_grid(lv, x0_lat, "velocity_keeping") for lv in (1, 2, 3)]
+    prob = {"t": grids[0][0], "lon": grids[0][1], "d": grids[0][2], "x0_lon": x0_lon, "x0_lat": x0_lat, "x0_orientation": float(x[2]),
+            "x0_time_step": int(x[7]), "lon_mode": "velocity_keeping", "low_vel_mode": False, "dt": meta["dt"], "N": meta["N"],
+            "factor": 1, "draw_all": True, "constraints": O.CONSTRAINTS,
+            "cost": {"kind": "default", "desired_speed": meta["desired_velocity"], "desired_s": None, "desired_d": 0.0, "w_a": 5},
+            "vehicle": O.vehicle_dict(), "ref": {k: z[k] for k in ("ref_pos", "ref_theta", "ref_curv", "ref_curv_d")},
+            "ccosy": {"path": z["cc_path"], "S": z["cc_S"], "normals": z["cc_normals"], "limit": 20.0},
+            "obstacles": golden_io.unpack_obstacles(z, "ob_")}
+    eng = H.engine_for(prob)
+    levels = [(t, lon, d, np.array([traj_len_of(q, meta["dt"]) for q in t], dtype=np.int32)) for t, lon, d in grids]
+    records, chosen = eng.plan_levels(H.inputs_for(prob, want_all_states=True), levels)
+    assert chosen == 2
+    for j, lv in enumerate(meta["cycles"][ci]["levels"]):
+        assert (records[j].n_candidates, records[j].winner, records[j].n_infeasible_kinematics, records[j].n_infeasible_collision) == \
+            (lv["n"], lv["winner"], lv["n_inf_kin"], lv["n_inf_col"])
+    ws = z["c%d_l2_winner_states" % ci]
+    assert H.rel_err(ws, eng.fetch_states(records[2].winner)) < 1e-9
+    # nothing feasible anywhere: all records, last level chosen, no winner
+    blocked = dict(prob)
+    ob = dict(prob["obstacles"])
+    j0 = int(np.argmax(prob["ref"]["ref_pos"] > x0_lon[0]))
+    wall = [[prob["ccosy"]["path"][j0][0], prob["ccosy"]["path"][j0][1], prob["ref"]["ref_theta"][j0] + np.pi / 2, 30.0, 6.0]]
+    ob["static_boxes"] = np.vstack([np.asarray(ob["static_boxes"]).reshape(-1, 5), wall])
+    blocked["obstacles"] = ob
+    eng2 = H.engine_for(blocked)
+    records, chosen = eng2.plan_levels(H.inputs_for(blocked), levels)
+    assert chosen == 2 and all(records[j].winner == -1 for j in range(3))
+    assert [records[j].n_candidates for j in range(3)] == [len(t) * len(lon) * len(d) for t, lon, d in grids]
+    eng.close()
+    eng2.close()

@@ -40,6 +40,9 @@ def main():
               "_plan_inputs", "_device_cost_spec", "_view", "_reset_statistics"):
         wrap(P, n)
     wrap(_lib.Engine, "plan_grid", "Engine.plan_grid")
+    wrap(_lib.Engine, "plan_levels", "Engine.plan_levels")
+    wrap(_lib.Engine, "select_level", "Engine.select_level")
+    wrap(P, "_cycle_levels")
     wrap(_lib.Engine, "fetch_states", "Engine.fetch_states")
     wrap(_lib.Engine, "_grid_args", "Engine._grid_args")
     wrap(S.FixedIntervalSampling, "sample_grid", "sample_grid")
