@@ -276,6 +276,7 @@ class Engine:
         self._N = inputs.N
         self._n_cand = t.size * lon.size * d.size
         self._keep = (t, lon, d, tl)
+        self._cyc_selected = None
         self.plan_generation += 1
         return (C.byref(inputs), t.size, _p(t, _dp), _p(tl, _ip), lon.size, _p(lon, _dp), d.size, _p(d, _dp))
 
@@ -342,7 +343,7 @@ class Engine:
         chosen = b["chosen"].value
         self._level_counts = counts
         self._n_cand = counts[chosen]
-        self._cyc_chosen = chosen
+        self._cyc_chosen = self._cyc_selected = chosen
         return b["res"], chosen
 
     def cycle_winner_states(self):
@@ -362,8 +363,11 @@ class Engine:
 
     def select_level(self, level):
         """After ``plan_levels``: make fetch_states / fetch_candidates / fetch_coeffs address that evaluated level."""
+        if getattr(self, "_cyc_selected", None) == level:
+            return
         self._check(self._lib.rp_select_level(self._ctx, int(level)))
         self._n_cand = self._level_counts[level]
+        self._cyc_selected = level
 
     def plan_list(self, inputs, coeffs_lon, coeffs_lat, traj_len, skip=None):
         cl = _f64(coeffs_lon).reshape(-1, 6)
@@ -372,6 +376,7 @@ class Engine:
         sk = np.ascontiguousarray(skip, dtype=np.uint8) if skip is not None else None
         self._N = inputs.N
         self._n_cand = cl.shape[0]
+        self._cyc_selected = None
         self.plan_generation += 1
         res = PlanResult()
         self._check(self._lib.rp_plan_list(self._ctx, C.byref(inputs), cl.shape[0], _p(cl, _dp), _p(ct, _dp),

@@ -97,6 +97,8 @@ __device__ __forceinline__ int locate_segment(const double* __restrict__ a, int 
 struct StepIn {
     const double *cs, *cd;       // the candidate's longitudinal / lateral coefficients (re-read every step: L1-resident,
                                  // the longitudinal row is a warp-wide broadcast; keeps 24 registers free)
+    const double* lr;            // LATROWS: the candidate's column of the lateral table (+ i * lr_stride per step)
+    int lr_stride;
     double th_prev, kap_prev;
     int i;
 };
@@ -218,7 +220,9 @@ __device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables&
 }
 
 // the candidate's own part of the step, given the longitudinal row
-template <bool EXACT>
+// LATROWS: d, d_dot, d_ddot of the step come from the lateral table (lat_rows_thread; high-velocity grid bundles: the
+// lateral polynomial over the time grid is the same for every lon sample) instead of three polynomial evaluations
+template <bool EXACT, bool LATROWS>
 __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables& R, const LimitRcp& Y, const LonRow& L,
                                             const double* __restrict__ cd_ptr, double cs0, double th_prev, double kap_prev,
                                             int i) {
@@ -227,6 +231,13 @@ __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables
     const double dt = in.dt;
     Divider<EXACT> D;
     StepOut o;
+    const double s = L.s, sv = L.sv, sa = L.sa;
+    double d, dv, da;
+    if (LATROWS) {
+        const double2* r = reinterpret_cast<const double2*>(cd_ptr);          // (the caller passes the table entry)
+        const double2 u = __ldg(r), w = __ldg(r + 1);
+        d = u.x; dv = u.y; da = w.x;
+    } else {
     double cd[6];
     {
         const double2* b = reinterpret_cast<const double2*>(cd_ptr);
@@ -236,8 +247,6 @@ __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables
             cd[2 * q] = w.x; cd[2 * q + 1] = w.y;
         }
     }
-    const double s = L.s, sv = L.sv, sa = L.sa;
-    double d, dv, da;
     if (!low_vel) {
         const double tt = (double)i * dt;
         const double t2 = tt * tt, t3 = t2 * tt, t4 = t2 * t2, t5 = t4 * tt;
@@ -252,6 +261,7 @@ __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables
         da = poly_acc(cd, s1, s2, s3);
     }
     dv = fabs(dv) < kEps ? 0.0 : dv;
+    }
     o.pre = L.flags & LR_PRE;
 
     // ---- orientation (:810-873) ----------------------------------------------------------------------
@@ -271,34 +281,22 @@ __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables
     }
     const double th_ref = L.th_ref;
     const bool carry = !moving && !low_vel;
-    double th_cl, th_gl, cosT, tanT;
+    const double k_r = L.k_r, k_r_d = L.k_r_d;
+    double th_cl, th_gl, cosT, kappa, v, a;
+    // ---- orientation (:842-873), curvature, velocity, acceleration (:876-896) ----------------------------------------
     if (!carry) {
         th_cl = atan(dp);                                       // np.arctan2(dp, 1.0)
         th_gl = th_cl + th_ref;
-        // theta_cl = atan(dp): cos(theta_cl) = 1 / sqrt(1 + dp^2), tan(theta_cl) = dp (<= 1 ulp from libm)
-        const double hyp = sqrt(1.0 + dp * dp);
-        cosT = D.div_nz(1.0, hyp, D.rcp(hyp));
-        tanT = dp;
-        heading_cos_sin(cosT, tanT, L.c_ref, L.s_ref, o.cn, o.sn);
+        motion_moving(D, dp, dpp, d, k_r, k_r_d, sv, sa, cosT, kappa, v, a);
+        heading_cos_sin(cosT, dp, L.c_ref, L.s_ref, o.cn, o.sn);
     } else {
         // standstill in high-velocity mode keeps the previous global orientation (:866-873)
         th_gl = i > 0 ? th_prev : in.x0_orientation;
         th_cl = th_gl - th_ref;
-        cosT = cos(th_cl);
-        tanT = tan(th_cl);
+        double tanT;
+        motion_carry(D, th_cl, dp, dpp, d, k_r, k_r_d, sv, sa, cosT, tanT, kappa, v, a);
         sincos(th_gl, &o.sn, &o.cn);
     }
-
-    // ---- curvature, velocity, acceleration (:876-896) -------------------------------------------------
-    const double k_r = L.k_r, k_r_d = L.k_r_d;
-    const double oneKrD = (1 - k_r * d);
-    const double y_cos = D.rcp(cosT);
-    const double q = D.div_nz(cosT, oneKrD, D.rcp(oneKrD));
-    const double kappa = (dpp + (k_r * dp + k_r_d * d) * tanT) * cosT * (q * q) + q * k_r;
-    const double v = sv * D.div_nz(oneKrD, cosT, y_cos);
-    const double a = D.div(sa * oneKrD, cosT, y_cos) +
-                     D.div(sv * sv, cosT, y_cos) * (oneKrD * tanT * (D.div(kappa * oneKrD, cosT, y_cos) - k_r) -
-                                                    (k_r_d * d + k_r * dp));
 
     // ---- the five ordered limit checks (:971-1017), all evaluated, first violation selected ---------------
     {
@@ -339,15 +337,45 @@ __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables
     return o;
 }
 
-template <bool EXACT>
+template <bool EXACT, bool LATROWS>
 __device__ __forceinline__ StepOut poly_step(const PlanParams& P, const RefTables& R, const LimitRcp& Y, const StepIn& I) {
     const LonRow L = lon_part<EXACT>(P, R, I.cs, I.i);
-    return lat_part<EXACT>(P, R, Y, L, I.cd, __ldg(I.cs), I.th_prev, I.kap_prev, I.i);
+    return lat_part<EXACT, LATROWS>(P, R, Y, L, LATROWS ? I.lr + (size_t)I.i * I.lr_stride : I.cd, __ldg(I.cs), I.th_prev,
+                                    I.kap_prev, I.i);
 }
 
 // the rare exact redo: out of line, so its plain divisions (each with a slow-path call) stay out of the hot loop
+template <bool LATROWS>
 __device__ __noinline__ StepOut poly_step_exact(const PlanParams& P, const RefTables& R, const LimitRcp& Y, StepIn I) {
-    return poly_step<true>(P, R, Y, I);
+    return poly_step<true, LATROWS>(P, R, Y, I);
+}
+
+// the lateral table of a high-velocity grid bundle: entry [it][i][id] = d, d_dot (eps-clamped, :777), d_ddot of the lateral
+// polynomial (t[it], d[id]) at time i * dt, i < traj_len[it] -- exactly what lat_part evaluates per candidate, once per
+// (t, d) pair instead of once per (t, lon, d) candidate.  One thread per (it, chunk of 8 steps, id); it re-solves its own
+// polynomial (coeff_thread's expressions) because the coefficient blocks of the same launch may not have finished.
+__device__ __forceinline__ void lat_rows_thread(int q, int n_t, int n_d, int Np1, const double* __restrict__ t,
+                                                const double* __restrict__ dsamp, const int* __restrict__ traj_len,
+                                                double x0d, double x0dd, double x0ddd, double dt, double* __restrict__ out) {
+    const int n_chunks = (Np1 + 7) / 8;
+    if (q >= n_t * n_chunks * n_d) return;
+    const int id = q % n_d;
+    const int rest = q / n_d;
+    const int chunk = rest % n_chunks, it = rest / n_chunks;
+    int tl = traj_len[it];
+    tl = tl > Np1 ? Np1 : tl;
+    if (chunk * 8 >= tl) return;
+    double c[6];
+    solve_quintic(x0d, x0dd, x0ddd, dsamp[id], 0.0, 0.0, t[it], c);
+    for (int i = chunk * 8; i < chunk * 8 + 8 && i < tl; ++i) {
+        const double tt = (double)i * dt;
+        const double t2 = tt * tt, t3 = t2 * tt, t4 = t2 * t2, t5 = t4 * tt;
+        double dv = poly_vel(c, tt, t2, t3, t4);
+        dv = fabs(dv) < kEps ? 0.0 : dv;
+        double2* o = reinterpret_cast<double2*>(out + (((size_t)it * Np1 + i) * n_d + id) * 4);
+        o[0] = make_double2(poly_pos(c, tt, t2, t3, t4, t5), dv);
+        o[1] = make_double2(poly_acc(c, tt, t2, t3), 0.0);
+    }
 }
 
 // rows [step][obstacle] for the launch's time window x0.time_step + step * factor (reactive_planner.py:1040)
@@ -385,7 +413,7 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 // candidate and write nothing.
 // ONE_GROUP: the host guarantees G == 1 for every chunk (grid form, n_d a multiple of 32, aligned shard): the group
 // arithmetic folds away at compile time.
-template <int BLOCK, bool ONE_GROUP, int PF>
+template <int BLOCK, bool ONE_GROUP, int PF, bool LATROWS = false>
 __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k, bool valid,
                                            double* __restrict__ acc, double* __restrict__ s_vmid,
                                            double* __restrict__ rows) {
@@ -427,6 +455,8 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         const int id = rem - il * P.n_d;
         I.cs = P.lon_coef + (size_t)(it * P.n_lon + il) * 6;
         I.cd = P.lat_coef + (size_t)(low_vel ? k : it * P.n_d + id) * 6;
+        I.lr = LATROWS ? P.lat_rows + ((size_t)it * Np1 * P.n_d + id) * 4 : nullptr;
+        I.lr_stride = P.n_d * 4;
         tl = P.traj_len[it];
         filtered = (in.lon_mode == RP_STOPPING) && !(in.x0_lon[0] < P.lon_samples[il]);
         if (ONE_GROUP) {
@@ -442,6 +472,8 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     } else {
         I.cs = P.lon_coef + (size_t)k * 6;
         I.cd = P.lat_coef + (size_t)k * 6;
+        I.lr = nullptr;
+        I.lr_stride = 0;
         tl = P.traj_len[k];
         filtered = P.skip != nullptr && P.skip[k] != 0;
         grp = lane;
@@ -501,8 +533,8 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             L.c_ref = c[384]; L.s_ref = c[416];
             L.flags = rflags[item];
             heavy_dynmask = rflags[32 + item];
-            StepOut o = lat_part<false>(P, R, Y, L, I.cd, cs0, th_gl, kappa, i);
-            if (o.reject & 0x80000000u) o = poly_step_exact(P, R, Y, I);
+            StepOut o = lat_part<false, LATROWS>(P, R, Y, L, LATROWS ? I.lr + (size_t)i * I.lr_stride : I.cd, cs0, th_gl, kappa, i);
+            if (o.reject & 0x80000000u) o = poly_step_exact<LATROWS>(P, R, Y, I);
             pre |= o.pre;
             if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
             if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
@@ -649,7 +681,7 @@ __device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs,
 }
 
 // ---- one bundle: persistent grid, warps draw chunks of 32 candidates from a counter -----------------------------
-template <int BLOCK, bool ONE_GROUP>
+template <int BLOCK, bool ONE_GROUP, bool LATROWS = false>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
@@ -694,7 +726,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         if (g >= P.n_groups) break;
         bool valid;
         const int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
-        cand_march<BLOCK, ONE_GROUP, 2>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, ONE_GROUP, 2, LATROWS>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 

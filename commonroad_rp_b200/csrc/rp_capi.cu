@@ -137,7 +137,7 @@ struct rp_ctx {
     Geometry main_geom{}, index_geom{}, cand_geom{};
     bool main_is_cand = false, main_one_group = false, small_path_last = false;          // geometry in main_geom/d_segs belongs to the candidate-major kernel
     int kernel_policy = RP_KERNEL_AUTO;
-    DevBuf d_work, d_dyn_rows;
+    DevBuf d_work, d_dyn_rows, d_lat_rows;
     int index_geom_np1 = -1, index_geom_count = -1;
     long long index_geom_tables = -1;
     double ref_inv_step = 1.0, ps_inv_step = 1.0;
@@ -503,6 +503,7 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     if ((int)G.smem > granted) {
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         granted = (int)G.smem;
     }
     int occ = 0;
@@ -775,7 +776,7 @@ int rp_ctx_destroy(rp_ctx* ctx) {
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all,
                       &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best,
-                      &ctx->d_work, &ctx->d_clr, &ctx->d_dyn_rows})
+                      &ctx->d_work, &ctx->d_clr, &ctx->d_dyn_rows, &ctx->d_lat_rows})
         b->release();
     for (DevBuf* b : {&ctx->d_cycle_res, &ctx->d_ticket, &ctx->d_best4}) b->release();
     if (ctx->h_cycle) cudaFreeHost(ctx->h_cycle);
@@ -1052,6 +1053,12 @@ static int launch_plan(rp_ctx* ctx) {
     const double hl_ = 0.5 * ctx->veh.length, hw_ = 0.5 * ctx->veh.width;
     const float r_ego_f_up = std::nextafterf((float)std::sqrt(hl_ * hl_ + hw_ * hw_), std::numeric_limits<float>::infinity());
     const float wb_rear_f_up = std::nextafterf((float)std::fabs(ctx->veh.wb_rear_axle), std::numeric_limits<float>::infinity());
+    // lateral table of the candidate-major kernel: high-velocity grid bundles whose chunks of 32 candidates share one
+    // (t, lon) pair (the ONE_GROUP instantiation) read d, d_dot, d_ddot per step instead of evaluating three polynomials
+    const bool use_lat_rows = cand_main && ctx->mode == 0 && !ctx->in.low_vel_mode && ctx->n_d > 0 && ctx->n_d % 32 == 0 &&
+                              first % 32 == 0 && count % 32 == 0;
+    if (use_lat_rows)
+        if (int rc = ctx->d_lat_rows.ensure((size_t)ctx->n_t * Np1 * ctx->n_d * 4 * sizeof(double))) return rc;
     bool dyn_rows_done = false;         // the prep launch ran: coefficients, dynamic-obstacle rows, scratch words reset
     if (ctx->mode == 0 && n > 0) {
         const int n_lon_sys = ctx->n_t * ctx->n_lon;
@@ -1073,13 +1080,18 @@ static int launch_plan(rp_ctx* ctx) {
         A.x0_time_step = ctx->in.x0_time_step; A.factor = ctx->in.factor; A.Np1 = Np1;
         A.r_ego_f_up = r_ego_f_up; A.wb_rear_f_up = wb_rear_f_up;
         A.dyn_rows = ctx->d_dyn_rows.as<float4>();
+        A.n_dyn_blocks = (dyn_total + 127) / 128;
+        A.lat_rows = use_lat_rows ? ctx->d_lat_rows.as<double>() : nullptr;
+        A.traj_len = reinterpret_cast<const int*>(sb + ctx->off_len);
+        A.dt = ctx->in.dt;
+        const int n_lat_row_threads = use_lat_rows ? ctx->n_t * ((Np1 + 7) / 8) * ctx->n_d : 0;
         if (int rc = ctx->d_argmin.ensure(sizeof(rp::ArgminScratch))) return rc;
         if (int rc = ctx->d_work.ensure(sizeof(int))) return rc;
         if (int rc = ctx->d_best.ensure(sizeof(unsigned long long))) return rc;
         A.argmin_counts = reinterpret_cast<int*>(ctx->d_argmin.p);
         A.work_counter = ctx->d_work.as<int>();
         A.best_bits = ctx->d_best.as<unsigned long long>();
-        rp::prep_kernel<<<A.n_coeff_blocks + (dyn_total + 127) / 128, 128, 0, ctx->stream>>>(A);
+        rp::prep_kernel<<<A.n_coeff_blocks + A.n_dyn_blocks + (n_lat_row_threads + 127) / 128, 128, 0, ctx->stream>>>(A);
         RP_CUDA(cudaGetLastError());
         dyn_rows_done = true;
     }
@@ -1113,7 +1125,9 @@ static int launch_plan(rp_ctx* ctx) {
                 P.dyn_rows = ctx->d_dyn_rows.as<float4>();
             }
             const Geometry& G = ctx->main_geom;
-            if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+            P.lat_rows = (use_lat_rows && ctx->main_one_group) ? ctx->d_lat_rows.as<double>() : nullptr;
+            if (P.lat_rows) rp::cand_kernel<RP_CAND_THREADS, true, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+            else if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
             else rp::cand_kernel<RP_CAND_THREADS, false><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
             RP_CUDA(cudaGetLastError());
         } else if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;

@@ -102,6 +102,8 @@ struct PlanParams {
     int* work_counter;           // chunk dispenser (zeroed before the launch)
     int n_acc_rows;              // np.sum accumulator rows kept in shared memory
     const float4* dyn_rows;      // [Np1][n_dyn] single-precision circles of the launch's time window (null: none staged)
+    const double* lat_rows;      // [n_t][Np1][n_d][4] = d, d_dot (clamped), d_ddot, - of the lateral polynomials on the time
+                                 // grid (high-velocity grid bundles: shared by all lon samples; null: evaluated per candidate)
 };
 
 __device__ __forceinline__ int pack_info(int status, int reason, int step) {
@@ -399,28 +401,28 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const ARGS* __re
             const double k0 = R.curv[j0], kd0 = R.curv_d[j0];
             const double k_r = (R.curv[j1] - k0) * lam + k0;
             const double k_r_d = (R.curv_d[j1] - kd0) * lam + kd0;
-            const double oneKrD = (1 - k_r * d);
-            double cosT, tanT;
+            double cosT;
             if (!carry) {
-                // theta_cl = atan(dp): cos(theta_cl) = 1 / sqrt(1 + dp^2), tan(theta_cl) = dp (<= 1 ulp from libm)
-                cosT = 1.0 / sqrt(1.0 + dp * dp);
-                tanT = dp;
+                // shared with the candidate-major kernel (rp_device.cuh motion_moving): shared-reciprocal quotients first,
+                // plain divisions if an operand left their proven window -- identical bits either way
+                Divider<false> D;
+                motion_moving(D, dp, dpp, d, k_r, k_r_d, sv, sa, cosT, kappa, v, a);
+                if (D.reject & 0x80000000u) {
+                    Divider<true> E;
+                    motion_moving(E, dp, dpp, d, k_r, k_r_d, sv, sa, cosT, kappa, v, a);
+                }
                 double s_ref, c_ref;
                 sincos(th_ref, &s_ref, &c_ref);
-                heading_cos_sin(cosT, tanT, c_ref, s_ref, cn, sn);
+                heading_cos_sin(cosT, dp, c_ref, s_ref, cn, sn);
             } else {
-                cosT = cos(th_cl);
-                tanT = tan(th_cl);
+                double tanT;
+                Divider<true> E;
+                motion_carry(E, th_cl, dp, dpp, d, k_r, k_r_d, sv, sa, cosT, tanT, kappa, v, a);
                 sincos(th_gl, &sn, &cn);
             }
             // cos / sin of the heading for the collision phase: the head of the (tail-only) increment rows is free
             scratch[4 * Np1 + i] = cn;
             scratch[5 * Np1 + i] = sn;
-            const double q = ddiv(cosT, oneKrD);
-            kappa = (dpp + (k_r * dp + k_r_d * d) * tanT) * cosT * (q * q) + q * k_r;
-            v = sv * ddiv(oneKrD, cosT);
-            a = ddiv(sa * oneKrD, cosT) + ddiv(sv * sv, cosT) * (oneKrD * tanT * (ddiv(kappa * oneKrD, cosT) - k_r) -
-                                                                (k_r_d * d + k_r * dp));
             s_kap[i] = kappa;
         }
         __syncthreads();                                                            // theta/kappa rows complete

@@ -94,6 +94,11 @@ struct PrepArgs {
     int x0_time_step, factor, Np1;
     float r_ego_f_up, wb_rear_f_up;
     float4* dyn_rows;
+    int n_dyn_blocks;
+    // lateral table of the candidate-major kernel (lat_rows_thread; null: not used)
+    double* lat_rows;
+    const int* traj_len;
+    double dt;
     // per-cycle scratch words this launch resets for the kernels after it (instead of separate memset nodes)
     int* argmin_counts;                 // [16]
     int* work_counter;                  // chunk dispenser of the candidate-major kernel (may be null)
@@ -109,9 +114,12 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ PrepA
     if ((int)blockIdx.x < A.n_coeff_blocks)
         coeff_thread(blockIdx.x * blockDim.x + threadIdx.x, A.n_t, A.n_lon, A.n_d, A.low_vel, A.lon_mode, A.t, A.lon, A.d, A.x0s,
                      A.x0sd, A.x0sdd, A.x0d, A.x0dd, A.x0ddd, A.lon_coef, A.lat_coef, A.lat_tau);
-    else
+    else if ((int)blockIdx.x < A.n_coeff_blocks + A.n_dyn_blocks)
         dyn_rows_thread((blockIdx.x - A.n_coeff_blocks) * blockDim.x + threadIdx.x, A.obs, A.x0_time_step, A.factor, A.Np1,
                         A.r_ego_f_up, A.wb_rear_f_up, A.dyn_rows);
+    else
+        lat_rows_thread((blockIdx.x - A.n_coeff_blocks - A.n_dyn_blocks) * blockDim.x + threadIdx.x, A.n_t, A.n_d, A.Np1, A.t, A.d,
+                        A.traj_len, A.x0d, A.x0dd, A.x0ddd, A.dt, A.lat_rows);
 }
 
 // ---- batch of independent scenarios (blockIdx.y = scenario; see cand_batch_kernel) --------------------------------

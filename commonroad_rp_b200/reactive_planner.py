@@ -40,7 +40,15 @@ class _LazyViews(collections.abc.Sequence):
     the cycle, each created (and cached) on first access.  ``copy.deepcopy`` gives a plain list of materialised copies."""
 
     def __init__(self, make, order):
-        self._make, self._order, self._cache = make, order, {}
+        """order: the candidate indices in list order, or a callable producing them on first use (the per-candidate
+        verdicts are then fetched from the device only if somebody looks at the stored trajectories)"""
+        self._make, self._order_src, self._cache = make, order, {}
+
+    @property
+    def _order(self):
+        if callable(self._order_src):
+            self._order_src = self._order_src()
+        return self._order_src
 
     def __len__(self):
         return len(self._order)
@@ -660,11 +668,9 @@ class ReactivePlanner(object):
         arrays = dev["arrays"] = _BundleArrays(eng, eng.plan_generation, want_all, level=level_index)
         from_block = False
         if level_index is not None:
-            # (a fresh cycle launch already addresses the chosen level; its winner's states lie in the mapped result block)
-            from_block = self._spec is None or len(self._spec["records"]) - 1 == level_index
-            if not (from_block and getattr(eng, "_cyc_chosen", -1) == level_index):
-                eng.select_level(level_index)
-                from_block = False
+            eng.select_level(level_index)           # (no library call when the engine already addresses that level)
+            # the chosen level's winner states lie in the mapped result block the kernel wrote
+            from_block = getattr(eng, "_cyc_chosen", -1) == level_index
         self.last_result = res
         if log:
             logger.info(f"Kinematic + cost + collision checks took:  \t{time.time() - t0:.7f}s")
@@ -683,8 +689,10 @@ class ReactivePlanner(object):
         if self._draw_traj_set:
             # feasible candidates first, then the kinematically infeasible ones (reference :1121-1128); the views are
             # created when they are looked at (plotting), not 3 000 Python objects per cycle up front
-            status = np.asarray(arrays["status"])
-            order = np.concatenate([np.nonzero(np.isin(status, (0, 2, 4)))[0], np.nonzero(status == 1)[0]])
+            def order():
+                status = np.asarray(arrays["status"])
+                return np.concatenate([np.nonzero(np.isin(status, (0, 2, 4)))[0], np.nonzero(status == 1)[0]])
+
             self.stored_trajectories = _LazyViews(lambda k: self._view(trajectory_bundle, k, arrays), order)
 
         if winner < 0:

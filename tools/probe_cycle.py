@@ -66,6 +66,18 @@ def main():
             n = sum(len(a) * len(b) * len(c) for a, b, c, _ in levels[:nl])
             print("check_collision=%d plan_levels %d level(s) %5d cand: p50 %.1f us  p95 %.1f us  min %.1f us" % (
                 lazy, nl, n, np.percentile(ts, 50), np.percentile(ts, 95), ts.min()))
+        if lazy == 1:
+            for gap_us in (0, 50, 100, 200, 1000):
+                ts = []
+                for _ in range(reps):
+                    t_end = time.perf_counter() + gap_us * 1e-6
+                    while time.perf_counter() < t_end:
+                        pass
+                    t0 = time.perf_counter()
+                    rec, chosen = eng.plan_levels(inputs, levels[:3])
+                    ts.append(time.perf_counter() - t0)
+                ts = np.array(ts) * 1e6
+                print("  host busy-wait %4d us between cycles: plan_levels(3 levels) p50 %.1f us  p95 %.1f us" % (gap_us, np.percentile(ts, 50), np.percentile(ts, 95)))
         t, lon, d, tl = levels[0]
         for _ in range(20):
             eng.plan_grid(inputs, t, lon, d, tl)
