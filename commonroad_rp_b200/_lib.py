@@ -103,6 +103,7 @@ SIGNATURES = {
     "rp_batch_launch": (C.c_int, [C.c_void_p]),
     "rp_batch_results": (C.c_int, [C.c_void_p, C.POINTER(PlanResult)]),
     "rp_batch_fetch_candidates": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, _ip, _ip]),
+    "rp_batch_winner_states": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "rp_batch_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "rp_initial_states": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip, _dp, _dp, _ip]),
     "rp_batch_initial_states": (C.c_int, [C.c_void_p, _dp, _ip, _dp, _dp, _ip]),
@@ -590,6 +591,13 @@ class Batch:
         lon, lat, status = np.empty((n, 3)), np.empty((n, 3)), np.empty(n, dtype=np.int32)
         self._check(self._lib.rp_batch_initial_states(self._b, _p(x0, _dp), _p(lv, _ip), _p(lon, _dp), _p(lat, _dp), _p(status, _ip)))
         return lon, lat, status
+
+    def winner_states(self, step):
+        """state of every scenario's winner at time step ``step`` (n, 16): x, y, theta, v, a, kappa, s, s_dot, s_ddot, d,
+        d_dot, d_ddot, valid -- where the next replanning cycle of a closed-loop batch starts"""
+        out = np.empty((len(self.engines), 16), dtype=np.float64)
+        self._check(self._lib.rp_batch_winner_states(self._b, int(step), _p(out, _dp)))
+        return out
 
     def last_ms(self):
         """(device milliseconds of the last launch, candidates it evaluated)"""

@@ -126,7 +126,13 @@ struct LonRow {
 };
 enum : unsigned { LR_PRE = 3u, LR_MOVING = 4u, LR_OK_S = 8u, LR_REJECT = 16u };
 constexpr int kLonRowDoubles = 14;
-constexpr int kWarpRowDoubles = kLonRowDoubles * 32 + 32;     // + [32] flag words + [32] dynamic-obstacle masks
+// row slots per warp: 32 in general; the ONE_GROUP instantiation (one longitudinal polynomial per warp) may refresh fewer
+// steps at a time to leave shared memory for more resident warps
+#ifndef RP_CAND_ONE_GROUP_SLOTS
+#define RP_CAND_ONE_GROUP_SLOTS 32
+#endif
+__host__ __device__ constexpr int warp_row_doubles(int slots) { return kLonRowDoubles * slots + slots; }   // + flag words + dynamic-obstacle masks
+constexpr int kWarpRowDoubles = warp_row_doubles(32);
 
 template <bool EXACT>
 __device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables& R, const double* __restrict__ cs_ptr, int i) {
@@ -413,7 +419,7 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 // candidate and write nothing.
 // ONE_GROUP: the host guarantees G == 1 for every chunk (grid form, n_d a multiple of 32, aligned shard): the group
 // arithmetic folds away at compile time.
-template <int BLOCK, bool ONE_GROUP, int PF, bool LATROWS = false>
+template <int BLOCK, bool ONE_GROUP, int PF, bool LATROWS = false, int SLOTS = 32>
 __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k, bool valid,
                                            double* __restrict__ acc, double* __restrict__ s_vmid,
                                            double* __restrict__ rows) {
@@ -482,10 +488,11 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     }
     if (tl > Np1) tl = Np1;
     const int tl_warp = P.mode == 0 ? tl : __reduce_max_sync(0xffffffffu, tl);
-    const int W = ONE_GROUP ? 32 : 32 / G;               // steps per refresh of the rows
-    const int item_g = ONE_GROUP ? 0 : lane / W;         // the (group, step offset) this lane computes
-    const int item_w = ONE_GROUP ? lane : lane - item_g * W;
-    unsigned* const rflags = reinterpret_cast<unsigned*>(rows + kLonRowDoubles * 32);
+    const int W = ONE_GROUP ? SLOTS : 32 / G;            // steps per refresh of the rows
+    // the (group, step offset) this lane computes (idle if item_g >= G)
+    const int item_g = (ONE_GROUP && SLOTS == 32) ? 0 : lane / W;
+    const int item_w = (ONE_GROUP && SLOTS == 32) ? lane : lane - item_g * W;
+    unsigned* const rflags = reinterpret_cast<unsigned*>(rows + kLonRowDoubles * SLOTS);
     int row_base = 0, row_next = 0;
 
     unsigned pre = 0u, bad = NONE, pbad = NONE, col = NONE;
@@ -511,12 +518,12 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
                 if (step < tl) {
                     const double* cs_item = P.mode == 0 ? cs_group0 + (size_t)item_g * 6 : I.cs;
                     const LonRow w = lon_part<false>(P, R, cs_item, step);
-                    double* c = rows + lane;
-                    c[0] = w.s; c[32] = w.sv; c[64] = w.sa; c[96] = w.y_sv; c[128] = w.y_sv2; c[160] = w.th_ref;
-                    c[192] = w.k_r; c[224] = w.k_r_d; c[256] = w.bx; c[288] = w.by; c[320] = w.nx; c[352] = w.ny;
-                    c[384] = w.c_ref; c[416] = w.s_ref;
+                    double* c = rows + lane;                   // (lane == item index: item_g * W + item_w)
+                    c[0] = w.s; c[SLOTS] = w.sv; c[2 * SLOTS] = w.sa; c[3 * SLOTS] = w.y_sv; c[4 * SLOTS] = w.y_sv2;
+                    c[5 * SLOTS] = w.th_ref; c[6 * SLOTS] = w.k_r; c[7 * SLOTS] = w.k_r_d; c[8 * SLOTS] = w.bx; c[9 * SLOTS] = w.by;
+                    c[10 * SLOTS] = w.nx; c[11 * SLOTS] = w.ny; c[12 * SLOTS] = w.c_ref; c[13 * SLOTS] = w.s_ref;
                     rflags[lane] = w.flags;
-                    rflags[32 + lane] = w.dynmask;
+                    rflags[SLOTS + lane] = w.dynmask;
                 }
             }
             __syncwarp();
@@ -528,11 +535,11 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             const int item = grp * W + (i - row_base);
             const double* c = rows + item;
             LonRow L;
-            L.s = c[0]; L.sv = c[32]; L.sa = c[64]; L.y_sv = c[96]; L.y_sv2 = c[128]; L.th_ref = c[160];
-            L.k_r = c[192]; L.k_r_d = c[224]; L.bx = c[256]; L.by = c[288]; L.nx = c[320]; L.ny = c[352];
-            L.c_ref = c[384]; L.s_ref = c[416];
+            L.s = c[0]; L.sv = c[SLOTS]; L.sa = c[2 * SLOTS]; L.y_sv = c[3 * SLOTS]; L.y_sv2 = c[4 * SLOTS]; L.th_ref = c[5 * SLOTS];
+            L.k_r = c[6 * SLOTS]; L.k_r_d = c[7 * SLOTS]; L.bx = c[8 * SLOTS]; L.by = c[9 * SLOTS]; L.nx = c[10 * SLOTS];
+            L.ny = c[11 * SLOTS]; L.c_ref = c[12 * SLOTS]; L.s_ref = c[13 * SLOTS];
             L.flags = rflags[item];
-            heavy_dynmask = rflags[32 + item];
+            heavy_dynmask = rflags[SLOTS + item];
             StepOut o = lat_part<false, LATROWS>(P, R, Y, L, LATROWS ? I.lr + (size_t)i * I.lr_stride : I.cd, cs0, th_gl, kappa, i);
             if (o.reject & 0x80000000u) o = poly_step_exact<LATROWS>(P, R, Y, I);
             pre |= o.pre;
@@ -708,8 +715,9 @@ cand_kernel(const __grid_constant__ PlanParams P) {
     sp += BLOCK;
     LimitRcp* const s_Y = reinterpret_cast<LimitRcp*>(sp);
     sp += 4;
-    double* const s_rows = sp + (size_t)(tid >> 5) * kWarpRowDoubles;   // this warp's longitudinal rows
-    sp += (size_t)(BLOCK / 32) * kWarpRowDoubles;
+    constexpr int SLOTS = ONE_GROUP ? RP_CAND_ONE_GROUP_SLOTS : 32;
+    double* const s_rows = sp + (size_t)(tid >> 5) * warp_row_doubles(SLOTS);   // this warp's longitudinal rows
+    sp += (size_t)(BLOCK / 32) * warp_row_doubles(SLOTS);
     Segment* const s_segs = reinterpret_cast<Segment*>(sp);
     for (int q = tid; q < P.n_segs; q += BLOCK) s_segs[q] = P.segs[q];
     if (tid == 0) {
@@ -726,7 +734,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         if (g >= P.n_groups) break;
         bool valid;
         const int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
-        cand_march<BLOCK, ONE_GROUP, 2, LATROWS>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, ONE_GROUP, 2, LATROWS, SLOTS>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 

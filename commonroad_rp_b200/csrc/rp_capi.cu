@@ -475,7 +475,7 @@ int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry
 
 // Launch geometry of the candidate-major kernel (rp_cand.cuh): segments sorted by traj_len, longest first,
 // cut into chunks of 32 candidates that the warps of a persistent grid draw from a counter.
-int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, int n_acc_rows) {
+int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, int n_acc_rows, bool one_group) {
     std::stable_sort(segs.begin(), segs.end(), [](const rp::Segment& a, const rp::Segment& b) { return a.tl > b.tl; });
     G.big = false;
     G.threads = RP_CAND_THREADS;
@@ -491,7 +491,7 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
     const size_t budget = (size_t)ctx->max_smem_optin;
     const size_t acc_bytes = (size_t)(n_acc_rows * 8 + 1) * G.threads * sizeof(double);    // + v_mid
     const size_t fixed = (size_t)segs.size() * sizeof(rp::Segment) + 128 +
-                         (size_t)(G.threads / 32) * rp::kWarpRowDoubles * sizeof(double);     // the warps' longitudinal rows
+                         (size_t)(G.threads / 32) * rp::warp_row_doubles(one_group ? RP_CAND_ONE_GROUP_SLOTS : 32) * sizeof(double);   // the warps' longitudinal rows
     G.stage_dyn = 0;                                   // dynamic-obstacle rows are read through L1 (dyn_rows_kernel)
     G.smem = acc_bytes + fixed;
     G.stage_ref = 0;                                   // reference tables through L1 (staging them cost occupancy, profiles/README.md)
@@ -613,7 +613,7 @@ int prepare_main_geometry(rp_ctx* ctx, int first, int count) {
         // one longitudinal group per chunk of 32: grid form, n_d a multiple of 32, shard boundaries on multiples of 32
         ctx->main_one_group = ctx->mode == 0 && ctx->n_d > 0 && ctx->n_d % 32 == 0 && first % 32 == 0 && count % 32 == 0;
         std::vector<rp::Segment> sorted = segs;
-        if (plan_cand_geometry(ctx, Np1, sorted, ctx->main_geom, cand_acc_rows(ctx->in)) == RP_OK) {
+        if (plan_cand_geometry(ctx, Np1, sorted, ctx->main_geom, cand_acc_rows(ctx->in), ctx->main_one_group) == RP_OK) {
             segs.swap(sorted);
         } else {
             ctx->main_is_cand = false;          // e.g. a segment table too long for its shared memory: the other schedule
@@ -2142,6 +2142,26 @@ int rp_batch_fetch_candidates(rp_batch* b, int k, double* cost, int32_t* status,
         if (reason) reason[q] = (info[q] >> 8) & 0xFF;
         if (step) step[q] = ((info[q] >> 16) & 0xFFFF) - 1;
     }
+    return RP_OK;
+}
+
+int rp_batch_winner_states(rp_batch* b, int step, double* out) {
+    if (!b || !out) return fail(RP_ERR_ARG, "null argument");
+    if (!b->launched) return fail(RP_ERR_STATE, "no batch launched");
+    if (step < 0) return fail(RP_ERR_ARG, "negative time step");
+    RP_CUDA(cudaSetDevice(b->device));
+    const int n = (int)b->ctxs.size();
+    for (int k = 0; k < n; ++k)
+        if (step > b->slots[k].in.N) return fail(RP_ERR_ARG, "time step beyond a scenario's horizon");
+    DevBuf d_out;
+    if (int rc = d_out.ensure((size_t)n * 16 * sizeof(double))) return rc;
+    rp::batch_winner_step_kernel<<<(n + 63) / 64, 64, 0, b->stream>>>(reinterpret_cast<const PlanParams*>(b->d_stage.p),
+                                                                     b->d_results.as<rp::PlanResultDev>(), n, step, d_out.as<double>());
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    d_out.release();
+    if (e != cudaSuccess) return fail(RP_ERR_CUDA, cudaGetErrorString(e));
     return RP_OK;
 }
 

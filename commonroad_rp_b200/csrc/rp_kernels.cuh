@@ -397,6 +397,70 @@ __global__ void __launch_bounds__(256) argmin_batch_kernel(const PlanParams* __r
     block_select(P.cost, P.info, 0, P.n_cand, results + blockIdx.x);
 }
 
+// Closed-loop batches (run_planner.py:84-107 for many scenarios at once): the state of every scenario's winner at time
+// step `step` -- where the next replanning cycle starts -- in ONE launch, one thread per scenario marching 0 .. step with
+// the exact form of the per-step code (standstill carry, horizon extension included).
+// out[sc][16] = x, y, theta, v, a, kappa, s, s_dot, s_ddot, d, d_dot, d_ddot, valid (1 / 0: no winner), -, -, -
+__global__ void __launch_bounds__(64) batch_winner_step_kernel(const PlanParams* __restrict__ params,
+                                                               const PlanResultDev* __restrict__ results, int n, int step,
+                                                               double* __restrict__ out) {
+    const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sc >= n) return;
+    const PlanParams& P = params[sc];
+    double* o = out + (size_t)sc * 16;
+    const int k = results[sc].r.winner;
+    for (int q = 0; q < 16; ++q) o[q] = 0.;
+    if (k < 0 || P.mode != 0) return;
+    const rp_plan_inputs& in = P.in;
+    const bool low_vel = in.low_vel_mode != 0;
+    const int per_t = P.n_lon * P.n_d;
+    const int it = k / per_t, rem = k - it * per_t, il = rem / P.n_d, id = rem - il * P.n_d;
+    StepIn I;
+    I.cs = P.lon_coef + (size_t)(it * P.n_lon + il) * 6;
+    I.cd = P.lat_coef + (size_t)(low_vel ? k : it * P.n_d + id) * 6;
+    I.lr = nullptr;
+    I.lr_stride = 0;
+    int tl = P.traj_len[it];
+    tl = tl > P.Np1 ? P.Np1 : tl;
+    LimitRcp Y{0., 0., 0.};                                  // (unused by the exact form)
+    const int last = step < tl ? step : tl - 1;
+    StepOut so{};
+    double th = 0., kap = 0.;
+    for (int i = 0; i <= last; ++i) {
+        I.i = i; I.th_prev = th; I.kap_prev = kap;
+        so = poly_step<true, false>(P, P.ref, Y, I);
+        th = so.th_gl; kap = so.kappa;
+    }
+    const double tt = (double)last * in.dt;
+    const double t2 = tt * tt, t3 = t2 * tt;
+    double cs[6], cd[6];
+    for (int q = 0; q < 6; ++q) { cs[q] = I.cs[q]; cd[q] = I.cd[q]; }
+    const double sa = poly_acc(cs, tt, t2, t3);
+    double da;
+    if (!low_vel) {
+        da = poly_acc(cd, tt, t2, t3);
+    } else {
+        const double s1 = so.s - cs[0];
+        da = poly_acc(cd, s1, s1 * s1, s1 * s1 * s1);
+    }
+    double x = so.x, y = so.y, v = so.v, s = so.s, d = so.d;
+    if (step >= tl) {
+        // horizon extension (trajectories.py:168-197, :302-332), as in cand_march
+        double ax = 0., ay = 0.;
+        for (int i = tl; i <= step; ++i) {
+            const double tau = (double)(i - tl + 1) * in.dt;
+            double v_tmp = so.v + tau * so.a;
+            v_tmp = v_tmp * (v_tmp >= 0 ? 1.0 : 0.0);
+            const double ix = in.dt * v_tmp * so.cn, iy = in.dt * v_tmp * so.sn;
+            if (i == tl) { ax = ix; ay = iy; } else { ax += ix; ay += iy; }
+            if (i == step) { v = v_tmp; s = so.s + tau * so.sv; d = so.d + tau * so.dv; }
+        }
+        x = so.x + ax; y = so.y + ay;
+    }
+    o[0] = x; o[1] = y; o[2] = so.th_gl; o[3] = v; o[4] = so.a; o[5] = so.kappa;
+    o[6] = s; o[7] = so.sv; o[8] = sa; o[9] = d; o[10] = so.dv; o[11] = da; o[12] = 1.0;
+}
+
 // replanning-size bundle: selection + the winner's 14 x (N + 1) state block gathered from the states the main launch
 // wrote for every kept candidate -- one launch instead of partial / merge / count / winner-state re-evaluation
 __global__ void __launch_bounds__(256) select_small_kernel(const double* __restrict__ cost, const int* __restrict__ info, int first,
@@ -880,9 +944,12 @@ __global__ void __launch_bounds__(128) initial_states_kernel(int n_states, const
         } else {
             const double disc = qb * qb - 4.0 * qa * qc;
             if (disc >= 0.0) {
+                // cancellation-free form of (-qb +- sqrt(disc)) / (2 qa): qa is tiny on gently curved paths
                 const double sq = sqrt(disc);
-                roots[0] = (-qb + sq) / (2.0 * qa);
-                roots[1] = (-qb - sq) / (2.0 * qa);
+                const double qq = -0.5 * (qb + copysign(sq, qb));
+                if (qq == 0.0) { roots[0] = 0.0; roots[1] = 0.0; }
+                else if (qb >= 0.0) { roots[0] = qc / qq; roots[1] = qq / qa; }
+                else { roots[0] = qq / qa; roots[1] = qc / qq; }
                 n_roots = 2;
             }
         }

@@ -112,7 +112,9 @@ class ScenarioBatch:
             stream = st if stream is None else stream
         self.device, self.stream = device, stream
         self.engines = []
+        self.coordinate_systems = {}
         self._batch = None
+        self.x0_cart = self.x0_lon = self.x0_lat = None
 
     def add_scenario(self, vehicle, coordinate_system, collision_checker, proj_limit=20.0):
         """vehicle: VehicleConfiguration; coordinate_system: CoordinateSystem, or the (smoothed, de-duplicated)
@@ -136,6 +138,64 @@ class ScenarioBatch:
             self._batch.close()
             self._batch = None
         return len(self.engines) - 1
+
+    def add_scenario_from(self, scenario, reference_path, vehicle, road_boundary_method="obb_rectangles", proj_limit=20.0,
+                          continuous_collision_check=False):
+        """A CommonRoad scenario (commonroad-io objects, or the package's own reader ``utility.scenario_io``) -> the
+        scenario's device tables: static obstacles, dynamic obstacles as per-time-index boxes, the road boundary of its
+        lanelet network (``ReactivePlanner.set_collision_checker``, reference reactive_planner.py:218-256), and the
+        reference tables derived on the device from ``reference_path`` (smoothed and resampled on the host like
+        ``CoordinateSystem.__init__``).  Returns the scenario's index."""
+        from commonroad_rp_b200 import collision as rpc
+        from commonroad_rp_b200.utility.utils_coordinate_system import CoordinateSystem
+        cc = rpc.CollisionChecker()
+        for ob in scenario.static_obstacles:
+            cc.add_collision_object(rpc.create_collision_object(ob))
+        for ob in scenario.dynamic_obstacles:
+            tvo = rpc.create_collision_object(ob)
+            if continuous_collision_check:
+                tvo, err = rpc.trajectory_preprocess_obb_sum(tvo)
+                if err == -1:
+                    raise Exception("Invalid input for trajectory_preprocess_obb_sum: dynamic obstacle elements overlap")
+            cc.add_collision_object(tvo)
+        cc.add_collision_object(rpc.create_road_boundary_obstacle(scenario, method=road_boundary_method)[1])
+        co = reference_path if isinstance(reference_path, CoordinateSystem) else CoordinateSystem(reference_path)
+        k = self.add_scenario(vehicle, co, cc, proj_limit)
+        self.coordinate_systems[k] = co
+        return k
+
+    # ---- closed loop over replanning cycles (run_planner.py:61-107 for every scenario at once) ----
+    def reset(self, states_cart, low_vel_mode=0, states_curv=None):
+        """``ReactivePlanner.reset(initial_state_cart=..., initial_state_curv=...)`` (reference :172-216) for all scenarios:
+        Cartesian rear-axle states x0[n][6] = x, y, orientation, velocity, acceleration, steering_angle; the curvilinear
+        states are taken from ``states_curv = (lon[n][3], lat[n][3])`` or projected onto each scenario's own reference
+        path in ONE launch (rp_batch_initial_states; status 1 / 2 raise the reference's exceptions).  Returns (lon, lat)."""
+        import numpy as np
+        x0 = np.ascontiguousarray(states_cart, dtype=np.float64).reshape(len(self.engines), 6)
+        if states_curv is None:
+            lon, lat, status = self.batch.initial_states(x0, low_vel_mode)
+            if (status == 1).any():
+                raise ValueError("Initial state could not be transformed (scenarios %s)." % np.flatnonzero(status == 1).tolist())
+            if (status == 2).any():
+                raise Exception("Initial state or reference incorrect! Curvilinear velocity is negative (scenarios %s)"
+                                % np.flatnonzero(status == 2).tolist())
+        else:
+            lon = np.ascontiguousarray(states_curv[0], dtype=np.float64).reshape(-1, 3)
+            lat = np.ascontiguousarray(states_curv[1], dtype=np.float64).reshape(-1, 3)
+        self.x0_cart, self.x0_lon, self.x0_lat = x0, lon, lat
+        return lon, lat
+
+    def advance(self, steps):
+        """After ``plan``: move every scenario ``steps`` time steps along its winner (the next replanning cycle starts
+        there, run_planner.py:84-107) -- one launch for all scenarios.  Updates x0_cart / x0_lon / x0_lat in place for
+        the scenarios that have a winner and returns the (n, 16) state rows (column 12: 1 = advanced)."""
+        w = self.batch.winner_states(steps)
+        ok = w[:, 12] > 0.5
+        if getattr(self, "x0_cart", None) is not None:
+            self.x0_cart[ok, 0:5] = w[ok, 0:5]                     # x, y, orientation, velocity, acceleration
+            self.x0_lon[ok] = w[ok, 6:9]
+            self.x0_lat[ok] = w[ok, 9:12]
+        return w
 
     def __len__(self):
         return len(self.engines)

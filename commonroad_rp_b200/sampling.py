@@ -215,14 +215,56 @@ class FixedIntervalSampling(SamplingSpace):
         return out
 
 
+class IntervalCorridor(dict):
+    """A driving corridor as plain interval arrays: ``time index -> (n, 6) array`` whose rows are the curvilinear
+    bounding intervals (s_lo, s_hi, d_lo, d_hi, v_lo, v_hi) of the reach-set nodes at that time -- what
+    commonroad_reach's ReachNode exposes as p_lon_min/max, p_lat_min/max, v_lon_min/max.  ``CorridorSampling`` accepts
+    it in place of a commonroad_reach ``DrivingCorridor`` (which needs CommonRoad-Reach installed); the four reach
+    operations the reference calls (sampling.py:312, :365-371) are then the interval versions below."""
+
+    def __init__(self, intervals):
+        super().__init__({int(k): np.asarray(v, dtype=np.float64).reshape(-1, 6) for k, v in dict(intervals).items()})
+
+
+class _IntervalReachOperations:
+    """commonroad_reach.utility.reach_operation on IntervalCorridor node arrays"""
+
+    @staticmethod
+    def lon_velocity_interval_connected_set(nodes):
+        return (float(np.min(nodes[:, 4])), float(np.max(nodes[:, 5]))) if len(nodes) else (0.0, 0.0)
+
+    @staticmethod
+    def determine_overlapping_nodes_with_lon_pos(nodes, lon_pos):
+        return nodes[(nodes[:, 0] <= lon_pos) & (lon_pos <= nodes[:, 1])]
+
+    @staticmethod
+    def determine_connected_components(nodes):
+        """nodes whose lateral intervals overlap (transitively) form one connected set; ordered by lower bound"""
+        nodes = np.asarray(nodes, dtype=np.float64).reshape(-1, 6)
+        if len(nodes) == 0:
+            return []
+        nodes = nodes[np.argsort(nodes[:, 2], kind="stable")]
+        groups, start, hi = [], 0, nodes[0, 3]
+        for k in range(1, len(nodes)):
+            if nodes[k, 2] > hi:
+                groups.append(nodes[start:k])
+                start, hi = k, nodes[k, 3]
+            else:
+                hi = max(hi, nodes[k, 3])
+        groups.append(nodes[start:])
+        return groups
+
+    @staticmethod
+    def lat_interval_connected_set(nodes):
+        return float(np.min(nodes[:, 2])), float(np.max(nodes[:, 3]))
+
+
 class CorridorSampling(SamplingSpace):
-    """Adaptive sampling inside a precomputed collision-free driving corridor (reference :273-397).
-    Needs CommonRoad-Reach, like the reference; candidates reach the GPU through the generic list form
-    (``rp_plan_list``)."""
+    """Adaptive sampling inside a precomputed collision-free driving corridor (reference :273-397): a
+    commonroad_reach ``DrivingCorridor`` (needs CommonRoad-Reach, like the reference) or an ``IntervalCorridor`` of plain
+    (s, d, v) interval arrays.  Candidates reach the GPU through the generic list form (``rp_plan_list``)."""
 
     def __init__(self, config: ReactivePlannerConfiguration):
-        if not cr_reach_installed:
-            raise ImportError("<CorridorSampling>: Please install CommonRoad-Reach to use adaptive corridor sampling!")
         num_sampling_levels = config.sampling.num_sampling_levels
         super().__init__(num_sampling_levels)
         self.dt = config.planning.dt
@@ -239,10 +281,17 @@ class CorridorSampling(SamplingSpace):
 
     @driving_corridor.setter
     def driving_corridor(self, corridor):
+        if isinstance(corridor, IntervalCorridor):
+            self._ops = _IntervalReachOperations
+        elif cr_reach_installed:
+            self._ops = util_reach_operation
+        else:
+            raise ImportError("<CorridorSampling>: Please install CommonRoad-Reach to use adaptive corridor sampling "
+                              "(or pass an IntervalCorridor of plain interval arrays)!")
         self._corridor = corridor
         self._velocity_constraints = dict()
         for time_idx, connected_reach_set in self._corridor.items():
-            lo, hi = util_reach_operation.lon_velocity_interval_connected_set(connected_reach_set)[:2]
+            lo, hi = self._ops.lon_velocity_interval_connected_set(connected_reach_set)[:2]
             self._velocity_constraints[time_idx] = [lo, hi]
 
     @SamplingSpace.samples_d.setter
@@ -293,11 +342,11 @@ class CorridorSampling(SamplingSpace):
             traj_lon = QuarticTrajectory(tau_0=0, delta_tau=t, x_0=x0_lon.copy(), x_d=np.array([v, 0]), coeffs=c_lon[q])
             lon_trajs.append(traj_lon)
             end_pos_lon = traj_lon.calc_position(t, t ** 2, t ** 3, t ** 4, t ** 5)
-            overlap = util_reach_operation.determine_overlapping_nodes_with_lon_pos(self._corridor[time_step], end_pos_lon)
+            overlap = self._ops.determine_overlapping_nodes_with_lon_pos(self._corridor[time_step], end_pos_lon)
             if len(list(overlap)) == 0:
                 continue
-            for lat_con_set in util_reach_operation.determine_connected_components(list(overlap)):
-                lo, hi = util_reach_operation.lat_interval_connected_set(lat_con_set)[:2]
+            for lat_con_set in self._ops.determine_connected_components(list(overlap)):
+                lo, hi = self._ops.lat_interval_connected_set(lat_con_set)[:2]
                 d_samples = set(np.linspace(lo, hi, num_samples))
                 if lo < 0 < hi:
                     d_samples = d_samples.union({0})

@@ -1,5 +1,5 @@
-"""Small host helpers of the reference's ``utility/general.py``: scenario loading (delegated to
-commonroad-io), the desired velocity implied by a planning problem, orientation folding."""
+"""Small host helpers of the reference's ``utility/general.py``: scenario loading (commonroad-io, or the package's
+own XML reader), the desired velocity implied by a planning problem, orientation folding."""
 from typing import Optional
 
 import numpy as np
@@ -8,12 +8,15 @@ _TWO_PI = 2 * np.pi
 
 
 def load_scenario_and_planning_problem(path_scenario, idx_planning_problem: Optional[int] = None):
-    """(scenario, planning problem, planning problem set) from a CommonRoad XML file.  Needs commonroad-io;
-    without it pass scenario objects or a ``collision.CollisionChecker`` to the planner directly."""
+    """(scenario, planning problem, planning problem set) from a CommonRoad XML file (reference utility/general.py:11-29):
+    through commonroad-io when it is installed, else through the package's own reader (utility/scenario_io.py; the
+    planning problem set is then None)."""
     try:
         from commonroad.common.file_reader import CommonRoadFileReader
-    except ImportError as exc:
-        raise ImportError("reading CommonRoad XML requires commonroad-io") from exc
+    except ImportError:
+        from commonroad_rp_b200.utility.scenario_io import read_commonroad_xml
+        scenario, problem = read_commonroad_xml(path_scenario, idx_planning_problem)
+        return scenario, problem, None
     scenario, problem_set = CommonRoadFileReader(path_scenario).open()
     if idx_planning_problem is None:
         problem = next(iter(problem_set.planning_problem_dict.values()))

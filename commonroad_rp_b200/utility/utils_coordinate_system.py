@@ -205,8 +205,15 @@ class PolylineFrame:
             else:
                 disc = qb[j] * qb[j] - 4.0 * qa[j] * qc[j]
                 if disc >= 0.0:
+                    # cancellation-free form of (-qb +- sqrt(disc)) / (2 qa) (qa is tiny on gently curved paths)
                     r = math.sqrt(disc)
-                    roots += [(-qb[j] + r) / (2.0 * qa[j]), (-qb[j] - r) / (2.0 * qa[j])]
+                    qq = -0.5 * (qb[j] + math.copysign(r, qb[j]))
+                    if qq == 0.0:
+                        roots += [0.0, 0.0]
+                    elif qb[j] >= 0.0:
+                        roots += [qc[j] / qq, qq / qa[j]]
+                    else:
+                        roots += [qq / qa[j], qc[j] / qq]
             for lam in roots:
                 if -1e-12 <= lam <= 1.0 + 1e-12:
                     lam = min(max(lam, 0.0), 1.0)

@@ -282,6 +282,10 @@ int rp_batch_set_inputs_all(rp_batch* b, const rp_plan_inputs* in, const int32_t
 int rp_batch_launch(rp_batch* b);                              /* asynchronous on the batch's stream */
 int rp_batch_results(rp_batch* b, rp_plan_result* out);        /* out[rp_batch_size]; synchronises */
 int rp_batch_fetch_candidates(rp_batch* b, int k, double* cost, int32_t* status, int32_t* reason, int32_t* step);
+/* closed-loop batches (run_planner.py:84-107 for every scenario at once): the state of each scenario's winner at time step
+ * `step` of its trajectory, where the next replanning cycle starts -- one launch.  out[rp_batch_size][16] = x, y, theta, v,
+ * a, kappa, s, s_dot, s_ddot, d, d_dot, d_ddot, valid (0: the scenario has no winner), 3 unused */
+int rp_batch_winner_states(rp_batch* b, int step, double* out);
 /* device time of the last rp_batch_launch (its four launches) and the candidates it evaluated */
 int rp_batch_last_ms(rp_batch* b, float* ms, long long* n_candidates);
 

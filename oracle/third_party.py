@@ -206,8 +206,16 @@ class CurvilinearCoordinateSystem:
             else:
                 disc = qb * qb - 4.0 * qa * qc
                 if disc >= 0.0:
+                    # cancellation-free form of (-qb +- sqrt(disc)) / (2 qa): on gently curved paths qa is tiny and the
+                    # textbook formula loses half the digits (1e-7 m on s; tests/test_third_party_properties.py)
                     sq = math.sqrt(disc)
-                    roots.extend([(-qb + sq) / (2.0 * qa), (-qb - sq) / (2.0 * qa)])
+                    qq = -0.5 * (qb + math.copysign(sq, qb))
+                    if qq == 0.0:
+                        roots.extend([0.0, 0.0])
+                    elif qb >= 0.0:
+                        roots.extend([qc / qq, qq / qa])           # (-qb + sq) / 2qa, (-qb - sq) / 2qa
+                    else:
+                        roots.extend([qq / qa, qc / qq])
             for lam in roots:
                 if -1e-12 <= lam <= 1.0 + 1e-12:
                     lam = min(max(lam, 0.0), 1.0)

@@ -471,3 +471,205 @@ def test_reference_tables_derived_on_the_device():
     assert H.rel_err(ra["winner_states"], rb["winner_states"]) < 1e-9
     eng_a.close()
     eng_b.close()
+
+
+def test_corridor_sampling_on_interval_arrays_matches_oracle():
+    """CorridorSampling (sampling.py:273-397) fed with plain (s, d, v) interval arrays -- no
+    CommonRoad-Reach -- reaches the GPU through the list form; verdicts, winner and counters equal the oracle's evaluation
+    of the same candidate list"""
+    from commonroad_rp_b200.sampling import CorridorSampling, IntervalCorridor
+    p, scn = _planner(seed=3, N=20, s_dot0=12.0)
+    s0 = p.x_0_cl[0][0]
+    corridor = {}
+    for k in range(0, 21):
+        s_mid = s0 + 12.0 * 0.1 * k
+        corridor[k] = np.array([[s_mid - 8.0, s_mid + 10.0, -2.5, 0.4, 8.0, 14.0],
+                                [s_mid - 6.0, s_mid + 12.0, 0.1, 1.2, 10.0, 15.0],
+                                [s_mid - 2.0, s_mid + 6.0, 2.2, 3.0, 9.0, 11.0]])
+    cs = CorridorSampling(p.config)
+    cs.driving_corridor = IntervalCorridor(corridor)
+    p.set_sampling_space(cs)
+    p.reset(initial_state_cart=p.x_0, initial_state_curv=p.x_0_cl, collision_checker=p.collision_checker,
+            coordinate_system=p.coordinate_system)
+    out = p.plan(current_sampling_level=2)
+    res = p.last_result
+    assert res.n_candidates > 100
+    cands = cs.generate_trajectories_at_level(2, p.x_0_cl[0], p.x_0_cl[1], "velocity_keeping", False)
+    assert len(cands) == res.n_candidates
+    cl = np.array([c.trajectory_long.coeffs for c in cands])
+    ct = np.array([c.trajectory_lat.coeffs for c in cands])
+    dtau = np.array([c.trajectory_long.delta_tau for c in cands])
+    tables = O.reference_tables(scn["ref_path"])
+    prob = H.make_problem(scn, [1.0], [1.0], [0.0], p.x_0_cl[0], p.x_0_cl[1], N=20, x0_orientation=p.x_0.orientation,
+                          desired_speed=12.0, tables=tables)
+    o = O.plan_candidates(cl, ct, dtau, prob, want_states=True, full_collision=False)
+    assert o["winner"] == res.winner and (out is not None) == (o["winner"] >= 0)
+    assert o["n_infeasible_kinematics"] == p.infeasible_count_kinematics
+    assert o["n_infeasible_collision"] == p.infeasible_count_collision
+    if out is not None:
+        got = np.array([[st.position[0], st.position[1], st.velocity] for st in out[0].state_list]).T
+        assert H.rel_err(o["states"][o["winner"]][[0, 1, 3]], got) < 1e-9
+
+
+def _write_commonroad_xml(path):
+    """a small CommonRoad 2020a file of our own: a straight two-lane road (lanelets 1 -> 2, neighbour 3 -> 4 on the left)
+    with a side road (5) branching off lanelet 1's end to the right, a parked car, a moving car, a planning problem"""
+    def bound(xs, ys):
+        return "".join("<point><x>%.6f</x><y>%.6f</y></point>" % (x, y) for x, y in zip(xs, ys))
+
+    def lanelet(lid, xs, yl, yr, succ=(), pred=(), adj_l=None, adj_r=None):
+        s = '<lanelet id="%d"><leftBound>%s</leftBound><rightBound>%s</rightBound>' % (lid, bound(xs, yl), bound(xs, yr))
+        s += "".join('<predecessor ref="%d"/>' % p for p in pred) + "".join('<successor ref="%d"/>' % q for q in succ)
+        if adj_l is not None:
+            s += '<adjacentLeft ref="%d" drivingDir="same"/>' % adj_l
+        if adj_r is not None:
+            s += '<adjacentRight ref="%d" drivingDir="same"/>' % adj_r
+        return s + "</lanelet>"
+
+    x1, x2 = np.arange(0.0, 61.0, 1.0), np.arange(60.0, 161.0, 1.0)
+    one = np.ones_like
+    xml = ['<?xml version="1.0" ?><commonRoad commonRoadVersion="2020a" benchmarkID="ZAM_Synth-1_1_T-1" timeStepSize="0.1">']
+    xml.append(lanelet(1, x1, 1.75 * one(x1), -1.75 * one(x1), succ=(2, 5), adj_l=3))
+    xml.append(lanelet(2, x2, 1.75 * one(x2), -1.75 * one(x2), pred=(1,), adj_l=4))
+    xml.append(lanelet(3, x1, 5.25 * one(x1), 1.75 * one(x1), succ=(4,), adj_r=1))
+    xml.append(lanelet(4, x2, 5.25 * one(x2), 1.75 * one(x2), pred=(3,), adj_r=2))
+    # side road: leaves lanelet 1 at x = 60 and bends away to the right
+    u = np.linspace(0.0, 1.0, 31)
+    cx, cy = 60.0 + 40.0 * u, -25.0 * u ** 2
+    th = np.arctan2(-50.0 * u, 40.0)
+    xml.append('<lanelet id="5"><leftBound>%s</leftBound><rightBound>%s</rightBound><predecessor ref="1"/></lanelet>' % (
+        bound(cx - 1.75 * np.sin(th), cy + 1.75 * np.cos(th)), bound(cx + 1.75 * np.sin(th), cy - 1.75 * np.cos(th))))
+    xml.append('<staticObstacle id="30"><type>parkedVehicle</type><shape><rectangle><length>4.5</length><width>2.0</width>'
+               '</rectangle></shape><initialState><position><point><x>55.0</x><y>-0.9</y></point></position>'
+               '<orientation><exact>0.05</exact></orientation><time><exact>0</exact></time></initialState></staticObstacle>')
+    states = "".join('<state><position><point><x>%.4f</x><y>3.5</y></point></position><orientation><exact>0.0</exact></orientation>'
+                     '<time><exact>%d</exact></time><velocity><exact>9.0</exact></velocity></state>' % (20.0 + 0.9 * k, k)
+                     for k in range(1, 61))
+    xml.append('<dynamicObstacle id="31"><type>car</type><shape><rectangle><length>4.8</length><width>1.9</width></rectangle></shape>'
+               '<initialState><position><point><x>20.0</x><y>3.5</y></point></position><orientation><exact>0.0</exact></orientation>'
+               '<time><exact>0</exact></time><velocity><exact>9.0</exact></velocity></initialState><trajectory>%s</trajectory>'
+               '</dynamicObstacle>' % states)
+    xml.append('<planningProblem id="100"><initialState><position><point><x>12.0</x><y>0.2</y></point></position>'
+               '<orientation><exact>0.01</exact></orientation><time><exact>0</exact></time><velocity><exact>11.0</exact></velocity>'
+               '<yawRate><exact>0.0</exact></yawRate><slipAngle><exact>0.0</exact></slipAngle></initialState>'
+               '<goalState><position><lanelet ref="2"/></position><time><intervalStart>40</intervalStart><intervalEnd>80</intervalEnd></time>'
+               '<velocity><intervalStart>8.0</intervalStart><intervalEnd>14.0</intervalEnd></velocity></goalState></planningProblem>')
+    xml.append("</commonRoad>")
+    with open(path, "w") as fh:
+        fh.write("".join(xml))
+
+
+def test_scenario_file_to_device_tables_through_the_planner(tmp_path):
+    """SURVEY 8f rank 4, second half: a CommonRoad XML file -> scenario objects (the package's own reader when
+    commonroad-io is absent) -> ReactivePlanner(config) builds checker, road boundary and device tables itself
+    (reference utility/general.py:11-29, reactive_planner.py:218-256); the cycle equals the oracle's on the arrays the
+    checker holds, and a ScenarioBatch fed from the same scenario object selects the same trajectory"""
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200.parallel import ScenarioBatch
+    from commonroad_rp_b200.reactive_planner import ReactivePlanner
+    from commonroad_rp_b200.utility import scenario_io
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    from commonroad_rp_b200.utility.general import load_scenario_and_planning_problem
+    path = str(tmp_path / "ZAM_Synth-1_1_T-1.xml")
+    _write_commonroad_xml(path)
+    scenario, problem, _ = load_scenario_and_planning_problem(path)
+    assert len(scenario.lanelet_network.lanelets) == 5 and len(scenario.dynamic_obstacles) == 1
+    route = scenario_io.find_route(scenario, problem)
+    assert route == [1, 2]
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = 20
+    cfg.planning.planning_horizon = 2.0
+    cfg.update(scenario=scenario, planning_problem=problem)
+    planner = ReactivePlanner(cfg)                     # reset(): x0 from the planning problem, checker from the scenario
+    ref_path = scenario_io.route_reference_path(scenario, route, extend_back=5.0)
+    planner.set_reference_path(ref_path)
+    planner.set_desired_velocity(current_speed=planner.x_0.velocity)
+    assert planner._desired_speed == 11.0              # mid-point of the goal interval (utility/general.py:32-46)
+    out = planner.plan()
+    assert out is not None and not planner.goal_reached()
+    res = planner.last_result
+    arr = planner.collision_checker.device_arrays()
+    # road boundary: the junction mouth between lanelet 1 and the side road carries no wall, the outer borders do
+    seg_mid = arr["static_obb"][1:, :2]
+    on_right_border = np.abs(seg_mid[:, 1] + 1.75) < 1e-9
+    assert not np.any(on_right_border & (seg_mid[:, 0] > 63.0) & (seg_mid[:, 0] < 75.0))     # the side road's mouth is open
+    assert np.any(on_right_border & (np.abs(seg_mid[:, 0] - 55.5) < 1e-9)) and np.any(on_right_border & (seg_mid[:, 0] > 80.0))
+    assert np.any(np.abs(seg_mid[:, 1] - 5.25) < 1e-9) and len(arr["dyn_boxes"][0]) == 61
+    # the oracle on the same arrays
+    co = planner.coordinate_system
+    tb = co.device_tables()
+    x0_lon, x0_lat = planner.x_0_cl
+    bundle = planner._create_trajectory_bundle(x0_lon, x0_lat, samp_level=1)
+    dev = bundle.device
+    st = arr["static_obb"]
+    obstacles = {"static_boxes": np.zeros((0, 5)), "boundary_boxes": st, "boundary_tris": arr["tris"], "dyn_t0": arr["dyn_t0"],
+                 "dyn_states": [b[:, :3] for b in arr["dyn_boxes"]], "dyn_lw": [(2 * b[0, 3], 2 * b[0, 4]) for b in arr["dyn_boxes"]]}
+    prob = {"t": dev["t"], "lon": dev["lon"], "d": dev["d"], "x0_lon": np.array(x0_lon), "x0_lat": np.array(x0_lat),
+            "x0_orientation": planner.x_0.orientation, "x0_time_step": 0, "lon_mode": "velocity_keeping", "low_vel_mode": False,
+            "dt": 0.1, "N": 20, "factor": 1, "draw_all": False, "constraints": O.CONSTRAINTS,
+            "cost": {"kind": "default", "desired_speed": 11.0, "desired_s": None, "desired_d": 0.0, "w_a": 5},
+            "vehicle": O.vehicle_dict(), "ref": {k: tb[k] for k in ("ref_pos", "ref_theta", "ref_curv", "ref_curv_d")},
+            "ccosy": {"path": tb["path_xy"], "S": tb["path_s"], "normals": tb["path_normals"], "limit": tb["proj_limit"]},
+            "obstacles": obstacles}
+    o = O.plan_grid(prob, want_states=True, full_collision=False)
+    assert o["winner"] == res.winner and o["n_infeasible_kinematics"] == res.n_infeasible_kinematics
+    assert o["n_infeasible_collision"] == res.n_infeasible_collision
+    got = np.array([[s.position[0], s.position[1], s.velocity] for s in out[0].state_list]).T
+    assert H.rel_err(o["states"][o["winner"]][[0, 1, 3]], got) < 1e-9
+    # the same scenario object through the batch path
+    batch = ScenarioBatch()
+    batch.add_scenario_from(scenario, ref_path, cfg.vehicle)
+    inputs = planner._plan_inputs(x0_lon, x0_lat, planner._device_cost_spec(), False)
+    r = batch.plan([(inputs, dev["t"], dev["lon"], dev["d"])])[0]
+    assert r.winner == res.winner and r.n_infeasible_collision == res.n_infeasible_collision
+    batch.close()
+
+
+def test_closed_loop_scenario_batch_equals_individual_planners():
+    """SURVEY 8f rank 1 ("batched multi-scenario reset()"): three replanning cycles of several scenarios as ONE batch --
+    plan, advance every scenario three steps along its winner (rp_batch_winner_states), next cycle -- against one
+    ReactivePlanner per scenario running run_planner.py's loop (plan, reset to state_list[3] / lon_list[3] / lat_list[3])"""
+    from commonroad_rp_b200 import collision
+    from commonroad_rp_b200.parallel import ScenarioBatch
+    from commonroad_rp_b200.state import ReactivePlannerState
+    planners, scns = [], []
+    for sid in range(5):
+        p, scn = _planner(seed=20 + sid, N=20, s_dot0=9.0 + sid, d0=0.1 * sid - 0.2)
+        planners.append(p)
+        scns.append(scn)
+    batch = ScenarioBatch()
+    for p in planners:
+        batch.add_scenario(p.vehicle_params, p.coordinate_system, p.collision_checker)
+    x0 = np.array([[p.x_0.position[0], p.x_0.position[1], p.x_0.orientation, p.x_0.velocity, 0.0, 0.0] for p in planners])
+    lon, lat = batch.reset(x0)                                       # Cartesian -> curvilinear for all scenarios in one launch
+    for k, p in enumerate(planners):
+        # (the test planners' curvilinear VELOCITIES are set by hand, only the positions derive from the Cartesian state)
+        assert abs(p.x_0_cl[0][0] - lon[k][0]) < 1e-8 and abs(p.x_0_cl[1][0] - lat[k][0]) < 1e-8
+    batch.reset(x0, states_curv=(np.array([p.x_0_cl[0] for p in planners]), np.array([p.x_0_cl[1] for p in planners])))
+    level, steps = 2, 3
+    for cycle in range(3):
+        outs, cyc = [], []
+        for k, p in enumerate(planners):
+            p.set_desired_velocity(current_speed=p.x_0.velocity)
+            outs.append(p.plan(current_sampling_level=level))
+            assert outs[-1] is not None
+            t, lon_s, d = p.sampling_space.sample_grid(level, batch.x0_lat[k], "velocity_keeping")
+            p._low_vel_mode = bool(batch.x0_cart[k, 3] < p.config.planning.low_vel_mode_threshold)
+            inputs = type(p._inputs).from_buffer_copy(p._plan_inputs(batch.x0_lon[k], batch.x0_lat[k], p._device_cost_spec(), False))
+            inputs.x0_orientation = float(batch.x0_cart[k, 2])
+            cyc.append((inputs, t, lon_s, d))
+        res = batch.plan(cyc)
+        assert [r.winner for r in res] == [p.last_result.winner for p in planners], cycle
+        w = batch.advance(steps)
+        for k, (p, out) in enumerate(zip(planners, outs)):
+            cart, _, lon_list, lat_list = out
+            st = cart.state_list[steps]
+            want = [st.position[0], st.position[1], st.orientation, st.velocity, st.acceleration]
+            assert w[k, 12] == 1.0 and H.rel_err(want, w[k, 0:5]) < 1e-9, (cycle, k)
+            assert H.rel_err(lon_list[steps], w[k, 6:9]) < 1e-9 and H.rel_err(lat_list[steps], w[k, 9:12]) < 1e-9, (cycle, k)
+            assert np.array_equal(batch.x0_lon[k], w[k, 6:9])
+            nxt = ReactivePlannerState(time_step=st.time_step, position=st.position, orientation=st.orientation, velocity=st.velocity,
+                                       acceleration=st.acceleration, yaw_rate=st.yaw_rate, steering_angle=st.steering_angle)
+            p.reset(initial_state_cart=nxt, initial_state_curv=(lon_list[steps], lat_list[steps]),
+                    collision_checker=p.collision_checker, coordinate_system=p.coordinate_system)
+    batch.close()

@@ -312,3 +312,30 @@ def test_road_boundary_of_a_crossing_has_no_walls_inside_the_junction():
     l2 = _strip(0.0, 30.0, 3.0, 6.0, True, adj_right=1)
     segs2 = collision.road_boundary_segments([l1, l2])
     assert len(segs2) == 60 and set(np.round(0.5 * (segs2[:, 0, 1] + segs2[:, 1, 1]), 6)) == {0.0, 6.0}
+
+
+def test_interval_corridor_reach_operations():
+    """CorridorSampling on plain (s, d, v) interval arrays (no CommonRoad-Reach): the four reach operations of
+    sampling.py:312, :365-371 on node rows (s_lo, s_hi, d_lo, d_hi, v_lo, v_hi)"""
+    from commonroad_rp_b200.sampling import CorridorSampling, IntervalCorridor, _IntervalReachOperations as ops
+    from commonroad_rp_b200.utility.config import ReactivePlannerConfiguration
+    nodes = np.array([[10.0, 14.0, -1.0, 0.5, 4.0, 6.0],      # two nodes overlapping laterally ...
+                      [12.0, 16.0, 0.2, 1.5, 5.0, 8.0],
+                      [11.0, 15.0, 2.5, 3.0, 3.0, 5.0],       # ... one apart (another lane)
+                      [30.0, 34.0, -0.5, 0.5, 9.0, 9.5]])     # not reached longitudinally
+    assert ops.lon_velocity_interval_connected_set(nodes) == (3.0, 9.5)
+    hit = ops.determine_overlapping_nodes_with_lon_pos(nodes, 13.0)
+    assert len(hit) == 3
+    comps = ops.determine_connected_components(list(hit))
+    assert [len(c) for c in comps] == [2, 1]
+    assert ops.lat_interval_connected_set(comps[0]) == (-1.0, 1.5) and ops.lat_interval_connected_set(comps[1]) == (2.5, 3.0)
+    assert ops.determine_connected_components([]) == []
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = 20
+    cs = CorridorSampling(cfg)                                   # constructing needs no CommonRoad-Reach ...
+    with pytest.raises(AttributeError):
+        cs.generate_trajectories_at_level(1, [0, 10, 0], [0, 0, 0], "velocity_keeping", False)
+    with pytest.raises(ImportError):
+        cs.driving_corridor = {0: object()}                      # ... a commonroad_reach corridor does
+    cs.driving_corridor = IntervalCorridor({k: nodes for k in range(0, 25)})
+    assert cs._velocity_constraints[3] == [3.0, 9.5]
