@@ -16,8 +16,11 @@ the winner's state block.
              cycle's inputs and D2H of the result + winner states inside the timed region
   roofline   the fused kernel against the MEASURED FP64-FMA peak (this path is FP64-pipe bound, not
              HBM or tensor bound -- SURVEY 8d); algorithmic work = 200 flop per candidate-timestep
-  N > 1      the bundle grows with N (64*N velocity samples) and is sharded t-major over the ranks; one
-             small NCCL all-gather of (cost, index) records picks the global arg-min (weak scaling)
+  N > 1      weak scaling: the bundle grows with N (64*N velocity samples) and is sharded over the ranks by interleaving
+             the lon samples (every rank sees the same mix of horizons); the shard records are exchanged by two kernels
+             storing into peer-mapped mailboxes over NVLink (rp_peer_*; `--exchange nccl` keeps the NCCL form).  The same
+             line carries `strong_scaling` (the FIXED 64 x 64 x 32 bundle over the N ranks) and `scenario_batch`
+             (BASELINE configs[4]: independent scenarios, scenario-major shards, 512 per rank at N = 8)
 """
 import argparse
 import json
@@ -269,11 +272,13 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
     keys = ("static_boxes", "dyn_t0", "dyn_states", "dyn_lw", "boundary_boxes", "boundary_tris")
     batch = ScenarioBatch(device, stream_handle)
     cycle, n_cand = [], 0
+    samplers, x0_cart, x0_curv = [], [], []
     for sid in range(rank * n_scenarios, (rank + 1) * n_scenarios):       # scenario-major shards: no exchange on the data path
         scn, s_dot0, d0 = synthetic.scenario_seeded(sid)
         co = CoordinateSystem(scn["ref_path"])
         batch.add_scenario(cfg.vehicle, co, collision.checker_from_arrays(**{k: scn[k] for k in keys}))
         fs = FixedIntervalSampling(cfg)
+        samplers.append(fs)
         lo = max(0, s_dot0 - 0.125 * fs.horizon * cfg.vehicle.a_max)
         fs.samples_v = VelocitySampling(lo, max(lo + 5.0, s_dot0 + 2), 4)
         t, lon, d = fs.sample_grid(3, [d0, 0.0, 0.0], "velocity_keeping")
@@ -281,6 +286,9 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
         j = int(np.argmax(co.ref_pos > s0)) - 1
         inputs = Engine.make_inputs([s0, s_dot0, 0.0], [d0, 0.0, 0.0], float(co.ref_theta[j]), 0, s_dot0 < 4.0,
                                     "velocity_keeping", N_HORIZON, DT, desired_speed=s_dot0)
+        xy = co.convert_to_cartesian_coords(s0, d0)
+        x0_cart.append([xy[0], xy[1], float(co.ref_theta[j]), s_dot0, 0.0, 0.0])
+        x0_curv.append(([s0, s_dot0, 0.0], [d0, 0.0, 0.0]))
         from commonroad_rp_b200._lib import traj_len_of
         cycle.append((inputs, np.asarray(t, dtype=np.float64), np.asarray(lon, dtype=np.float64), np.asarray(d, dtype=np.float64),
                       np.asarray([traj_len_of(x, DT) for x in t], dtype=np.int32)))
@@ -309,6 +317,47 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         dt_s, dev_ms = float(agg[0].item()), [float(agg[1].item())]
         n_cand, n_win, n_scenarios = int(cnt[0].item()), int(cnt[1].item()), n_scenarios * world
+    # ---- closed loop (run_planner.py:61-107 for all scenarios at once): plan, advance every scenario three steps along its
+    # winner (rp_batch_winner_states, one launch), re-derive the velocity samples from the new speed (:332-335), next cycle
+    closed = None
+    if n_win > 0:
+        batch.reset(np.array(x0_cart), states_curv=(np.array([c[0] for c in x0_curv]), np.array([c[1] for c in x0_curv])))
+        a_max, horizon = cfg.vehicle.a_max, N_HORIZON * DT
+        host_s, wall_s, dev2, steps_per_cycle, closed_cycles = 0.0, 0.0, [], 3, 5
+        time_step = 0
+        cur = list(cycle)
+        for c in range(closed_cycles + 1):
+            t_a = time.perf_counter()
+            if c > 0:
+                time_step += steps_per_cycle
+                cur = []
+                for k, fs in enumerate(samplers):
+                    v = float(batch.x0_cart[k, 3])
+                    lo = max(0, v - 0.125 * horizon * a_max)
+                    fs.samples_v = VelocitySampling(lo, max(lo + 5.0, v + 2), 4)
+                    t, lon, d = fs.sample_grid(3, batch.x0_lat[k], "velocity_keeping")
+                    inp = cycle[k][0]
+                    inp.x0_lon[:] = batch.x0_lon[k].tolist()
+                    inp.x0_lat[:] = batch.x0_lat[k].tolist()
+                    inp.x0_orientation = float(batch.x0_cart[k, 2])
+                    inp.x0_time_step = time_step
+                    inp.low_vel_mode = int(v < 4.0)
+                    cur.append((inp, t, lon, d, cycle[k][4]))
+            pk = Batch.pack(cur)
+            t_b = time.perf_counter()
+            res_c = batch.plan(pk)
+            batch.advance(steps_per_cycle)
+            t_c = time.perf_counter()
+            if c > 0:
+                host_s += t_b - t_a
+                wall_s += t_c - t_a
+                dev2.append(batch.batch.last_ms()[0])
+        closed = {"cycles": closed_cycles, "steps_between_cycles": steps_per_cycle,
+                  "ms_per_cycle_of_one_ranks_scenarios": 1e3 * wall_s / closed_cycles,
+                  "host_resampling_ms_per_cycle": 1e3 * host_s / closed_cycles, "device_ms_per_cycle": float(np.mean(dev2)),
+                  "scenarios_with_winner_last_cycle": sum(1 for r in res_c if r.winner >= 0),
+                  "note": "every cycle starts from the state three steps along the previous winner (one launch for all "
+                          "scenarios); the host re-iterates each scenario's Python sample sets (set order = enumeration order)"}
     batch.plan_one_by_one(cycle)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -321,6 +370,9 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
             "ms_per_cycle_of_all_scenarios": 1e3 * dt_s, "device_ms_per_cycle": float(np.mean(dev_ms)),
             "device_value": n_cand / (float(np.mean(dev_ms)) * 1e-3), "scenarios_with_winner": n_win,
             "one_launch_chain_per_scenario": {"value": n_local / one_s, "ms_per_cycle_of_one_ranks_scenarios": 1e3 * one_s},
+            "timed_cycles": cycles, "closed_loop": closed,
+            "workload": "BASELINE configs[4]: %d independent seeded scenarios (%d per rank), default level-3 grid at N = 60"
+                        % (n_scenarios, n_scenarios // max(world, 1)),
             "note": "rp_batch_*: one H2D, four launches, one D2H per cycle of all scenarios; wall clock incl. host "
                     "staging of every scenario's inputs (host buffers) and D2H of every result"}
 
@@ -418,10 +470,14 @@ def main():
                     help="N > 1: the arg-min exchange of the sharded bundle -- stores into peer-mapped mailboxes over NVLink "
                          "(rp_peer_*) or an NCCL all-gather + all-reduce")
     ap.add_argument("--full-states", action="store_true", help="also time the full-state (HBM-heavy) variant")
-    ap.add_argument("--scenarios", type=int, default=64,
-                    help="independent scenarios PER RANK of the scenario-batch leg (BASELINE configs[4]: 512 per GPU)")
+    ap.add_argument("--scenarios", type=int, default=None,
+                    help="independent scenarios PER RANK of the scenario-batch leg (default: 512 at --gpus 8 = BASELINE "
+                         "configs[4]'s 4 096 scenarios, else 64)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    warmup_requested = args.warmup
+    if args.impl == "b200" and args.warmup < 3:
+        print("[bench] --warmup %d raised to 3 (timing rules: at least three warm-up steps)" % args.warmup, file=sys.stderr)
+        args.warmup = 3
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -449,11 +505,13 @@ def main():
     eng = make_engine(work, local_rank, stream.cuda_stream)
     inputs = make_inputs(work)
     n_total = work["n_cand"]
-    per_rank = (n_total + world - 1) // world
-    first = rank * per_rank
-    count = max(0, min(per_rank, n_total - first))
+    if args.scenarios is None:
+        args.scenarios = 512 if world == 8 else 64
+    # shards: the lon samples interleaved over the ranks (rank r: lon indices r, r + N, ...; every sampled t and d)
+    n_lon_r = len(range(rank, len(work["lon"]), world))
+    count = len(work["t"]) * n_lon_r * len(work["d"])
     if world > 1:
-        eng.set_candidate_range(first, count)
+        eng.set_candidate_stripe(rank, world)
     Np1 = N_HORIZON + 1
 
     from commonroad_rp_b200.parallel import PeerExchange, global_argmin
@@ -550,6 +608,7 @@ def main():
     total_ms = float(total_ms.item())
     res = eng.grid_result()
     main_kernel = eng.last_main_kernel()
+    launches_main = eng.launches_per_plan()
     exchange_check = None
     if peer is not None:
         # the peer-memory exchange against the NCCL one on the same bundle: identical winner / totals / count
@@ -623,7 +682,67 @@ def main():
         lazy_res = eng.grid_result()
         assert lazy_res.winner == res.winner and lazy_res.n_infeasible_collision == res.n_infeasible_collision
 
-    scen = scenario_batch_rate(local_rank, stream.cuda_stream, n_scenarios=args.scenarios, rank=rank, world=world)
+    # ---- strong scaling: the FIXED 64 x 64 x 32 bundle (BASELINE configs[3] itself) over the N ranks -----------------
+    strong = None
+    if world > 1:
+        work1 = dense_workload(1)
+        n1 = work1["n_cand"]
+        inputs1 = make_inputs(work1)
+        eng.grid_upload(inputs1, work1["t"], work1["lon"], work1["d"])
+
+        def timed_cycles(k_steps):
+            for _ in range(args.warmup):
+                step_device()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a0 = [torch.cuda.Event(enable_timing=True) for _ in range(k_steps)]
+            a1 = [torch.cuda.Event(enable_timing=True) for _ in range(k_steps)]
+            for k in range(k_steps):
+                flush.fill_(k & 0xFF)
+                a0[k].record(stream)
+                step_device()
+                a1[k].record(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            tot = torch.tensor([float(np.sum([x.elapsed_time(y) for x, y in zip(a0, a1)]))], dtype=torch.float64, device=dev)
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+            return float(tot.item()) / k_steps
+
+        eng.set_candidate_stripe(rank, world)
+        sharded_ms = timed_cycles(args.steps)
+        res_s = eng.grid_result()
+        kernel_s = eng.last_main_kernel()
+        # the same bundle unsharded on every rank (no exchange): the single-GPU time of this very run
+        eng.set_candidate_stripe(0, 1)
+        single_ms = []
+        for _ in range(args.warmup):
+            eng.grid_launch()
+        torch.cuda.synchronize()
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_a.record(stream)
+            eng.grid_launch()
+            e_b.record(stream)
+            torch.cuda.synchronize()
+            single_ms.append(e_a.elapsed_time(e_b))
+        res_1 = eng.grid_result()
+        assert (res_s.winner, res_s.n_infeasible_kinematics, res_s.n_infeasible_collision) == \
+            (res_1.winner, res_1.n_infeasible_kinematics, res_1.n_infeasible_collision)
+        from commonroad_rp_b200 import _lib as _l0
+        strong = {"workload": "dense sampling sweep 64 d x 64 v x 32 t, 60-step horizon: the FIXED bundle, lon samples interleaved "
+                              "over %d ranks (%d candidates per rank)" % (world, n1 // world),
+                  "ms_per_cycle": sharded_ms, "value": n1 / (sharded_ms * 1e-3), "unit": UNIT,
+                  "single_gpu_ms_per_cycle_same_run": float(np.mean(single_ms)),
+                  "speedup_vs_single_gpu": float(np.mean(single_ms)) / sharded_ms,
+                  "kernel": "candidate-major" if kernel_s == _l0.KERNEL_CANDIDATE_MAJOR else "step-parallel",
+                  "winner": int(res_s.winner),
+                  "note": "a shard of 131 072 / N candidates is one partial wave of warp marches (or one wave of the "
+                          "step-parallel kernel): the cycle is bound by one march / the launch chain, not by throughput"}
+        eng.set_candidate_stripe(rank, world)
+
+    scen = scenario_batch_rate(local_rank, stream.cuda_stream, n_scenarios=args.scenarios, rank=rank, world=world,
+                               cycles=20 if args.scenarios >= 256 else 10)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -641,8 +760,14 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
+        # the cycle's answer (the reference's own run of this bundle, tests/golden/big_dense_full.npz: winner 97084,
+        # 2 713 kinematic rejects, 8 179 colliders ranked before the winner -- at N = 1)
+        "winner": int(res.winner), "n_feasible": int(res.n_feasible),
+        "n_infeasible_kinematics": int(res.n_infeasible_kinematics), "n_infeasible_collision": int(res.n_infeasible_collision),
+        "n_collision_total": int(res.n_collision_total),
         "config": {"workload": "dense sampling sweep 64 d x %d v x 32 t, 60-step horizon (BASELINE configs[3]%s)"
-                               % (64 * n_gpus, "" if n_gpus == 1 else "; v grid scaled with N, bundle sharded t-major, arg-min exchange: " +
+                               % (64 * n_gpus, "" if n_gpus == 1 else "; v grid scaled with N, lon samples interleaved over the ranks "
+                                  "(rp_set_candidate_stripe), arg-min exchange: " +
                                   ("stores into peer-mapped mailboxes over NVLink (rp_peer_*)" if peer is not None else "NCCL")),
                    "candidates_per_cycle": n_total, "time_steps": Np1, "l2": "flushed between timed iterations (256 MiB fill)",
                    "mode": "select-only (winner states materialised), fmad off for parity"},
@@ -652,21 +777,25 @@ def main():
         "stage_ms": {"coeff": float(stage_ms[0]), "fused": float(stage_ms[1]), "argmin": float(stage_ms[2]),
                      "winner_states": float(stage_ms[3]),
                      "note": "second pass of the same K steps with the library's stage events on (ms_per_step_with_stage_events)"},
-        "winner": int(res.winner), "n_feasible": int(res.n_feasible),
+        "warmup_requested": warmup_requested,
+        "strong_scaling": strong,
         "exchange": None if world == 1 else {"kind": "peer" if peer is not None else "nccl", "equals_nccl": exchange_check},
         "e2e": {"value": n_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "rp_plan_grid + rp_fetch_states (host buffers)"},
         # NCCL exchange: record export, merge, count kernels of this library (+ NCCL's own two)
-        "gpu_launches": int((eng.launches_per_plan() + (3 if (world > 1 and peer is None) else 0)) * args.steps),
+        "gpu_launches": int((launches_main + (3 if (world > 1 and peer is None) else 0)) * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak if fp64_peak else None,
                      "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
                      "fp64_pipe_active_pct_ncu": ncu.get("fp64_pipe_active_pct"),
                      "kernel": kernel_name, "kernel_ms": fused_mean_ms,
-                     "peak_source": "DFMA micro-benchmark measured in this run (FMA = 2 flop); "
-                                    "algorithmic work = 200 flop per candidate-timestep (SURVEY 8d)",
+                     "peak_source": "DFMA micro-benchmark measured in this process right before the timed region (rp_measure_fp64_peak: "
+                                    "148 x 8 blocks x 256 threads x 8 independent chains x 20 000 FMA, best of 4 timed launches after "
+                                    "one warm-up, FMA = 2 flop; SM clock: `clocks`); MEASURED_PEAKS.json has no FP64 entry.  "
+                                    "Algorithmic work = 200 flop per candidate-timestep (SURVEY 8d)",
+                     "peak_samples": 4,
                      # the path multiplies and adds separately (--fmad=false: the reference's IEEE operation order decides
                      # flags bit-exactly), one flop per FP64 issue slot: the attainable ceiling is half the FMA peak
                      "frac_of_unfused_ceiling": 2.0 * achieved_tf / fp64_peak if fp64_peak else None,

@@ -83,6 +83,7 @@ SIGNATURES = {
     "rp_cycle_limits": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "rp_plan_list": (C.c_int, [C.c_void_p, C.POINTER(PlanInputs), C.c_int, _dp, _dp, _ip, _bp, C.POINTER(PlanResult)]),
     "rp_set_candidate_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "rp_set_candidate_stripe": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rp_ctx_set_kernel_policy": (C.c_int, [C.c_void_p, C.c_int]),
     "rp_export_record_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rp_count_colliders_before_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -411,6 +412,10 @@ class Engine:
 
     def set_candidate_range(self, first, count):
         self._check(self._lib.rp_set_candidate_range(self._ctx, int(first), int(count)))
+
+    def set_candidate_stripe(self, rank, world):
+        """lon-interleaved shard of a grid bundle (every rank gets the same mix of horizons); world <= 1 resets"""
+        self._check(self._lib.rp_set_candidate_stripe(self._ctx, int(rank), int(world)))
 
     def export_record_dev(self, dev_ptr):
         self._check(self._lib.rp_export_record_dev(self._ctx, C.c_void_p(int(dev_ptr))))

@@ -733,7 +733,8 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= P.n_groups) break;
         bool valid;
-        const int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
+        int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
+        if (P.stripe_world > 1) k = Stripe{P.stripe_rank, P.stripe_world, P.n_lon, P.n_d}.real(k);     // lon-interleaved shard
         cand_march<BLOCK, ONE_GROUP, 2, LATROWS, SLOTS>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }

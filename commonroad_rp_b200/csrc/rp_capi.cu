@@ -114,6 +114,7 @@ struct rp_ctx {
     rp_plan_inputs in{};
     int mode = 0, n_t = 0, n_lon = 0, n_d = 0, n_cand = 0;
     int range_first = 0, range_count = -1;
+    int stripe_rank = 0, stripe_world = 0;       // lon-interleaved shard (rp_set_candidate_stripe); world <= 1: off
     bool have_inputs = false, have_plan = false, states_all_valid = false;
     DevBuf d_samples;                   // t | lon | d (doubles) then traj_len (ints)
     DevBuf d_lon_coef, d_lat_coef, d_lat_tau, d_skip;
@@ -521,6 +522,24 @@ int cand_acc_rows(const rp_plan_inputs& in) {
     return 3 + ((!fs && in.has_desired_speed) ? 1 : 0) + ((!fs && in.has_desired_s) ? 1 : 0);
 }
 
+bool stripe_on(const rp_ctx* ctx) { return ctx->stripe_world > 1 && ctx->mode == 0; }
+int stripe_n_lon(const rp_ctx* ctx) { return (ctx->n_lon - ctx->stripe_rank + ctx->stripe_world - 1) / ctx->stripe_world; }
+rp::Stripe stripe_of(const rp_ctx* ctx) {
+    return stripe_on(ctx) ? rp::Stripe{ctx->stripe_rank, ctx->stripe_world, ctx->n_lon, ctx->n_d} : rp::Stripe{0, 0, 0, 0};
+}
+// the shard of the next launch: [first, first + count) in the launch's (virtual, for stripes) enumeration
+void shard_extent(const rp_ctx* ctx, int& first, int& count) {
+    const int n = ctx->n_cand;
+    first = 0;
+    count = n;
+    if (stripe_on(ctx)) {
+        count = ctx->n_t * std::max(0, stripe_n_lon(ctx)) * ctx->n_d;
+    } else if (ctx->range_count >= 0) {
+        first = std::min(ctx->range_first, n);
+        count = std::min(ctx->range_count, n - first);
+    }
+}
+
 // which kernel evaluates the main launch (the winner-state / on-demand launches always use fused_kernel)
 bool use_cand_kernel(const rp_ctx* ctx, int count) {
     constexpr int kCandMin = 24576;                    // AUTO: candidate-major from this many candidates up
@@ -582,6 +601,8 @@ void fill_common(rp_ctx* ctx, PlanParams& P, const Geometry& G, const rp::Segmen
     }
     P.lon_coef = ctx->d_lon_coef.as<double>();
     P.lat_coef = ctx->d_lat_coef.as<double>();
+    P.stripe_rank = 0;                         // (set by the main launch of a striped shard only)
+    P.stripe_world = 0;
 }
 
 int launch_fused(rp_ctx* ctx, const PlanParams& P, const Geometry& G) {
@@ -598,7 +619,7 @@ int prepare_main_geometry(rp_ctx* ctx, int first, int count) {
     const int Np1 = ctx->in.N + 1;
     std::vector<rp::Segment> segs;
     if (ctx->mode == 0) {
-        const int per_t = ctx->n_lon * ctx->n_d;
+        const int per_t = (stripe_on(ctx) ? std::max(0, stripe_n_lon(ctx)) : ctx->n_lon) * ctx->n_d;   // (virtual enumeration of a stripe)
         for (int it = 0; it < ctx->n_t && per_t > 0; ++it) {
             const int b = std::max(first, it * per_t), e = std::min(first + count, (it + 1) * per_t);
             if (b < e) segs.push_back(rp::Segment{b, e, ctx->h_traj_len[it], 0, 0, 0});
@@ -948,6 +969,19 @@ int rp_set_candidate_range(rp_ctx* ctx, int first, int count) {
     if (count >= 0 && first < 0) return fail(RP_ERR_ARG, "negative range start");
     ctx->range_first = count < 0 ? 0 : first;
     ctx->range_count = count;
+    ctx->stripe_world = 0;                     // a contiguous range replaces a stripe
+    ctx->stripe_rank = 0;
+    ctx->segs_dirty = true;
+    return RP_OK;
+}
+
+int rp_set_candidate_stripe(rp_ctx* ctx, int rank, int world) {
+    if (!ctx) return fail(RP_ERR_ARG, "null context");
+    if (world > 1 && (rank < 0 || rank >= world)) return fail(RP_ERR_ARG, "stripe rank out of range");
+    ctx->stripe_rank = world > 1 ? rank : 0;
+    ctx->stripe_world = world > 1 ? world : 0;
+    ctx->range_first = 0;
+    ctx->range_count = -1;
     ctx->segs_dirty = true;
     return RP_OK;
 }
@@ -1011,13 +1045,12 @@ static int launch_plan(rp_ctx* ctx) {
     const int Np1 = ctx->in.N + 1;
     const int n = ctx->n_cand;
     int first = 0, count = n;
-    if (ctx->range_count >= 0) {
-        first = std::min(ctx->range_first, n);
-        count = std::min(ctx->range_count, n - first);
-    }
+    shard_extent(ctx, first, count);
+    const bool sharded = ctx->range_count >= 0 || stripe_on(ctx);
+    const rp::Stripe sm = stripe_of(ctx);
     // every argument check comes before the first kernel of the chain: a rank that fails here has enqueued nothing
     // and has not advanced the peer epoch
-    if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision && ctx->range_count >= 0)
+    if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision && sharded)
         return fail(RP_ERR_ARG, "continuous collision check is not available for sharded bundles");
     if (int rc = ctx->d_cost.ensure((size_t)std::max(n, 1) * sizeof(double))) return rc;
     if (int rc = ctx->d_info.ensure((size_t)std::max(n, 1) * sizeof(int))) return rc;
@@ -1035,9 +1068,9 @@ static int launch_plan(rp_ctx* ctx) {
     // replanning-size bundles: the main launch writes the states of every kept candidate (a few MB at most) and ONE
     // block selects the winner and gathers its states -- 3 launches per cycle instead of 6
     // sharded bundle with an open peer group: the selection chain ends with the exchange over peer-mapped memory
-    const bool peer_mode = ctx->peer_ready && ctx->range_count >= 0;
+    const bool peer_mode = ctx->peer_ready && sharded;
     ctx->peer_mode_last = peer_mode;
-    const bool small_path = !peer_mode && count > 0 && (long long)n * Np1 <= 262144 && !use_cand_kernel(ctx, count);
+    const bool small_path = !peer_mode && !stripe_on(ctx) && count > 0 && (long long)n * Np1 <= 262144 && !use_cand_kernel(ctx, count);
     ctx->small_path_last = small_path;
     if (small_path && !ctx->in.want_all_states) {
         if (int rc = ctx->d_states_all.ensure((size_t)n * 14 * Np1 * sizeof(double))) return rc;
@@ -1105,6 +1138,8 @@ static int launch_plan(rp_ctx* ctx) {
         P.info = ctx->d_info.as<int>();
         P.states = (ctx->in.want_all_states || small_path) ? ctx->d_states_all.as<double>() : nullptr;
         P.states_by_slot = 0;
+        P.stripe_rank = sm.rank;
+        P.stripe_world = sm.world;
         if (ctx->in.check_collision == 2) {
             if (int rc = ctx->d_best.ensure(sizeof(unsigned long long))) return rc;
             if (!dyn_rows_done)             // (the prep launch of the grid form resets the per-cycle scratch words)
@@ -1143,15 +1178,15 @@ static int launch_plan(rp_ctx* ctx) {
         rp::ArgminScratch* sc = ctx->d_argmin.as<rp::ArgminScratch>();
         if (!dyn_rows_done) RP_CUDA(cudaMemsetAsync(sc, 0, sizeof(int) * 16, ctx->stream));
         const int nb = std::max(1, std::min(512, std::min(2 * ctx->num_sms, (count + 255) / 256)));
-        rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc);
+        rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc, sm);
         rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres);
         if (peer_mode) {
             const unsigned long long epoch = ++ctx->peer_epoch;
             rp::peer_merge_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_table, epoch, dres);
             rp::peer_count_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->peer_table, epoch, ctx->d_cost.as<double>(), ctx->d_info.as<int>(),
-                                                               first, count, dres);
+                                                               first, count, dres, sm);
         } else {
-            rp::count_before_result_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, dres);
+            rp::count_before_result_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, dres, sm);
         }
     }
     RP_CUDA(cudaGetLastError());
@@ -1290,7 +1325,7 @@ int rp_plan_levels(rp_ctx* ctx, const rp_plan_inputs* in, int n_levels, const in
     if (int rc = check_inputs(in)) return rc;
     if (n_levels < 1 || n_levels > rp::kMaxLevels) return fail(RP_ERR_ARG, "rp_plan_levels: 1 .. 4 levels");
     if (!n_t || !n_lon || !n_d || !t_cat || !traj_len_cat || !lon_cat || !d_cat || !out) return fail(RP_ERR_ARG, "null array");
-    if (ctx->range_count >= 0) return fail(RP_ERR_ARG, "rp_plan_levels does not shard (reset rp_set_candidate_range)");
+    if (ctx->range_count >= 0 || ctx->stripe_world > 1) return fail(RP_ERR_ARG, "rp_plan_levels does not shard (reset rp_set_candidate_range)");
     if (in->continuous_collision_check) return fail(RP_ERR_ARG, "rp_plan_levels does not run the continuous collision check");
     if (in->cost_kind == RP_COST_NONE && n_levels > 1)
         return fail(RP_ERR_ARG, "rp_plan_levels: without a device cost the host selects, one level at a time");
@@ -1777,16 +1812,12 @@ int rp_count_colliders_before_dev(rp_ctx* ctx, const double* dev_winner2, double
     if (int rc = bind(ctx)) return rc;
     if (!dev_winner2 || !dev_out1) return fail(RP_ERR_ARG, "null device pointer");
     if (!ctx->have_plan) return fail(RP_ERR_STATE, "no plan launched");
-    const int n = ctx->n_cand;
-    int first = 0, count = n;
-    if (ctx->range_count >= 0) {
-        first = std::min(ctx->range_first, n);
-        count = std::min(ctx->range_count, n - first);
-    }
+    int first = 0, count = 0;
+    shard_extent(ctx, first, count);
     RP_CUDA(cudaMemsetAsync(dev_out1, 0, sizeof(double), ctx->stream));
     const int blocks = std::max(1, std::min(ctx->num_sms, (count + 255) / 256));
     rp::count_before_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first,
-                                                              count, dev_winner2, dev_out1);
+                                                              count, dev_winner2, dev_out1, stripe_of(ctx));
     RP_CUDA(cudaGetLastError());
     return RP_OK;
 }

@@ -102,8 +102,27 @@ struct PlanParams {
     int* work_counter;           // chunk dispenser (zeroed before the launch)
     int n_acc_rows;              // np.sum accumulator rows kept in shared memory
     const float4* dyn_rows;      // [Np1][n_dyn] single-precision circles of the launch's time window (null: none staged)
+    // lon-interleaved shard of a grid bundle (rp_set_candidate_stripe; world <= 1: off): the launch enumerates the shard's
+    // candidates compactly ("virtual" index) and stripe_to_real() maps them into the bundle's enumeration space
+    int stripe_rank, stripe_world;
     const double* lat_rows;      // [n_t][Np1][n_d][4] = d, d_dot (clamped), d_ddot, - of the lateral polynomials on the time
                                  // grid (high-velocity grid bundles: shared by all lon samples; null: evaluated per candidate)
+};
+
+// Multi-GPU shards that are ALIKE instead of contiguous: rank r of `world` owns the lon samples il = r, r + world, ... of
+// EVERY sampled t, so all ranks see the same mix of traj_len (contiguous t-major tiles differ in it and the exchange waits
+// for the slowest rank).  Virtual index kv = (it * n_lon_r + jl) * n_d + id, il = rank + jl * world.
+struct Stripe {
+    int rank, world, n_lon, n_d;
+    __device__ __forceinline__ int real(int kv) const {
+        if (world <= 1) return kv;
+        const int n_lon_r = (n_lon - rank + world - 1) / world;
+        const int per_t_r = n_lon_r * n_d;
+        const int it = kv / per_t_r;
+        const int rem = kv - it * per_t_r;
+        const int jl = rem / n_d;
+        return (it * n_lon + rank + jl * world) * n_d + (rem - jl * n_d);
+    }
 };
 
 __device__ __forceinline__ int pack_info(int status, int reason, int step) {
@@ -234,7 +253,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const ARGS* __re
         bool valid = lane && slot < seg.k_end;
         int k = -1;
         if (valid) {
-            k = P.index ? P.index[slot] : slot;
+            k = P.index ? P.index[slot] : (P.stripe_world > 1 ? Stripe{P.stripe_rank, P.stripe_world, P.n_lon, P.n_d}.real(slot) : slot);
             if (k < 0 || k >= P.n_cand) valid = false;
         }
         double* const scratch = slots + (size_t)(lane ? c : 0) * per_slot;

@@ -202,7 +202,7 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 __global__ void __launch_bounds__(256) argmin_partial_kernel(const double* __restrict__ cost, const int* __restrict__ info,
-                                                             int first, int count, ArgminScratch* sc) {
+                                                             int first, int count, ArgminScratch* sc, Stripe sm) {
     __shared__ double w_cost[8];
     __shared__ int w_idx[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) argmin_partial_kernel(const double* __res
     int l_feas = 0, l_colt = 0, l_filt = 0;
     int l_reason[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int q = blockIdx.x * blockDim.x + tid; q < count; q += gridDim.x * blockDim.x) {
-        const int k = first + q;
+        const int k = sm.real(first + q);
         const int w = info[k];
         const int st = w & 0xFF;
         if (st == ST_FEASIBLE) {
@@ -286,14 +286,14 @@ __global__ void __launch_bounds__(512) argmin_merge_kernel(const ArgminScratch* 
 // colliders ranked before the winner (all colliders when there is no winner)
 __global__ void __launch_bounds__(256) count_before_result_kernel(const double* __restrict__ cost,
                                                                   const int* __restrict__ info, int first, int count,
-                                                                  PlanResultDev* out) {
+                                                                  PlanResultDev* out, Stripe sm) {
     if (out->r.n_collision_total == 0) return;
     const int wi = out->r.winner;
     const double wc = out->r.winner_cost;
     const bool none = wi < 0;
     int local = 0;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
-        const int k = first + q;
+        const int k = sm.real(first + q);
         if ((info[k] & 0xFF) == ST_COLLISION) {
             if (none || lex_less(cost[k], k, wc, wi)) ++local;
         }
@@ -588,7 +588,7 @@ __global__ void merge_records_kernel(const double* __restrict__ gathered, int wo
 // colliders of this shard ranked before the GLOBAL winner (lazy collision count, App. B#12)
 __global__ void __launch_bounds__(256) count_before_kernel(const double* __restrict__ cost, const int* __restrict__ info,
                                                            int first, int count, const double* __restrict__ winner,
-                                                           double* __restrict__ out) {
+                                                           double* __restrict__ out, Stripe sm) {
     __shared__ int total;
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(256) count_before_kernel(const double* __restr
     const bool none = !(wi < __longlong_as_double(0x7ff0000000000000LL));
     int local = 0;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
-        const int k = first + q;
+        const int k = sm.real(first + q);
         if ((info[k] & 0xFF) == ST_COLLISION) {
             const double c = cost[k];
             if (none || c < wc || (c == wc && (double)k < wi)) ++local;
@@ -849,7 +849,7 @@ __global__ void __launch_bounds__(32) peer_merge_kernel(const __grid_constant__ 
 
 __global__ void __launch_bounds__(256) peer_count_kernel(const __grid_constant__ PeerTable T, unsigned long long epoch,
                                                          const double* __restrict__ cost, const int* __restrict__ info,
-                                                         int first, int count, PlanResultDev* res) {
+                                                         int first, int count, PlanResultDev* res, Stripe sm) {
     __shared__ int total;
     __shared__ unsigned int s_ticket;
     PeerMailbox* const mine = T.box[T.rank];
@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(256) peer_count_kernel(const __grid_constant__
     const bool none = wi < 0;
     int local = 0;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
-        const int k = first + q;
+        const int k = sm.real(first + q);
         if ((info[k] & 0xFF) == ST_COLLISION) {
             if (none || lex_less(cost[k], k, wc, wi)) ++local;
         }

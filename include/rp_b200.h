@@ -230,6 +230,13 @@ int rp_plan_list(rp_ctx* ctx, const rp_plan_inputs* in, int n_cand, const double
  * rp_grid_launch / rp_plan_grid.  count < 0 resets to the whole bundle. */
 int rp_set_candidate_range(rp_ctx* ctx, int first, int count);
 
+/* Shard `rank` of `world` of a GRID bundle by interleaving the lon samples: the rank owns lon indices rank, rank + world,
+ * ... of every sampled t (and all d), so every rank's shard has the same mix of horizons (contiguous t-major tiles
+ * differ in traj_len and the exchange waits for the slowest).  Replaces a candidate range and vice versa; world <= 1
+ * resets to the whole bundle.  Results, counters and the peer exchange work as for ranges; winner indices are the
+ * bundle's enumeration indices. */
+int rp_set_candidate_stripe(rp_ctx* ctx, int rank, int world);
+
 /* Multi-GPU arg-min plumbing for sharded bundles (device pointers, asynchronous on the context's stream):
  * rp_export_record_dev writes [best cost (+inf if none), best enumeration index as double (+inf if none),
  * n_infeasible_kinematics, n_feasible] of this rank's shard to dev_dst4 for an NCCL all-gather;

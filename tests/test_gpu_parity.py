@@ -371,3 +371,43 @@ def test_cycle_launch_escalates_to_the_level_that_has_a_winner():
     assert [records[j].n_candidates for j in range(3)] == [len(t) * len(lon) * len(d) for t, lon, d in grids]
     eng.close()
     eng2.close()
+
+
+@pytest.mark.parametrize("kernel", ["candidate_major", "step_parallel"])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_lon_interleaved_shards_merge_to_the_unsharded_result(kernel, world):
+    """rp_set_candidate_stripe: rank r owns the lon samples r, r + world, ... of every sampled t (shards with the same mix
+    of horizons); the shards' verdicts are those of the unsharded bundle and merge to the same winner / counters"""
+    from commonroad_rp_b200 import _lib
+    prob = _bundle(seed=3, level=3, N=30, s_dot0=11.0)
+    eng = H.engine_for(prob)
+    eng.set_kernel_policy(_lib.KERNEL_CANDIDATE_MAJOR if kernel == "candidate_major" else _lib.KERNEL_STEP_PARALLEL)
+    inputs = H.inputs_for(prob, check_collision=_lib.COLLISION_ALL)
+    full = eng.plan_grid(inputs, prob["t"], prob["lon"], prob["d"])
+    cost_f, status_f, reason_f, step_f = eng.fetch_candidates()
+    n_t, n_lon, n_d = len(prob["t"]), len(prob["lon"]), len(prob["d"])
+    seen = np.zeros(full.n_candidates, dtype=int)
+    recs = []
+    for rank in range(world):
+        eng.set_candidate_stripe(rank, world)
+        r = eng.plan_grid(inputs, prob["t"], prob["lon"], prob["d"])
+        cost, status, reason, step = eng.fetch_candidates()
+        own = np.zeros((n_t, n_lon, n_d), dtype=bool)
+        own[:, rank::world, :] = True
+        own = own.ravel()
+        assert r.n_candidates == int(own.sum())
+        assert np.array_equal(status[own], status_f[own]) and np.array_equal(step[own], step_f[own])
+        assert np.array_equal(cost[own].view(np.int64), cost_f[own].view(np.int64))
+        assert r.winner < 0 or own[r.winner]
+        seen += own
+        recs.append(r)
+    assert np.all(seen == 1)
+    eng.set_candidate_stripe(0, 1)
+    best = min((r for r in recs if r.winner >= 0), key=lambda r: (r.winner_cost, r.winner))
+    assert best.winner == full.winner and best.winner_cost == full.winner_cost
+    assert sum(r.n_infeasible_kinematics for r in recs) == full.n_infeasible_kinematics
+    assert sum(r.n_collision_total for r in recs) == full.n_collision_total
+    assert sum(r.n_feasible for r in recs) == full.n_feasible
+    again = eng.plan_grid(inputs, prob["t"], prob["lon"], prob["d"])
+    assert again.winner == full.winner and again.n_candidates == full.n_candidates
+    eng.close()

@@ -69,8 +69,11 @@ def _worker(rank, world, port, n_dev, kernel, out_q):
     ex = PeerExchange(eng)
     got = []
     for cycle in range(3):
-        first, count = shard_range(n, (rank + cycle) % world, world)     # the shards change hands between cycles
-        eng.set_candidate_range(first, count)
+        if cycle == 2:
+            eng.set_candidate_stripe((rank + cycle) % world, world)          # lon-interleaved shards instead of t-major tiles
+        else:
+            first, count = shard_range(n, (rank + cycle) % world, world)     # the shards change hands between cycles
+            eng.set_candidate_range(first, count)
         r = eng.plan_grid(H.inputs_for(prob, check_collision=_lib.COLLISION_ALL), prob["t"], prob["lon"], prob["d"])
         got.append((_as_tuple(r), eng.fetch_states(r.winner)))
     out_q.put((rank, got))
