@@ -152,7 +152,8 @@ struct rp_ctx {
     rp::PeerMailbox* peer_mine = nullptr;           // cudaMalloc'ed, exported through CUDA IPC
     void* peer_opened[rp::kMaxPeers] = {};          // the other ranks' mailboxes (cudaIpcOpenMemHandle)
     rp::PeerTable peer_table{};
-    bool peer_ready = false, peer_mode_last = false;
+    bool peer_ready = false, peer_mode_last = false, peer_table_dirty = true;
+    DevBuf d_peer_table;                            // the table in device memory (read by the merge block)
     unsigned long long peer_epoch = 0;
 
     // one replanning cycle in one launch (rp_plan_levels)
@@ -799,7 +800,7 @@ int rp_ctx_destroy(rp_ctx* ctx) {
                       &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best,
                       &ctx->d_work, &ctx->d_clr, &ctx->d_dyn_rows, &ctx->d_lat_rows})
         b->release();
-    for (DevBuf* b : {&ctx->d_cycle_res, &ctx->d_ticket, &ctx->d_best4}) b->release();
+    for (DevBuf* b : {&ctx->d_cycle_res, &ctx->d_ticket, &ctx->d_best4, &ctx->d_peer_table}) b->release();
     if (ctx->h_cycle) cudaFreeHost(ctx->h_cycle);
     ctx->h_stage.release();
     ctx->h_result.release();
@@ -1179,13 +1180,19 @@ static int launch_plan(rp_ctx* ctx) {
         if (!dyn_rows_done) RP_CUDA(cudaMemsetAsync(sc, 0, sizeof(int) * 16, ctx->stream));
         const int nb = std::max(1, std::min(512, std::min(2 * ctx->num_sms, (count + 255) / 256)));
         rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc, sm);
-        rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres);
         if (peer_mode) {
+            // the shard's merge block goes straight on to the exchange of the shard records (no separate launch)
             const unsigned long long epoch = ++ctx->peer_epoch;
-            rp::peer_merge_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_table, epoch, dres);
+            if (int rc = ctx->d_peer_table.ensure(sizeof(rp::PeerTable))) return rc;
+            if (ctx->peer_table_dirty) {
+                RP_CUDA(cudaMemcpyAsync(ctx->d_peer_table.p, &ctx->peer_table, sizeof(rp::PeerTable), cudaMemcpyHostToDevice, ctx->stream));
+                ctx->peer_table_dirty = false;
+            }
+            rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres, ctx->d_peer_table.as<rp::PeerTable>(), epoch);
             rp::peer_count_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->peer_table, epoch, ctx->d_cost.as<double>(), ctx->d_info.as<int>(),
                                                                first, count, dres, sm);
         } else {
+            rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres);
             rp::count_before_result_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, dres, sm);
         }
     }
@@ -1860,6 +1867,7 @@ int rp_peer_open(rp_ctx* ctx, int rank, int world, const unsigned char* handles)
         ctx->peer_table.box[r] = static_cast<rp::PeerMailbox*>(p);
     }
     ctx->peer_ready = true;
+    ctx->peer_table_dirty = true;
     return RP_OK;
 }
 
@@ -1885,8 +1893,8 @@ int rp_launches_per_plan(rp_ctx* ctx) {
     // coeff, fused, argmin partial / merge / count, winner states (+ the dynamic-obstacle rows of the candidate-major kernel)
     if (ctx->cycle_valid) return 1;                               // rp_plan_levels: the whole cycle is one kernel
     if (ctx->small_path_last) return ctx->mode == 0 ? 3 : 2;      // coeff, fused (states of every kept candidate), select
-    if (ctx->peer_mode_last)        // prep, main kernel, argmin partial / merge, peer merge / count, winner states
-        return ctx->mode == 0 ? 7 : 6 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
+    if (ctx->peer_mode_last)        // prep, main kernel, argmin partial / merge + record exchange, peer count, winner states
+        return ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
     // prep (coefficients + dynamic-obstacle rows), main kernel, argmin partial / merge / count, winner states; the list
     // form has no coefficient solve but, for the candidate-major kernel, its own dynamic-obstacle rows launch
     return ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);

@@ -253,8 +253,14 @@ __global__ void __launch_bounds__(256) argmin_partial_kernel(const double* __res
     }
 }
 
+struct PeerTable;
+__device__ __forceinline__ void peer_merge_warp(const PeerTable& T, unsigned long long epoch, PlanResultDev* res);
+
+// peer != nullptr (sharded bundle with an open peer group): the block's first warp goes straight on to the exchange of
+// the shard records (peer_merge_warp) -- one launch fewer per cycle than a separate exchange kernel
 __global__ void __launch_bounds__(512) argmin_merge_kernel(const ArgminScratch* __restrict__ sc, int n_part, int count,
-                                                           PlanResultDev* out) {
+                                                           PlanResultDev* out, const PeerTable* __restrict__ peer = nullptr,
+                                                           unsigned long long epoch = 0ULL) {
     __shared__ double w_cost[16];
     __shared__ int w_idx[16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -279,6 +285,10 @@ __global__ void __launch_bounds__(512) argmin_merge_kernel(const ArgminScratch* 
             r.n_collision_total = sc->counts[2];
             for (int z = 0; z < 8; ++z) r.reason_counts[z] = sc->counts[8 + z];
             out->n_filtered = sc->counts[3];
+        }
+        if (peer != nullptr) {
+            __syncwarp();
+            peer_merge_warp(*peer, epoch, out);
         }
     }
 }
@@ -779,10 +789,9 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(32) peer_merge_kernel(const __grid_constant__ PeerTable T, unsigned long long epoch,
-                                                        PlanResultDev* __restrict__ res) {
+__device__ __forceinline__ void peer_merge_warp(const PeerTable& T, unsigned long long epoch, PlanResultDev* res) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    const int lane = threadIdx.x, par = (int)(epoch & 1ULL);
+    const int lane = threadIdx.x & 31, par = (int)(epoch & 1ULL);
     PeerMailbox* const mine = T.box[T.rank];
     if (lane == 0) { mine->local_count = 0; mine->ticket = 0u; res->peer_error = 0; }
     bool ok = true;
@@ -845,6 +854,11 @@ __global__ void __launch_bounds__(32) peer_merge_kernel(const __grid_constant__ 
         for (int z = 0; z < 8; ++z) r.reason_counts[z] = (int)sums[5 + z];
         r.n_infeasible_collision = 0;                  // filled by peer_count_kernel
     }
+}
+
+__global__ void __launch_bounds__(32) peer_merge_kernel(const __grid_constant__ PeerTable T, unsigned long long epoch,
+                                                        PlanResultDev* __restrict__ res) {
+    peer_merge_warp(T, epoch, res);
 }
 
 __global__ void __launch_bounds__(256) peer_count_kernel(const __grid_constant__ PeerTable T, unsigned long long epoch,
