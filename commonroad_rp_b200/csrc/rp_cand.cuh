@@ -291,7 +291,7 @@ __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables
     double th_cl, th_gl, cosT, kappa, v, a;
     // ---- orientation (:842-873), curvature, velocity, acceleration (:876-896) ----------------------------------------
     if (!carry) {
-        th_cl = atan(dp);                                       // np.arctan2(dp, 1.0)
+        th_cl = rp_atan(dp);                                       // np.arctan2(dp, 1.0)
         th_gl = th_cl + th_ref;
         motion_moving(D, dp, dpp, d, k_r, k_r_d, sv, sa, cosT, kappa, v, a);
         heading_cos_sin(cosT, dp, L.c_ref, L.s_ref, o.cn, o.sn);

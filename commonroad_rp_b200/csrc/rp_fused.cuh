@@ -395,7 +395,7 @@ __device__ __forceinline__ void fused_body(const PlanParams& P, const ARGS* __re
             th_ref = interpolate_angle(s, p0, p1, R.theta[j0], R.theta[j1]);
             carry = !(sv > 0.001) && !low_vel;
             if (!carry) {
-                th_cl = atan(dp);                                // np.arctan2(dp, 1.0)
+                th_cl = rp_atan(dp);                                // np.arctan2(dp, 1.0)
                 th_gl = th_cl + th_ref;
                 s_th[i] = th_gl;
             }
