@@ -240,9 +240,9 @@ __device__ __forceinline__ StepOut lat_part(const PlanParams& P, const RefTables
     const double s = L.s, sv = L.sv, sa = L.sa;
     double d, dv, da;
     if (LATROWS) {
-        const double2* r = reinterpret_cast<const double2*>(cd_ptr);          // (the caller passes the table entry)
-        const double2 u = __ldg(r), w = __ldg(r + 1);
-        d = u.x; dv = u.y; da = w.x;
+        // (the caller passes a pointer to the step's three values: the table entry itself, or a copy it fetched one
+        // step ahead -- the table lives in L2, and the march would wait for it at the head of every step otherwise)
+        d = cd_ptr[0]; dv = cd_ptr[1]; da = cd_ptr[2];
     } else {
     double cd[6];
     {
@@ -506,6 +506,12 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     double cn = 1., sn = 0.;                       // cos / sin of th_gl
     double ax = 0., ay = 0.;                       // np.cumsum of the extension increments
 
+    double lat_next[3] = {0., 0., 0.};             // LATROWS: the lateral values of the NEXT polynomial step
+    if (LATROWS && tl > 0) {
+        const double2* r = reinterpret_cast<const double2*>(I.lr);
+        const double2 u = __ldg(r), w = __ldg(r + 1);
+        lat_next[0] = u.x; lat_next[1] = u.y; lat_next[2] = w.x;
+    }
     for (int i = 0; i < Np1; ++i) {
         double px, py;                             // rear-axle position of this step
         unsigned heavy_dynmask = 0xffffffffu;      // polynomial steps: the obstacles that can reach this step's lateral line
@@ -540,7 +546,13 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             L.ny = c[11 * SLOTS]; L.c_ref = c[12 * SLOTS]; L.s_ref = c[13 * SLOTS];
             L.flags = rflags[item];
             heavy_dynmask = rflags[SLOTS + item];
-            StepOut o = lat_part<false, LATROWS>(P, R, Y, L, LATROWS ? I.lr + (size_t)i * I.lr_stride : I.cd, cs0, th_gl, kappa, i);
+            double lat_now[3] = {lat_next[0], lat_next[1], lat_next[2]};
+            if (LATROWS && i + 1 < tl) {                       // next step's lateral values: in flight during this step
+                const double2* r = reinterpret_cast<const double2*>(I.lr + (size_t)(i + 1) * I.lr_stride);
+                const double2 u = __ldg(r), w = __ldg(r + 1);
+                lat_next[0] = u.x; lat_next[1] = u.y; lat_next[2] = w.x;
+            }
+            StepOut o = lat_part<false, LATROWS>(P, R, Y, L, LATROWS ? lat_now : I.cd, cs0, th_gl, kappa, i);
             if (o.reject & 0x80000000u) o = poly_step_exact<LATROWS>(P, R, Y, I);
             pre |= o.pre;
             if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
