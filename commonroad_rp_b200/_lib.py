@@ -323,20 +323,31 @@ class Engine:
             b["refs"] = (C.byref(b["n_eval"]), C.byref(b["chosen"]))
         n, bt, bl, bd, btl = b["n"], b["t"], b["lon"], b["d"], b["tl"]
         ot = ol = od = 0
-        counts = []
+        counts, seen = [], []
+        last = b.get("last", ())
         for j, (t, lon, d, tl) in enumerate(levels):
             nt, nl, nd = len(t), len(lon), len(d)
-            n[0, j] = nt
-            n[1, j] = nl
-            n[2, j] = nd
-            bt[ot:ot + nt] = t
-            btl[ot:ot + nt] = tl
-            bl[ol:ol + nl] = lon
+            # the sampled horizons / lon samples of a level are usually the very same (cached) arrays as in the last cycle
+            # at the same place of the staging buffers: copied again only when they are not
+            prev = last[j] if j < len(last) else None
+            if prev is not None and (t.flags.writeable or tl.flags.writeable or lon.flags.writeable):
+                prev = None                  # (only read-only arrays -- the sampling caches -- are trusted to be unchanged)
+            if prev is None or prev[0] is not t or prev[1] is not tl or prev[4] != ot:
+                bt[ot:ot + nt] = t
+                btl[ot:ot + nt] = tl
+                n[0, j] = nt
+            if prev is None or prev[2] is not lon or prev[5] != ol:
+                bl[ol:ol + nl] = lon
+                n[1, j] = nl
             bd[od:od + nd] = d
+            if prev is None or prev[3] != nd:
+                n[2, j] = nd
+            counts.append(nt * nl * nd)
+            seen.append((t, tl, lon, nd, ot, ol))
             ot += nt
             ol += nl
             od += nd
-            counts.append(nt * nl * nd)
+        b["last"] = seen
         self._N = inputs.N
         self.plan_generation += 1
         rc = self._lib.rp_plan_levels(self._ctx, C.byref(inputs), len(levels), *b["ptr"], b["res"], *b["refs"])

@@ -25,5 +25,25 @@ def build_library(force=False, verbose=False):
     return OUT
 
 
+PACK_SRC = os.path.join(HERE, "csrc", "rp_pack.c")
+
+
+def pack_module_path():
+    import sysconfig
+    return os.path.join(HERE, "_rp_pack" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pack_module(force=False):
+    """The CPython helper for plan()'s output packing (csrc/rp_pack.c); host glue, optional at run time."""
+    import sysconfig
+    out = pack_module_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(PACK_SRC):
+        return out
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", out, PACK_SRC, "-lm"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
+    print(build_pack_module(force=True))

@@ -71,6 +71,11 @@ class _LazyViews(collections.abc.Sequence):
 
 logger = logging.getLogger("RP_LOGGER")
 
+try:        # CPython helper for the output packing (csrc/rp_pack.c, built by build.py); the Python loop below is the fallback
+    from commonroad_rp_b200 import _rp_pack
+except ImportError:
+    _rp_pack = None
+
 _EPS = 1e-5
 _TWO_PI = 2.0 * math.pi
 
@@ -598,7 +603,9 @@ class ReactivePlanner(object):
         if hit is None or hit[0] is not t or hit[1] != dt:
             if len(cls._traj_len_cache) > 256:
                 cls._traj_len_cache.clear()
-            hit = cls._traj_len_cache[id(t)] = (t, dt, np.array([_lib.traj_len_of(x, dt) for x in t], dtype=np.int32))
+            tl = np.array([_lib.traj_len_of(x, dt) for x in t], dtype=np.int32)
+            tl.flags.writeable = False
+            hit = cls._traj_len_cache[id(t)] = (t, dt, tl)
         return hit[2]
 
     def _get_optimal_trajectory(self, trajectory_bundle: TrajectoryBundle) -> Union[TrajectorySample, None]:
@@ -751,6 +758,20 @@ class ReactivePlanner(object):
         ca, cu = trajectory.cartesian, trajectory.curvilinear
         factor = self.config.planning.factor
         x_0 = self.x_0
+        device_block = getattr(trajectory, "_rows_untouched", None) is not None and trajectory._rows_untouched()
+        if device_block and _rp_pack is not None and not HAVE_COMMONROAD_IO:
+            # the whole packing in one C call (csrc/rp_pack.c): state objects, steering angles, yaw rates, orientation
+            # shift, the two curvilinear lists -- the same per-state arithmetic as the reference's loop (:520-556)
+            block = trajectory._state_block[0]
+            t0 = x_0.time_step
+            cart_list, lon_list, lat_list = _rp_pack.pack(ReactivePlannerState, block, list(np.ascontiguousarray(block[0:2].T)),
+                                                          int(t0), int(factor), float(self.dt), float(self.vehicle_params.wheelbase),
+                                                          float(x_0.yaw_rate), x_0.orientation - math.pi, x_0.orientation + math.pi)
+            pos_curv = block[7:9].T
+            rows = block[2:6]
+            curv_traj = _LazyTrajectory(t0, lambda: _curvilinear_states(t0, factor, np.ascontiguousarray(pos_curv), rows[1].tolist(),
+                                                                        rows[2].tolist(), rows[0].tolist(), rows[3].tolist()))
+            return Trajectory(t0, cart_list), curv_traj, lon_list, lat_list
         n = len(ca.x)
         theta = ca.theta
         steering = np.arctan2(self.vehicle_params.wheelbase * ca.kappa, 1.0)
@@ -759,7 +780,7 @@ class ReactivePlanner(object):
         yaw_rate[0] = x_0.yaw_rate
         yaw_rate[1:] = (theta[1:] - theta[:-1]) / self.dt
         t0 = x_0.time_step
-        if getattr(trajectory, "_rows_untouched", None) is not None and trajectory._rows_untouched():
+        if device_block:
             # device result: the 14 rows are views of one block -- one transpose / tolist per group instead of one per row
             block = trajectory._state_block[0]
             rows = block.tolist()

@@ -160,7 +160,9 @@ class FixedIntervalSampling(SamplingSpace):
         cache = self.__dict__.setdefault("_order_cache", {})
         hit = cache.get(key)
         if hit is None or hit[0] is not sample_set or hit[2] != len(sample_set):
-            hit = cache[key] = (sample_set, np.fromiter(sample_set, dtype=np.float64), len(sample_set))
+            arr = np.fromiter(sample_set, dtype=np.float64)
+            arr.flags.writeable = False
+            hit = cache[key] = (sample_set, arr, len(sample_set))
         return hit[1]
 
     def generate_trajectories_at_level(self, level_sampling: int, x_0_lon: np.ndarray, x_0_lat: np.ndarray,

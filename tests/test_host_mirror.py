@@ -339,3 +339,45 @@ def test_interval_corridor_reach_operations():
         cs.driving_corridor = {0: object()}                      # ... a commonroad_reach corridor does
     cs.driving_corridor = IntervalCorridor({k: nodes for k in range(0, 25)})
     assert cs._velocity_constraints[3] == [3.0, 9.5]
+
+
+def test_c_output_packing_equals_python_packing():
+    """csrc/rp_pack.c (one C call for plan()'s output packing, reference :514-568) against the Python loop it replaces:
+    identical state lists incl. the orientation shift, steering angles, yaw rates, time steps, the lazy curvilinear list"""
+    import json
+    from commonroad_rp_b200 import build, reactive_planner as RP
+    from commonroad_rp_b200.trajectories import DeviceTrajectorySample
+    from tests import golden_io, helpers as H
+    build.build_pack_module()
+    import importlib
+    pack = importlib.import_module("commonroad_rp_b200._rp_pack")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "plan_free.npz"))
+    prob = golden_io.unpack_problem(z)
+    meta = json.loads(str(z["plan_meta"]))
+    planner = H.planner_from_fixture(prob, z["ref_path_raw"], z["x0"], desired_velocity=meta["desired_velocity"])
+    n = z["out_cart"].shape[1]
+
+    def sample():
+        blk = np.vstack([z["out_cart"][[0, 1, 2, 3, 4]], np.zeros((2, n)), z["out_lon"].T[0:1], z["out_lat"].T[0:1], np.zeros((1, n)),
+                         z["out_lon"].T[1:3], z["out_lat"].T[1:3]])
+        blk[5] = np.tan(z["out_cart"][6]) / planner.vehicle_params.wheelbase
+        blk[2, 5:9] += 2 * np.pi                                   # exercise the orientation shift
+        ts = DeviceTrajectorySample(planner.horizon, planner.dt, lambda: (None, None))
+        ts._set_states(np.ascontiguousarray(blk))
+        return ts
+
+    saved = RP._rp_pack
+    try:
+        RP._rp_pack = pack
+        a = planner._compute_trajectory_pair(sample())
+        RP._rp_pack = None
+        b = planner._compute_trajectory_pair(sample())
+    finally:
+        RP._rp_pack = saved
+    ga, gb = H.plan_output_arrays(a), H.plan_output_arrays(b)
+    for key in ga:
+        assert np.array_equal(ga[key], gb[key]), key
+    assert type(a[0].state_list[0]) is type(b[0].state_list[0]) and isinstance(a[2][1], list) and isinstance(a[2][1][0], float)
+    assert np.max(np.abs(ga["out_cart"][2] - z["out_cart"][2])) < 1e-9       # the shift folded the extra turn away
+    with pytest.raises(ValueError):
+        pack.pack(type(a[0].state_list[0]), np.zeros(13), [], 0, 1, 0.1, 2.5, 0.0, -3.0, 3.0)
