@@ -169,8 +169,9 @@ def _cyclic_fixture(name="ZAM_Over-1_1"):
     return z, meta, golden_io.unpack_obstacles(z, "ob_")
 
 
-def replanning_latency_b200(name="ZAM_Over-1_1", repeats=5):
-    """p50 wall time of ReactivePlanner.plan() (this repo's drop-in API) over the scenario's replanning cycles."""
+def replanning_latency_b200(name="ZAM_Over-1_1", repeats=5, speculation=None):
+    """p50 wall time of ReactivePlanner.plan() (this repo's drop-in API) over the scenario's replanning cycles.
+    ``speculation``: the planner's policy for evaluating the following sampling levels in the same launch (None: default)."""
     from commonroad_rp_b200 import collision
     from commonroad_rp_b200.reactive_planner import ReactivePlanner
     from commonroad_rp_b200.state import ReactivePlannerState
@@ -190,6 +191,8 @@ def replanning_latency_b200(name="ZAM_Over-1_1", repeats=5):
 
     cfg.update(scenario=_Empty(), planning_problem=None)
     planner = ReactivePlanner(cfg)
+    if speculation is not None:
+        planner.speculation = speculation
     cc = collision.checker_from_arrays(**ob)
     co = CoordinateSystem(z["ref_path_raw"])
     times = []
@@ -211,7 +214,7 @@ def replanning_latency_b200(name="ZAM_Over-1_1", repeats=5):
     t_ms = np.array(times) * 1e3
     return {"p50_ms": float(np.percentile(t_ms, 50)), "p95_ms": float(np.percentile(t_ms, 95)), "cycles": len(t_ms),
             "scenario": "%s, N=%d, cyclic replanning inputs of the reference run (tests/golden)" % (name, meta["N"]),
-            "api": "ReactivePlanner.plan()"}
+            "api": "ReactivePlanner.plan()", "speculation": planner.speculation}
 
 
 def replanning_latency_port(name="ZAM_Over-1_1", max_cycles=6):
@@ -823,6 +826,10 @@ def main():
     line["p50_replanning_cycle_ms"]["other_bundled_scenarios"] = {
         name: {k: v for k, v in replanning_latency_b200(name, repeats=3).items() if k in ("p50_ms", "p95_ms", "cycles")}
         for name in ("ZAM_Tjunction-1_42_T-1", "DEU_Test-1_1_T-1")}
+    # the other policy: every cycle is ONE submission whatever happens (levels 1..3 always go together)
+    line["p50_replanning_cycle_ms"]["speculation_always"] = {
+        name: {k: v for k, v in replanning_latency_b200(name, repeats=3, speculation="always").items()
+               if k in ("p50_ms", "p95_ms", "cycles")} for name in ("ZAM_Over-1_1", "DEU_Test-1_1_T-1")}
     line["scenario_batch"] = scen
     if not args.no_cpu_baseline:
         line["p50_replanning_cycle_ms"]["cpu_port"] = replanning_latency_port()

@@ -94,6 +94,9 @@ def _curvilinear_states(t0, factor, pos_curv, v_l, a_l, th_l, kap_l):
     return out
 
 
+_REASON_INDEX = {name: i for i, name in enumerate(_lib.REASON_NAMES)}
+
+
 class _LazyTrajectory(Trajectory):
     """Trajectory whose ``state_list`` is built on first access (only used with the package's own stand-in classes)"""
 
@@ -185,7 +188,14 @@ class ReactivePlanner(object):
         # with the current one -- as long as their candidates x time steps stay below this budget (about one wave of the
         # step-parallel kernel) -- and picks the lowest level with a winner; 0 = one level per submission
         self.speculation_budget = 200000
+        # when plan() lets the device evaluate the following sampling levels in the same launch: "after_failure" -- the
+        # first level of a cycle goes alone (it nearly always has a winner), and when it has none ALL the remaining
+        # levels go in the second launch (an escalating cycle costs two submissions, never three); "always" -- from the
+        # first launch on (one submission per cycle whatever happens, ~15 us more host work in the cycles that do not
+        # escalate); "never"
+        self.speculation = "after_failure"
         self._escalating = False       # inside plan()'s escalation loop
+        self._level_failed = False     # a level of the current plan() call ended without a winner
         self._spec = None              # records of the levels evaluated ahead in the current cycle
         self._plan_serial = 0
         self._inputs = None            # the rp_plan_inputs struct, reused across cycles
@@ -580,7 +590,9 @@ class ReactivePlanner(object):
         work = dev["n"] * Np1
         if n_samp > max_samples or n_seg > max_segments or work > max_work:
             return None
-        if self._escalating and not cost_generic and self.speculation_budget > 0:
+        ahead = self._escalating and not cost_generic and self.speculation_budget > 0 and (
+            self.speculation == "always" or (self.speculation == "after_failure" and self._level_failed))
+        if ahead:
             for lvl in range(dev["level"] + 1, self.sampling_level):
                 if len(levels) >= max_levels:
                     break
@@ -691,7 +703,7 @@ class ReactivePlanner(object):
         self._infeasible_count_kinematics = int(res.n_infeasible_kinematics)
         self._infeasible_count_collision = int(n_collision)
         for constraint in self.config.planning.constraints_to_check:
-            self._infeasible_reason_dict[constraint] = int(res.reason_counts[_lib.REASON_NAMES.index(constraint)])
+            self._infeasible_reason_dict[constraint] = int(res.reason_counts[_REASON_INDEX[constraint]])
 
         if self._draw_traj_set:
             # feasible candidates first, then the kinematically infeasible ones (reference :1121-1128); the views are
@@ -859,6 +871,7 @@ class ReactivePlanner(object):
         self._plan_serial += 1
         self._spec = None
         self._escalating = current_sampling_level is None        # the device may evaluate the following levels ahead
+        self._level_failed = False
         try:
             while optimal_trajectory is None and i < self.sampling_level:
                 bundle = self._create_trajectory_bundle(x_0_lon, x_0_lat, samp_level=i)
@@ -870,6 +883,7 @@ class ReactivePlanner(object):
                     logger.info(f"Rejected {self.infeasible_count_collision} infeasible trajectories due to collisions")
                 if current_sampling_level is not None:
                     break
+                self._level_failed = optimal_trajectory is None
                 i += 1
         finally:
             self._escalating = False

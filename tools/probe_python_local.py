@@ -45,7 +45,7 @@ class FakeEngine:
 
 
 def main():
-    z = np.load(os.path.join(ROOT, "tests", "golden", "cyc_ZAM_Over-1_1.npz"))
+    z = dict(np.load(os.path.join(ROOT, "tests", "golden", "cyc_ZAM_Over-1_1.npz")))
     meta = json.loads(str(z["meta"]))
     cfg = ReactivePlannerConfiguration()
     cfg.planning.time_steps_computation = meta["N"]
@@ -59,6 +59,8 @@ def main():
     planner = ReactivePlanner(cfg)
     fake = FakeEngine()
     planner._engine = fake
+    if os.environ.get("RP_SPECULATION"):
+        planner.speculation = os.environ["RP_SPECULATION"]
     planner._sync_device_tables = lambda: None
     cc = collision.checker_from_arrays(**golden_io.unpack_obstacles(z, "ob_"))
     co = CoordinateSystem(z["ref_path_raw"])
