@@ -4,12 +4,17 @@ There is deliberately NO CPU fallback: if the CUDA library is missing or a call 
 exception is raised.  ``Engine`` is a thin owner of one ``rp_ctx`` (one CUDA device + stream).
 """
 import ctypes as C
+import struct
 import functools
 import os
 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+try:        # optional CPython helper (csrc/rp_pack.c, built by build.py): a faster binding of the per-cycle call
+    from commonroad_rp_b200 import _rp_pack
+except ImportError:
+    _rp_pack = None
 LIB_PATH = os.environ.get("RP_B200_LIB", os.path.join(_HERE, "librp_b200.so"))   # override: kernel A/B experiments
 
 N_REASONS = 8
@@ -44,6 +49,11 @@ class PlanInputs(C.Structure):
         ("want_all_states", C.c_int32), ("check_collision", C.c_int32),
         ("continuous_collision_check", C.c_int32), ("reserved_", C.c_int32),
     ]
+
+
+# the same layout for struct.pack_into (one call fills the whole struct; reactive_planner._plan_inputs)
+PLAN_INPUTS_STRUCT = struct.Struct("@7d4id2iI3i4d4i")
+assert PLAN_INPUTS_STRUCT.size == C.sizeof(PlanInputs)
 
 
 class PlanResult(C.Structure):
@@ -321,6 +331,27 @@ class Engine:
             b["ptr"] = (b["n"][0].ctypes.data, b["n"][1].ctypes.data, b["n"][2].ctypes.data, b["t"].ctypes.data,
                         b["tl"].ctypes.data, b["lon"].ctypes.data, b["d"].ctypes.data)
             b["refs"] = (C.byref(b["n_eval"]), C.byref(b["chosen"]))
+            b["fast"] = None
+            if _rp_pack is not None and hasattr(_rp_pack, "plan_levels"):
+                # (csrc/rp_pack.c: the same rp_plan_levels call entered through its exported address, no ctypes marshalling)
+                b["fast"] = (C.cast(self._lib.rp_plan_levels, C.c_void_p).value,
+                             self._ctx.value if hasattr(self._ctx, "value") else int(self._ctx), C.addressof(b["res"]))
+        fast = b["fast"]
+        if fast is not None:
+            try:
+                rc, chosen, _, counts = _rp_pack.plan_levels(fast[0], fast[1], C.addressof(inputs), levels, fast[2])
+            except (TypeError, ValueError):
+                rc = None                  # unusual array types / sizes: the ctypes path below converts or reports them
+            if rc is not None:
+                self._N = inputs.N
+                self.plan_generation += 1
+                b["last"] = ()
+                if rc != 0:
+                    self._check(rc)
+                self._level_counts = counts
+                self._n_cand = counts[chosen]
+                self._cyc_chosen = self._cyc_selected = chosen
+                return b["res"], chosen
         n, bt, bl, bd, btl = b["n"], b["t"], b["lon"], b["d"], b["tl"]
         ot = ol = od = 0
         counts, seen = [], []

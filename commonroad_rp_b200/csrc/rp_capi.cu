@@ -1308,6 +1308,11 @@ int rp_debug_launch_floor(rp_ctx* ctx, int iters, double* us4) {
     cudaFreeHost(h);
     return RP_OK;
 }
+int rp_debug_block_times(rp_ctx* ctx, long long* out, int n_blocks, int* grid, int* threads) {
+    if (grid) *grid = ctx->cycle_geom.grid;
+    if (threads) *threads = ctx->cycle_geom.threads;
+    return cudaMemcpyFromSymbol(out, rp::g_block_t, sizeof(long long) * 3 * n_blocks) == cudaSuccess ? RP_OK : RP_ERR_CUDA;
+}
 int rp_debug_stamps(long long* out32) {
     return cudaMemcpyFromSymbol(out32, rp::g_stamps, sizeof(long long) * 32) == cudaSuccess ? RP_OK : RP_ERR_CUDA;
 }

@@ -151,6 +151,7 @@ constexpr int kSlotExtra = 16 + 40 + 5 + 5 + 2;
 // development aid (-DRP_CYCLE_TIMING, tools/probe_cycle.py): cycle stamps of block 0 at the phase boundaries
 #ifdef RP_CYCLE_TIMING
 __device__ long long g_stamps[32];
+__device__ long long g_block_t[3 * 1024];       // per block: entry, body end, smid (globaltimer ns)
 __device__ __forceinline__ long long rp_globaltimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define RP_STAMP(n) do { if (blockIdx.x == 0 && threadIdx.x == 0) { g_stamps[n] = clock64(); if ((n) == 0 || (n) == 11) g_stamps[16 + (n)] = rp_globaltimer(); } } while (0)
 #else

@@ -503,8 +503,17 @@ __global__ void __launch_bounds__(MAXT, 2)
 cycle_kernel(const __grid_constant__ PlanParams P, const __grid_constant__ ARGS A, PlanResultDev* __restrict__ d_res) {
     extern __shared__ double smem[];
     RP_STAMP(0);
+#ifdef RP_CYCLE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_block_t[3 * blockIdx.x] = rp_globaltimer(); g_block_t[3 * blockIdx.x + 2] = smid;
+    }
+#endif
     fused_body<MAXT, true, ARGS>(P, &A, smem);
     RP_STAMP(11);
+#ifdef RP_CYCLE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 1024) g_block_t[3 * blockIdx.x + 1] = rp_globaltimer();
+#endif
     // ---- the last block to finish selects (a12 / a14, trajectories.py:502-510, reactive_planner.py:616-636, :1065-1136)
     __shared__ unsigned s_ticket;
     __threadfence();

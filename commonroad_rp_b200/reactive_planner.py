@@ -463,39 +463,28 @@ class ReactivePlanner(object):
         pi = self._inputs
         if pi is None:
             pi = self._inputs = _lib.PlanInputs()
-        pi.x0_lon[0], pi.x0_lon[1], pi.x0_lon[2] = x_0_lon[0], x_0_lon[1], x_0_lon[2]
-        pi.x0_lat[0], pi.x0_lat[1], pi.x0_lat[2] = x_0_lat[0], x_0_lat[1], x_0_lat[2]
-        pi.x0_orientation = self.x_0.orientation
-        pi.x0_time_step = int(self.x_0.time_step)
-        pi.low_vel_mode = 1 if self._low_vel_mode else 0
-        pi.lon_mode = _lib.STOPPING if self.config.sampling.longitudinal_mode == "stopping" else _lib.VELOCITY_KEEPING
-        pi.N = self.N
-        pi.dt = self.dt
-        pi.factor = int(p.factor)
-        pi.draw_all = 1 if self._draw_traj_set else 0
         key = tuple(p.constraints_to_check)
         if key != self._constraint_key:
             mask = 0
             for name in key:
                 mask |= _lib.CONSTRAINT_BITS[name]
             self._constraint_key, self._constraint_mask = key, mask
-        pi.constraint_mask = self._constraint_mask
         kind = cost_spec["cost_kind"]
-        pi.cost_kind = kind
         ds, dp = cost_spec["desired_speed"], cost_spec["desired_s"]
-        pi.has_desired_speed = 0 if ds is None else 1
-        pi.has_desired_s = 0 if dp is None else 1
-        pi.desired_speed = 0.0 if ds is None else ds
-        pi.desired_s = 0.0 if dp is None else dp
-        pi.desired_d = cost_spec["desired_d"]
-        pi.w_a = cost_spec["w_a"]
-        pi.want_all_states = 1 if want_all_states else 0
         if check_collision is None:
             # the reference's collision pass is lazy (:1031-1063); full flags only when every trajectory is kept
             check_collision = _lib.COLLISION_ALL if (want_all_states or kind == _lib.COST_NONE) else _lib.COLLISION_LAZY
-        pi.check_collision = check_collision
-        # reference :1049-1058 (the hull check of the first discretely collision-free candidate, on the device)
-        pi.continuous_collision_check = 1 if (p.continuous_collision_check and kind != _lib.COST_NONE) else 0
+        # one pack_into for the whole struct (field order of _lib.PlanInputs / rp_plan_inputs)
+        _lib.PLAN_INPUTS_STRUCT.pack_into(
+            pi, 0, x_0_lon[0], x_0_lon[1], x_0_lon[2], x_0_lat[0], x_0_lat[1], x_0_lat[2], self.x_0.orientation,
+            int(self.x_0.time_step), 1 if self._low_vel_mode else 0,
+            _lib.STOPPING if self.config.sampling.longitudinal_mode == "stopping" else _lib.VELOCITY_KEEPING, self.N,
+            self.dt, int(p.factor), 1 if self._draw_traj_set else 0, self._constraint_mask,
+            kind, 0 if ds is None else 1, 0 if dp is None else 1,
+            0.0 if ds is None else ds, 0.0 if dp is None else dp, cost_spec["desired_d"], cost_spec["w_a"],
+            1 if want_all_states else 0, check_collision,
+            # reference :1049-1058 (the hull check of the first discretely collision-free candidate, on the device)
+            1 if (p.continuous_collision_check and kind != _lib.COST_NONE) else 0, 0)
         return pi
 
     def _device_cost_spec(self):
@@ -523,8 +512,10 @@ class ReactivePlanner(object):
         if hasattr(self.sampling_space, "sample_grid"):
             t, lon, d = self.sampling_space.sample_grid(samp_level, x_0_lat, mode)
             bundle = TrajectoryBundle(lambda: self._materialise_views(bundle), cost_function=self.cost_function)
-            bundle.device = {"kind": "grid", "t": t, "lon": lon, "d": d, "x_0_lon": np.asarray(x_0_lon, dtype=np.float64),
-                             "x_0_lat": np.asarray(x_0_lat, dtype=np.float64), "mode": mode,
+            # (the initial states as plain tuples: read three times per cycle, turned into arrays only by the lazy
+            # polynomial objects)
+            bundle.device = {"kind": "grid", "t": t, "lon": lon, "d": d, "x_0_lon": tuple(x_0_lon),
+                             "x_0_lat": tuple(x_0_lat), "mode": mode,
                              "low_vel": bool(self._low_vel_mode), "n": len(t) * len(lon) * len(d), "level": samp_level,
                              "serial": self._plan_serial}
         else:
@@ -544,14 +535,14 @@ class ReactivePlanner(object):
         il, idd = divmod(rem, n_d)
         t, lon, d = float(dev["t"][it]), float(dev["lon"][il]), float(dev["d"][idd])
         if dev["mode"] == "velocity_keeping":
-            tl = QuarticTrajectory(tau_0=0, delta_tau=t, x_0=dev["x_0_lon"].copy(), x_d=np.array([lon, 0.0]))
+            tl = QuarticTrajectory(tau_0=0, delta_tau=t, x_0=np.array(dev["x_0_lon"], dtype=np.float64), x_d=np.array([lon, 0.0]))
         else:
-            tl = QuinticTrajectory(tau_0=0, delta_tau=t, x_0=dev["x_0_lon"].copy(), x_d=np.array([lon, 0.0, 0.0]))
+            tl = QuinticTrajectory(tau_0=0, delta_tau=t, x_0=np.array(dev["x_0_lon"], dtype=np.float64), x_d=np.array([lon, 0.0, 0.0]))
         tau_lat = t
         if dev["low_vel"]:
             s_goal = tl.evaluate_state_at_tau(t)[0] - dev["x_0_lon"][0]
             tau_lat = t if s_goal <= 0 else s_goal
-        lat = QuinticTrajectory(tau_0=0, delta_tau=tau_lat, x_0=dev["x_0_lat"].copy(), x_d=np.array([d, 0.0, 0.0]))
+        lat = QuinticTrajectory(tau_0=0, delta_tau=tau_lat, x_0=np.array(dev["x_0_lat"], dtype=np.float64), x_d=np.array([d, 0.0, 0.0]))
         return tl, lat
 
     def _view(self, bundle, k, arrays):
@@ -647,8 +638,8 @@ class ReactivePlanner(object):
         level_index = None
         spec = self._spec
         if (spec is not None and dev["kind"] == "grid" and spec["serial"] == dev.get("serial") and dev["level"] in spec["index"]
-                and spec["generation"] == eng.plan_generation and np.array_equal(spec["x_0_lon"], dev["x_0_lon"])
-                and np.array_equal(spec["x_0_lat"], dev["x_0_lat"])):
+                and spec["generation"] == eng.plan_generation and tuple(spec["x_0_lon"]) == tuple(dev["x_0_lon"])
+                and tuple(spec["x_0_lat"]) == tuple(dev["x_0_lat"])):
             # this level was evaluated ahead, together with the previous one: no new submission
             level_index = spec["index"][dev["level"]]
             res = spec["records"][level_index]
@@ -767,14 +758,13 @@ class ReactivePlanner(object):
     def _compute_trajectory_pair(self, trajectory: TrajectorySample) -> Tuple[Trajectory, Trajectory, List, List]:
         """Optimal sample -> (Cartesian Trajectory, curvilinear Trajectory, lon list, lat list)
         (reference :514-568)."""
-        ca, cu = trajectory.cartesian, trajectory.curvilinear
         factor = self.config.planning.factor
         x_0 = self.x_0
-        device_block = getattr(trajectory, "_rows_untouched", None) is not None and trajectory._rows_untouched()
+        block = trajectory._device_block() if hasattr(trajectory, "_device_block") else None
+        device_block = block is not None
         if device_block and _rp_pack is not None and not HAVE_COMMONROAD_IO:
             # the whole packing in one C call (csrc/rp_pack.c): state objects, steering angles, yaw rates, orientation
             # shift, the two curvilinear lists -- the same per-state arithmetic as the reference's loop (:520-556)
-            block = trajectory._state_block[0]
             t0 = x_0.time_step
             cart_list, lon_list, lat_list = _rp_pack.pack(ReactivePlannerState, block, list(np.ascontiguousarray(block[0:2].T)),
                                                           int(t0), int(factor), float(self.dt), float(self.vehicle_params.wheelbase),
@@ -784,6 +774,7 @@ class ReactivePlanner(object):
             curv_traj = _LazyTrajectory(t0, lambda: _curvilinear_states(t0, factor, np.ascontiguousarray(pos_curv), rows[1].tolist(),
                                                                         rows[2].tolist(), rows[0].tolist(), rows[3].tolist()))
             return Trajectory(t0, cart_list), curv_traj, lon_list, lat_list
+        ca, cu = trajectory.cartesian, trajectory.curvilinear
         n = len(ca.x)
         theta = ca.theta
         steering = np.arctan2(self.vehicle_params.wheelbase * ca.kappa, 1.0)
@@ -794,7 +785,6 @@ class ReactivePlanner(object):
         t0 = x_0.time_step
         if device_block:
             # device result: the 14 rows are views of one block -- one transpose / tolist per group instead of one per row
-            block = trajectory._state_block[0]
             rows = block.tolist()
             th_l, v_l, a_l, kap_l = rows[2], rows[3], rows[4], rows[5]
             pos_cart = np.ascontiguousarray(block[0:2].T)
@@ -888,8 +878,8 @@ class ReactivePlanner(object):
         finally:
             self._escalating = False
 
-        if (optimal_trajectory is None or optimal_trajectory.cartesian.v[self._standstill_lookahead] <= 0.05) \
-                and self.x_0.velocity <= 0.05:
+        if self.x_0.velocity <= 0.05 and \
+                (optimal_trajectory is None or optimal_trajectory.cartesian.v[self._standstill_lookahead] <= 0.05):
             logger.info("Planning standstill for the current scenario")
             optimal_trajectory = self._compute_standstill_trajectory()
             if optimal_trajectory is None and current_sampling_level == self.sampling_level:

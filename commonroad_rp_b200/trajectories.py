@@ -168,6 +168,8 @@ class TrajectorySample(Sample):
     def _materialise(self):
         """Pull this candidate's state block from the device (once)."""
         b = self._backing
+        if self.__dict__.get("_pending_block") is not None:
+            self._build_from_block()
         if b is None or self._cartesian is not None:
             return
         if b.engine.plan_generation == b.generation and hasattr(b.bundle_arrays, "select"):
@@ -182,6 +184,17 @@ class TrajectorySample(Sample):
                                               dd=st[12], ddd=st[13])
 
     def _set_states(self, st: np.ndarray):
+        """The candidate's 14 x (N + 1) device state block; the two sample objects over its rows are built when
+        ``cartesian`` / ``curvilinear`` are first read (plan()'s output packing reads the block itself)."""
+        self._pending_block = st
+        self._state_block = None
+        self._cartesian = self._curvilinear = None
+
+    def _build_from_block(self):
+        st = self.__dict__.get("_pending_block")
+        if st is None:
+            return
+        self._pending_block = None
         n = st.shape[1]
         r = tuple(st)                     # the 14 row views handed to the two samples
         self._state_block = (st, r)       # output packing reads the block whole while the samples still hold these rows
@@ -189,8 +202,17 @@ class TrajectorySample(Sample):
         self._curvilinear = CurviLinearSample(r[7], r[8], r[9], current_time_step=n, ss=r[10], sss=r[11],
                                               dd=r[12], ddd=r[13])
 
+    def _device_block(self):
+        """The device state block while nobody replaced or re-bound the samples' rows, else None."""
+        st = self.__dict__.get("_pending_block")
+        if st is not None:
+            return st
+        return self._state_block[0] if self._rows_untouched() else None
+
     def _rows_untouched(self) -> bool:
         """True while cartesian / curvilinear still hold exactly the row views of the device block."""
+        if self.__dict__.get("_pending_block") is not None:
+            return True
         blk = getattr(self, "_state_block", None)
         if blk is None or self._cartesian is None or self._curvilinear is None:
             return False
@@ -205,7 +227,7 @@ class TrajectorySample(Sample):
         self.trajectory_long, self.trajectory_lat          # (lazy views build their polynomial objects now)
         new = TrajectorySample.__new__(TrajectorySample)
         for k, v in self.__dict__.items():
-            setattr(new, k, None if k in ("_backing", "_state_block", "_poly_factory") else copy.deepcopy(v, memo))
+            setattr(new, k, None if k in ("_backing", "_state_block", "_poly_factory", "_pending_block") else copy.deepcopy(v, memo))
         if self._backing is not None:
             new._cost = self.cost
             new._label = self.feasibility_label
@@ -213,6 +235,8 @@ class TrajectorySample(Sample):
 
     def _materialise_if_available(self):
         b = self._backing
+        if self.__dict__.get("_pending_block") is not None:
+            self._build_from_block()
         if b is not None and self._cartesian is None and b.engine.plan_generation == b.generation:
             status = int(b.bundle_arrays["status"][b.index])
             if status in (0, 2, 4) or b.bundle_arrays.get("all_states", False):
@@ -250,8 +274,11 @@ class TrajectorySample(Sample):
 
     @property
     def curvilinear(self) -> CurviLinearSample:
-        if self._curvilinear is None and self._backing is not None:
-            self._materialise_if_available()
+        if self._curvilinear is None:
+            if self.__dict__.get("_pending_block") is not None:
+                self._build_from_block()
+            elif self._backing is not None:
+                self._materialise_if_available()
         return self._curvilinear
 
     @curvilinear.setter
@@ -261,8 +288,11 @@ class TrajectorySample(Sample):
 
     @property
     def cartesian(self) -> CartesianSample:
-        if self._cartesian is None and self._backing is not None:
-            self._materialise_if_available()
+        if self._cartesian is None:
+            if self.__dict__.get("_pending_block") is not None:
+                self._build_from_block()
+            elif self._backing is not None:
+                self._materialise_if_available()
         return self._cartesian
 
     @cartesian.setter
@@ -292,8 +322,8 @@ class TrajectorySample(Sample):
         return self.cartesian.length()
 
     def enlarge(self, dt: float):
-        self._cartesian.enlarge(dt)
-        self._curvilinear.enlarge(dt)
+        self.cartesian.enlarge(dt)
+        self.curvilinear.enlarge(dt)
 
 
 class DeviceTrajectorySample(TrajectorySample):

@@ -381,3 +381,34 @@ def test_c_output_packing_equals_python_packing():
     assert np.max(np.abs(ga["out_cart"][2] - z["out_cart"][2])) < 1e-9       # the shift folded the extra turn away
     with pytest.raises(ValueError):
         pack.pack(type(a[0].state_list[0]), np.zeros(13), [], 0, 1, 0.1, 2.5, 0.0, -3.0, 3.0)
+
+
+def test_c_binding_of_the_cycle_call_passes_the_same_arguments():
+    """csrc/rp_pack.c plan_levels: the levels' arrays concatenated exactly as Engine.plan_levels' ctypes path stages them"""
+    import ctypes as C
+    _rp_pack = pytest.importorskip("commonroad_rp_b200._rp_pack")
+    seen = {}
+    proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                        C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                        C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32))
+
+    def fake(ctx, inp, n_levels, n_t, n_lon, n_d, t_cat, tl_cat, lon_cat, d_cat, out, n_eval, chosen):
+        nt, nl, nd = sum(n_t[:n_levels]), sum(n_lon[:n_levels]), sum(n_d[:n_levels])
+        seen.update(ctx=ctx, inp=inp, out=out, n=(list(n_t[:n_levels]), list(n_lon[:n_levels]), list(n_d[:n_levels])),
+                    t=list(t_cat[:nt]), tl=list(tl_cat[:nt]), lon=list(lon_cat[:nl]), d=list(d_cat[:nd]))
+        n_eval[0], chosen[0] = 2, 1
+        return 0
+
+    cb = proto(fake)
+    levels = [(np.array([1.0, 2.0]), np.array([3.0, 4.0, 5.0]), np.array([0.5]), np.array([11, 21], dtype=np.int32)),
+              (np.array([1.0, 1.5, 2.0]), np.array([3.0]), np.array([0.5, -0.5]), np.array([11, 16, 21], dtype=np.int32))]
+    rc, chosen, n_eval, counts = _rp_pack.plan_levels(C.cast(cb, C.c_void_p).value, 1234, 5678, levels, 91011)
+    assert (rc, chosen, n_eval, counts) == (0, 1, 2, (6, 6))
+    assert (seen["ctx"], seen["inp"], seen["out"]) == (1234, 5678, 91011)
+    assert seen["n"] == ([2, 3], [3, 1], [1, 2])
+    assert seen["t"] == [1.0, 2.0, 1.0, 1.5, 2.0] and seen["tl"] == [11, 21, 11, 16, 21]
+    assert seen["lon"] == [3.0, 4.0, 5.0, 3.0] and seen["d"] == [0.5, 0.5, -0.5]
+    with pytest.raises(TypeError):          # float32 samples: left to the ctypes path (which converts)
+        _rp_pack.plan_levels(C.cast(cb, C.c_void_p).value, 0, 0, [(np.zeros(2, np.float32),) + levels[0][1:]], 0)
+    with pytest.raises(ValueError):
+        _rp_pack.plan_levels(C.cast(cb, C.c_void_p).value, 0, 0, [(np.zeros(500), levels[0][1], levels[0][2], np.zeros(500, np.int32))], 0)

@@ -147,6 +147,15 @@ def stamps():
             gl.append([g[11] - g[0], g[15] - g[0], g[12] - g[0], g[13] - g[0], g[14] - g[0]])
         print("globaltimer ns since block 0 entry: block-0 body end %d, LAST block's fence done %d, selection start %d, "
               "select+gather done %d, flag %d" % tuple(np.median(np.array(gl[10:]), axis=0)))
+        bt = (C.c_longlong * (3 * 1024))()
+        grid, threads = C.c_int(), C.c_int()
+        lib.rp_debug_block_times.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.rp_debug_block_times(eng._ctx, bt, 1024, C.byref(grid), C.byref(threads))
+        g = min(grid.value, 1024)
+        b = np.array(bt[:3 * g], dtype=np.int64).reshape(g, 3)
+        t00 = b[:, 0].min()
+        print("grid %d x %d threads; last cycle, per block (entry ns, body ns, sm):" % (grid.value, threads.value))
+        print("  " + " ".join("%d:%d+%d@%d" % (i, b[i, 0] - t00, b[i, 1] - b[i, 0], b[i, 2]) for i in range(g)))
         a = np.median(np.array(acc[10:]), axis=0)
         print("levels", nl, "wall p50 %.1f us" % (np.median(wall[-40:]) * 1e6), "(cycles since entry; block 0, its LAST group)")
         for k in range(1, 15):

@@ -47,6 +47,20 @@ def main():
     wrap(_lib.Engine, "_grid_args", "Engine._grid_args")
     wrap(S.FixedIntervalSampling, "sample_grid", "sample_grid")
     wrap(RP, "shift_orientation", "shift_orientation")
+    wrap(_lib.Engine, "cycle_winner_states", "Engine.cycle_winner_states")
+    from commonroad_rp_b200 import trajectories as T
+    wrap(T.TrajectorySample, "_set_states", "_set_states")
+    wrap(P, "plan", "plan")
+    if RP._rp_pack is not None:
+        class _Shim:
+            pack = staticmethod(RP._rp_pack.pack)
+        RP._rp_pack = _Shim
+        wrap(_Shim, "pack", "_rp_pack.pack")
+    if _lib._rp_pack is not None:
+        class _Shim2:
+            plan_levels = staticmethod(_lib._rp_pack.plan_levels)
+        _lib._rp_pack = _Shim2
+        wrap(_Shim2, "plan_levels", "C rp_plan_levels (via _rp_pack)")
     res = bench.replanning_latency_b200("ZAM_Over-1_1", repeats=5)
     n = res["cycles"]
     print(res["p50_ms"], res["p95_ms"], n)

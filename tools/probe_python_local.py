@@ -96,7 +96,7 @@ def main():
     else:
         run(200)
     t = np.array(times) * 1e6
-    print("pure-Python plan() overhead: p50 %.1f us  p95 %.1f us  (n=%d)" % (np.percentile(t, 50), np.percentile(t, 95), len(t)))
+    print("pure-Python plan() overhead: p10 %.1f us  p50 %.1f us  p95 %.1f us  (n=%d)" % (np.percentile(t, 10), np.percentile(t, 50), np.percentile(t, 95), len(t)))
 
 
 if __name__ == "__main__":
