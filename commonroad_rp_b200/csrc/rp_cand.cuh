@@ -419,7 +419,20 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 // candidate and write nothing.
 // ONE_GROUP: the host guarantees G == 1 for every chunk (grid form, n_d a multiple of 32, aligned shard): the group
 // arithmetic folds away at compile time.
-template <int BLOCK, bool ONE_GROUP, int PF, bool LATROWS = false, int SLOTS = 32>
+// the tiles (32 consecutive candidates) of the first pass of the deferred collision check: a pseudo-random sixteenth
+// (the bound on the winner's cost comes from them)
+__device__ __forceinline__ bool defer_sampled(int tile) { return (((unsigned)tile * 0x9E3779B1u) >> 28) == 0u; }
+// put candidate k on a pass's list: its bit in the tile's mask; whoever sets the first bit lists the tile
+__device__ __forceinline__ void defer_enlist(const PlanParams& P, int k, int pass, int n_tiles) {
+    const int tile = k >> 5;
+    if (atomicOr(P.defer_mask + tile, 1u << (k & 31)) == 0u) P.defer_list[pass * n_tiles + atomicAdd(P.defer_count + pass, 1)] = tile;
+}
+
+// DEFER: the march does not check collisions; it stores the ego box of every step while the candidate is still
+// kinematically feasible (P.pose) and leaves feasible candidates ST_UNCHECKED for deferred_collision_kernel.
+// (Letting the march itself check every 16th chunk -- taken first from the queue -- instead of a first deferred pass was
+// measured: the slower chunks stretch the march by 19 us, the saved pass is worth 17.)
+template <int BLOCK, bool ONE_GROUP, int PF, bool LATROWS = false, int SLOTS = 32, bool DEFER = false>
 __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k, bool valid,
                                            double* __restrict__ acc, double* __restrict__ s_vmid,
                                            double* __restrict__ rows) {
@@ -427,6 +440,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     const ObstacleTables& O = P.obs;
     const rp_plan_inputs& in = P.in;
     const bool low_vel = in.low_vel_mode != 0;
+    const bool store_boxes = DEFER && P.pose != nullptr;
     const double dt = in.dt;
     const unsigned NONE = 0xFFFFFFFFu;
     const bool fs = in.cost_kind == RP_COST_FAILSAFE;
@@ -614,8 +628,15 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             if (i == mid) s_vmid[0] = c_v;                   // v[int(len(v) / 2)]
         }
 
-        // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046), speculative ---------------------
-        if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u) {
+        // ---- ego-vs-obstacle check (reactive_planner.py:1026-1046) ------------------------------------
+        if (DEFER) {
+            // the box of this step for the deferred check (only candidates that end feasible are read back)
+            if (store_boxes && valid && !filtered && bad == NONE && pbad == NONE && pre == 0u) {
+                double2* rec = reinterpret_cast<double2*>(P.pose) + (((size_t)(k >> 5) * Np1 + i) * 32 + (k & 31)) * 2;
+                rec[0] = make_double2(px + P.wb_rear * cn, py + P.wb_rear * sn);
+                rec[1] = make_double2(cn, sn);
+            }
+        } else if (in.check_collision && col == NONE && bad == NONE && pbad == NONE && pre == 0u) {
             const double ecx = px + P.wb_rear * cn;
             const double ecy = py + P.wb_rear * sn;
             const int tidx = in.x0_time_step + i * in.factor;
@@ -648,7 +669,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         reason = R_PROJECTION;
         step = (int)pbad;
     } else {
-        status = ST_FEASIBLE;
+        status = (store_boxes && in.check_collision) ? ST_UNCHECKED : ST_FEASIBLE;
         if (costed) {
             double res_a, res_d, res_th, res_v = 0., res_s = 0.;     // np.sum results
             if (Np1 >= 8 && n8 == Np1) {                       // no remainder: the tree was not taken in the loop
@@ -684,6 +705,8 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     }
     P.info[k] = pack_info(status, reason, step);
     if (P.cost) P.cost[k] = cost;
+    // first pass of the deferred check: the feasible candidates of a pseudo-random sixteenth of the tiles
+    if (DEFER && status == ST_UNCHECKED && defer_sampled(k >> 5)) defer_enlist(P, k, 0, (P.n_cand + 31) >> 5);
 }
 
 // locate chunk g of 32 candidates in the segment table (sorted by traj_len, longest first): the lane's candidate,
@@ -700,7 +723,7 @@ __device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs,
 }
 
 // ---- one bundle: persistent grid, warps draw chunks of 32 candidates from a counter -----------------------------
-template <int BLOCK, bool ONE_GROUP, bool LATROWS = false>
+template <int BLOCK, bool ONE_GROUP, bool LATROWS = false, bool DEFER = false>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
@@ -747,8 +770,73 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         bool valid;
         int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
         if (P.stripe_world > 1) k = Stripe{P.stripe_rank, P.stripe_world, P.n_lon, P.n_d}.real(k);     // lon-interleaved shard
-        cand_march<BLOCK, ONE_GROUP, 2, LATROWS, SLOTS>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, ONE_GROUP, 2, LATROWS, SLOTS, DEFER>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
+}
+
+// ---- deferred collision check of one bundle (after cand_kernel<.., DEFER = true>; check_collision = 2) -------------
+// The reference's collision pass is lazy (reactive_planner.py:1031-1063): it walks the feasible candidates in cost order
+// and stops at the first collision-free one.  Here:
+//   pass 1  the feasible candidates of a pseudo-random sixteenth of the tiles (listed by the march) are checked; the
+//           cheapest collision-free one bounds the winner's cost (best_bits)
+//   gather  every still unchecked candidate at or below the bound is listed
+//   pass 2  those are checked: now every candidate ranked before the winner has its verdict, which is all the
+//           reference looks at; the rest stay ST_UNCHECKED
+// One BLOCK per listed tile of 32 consecutive candidates, lane = candidate, warp w = time steps w, w + 16, ...: the lanes
+// of a warp are neighbours in d at the same time step -- the same cells and obstacle rows, as in the march -- and the
+// N + 1 boxes of a candidate are checked by 16 warps at once instead of an (N + 1)-step march.  The verdict (status, first
+// colliding step) is what the march itself would have recorded: same boxes (stored by the march), same tests.
+constexpr int kDeferThreads = 512;
+__global__ void __launch_bounds__(kDeferThreads) deferred_collision_kernel(const __grid_constant__ PlanParams P, const int* __restrict__ list,
+                                                                           const int* __restrict__ n_listed) {
+    __shared__ int s_first[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = *n_listed;
+    const ObstacleTables& O = P.obs;
+    const int Np1 = P.Np1;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int tile = list[b];
+        const unsigned mask = P.defer_mask[tile];
+        if (threadIdx.x < 32) s_first[threadIdx.x] = 0x7fffffff;
+        __syncthreads();
+        if (threadIdx.x == 0) P.defer_mask[tile] = 0u;                  // clean for the next pass / cycle
+        const bool active = (mask >> lane) & 1u;
+        const double2* rec0 = reinterpret_cast<const double2*>(P.pose) + ((size_t)tile * Np1 * 32 + lane) * 2;
+        // the boxes were written to DRAM by the march: start all of this warp's fetches now (one sector per lane and step)
+        if (active)
+            for (int i = warp + kDeferThreads / 32; i < Np1; i += kDeferThreads / 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec0 + (size_t)i * 64));
+        for (int i = warp; i < Np1; i += kDeferThreads / 32) {
+            if (!active || reinterpret_cast<volatile int*>(s_first)[lane] < i) continue;                    // (a smaller colliding step is already known)
+            const double2* rec = rec0 + (size_t)i * 64;
+            const double2 c = __ldcs(rec), h = __ldcs(rec + 1);
+            const int tidx = P.in.x0_time_step + i * P.in.factor;
+            const bool hit = (P.dyn_rows ? dyn_collides_f32(O, P.dyn_rows + (size_t)i * O.n_dyn, tidx, c.x, c.y, h.x, h.y, P.half_len,
+                                                            P.half_wid, 0xffffffffu)
+                                         : dyn_collides_global(O, tidx, c.x, c.y, h.x, h.y, P.half_len, P.half_wid, P.r_ego)) ||
+                             static_collides<2>(O, c.x, c.y, h.x, h.y, P.half_len, P.half_wid);
+            if (hit) atomicMin(&s_first[lane], i);
+        }
+        __syncthreads();
+        if (warp == 0 && active) {
+            const int k = tile * 32 + lane;
+            const int step = s_first[lane];
+            P.info[k] = step != 0x7fffffff ? pack_info(ST_COLLISION, R_NONE, step) : pack_info(ST_FEASIBLE, R_NONE, -1);
+            if (step == 0x7fffffff) atomicMin(P.best_bits, (unsigned long long)__double_as_longlong(P.cost[k]));
+        }
+        __syncthreads();
+    }
+}
+
+// second list: unchecked candidates of the shard whose cost does not exceed the bound of the first pass
+__global__ void __launch_bounds__(256) deferred_gather_kernel(const __grid_constant__ PlanParams P, int first, int count) {
+    const int q = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+    if (q >= count) return;
+    int k = first + q;
+    if (P.stripe_world > 1) k = Stripe{P.stripe_rank, P.stripe_world, P.n_lon, P.n_d}.real(k);
+    if ((P.info[k] & 0xFF) != ST_UNCHECKED) return;
+    if ((unsigned long long)__double_as_longlong(P.cost[k]) > *P.best_bits) return;
+    defer_enlist(P, k, 1, (P.n_cand + 31) >> 5);
 }
 
 // ---- a batch of independent scenarios (BASELINE configs[4]): ONE launch over all (scenario, chunk) pairs --------

@@ -138,7 +138,7 @@ struct rp_ctx {
     Geometry main_geom{}, index_geom{}, cand_geom{};
     bool main_is_cand = false, main_one_group = false, small_path_last = false;          // geometry in main_geom/d_segs belongs to the candidate-major kernel
     int kernel_policy = RP_KERNEL_AUTO;
-    DevBuf d_work, d_dyn_rows, d_lat_rows;
+    DevBuf d_work, d_dyn_rows, d_lat_rows, d_pose, d_defer_list, d_defer_mask;
     int index_geom_np1 = -1, index_geom_count = -1;
     long long index_geom_tables = -1;
     double ref_inv_step = 1.0, ps_inv_step = 1.0;
@@ -506,6 +506,9 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         granted = (int)G.smem;
     }
     int occ = 0;
@@ -1120,7 +1123,7 @@ static int launch_plan(rp_ctx* ctx) {
         A.dt = ctx->in.dt;
         const int n_lat_row_threads = use_lat_rows ? ctx->n_t * ((Np1 + 7) / 8) * ctx->n_d : 0;
         if (int rc = ctx->d_argmin.ensure(sizeof(rp::ArgminScratch))) return rc;
-        if (int rc = ctx->d_work.ensure(sizeof(int))) return rc;
+        if (int rc = ctx->d_work.ensure(sizeof(int) * rp::kWorkWords)) return rc;
         if (int rc = ctx->d_best.ensure(sizeof(unsigned long long))) return rc;
         A.argmin_counts = reinterpret_cast<int*>(ctx->d_argmin.p);
         A.work_counter = ctx->d_work.as<int>();
@@ -1148,8 +1151,8 @@ static int launch_plan(rp_ctx* ctx) {
             P.best_bits = ctx->d_best.as<unsigned long long>();
         }
         if (ctx->main_is_cand) {
-            if (int rc = ctx->d_work.ensure(sizeof(int))) return rc;
-            if (!dyn_rows_done) RP_CUDA(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(int), ctx->stream));
+            if (int rc = ctx->d_work.ensure(sizeof(int) * rp::kWorkWords)) return rc;
+            if (!dyn_rows_done) RP_CUDA(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(int) * rp::kWorkWords, ctx->stream));
             P.work_counter = ctx->d_work.as<int>();
             P.n_acc_rows = cand_acc_rows(ctx->in);
             P.dyn_rows = nullptr;
@@ -1162,10 +1165,42 @@ static int launch_plan(rp_ctx* ctx) {
             }
             const Geometry& G = ctx->main_geom;
             P.lat_rows = (use_lat_rows && ctx->main_one_group) ? ctx->d_lat_rows.as<double>() : nullptr;
-            if (P.lat_rows) rp::cand_kernel<RP_CAND_THREADS, true, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
-            else if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
-            else rp::cand_kernel<RP_CAND_THREADS, false><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+            // the reference's lazy collision pass (check_collision = 2): the march stores the ego boxes (32 bytes per
+            // candidate-timestep) and the checks run afterwards, all time steps of a candidate at once, for the
+            // candidates that can be ranked before the winner (rp_cand.cuh, deferred_collision_kernel)
+            const bool defer = ctx->in.check_collision == 2 && ctx->in.cost_kind != RP_COST_NONE;
+            P.pose = nullptr;
+            if (defer) {
+                if (int rc = ctx->d_pose.ensure((size_t)((n + 31) / 32) * Np1 * 32 * 4 * sizeof(double))) return rc;
+                const size_t n_tiles = (size_t)(n + 31) / 32;
+                if (int rc = ctx->d_defer_list.ensure(2 * n_tiles * sizeof(int))) return rc;
+                if (ctx->d_defer_mask.cap < n_tiles * sizeof(unsigned)) {       // (the checker leaves the masks it used clear)
+                    if (int rc = ctx->d_defer_mask.ensure(n_tiles * sizeof(unsigned))) return rc;
+                    RP_CUDA(cudaMemsetAsync(ctx->d_defer_mask.p, 0, ctx->d_defer_mask.cap, ctx->stream));
+                }
+                P.pose = ctx->d_pose.as<double>();
+                P.defer_list = ctx->d_defer_list.as<int>();
+                P.defer_count = ctx->d_work.as<int>() + 1;
+                P.defer_mask = ctx->d_defer_mask.as<unsigned>();
+            }
+            if (defer) {
+                if (P.lat_rows) rp::cand_kernel<RP_CAND_THREADS, true, true, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+                else if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true, false, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+                else rp::cand_kernel<RP_CAND_THREADS, false, false, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+            } else {
+                if (P.lat_rows) rp::cand_kernel<RP_CAND_THREADS, true, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+                else if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+                else rp::cand_kernel<RP_CAND_THREADS, false><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+            }
             RP_CUDA(cudaGetLastError());
+            if (defer) {
+                const int n_tiles = (n + 31) / 32;
+                const int check_blocks = std::max(1, std::min(n_tiles, 8 * ctx->num_sms));
+                rp::deferred_collision_kernel<<<check_blocks, rp::kDeferThreads, 0, ctx->stream>>>(P, P.defer_list, P.defer_count);
+                rp::deferred_gather_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(P, first, count);
+                rp::deferred_collision_kernel<<<check_blocks, rp::kDeferThreads, 0, ctx->stream>>>(P, P.defer_list + n_tiles, P.defer_count + 1);
+                RP_CUDA(cudaGetLastError());
+            }
         } else if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
         ctx->states_all_valid = ctx->in.want_all_states != 0;
     }
@@ -1898,11 +1933,13 @@ int rp_launches_per_plan(rp_ctx* ctx) {
     // coeff, fused, argmin partial / merge / count, winner states (+ the dynamic-obstacle rows of the candidate-major kernel)
     if (ctx->cycle_valid) return 1;                               // rp_plan_levels: the whole cycle is one kernel
     if (ctx->small_path_last) return ctx->mode == 0 ? 3 : 2;      // coeff, fused (states of every kept candidate), select
+    // the candidate-major kernel defers the checks of the lazy collision pass: check, gather, check
+    const int deferred = (ctx->main_is_cand && ctx->in.check_collision == 2 && ctx->in.cost_kind != RP_COST_NONE) ? 3 : 0;
     if (ctx->peer_mode_last)        // prep, main kernel, argmin partial / merge + record exchange, peer count, winner states
-        return ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
+        return deferred + (ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
     // prep (coefficients + dynamic-obstacle rows), main kernel, argmin partial / merge / count, winner states; the list
     // form has no coefficient solve but, for the candidate-major kernel, its own dynamic-obstacle rows launch
-    return ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0);
+    return deferred + (ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
 }
 
 }  // extern "C"

@@ -107,6 +107,14 @@ struct PlanParams {
     int stripe_rank, stripe_world;
     const double* lat_rows;      // [n_t][Np1][n_d][4] = d, d_dot (clamped), d_ddot, - of the lateral polynomials on the time
                                  // grid (high-velocity grid bundles: shared by all lon samples; null: evaluated per candidate)
+    // deferred collision check of the candidate-major kernel (deferred_collision_kernel): the march stores the ego box of
+    // every step as a 32-byte record (centre x, centre y, cos, sin) at [(k >> 5)][step][k & 31] -- the warp's store of
+    // one step is 1 KB contiguous, the checker's read of one (candidate, step) is exactly one sector
+    double* pose;
+    int* defer_list;             // tiles (32 consecutive candidates, k >> 5) awaiting the deferred check: [0, n_tiles) first
+                                 // pass, [n_tiles, 2 n_tiles) second pass
+    int* defer_count;            // [2] lengths of the two lists (zeroed with the work counter)
+    unsigned* defer_mask;        // [n_tiles] which candidates of a listed tile are to be checked (cleared by the checker)
 };
 
 // Multi-GPU shards that are ALIKE instead of contiguous: rank r of `world` owns the lon samples il = r, r + world, ... of

@@ -101,14 +101,16 @@ struct PrepArgs {
     double dt;
     // per-cycle scratch words this launch resets for the kernels after it (instead of separate memset nodes)
     int* argmin_counts;                 // [16]
-    int* work_counter;                  // chunk dispenser of the candidate-major kernel (may be null)
+    int* work_counter;                  // [kWorkWords] chunk dispenser of the candidate-major kernel + its deferred-check list lengths (may be null)
     unsigned long long* best_bits;      // lazy collision bound of the step-parallel kernel (may be null)
 };
+
+constexpr int kWorkWords = 4;          // chunk dispenser, the two list lengths of the deferred collision check, spare
 
 __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ PrepArgs A) {
     if (blockIdx.x == 0) {
         if (threadIdx.x < 16 && A.argmin_counts) A.argmin_counts[threadIdx.x] = 0;
-        if (threadIdx.x == 16 && A.work_counter) *A.work_counter = 0;
+        if (threadIdx.x >= 20 && threadIdx.x < 20 + kWorkWords && A.work_counter) A.work_counter[threadIdx.x - 20] = 0;
         if (threadIdx.x == 17 && A.best_bits) *A.best_bits = 0x7f7f7f7f7f7f7f7fULL;     // ~1.4e306
     }
     if ((int)blockIdx.x < A.n_coeff_blocks)

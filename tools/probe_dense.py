@@ -21,6 +21,8 @@ def main():
     work = bench.dense_workload(1)
     eng = bench.make_engine(work, 0, stream.cuda_stream)
     inputs = bench.make_inputs(work)
+    if os.environ.get("RP_PROBE_COLLISION"):
+        inputs.check_collision = int(os.environ["RP_PROBE_COLLISION"])       # 0: the march alone
     eng.grid_upload(inputs, work["t"], work["lon"], work["d"])
     for _ in range(5):
         eng.grid_launch()
