@@ -105,11 +105,11 @@ def inputs_for(prob, want_all_states=False, check_collision=True):
         continuous_collision_check=prob.get("continuous", False))
 
 
-def run_engine_grid(eng, prob, want_all_states=True, kernel=None):
+def run_engine_grid(eng, prob, want_all_states=True, kernel=None, check_collision=True):
     """kernel: None (context default) or _lib.KERNEL_* -- which schedule evaluates the main launch."""
     if kernel is not None:
         eng.set_kernel_policy(kernel)
-    res = eng.plan_grid(inputs_for(prob, want_all_states), prob["t"], prob["lon"], prob["d"])
+    res = eng.plan_grid(inputs_for(prob, want_all_states, check_collision), prob["t"], prob["lon"], prob["d"])
     cost, status, reason, step = eng.fetch_candidates()
     cl, ct, tau = eng.fetch_coeffs()
     out = {

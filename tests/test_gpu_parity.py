@@ -12,8 +12,13 @@ pytestmark = pytest.mark.gpu
 
 
 def _bundle(seed, level, N, low_vel=False, lon_mode="velocity_keeping", draw_all=False, s_dot0=15.0, d0=0.3,
-            amplitude=20.0, wavelength=40.0, t_min=0.4, x0_time_step=0, desired_s=None, static_offset=0.0):
-    scn = synthetic.make_scenario(seed=seed, amplitude=amplitude, wavelength=wavelength, static_offset=static_offset)
+            amplitude=20.0, wavelength=40.0, t_min=0.4, x0_time_step=0, desired_s=None, static_offset=0.0, wall=False,
+            **scn_kw):
+    scn = synthetic.make_scenario(seed=seed, amplitude=amplitude, wavelength=wavelength, static_offset=static_offset, **scn_kw)
+    if wall:        # a wall across the road where the vehicle starts: every candidate collides at its first step
+        scn = dict(scn)
+        scn["static_boxes"] = np.concatenate([np.asarray(scn["static_boxes"], dtype=np.float64).reshape(-1, 5),
+                                              np.array([[scn["ref_path"][10, 0], scn["ref_path"][10, 1], 0.0, 4.0, 200.0]])])
     dt = 0.1
     if lon_mode == "velocity_keeping":
         lo = max(0.0, s_dot0 - 0.125 * N * dt * 11.5)
@@ -411,3 +416,69 @@ def test_lon_interleaved_shards_merge_to_the_unsharded_result(kernel, world):
     again = eng.plan_grid(inputs, prob["t"], prob["lon"], prob["d"])
     assert again.winner == full.winner and again.n_candidates == full.n_candidates
     eng.close()
+
+
+@pytest.mark.parametrize("shard", ["none", "range", "stripe"])
+def test_deferred_lazy_collision_check_equals_full_checking(shard):
+    """candidate-major schedule, check_collision = 2: ego boxes stored by the march, collision verdicts by the deferred
+    tile-parallel checker.  Against full checking (every flag, checked while marching): same winner, cost and lazy
+    collision count; identical verdicts for everything ranked up to the winner; the rest is either unchecked or identical.
+    Cases: dynamic + static obstacles, road boundary as triangles, low-velocity mode, stopping mode (filtered goals), a
+    bundle where everything collides (no bound: the second pass checks all), one where nothing does; shards by range and
+    by lon-interleaved stripes"""
+    from commonroad_rp_b200 import _lib
+    cases = [dict(seed=2, level=3, N=60, s_dot0=12.0), dict(seed=1, level=3, N=20, d0=-0.4),
+             dict(seed=4, level=3, N=30, s_dot0=9.0, boundary_kind="tris", boundary_offset=3.4), dict(seed=3, level=3, N=20, s_dot0=3.0, low_vel=True),
+             dict(seed=6, level=3, N=30, s_dot0=8.0, lon_mode="stopping", desired_s=24.0), dict(seed=5, level=2, N=33, s_dot0=14.0)]
+    n_unchecked = 0
+    for case in cases:
+        prob = _bundle(**case)
+        variants = [("as is", prob)]
+        if shard == "none":
+            variants.append(("wall", _bundle(wall=True, **case)))
+        for tag, pr in variants:
+            eng = H.engine_for(pr)
+            eng.set_kernel_policy(_lib.KERNEL_CANDIDATE_MAJOR)
+            n_lon = len(pr["lon"])
+            shards = {"none": [None], "range": [(0, 0.4), (0.4, 1.0)], "stripe": [(0, 2), (1, 2)] if n_lon >= 2 else [None]}[shard]
+            for sh in shards:
+                n_all = len(pr["t"]) * n_lon * len(pr["d"])
+                own = np.ones(n_all, dtype=bool)
+                if shard == "range" and sh is not None:
+                    first = int(sh[0] * n_all) // 32 * 32
+                    eng.set_candidate_range(first, int(sh[1] * n_all) - first)
+                    own[:] = False
+                    own[first:int(sh[1] * n_all)] = True
+                elif shard == "stripe" and sh is not None:
+                    eng.set_candidate_stripe(*sh)
+                    own = np.zeros((len(pr["t"]), n_lon, len(pr["d"])), dtype=bool)
+                    own[:, sh[0]::sh[1], :] = True
+                    own = own.ravel()
+                full = eng.plan_grid(H.inputs_for(pr, check_collision=_lib.COLLISION_ALL), pr["t"], pr["lon"], pr["d"])
+                cost_f, status_f, reason_f, step_f = eng.fetch_candidates()
+                for rep in range(2):
+                    lazy = eng.plan_grid(H.inputs_for(pr, check_collision=_lib.COLLISION_LAZY), pr["t"], pr["lon"], pr["d"])
+                    assert eng.last_main_kernel() == _lib.KERNEL_CANDIDATE_MAJOR
+                    cost_l, status_l, reason_l, step_l = eng.fetch_candidates()
+                    what = (case, tag, sh, rep)
+                    assert lazy.winner == full.winner and (lazy.winner_cost == full.winner_cost or lazy.winner < 0), what
+                    assert lazy.n_infeasible_collision == full.n_infeasible_collision, what
+                    assert lazy.n_infeasible_kinematics == full.n_infeasible_kinematics and lazy.n_feasible == full.n_feasible, what
+                    assert list(lazy.reason_counts) == list(full.reason_counts), what
+                    n = len(cost_f)
+                    idx = np.arange(n)
+                    before = ((cost_f < full.winner_cost) | ((cost_f == full.winner_cost) & (idx <= full.winner))) if full.winner >= 0 \
+                        else np.isin(status_f, (0, 2))
+                    assert lazy.n_candidates == int(own.sum()), what
+                    unchecked = (status_l == _lib.ST_UNCHECKED) & own
+                    assert not (unchecked & before).any(), what
+                    assert np.all(np.isin(status_f[unchecked], (0, 2))), what
+                    same = ~unchecked & own
+                    assert np.array_equal(status_f[same], status_l[same]) and np.array_equal(step_f[same], step_l[same]), what
+                    assert np.array_equal(reason_f[same], reason_l[same]), what
+                    assert np.array_equal(cost_f[own].view(np.int64), cost_l[own].view(np.int64)), what
+                    n_unchecked += int(unchecked.sum())
+                    if tag == "wall":
+                        assert lazy.winner < 0 and not unchecked.any(), what
+            eng.close()
+    assert n_unchecked > 0

@@ -226,11 +226,20 @@ def test_full_size_dense_bundle_properties():
     import bench
     work = bench.dense_workload(1)
     eng = bench.make_engine(work, 0, None)
-    inputs = bench.make_inputs(work)
+    # the bench's own inputs run the lazy collision pass (check_collision = 2): same winner and counters as full checking,
+    # nothing ranked before the winner left without a verdict
+    lazy = eng.plan_grid(bench.make_inputs(work), work["t"], work["lon"], work["d"])
+    cost_l, status_l, _, _ = eng.fetch_candidates()
+    inputs = bench.make_inputs(work, check_collision=1)
     res = eng.plan_grid(inputs, work["t"], work["lon"], work["d"])
     n = work["n_cand"]
     assert res.n_candidates == n == 131072
     cost, status, reason, step = eng.fetch_candidates()
+    assert (lazy.winner, lazy.winner_cost, lazy.n_infeasible_collision, lazy.n_infeasible_kinematics, lazy.n_feasible) == \
+        (res.winner, res.winner_cost, res.n_infeasible_collision, res.n_infeasible_kinematics, res.n_feasible)
+    ranked_before = (cost < res.winner_cost) | ((cost == res.winner_cost) & (np.arange(n) <= res.winner))
+    assert np.array_equal(status_l[ranked_before], status[ranked_before]) and np.array_equal(cost_l, cost, equal_nan=True)
+    assert np.all(np.isin(status[status_l == 4], (0, 2))) and np.array_equal(status_l[status_l != 4], status[status_l != 4])
     ws = eng.fetch_states(res.winner)
     # (1) arg-min property: the winner is the lexicographic minimum over feasible, collision-free candidates
     ok = status == 0
