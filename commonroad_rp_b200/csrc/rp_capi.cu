@@ -146,6 +146,8 @@ struct rp_ctx {
     // "copy done" events of the pinned staging buffers: a buffer is rewritten only after ITS last copy finished
     // (waiting on the whole stream would serialise back-to-back cycles of many contexts sharing one stream)
     cudaEvent_t ev_stage = nullptr, ev_segs = nullptr, ev_result = nullptr;
+    cudaStream_t side_stream = nullptr;             // the collider count of a cycle runs beside the winner-state launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool stage_pending = false, segs_pending = false;
 
     // multi-GPU exchange over peer-mapped memory (rp_peer_*)
@@ -782,6 +784,9 @@ int rp_ctx_create(int device, void* stream, rp_ctx** out) {
     cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_segs, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_result, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     static_assert(sizeof(rp::PlanResultDev) <= rp_ctx::kResBytes, "result block header too small");
     if (ctx->d_result.ensure(rp_ctx::kResBytes) || ctx->h_result.ensure(rp_ctx::kResBytes) ||
         ctx->d_index.ensure(sizeof(int))) {
@@ -801,7 +806,8 @@ int rp_ctx_destroy(rp_ctx* ctx) {
                       &ctx->d_dyn_meta, &ctx->d_samples, &ctx->d_lon_coef, &ctx->d_lat_coef, &ctx->d_lat_tau,
                       &ctx->d_skip, &ctx->d_cost, &ctx->d_info, &ctx->d_states_all,
                       &ctx->d_result, &ctx->d_index, &ctx->d_segs, &ctx->d_segs_index, &ctx->d_argmin, &ctx->d_best,
-                      &ctx->d_work, &ctx->d_clr, &ctx->d_dyn_rows, &ctx->d_lat_rows})
+                      &ctx->d_work, &ctx->d_clr, &ctx->d_dyn_rows, &ctx->d_lat_rows, &ctx->d_pose, &ctx->d_defer_list,
+                      &ctx->d_defer_mask})
         b->release();
     for (DevBuf* b : {&ctx->d_cycle_res, &ctx->d_ticket, &ctx->d_best4, &ctx->d_peer_table}) b->release();
     if (ctx->h_cycle) cudaFreeHost(ctx->h_cycle);
@@ -812,8 +818,12 @@ int rp_ctx_destroy(rp_ctx* ctx) {
     for (auto& set : ctx->ev_ring)
         for (auto& e : set)
             if (e) cudaEventDestroy(e);
-    for (cudaEvent_t e : {ctx->ev_stage, ctx->ev_segs, ctx->ev_result})
+    for (cudaEvent_t e : {ctx->ev_stage, ctx->ev_segs, ctx->ev_result, ctx->ev_fork, ctx->ev_join})
         if (e) cudaEventDestroy(e);
+    if (ctx->side_stream) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RP_OK;
@@ -1206,6 +1216,7 @@ static int launch_plan(rp_ctx* ctx) {
     }
     if (ctx->stage_timing) cudaEventRecord(ctx->ev[2], ctx->stream);
     rp::PlanResultDev* dres = ctx->d_result.as<rp::PlanResultDev>();
+    const bool side_count = !small_path && !ctx->stage_timing && ctx->side_stream != nullptr;
     if (small_path) {
         rp::select_small_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count,
                                                             ctx->d_states_all.as<double>(), Np1, dres, ctx->d_states_one());
@@ -1215,6 +1226,10 @@ static int launch_plan(rp_ctx* ctx) {
         if (!dyn_rows_done) RP_CUDA(cudaMemsetAsync(sc, 0, sizeof(int) * 16, ctx->stream));
         const int nb = std::max(1, std::min(512, std::min(2 * ctx->num_sms, (count + 255) / 256)));
         rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc, sm);
+        // the count of colliders ranked before the winner (and, sharded, its exchange) needs the merged winner only, like
+        // the winner-state launch below: the two run side by side (the count on the side stream, joined before anything
+        // else touches the result block).  With stage timing on, the chain stays serial so that the stages add up.
+        cudaStream_t cs = ctx->stream;
         if (peer_mode) {
             // the shard's merge block goes straight on to the exchange of the shard records (no separate launch)
             const unsigned long long epoch = ++ctx->peer_epoch;
@@ -1224,12 +1239,23 @@ static int launch_plan(rp_ctx* ctx) {
                 ctx->peer_table_dirty = false;
             }
             rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres, ctx->d_peer_table.as<rp::PeerTable>(), epoch);
-            rp::peer_count_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->peer_table, epoch, ctx->d_cost.as<double>(), ctx->d_info.as<int>(),
-                                                               first, count, dres, sm);
+            if (side_count) {
+                RP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                RP_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+                cs = ctx->side_stream;
+            }
+            rp::peer_count_kernel<<<nb, 256, 0, cs>>>(ctx->peer_table, epoch, ctx->d_cost.as<double>(), ctx->d_info.as<int>(),
+                                                      first, count, dres, sm);
         } else {
             rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres);
-            rp::count_before_result_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, dres, sm);
+            if (side_count) {
+                RP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                RP_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+                cs = ctx->side_stream;
+            }
+            rp::count_before_result_kernel<<<nb, 256, 0, cs>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, dres, sm);
         }
+        if (side_count) RP_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
     }
     RP_CUDA(cudaGetLastError());
     if (ctx->stage_timing) cudaEventRecord(ctx->ev[3], ctx->stream);
@@ -1237,6 +1263,7 @@ static int launch_plan(rp_ctx* ctx) {
     if ((count > 0 || peer_mode) && !small_path) {          // peer mode: the GLOBAL winner, on every rank
         if (int rc = launch_states_for_index(ctx, &dres->r.winner, 1, ctx->d_states_one())) return rc;
     }
+    if (side_count) RP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     if (count > 0 && ctx->in.continuous_collision_check && ctx->in.check_collision) {
         rp::continuous_check_kernel<<<1, 128, 0, ctx->stream>>>(ctx->obs, ctx->d_states_one(), Np1, ctx->in.x0_time_step,
                                                                 0.5 * ctx->veh.length, 0.5 * ctx->veh.width, ctx->veh.wb_rear_axle,
