@@ -423,9 +423,10 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 // (the bound on the winner's cost comes from them)
 __device__ __forceinline__ bool defer_sampled(int tile) { return (((unsigned)tile * 0x9E3779B1u) >> 28) == 0u; }
 // put candidate k on a pass's list: its bit in the tile's mask; whoever sets the first bit lists the tile
-__device__ __forceinline__ void defer_enlist(const PlanParams& P, int k, int pass, int n_tiles) {
+__device__ __forceinline__ void defer_enlist(const PlanParams& P, int k, int pass) {
     const int tile = k >> 5;
-    if (atomicOr(P.defer_mask + tile, 1u << (k & 31)) == 0u) P.defer_list[pass * n_tiles + atomicAdd(P.defer_count + pass, 1)] = tile;
+    if (atomicOr(P.defer_mask + tile, 1u << (k & 31)) == 0u)
+        (pass ? P.defer_list2 : P.defer_list)[atomicAdd(P.defer_count + pass, 1)] = P.defer_tag | tile;
 }
 
 // DEFER: the march does not check collisions; it stores the ego box of every step while the candidate is still
@@ -706,7 +707,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
     P.info[k] = pack_info(status, reason, step);
     if (P.cost) P.cost[k] = cost;
     // first pass of the deferred check: the feasible candidates of a pseudo-random sixteenth of the tiles
-    if (DEFER && status == ST_UNCHECKED && defer_sampled(k >> 5)) defer_enlist(P, k, 0, (P.n_cand + 31) >> 5);
+    if (DEFER && status == ST_UNCHECKED && defer_sampled(k >> 5)) defer_enlist(P, k, 0);
 }
 
 // locate chunk g of 32 candidates in the segment table (sorted by traj_len, longest first): the lane's candidate,
@@ -787,44 +788,58 @@ cand_kernel(const __grid_constant__ PlanParams P) {
 // N + 1 boxes of a candidate are checked by 16 warps at once instead of an (N + 1)-step march.  The verdict (status, first
 // colliding step) is what the march itself would have recorded: same boxes (stored by the march), same tests.
 constexpr int kDeferThreads = 512;
+// all threads of the block; s_first: 32 ints of shared memory
+__device__ __forceinline__ void deferred_check_tile(const PlanParams& P, int tile, int* s_first) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ObstacleTables& O = P.obs;
+    const int Np1 = P.Np1;
+    const unsigned mask = P.defer_mask[tile];
+    if (threadIdx.x < 32) s_first[threadIdx.x] = 0x7fffffff;
+    __syncthreads();
+    if (threadIdx.x == 0) P.defer_mask[tile] = 0u;                  // clean for the next pass / cycle
+    const bool active = (mask >> lane) & 1u;
+    const double2* rec0 = reinterpret_cast<const double2*>(P.pose) + ((size_t)tile * Np1 * 32 + lane) * 2;
+    // the boxes were written to DRAM by the march: start all of this warp's fetches now (one sector per lane and step)
+    if (active)
+        for (int i = warp + kDeferThreads / 32; i < Np1; i += kDeferThreads / 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rec0 + (size_t)i * 64));
+    const float4* dyn_rows = P.dyn_rows;
+    for (int i = warp; i < Np1; i += kDeferThreads / 32) {
+        if (!active || reinterpret_cast<volatile int*>(s_first)[lane] < i) continue;        // (a smaller colliding step is already known)
+        const double2* rec = rec0 + (size_t)i * 64;
+        const double2 c = __ldcs(rec), h = __ldcs(rec + 1);
+        const int tidx = P.in.x0_time_step + i * P.in.factor;
+        const bool hit = (dyn_rows ? dyn_collides_f32(O, dyn_rows + (size_t)i * O.n_dyn, tidx, c.x, c.y, h.x, h.y, P.half_len, P.half_wid,
+                                                      0xffffffffu)
+                                   : dyn_collides_global(O, tidx, c.x, c.y, h.x, h.y, P.half_len, P.half_wid, P.r_ego)) ||
+                         static_collides<2>(O, c.x, c.y, h.x, h.y, P.half_len, P.half_wid);
+        if (hit) atomicMin(&s_first[lane], i);
+    }
+    __syncthreads();
+    if (warp == 0 && active) {
+        const int k = tile * 32 + lane;
+        const int step = s_first[lane];
+        P.info[k] = step != 0x7fffffff ? pack_info(ST_COLLISION, R_NONE, step) : pack_info(ST_FEASIBLE, R_NONE, -1);
+        if (step == 0x7fffffff) atomicMin(P.best_bits, (unsigned long long)__double_as_longlong(P.cost[k]));
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kDeferThreads) deferred_collision_kernel(const __grid_constant__ PlanParams P, const int* __restrict__ list,
                                                                            const int* __restrict__ n_listed) {
     __shared__ int s_first[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = *n_listed;
-    const ObstacleTables& O = P.obs;
-    const int Np1 = P.Np1;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) deferred_check_tile(P, list[b], s_first);
+}
+
+// the same for a batch of scenarios: the lists are shared, an entry names scenario and tile
+__global__ void __launch_bounds__(kDeferThreads) deferred_collision_batch_kernel(const PlanParams* __restrict__ params, const int* __restrict__ list,
+                                                                                 const int* __restrict__ n_listed) {
+    __shared__ int s_first[32];
+    const int n = *n_listed;
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
-        const int tile = list[b];
-        const unsigned mask = P.defer_mask[tile];
-        if (threadIdx.x < 32) s_first[threadIdx.x] = 0x7fffffff;
-        __syncthreads();
-        if (threadIdx.x == 0) P.defer_mask[tile] = 0u;                  // clean for the next pass / cycle
-        const bool active = (mask >> lane) & 1u;
-        const double2* rec0 = reinterpret_cast<const double2*>(P.pose) + ((size_t)tile * Np1 * 32 + lane) * 2;
-        // the boxes were written to DRAM by the march: start all of this warp's fetches now (one sector per lane and step)
-        if (active)
-            for (int i = warp + kDeferThreads / 32; i < Np1; i += kDeferThreads / 32)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec0 + (size_t)i * 64));
-        for (int i = warp; i < Np1; i += kDeferThreads / 32) {
-            if (!active || reinterpret_cast<volatile int*>(s_first)[lane] < i) continue;                    // (a smaller colliding step is already known)
-            const double2* rec = rec0 + (size_t)i * 64;
-            const double2 c = __ldcs(rec), h = __ldcs(rec + 1);
-            const int tidx = P.in.x0_time_step + i * P.in.factor;
-            const bool hit = (P.dyn_rows ? dyn_collides_f32(O, P.dyn_rows + (size_t)i * O.n_dyn, tidx, c.x, c.y, h.x, h.y, P.half_len,
-                                                            P.half_wid, 0xffffffffu)
-                                         : dyn_collides_global(O, tidx, c.x, c.y, h.x, h.y, P.half_len, P.half_wid, P.r_ego)) ||
-                             static_collides<2>(O, c.x, c.y, h.x, h.y, P.half_len, P.half_wid);
-            if (hit) atomicMin(&s_first[lane], i);
-        }
-        __syncthreads();
-        if (warp == 0 && active) {
-            const int k = tile * 32 + lane;
-            const int step = s_first[lane];
-            P.info[k] = step != 0x7fffffff ? pack_info(ST_COLLISION, R_NONE, step) : pack_info(ST_FEASIBLE, R_NONE, -1);
-            if (step == 0x7fffffff) atomicMin(P.best_bits, (unsigned long long)__double_as_longlong(P.cost[k]));
-        }
-        __syncthreads();
+        const unsigned e = (unsigned)list[b];
+        deferred_check_tile(params[e >> kDeferTileBits], (int)(e & ((1u << kDeferTileBits) - 1u)), s_first);
     }
 }
 
@@ -836,7 +851,16 @@ __global__ void __launch_bounds__(256) deferred_gather_kernel(const __grid_const
     if (P.stripe_world > 1) k = Stripe{P.stripe_rank, P.stripe_world, P.n_lon, P.n_d}.real(k);
     if ((P.info[k] & 0xFF) != ST_UNCHECKED) return;
     if ((unsigned long long)__double_as_longlong(P.cost[k]) > *P.best_bits) return;
-    defer_enlist(P, k, 1, (P.n_cand + 31) >> 5);
+    defer_enlist(P, k, 1);
+}
+
+__global__ void __launch_bounds__(256) deferred_gather_batch_kernel(const PlanParams* __restrict__ params) {
+    const PlanParams& P = params[blockIdx.y];
+    const int k = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+    if (k >= P.n_cand || P.pose == nullptr) return;
+    if ((P.info[k] & 0xFF) != ST_UNCHECKED) return;
+    if ((unsigned long long)__double_as_longlong(P.cost[k]) > *P.best_bits) return;
+    defer_enlist(P, k, 1);
 }
 
 // ---- a batch of independent scenarios (BASELINE configs[4]): ONE launch over all (scenario, chunk) pairs --------
@@ -851,7 +875,7 @@ struct BatchTable {
     int* work_counter;
 };
 
-template <int BLOCK>
+template <int BLOCK, bool DEFER = false>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_batch_kernel(const __grid_constant__ BatchTable B) {
     extern __shared__ double smem[];
@@ -889,7 +913,7 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
         }
         bool valid;
         const int k = chunk_candidate(P.segs, P.n_segs, g - B.chunk_prefix[lo], lane, valid);
-        cand_march<BLOCK, false, 1>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, false, 1, false, 32, DEFER>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 

@@ -1190,6 +1190,8 @@ static int launch_plan(rp_ctx* ctx) {
                 }
                 P.pose = ctx->d_pose.as<double>();
                 P.defer_list = ctx->d_defer_list.as<int>();
+                P.defer_list2 = P.defer_list + n_tiles;
+                P.defer_tag = 0;
                 P.defer_count = ctx->d_work.as<int>() + 1;
                 P.defer_mask = ctx->d_defer_mask.as<unsigned>();
             }
@@ -1208,7 +1210,7 @@ static int launch_plan(rp_ctx* ctx) {
                 const int check_blocks = std::max(1, std::min(n_tiles, 8 * ctx->num_sms));
                 rp::deferred_collision_kernel<<<check_blocks, rp::kDeferThreads, 0, ctx->stream>>>(P, P.defer_list, P.defer_count);
                 rp::deferred_gather_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(P, first, count);
-                rp::deferred_collision_kernel<<<check_blocks, rp::kDeferThreads, 0, ctx->stream>>>(P, P.defer_list + n_tiles, P.defer_count + 1);
+                rp::deferred_collision_kernel<<<check_blocks, rp::kDeferThreads, 0, ctx->stream>>>(P, P.defer_list2, P.defer_count + 1);
                 RP_CUDA(cudaGetLastError());
             }
         } else if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
@@ -1991,10 +1993,12 @@ struct rp_batch {
     std::vector<Slot> slots;
     PinBuf h_stage, h_results;
     DevBuf d_stage, d_lon_coef, d_lat_coef, d_cost, d_info, d_dyn_rows, d_results, d_work;
+    DevBuf d_pose, d_defer_list, d_defer_mask, d_best;         // deferred collision check (all scenarios in lazy mode)
     cudaEvent_t ev_stage = nullptr, ev_results = nullptr, ev0 = nullptr, ev1 = nullptr;
     bool stage_pending = false, launched = false;
     long long total_cand = 0;
     int smem_granted = 0;
+    bool deferred_last = false;
 };
 
 extern "C" {
@@ -2028,7 +2032,8 @@ int rp_batch_destroy(rp_batch* b) {
     cudaStreamSynchronize(b->stream);
     for (rp_ctx* c : b->ctxs)
         if (c->ext_busy == b->ev1) c->ext_busy = nullptr;
-    for (DevBuf* q : {&b->d_stage, &b->d_lon_coef, &b->d_lat_coef, &b->d_cost, &b->d_info, &b->d_dyn_rows, &b->d_results, &b->d_work})
+    for (DevBuf* q : {&b->d_stage, &b->d_lon_coef, &b->d_lat_coef, &b->d_cost, &b->d_info, &b->d_dyn_rows, &b->d_results, &b->d_work,
+                      &b->d_pose, &b->d_defer_list, &b->d_defer_mask, &b->d_best})
         q->release();
     b->h_stage.release();
     b->h_results.release();
@@ -2091,9 +2096,11 @@ int rp_batch_launch(rp_batch* b) {
     std::vector<size_t> off_samples(n), off_segs(n);
     std::vector<std::vector<rp::Segment>> segs(n);
     std::vector<int> prefix(n + 1, 0);
-    std::vector<size_t> off_lon(n), off_lat(n), off_cand(n), off_rows(n);
-    size_t n_lon_tot = 0, n_lat_tot = 0, n_cand_tot = 0, n_rows_tot = 0;
-    int max_sys = 0, max_rows = 0, acc_rows = 0;
+    std::vector<size_t> off_lon(n), off_lat(n), off_cand(n), off_rows(n), off_tiles(n), off_pose(n);
+    size_t n_lon_tot = 0, n_lat_tot = 0, n_cand_tot = 0, n_rows_tot = 0, n_tiles_tot = 0, n_pose_tot = 0;
+    int max_sys = 0, max_rows = 0, acc_rows = 0, max_cand = 0;
+    // the lazy collision pass is deferred (rp_cand.cuh, deferred_collision_batch_kernel) when EVERY scenario asks for it
+    bool defer = n < (1 << (32 - rp::kDeferTileBits - 1));
     for (int k = 0; k < n; ++k) {
         rp_ctx* c = b->ctxs[k];
         const rp_batch::Slot& s = b->slots[k];
@@ -2119,7 +2126,13 @@ int rp_batch_launch(rp_batch* b) {
         const int n_cand = n_t * per_t;
         const int n_lon_sys = n_t * n_lon, n_lat_sys = s.in.low_vel_mode ? n_cand : n_t * n_d;
         off_lon[k] = n_lon_tot; off_lat[k] = n_lat_tot; off_cand[k] = n_cand_tot; off_rows[k] = n_rows_tot;
+        off_tiles[k] = n_tiles_tot; off_pose[k] = n_pose_tot;
         n_lon_tot += (size_t)n_lon_sys; n_lat_tot += (size_t)n_lat_sys; n_cand_tot += (size_t)n_cand;
+        const size_t tiles = (size_t)(n_cand + 31) / 32;
+        n_tiles_tot += tiles;
+        n_pose_tot += tiles * Np1 * 32 * 4;                   // doubles
+        max_cand = std::max(max_cand, n_cand);
+        defer = defer && s.in.check_collision == 2 && s.in.cost_kind != RP_COST_NONE && tiles < ((size_t)1 << rp::kDeferTileBits);
         const int rows = (c->obs.n_dyn > 0 && s.in.check_collision) ? Np1 * c->obs.n_dyn : 0;
         n_rows_tot += (size_t)rows;
         max_sys = std::max(max_sys, n_lon_sys + n_lat_sys);
@@ -2137,7 +2150,16 @@ int rp_batch_launch(rp_batch* b) {
     if (int rc = b->d_dyn_rows.ensure(std::max<size_t>(n_rows_tot, 1) * sizeof(float4))) return rc;
     if (int rc = b->d_results.ensure((size_t)n * sizeof(rp::PlanResultDev))) return rc;
     if (int rc = b->h_results.ensure((size_t)n * sizeof(rp::PlanResultDev))) return rc;
-    if (int rc = b->d_work.ensure(sizeof(int))) return rc;
+    if (int rc = b->d_work.ensure(sizeof(int) * rp::kWorkWords)) return rc;
+    if (defer) {
+        if (int rc = b->d_pose.ensure(std::max<size_t>(n_pose_tot, 1) * sizeof(double))) return rc;
+        if (int rc = b->d_defer_list.ensure(2 * std::max<size_t>(n_tiles_tot, 1) * sizeof(int))) return rc;
+        if (int rc = b->d_best.ensure((size_t)n * sizeof(unsigned long long))) return rc;
+        if (b->d_defer_mask.cap < n_tiles_tot * sizeof(unsigned)) {            // (the checker leaves the masks it used clear)
+            if (int rc = b->d_defer_mask.ensure(std::max<size_t>(n_tiles_tot, 1) * sizeof(unsigned))) return rc;
+            RP_CUDA(cudaMemsetAsync(b->d_defer_mask.p, 0, b->d_defer_mask.cap, b->stream));
+        }
+    }
     char* hs = static_cast<char*>(b->h_stage.p);
     const char* ds = static_cast<const char*>(b->d_stage.p);
     std::memcpy(hs + off_prefix, prefix.data(), prefix.size() * sizeof(int));
@@ -2180,12 +2202,23 @@ int rp_batch_launch(rp_batch* b) {
         P.work_counter = nullptr;
         P.n_acc_rows = cand_acc_rows(s.in);
         P.dyn_rows = (c->obs.n_dyn > 0 && s.in.check_collision) ? b->d_dyn_rows.as<float4>() + off_rows[k] : nullptr;
+        P.pose = nullptr;
+        if (defer) {
+            P.pose = b->d_pose.as<double>() + off_pose[k];
+            P.defer_list = b->d_defer_list.as<int>();
+            P.defer_list2 = P.defer_list + n_tiles_tot;
+            P.defer_count = b->d_work.as<int>() + 1;
+            P.defer_mask = b->d_defer_mask.as<unsigned>() + off_tiles[k];
+            P.defer_tag = k << rp::kDeferTileBits;
+            P.best_bits = b->d_best.as<unsigned long long>() + k;
+        }
         hp[k] = P;
     }
     RP_CUDA(cudaMemcpyAsync(b->d_stage.p, b->h_stage.p, stage_bytes, cudaMemcpyHostToDevice, b->stream));
     RP_CUDA(cudaEventRecord(b->ev_stage, b->stream));
     b->stage_pending = true;
-    RP_CUDA(cudaMemsetAsync(b->d_work.p, 0, sizeof(int), b->stream));
+    RP_CUDA(cudaMemsetAsync(b->d_work.p, 0, sizeof(int) * rp::kWorkWords, b->stream));
+    if (defer) RP_CUDA(cudaMemsetAsync(b->d_best.p, 0x7f, (size_t)n * sizeof(unsigned long long), b->stream));      // ~1.4e306
     cudaEventRecord(b->ev0, b->stream);
     const PlanParams* dparams = reinterpret_cast<const PlanParams*>(ds);
     if (max_sys > 0) rp::coeff_batch_kernel<<<dim3((max_sys + 127) / 128, n), 128, 0, b->stream>>>(dparams);
@@ -2202,6 +2235,7 @@ int rp_batch_launch(rp_batch* b) {
                             (size_t)(threads / 32) * rp::kWarpRowDoubles * sizeof(double) + 64;
         if ((int)smem > b->smem_granted) {
             RP_CUDA(cudaFuncSetAttribute(rp::cand_batch_kernel<RP_CAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RP_CUDA(cudaFuncSetAttribute(rp::cand_batch_kernel<RP_CAND_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             b->smem_granted = (int)smem;
         }
         int occ = 0;
@@ -2209,8 +2243,19 @@ int rp_batch_launch(rp_batch* b) {
         if (occ < 1) return fail(RP_ERR_CUDA, "batch kernel does not fit on an SM");
         const int wpb = threads / 32;
         const int grid = std::max(1, std::min((prefix[n] + wpb - 1) / wpb, occ * b->num_sms));
-        rp::cand_batch_kernel<RP_CAND_THREADS><<<grid, threads, smem, b->stream>>>(T);
+        if (defer) {
+            rp::cand_batch_kernel<RP_CAND_THREADS, true><<<grid, threads, smem, b->stream>>>(T);
+            const int check_blocks = (int)std::max<size_t>(1, std::min<size_t>(n_tiles_tot, (size_t)8 * b->num_sms));
+            int* lists = b->d_defer_list.as<int>();
+            int* counts = b->d_work.as<int>() + 1;
+            rp::deferred_collision_batch_kernel<<<check_blocks, rp::kDeferThreads, 0, b->stream>>>(dparams, lists, counts);
+            rp::deferred_gather_batch_kernel<<<dim3((max_cand + 255) / 256, n), 256, 0, b->stream>>>(dparams);
+            rp::deferred_collision_batch_kernel<<<check_blocks, rp::kDeferThreads, 0, b->stream>>>(dparams, lists + n_tiles_tot, counts + 1);
+        } else {
+            rp::cand_batch_kernel<RP_CAND_THREADS><<<grid, threads, smem, b->stream>>>(T);
+        }
     }
+    b->deferred_last = defer && prefix[n] > 0;
     rp::argmin_batch_kernel<<<n, 256, 0, b->stream>>>(dparams, b->d_results.as<rp::PlanResultDev>());
     RP_CUDA(cudaGetLastError());
     cudaEventRecord(b->ev1, b->stream);

@@ -111,11 +111,13 @@ struct PlanParams {
     // every step as a 32-byte record (centre x, centre y, cos, sin) at [(k >> 5)][step][k & 31] -- the warp's store of
     // one step is 1 KB contiguous, the checker's read of one (candidate, step) is exactly one sector
     double* pose;
-    int* defer_list;             // tiles (32 consecutive candidates, k >> 5) awaiting the deferred check: [0, n_tiles) first
-                                 // pass, [n_tiles, 2 n_tiles) second pass
+    int* defer_list;             // tiles (32 consecutive candidates, k >> 5) awaiting the deferred check, first pass ...
+    int* defer_list2;            // ... and second pass; entries are defer_tag | tile (a scenario batch shares the lists)
     int* defer_count;            // [2] lengths of the two lists (zeroed with the work counter)
     unsigned* defer_mask;        // [n_tiles] which candidates of a listed tile are to be checked (cleared by the checker)
+    int defer_tag;               // scenario index << kDeferTileBits in a batch, 0 for a single bundle
 };
+constexpr int kDeferTileBits = 20;         // tiles per bundle < 2^20 (33 M candidates), scenarios per batch < 2^11
 
 // Multi-GPU shards that are ALIKE instead of contiguous: rank r of `world` owns the lon samples il = r, r + world, ... of
 // EVERY sampled t, so all ranks see the same mix of traj_len (contiguous t-major tiles differ in it and the exchange waits

@@ -291,8 +291,10 @@ def test_big_bundle_matches_reference_fixture(path, kernel):
     eng.close()
 
 
-def test_scenario_batch_matches_reference_fixtures():
-    """the batch path (rp_batch_*: one launch chain for all scenarios) on the reference-generated configs[4] bundles"""
+@pytest.mark.parametrize("collision_mode", [1, 2], ids=["all_flags", "lazy_pass"])
+def test_scenario_batch_matches_reference_fixtures(collision_mode):
+    """the batch path (rp_batch_*: one launch chain for all scenarios) on the reference-generated configs[4] bundles, with a
+    collision flag for every candidate and with the reference's lazy pass (deferred checker over the shared tile lists)"""
     from commonroad_rp_b200 import _lib
     paths = [p for p in BIG if "batch_" in os.path.basename(p)]
     assert len(paths) >= 2
@@ -302,7 +304,7 @@ def test_scenario_batch_matches_reference_fixtures():
     batch = _lib.Batch(engines)
     for rep in range(2):
         for k, pr in enumerate(probs):
-            batch.set_inputs(k, H.inputs_for(pr), pr["t"], pr["lon"], pr["d"])
+            batch.set_inputs(k, H.inputs_for(pr, check_collision=collision_mode), pr["t"], pr["lon"], pr["d"])
         batch.launch()
         res = batch.results()
         for k, (z, r) in enumerate(zip(zs, res)):

@@ -376,6 +376,36 @@ def test_scenario_batch_equals_individual_plans():
             c0, st0, r0, sp0 = arrays[k]
             assert np.array_equal(status, st0) and np.array_equal(reason, r0) and np.array_equal(step, sp0), k
             assert np.array_equal(cost.view(np.int64), c0.view(np.int64)), k          # identical bits
+    # the reference's lazy collision pass for every scenario (check_collision = 2): the batch march stores the ego boxes and
+    # the deferred checker runs over the shared tile lists -- winner, counters and everything ranked before the winner as
+    # with full checking; the rest either unchecked or identical
+    import copy
+    lazy_cycle = []
+    for inputs, t, lon, d in cycle:
+        li = copy.copy(inputs)
+        li.check_collision = _lib.COLLISION_LAZY
+        lazy_cycle.append((li, t, lon, d))
+    n_unchecked = 0
+    for rep in range(2):
+        res = batch.plan(lazy_cycle)
+        for k, (r, sgl) in enumerate(zip(res, single)):
+            assert (r.winner, r.n_infeasible_kinematics, r.n_infeasible_collision, r.n_feasible, list(r.reason_counts)) == \
+                (sgl[0], sgl[2], sgl[3], sgl[4], sgl[6]), (k, rep)
+            assert same(r.winner_cost, sgl[1])
+            cost, status, reason, step = batch.batch.fetch_candidates(k)
+            c0, st0, r0, sp0 = arrays[k]
+            assert np.array_equal(cost.view(np.int64), c0.view(np.int64)), k
+            unchecked = status == _lib.ST_UNCHECKED
+            assert np.all(np.isin(st0[unchecked], (0, 2))), k
+            assert np.array_equal(status[~unchecked], st0[~unchecked]) and np.array_equal(step[~unchecked], sp0[~unchecked]), k
+            if r.winner >= 0:
+                before = (c0 < r.winner_cost) | ((c0 == r.winner_cost) & (np.arange(len(c0)) <= r.winner))
+                assert not (unchecked & before).any(), k
+            else:
+                assert not unchecked.any(), k
+            n_unchecked += int(unchecked.sum())
+    assert n_unchecked > 0
+    assert [r.winner for r in batch.plan(cycle)] == [s[0] for s in single]          # and back to full checking
     packed = _lib.Batch.pack(cycle)           # all scenarios' inputs in one call
     assert [r.winner for r in batch.plan(packed)] == [s[0] for s in single]
     one = batch.plan_one_by_one(cycle)
