@@ -287,8 +287,9 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
         t, lon, d = fs.sample_grid(3, [d0, 0.0, 0.0], "velocity_keeping")
         s0 = float(co.ref_pos[10])
         j = int(np.argmax(co.ref_pos > s0)) - 1
+        # (check_collision = 2: the reference's lazy collision pass, as in the headline)
         inputs = Engine.make_inputs([s0, s_dot0, 0.0], [d0, 0.0, 0.0], float(co.ref_theta[j]), 0, s_dot0 < 4.0,
-                                    "velocity_keeping", N_HORIZON, DT, desired_speed=s_dot0)
+                                    "velocity_keeping", N_HORIZON, DT, desired_speed=s_dot0, check_collision=2)
         xy = co.convert_to_cartesian_coords(s0, d0)
         x0_cart.append([xy[0], xy[1], float(co.ref_theta[j]), s_dot0, 0.0, 0.0])
         x0_curv.append(([s0, s_dot0, 0.0], [d0, 0.0, 0.0]))
