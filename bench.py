@@ -377,7 +377,8 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
             "timed_cycles": cycles, "closed_loop": closed,
             "workload": "BASELINE configs[4]: %d independent seeded scenarios (%d per rank), default level-3 grid at N = 60"
                         % (n_scenarios, n_scenarios // max(world, 1)),
-            "note": "rp_batch_*: one H2D, four launches, one D2H per cycle of all scenarios; wall clock incl. host "
+            "note": "rp_batch_*: one H2D, seven launches (coefficients, obstacle rows, march, deferred collision check x 2 + "
+                    "gather, selection), one D2H per cycle of all scenarios; wall clock incl. host "
                     "staging of every scenario's inputs (host buffers) and D2H of every result"}
 
 

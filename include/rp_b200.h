@@ -100,10 +100,13 @@ typedef struct rp_plan_inputs {
     int32_t want_all_states;     /* 1: keep the 14 x (N+1) state block of EVERY candidate     */
     int32_t check_collision;     /* 0: skip a13; 1: check every kinematically feasible candidate; 2: lazy, like the
                                     reference's cost-ordered pass (:1031-1063): candidates costlier than the best
-                                    collision-free one found so far need not be visited (the
-                                    step-parallel schedule skips them: RP_FEASIBLE_UNCHECKED; the candidate-major
-                                    schedule checks while it marches).  Winner and n_infeasible_collision are
-                                    identical in modes 1 and 2.                                         */
+                                    collision-free one found so far need not be visited and stay
+                                    RP_FEASIBLE_UNCHECKED (the step-parallel schedule skips them as it goes; the
+                                    candidate-major schedule and the scenario batch store the ego boxes while they
+                                    march and check afterwards only what can be ranked before the winner).  Every
+                                    candidate ranked up to the winner has its verdict; winner, winner_cost,
+                                    n_infeasible_collision and the kinematic counters are identical in modes 1
+                                    and 2; n_collision_total counts the colliders that were visited.      */
     int32_t continuous_collision_check;   /* config.planning.continuous_collision_check (:1049-1058): the first discretely
                                     collision-free candidate in cost order is re-checked with the OBB-sum hulls of its
                                     consecutive poses (time indices x0_time_step + i); a hit ends the level without a
