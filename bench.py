@@ -369,12 +369,57 @@ def scenario_batch_rate(device, stream_handle, n_scenarios=64, cycles=3, rank=0,
         batch.plan_one_by_one(cycle)
     torch.cuda.synchronize()
     one_s = (time.perf_counter() - t1) / cycles
+    # ---- stress point of BASELINE configs[4]: the DENSE grid (32 t x 64 v x (64 d + d0)) on a subset of the
+    # scenarios -- 64 per rank at --gpus 8 (the 512-scenario subset), 8 per rank otherwise -- in one launch chain
+    dense = None
+    n_dense = min(n_scenarios // max(world, 1) if world > 1 else n_scenarios, 64 if world >= 8 else 8)
+    if n_dense > 0:
+        from commonroad_rp_b200._lib import traj_len_of
+        td, vd, dd, _ = synthetic.dense_grid(n_v=64)
+        t_arr = np.asarray([float(x) for x in set(td)], dtype=np.float64)
+        v_arr = np.asarray([float(x) for x in set(vd)], dtype=np.float64)
+        tl_arr = np.asarray([traj_len_of(x, DT) for x in t_arr], dtype=np.int32)
+        dense_cycle = []
+        for k in range(len(cycle)):
+            inp = cycle[k][0]
+            d_arr = np.asarray([float(x) for x in set(dd).union({float(inp.x0_lat[0])})], dtype=np.float64)
+            if k < n_dense:
+                dense_cycle.append((inp, t_arr, v_arr, d_arr, tl_arr))
+            else:           # the other scenarios of the batch idle on one candidate
+                dense_cycle.append((inp, t_arr[:1], v_arr[:1], d_arr[:1], tl_arr[:1]))
+        pk = Batch.pack(dense_cycle)
+        n_dense_cand = sum(len(c[1]) * len(c[2]) * len(c[3]) for c in dense_cycle)
+        for _ in range(2):
+            batch.plan(pk)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t2 = time.perf_counter()
+        dms = []
+        for _ in range(3):
+            res_d = batch.plan(pk)
+            dms.append(batch.batch.last_ms()[0])
+        torch.cuda.synchronize()
+        dd_s = (time.perf_counter() - t2) / 3
+        n_dw = sum(1 for r in res_d[:n_dense] if r.winner >= 0)
+        if world > 1:
+            agg = torch.tensor([dd_s, float(np.mean(dms))], dtype=torch.float64, device="cuda:%d" % device)
+            dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+            cnt = torch.tensor([float(n_dense_cand), float(n_dw)], dtype=torch.float64, device="cuda:%d" % device)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            dd_s, dms, n_dense_cand, n_dw = float(agg[0].item()), [float(agg[1].item())], int(cnt[0].item()), int(cnt[1].item())
+        dense = {"value": n_dense_cand / dd_s, "unit": UNIT, "dense_scenarios": n_dense * max(world, 1),
+                 "candidates_per_dense_scenario": int(len(t_arr) * len(v_arr) * len(dense_cycle[0][3])),
+                 "ms_per_cycle_of_all_scenarios": 1e3 * dd_s, "device_ms_per_cycle": float(np.mean(dms)),
+                 "device_value": n_dense_cand / (float(np.mean(dms)) * 1e-3), "dense_scenarios_with_winner": n_dw,
+                 "note": "the dense 32 t x 64 v x (64 d + d0) grid at N = 60 on every one of these scenarios, all in one "
+                         "launch chain (rp_batch_*); 3 timed cycles, wall clock incl. host staging and result D2H"}
     batch.close()
     return {"value": n_cand / dt_s, "unit": UNIT, "scenarios": n_scenarios, "candidates_per_scenario": n_cand // n_scenarios,
             "ms_per_cycle_of_all_scenarios": 1e3 * dt_s, "device_ms_per_cycle": float(np.mean(dev_ms)),
             "device_value": n_cand / (float(np.mean(dev_ms)) * 1e-3), "scenarios_with_winner": n_win,
             "one_launch_chain_per_scenario": {"value": n_local / one_s, "ms_per_cycle_of_one_ranks_scenarios": 1e3 * one_s},
-            "timed_cycles": cycles, "closed_loop": closed,
+            "timed_cycles": cycles, "closed_loop": closed, "dense_grid_stress": dense,
             "workload": "BASELINE configs[4]: %d independent seeded scenarios (%d per rank), default level-3 grid at N = 60"
                         % (n_scenarios, n_scenarios // max(world, 1)),
             "note": "rp_batch_*: one H2D, seven launches (coefficients, obstacle rows, march, deferred collision check x 2 + "

@@ -408,6 +408,10 @@ int build_obstacle_tables(rp_ctx* ctx) {
     return RP_OK;
 }
 
+// deferred collision check: upper bound of the ego-box store of one launch (32 bytes per candidate-timestep; the dense
+// sweep needs 256 MB, 64 dense scenarios in one batch 16 GB)
+constexpr size_t kDeferMaxBytes = (size_t)48 << 30;
+
 // ---- launch geometry of the fused kernel ---------------------------------------------------------
 // Fill C / g_begin of the segments (k ranges and tl given), size shared memory, query occupancy.
 int plan_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geometry& G, bool cycle = false, int threads = 0) {
@@ -1178,7 +1182,9 @@ static int launch_plan(rp_ctx* ctx) {
             // the reference's lazy collision pass (check_collision = 2): the march stores the ego boxes (32 bytes per
             // candidate-timestep) and the checks run afterwards, all time steps of a candidate at once, for the
             // candidates that can be ranked before the winner (rp_cand.cuh, deferred_collision_kernel)
-            const bool defer = ctx->in.check_collision == 2 && ctx->in.cost_kind != RP_COST_NONE;
+            const bool defer = ctx->in.check_collision == 2 && ctx->in.cost_kind != RP_COST_NONE &&
+                               (size_t)((n + 31) / 32) * Np1 * 32 * 4 * sizeof(double) <= kDeferMaxBytes &&
+                               (n + 31) / 32 < (1 << rp::kDeferTileBits);
             P.pose = nullptr;
             if (defer) {
                 if (int rc = ctx->d_pose.ensure((size_t)((n + 31) / 32) * Np1 * 32 * 4 * sizeof(double))) return rc;
@@ -2139,6 +2145,8 @@ int rp_batch_launch(rp_batch* b) {
         max_rows = std::max(max_rows, rows);
         acc_rows = std::max(acc_rows, cand_acc_rows(s.in));
     }
+    // (the stored ego boxes: 32 bytes per candidate-timestep; beyond the cap the march checks collisions itself)
+    if (n_pose_tot * sizeof(double) > kDeferMaxBytes) defer = false;
     const size_t stage_bytes = off;
     if (b->stage_pending) RP_CUDA(cudaEventSynchronize(b->ev_stage));          // last copy out of the pinned buffer (before it may be re-allocated)
     if (int rc = b->h_stage.ensure(stage_bytes)) return rc;
