@@ -421,7 +421,10 @@ __global__ void dyn_rows_kernel(ObstacleTables O, int x0_time_step, int factor, 
 // arithmetic folds away at compile time.
 // the tiles (32 consecutive candidates) of the first pass of the deferred collision check: a pseudo-random sixteenth
 // (the bound on the winner's cost comes from them)
-__device__ __forceinline__ bool defer_sampled(int tile) { return (((unsigned)tile * 0x9E3779B1u) >> 28) == 0u; }
+#ifndef RP_DEFER_SAMPLE_SHIFT
+#define RP_DEFER_SAMPLE_SHIFT 28          // 1 tile in 2^(32 - shift)
+#endif
+__device__ __forceinline__ bool defer_sampled(int tile) { return (((unsigned)tile * 0x9E3779B1u) >> RP_DEFER_SAMPLE_SHIFT) == 0u; }
 // put candidate k on a pass's list: its bit in the tile's mask; whoever sets the first bit lists the tile
 __device__ __forceinline__ void defer_enlist(const PlanParams& P, int k, int pass) {
     const int tile = k >> 5;
