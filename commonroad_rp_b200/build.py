@@ -39,8 +39,14 @@ def build_pack_module(force=False):
     out = pack_module_path()
     if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(PACK_SRC):
         return out
-    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", out, PACK_SRC, "-lm"]
-    subprocess.run(cmd, check=True)
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"]]
+    try:            # with the numpy headers the helper also creates the states' position arrays
+        import numpy as np
+        if os.path.exists(os.path.join(np.get_include(), "numpy", "arrayobject.h")):
+            cmd += ["-DRP_PACK_NUMPY", "-I", np.get_include()]
+    except ImportError:
+        pass
+    subprocess.run(cmd + ["-o", out, PACK_SRC, "-lm"], check=True)
     return out
 
 

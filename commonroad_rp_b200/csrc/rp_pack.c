@@ -18,6 +18,10 @@
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <math.h>
+#ifdef RP_PACK_NUMPY          /* build.py defines it when the numpy headers are there: positions are created here */
+#define NPY_NO_DEPRECATED_API NPY_1_7_API_VERSION
+#include <numpy/arrayobject.h>
+#endif
 
 static PyObject *k_time_step, *k_position, *k_steering_angle, *k_velocity, *k_orientation, *k_acceleration, *k_yaw_rate;
 static PyObject* k_dict;
@@ -69,11 +73,20 @@ static PyObject* pack(PyObject* self, PyObject* args) {
         const double* b = (const double*)view.buf;
         const double *th = b + 2 * n, *v = b + 3 * n, *a = b + 4 * n, *kap = b + 5 * n;
         const double *s = b + 7 * n, *d = b + 8 * n, *sv = b + 10 * n, *sa = b + 11 * n, *dv = b + 12 * n, *da = b + 13 * n;
-        pos_fast = PySequence_Fast(positions, "positions must be a sequence");
-        if (!pos_fast) goto done;
-        if (PySequence_Fast_GET_SIZE(pos_fast) != n) {
-            PyErr_SetString(PyExc_ValueError, "positions must have one entry per state");
+        const int make_positions = positions == Py_None;      /* None: one new (2,) float64 array per state, made here */
+#ifndef RP_PACK_NUMPY
+        if (make_positions) {
+            PyErr_SetString(PyExc_TypeError, "positions=None needs the numpy build of _rp_pack");
             goto done;
+        }
+#endif
+        if (!make_positions) {
+            pos_fast = PySequence_Fast(positions, "positions must be a sequence");
+            if (!pos_fast) goto done;
+            if (PySequence_Fast_GET_SIZE(pos_fast) != n) {
+                PyErr_SetString(PyExc_ValueError, "positions must have one entry per state");
+                goto done;
+            }
         }
         empty = PyTuple_New(0);
         cart = PyList_New(n);
@@ -89,8 +102,26 @@ static PyObject* pack(PyObject* self, PyObject* args) {
             const double steering = atan2(wheelbase * kap[i], 1.0);              /* :540-541 */
             PyObject* dct = PyDict_New();
             if (!dct) goto done;
-            PyObject* pos = PySequence_Fast_GET_ITEM(pos_fast, i);
-            if (set_steal(dct, k_time_step, PyLong_FromLong(ts)) < 0 || PyDict_SetItem(dct, k_position, pos) < 0 ||
+            PyObject* pos = NULL;
+            int pos_owned = 0;
+#ifdef RP_PACK_NUMPY
+            if (make_positions) {
+                npy_intp two = 2;
+                pos = PyArray_SimpleNew(1, &two, NPY_DOUBLE);
+                if (!pos) {
+                    Py_DECREF(dct);
+                    goto done;
+                }
+                double* pd = (double*)PyArray_DATA((PyArrayObject*)pos);
+                pd[0] = b[i];
+                pd[1] = b[n + i];
+                pos_owned = 1;
+            }
+#endif
+            if (!pos) pos = PySequence_Fast_GET_ITEM(pos_fast, i);
+            const int pos_rc = PyDict_SetItem(dct, k_position, pos);
+            if (pos_owned) Py_DECREF(pos);
+            if (set_steal(dct, k_time_step, PyLong_FromLong(ts)) < 0 || pos_rc < 0 ||
                 set_steal(dct, k_steering_angle, PyFloat_FromDouble(steering)) < 0 ||
                 set_steal(dct, k_velocity, PyFloat_FromDouble(v[i])) < 0 ||
                 set_steal(dct, k_orientation, PyFloat_FromDouble(theta)) < 0 ||
@@ -223,5 +254,13 @@ PyMODINIT_FUNC PyInit__rp_pack(void) {
     k_acceleration = PyUnicode_InternFromString("acceleration");
     k_yaw_rate = PyUnicode_InternFromString("yaw_rate");
     k_dict = PyUnicode_InternFromString("__dict__");
-    return PyModule_Create(&module);
+    PyObject* m = PyModule_Create(&module);
+    if (!m) return NULL;
+#ifdef RP_PACK_NUMPY
+    import_array();
+    PyModule_AddIntConstant(m, "MAKES_POSITIONS", 1);
+#else
+    PyModule_AddIntConstant(m, "MAKES_POSITIONS", 0);
+#endif
+    return m;
 }

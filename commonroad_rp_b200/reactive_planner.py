@@ -75,6 +75,7 @@ try:        # CPython helper for the output packing (csrc/rp_pack.c, built by bu
     from commonroad_rp_b200 import _rp_pack
 except ImportError:
     _rp_pack = None
+_PACK_MAKES_POSITIONS = bool(getattr(_rp_pack, "MAKES_POSITIONS", 0))
 
 _EPS = 1e-5
 _TWO_PI = 2.0 * math.pi
@@ -766,9 +767,10 @@ class ReactivePlanner(object):
             # the whole packing in one C call (csrc/rp_pack.c): state objects, steering angles, yaw rates, orientation
             # shift, the two curvilinear lists -- the same per-state arithmetic as the reference's loop (:520-556)
             t0 = x_0.time_step
-            cart_list, lon_list, lat_list = _rp_pack.pack(ReactivePlannerState, block, list(np.ascontiguousarray(block[0:2].T)),
-                                                          int(t0), int(factor), float(self.dt), float(self.vehicle_params.wheelbase),
-                                                          float(x_0.yaw_rate), x_0.orientation - math.pi, x_0.orientation + math.pi)
+            positions = None if _PACK_MAKES_POSITIONS else list(np.ascontiguousarray(block[0:2].T))
+            cart_list, lon_list, lat_list = _rp_pack.pack(ReactivePlannerState, block, positions,
+                                                          int(t0), int(factor), self.dt, self.vehicle_params.wheelbase,
+                                                          x_0.yaw_rate, x_0.orientation - math.pi, x_0.orientation + math.pi)
             pos_curv = block[7:9].T
             rows = block[2:6]
             curv_traj = _LazyTrajectory(t0, lambda: _curvilinear_states(t0, factor, np.ascontiguousarray(pos_curv), rows[1].tolist(),

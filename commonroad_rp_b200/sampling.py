@@ -148,22 +148,23 @@ class FixedIntervalSampling(SamplingSpace):
         (reference :218, :220, :226) -- as float64 arrays for ``rp_plan_grid``.  Enumeration index of a
         candidate = (i_t * n_lon + i_lon) * n_d + i_d."""
         self._longitudinal_mode = longitudinal_mode
-        t = self._ordered(("t", level_sampling), self.samples_t.samples_at_level(level_sampling))
-        lon = self._ordered((longitudinal_mode, level_sampling), self._get_lon_samples(level_sampling))
+        t_set = self.samples_t.samples_at_level(level_sampling)
+        lon_set = self._get_lon_samples(level_sampling)
+        # the t / lon arrays are re-read whenever a set object (or its size) changed; they are shared between cycles:
+        # callers must not write to them (read-only arrays)
+        memo = self.__dict__.get("_grid_memo")
+        if memo is None:
+            memo = self._grid_memo = {}
+        hit = memo.get((level_sampling, longitudinal_mode))
+        if hit is None or hit[0] is not t_set or hit[1] is not lon_set or hit[2] != len(t_set) or hit[3] != len(lon_set):
+            t = np.fromiter(t_set, dtype=np.float64)
+            lon = np.fromiter(lon_set, dtype=np.float64)
+            t.flags.writeable = False
+            lon.flags.writeable = False
+            hit = memo[(level_sampling, longitudinal_mode)] = (t_set, lon_set, len(t_set), len(lon_set), t, lon)
         # the union builds a new set whose order depends on d0: iterated afresh every cycle (SURVEY App. B#1)
-        d = np.fromiter(self.samples_d.samples_at_level(level_sampling).union({x_0_lat[0]}), dtype=np.float64)
-        return t, lon, d
-
-    def _ordered(self, key, sample_set):
-        """iteration order of a sample set as an array; re-read whenever the set object (or its size) changed.  The
-        arrays are shared between cycles: callers must not write to them."""
-        cache = self.__dict__.setdefault("_order_cache", {})
-        hit = cache.get(key)
-        if hit is None or hit[0] is not sample_set or hit[2] != len(sample_set):
-            arr = np.fromiter(sample_set, dtype=np.float64)
-            arr.flags.writeable = False
-            hit = cache[key] = (sample_set, arr, len(sample_set))
-        return hit[1]
+        d = np.fromiter(self.samples_d.samples_at_level(level_sampling).union((x_0_lat[0],)), dtype=np.float64)
+        return hit[4], hit[5], d
 
     def generate_trajectories_at_level(self, level_sampling: int, x_0_lon: np.ndarray, x_0_lat: np.ndarray,
                                        longitudinal_mode: str, low_vel_mode: bool) -> List[TrajectorySample]:
