@@ -791,6 +791,9 @@ cand_kernel(const __grid_constant__ PlanParams P) {
 // N + 1 boxes of a candidate are checked by 16 warps at once instead of an (N + 1)-step march.  The verdict (status, first
 // colliding step) is what the march itself would have recorded: same boxes (stored by the march), same tests.
 constexpr int kDeferThreads = 512;
+#ifndef RP_DEFER_MIN_BLOCKS
+#define RP_DEFER_MIN_BLOCKS 2          // 64 registers: two 16-warp blocks per SM (3 / 4 blocks spill: measured slower)
+#endif
 // all threads of the block; s_first: 32 ints of shared memory
 __device__ __forceinline__ void deferred_check_tile(const PlanParams& P, int tile, int* s_first) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -828,7 +831,7 @@ __device__ __forceinline__ void deferred_check_tile(const PlanParams& P, int til
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kDeferThreads) deferred_collision_kernel(const __grid_constant__ PlanParams P, const int* __restrict__ list,
+__global__ void __launch_bounds__(kDeferThreads, RP_DEFER_MIN_BLOCKS) deferred_collision_kernel(const __grid_constant__ PlanParams P, const int* __restrict__ list,
                                                                            const int* __restrict__ n_listed) {
     __shared__ int s_first[32];
     const int n = *n_listed;
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(kDeferThreads) deferred_collision_kernel(const
 }
 
 // the same for a batch of scenarios: the lists are shared, an entry names scenario and tile
-__global__ void __launch_bounds__(kDeferThreads) deferred_collision_batch_kernel(const PlanParams* __restrict__ params, const int* __restrict__ list,
+__global__ void __launch_bounds__(kDeferThreads, RP_DEFER_MIN_BLOCKS) deferred_collision_batch_kernel(const PlanParams* __restrict__ params, const int* __restrict__ list,
                                                                                  const int* __restrict__ n_listed) {
     __shared__ int s_first[32];
     const int n = *n_listed;
