@@ -134,7 +134,9 @@ constexpr int kLonRowDoubles = 14;
 __host__ __device__ constexpr int warp_row_doubles(int slots) { return kLonRowDoubles * slots + slots; }   // + flag words + dynamic-obstacle masks
 constexpr int kWarpRowDoubles = warp_row_doubles(32);
 
-template <bool EXACT>
+// DYNMASK: also compute the row's mask of dynamic obstacles that can reach its lateral line (not needed when the march
+// does not check collisions)
+template <bool EXACT, bool DYNMASK = true>
 __device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables& R, const double* __restrict__ cs_ptr, int i) {
     Divider<EXACT> D;
     LonRow o;
@@ -207,7 +209,7 @@ __device__ __forceinline__ LonRow lon_part(const PlanParams& P, const RefTables&
     // centre is farther than (reach + wb_rear + margin) from the LINE cannot touch any of them.  Conservative, single
     // precision (row.w carries that radius, dyn_rows_kernel); the lanes test only the surviving obstacles.
     o.dynmask = 0xffffffffu;
-    if (P.dyn_rows != nullptr && P.obs.n_dyn <= 32) {
+    if (DYNMASK && P.dyn_rows != nullptr && P.obs.n_dyn <= 32) {
         const ObstacleTables& O = P.obs;
         const float4* row = P.dyn_rows + (size_t)i * O.n_dyn;
         const float fbx = (float)(o.bx - O.org_x), fby = (float)(o.by - O.org_y), fnx = (float)o.nx, fny = (float)o.ny;
@@ -541,13 +543,13 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
                 // grid form: every group has the chunk's traj_len; list form: W == 1, the item is the lane's own candidate
                 if (step < tl) {
                     const double* cs_item = P.mode == 0 ? cs_group0 + (size_t)item_g * 6 : I.cs;
-                    const LonRow w = lon_part<false>(P, R, cs_item, step);
+                    const LonRow w = lon_part<false, !DEFER>(P, R, cs_item, step);
                     double* c = rows + lane;                   // (lane == item index: item_g * W + item_w)
                     c[0] = w.s; c[SLOTS] = w.sv; c[2 * SLOTS] = w.sa; c[3 * SLOTS] = w.y_sv; c[4 * SLOTS] = w.y_sv2;
                     c[5 * SLOTS] = w.th_ref; c[6 * SLOTS] = w.k_r; c[7 * SLOTS] = w.k_r_d; c[8 * SLOTS] = w.bx; c[9 * SLOTS] = w.by;
                     c[10 * SLOTS] = w.nx; c[11 * SLOTS] = w.ny; c[12 * SLOTS] = w.c_ref; c[13 * SLOTS] = w.s_ref;
                     rflags[lane] = w.flags;
-                    rflags[SLOTS + lane] = w.dynmask;
+                    if (!DEFER) rflags[SLOTS + lane] = w.dynmask;
                 }
             }
             __syncwarp();
@@ -563,7 +565,7 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
             L.k_r = c[6 * SLOTS]; L.k_r_d = c[7 * SLOTS]; L.bx = c[8 * SLOTS]; L.by = c[9 * SLOTS]; L.nx = c[10 * SLOTS];
             L.ny = c[11 * SLOTS]; L.c_ref = c[12 * SLOTS]; L.s_ref = c[13 * SLOTS];
             L.flags = rflags[item];
-            heavy_dynmask = rflags[SLOTS + item];
+            if (!DEFER) heavy_dynmask = rflags[SLOTS + item];
             double lat_now[3] = {lat_next[0], lat_next[1], lat_next[2]};
             if (LATROWS && i + 1 < tl) {                       // next step's lateral values: in flight during this step
                 const double2* r = reinterpret_cast<const double2*>(I.lr + (size_t)(i + 1) * I.lr_stride);
