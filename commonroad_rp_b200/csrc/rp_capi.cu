@@ -2264,7 +2264,7 @@ int rp_batch_launch(rp_batch* b) {
         }
     }
     b->deferred_last = defer && prefix[n] > 0;
-    rp::argmin_batch_kernel<<<n, 256, 0, b->stream>>>(dparams, b->d_results.as<rp::PlanResultDev>());
+    rp::argmin_batch_kernel<<<n, 1024, 0, b->stream>>>(dparams, b->d_results.as<rp::PlanResultDev>());
     RP_CUDA(cudaGetLastError());
     cudaEventRecord(b->ev1, b->stream);
     for (rp_ctx* c : b->ctxs) c->ext_busy = b->ev1;          // table updates of a member context wait for this cycle

@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(256) count_before_result_kernel(const double* 
 // before the winner.  Used per scenario of a batch and for replanning-size bundles (one launch instead of three).
 __device__ __forceinline__ void block_select(const double* __restrict__ cost, const int* __restrict__ info, int first,
                                              int count, PlanResultDev* __restrict__ out) {
-    __shared__ double w_cost[8];
-    __shared__ int w_idx[8];
+    __shared__ double w_cost[32];
+    __shared__ int w_idx[32];
     __shared__ int s_counts[16];
     __shared__ double s_wc;
     __shared__ int s_wi, s_before;
@@ -368,7 +368,7 @@ __device__ __forceinline__ void block_select(const double* __restrict__ cost, co
     }
     __syncthreads();
     if (warp == 0) {
-        const int n_warps = (int)(blockDim.x >> 5);             // (blocks of 64 .. 256 threads)
+        const int n_warps = (int)(blockDim.x >> 5);             // (blocks of 64 .. 1024 threads)
         bc = lane < n_warps ? w_cost[lane] : __longlong_as_double(0x7ff0000000000000LL);
         bi = lane < n_warps ? w_idx[lane] : 0x7fffffff;
         warp_lexmin(bc, bi);
@@ -404,7 +404,8 @@ __device__ __forceinline__ void block_select(const double* __restrict__ cost, co
 }
 
 // one block per scenario of a batch
-__global__ void __launch_bounds__(256) argmin_batch_kernel(const PlanParams* __restrict__ params, PlanResultDev* __restrict__ results) {
+// (1 024 threads: a scenario's few thousand candidates are two passes of a handful of iterations per thread)
+__global__ void __launch_bounds__(1024) argmin_batch_kernel(const PlanParams* __restrict__ params, PlanResultDev* __restrict__ results) {
     const PlanParams& P = params[blockIdx.x];
     block_select(P.cost, P.info, 0, P.n_cand, results + blockIdx.x);
 }
