@@ -412,3 +412,82 @@ def test_c_binding_of_the_cycle_call_passes_the_same_arguments():
         _rp_pack.plan_levels(C.cast(cb, C.c_void_p).value, 0, 0, [(np.zeros(2, np.float32),) + levels[0][1:]], 0)
     with pytest.raises(ValueError):
         _rp_pack.plan_levels(C.cast(cb, C.c_void_p).value, 0, 0, [(np.zeros(500), levels[0][1], levels[0][2], np.zeros(500, np.int32))], 0)
+
+
+class _FakeCycleEngine:
+    """stands in for _lib.Engine in plan()'s cycle path: records what each rp_plan_levels submission contained and answers
+    from a table {level size: has a winner}"""
+    plan_generation = 0
+    _cyc_chosen = 0
+    _cyc_selected = 0
+
+    def __init__(self, winners, states):
+        self.res = (_lib.PlanResult * 4)()
+        self.winners, self.states, self.submissions = winners, states, []
+
+    def cycle_limits(self):
+        return (4, 448, 128, 1 << 20)
+
+    def plan_levels(self, inputs, levels):
+        self.plan_generation += 1
+        sizes = [len(t) * len(lon) * len(d) for t, lon, d, _ in levels]
+        self.submissions.append(sizes)
+        chosen = len(levels) - 1
+        for j, n in enumerate(sizes):
+            ok = self.winners[len(levels[j][2])]            # keyed by the level's number of d samples
+            self.res[j].winner = 3 if ok else -1
+            self.res[j].n_candidates = n
+            self.res[j].n_infeasible_kinematics = 10 * (j + 1)
+            self.res[j].winner_cost = 1.0
+            if ok:
+                chosen = j
+                break
+        self._cyc_chosen = self._cyc_selected = chosen
+        return self.res, chosen
+
+    def select_level(self, j):
+        self._cyc_selected = j
+
+    def cycle_winner_states(self):
+        return self.states.copy()
+
+    def fetch_states(self, k):
+        return self.states.copy()
+
+
+@pytest.mark.parametrize("policy,winning_level,expected", [
+    ("after_failure", 1, [1]), ("after_failure", 2, [1, 2]), ("after_failure", 3, [1, 2]), ("after_failure", None, [1, 2]),
+    ("always", 1, [3]), ("always", 3, [3]), ("never", 3, [1, 1, 1]), ("never", 1, [1])])
+def test_speculation_policy_of_the_escalation_loop(policy, winning_level, expected):
+    """plan()'s level escalation (reference reactive_planner.py:616-636) on the cycle path: how many rp_plan_levels
+    submissions a cycle takes and how many sampling levels each carries, per ``ReactivePlanner.speculation``; the result is
+    the escalation loop's whatever the policy (lowest level with a winner; counters of the last level reached)"""
+    from commonroad_rp_b200.reactive_planner import ReactivePlanner
+    from commonroad_rp_b200.state import ReactivePlannerState
+    from tests.helpers import EmptyScenario
+    cfg = ReactivePlannerConfiguration()
+    cfg.planning.time_steps_computation = 20
+    cfg.sampling.t_min = 0.4
+    cfg.update(scenario=EmptyScenario(), planning_problem=None)
+    planner = ReactivePlanner(cfg)
+    planner.speculation = policy
+    scn = synthetic.make_scenario(seed=0)
+    co = CoordinateSystem(scn["ref_path"])
+    states = np.zeros((14, 21))
+    states[3] = 10.0                                                        # velocity row: no standstill fallback
+    n_d = {1: 6, 2: 10, 3: 18}                                              # d samples per level (+ d0)
+    fake = _FakeCycleEngine({n_d[lv]: (lv == winning_level) for lv in (1, 2, 3)}, states)
+    planner._engine = fake
+    planner._sync_device_tables = lambda: None
+    x0 = ReactivePlannerState(time_step=0, position=np.array([10.0, 0.0]), orientation=0.0, velocity=10.0, acceleration=0.0,
+                              yaw_rate=0.0, steering_angle=0.0)
+    planner.reset(initial_state_cart=x0, initial_state_curv=([10.0, 10.0, 0.0], [0.3, 0.0, 0.0]),
+                  collision_checker=collision.CollisionChecker(), coordinate_system=co)
+    planner.set_desired_velocity(desired_velocity=10.0, current_speed=10.0)
+    out = planner.plan()
+    assert [len(s) for s in fake.submissions] == expected
+    assert (out is not None) == (winning_level is not None)
+    reached = winning_level if winning_level is not None else 3
+    # counters are those of the last level the loop reached: its position inside ITS submission decides the record
+    per_submission = {"after_failure": {1: 0, 2: 0, 3: 1}, "always": {1: 0, 2: 1, 3: 2}, "never": {1: 0, 2: 0, 3: 0}}[policy]
+    assert planner.infeasible_count_kinematics == 10 * (per_submission[reached] + 1)
