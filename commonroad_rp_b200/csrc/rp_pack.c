@@ -24,24 +24,28 @@
 #endif
 
 static PyObject *k_time_step, *k_position, *k_steering_angle, *k_velocity, *k_orientation, *k_acceleration, *k_yaw_rate;
-static PyObject* k_dict;
 
 static const double TWO_PI = 6.283185307179586;
 
-/* new instance of a plain Python class with the given instance dictionary (cls.__new__(cls); obj.__dict__ = d) */
-static PyObject* instance_with_dict(PyTypeObject* cls, PyObject* empty, PyObject* d) {
-    PyObject* obj = cls->tp_new(cls, empty, NULL);
-    if (!obj) return NULL;
-    if (PyObject_SetAttr(obj, k_dict, d) < 0) {
-        Py_DECREF(obj);
+/* [a, b, c] as a new list of floats */
+static PyObject* list3(double a, double b, double c) {
+    PyObject* l = PyList_New(3);
+    if (!l) return NULL;
+    PyObject *x = PyFloat_FromDouble(a), *y = PyFloat_FromDouble(b), *z = PyFloat_FromDouble(c);
+    if (!x || !y || !z) {
+        Py_XDECREF(x); Py_XDECREF(y); Py_XDECREF(z);
+        Py_DECREF(l);
         return NULL;
     }
-    return obj;
+    PyList_SET_ITEM(l, 0, x);
+    PyList_SET_ITEM(l, 1, y);
+    PyList_SET_ITEM(l, 2, z);
+    return l;
 }
 
-static int set_steal(PyObject* d, PyObject* key, PyObject* value) {
+static int attr_steal(PyObject* obj, PyObject* key, PyObject* value) {
     if (!value) return -1;
-    const int rc = PyDict_SetItem(d, key, value);
+    const int rc = PyObject_SetAttr(obj, key, value);
     Py_DECREF(value);
     return rc;
 }
@@ -100,8 +104,10 @@ static PyObject* pack(PyObject* self, PyObject* args) {
             while (theta > hi) theta -= TWO_PI;
             const double yaw_rate = i == 0 ? yaw0 : (th[i] - th[i - 1]) / dt;     /* :536-539 */
             const double steering = atan2(wheelbase * kap[i], 1.0);              /* :540-541 */
-            PyObject* dct = PyDict_New();
-            if (!dct) goto done;
+            /* a fresh instance whose attributes are set one by one (the interpreter's own fast path for instance
+               attributes; same attribute order as ReactivePlannerState.__init__) */
+            PyObject* st = cls->tp_new(cls, empty, NULL);
+            if (!st) goto done;
             PyObject* pos = NULL;
             int pos_owned = 0;
 #ifdef RP_PACK_NUMPY
@@ -109,7 +115,7 @@ static PyObject* pack(PyObject* self, PyObject* args) {
                 npy_intp two = 2;
                 pos = PyArray_SimpleNew(1, &two, NPY_DOUBLE);
                 if (!pos) {
-                    Py_DECREF(dct);
+                    Py_DECREF(st);
                     goto done;
                 }
                 double* pd = (double*)PyArray_DATA((PyArrayObject*)pos);
@@ -119,23 +125,20 @@ static PyObject* pack(PyObject* self, PyObject* args) {
             }
 #endif
             if (!pos) pos = PySequence_Fast_GET_ITEM(pos_fast, i);
-            const int pos_rc = PyDict_SetItem(dct, k_position, pos);
+            int rc = attr_steal(st, k_time_step, PyLong_FromLong(ts));
+            if (rc == 0) rc = PyObject_SetAttr(st, k_position, pos);
             if (pos_owned) Py_DECREF(pos);
-            if (set_steal(dct, k_time_step, PyLong_FromLong(ts)) < 0 || pos_rc < 0 ||
-                set_steal(dct, k_steering_angle, PyFloat_FromDouble(steering)) < 0 ||
-                set_steal(dct, k_velocity, PyFloat_FromDouble(v[i])) < 0 ||
-                set_steal(dct, k_orientation, PyFloat_FromDouble(theta)) < 0 ||
-                set_steal(dct, k_acceleration, PyFloat_FromDouble(a[i])) < 0 ||
-                set_steal(dct, k_yaw_rate, PyFloat_FromDouble(yaw_rate)) < 0) {
-                Py_DECREF(dct);
+            if (rc < 0 || attr_steal(st, k_steering_angle, PyFloat_FromDouble(steering)) < 0 ||
+                attr_steal(st, k_velocity, PyFloat_FromDouble(v[i])) < 0 ||
+                attr_steal(st, k_orientation, PyFloat_FromDouble(theta)) < 0 ||
+                attr_steal(st, k_acceleration, PyFloat_FromDouble(a[i])) < 0 ||
+                attr_steal(st, k_yaw_rate, PyFloat_FromDouble(yaw_rate)) < 0) {
+                Py_DECREF(st);
                 goto done;
             }
-            PyObject* st = instance_with_dict(cls, empty, dct);
-            Py_DECREF(dct);
-            if (!st) goto done;
             PyList_SET_ITEM(cart, i, st);
-            PyObject* l3 = Py_BuildValue("[ddd]", s[i], sv[i], sa[i]);
-            PyObject* t3 = Py_BuildValue("[ddd]", d[i], dv[i], da[i]);
+            PyObject* l3 = list3(s[i], sv[i], sa[i]);
+            PyObject* t3 = list3(d[i], dv[i], da[i]);
             if (!l3 || !t3) {
                 Py_XDECREF(l3);
                 Py_XDECREF(t3);
@@ -253,7 +256,6 @@ PyMODINIT_FUNC PyInit__rp_pack(void) {
     k_orientation = PyUnicode_InternFromString("orientation");
     k_acceleration = PyUnicode_InternFromString("acceleration");
     k_yaw_rate = PyUnicode_InternFromString("yaw_rate");
-    k_dict = PyUnicode_InternFromString("__dict__");
     PyObject* m = PyModule_Create(&module);
     if (!m) return NULL;
 #ifdef RP_PACK_NUMPY

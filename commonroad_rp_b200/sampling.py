@@ -155,16 +155,20 @@ class FixedIntervalSampling(SamplingSpace):
         memo = self.__dict__.get("_grid_memo")
         if memo is None:
             memo = self._grid_memo = {}
-        hit = memo.get((level_sampling, longitudinal_mode))
-        if hit is None or hit[0] is not t_set or hit[1] is not lon_set or hit[2] != len(t_set) or hit[3] != len(lon_set):
+        ht = memo.get(level_sampling)                           # (t and lon separately: set_desired_velocity replaces
+        if ht is None or ht[0] is not t_set or ht[1] != len(t_set):   # the velocity samples every cycle, the t samples stay)
             t = np.fromiter(t_set, dtype=np.float64)
-            lon = np.fromiter(lon_set, dtype=np.float64)
             t.flags.writeable = False
+            ht = memo[level_sampling] = (t_set, len(t_set), t)
+        key = (level_sampling, longitudinal_mode)
+        hl = memo.get(key)
+        if hl is None or hl[0] is not lon_set or hl[1] != len(lon_set):
+            lon = np.fromiter(lon_set, dtype=np.float64)
             lon.flags.writeable = False
-            hit = memo[(level_sampling, longitudinal_mode)] = (t_set, lon_set, len(t_set), len(lon_set), t, lon)
+            hl = memo[key] = (lon_set, len(lon_set), lon)
         # the union builds a new set whose order depends on d0: iterated afresh every cycle
         d = np.fromiter(self.samples_d.samples_at_level(level_sampling).union((x_0_lat[0],)), dtype=np.float64)
-        return hit[4], hit[5], d
+        return ht[2], hl[2], d
 
     def generate_trajectories_at_level(self, level_sampling: int, x_0_lon: np.ndarray, x_0_lat: np.ndarray,
                                        longitudinal_mode: str, low_vel_mode: bool) -> List[TrajectorySample]:
