@@ -275,7 +275,8 @@ int rp_peer_close(rp_ctx* ctx);
 /* ---- batches of independent scenarios (reactive_planner.py has no counterpart: one ReactivePlanner per scenario
  * and process; BASELINE configs[4]) ------------------------------------------------------------------------------
  * A batch groups contexts of ONE device -- each with its own vehicle, reference and obstacle tables -- and
- * evaluates one replanning cycle of all of them with one host->device copy, four launches (no per-scenario launch)
+ * evaluates one replanning cycle of all of them with one host->device copy, four launches -- seven when every scenario
+ * asks for the lazy collision pass (check_collision = 2: ego boxes stored by the march, deferred checker) -- (no per-scenario launch)
  * and one device->host copy.  Select-only mode (no draw_all / want_all_states), N + 1 <= 128.  stream: as in
  * rp_ctx_create (NULL: the first context's stream).  The contexts stay usable on their own between batch cycles. */
 typedef struct rp_batch rp_batch;
@@ -296,7 +297,7 @@ int rp_batch_fetch_candidates(rp_batch* b, int k, double* cost, int32_t* status,
  * `step` of its trajectory, where the next replanning cycle starts -- one launch.  out[rp_batch_size][16] = x, y, theta, v,
  * a, kappa, s, s_dot, s_ddot, d, d_dot, d_ddot, valid (0: the scenario has no winner), 3 unused */
 int rp_batch_winner_states(rp_batch* b, int step, double* out);
-/* device time of the last rp_batch_launch (its four launches) and the candidates it evaluated */
+/* device time of the last rp_batch_launch (all its launches) and the candidates it evaluated */
 int rp_batch_last_ms(rp_batch* b, float* ms, long long* n_candidates);
 
 /* ---- results of the last plan call ----------------------------------------------------------- */
