@@ -405,6 +405,13 @@ def test_scenario_batch_equals_individual_plans():
                 assert not unchecked.any(), k
             n_unchecked += int(unchecked.sum())
     assert n_unchecked > 0
+    # a batch whose scenarios ask for different collision modes keeps the checks inside the march for all of them
+    mixed = [lazy_cycle[k] if k % 2 else cycle[k] for k in range(len(cycle))]
+    res = batch.plan(mixed)
+    for k, (r, sgl) in enumerate(zip(res, single)):
+        assert (r.winner, r.n_infeasible_kinematics, r.n_infeasible_collision, r.n_feasible) == (sgl[0], sgl[2], sgl[3], sgl[4]), k
+        _, status, _, _ = batch.batch.fetch_candidates(k)
+        assert np.array_equal(status, arrays[k][1]), k                               # (no unchecked candidates: every flag)
     assert [r.winner for r in batch.plan(cycle)] == [s[0] for s in single]          # and back to full checking
     packed = _lib.Batch.pack(cycle)           # all scenarios' inputs in one call
     assert [r.winner for r in batch.plan(packed)] == [s[0] for s in single]
