@@ -438,7 +438,8 @@ __device__ __forceinline__ void defer_enlist(const PlanParams& P, int k, int pas
 // kinematically feasible (P.pose) and leaves feasible candidates ST_UNCHECKED for deferred_collision_kernel.
 // (Letting the march itself check every 16th chunk -- taken first from the queue -- instead of a first deferred pass was
 // measured: the slower chunks stretch the march by 19 us, the saved pass is worth 17.)
-template <int BLOCK, bool ONE_GROUP, int PF, bool LATROWS = false, int SLOTS = 32, bool DEFER = false>
+// SPLIT: all lanes of a warp share one traj_len (grid form: a chunk never crosses a sampled t) -- two loops, see below
+template <int BLOCK, bool ONE_GROUP, int PF, bool LATROWS = false, int SLOTS = 32, bool DEFER = false, bool SPLIT = ONE_GROUP>
 __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables& R, const LimitRcp& Y, int k, bool valid,
                                            double* __restrict__ acc, double* __restrict__ s_vmid,
                                            double* __restrict__ rows) {
@@ -532,70 +533,10 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         const double2 u = __ldg(r), w = __ldg(r + 1);
         lat_next[0] = u.x; lat_next[1] = u.y; lat_next[2] = w.x;
     }
-    for (int i = 0; i < Np1; ++i) {
-        double px, py;                             // rear-axle position of this step
-        unsigned heavy_dynmask = 0xffffffffu;      // polynomial steps: the obstacles that can reach this step's lateral line
-        double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
-        if (i == row_next && i < tl_warp) {            // warp-uniform: refresh the rows of steps i .. i + W - 1
-            __syncwarp();
-            if (item_g < G) {
-                const int step = i + item_w;
-                // grid form: every group has the chunk's traj_len; list form: W == 1, the item is the lane's own candidate
-                if (step < tl) {
-                    const double* cs_item = P.mode == 0 ? cs_group0 + (size_t)item_g * 6 : I.cs;
-                    const LonRow w = lon_part<false, !DEFER>(P, R, cs_item, step);
-                    double* c = rows + lane;                   // (lane == item index: item_g * W + item_w)
-                    c[0] = w.s; c[SLOTS] = w.sv; c[2 * SLOTS] = w.sa; c[3 * SLOTS] = w.y_sv; c[4 * SLOTS] = w.y_sv2;
-                    c[5 * SLOTS] = w.th_ref; c[6 * SLOTS] = w.k_r; c[7 * SLOTS] = w.k_r_d; c[8 * SLOTS] = w.bx; c[9 * SLOTS] = w.by;
-                    c[10 * SLOTS] = w.nx; c[11 * SLOTS] = w.ny; c[12 * SLOTS] = w.c_ref; c[13 * SLOTS] = w.s_ref;
-                    rflags[lane] = w.flags;
-                    if (!DEFER) rflags[SLOTS + lane] = w.dynmask;
-                }
-            }
-            __syncwarp();
-            row_base = i;
-            row_next = i + W;
-        }
-        if (i < tl) {
-            I.i = i; I.th_prev = th_gl; I.kap_prev = kappa;
-            const int item = grp * W + (i - row_base);
-            const double* c = rows + item;
-            LonRow L;
-            L.s = c[0]; L.sv = c[SLOTS]; L.sa = c[2 * SLOTS]; L.y_sv = c[3 * SLOTS]; L.y_sv2 = c[4 * SLOTS]; L.th_ref = c[5 * SLOTS];
-            L.k_r = c[6 * SLOTS]; L.k_r_d = c[7 * SLOTS]; L.bx = c[8 * SLOTS]; L.by = c[9 * SLOTS]; L.nx = c[10 * SLOTS];
-            L.ny = c[11 * SLOTS]; L.c_ref = c[12 * SLOTS]; L.s_ref = c[13 * SLOTS];
-            L.flags = rflags[item];
-            if (!DEFER) heavy_dynmask = rflags[SLOTS + item];
-            double lat_now[3] = {lat_next[0], lat_next[1], lat_next[2]};
-            if (LATROWS && i + 1 < tl) {                       // next step's lateral values: in flight during this step
-                const double2* r = reinterpret_cast<const double2*>(I.lr + (size_t)(i + 1) * I.lr_stride);
-                const double2 u = __ldg(r), w = __ldg(r + 1);
-                lat_next[0] = u.x; lat_next[1] = u.y; lat_next[2] = w.x;
-            }
-            StepOut o = lat_part<false, LATROWS>(P, R, Y, L, LATROWS ? lat_now : I.cd, cs0, th_gl, kappa, i);
-            if (o.reject & 0x80000000u) o = poly_step_exact<LATROWS>(P, R, Y, I);
-            pre |= o.pre;
-            if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
-            if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
-            x = o.x; y = o.y; th_gl = o.th_gl; th_cl = o.th_cl; v = o.v; a = o.a; kappa = o.kappa;
-            s = o.s; sv = o.sv; d = o.d; dv = o.dv;
-            cn = o.cn; sn = o.sn;
-            px = x; py = y;
-            c_a = a; c_v = v; c_s = s; c_d = d; c_th = th_cl;
-        } else {
-            // ---- horizon extension (trajectories.py:168-197, :302-332) ---------------------------
-            const double tau = (double)(i - tl + 1) * dt;      // np.arange(1, steps + 1) * dt
-            double v_tmp = v + tau * a;
-            v_tmp = v_tmp * (v_tmp >= 0 ? 1.0 : 0.0);
-            const double ix = dt * v_tmp * cn, iy = dt * v_tmp * sn;
-            if (i == tl) { ax = ix; ay = iy; } else { ax += ix; ay += iy; }   // np.cumsum: sequential adds
-            px = x + ax; py = y + ay;
-            c_a = a; c_v = v_tmp;
-            c_s = s + tau * sv;                                // curvilinear tail (App. B#7)
-            c_d = d + tau * dv;
-            c_th = th_cl;
-        }
-
+    // the part of a step that the polynomial phase and the horizon extension share: cost terms, ego box / collision check,
+    // end values
+    auto step_tail = [&](const int i, const double px, const double py, const double c_a, const double c_v, const double c_s,
+                         const double c_d, const double c_th, const unsigned heavy_dynmask) {
         // ---- cost terms in numpy's np.sum order (cost_function.py:51-71) ------------------------------
         if (costed) {
             const double t0 = w_a * c_a, t3 = 0.25 * (des_d - c_d), t4 = 0.25 * fabs(c_th);
@@ -654,6 +595,144 @@ __device__ __forceinline__ void cand_march(const PlanParams& P, const RefTables&
         }
         if (i == Np1 - 1) {                                   // park the end values for the terminal terms
             v = c_v; s = c_s; d = c_d; th_cl = c_th;
+        }
+    };
+    if (SPLIT) {
+        // every lane of the warp has the chunk's traj_len: the polynomial steps and the horizon extension are two loops, so
+        // the values the extension starts from are results of the first loop, not state carried through it
+        for (int i = 0; i < tl; ++i) {
+            double px, py;                             // rear-axle position of this step
+            unsigned heavy_dynmask = 0xffffffffu;      // polynomial steps: the obstacles that can reach this step's lateral line
+            double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
+            if (i == row_next && i < tl_warp) {            // warp-uniform: refresh the rows of steps i .. i + W - 1
+                __syncwarp();
+                if (item_g < G) {
+                    const int step = i + item_w;
+                    // grid form: every group has the chunk's traj_len; list form: W == 1, the item is the lane's own candidate
+                    if (step < tl) {
+                        const double* cs_item = P.mode == 0 ? cs_group0 + (size_t)item_g * 6 : I.cs;
+                        const LonRow w = lon_part<false, !DEFER>(P, R, cs_item, step);
+                        double* c = rows + lane;                   // (lane == item index: item_g * W + item_w)
+                        c[0] = w.s; c[SLOTS] = w.sv; c[2 * SLOTS] = w.sa; c[3 * SLOTS] = w.y_sv; c[4 * SLOTS] = w.y_sv2;
+                        c[5 * SLOTS] = w.th_ref; c[6 * SLOTS] = w.k_r; c[7 * SLOTS] = w.k_r_d; c[8 * SLOTS] = w.bx; c[9 * SLOTS] = w.by;
+                        c[10 * SLOTS] = w.nx; c[11 * SLOTS] = w.ny; c[12 * SLOTS] = w.c_ref; c[13 * SLOTS] = w.s_ref;
+                        rflags[lane] = w.flags;
+                        if (!DEFER) rflags[SLOTS + lane] = w.dynmask;
+                    }
+                }
+                __syncwarp();
+                row_base = i;
+                row_next = i + W;
+            }
+            {
+                I.i = i; I.th_prev = th_gl; I.kap_prev = kappa;
+                const int item = grp * W + (i - row_base);
+                const double* c = rows + item;
+                LonRow L;
+                L.s = c[0]; L.sv = c[SLOTS]; L.sa = c[2 * SLOTS]; L.y_sv = c[3 * SLOTS]; L.y_sv2 = c[4 * SLOTS]; L.th_ref = c[5 * SLOTS];
+                L.k_r = c[6 * SLOTS]; L.k_r_d = c[7 * SLOTS]; L.bx = c[8 * SLOTS]; L.by = c[9 * SLOTS]; L.nx = c[10 * SLOTS];
+                L.ny = c[11 * SLOTS]; L.c_ref = c[12 * SLOTS]; L.s_ref = c[13 * SLOTS];
+                L.flags = rflags[item];
+                if (!DEFER) heavy_dynmask = rflags[SLOTS + item];
+                double lat_now[3] = {lat_next[0], lat_next[1], lat_next[2]};
+                if (LATROWS && i + 1 < tl) {                       // next step's lateral values: in flight during this step
+                    const double2* r = reinterpret_cast<const double2*>(I.lr + (size_t)(i + 1) * I.lr_stride);
+                    const double2 u = __ldg(r), w = __ldg(r + 1);
+                    lat_next[0] = u.x; lat_next[1] = u.y; lat_next[2] = w.x;
+                }
+                StepOut o = lat_part<false, LATROWS>(P, R, Y, L, LATROWS ? lat_now : I.cd, cs0, th_gl, kappa, i);
+                if (o.reject & 0x80000000u) o = poly_step_exact<LATROWS>(P, R, Y, I);
+                pre |= o.pre;
+                if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
+                if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
+                x = o.x; y = o.y; th_gl = o.th_gl; th_cl = o.th_cl; v = o.v; a = o.a; kappa = o.kappa;
+                s = o.s; sv = o.sv; d = o.d; dv = o.dv;
+                cn = o.cn; sn = o.sn;
+                px = x; py = y;
+                c_a = a; c_v = v; c_s = s; c_d = d; c_th = th_cl;
+            }
+            step_tail(i, px, py, c_a, c_v, c_s, c_d, c_th, heavy_dynmask);
+        }
+        for (int i = tl; i < Np1; ++i) {
+            double px, py, c_a, c_v, c_s, c_d, c_th;
+                // ---- horizon extension (trajectories.py:168-197, :302-332) ---------------------------
+                const double tau = (double)(i - tl + 1) * dt;      // np.arange(1, steps + 1) * dt
+                double v_tmp = v + tau * a;
+                v_tmp = v_tmp * (v_tmp >= 0 ? 1.0 : 0.0);
+                const double ix = dt * v_tmp * cn, iy = dt * v_tmp * sn;
+                if (i == tl) { ax = ix; ay = iy; } else { ax += ix; ay += iy; }   // np.cumsum: sequential adds
+                px = x + ax; py = y + ay;
+                c_a = a; c_v = v_tmp;
+                c_s = s + tau * sv;                                // curvilinear tail (App. B#7)
+                c_d = d + tau * dv;
+                c_th = th_cl;
+            step_tail(i, px, py, c_a, c_v, c_s, c_d, c_th, 0xffffffffu);
+        }
+    } else {
+        for (int i = 0; i < Np1; ++i) {
+            double px, py;                             // rear-axle position of this step
+            unsigned heavy_dynmask = 0xffffffffu;      // polynomial steps: the obstacles that can reach this step's lateral line
+            double c_a, c_v, c_s, c_d, c_th;           // values entering the cost terms
+            if (i == row_next && i < tl_warp) {            // warp-uniform: refresh the rows of steps i .. i + W - 1
+                __syncwarp();
+                if (item_g < G) {
+                    const int step = i + item_w;
+                    // grid form: every group has the chunk's traj_len; list form: W == 1, the item is the lane's own candidate
+                    if (step < tl) {
+                        const double* cs_item = P.mode == 0 ? cs_group0 + (size_t)item_g * 6 : I.cs;
+                        const LonRow w = lon_part<false, !DEFER>(P, R, cs_item, step);
+                        double* c = rows + lane;                   // (lane == item index: item_g * W + item_w)
+                        c[0] = w.s; c[SLOTS] = w.sv; c[2 * SLOTS] = w.sa; c[3 * SLOTS] = w.y_sv; c[4 * SLOTS] = w.y_sv2;
+                        c[5 * SLOTS] = w.th_ref; c[6 * SLOTS] = w.k_r; c[7 * SLOTS] = w.k_r_d; c[8 * SLOTS] = w.bx; c[9 * SLOTS] = w.by;
+                        c[10 * SLOTS] = w.nx; c[11 * SLOTS] = w.ny; c[12 * SLOTS] = w.c_ref; c[13 * SLOTS] = w.s_ref;
+                        rflags[lane] = w.flags;
+                        if (!DEFER) rflags[SLOTS + lane] = w.dynmask;
+                    }
+                }
+                __syncwarp();
+                row_base = i;
+                row_next = i + W;
+            }
+            if (i < tl) {
+                I.i = i; I.th_prev = th_gl; I.kap_prev = kappa;
+                const int item = grp * W + (i - row_base);
+                const double* c = rows + item;
+                LonRow L;
+                L.s = c[0]; L.sv = c[SLOTS]; L.sa = c[2 * SLOTS]; L.y_sv = c[3 * SLOTS]; L.y_sv2 = c[4 * SLOTS]; L.th_ref = c[5 * SLOTS];
+                L.k_r = c[6 * SLOTS]; L.k_r_d = c[7 * SLOTS]; L.bx = c[8 * SLOTS]; L.by = c[9 * SLOTS]; L.nx = c[10 * SLOTS];
+                L.ny = c[11 * SLOTS]; L.c_ref = c[12 * SLOTS]; L.s_ref = c[13 * SLOTS];
+                L.flags = rflags[item];
+                if (!DEFER) heavy_dynmask = rflags[SLOTS + item];
+                double lat_now[3] = {lat_next[0], lat_next[1], lat_next[2]};
+                if (LATROWS && i + 1 < tl) {                       // next step's lateral values: in flight during this step
+                    const double2* r = reinterpret_cast<const double2*>(I.lr + (size_t)(i + 1) * I.lr_stride);
+                    const double2 u = __ldg(r), w = __ldg(r + 1);
+                    lat_next[0] = u.x; lat_next[1] = u.y; lat_next[2] = w.x;
+                }
+                StepOut o = lat_part<false, LATROWS>(P, R, Y, L, LATROWS ? lat_now : I.cd, cs0, th_gl, kappa, i);
+                if (o.reject & 0x80000000u) o = poly_step_exact<LATROWS>(P, R, Y, I);
+                pre |= o.pre;
+                if (o.reason != R_NONE && bad == NONE) bad = ((unsigned)i << 8) | (unsigned)o.reason;
+                if (o.proj_fail && pbad == NONE) pbad = (unsigned)i;
+                x = o.x; y = o.y; th_gl = o.th_gl; th_cl = o.th_cl; v = o.v; a = o.a; kappa = o.kappa;
+                s = o.s; sv = o.sv; d = o.d; dv = o.dv;
+                cn = o.cn; sn = o.sn;
+                px = x; py = y;
+                c_a = a; c_v = v; c_s = s; c_d = d; c_th = th_cl;
+            } else {
+                // ---- horizon extension (trajectories.py:168-197, :302-332) ---------------------------
+                const double tau = (double)(i - tl + 1) * dt;      // np.arange(1, steps + 1) * dt
+                double v_tmp = v + tau * a;
+                v_tmp = v_tmp * (v_tmp >= 0 ? 1.0 : 0.0);
+                const double ix = dt * v_tmp * cn, iy = dt * v_tmp * sn;
+                if (i == tl) { ax = ix; ay = iy; } else { ax += ix; ay += iy; }   // np.cumsum: sequential adds
+                px = x + ax; py = y + ay;
+                c_a = a; c_v = v_tmp;
+                c_s = s + tau * sv;                                // curvilinear tail (App. B#7)
+                c_d = d + tau * dv;
+                c_th = th_cl;
+            }
+            step_tail(i, px, py, c_a, c_v, c_s, c_d, c_th, heavy_dynmask);
         }
     }
 
@@ -921,7 +1000,7 @@ cand_batch_kernel(const __grid_constant__ BatchTable B) {
         }
         bool valid;
         const int k = chunk_candidate(P.segs, P.n_segs, g - B.chunk_prefix[lo], lane, valid);
-        cand_march<BLOCK, false, 1, false, 32, DEFER>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, false, 1, false, 32, DEFER, true>(P, P.ref, *s_Y, k, valid, acc, s_vmid, s_rows);     // (batches are grid form)
     }
 }
 
