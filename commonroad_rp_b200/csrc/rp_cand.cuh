@@ -808,7 +808,8 @@ __device__ __forceinline__ int chunk_candidate(const Segment* __restrict__ segs,
 }
 
 // ---- one bundle: persistent grid, warps draw chunks of 32 candidates from a counter -----------------------------
-template <int BLOCK, bool ONE_GROUP, bool LATROWS = false, bool DEFER = false>
+// SPLIT: grid form (every warp shares one traj_len); the list form keeps polynomial steps and extension in one loop
+template <int BLOCK, bool ONE_GROUP, bool LATROWS = false, bool DEFER = false, bool SPLIT = ONE_GROUP>
 __global__ void __launch_bounds__(BLOCK, RP_CAND_MIN_BLOCKS)
 cand_kernel(const __grid_constant__ PlanParams P) {
     extern __shared__ double smem[];
@@ -855,7 +856,7 @@ cand_kernel(const __grid_constant__ PlanParams P) {
         bool valid;
         int k = chunk_candidate(s_segs, P.n_segs, g, lane, valid);
         if (P.stripe_world > 1) k = Stripe{P.stripe_rank, P.stripe_world, P.n_lon, P.n_d}.real(k);     // lon-interleaved shard
-        cand_march<BLOCK, ONE_GROUP, 2, LATROWS, SLOTS, DEFER>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
+        cand_march<BLOCK, ONE_GROUP, 2, LATROWS, SLOTS, DEFER, SPLIT>(P, R, *s_Y, k, valid, acc, s_vmid, s_rows);
     }
 }
 

@@ -515,6 +515,8 @@ int plan_cand_geometry(rp_ctx* ctx, int Np1, std::vector<rp::Segment>& segs, Geo
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        RP_CUDA(cudaFuncSetAttribute(rp::cand_kernel<RP_CAND_THREADS, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         granted = (int)G.smem;
     }
     int occ = 0;
@@ -1204,10 +1206,12 @@ static int launch_plan(rp_ctx* ctx) {
             if (defer) {
                 if (P.lat_rows) rp::cand_kernel<RP_CAND_THREADS, true, true, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
                 else if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true, false, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+                else if (ctx->mode == 0) rp::cand_kernel<RP_CAND_THREADS, false, false, true, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
                 else rp::cand_kernel<RP_CAND_THREADS, false, false, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
             } else {
                 if (P.lat_rows) rp::cand_kernel<RP_CAND_THREADS, true, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
                 else if (ctx->main_one_group) rp::cand_kernel<RP_CAND_THREADS, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
+                else if (ctx->mode == 0) rp::cand_kernel<RP_CAND_THREADS, false, false, false, true><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
                 else rp::cand_kernel<RP_CAND_THREADS, false><<<G.grid, G.threads, G.smem, ctx->stream>>>(P);
             }
             RP_CUDA(cudaGetLastError());
