@@ -1191,7 +1191,7 @@ static int launch_plan(rp_ctx* ctx) {
             if (defer) {
                 if (int rc = ctx->d_pose.ensure((size_t)((n + 31) / 32) * Np1 * 32 * 4 * sizeof(double))) return rc;
                 const size_t n_tiles = (size_t)(n + 31) / 32;
-                if (int rc = ctx->d_defer_list.ensure(2 * n_tiles * sizeof(int))) return rc;
+                if (int rc = ctx->d_defer_list.ensure((n_tiles + (size_t)std::max(n, 1)) * sizeof(int))) return rc;    // tiles, then candidates
                 if (ctx->d_defer_mask.cap < n_tiles * sizeof(unsigned)) {       // (the checker leaves the masks it used clear)
                     if (int rc = ctx->d_defer_mask.ensure(n_tiles * sizeof(unsigned))) return rc;
                     RP_CUDA(cudaMemsetAsync(ctx->d_defer_mask.p, 0, ctx->d_defer_mask.cap, ctx->stream));
@@ -1220,7 +1220,7 @@ static int launch_plan(rp_ctx* ctx) {
                 const int check_blocks = std::max(1, std::min(n_tiles, 8 * ctx->num_sms));
                 rp::deferred_collision_kernel<<<check_blocks, rp::kDeferThreads, 0, ctx->stream>>>(P, P.defer_list, P.defer_count);
                 rp::deferred_gather_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(P, first, count);
-                rp::deferred_collision_kernel<<<check_blocks, rp::kDeferThreads, 0, ctx->stream>>>(P, P.defer_list2, P.defer_count + 1);
+                rp::deferred_collision_list_kernel<<<check_blocks, rp::kDeferThreads, 0, ctx->stream>>>(P, P.defer_list2, P.defer_count + 1);
                 RP_CUDA(cudaGetLastError());
             }
         } else if (int rc = launch_fused(ctx, P, ctx->main_geom)) return rc;
