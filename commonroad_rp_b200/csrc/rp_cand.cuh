@@ -974,6 +974,49 @@ __global__ void __launch_bounds__(kDeferThreads, RP_DEFER_MIN_BLOCKS) deferred_c
     }
 }
 
+// second pass of a batch: the shared list names (scenario, candidate) pairs; the lanes of a block may belong to different
+// scenarios (their tables, horizons and bounds are read per lane)
+__global__ void __launch_bounds__(kDeferThreads, RP_DEFER_MIN_BLOCKS) deferred_collision_list_batch_kernel(const PlanParams* __restrict__ params,
+                                                                                                          const int* __restrict__ list,
+                                                                                                          const int* __restrict__ n_listed) {
+    __shared__ int s_first[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = *n_listed;
+    for (int b = blockIdx.x; b * 32 < n; b += gridDim.x) {
+        const int q = b * 32 + lane;
+        const bool active = q < n;
+        const unsigned e = active ? (unsigned)list[q] : 0u;
+        const PlanParams& P = params[e >> kDeferTileBits];
+        const int k = (int)(e & ((1u << kDeferTileBits) - 1u));
+        const ObstacleTables& O = P.obs;
+        const int Np1 = active ? P.Np1 : 0;
+        const float4* dyn_rows = P.dyn_rows;
+        if (threadIdx.x < 32) s_first[threadIdx.x] = 0x7fffffff;
+        __syncthreads();
+        const double2* rec0 = reinterpret_cast<const double2*>(P.pose) + ((size_t)(k >> 5) * Np1 * 32 + (k & 31)) * 2;
+        for (int i = warp + kDeferThreads / 32; i < Np1; i += kDeferThreads / 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rec0 + (size_t)i * 64));
+        for (int i = warp; i < Np1; i += kDeferThreads / 32) {
+            if (reinterpret_cast<volatile int*>(s_first)[lane] < i) continue;
+            const double2* rec = rec0 + (size_t)i * 64;
+            const double2 c = __ldcs(rec), h = __ldcs(rec + 1);
+            const int tidx = P.in.x0_time_step + i * P.in.factor;
+            const bool hit = (dyn_rows ? dyn_collides_f32(O, dyn_rows + (size_t)i * O.n_dyn, tidx, c.x, c.y, h.x, h.y, P.half_len, P.half_wid,
+                                                          0xffffffffu)
+                                       : dyn_collides_global(O, tidx, c.x, c.y, h.x, h.y, P.half_len, P.half_wid, P.r_ego)) ||
+                             static_collides<2>(O, c.x, c.y, h.x, h.y, P.half_len, P.half_wid);
+            if (hit) atomicMin(&s_first[lane], i);
+        }
+        __syncthreads();
+        if (warp == 0 && active) {
+            const int step = s_first[lane];
+            P.info[k] = step != 0x7fffffff ? pack_info(ST_COLLISION, R_NONE, step) : pack_info(ST_FEASIBLE, R_NONE, -1);
+            if (step == 0x7fffffff) atomicMin(P.best_bits, (unsigned long long)__double_as_longlong(P.cost[k]));
+        }
+        __syncthreads();
+    }
+}
+
 // second list: unchecked candidates of the shard whose cost does not exceed the bound of the first pass -- appended warp by
 // warp, in order (one atomic per warp)
 __global__ void __launch_bounds__(256) deferred_gather_kernel(const __grid_constant__ PlanParams P, int first, int count) {
@@ -998,10 +1041,16 @@ __global__ void __launch_bounds__(256) deferred_gather_kernel(const __grid_const
 __global__ void __launch_bounds__(256) deferred_gather_batch_kernel(const PlanParams* __restrict__ params) {
     const PlanParams& P = params[blockIdx.y];
     const int k = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
-    if (k >= P.n_cand || P.pose == nullptr) return;
-    if ((P.info[k] & 0xFF) != ST_UNCHECKED) return;
-    if ((unsigned long long)__double_as_longlong(P.cost[k]) > *P.best_bits) return;
-    defer_enlist(P, k, 1);
+    const int lane = threadIdx.x & 31;
+    const bool eligible = k < P.n_cand && P.pose != nullptr && (P.info[k] & 0xFF) == ST_UNCHECKED &&
+                          (unsigned long long)__double_as_longlong(P.cost[k]) <= *P.best_bits;
+    const unsigned m = __ballot_sync(0xffffffffu, eligible);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(P.defer_count + 1, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (eligible) P.defer_list2[base + __popc(m & ((1u << lane) - 1u))] = P.defer_tag | k;        // scenario << 20 | candidate
 }
 
 // ---- a batch of independent scenarios (BASELINE configs[4]): ONE launch over all (scenario, chunk) pairs --------

@@ -2142,7 +2142,7 @@ int rp_batch_launch(rp_batch* b) {
         n_tiles_tot += tiles;
         n_pose_tot += tiles * Np1 * 32 * 4;                   // doubles
         max_cand = std::max(max_cand, n_cand);
-        defer = defer && s.in.check_collision == 2 && s.in.cost_kind != RP_COST_NONE && tiles < ((size_t)1 << rp::kDeferTileBits);
+        defer = defer && s.in.check_collision == 2 && s.in.cost_kind != RP_COST_NONE && (size_t)n_cand < ((size_t)1 << rp::kDeferTileBits);
         const int rows = (c->obs.n_dyn > 0 && s.in.check_collision) ? Np1 * c->obs.n_dyn : 0;
         n_rows_tot += (size_t)rows;
         max_sys = std::max(max_sys, n_lon_sys + n_lat_sys);
@@ -2165,7 +2165,7 @@ int rp_batch_launch(rp_batch* b) {
     if (int rc = b->d_work.ensure(sizeof(int) * rp::kWorkWords)) return rc;
     if (defer) {
         if (int rc = b->d_pose.ensure(std::max<size_t>(n_pose_tot, 1) * sizeof(double))) return rc;
-        if (int rc = b->d_defer_list.ensure(2 * std::max<size_t>(n_tiles_tot, 1) * sizeof(int))) return rc;
+        if (int rc = b->d_defer_list.ensure((std::max<size_t>(n_tiles_tot, 1) + std::max<size_t>(n_cand_tot, 1)) * sizeof(int))) return rc;   // tiles, then (scenario, candidate) pairs
         if (int rc = b->d_best.ensure((size_t)n * sizeof(unsigned long long))) return rc;
         if (b->d_defer_mask.cap < n_tiles_tot * sizeof(unsigned)) {            // (the checker leaves the masks it used clear)
             if (int rc = b->d_defer_mask.ensure(std::max<size_t>(n_tiles_tot, 1) * sizeof(unsigned))) return rc;
@@ -2262,7 +2262,7 @@ int rp_batch_launch(rp_batch* b) {
             int* counts = b->d_work.as<int>() + 1;
             rp::deferred_collision_batch_kernel<<<check_blocks, rp::kDeferThreads, 0, b->stream>>>(dparams, lists, counts);
             rp::deferred_gather_batch_kernel<<<dim3((max_cand + 255) / 256, n), 256, 0, b->stream>>>(dparams);
-            rp::deferred_collision_batch_kernel<<<check_blocks, rp::kDeferThreads, 0, b->stream>>>(dparams, lists + n_tiles_tot, counts + 1);
+            rp::deferred_collision_list_batch_kernel<<<check_blocks, rp::kDeferThreads, 0, b->stream>>>(dparams, lists + n_tiles_tot, counts + 1);
         } else {
             rp::cand_batch_kernel<RP_CAND_THREADS><<<grid, threads, smem, b->stream>>>(T);
         }
