@@ -486,6 +486,19 @@ __global__ void __launch_bounds__(256) select_small_kernel(const double* __restr
     for (int q = threadIdx.x; q < 14 * Np1; q += blockDim.x) states_one[q] = src[q];
 }
 
+// result block of a launch chain (record + the winner's states) -> pinned host memory, then the epoch into a host flag the
+// caller spins on: no copy-engine hop and no event between the last kernel and the host (rp_grid_result)
+__global__ void __launch_bounds__(256) publish_result_kernel(const int4* __restrict__ src, int4* __restrict__ dst_host, int n16,
+                                                             unsigned long long* flag_host, unsigned long long epoch) {
+    for (int q = threadIdx.x; q < n16; q += blockDim.x) dst_host[q] = __ldcg(src + q);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(flag_host) = epoch;
+        __threadfence_system();
+    }
+}
+
 // ---- one replanning cycle in one launch (rp_plan_levels; structs in rp_fused.cuh) ------------------------------
 // Result block in MAPPED PINNED HOST memory: the last block of cycle_kernel writes it over PCIe and raises `flag` to the
 // cycle's epoch after a system-wide fence; the host spins on the flag -- no device->host copy node, no event.
