@@ -10,12 +10,18 @@
 // reference's own loop structure is the cheapest one: everything sequential-in-time lives in registers, there are
 // no barriers, and the lanes of a warp (adjacent candidates of one sampled t) share traj_len, the dynamic
 // obstacles of the step (one broadcast load per obstacle) and -- computed ONCE per warp, see cand_march -- everything
-// that depends on the longitudinal polynomial alone.  ~720 warp instructions per 32 candidate-timesteps.
+// that depends on the longitudinal polynomial alone.  ~720 warp instructions per 32 candidate-timesteps in round 1;
+// ~370 at the end of round 2 (lateral table, two loops per march, collision checks out of the march).
+//
+// Collision checks.  check_collision = 1 (a flag for every feasible candidate): inside the march, per step.
+// check_collision = 2 (the reference's lazy pass, reactive_planner.py:1031-1063): the march stores the ego box of every
+// step (PlanParams::pose) and the verdicts come afterwards from deferred_collision_kernel /
+// deferred_collision_list_kernel for the candidates that can be ranked before the winner (see there).
 //
 // The arithmetic is expression-for-expression the one of fused_kernel (same rp_device.cuh functions; divisions are
 // IEEE quotients in both), so both kernels give identical bits; only the schedule differs.  Not handled here (the
 // host routes these to fused_kernel): state output, draw mode, index mode, N + 1 > 128 (numpy's recursive pairwise
-// split), and bundles too small to fill the machine (one march of a warp is ~0.18 ms whatever the load).
+// split), and bundles too small to fill the machine (one march of a warp is ~0.08 ms whatever the load).
 //
 // Work distribution: the host sorts the segments (one per sampled t) by traj_len, longest first, and cuts them
 // into chunks of 32 candidates; warps of a persistent grid (one 512-thread block per SM) draw chunks from a global
