@@ -1239,7 +1239,9 @@ static int launch_plan(rp_ctx* ctx) {
         rp::ArgminScratch* sc = ctx->d_argmin.as<rp::ArgminScratch>();
         if (!dyn_rows_done) RP_CUDA(cudaMemsetAsync(sc, 0, sizeof(int) * 16, ctx->stream));
         const int nb = std::max(1, std::min(512, std::min(2 * ctx->num_sms, (count + 255) / 256)));
-        rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc, sm);
+        // (without a peer exchange the last partial block merges: no separate merge launch)
+        rp::argmin_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cost.as<double>(), ctx->d_info.as<int>(), first, count, sc, sm,
+                                                               peer_mode ? nullptr : dres);
         // the count of colliders ranked before the winner (and, sharded, its exchange) needs the merged winner only, like
         // the winner-state launch below: the two run side by side (the count on the side stream, joined before anything
         // else touches the result block).  With stage timing on, the chain stays serial so that the stages add up.
@@ -1261,7 +1263,6 @@ static int launch_plan(rp_ctx* ctx) {
             rp::peer_count_kernel<<<nb, 256, 0, cs>>>(ctx->peer_table, epoch, ctx->d_cost.as<double>(), ctx->d_info.as<int>(),
                                                       first, count, dres, sm);
         } else {
-            rp::argmin_merge_kernel<<<1, 512, 0, ctx->stream>>>(sc, nb, count, dres);
             if (side_count) {
                 RP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
                 RP_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
@@ -1997,10 +1998,10 @@ int rp_launches_per_plan(rp_ctx* ctx) {
     // the candidate-major kernel defers the checks of the lazy collision pass: check, gather, check
     const int deferred = (ctx->main_is_cand && ctx->in.check_collision == 2 && ctx->in.cost_kind != RP_COST_NONE) ? 3 : 0;
     if (ctx->peer_mode_last)        // prep, main kernel, argmin partial / merge + record exchange, peer count, winner states
-        return deferred + (ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
-    // prep (coefficients + dynamic-obstacle rows), main kernel, argmin partial / merge / count, winner states; the list
+        return deferred + (ctx->mode == 0 ? 5 : 4 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
+    // prep (coefficients + dynamic-obstacle rows), main kernel, argmin partial + merge (last block) / count, winner states; the list
     // form has no coefficient solve but, for the candidate-major kernel, its own dynamic-obstacle rows launch
-    return deferred + (ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
+    return deferred + (ctx->mode == 0 ? 5 : 4 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
 }
 
 }  // extern "C"

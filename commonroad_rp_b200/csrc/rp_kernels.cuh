@@ -203,10 +203,14 @@ __device__ __forceinline__ int warp_sum(int v) {
     return v;
 }
 
+// out != nullptr: the LAST block to finish merges the partials and writes the result record (one launch fewer; the
+// peer-exchange form keeps its own merge kernel, argmin_merge_kernel).  counts[1] is the blocks' ticket.
 __global__ void __launch_bounds__(256) argmin_partial_kernel(const double* __restrict__ cost, const int* __restrict__ info,
-                                                             int first, int count, ArgminScratch* sc, Stripe sm) {
+                                                             int first, int count, ArgminScratch* sc, Stripe sm,
+                                                             PlanResultDev* out = nullptr) {
     __shared__ double w_cost[8];
     __shared__ int w_idx[8];
+    __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double bc = __longlong_as_double(0x7ff0000000000000LL);       // +inf
     int bi = 0x7fffffff;
@@ -252,6 +256,43 @@ __global__ void __launch_bounds__(256) argmin_partial_kernel(const double* __res
         bi = lane < 8 ? w_idx[lane] : 0x7fffffff;
         warp_lexmin(bc, bi);
         if (lane == 0) { sc->part[blockIdx.x].cost = bc; sc->part[blockIdx.x].idx = bi; }
+    }
+    if (out == nullptr) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&sc->counts[1], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    bc = __longlong_as_double(0x7ff0000000000000LL);
+    bi = 0x7fffffff;
+    for (int q = tid; q < (int)gridDim.x; q += blockDim.x) {
+        const double c = __ldcg(&sc->part[q].cost);
+        const int k = __ldcg(&sc->part[q].idx);
+        if (lex_less(c, k, bc, bi)) { bc = c; bi = k; }
+    }
+    warp_lexmin(bc, bi);
+    __syncthreads();
+    if (lane == 0) { w_cost[warp] = bc; w_idx[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        bc = lane < 8 ? w_cost[lane] : __longlong_as_double(0x7ff0000000000000LL);
+        bi = lane < 8 ? w_idx[lane] : 0x7fffffff;
+        warp_lexmin(bc, bi);
+        if (lane == 0) {
+            const bool has_winner = bi != 0x7fffffff;
+            rp_plan_result& r = out->r;
+            const int n_feas = __ldcg(&sc->counts[0]), n_filt = __ldcg(&sc->counts[3]);
+            r.winner = has_winner ? bi : -1;
+            r.winner_cost = has_winner ? bc : __longlong_as_double(0x7ff8000000000000LL);
+            r.n_candidates = count;
+            r.n_feasible = n_feas;
+            r.n_infeasible_kinematics = count - n_filt - n_feas;
+            r.n_infeasible_collision = 0;              // filled by count_before_result_kernel
+            r.n_collision_total = __ldcg(&sc->counts[2]);
+            for (int z = 0; z < 8; ++z) r.reason_counts[z] = __ldcg(&sc->counts[8 + z]);
+            out->n_filtered = n_filt;
+        }
     }
 }
 

@@ -261,7 +261,7 @@ def test_big_bundle_lazy_collision_pass_matches_reference_fixture(path):
     for rep in range(2):                                   # (second cycle: the checker's masks / lists were left clean)
         g = H.run_engine_grid(eng, prob, want_all_states=False, kernel=_lib.KERNEL_CANDIDATE_MAJOR,
                               check_collision=_lib.COLLISION_LAZY)
-        assert eng.last_main_kernel() == _lib.KERNEL_CANDIDATE_MAJOR and eng.launches_per_plan() == 9
+        assert eng.last_main_kernel() == _lib.KERNEL_CANDIDATE_MAJOR and eng.launches_per_plan() == 8
         _check_big(z, g, os.path.basename(path))
         wc, wi = g["winner_cost"], g["winner"]
         n = g["n"]
