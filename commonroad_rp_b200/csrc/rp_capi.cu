@@ -1998,7 +1998,7 @@ int rp_launches_per_plan(rp_ctx* ctx) {
     // the candidate-major kernel defers the checks of the lazy collision pass: check, gather, check
     const int deferred = (ctx->main_is_cand && ctx->in.check_collision == 2 && ctx->in.cost_kind != RP_COST_NONE) ? 3 : 0;
     if (ctx->peer_mode_last)        // prep, main kernel, argmin partial / merge + record exchange, peer count, winner states
-        return deferred + (ctx->mode == 0 ? 5 : 4 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
+        return deferred + (ctx->mode == 0 ? 6 : 5 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
     // prep (coefficients + dynamic-obstacle rows), main kernel, argmin partial + merge (last block) / count, winner states; the list
     // form has no coefficient solve but, for the candidate-major kernel, its own dynamic-obstacle rows launch
     return deferred + (ctx->mode == 0 ? 5 : 4 + ((ctx->main_is_cand && ctx->obs.n_dyn > 0 && ctx->in.check_collision) ? 1 : 0));
