@@ -482,3 +482,38 @@ def test_deferred_lazy_collision_check_equals_full_checking(shard):
                         assert lazy.winner < 0 and not unchecked.any(), what
             eng.close()
     assert n_unchecked > 0
+
+
+def test_repeated_sample_arrays_are_read_afresh():
+    """Engine.plan_grid keeps the pointer objects of sample arrays it is handed again (host-side saving): the CONTENTS are
+    still read at every call, other calls in between do not disturb it, and new array objects are picked up"""
+    from commonroad_rp_b200 import _lib
+    from commonroad_rp_b200._lib import traj_len_of
+    prob = _bundle(seed=1, level=2, N=20)
+    other = _bundle(seed=1, level=2, N=20, d0=-0.35)
+    eng = H.engine_for(prob)
+    inputs = H.inputs_for(prob)
+    t, lon = np.array(prob["t"], dtype=np.float64), np.array(prob["lon"], dtype=np.float64)
+    d = np.array(prob["d"], dtype=np.float64)
+    d_other = np.array(other["d"], dtype=np.float64)
+    assert len(d_other) == len(d) and not np.array_equal(d_other, d)
+    tl = np.array([traj_len_of(x, prob["dt"]) for x in t], dtype=np.int32)
+    a = eng.plan_grid(inputs, t, lon, d, tl)
+    cost_a = eng.fetch_candidates()[0]
+    again = eng.plan_grid(inputs, t, lon, d, tl)                  # same objects: kept pointers
+    assert again.winner == a.winner and np.array_equal(eng.fetch_candidates()[0], cost_a, equal_nan=True)
+    fresh = eng.plan_grid(inputs, t, lon, d_other.copy(), tl)     # a new array object
+    cost_fresh = eng.fetch_candidates()[0]
+    assert not np.array_equal(cost_fresh, cost_a, equal_nan=True)
+    eng.plan_grid(inputs, t, lon, d, tl)
+    # a cycle launch in between changes the engine's candidate count; the kept arguments restore it
+    eng.plan_levels(inputs, [(t[:2], lon[:2], d[:3], tl[:2])])
+    back = eng.plan_grid(inputs, t, lon, d, tl)
+    assert back.winner == a.winner and len(eng.fetch_candidates()[0]) == len(cost_a)
+    d[:] = d_other                                                # the SAME object with new contents
+    changed = eng.plan_grid(inputs, t, lon, d, tl)
+    assert changed.winner == fresh.winner and np.array_equal(eng.fetch_candidates()[0], cost_fresh, equal_nan=True)
+    st = eng.fetch_states(changed.winner)
+    st2 = eng.fetch_states(changed.winner)
+    assert st is not st2 and np.array_equal(st, st2)               # (fetch_states hands out copies of its kept buffer)
+    eng.close()
